@@ -1,0 +1,249 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (/root/reference/etpgt)
+on CPU, with `oracle/pyg_shim` standing in for the absent `torch_geometric`.
+
+Run in the build container only (the GPU box has no /root/reference):
+    python oracle/make_golden.py
+The fixtures pin (a) the functional restatement in `oracle/model_ref.py` / `graph_ref.py`
+against the reference's own classes and (b) the CUDA path against both.  Every case stores
+inputs, the reference state_dict, fp32 outputs, and fp64 outputs + gradients (the model is
+re-run with `.double()` for ground truth).
+"""
+
+from __future__ import annotations
+
+import csv
+import sys
+import tempfile
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT / "oracle" / "pyg_shim"))
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, "/root/reference")
+
+from torch_geometric.data import Batch, Data  # noqa: E402
+
+from etpgt.model import (  # noqa: E402
+    create_gat,
+    create_graph_transformer,
+    create_graph_transformer_optimized,
+    create_graphsage,
+)
+from etpgt.model.base import SessionReadout  # noqa: E402
+from etpgt.train.dataloader import SessionDataset, collate_fn  # noqa: E402
+from etpgt.train.losses import create_loss_function  # noqa: E402
+from etpgt.utils.metrics import compute_ndcg_at_k, compute_recall_at_k  # noqa: E402
+
+OUT = ROOT / "tests" / "golden"
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+def random_sessions_batch(rng, num_sessions, num_items, min_nodes=2, max_nodes=7, symmetric=True):
+    """Block-diagonal batch of small session graphs with the shape statistics of
+    docs/architecture/C4_CODE.md:46-67 (B=32 -> ~150 nodes, ~280 edges)."""
+    graphs = []
+    for _ in range(num_sessions):
+        n = int(rng.integers(min_nodes, max_nodes + 1))
+        ids = np.sort(rng.choice(np.arange(1, num_items), size=n, replace=False))
+        pairs = [(a, b) for a in range(n) for b in range(a, n) if rng.random() < 0.45]
+        src = [a for a, _ in pairs]
+        dst = [b for _, b in pairs]
+        if symmetric:
+            src, dst = src + dst, dst + src
+        ei = torch.tensor([src, dst], dtype=torch.long).reshape(2, -1)
+        graphs.append(Data(x=torch.tensor(ids, dtype=torch.long), edge_index=ei))
+    return Batch.from_data_list(graphs)
+
+
+def run_model_case(name, factory, kwargs, batch, targets, negatives, loss_type, seed, pe=None):
+    torch.manual_seed(seed)
+    model = factory(**kwargs)
+    if pe is not None:
+        model.laplacian_pe._cached_pe = pe.clone()
+    # make BN affine / running stats non-trivial so the fixture exercises them
+    with torch.no_grad():
+        for bn in model.batch_norms:
+            bn.weight.uniform_(0.5, 1.5)
+            bn.bias.uniform_(-0.2, 0.2)
+            bn.running_mean.uniform_(-0.1, 0.1)
+            bn.running_var.uniform_(0.5, 1.5)
+    state0 = {k: v.clone() for k, v in model.state_dict().items()}
+    out = {"cfg_" + k: np.asarray(v) for k, v in kwargs.items() if isinstance(v, (int, float, bool))}
+    out.update({"x": npy(batch.x), "edge_index": npy(batch.edge_index), "batch": npy(batch.batch),
+                "target": npy(targets), "negatives": npy(negatives)})
+    for k, v in state0.items():
+        out["state/" + k] = npy(v)
+    loss_fn = create_loss_function(loss_type)
+
+    for dtype, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
+        torch.set_default_dtype(dtype)  # base.py:140 allocates the readout in the default dtype
+        model.load_state_dict(state0)
+        model = model.to(dtype)
+        if pe is not None:
+            model.laplacian_pe._cached_pe = pe.clone().to(dtype)
+        model.eval()
+        with torch.no_grad():
+            out[f"eval_out_{tag}"] = npy(model(batch))
+        model.train()
+        model.zero_grad()
+        sess = model(batch)
+        res = loss_fn(sess, targets, negatives, model.item_embedding)
+        loss = res[0] if isinstance(res, tuple) else res
+        loss.backward()
+        out[f"train_out_{tag}"] = npy(sess)
+        out[f"loss_{tag}"] = npy(loss)
+        if tag == "f64":  # ground truth, stored rounded to fp32 to keep the fixtures small
+            for pname, p in model.named_parameters():
+                if p.grad is not None:
+                    out["grad/" + pname] = npy(p.grad).astype(np.float32)
+            for bname, b in model.named_buffers():
+                if "running" in bname:
+                    out["after/" + bname] = npy(b).astype(np.float32)
+    torch.set_default_dtype(torch.float32)
+    np.savez_compressed(OUT / f"{name}.npz", **out)
+    print(f"wrote {name}.npz: N={batch.x.numel()} E={batch.edge_index.size(1)} loss={float(out['loss_f64']):.6f}")
+
+
+def model_cases():
+    rng = np.random.default_rng(20261018)
+    # (1) the reference's own conftest fixture (tests/conftest.py:8-71)
+    d1 = Data(x=torch.tensor([1, 2, 3]), edge_index=torch.tensor([[0, 1, 1, 2], [1, 0, 2, 1]]))
+    d2 = Data(x=torch.tensor([4, 5, 6, 7]), edge_index=torch.tensor([[0, 1, 1, 2, 2, 3], [1, 0, 2, 1, 3, 2]]))
+    dummy = Batch.from_data_list([d1, d2])
+    tgt = torch.tensor([10, 20])
+    neg = torch.tensor([[11, 12, 13, 14, 15], [21, 22, 23, 24, 25]])
+    small = dict(num_items=100, embedding_dim=32, hidden_dim=32, num_layers=2, num_heads=2, dropout=0.0)
+    pe_small = torch.randn(100, 16, generator=torch.Generator().manual_seed(7)).abs()
+    run_model_case("gt_opt_dummy", create_graph_transformer_optimized, small, dummy, tgt, neg, "bpr", 1, pe_small)
+    run_model_case("gt_opt_dummy_nope", create_graph_transformer_optimized,
+                   {**small, "use_laplacian_pe": False}, dummy, tgt, neg, "listwise", 2)
+    run_model_case("gt_ffn_dummy", create_graph_transformer, {**small, "use_laplacian_pe": False},
+                   dummy, tgt, neg, "dual", 3)
+    run_model_case("gat_dummy", create_gat, small, dummy, tgt, neg, "listwise", 4)
+    sage_small = {k: v for k, v in small.items() if k != "num_heads"}
+    run_model_case("sage_dummy", create_graphsage, sage_small, dummy, tgt, neg, "listwise", 5)
+
+    # (2) C4 shape-trace batch: B=32, production widths (D=256, H=2, k_pe=16), small catalogue
+    items = 400
+    b32 = random_sessions_batch(rng, 32, items)
+    tgt = torch.tensor(rng.integers(1, items, size=32))
+    neg = torch.tensor(rng.integers(1, items, size=(32, 5)))
+    prod = dict(num_items=items, embedding_dim=256, hidden_dim=256, num_layers=2, num_heads=2, dropout=0.0)
+    pe = torch.randn(items, 16, generator=torch.Generator().manual_seed(7)).abs()
+    run_model_case("gt_opt_b32", create_graph_transformer_optimized, prod, b32, tgt, neg, "bpr", 11, pe)
+    mid_pe = dict(num_items=items, embedding_dim=64, hidden_dim=64, num_layers=2, num_heads=2, dropout=0.0)
+    run_model_case("gt_opt_b32_dual", create_graph_transformer_optimized, mid_pe, b32, tgt, neg, "dual", 12, pe)
+
+    # (3) directed low->high edges with self loops and edge-less sessions (train_baseline rule, N1)
+    b_dir = random_sessions_batch(rng, 24, items, min_nodes=1, max_nodes=6, symmetric=False)
+    tgt = torch.tensor(rng.integers(1, items, size=24))
+    neg = torch.tensor(rng.integers(1, items, size=(24, 5)))
+    mid = dict(num_items=items, embedding_dim=64, hidden_dim=64, num_layers=2, num_heads=2, dropout=0.0)
+    run_model_case("gt_opt_directed", create_graph_transformer_optimized,
+                   {**mid, "use_laplacian_pe": False}, b_dir, tgt, neg, "listwise", 13)
+    run_model_case("gat_directed", create_gat, {**mid, "num_layers": 3, "num_heads": 4}, b_dir, tgt, neg, "bpr", 14)
+    run_model_case("sage_directed", create_graphsage,
+                   {k: v for k, v in {**mid, "num_layers": 3}.items() if k != "num_heads"},
+                   b_dir, tgt, neg, "bpr", 15)
+    for kind in ("max", "last", "attention"):
+        run_model_case(f"gt_opt_readout_{kind}", create_graph_transformer_optimized,
+                       {**mid, "use_laplacian_pe": False, "readout_type": kind}, b_dir, tgt, neg, "bpr", 16)
+
+
+def loss_readout_metric_cases():
+    torch.set_default_dtype(torch.float64)
+    g = torch.Generator().manual_seed(99)
+    sess = torch.randn(6, 32, generator=g, dtype=torch.float64)
+    emb = torch.nn.Embedding(50, 32).double()
+    tgt = torch.randint(1, 50, (6,), generator=g)
+    neg = torch.randint(1, 50, (6, 5), generator=g)
+    out = {"sess": npy(sess), "table": npy(emb.weight), "target": npy(tgt), "negatives": npy(neg)}
+    for kind, kw in (("bpr", {}), ("listwise", {"temperature": 0.5}), ("dual", {"alpha": 0.7, "temperature": 2.0}),
+                     ("sampled_softmax", {"temperature": 1.0})):
+        s = sess.clone().requires_grad_(True)
+        emb.zero_grad()
+        res = create_loss_function(kind, **kw)(s, tgt, neg, emb)
+        loss = res[0] if isinstance(res, tuple) else res
+        loss.backward()
+        out[f"{kind}/loss"], out[f"{kind}/dsess"], out[f"{kind}/dtable"] = npy(loss), npy(s.grad), npy(emb.weight.grad)
+        if isinstance(res, tuple):
+            out[f"{kind}/parts"] = np.asarray([res[1]["total"], res[1]["listwise"], res[1]["bpr"]])
+    # readouts (etpgt/model/base.py:136-193)
+    x = torch.randn(11, 32, generator=g, dtype=torch.float64)
+    bvec = torch.tensor([0, 0, 0, 1, 2, 2, 2, 2, 3, 3, 3])
+    out["ro/x"], out["ro/batch"] = npy(x), npy(bvec)
+    for kind in ("mean", "max", "last", "attention"):
+        ro = SessionReadout(32, kind).double()
+        if kind == "attention":
+            with torch.no_grad():
+                ro.attention.bias.fill_(0.3)
+            out["ro/att_w"], out["ro/att_b"] = npy(ro.attention.weight), npy(ro.attention.bias)
+        out[f"ro/{kind}"] = npy(ro(x, bvec))
+    # metrics known answers (tests/test_utils.py:62-93) + a random case
+    preds = torch.tensor([[1, 2, 3, 4, 5], [6, 7, 8, 9, 10], [11, 12, 13, 14, 15]])
+    tg = torch.tensor([1, 9, 99])
+    out["met/preds"], out["met/targets"] = npy(preds), npy(tg)
+    out["met/recall5"] = np.asarray(compute_recall_at_k(preds, tg, 5))
+    out["met/recall2"] = np.asarray(compute_recall_at_k(preds, tg, 2))
+    out["met/ndcg5"] = np.asarray(compute_ndcg_at_k(preds, tg, 5))
+    torch.set_default_dtype(torch.float32)
+    np.savez_compressed(OUT / "loss_readout_metrics.npz", **out)
+    print("wrote loss_readout_metrics.npz")
+
+
+def dataloader_case():
+    """Drives the reference SessionDataset/collate_fn (etpgt/train/dataloader.py:12-202) over a
+    small synthetic CSV pair so that the integer outputs of rows a1/a2 are pinned."""
+    rng = np.random.default_rng(5)
+    num_items, num_sessions = 60, 40
+    sessions = []
+    for s in range(num_sessions):
+        length = int(rng.integers(3, 9)) if s != 7 else 58  # one session longer than max_session_length
+        sessions.append(rng.integers(1, num_items, size=length))
+    pairs = {}
+    for items in sessions:  # window-5 co-occurrence, canonical i<=j (scripts/data/04_build_graph.py:57-71)
+        for a in range(len(items)):
+            for b in range(a + 1, min(a + 6, len(items))):
+                i, j = sorted((int(items[a]), int(items[b])))
+                pairs[(i, j)] = pairs.get((i, j), 0) + 1
+    edges = sorted(pairs.items(), key=lambda kv: -kv[1])  # count-descending, like the stored CSV
+    with tempfile.TemporaryDirectory() as tmp:
+        sp, gp = Path(tmp) / "train.csv", Path(tmp) / "graph_edges.csv"
+        with open(sp, "w", newline="") as f:
+            w = csv.writer(f)
+            w.writerow(["timestamp", "visitorid", "event", "itemid", "transactionid", "session_id"])
+            for s, items in enumerate(sessions):
+                for t, it in enumerate(items):
+                    w.writerow([1000 * s + t, s, "view", int(it), "", s])
+        with open(gp, "w", newline="") as f:
+            w = csv.writer(f)
+            w.writerow(["item_i", "item_j", "count", "last_ts", "event_pair_hist"])
+            for (i, j), c in edges:
+                w.writerow([i, j, c, 0, "{}"])
+        ds = SessionDataset(sp, gp, num_negatives=5, max_session_length=50)
+        torch.manual_seed(0)
+        samples = [ds[i] for i in range(len(ds))]
+        batch = collate_fn(samples)
+    flat = np.concatenate(sessions)
+    ptr = np.concatenate([[0], np.cumsum([len(s) for s in sessions])])
+    np.savez_compressed(
+        OUT / "dataloader.npz",
+        item_i=np.asarray([e[0][0] for e in edges]), item_j=np.asarray([e[0][1] for e in edges]),
+        sess_items=flat, sess_ptr=ptr, num_items=np.asarray(int(ds.num_items)),
+        x=npy(batch.x), edge_index=npy(batch.edge_index), batch=npy(batch.batch),
+        target=npy(batch.target_item), negatives=npy(batch.negative_items).reshape(len(samples), 5),
+    )
+    print(f"wrote dataloader.npz: N={batch.x.numel()} E={batch.edge_index.size(1)}")
+
+
+if __name__ == "__main__":
+    OUT.mkdir(parents=True, exist_ok=True)
+    model_cases()
+    loss_readout_metric_cases()
+    dataloader_case()

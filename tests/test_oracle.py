@@ -1,0 +1,186 @@
+"""CPU tests: the oracle restatement (oracle/model_ref.py, graph_ref.py, conv_ref.py) against the
+golden vectors that oracle/make_golden.py produced from the unmodified reference classes, and
+against the reference's own known-answer tests (tests/test_utils.py:62-93) and published
+parameter counts (docs/EXPERIMENTS.md:85-88)."""
+
+import numpy as np
+import pytest
+import torch
+
+from golden_util import Golden, rel_err
+from oracle import graph_ref, model_ref
+
+GT_CASES = ["gt_opt_dummy", "gt_opt_dummy_nope", "gt_opt_b32", "gt_opt_b32_dual", "gt_opt_directed",
+            "gt_opt_readout_max", "gt_opt_readout_last", "gt_opt_readout_attention", "gt_ffn_dummy"]
+
+
+def _gt_forward(g, dtype, training):
+    state = g.group("state", None)
+    state = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in state.items()}
+    cfg = g.cfg()
+    return model_ref.graph_transformer_forward(
+        state, g.tensor("x"), g.tensor("edge_index"), g.tensor("batch"),
+        num_layers=cfg["num_layers"], num_heads=cfg["num_heads"],
+        readout=str(g.raw.get("cfg_readout_type", "mean")), training=training,
+        use_ffn="ffns.0.0.weight" in state)
+
+
+@pytest.mark.parametrize("name", GT_CASES)
+def test_graph_transformer_restatement_matches_reference(name):
+    g = Golden(name)
+    if "readout" in name:
+        g.raw["cfg_readout_type"] = name.rsplit("_", 1)[1]
+    assert rel_err(_gt_forward(g, torch.float64, False), g.raw["eval_out_f64"]) < 1e-10
+    assert rel_err(_gt_forward(g, torch.float64, True), g.raw["train_out_f64"]) < 1e-10
+    assert rel_err(_gt_forward(g, torch.float32, True), g.raw["train_out_f32"]) < 1e-4
+
+
+@pytest.mark.parametrize("name,layers,heads", [("gat_dummy", 2, 2), ("gat_directed", 3, 4)])
+def test_gat_restatement_matches_reference(name, layers, heads):
+    g = Golden(name)
+    state = g.group("state", torch.float64)
+    convs = 1 + max(layers - 2, 0) + (1 if layers > 1 else 0)  # etpgt/model/gat.py:45-111
+    for training, key in ((False, "eval_out_f64"), (True, "train_out_f64")):
+        out = model_ref.gat_forward(state, g.tensor("x"), g.tensor("edge_index"), g.tensor("batch"),
+                                    num_convs=convs, num_heads=heads, training=training)
+        assert rel_err(out, g.raw[key]) < 1e-10
+
+
+@pytest.mark.parametrize("name,layers", [("sage_dummy", 2), ("sage_directed", 3)])
+def test_graphsage_restatement_matches_reference(name, layers):
+    g = Golden(name)
+    state = g.group("state", torch.float64)
+    for training, key in ((False, "eval_out_f64"), (True, "train_out_f64")):
+        out = model_ref.graphsage_forward(state, g.tensor("x"), g.tensor("edge_index"), g.tensor("batch"),
+                                          num_layers=layers, training=training)
+        assert rel_err(out, g.raw[key]) < 1e-10
+
+
+def test_training_gradients_and_running_stats_match_reference():
+    g = Golden("gt_opt_b32")
+    state = {k: (v.double().requires_grad_(True) if v.is_floating_point() else v)
+             for k, v in g.group("state").items()}
+    cfg = g.cfg()
+    sess, _, stats = model_ref.graph_transformer_forward(
+        state, g.tensor("x"), g.tensor("edge_index"), g.tensor("batch"), num_layers=cfg["num_layers"],
+        num_heads=cfg["num_heads"], training=True, return_nodes=True)
+    loss = model_ref.bpr_loss(sess, state["item_embedding.weight"], g.tensor("target"), g.tensor("negatives"))
+    assert abs(loss.item() - g.raw["loss_f64"].item()) < 1e-12
+    loss.backward()
+    for name, want in g.group("grad").items():
+        assert rel_err(state[name].grad, want) < 1e-6, name
+    for name, want in g.group("after").items():
+        if name in stats:
+            assert rel_err(stats[name], want) < 1e-6, name
+
+
+def test_losses_match_reference():
+    g = Golden("loss_readout_metrics")
+    sess0, table0 = g.tensor("sess"), g.tensor("table")
+    tgt, neg = g.tensor("target"), g.tensor("negatives")
+    cases = {
+        "bpr": lambda s, t: model_ref.bpr_loss(s, t, tgt, neg),
+        "listwise": lambda s, t: model_ref.listwise_loss(s, t, tgt, neg, 0.5),
+        "dual": lambda s, t: model_ref.dual_loss(s, t, tgt, neg, 0.7, 2.0)[0],
+        "sampled_softmax": lambda s, t: model_ref.listwise_loss(s, t, tgt, neg, 1.0),
+    }
+    for kind, fn in cases.items():
+        s, t = sess0.clone().requires_grad_(True), table0.clone().requires_grad_(True)
+        loss = fn(s, t)
+        loss.backward()
+        assert abs(loss.item() - g.raw[f"{kind}/loss"].item()) < 1e-12, kind
+        assert rel_err(s.grad, g.raw[f"{kind}/dsess"]) < 1e-10, kind
+        assert rel_err(t.grad, g.raw[f"{kind}/dtable"]) < 1e-10, kind
+    total, lw, bp = model_ref.dual_loss(sess0, table0, tgt, neg, 0.7, 2.0)
+    assert np.allclose([total.item(), lw.item(), bp.item()], g.raw["dual/parts"], atol=1e-12)
+
+
+def test_readouts_match_reference():
+    g = Golden("loss_readout_metrics")
+    x, bvec = g.tensor("ro/x"), g.tensor("ro/batch")
+    for kind in ("mean", "max", "last", "attention"):
+        out = model_ref.session_readout(x, bvec, 4, kind, g.tensor("ro/att_w"), g.tensor("ro/att_b"))
+        assert rel_err(out, g.raw[f"ro/{kind}"]) < 1e-12, kind
+    with pytest.raises(ValueError, match="Unknown readout type"):
+        model_ref.session_readout(x, bvec, 4, "median")
+
+
+def test_metrics_known_answers():
+    # the reference's only known-answer tests: tests/test_utils.py:62-93
+    g = Golden("loss_readout_metrics")
+    preds, tg = g.tensor("met/preds"), g.tensor("met/targets")
+    assert model_ref.recall_at_k(preds, tg, 5) == pytest.approx(2 / 3)
+    assert model_ref.recall_at_k(preds, tg, 2) == pytest.approx(1 / 3)
+    assert 0.4 < model_ref.ndcg_at_k(preds, tg, 5) < 0.5
+    assert model_ref.recall_at_k(preds, tg, 5) == pytest.approx(g.raw["met/recall5"].item())
+    assert model_ref.ndcg_at_k(preds, tg, 5) == pytest.approx(g.raw["met/ndcg5"].item(), abs=1e-7)
+
+
+def test_published_parameter_counts():
+    """docs/EXPERIMENTS.md:85-88 — 188 items, D=64, L=2, H=2: the structural pin of the PyG
+    stand-in (4 biased Linears + bias-free beta; one bias-free GAT lin; SAGE lin_l/lin_r)."""
+    from oracle import conv_ref  # noqa: F401  (puts the stand-in on sys.path)
+    from torch_geometric.nn import GATConv, SAGEConv, TransformerConv
+
+    count = lambda m: sum(p.numel() for p in m.parameters())  # noqa: E731
+    emb, bn = 188 * 64, 2 * 64
+    tconv = count(TransformerConv(64, 32, heads=2, beta=True))
+    assert emb + 2 * (tconv + bn) == 45952
+    ffn = 64 * 256 + 256 + 256 * 64 + 64
+    assert emb + 2 * (tconv + bn + ffn) == 112128
+    assert emb + 2 * (count(GATConv(64, 64, heads=2, concat=False)) + bn) == 29312
+    assert emb + 2 * (count(SAGEConv(64, 64)) + bn) == 28800
+
+
+def test_topk_ties_go_to_lower_id():
+    scores = torch.tensor([[1.0, 3.0, 3.0, 2.0, 3.0], [0.0, 0.0, 0.0, 0.0, 0.0]])
+    _, idx = model_ref.topk_lower_id(scores, 3)
+    assert idx.tolist() == [[1, 2, 4], [0, 1, 2]]
+
+
+# ------------------------------------------------------------------ integer oracle
+
+
+def test_dataloader_restatement_is_bit_exact():
+    g = Golden("dataloader")
+    ptr = g.raw["sess_ptr"]
+    sessions = [g.raw["sess_items"][ptr[i]:ptr[i + 1]] for i in range(len(ptr) - 1)]
+    out = graph_ref.collate_sessions(sessions, g.raw["item_i"], g.raw["item_j"])
+    assert np.array_equal(out["x"], g.raw["x"])
+    assert np.array_equal(np.stack([out["edge_src"], out["edge_dst"]]), g.raw["edge_index"])
+    assert np.array_equal(out["batch"], g.raw["batch"])
+    assert np.array_equal(out["target"], g.raw["target"])
+    # the reference's negatives obey the acceptance rule our sampler restates
+    for s, items in enumerate(sessions):
+        assert not set(g.raw["negatives"][s]) & set(items[-50:])
+        assert g.raw["negatives"][s].min() >= 1
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors, philox4x32 10 rounds
+    assert graph_ref.philox4x32_10((0, 0, 0, 0), (0, 0)) == (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)
+    assert graph_ref.philox4x32_10((0xFFFFFFFF,) * 4, (0xFFFFFFFF,) * 2) == (
+        0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)
+    assert graph_ref.philox4x32_10((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0)) == (
+        0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1)
+
+
+def test_negative_sampler_rule():
+    items = np.arange(1, 40)
+    neg = graph_ref.sample_negatives(seed=42, step=3, session_index=17, session_items=items, num_items=50, num_neg=64)
+    assert neg.min() >= 40 and neg.max() < 50  # never a session item, never padding id 0
+    again = graph_ref.sample_negatives(42, 3, 17, items, 50, 64)
+    assert np.array_equal(neg, again)
+    assert not np.array_equal(neg, graph_ref.sample_negatives(42, 4, 17, items, 50, 64))
+
+
+def test_csr_from_coo_is_stable():
+    src = np.array([2, 0, 1, 2, 0, 2, 1])
+    dst = np.array([1, 1, 0, 1, 2, 0, 1])
+    c = graph_ref.csr_from_coo(src, dst, 4)
+    assert c["rowptr"].tolist() == [0, 2, 6, 7, 7]
+    assert c["eperm"].tolist() == [2, 5, 0, 1, 3, 6, 4]
+    assert c["col"].tolist() == [1, 2, 2, 0, 2, 1, 0]
+    assert c["colptr"].tolist() == [0, 2, 4, 7, 7]
+    assert c["cpos"].tolist() == [3, 6, 0, 5, 1, 2, 4]
+    assert c["row"].tolist() == [1, 2, 0, 1, 0, 1, 1]
