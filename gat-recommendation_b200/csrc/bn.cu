@@ -1,0 +1,255 @@
+// a6: BatchNorm1d over the node rows of the whole batch, fused with the residual add (and the
+// ReLU of the GAT / GraphSAGE wrappers).  etpgt/model/graph_transformer.py:175-176,
+// gat.py:138-140, graphsage.py:76-77.
+//
+// The batch statistics couple every node of the (global) batch, so the op is split at the
+// reduction: stats (per-CTA column sums in double, fixed-order second stage) -> [caller may
+// all-reduce 2*dim doubles across ranks] -> finalize -> apply.  Streaming, HBM-bound:
+// stats reads N*dim*4 B; apply reads 2 rows and writes 1 per node.
+#include "common.cuh"
+
+namespace etpgt {
+namespace {
+
+constexpr int kRowsPerCta = 256;
+
+int stat_parts(int64_t n) {
+  int64_t parts = (n + kRowsPerCta - 1) / kRowsPerCta;
+  if (parts > 4 * kNumSMs) parts = 4 * kNumSMs;
+  return parts < 1 ? 1 : (int)parts;
+}
+
+// blockDim = (dim/4 lanes-x, rows-y): thread (tx, ty) strides over rows ty, ty+RY, ... of the
+// CTA's chunk and owns columns 4*tx..4*tx+3.  MODE 0: sum x, sum x^2.  MODE 1 (backward):
+// sum g, sum g*xhat with g = d_y * (relu ? y > 0 : 1).
+template <int MODE>
+__global__ void bn_partial_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                  const float* __restrict__ d_y, int64_t n, int dim,
+                                  const float* __restrict__ mean, const float* __restrict__ invstd, int relu,
+                                  int64_t chunk, double* __restrict__ partial /* [grid][2][dim] */) {
+  extern __shared__ double sm[];  // [blockDim.y][2][dim]
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int64_t begin = blockIdx.x * chunk;
+  const int64_t end = begin + chunk < n ? begin + chunk : n;
+  double s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0};
+  float4 mu = zero4(), is = zero4();
+  if (MODE == 1) { mu = ld4(mean + 4 * tx); is = ld4(invstd + 4 * tx); }
+  for (int64_t r = begin + ty; r < end; r += blockDim.y) {
+    const float4 a = ldg4(x + r * dim + 4 * tx);
+    if (MODE == 0) {
+      s0[0] += a.x; s0[1] += a.y; s0[2] += a.z; s0[3] += a.w;
+      s1[0] += (double)a.x * a.x; s1[1] += (double)a.y * a.y; s1[2] += (double)a.z * a.z; s1[3] += (double)a.w * a.w;
+    } else {
+      float4 g = ldg4(d_y + r * dim + 4 * tx);
+      if (relu) {
+        const float4 o = ldg4(y + r * dim + 4 * tx);
+        g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f; g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
+      }
+      s0[0] += g.x; s0[1] += g.y; s0[2] += g.z; s0[3] += g.w;
+      s1[0] += (double)g.x * ((a.x - mu.x) * is.x); s1[1] += (double)g.y * ((a.y - mu.y) * is.y);
+      s1[2] += (double)g.z * ((a.z - mu.z) * is.z); s1[3] += (double)g.w * ((a.w - mu.w) * is.w);
+    }
+  }
+  double* mine = sm + (size_t)ty * 2 * dim;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) { mine[4 * tx + c] = s0[c]; mine[dim + 4 * tx + c] = s1[c]; }
+  __syncthreads();
+  const int tid = ty * blockDim.x + tx;
+  for (int i = tid; i < 2 * dim; i += blockDim.x * blockDim.y) {
+    double s = 0;
+    for (int yy = 0; yy < (int)blockDim.y; ++yy) s += sm[(size_t)yy * 2 * dim + i];
+    partial[(int64_t)blockIdx.x * 2 * dim + i] = s;
+  }
+}
+
+__global__ void bn_reduce_kernel(const double* __restrict__ partial, int parts, int width, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= width) return;
+  double s = 0;
+  for (int p = 0; p < parts; ++p) s += partial[(int64_t)p * width + i];
+  out[i] = s;
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, int dim, float eps,
+                                   float momentum, float* __restrict__ mean, float* __restrict__ invstd,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= dim) return;
+  const double mu = sums[d] / count;
+  double var = sums[dim + d] / count - mu * mu;
+  if (var < 0) var = 0;
+  mean[d] = (float)mu;
+  invstd[d] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean != nullptr) {
+    const double unbiased = count > 1 ? var * count / (count - 1) : var;
+    running_mean[d] = (float)((1.0 - momentum) * running_mean[d] + momentum * mu);
+    running_var[d] = (float)((1.0 - momentum) * running_var[d] + momentum * unbiased);
+  }
+}
+
+__global__ void bn_from_running_kernel(const float* __restrict__ rm, const float* __restrict__ rv, int dim,
+                                       float eps, float* __restrict__ mean, float* __restrict__ invstd) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= dim) return;
+  mean[d] = rm[d];
+  invstd[d] = 1.f / sqrtf(rv[d] + eps);
+}
+
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const float* __restrict__ x, int64_t total4, int dim4, const float* __restrict__ mean,
+                const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ bias,
+                const float* __restrict__ residual, int relu, float* __restrict__ y) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % dim4) * 4;
+    const float4 a = ldg4(x + 4 * i);
+    const float4 mu = ld4(mean + c), is = ld4(invstd + c), ga = ld4(gamma + c), be = ld4(bias + c);
+    float4 o;
+    o.x = (a.x - mu.x) * is.x * ga.x + be.x;
+    o.y = (a.y - mu.y) * is.y * ga.y + be.y;
+    o.z = (a.z - mu.z) * is.z * ga.z + be.z;
+    o.w = (a.w - mu.w) * is.w * ga.w + be.w;
+    if (residual != nullptr) o = add4(o, ldg4(residual + 4 * i));
+    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    st4(y + 4 * i, o);
+  }
+}
+
+// d_x = gamma*invstd*(g - sum_g/count - xhat*sum_gxhat/count)   (training)
+//     = gamma*invstd*g                                         (eval)
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ d_y,
+                    int64_t total4, int dim, const float* __restrict__ mean, const float* __restrict__ invstd,
+                    const float* __restrict__ gamma, int relu, int training, const double* __restrict__ sums,
+                    double count, float* __restrict__ d_x) {
+  const int dim4 = dim / 4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % dim4) * 4;
+    float4 g = ldg4(d_y + 4 * i);
+    if (relu) {
+      const float4 o = ldg4(y + 4 * i);
+      g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f; g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
+    }
+    const float4 is = ld4(invstd + c), ga = ld4(gamma + c);
+    float4 r;
+    if (training) {
+      const float4 a = ldg4(x + 4 * i);
+      const float4 mu = ld4(mean + c);
+      const float inv_n = (float)(1.0 / count);
+      const float gs[4] = {(float)sums[c] * inv_n, (float)sums[c + 1] * inv_n, (float)sums[c + 2] * inv_n,
+                           (float)sums[c + 3] * inv_n};
+      const float gx[4] = {(float)sums[dim + c] * inv_n, (float)sums[dim + c + 1] * inv_n,
+                           (float)sums[dim + c + 2] * inv_n, (float)sums[dim + c + 3] * inv_n};
+      r.x = ga.x * is.x * (g.x - gs[0] - (a.x - mu.x) * is.x * gx[0]);
+      r.y = ga.y * is.y * (g.y - gs[1] - (a.y - mu.y) * is.y * gx[1]);
+      r.z = ga.z * is.z * (g.z - gs[2] - (a.z - mu.z) * is.z * gx[2]);
+      r.w = ga.w * is.w * (g.w - gs[3] - (a.w - mu.w) * is.w * gx[3]);
+    } else {
+      r.x = ga.x * is.x * g.x; r.y = ga.y * is.y * g.y; r.z = ga.z * is.z * g.z; r.w = ga.w * is.w * g.w;
+    }
+    st4(d_x + 4 * i, r);
+  }
+}
+
+__global__ void bn_param_grad_kernel(const double* __restrict__ local_sums, int dim, float* __restrict__ d_gamma,
+                                     float* __restrict__ d_bias) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= dim) return;
+  d_bias[d] = (float)local_sums[d];
+  d_gamma[d] = (float)local_sums[dim + d];
+}
+
+template <int MODE>
+int launch_partial(const float* x, const float* y, const float* d_y, int64_t n, int dim, const float* mean,
+                   const float* invstd, int relu, double* sums, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  const int parts = stat_parts(n);
+  const size_t need = align_up((size_t)parts * 2 * dim * sizeof(double));
+  if (ws_bytes < need) { set_error("bn: workspace %zu < %zu", ws_bytes, need); return ETPGT_EWORKSPACE; }
+  double* partial = static_cast<double*>(ws);
+  const int64_t chunk = n > 0 ? (n + parts - 1) / parts : 0;
+  const int tx = dim / 4;
+  const int ty = 256 / tx > 0 ? 256 / tx : 1;
+  const size_t smem = (size_t)ty * 2 * dim * sizeof(double);
+  bn_partial_kernel<MODE><<<parts, dim3(tx, ty), smem, stream>>>(x, y, d_y, n, dim, mean, invstd, relu, chunk, partial);
+  ETPGT_CHECK_LAUNCH("bn_partial");
+  bn_reduce_kernel<<<(2 * dim + 255) / 256, 256, 0, stream>>>(partial, parts, 2 * dim, sums);
+  ETPGT_CHECK_LAUNCH("bn_reduce");
+  return ETPGT_OK;
+}
+
+}  // namespace
+}  // namespace etpgt
+
+using namespace etpgt;
+
+extern "C" size_t etpgt_bn_workspace_bytes(int64_t n, int dim) {
+  return align_up((size_t)stat_parts(n) * 2 * dim * sizeof(double)) + 256;
+}
+
+extern "C" int etpgt_bn_stats(const float* x, int64_t n, int dim, double* sums, void* ws, size_t ws_bytes,
+                              etpgt_stream_t stream) {
+  ETPGT_REQUIRE(dim % 4 == 0 && dim >= 4 && dim <= 1024, "bn_stats: dim %d must be a multiple of 4 <= 1024", dim);
+  ETPGT_REQUIRE(n >= 0 && x && sums, "bn_stats: bad arguments");
+  return launch_partial<0>(x, nullptr, nullptr, n, dim, nullptr, nullptr, 0, sums, ws, ws_bytes,
+                           static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int etpgt_bn_finalize(const double* sums, double count, int dim, float eps, float momentum, float* mean,
+                                 float* invstd, float* running_mean, float* running_var, etpgt_stream_t stream) {
+  ETPGT_REQUIRE(count >= 1 && dim > 0 && sums && mean && invstd, "bn_finalize: bad arguments");
+  bn_finalize_kernel<<<(dim + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      sums, count, dim, eps, momentum, mean, invstd, running_mean, running_var);
+  ETPGT_CHECK_LAUNCH("bn_finalize");
+  return ETPGT_OK;
+}
+
+extern "C" int etpgt_bn_from_running(const float* running_mean, const float* running_var, int dim, float eps,
+                                     float* mean, float* invstd, etpgt_stream_t stream) {
+  ETPGT_REQUIRE(dim > 0 && running_mean && running_var && mean && invstd, "bn_from_running: bad arguments");
+  bn_from_running_kernel<<<(dim + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(running_mean, running_var,
+                                                                                        dim, eps, mean, invstd);
+  ETPGT_CHECK_LAUNCH("bn_from_running");
+  return ETPGT_OK;
+}
+
+extern "C" int etpgt_bn_apply(const float* x, int64_t n, int dim, const float* mean, const float* invstd,
+                              const float* gamma, const float* bias, const float* residual, int relu, float* y,
+                              etpgt_stream_t stream) {
+  ETPGT_REQUIRE(dim % 4 == 0 && dim >= 4, "bn_apply: dim %d must be a multiple of 4", dim);
+  ETPGT_REQUIRE(n >= 0 && x && mean && invstd && gamma && bias && y, "bn_apply: bad arguments");
+  if (n == 0) return ETPGT_OK;
+  const int64_t total4 = n * (dim / 4);
+  bn_apply_kernel<<<grid_for(total4, 256 * 4, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, total4, dim / 4, mean, invstd, gamma, bias, residual, relu, y);
+  ETPGT_CHECK_LAUNCH("bn_apply");
+  return ETPGT_OK;
+}
+
+extern "C" int etpgt_bn_bwd_stats(const float* x, const float* y, const float* d_y, int64_t n, int dim,
+                                  const float* mean, const float* invstd, int relu, double* sums, void* ws,
+                                  size_t ws_bytes, etpgt_stream_t stream) {
+  ETPGT_REQUIRE(dim % 4 == 0 && dim >= 4 && dim <= 1024, "bn_bwd_stats: dim %d must be a multiple of 4 <= 1024", dim);
+  ETPGT_REQUIRE(n >= 0 && x && d_y && mean && invstd && sums && (!relu || y), "bn_bwd_stats: bad arguments");
+  return launch_partial<1>(x, y, d_y, n, dim, mean, invstd, relu, sums, ws, ws_bytes,
+                           static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int etpgt_bn_bwd_apply(const float* x, const float* y, const float* d_y, int64_t n, int dim,
+                                  const float* mean, const float* invstd, const float* gamma, int relu,
+                                  int training, const double* sums, double count, const double* local_sums,
+                                  float* d_x, float* d_gamma, float* d_bias, etpgt_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ETPGT_REQUIRE(dim % 4 == 0 && dim >= 4, "bn_bwd_apply: dim %d must be a multiple of 4", dim);
+  ETPGT_REQUIRE(n >= 0 && d_y && mean && invstd && gamma && d_x && local_sums && (!training || (x && sums && count >= 1)),
+                "bn_bwd_apply: bad arguments");
+  if (n > 0) {
+    const int64_t total4 = n * (dim / 4);
+    bn_bwd_apply_kernel<<<grid_for(total4, 256 * 4, 8), 256, 0, stream>>>(x, y, d_y, total4, dim, mean, invstd, gamma,
+                                                                         relu, training, sums, count, d_x);
+    ETPGT_CHECK_LAUNCH("bn_bwd_apply");
+  }
+  if (d_gamma != nullptr && d_bias != nullptr) {
+    bn_param_grad_kernel<<<(dim + 127) / 128, 128, 0, stream>>>(local_sums, dim, d_gamma, d_bias);
+    ETPGT_CHECK_LAUNCH("bn_param_grad");
+  }
+  return ETPGT_OK;
+}

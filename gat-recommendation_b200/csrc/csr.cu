@@ -1,0 +1,136 @@
+// Destination-sorted CSR + source-sorted CSC from an int64 COO edge list, and segment
+// pointers from a sorted id vector.  Integer work, bit-exact against oracle/graph_ref.py.
+//
+// HBM-bound: 2 stable radix sorts of E (key,value) int32 pairs (cub::DeviceRadixSort, only
+// the bits needed for num_nodes) plus three streaming passes.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+
+namespace etpgt {
+namespace {
+
+constexpr int kThreads = 256;
+
+__global__ void narrow_keys_kernel(const int64_t* __restrict__ key64, int32_t* __restrict__ key32,
+                                   int32_t* __restrict__ iota, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    key32[i] = static_cast<int32_t>(key64[i]);
+    iota[i] = static_cast<int32_t>(i);
+  }
+}
+
+// ptr[r] = first position p with sorted_key[p] >= r, for r in [0, num_rows]; thread p fills
+// the rows between sorted_key[p-1] and sorted_key[p] (sentinels -1 and num_rows).
+template <typename KeyT>
+__global__ void boundaries_kernel(const KeyT* __restrict__ sorted_key, int64_t n, int64_t num_rows,
+                                  int32_t* __restrict__ ptr) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p <= n; p += (int64_t)gridDim.x * blockDim.x) {
+    int64_t prev = p == 0 ? -1 : static_cast<int64_t>(sorted_key[p - 1]);
+    int64_t cur = p == n ? num_rows : static_cast<int64_t>(sorted_key[p]);
+    if (cur > num_rows) cur = num_rows;
+    for (int64_t r = prev + 1; r <= cur; ++r) ptr[r] = static_cast<int32_t>(p);
+  }
+}
+
+// col[p] = src[eperm[p]]  (also emits the iota for the second sort)
+__global__ void gather_src_kernel(const int64_t* __restrict__ src, const int32_t* __restrict__ eperm,
+                                  int32_t* __restrict__ col, int32_t* __restrict__ iota, int64_t n) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    col[p] = static_cast<int32_t>(src[eperm[p]]);
+    iota[p] = static_cast<int32_t>(p);
+  }
+}
+
+// row[p] = dst_sorted[cpos[p]]
+__global__ void gather_i32_kernel(const int32_t* __restrict__ values, const int32_t* __restrict__ index,
+                                  int32_t* __restrict__ out, int64_t n) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x)
+    out[p] = values[index[p]];
+}
+
+int key_bits(int64_t num_nodes) {
+  int bits = 1;
+  while ((int64_t(1) << bits) < num_nodes && bits < 31) ++bits;
+  return bits;
+}
+
+size_t sort_temp_bytes(int64_t n, int bits) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const int32_t*)nullptr, (int32_t*)nullptr,
+                                  (const int32_t*)nullptr, (int32_t*)nullptr, static_cast<int>(n), 0, bits);
+  return bytes;
+}
+
+}  // namespace
+}  // namespace etpgt
+
+using namespace etpgt;
+
+extern "C" size_t etpgt_csr_workspace_bytes(int64_t num_edges, int64_t num_nodes) {
+  int64_t e = num_edges > 0 ? num_edges : 1;
+  // cub's temp-size query does not touch the device; 5 int32 arrays of E plus the sort temp
+  size_t temp = sort_temp_bytes(e, key_bits(num_nodes));
+  return 5 * align_up(e * sizeof(int32_t)) + align_up(temp) + 256;
+}
+
+extern "C" int etpgt_csr_from_coo(const int64_t* src, const int64_t* dst, int64_t num_edges, int64_t num_nodes,
+                                  int32_t* rowptr, int32_t* col, int32_t* eperm, int32_t* colptr,
+                                  int32_t* row, int32_t* cpos, void* ws, size_t ws_bytes,
+                                  etpgt_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ETPGT_REQUIRE(num_edges >= 0 && num_nodes >= 0, "csr_from_coo: negative size");
+  ETPGT_REQUIRE(num_edges < (int64_t(1) << 31) && num_nodes < (int64_t(1) << 31) - 1,
+                "csr_from_coo: sizes must fit int32");
+  ETPGT_REQUIRE(rowptr && colptr, "csr_from_coo: null output");
+  if (ws_bytes < etpgt_csr_workspace_bytes(num_edges, num_nodes)) {
+    set_error("csr_from_coo: workspace %zu < %zu", ws_bytes, etpgt_csr_workspace_bytes(num_edges, num_nodes));
+    return ETPGT_EWORKSPACE;
+  }
+  const int64_t E = num_edges;
+  const int grid_e = grid_for(E + 1, kThreads, 8);
+  if (E == 0) {
+    boundaries_kernel<int32_t><<<1, kThreads, 0, stream>>>(nullptr, 0, num_nodes, rowptr);
+    ETPGT_CHECK_LAUNCH("boundaries(rowptr, E=0)");
+    boundaries_kernel<int32_t><<<1, kThreads, 0, stream>>>(nullptr, 0, num_nodes, colptr);
+    ETPGT_CHECK_LAUNCH("boundaries(colptr, E=0)");
+    return ETPGT_OK;
+  }
+  Workspace w(ws, ws_bytes);
+  int32_t* key_a = w.take<int32_t>(E);
+  int32_t* key_b = w.take<int32_t>(E);   // dst in CSR order
+  int32_t* iota = w.take<int32_t>(E);
+  int32_t* key_c = w.take<int32_t>(E);   // src in CSC order
+  const int bits = key_bits(num_nodes);
+  size_t temp_bytes = sort_temp_bytes(E, bits);
+  void* temp = w.take<char>(temp_bytes);
+
+  narrow_keys_kernel<<<grid_e, kThreads, 0, stream>>>(dst, key_a, iota, E);
+  ETPGT_CHECK_LAUNCH("narrow_keys");
+  cudaError_t err = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, key_a, key_b, iota, eperm,
+                                                    static_cast<int>(E), 0, bits, stream);
+  if (err != cudaSuccess) { set_error("csr sort 1: %s", cudaGetErrorString(err)); return ETPGT_ECUDA; }
+  count_launch(4);
+  boundaries_kernel<int32_t><<<grid_e, kThreads, 0, stream>>>(key_b, E, num_nodes, rowptr);
+  ETPGT_CHECK_LAUNCH("boundaries(rowptr)");
+  gather_src_kernel<<<grid_e, kThreads, 0, stream>>>(src, eperm, col, iota, E);
+  ETPGT_CHECK_LAUNCH("gather_src");
+  err = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, col, key_c, iota, cpos, static_cast<int>(E), 0, bits,
+                                        stream);
+  if (err != cudaSuccess) { set_error("csr sort 2: %s", cudaGetErrorString(err)); return ETPGT_ECUDA; }
+  count_launch(4);
+  boundaries_kernel<int32_t><<<grid_e, kThreads, 0, stream>>>(key_c, E, num_nodes, colptr);
+  ETPGT_CHECK_LAUNCH("boundaries(colptr)");
+  gather_i32_kernel<<<grid_e, kThreads, 0, stream>>>(key_b, cpos, row, E);
+  ETPGT_CHECK_LAUNCH("gather_row");
+  return ETPGT_OK;
+}
+
+extern "C" int etpgt_segment_ptr(const int64_t* seg_ids, int64_t n, int64_t num_segments, int32_t* ptr,
+                                 etpgt_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ETPGT_REQUIRE(n >= 0 && num_segments >= 0 && n < (int64_t(1) << 31), "segment_ptr: bad size");
+  boundaries_kernel<int64_t><<<grid_for(n + 1, kThreads, 8), kThreads, 0, stream>>>(seg_ids, n, num_segments, ptr);
+  ETPGT_CHECK_LAUNCH("boundaries(segment_ptr)");
+  return ETPGT_OK;
+}

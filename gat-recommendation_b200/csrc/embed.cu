@@ -1,0 +1,184 @@
+// a4: item-embedding gather fused with the Laplacian-PE projection.
+//   out[n] = table[ids[n]] + pe[row(n)] @ w_pe^T + b_pe
+// etpgt/model/graph_transformer.py:140-152, etpgt/encodings/laplacian_pe.py:170-199.
+//
+// Gather-bound: per node one table row (DIM*4 B, 128-bit loads, a lane group per row), one PE
+// row (k_pe*4 B, broadcast) and one output row.  w_pe^T (k_pe x DIM) and b_pe are staged once
+// per CTA in shared memory so the projection costs no global traffic.
+#include "common.cuh"
+
+namespace etpgt {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxKpe = 64;
+
+template <int DIM>
+__global__ void __launch_bounds__(kThreads)
+embed_pe_fwd_kernel(const int64_t* __restrict__ ids, int64_t n, const float* __restrict__ table,
+                    const float* __restrict__ pe, int pe_per_node, const float* __restrict__ w_pe,
+                    const float* __restrict__ b_pe, int k_pe, float* __restrict__ out) {
+  using G = RowGeom<DIM>;
+  extern __shared__ float smem[];  // w^T [k_pe][DIM] then bias [DIM]
+  float* wt = smem;
+  float* bias = smem + (size_t)k_pe * DIM;
+  if (pe != nullptr) {
+    for (int i = threadIdx.x; i < k_pe * DIM; i += kThreads) {
+      const int d = i / k_pe, k = i % k_pe;  // w_pe is [DIM][k_pe] (nn.Linear weight)
+      wt[k * DIM + d] = w_pe[i];
+    }
+    for (int d = threadIdx.x; d < DIM; d += kThreads) bias[d] = b_pe[d];
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31;
+  const int lig = lane % G::LPN;
+  const int64_t groups_per_cta = (kThreads / 32) * G::GROUPS;
+  const int64_t group0 = blockIdx.x * groups_per_cta + (threadIdx.x >> 5) * G::GROUPS + lane / G::LPN;
+  for (int64_t node = group0; node < n; node += (int64_t)gridDim.x * groups_per_cta) {
+    const int64_t id = ids[node];
+    const float* trow = table + id * DIM;
+    float4 acc[G::V];
+#pragma unroll
+    for (int v = 0; v < G::V; ++v) acc[v] = ldg4(trow + 4 * (v * G::LPN + lig));
+    if (pe != nullptr) {
+      const float* prow = pe + (pe_per_node ? node : id) * (int64_t)k_pe;
+#pragma unroll
+      for (int v = 0; v < G::V; ++v) acc[v] = add4(acc[v], ld4(bias + 4 * (v * G::LPN + lig)));
+      for (int k = 0; k < k_pe; ++k) {
+        const float p = __ldg(prow + k);
+#pragma unroll
+        for (int v = 0; v < G::V; ++v) acc[v] = fma4(p, ld4(wt + k * DIM + 4 * (v * G::LPN + lig)), acc[v]);
+      }
+    }
+    float* orow = out + node * DIM;
+#pragma unroll
+    for (int v = 0; v < G::V; ++v) st4(orow + 4 * (v * G::LPN + lig), acc[v]);
+  }
+}
+
+// d_w_pe[d][k] = sum_n d_out[n][d] * pe[row(n)][k];  d_b_pe[d] = sum_n d_out[n][d].
+// Stage 1: CTA c owns a contiguous chunk of nodes; thread d accumulates k_pe+1 sums in
+// registers (PE rows staged through shared memory in tiles).  Stage 2 adds the per-CTA partials
+// in CTA order (fixed order -> deterministic).
+template <int DIM, int KPE>
+__global__ void __launch_bounds__(DIM)
+pe_wgrad_partial_kernel(const int64_t* __restrict__ ids, int64_t n, const float* __restrict__ d_out,
+                        const float* __restrict__ pe, int pe_per_node, int64_t chunk,
+                        float* __restrict__ partial /* [grid][DIM][KPE+1] */) {
+  constexpr int TILE = 32;
+  __shared__ float pe_tile[TILE][KPE];
+  const int d = threadIdx.x;
+  const int64_t begin = blockIdx.x * chunk;
+  const int64_t end = begin + chunk < n ? begin + chunk : n;
+  float acc[KPE + 1];
+#pragma unroll
+  for (int k = 0; k <= KPE; ++k) acc[k] = 0.f;
+  for (int64_t base = begin; base < end; base += TILE) {
+    const int rows = (int)(end - base < TILE ? end - base : TILE);
+    __syncthreads();
+    for (int i = threadIdx.x; i < rows * KPE; i += DIM) {
+      const int r = i / KPE, k = i % KPE;
+      const int64_t prow = pe_per_node ? base + r : ids[base + r];
+      pe_tile[r][k] = pe[prow * KPE + k];
+    }
+    __syncthreads();
+    for (int r = 0; r < rows; ++r) {
+      const float g = d_out[(base + r) * DIM + d];
+#pragma unroll
+      for (int k = 0; k < KPE; ++k) acc[k] = fmaf(g, pe_tile[r][k], acc[k]);
+      acc[KPE] += g;
+    }
+  }
+  float* dst = partial + ((int64_t)blockIdx.x * DIM + d) * (KPE + 1);
+#pragma unroll
+  for (int k = 0; k <= KPE; ++k) dst[k] = acc[k];
+}
+
+__global__ void pe_wgrad_reduce_kernel(const float* __restrict__ partial, int parts, int dim, int kpe,
+                                       float* __restrict__ d_w, float* __restrict__ d_b) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over dim*(kpe+1)
+  if (i >= dim * (kpe + 1)) return;
+  float s = 0.f;
+  for (int p = 0; p < parts; ++p) s += partial[(int64_t)p * dim * (kpe + 1) + i];
+  const int d = i / (kpe + 1), k = i % (kpe + 1);
+  if (k == kpe) d_b[d] = s; else d_w[d * kpe + k] = s;
+}
+
+int wgrad_parts(int64_t n) {
+  int64_t parts = (n + 255) / 256;
+  if (parts > 2 * kNumSMs) parts = 2 * kNumSMs;
+  return parts < 1 ? 1 : (int)parts;
+}
+
+}  // namespace
+}  // namespace etpgt
+
+using namespace etpgt;
+
+extern "C" int etpgt_embed_pe_fwd(const int64_t* ids, int64_t n, const float* table, int64_t num_items,
+                                  const float* pe, int pe_per_node, const float* w_pe, const float* b_pe,
+                                  int k_pe, int dim, float* out, etpgt_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ETPGT_REQUIRE(supported_dim(dim), "embed_pe_fwd: unsupported dim %d", dim);
+  ETPGT_REQUIRE(n >= 0 && num_items > 0, "embed_pe_fwd: bad size");
+  ETPGT_REQUIRE(pe == nullptr || (w_pe && b_pe && k_pe >= 1 && k_pe <= kMaxKpe), "embed_pe_fwd: bad PE arguments");
+  if (n == 0) return ETPGT_OK;
+  const size_t smem = pe ? ((size_t)k_pe * dim + dim) * sizeof(float) : 0;
+#define CALL(D)                                                                                     \
+  {                                                                                                 \
+    if (smem > 48 * 1024)                                                                           \
+      cudaFuncSetAttribute(embed_pe_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    const int64_t gpc = (kThreads / 32) * RowGeom<D>::GROUPS;                                       \
+    embed_pe_fwd_kernel<D><<<grid_for(n, (int)gpc * 4, 8), kThreads, smem, stream>>>(                \
+        ids, n, table, pe, pe_per_node, w_pe, b_pe, k_pe, out);                                     \
+  }
+  ETPGT_DISPATCH_DIM(dim, CALL)
+#undef CALL
+  ETPGT_CHECK_LAUNCH("embed_pe_fwd");
+  return ETPGT_OK;
+}
+
+extern "C" size_t etpgt_embed_pe_bwd_workspace_bytes(int64_t n, int dim, int k_pe) {
+  return etpgt_scatter_rows_workspace_bytes(n) +
+         align_up((size_t)wgrad_parts(n) * dim * (k_pe + 1) * sizeof(float)) + 256;
+}
+
+extern "C" int etpgt_embed_pe_bwd(const int64_t* ids, int64_t n, const float* d_out, int64_t num_items,
+                                  const float* pe, int pe_per_node, int k_pe, int dim, int64_t padding_idx,
+                                  float* d_table, float* d_w_pe, float* d_b_pe, void* ws, size_t ws_bytes,
+                                  etpgt_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ETPGT_REQUIRE(supported_dim(dim), "embed_pe_bwd: unsupported dim %d", dim);
+  ETPGT_REQUIRE(pe == nullptr || k_pe == 8 || k_pe == 16 || k_pe == 32,
+                "embed_pe_bwd: k_pe must be 8, 16 or 32 (got %d)", k_pe);
+  if (ws_bytes < etpgt_embed_pe_bwd_workspace_bytes(n, dim, k_pe)) {
+    set_error("embed_pe_bwd: workspace too small");
+    return ETPGT_EWORKSPACE;
+  }
+  if (d_table != nullptr && n > 0) {
+    int rc = etpgt_scatter_rows(ids, nullptr, d_out, n, 1, dim, num_items, padding_idx, d_table, ws,
+                                etpgt_scatter_rows_workspace_bytes(n), stream_);
+    if (rc != ETPGT_OK) return rc;
+  }
+  if (pe == nullptr) return ETPGT_OK;
+  ETPGT_REQUIRE(d_w_pe && d_b_pe, "embed_pe_bwd: null PE gradient outputs");
+  float* partial = reinterpret_cast<float*>(static_cast<char*>(ws) + etpgt_scatter_rows_workspace_bytes(n));
+  const int parts = wgrad_parts(n);
+  const int64_t chunk = n > 0 ? (n + parts - 1) / parts : 0;
+#define CALL_K(D, K) \
+  pe_wgrad_partial_kernel<D, K><<<parts, D, 0, stream>>>(ids, n, d_out, pe, pe_per_node, chunk, partial);
+#define CALL(D)                                   \
+  {                                               \
+    if (k_pe == 8) { CALL_K(D, 8) }               \
+    else if (k_pe == 16) { CALL_K(D, 16) }        \
+    else { CALL_K(D, 32) }                        \
+  }
+  ETPGT_DISPATCH_DIM(dim, CALL)
+#undef CALL
+#undef CALL_K
+  ETPGT_CHECK_LAUNCH("pe_wgrad_partial");
+  const int total = dim * (k_pe + 1);
+  pe_wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, stream>>>(partial, parts, dim, k_pe, d_w_pe, d_b_pe);
+  ETPGT_CHECK_LAUNCH("pe_wgrad_reduce");
+  return ETPGT_OK;
+}

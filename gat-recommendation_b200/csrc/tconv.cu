@@ -1,0 +1,435 @@
+// a5: fused TransformerConv over the destination-sorted CSR (forward) and CSR + CSC (backward).
+// PyG TransformerConv(concat=True, beta=True, root_weight=True) as reached from
+// etpgt/model/graph_transformer.py:73-98,174 (semantics: SURVEY.md §3.3 / oracle/conv_ref.py).
+//
+// Layout: qkvs [N, 4*DIM] row-major = query | key | value | skip, so the key and value rows an
+// edge gathers are one contiguous 2*DIM*4-byte span.  A lane group of LPN = min(32, DIM/4)
+// lanes owns one destination row; each lane keeps V = DIM/(4*LPN) float4 of it, and the
+// per-head dot products are butterfly reductions over the lanes of that head (head_reduce).
+// Softmax is one-pass (running max / running sum, flash-style) so every key/value row is read
+// exactly once; logits, alphas and the [E, DIM] gathers of the PyG path never exist in HBM.
+//
+// HBM-bound.  Algorithmic bytes (fp32): forward 2*DIM*4 per edge + 4*DIM*4 per node
+// (q, skip in; out, agg out); backward 4*DIM*4 per edge + 10*DIM*4 per node.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace etpgt {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kEdgeUnroll = 4;
+constexpr float kSoftmaxEps = 1e-16f;  // PyG utils.softmax: p / (sum + 1e-16)
+
+template <int DIM>
+__device__ __forceinline__ void load_row(const float* __restrict__ row, int lig, float4 (&dst)[RowGeom<DIM>::V]) {
+#pragma unroll
+  for (int v = 0; v < RowGeom<DIM>::V; ++v) dst[v] = ldg4(row + 4 * (v * RowGeom<DIM>::LPN + lig));
+}
+
+// ------------------------------------------------------------------------------- forward
+template <int DIM, int HEAD_DIM>
+__global__ void __launch_bounds__(kThreads)
+tconv_fwd_kernel(const float* __restrict__ qkvs, int64_t num_nodes, const int32_t* __restrict__ rowptr,
+                 const int32_t* __restrict__ col, const int32_t* __restrict__ eperm,
+                 const float* __restrict__ w_beta, const float* __restrict__ alpha_mask,
+                 float* __restrict__ out, float* __restrict__ agg_out, float* __restrict__ beta_out,
+                 float* __restrict__ m_out, float* __restrict__ invl_out) {
+  using G = RowGeom<DIM>;
+  constexpr int V = G::V, LPN = G::LPN;
+  constexpr int HEADS = DIM / HEAD_DIM;
+  constexpr int HEAD_F4 = HEAD_DIM / 4;
+  const float scale = rsqrtf((float)HEAD_DIM);
+  const int lane = threadIdx.x & 31;
+  const int lig = lane % LPN;
+  const int64_t warp_global = (blockIdx.x * (int64_t)kThreads + threadIdx.x) >> 5;
+  const int64_t node = warp_global * G::GROUPS + lane / LPN;
+  const bool valid = node < num_nodes;
+  if (warp_global * G::GROUPS >= num_nodes) return;  // whole warp out of range
+
+  const int64_t nrow = valid ? node : 0;
+  const float* self = qkvs + nrow * 4 * DIM;
+  float4 q[V];
+  load_row<DIM>(self, lig, q);
+  const int begin = valid ? rowptr[nrow] : 0;
+  const int deg = valid ? rowptr[nrow + 1] - begin : 0;
+  int deg_max = deg;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) deg_max = max(deg_max, __shfl_xor_sync(0xffffffffu, deg_max, off));
+
+  float m[V], l[V];
+  float4 acc[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) { m[v] = -INFINITY; l[v] = 0.f; acc[v] = zero4(); }
+
+  for (int e0 = 0; e0 < deg_max; e0 += kEdgeUnroll) {
+    float4 kr[kEdgeUnroll][V], vr[kEdgeUnroll][V];
+    int pos[kEdgeUnroll];
+#pragma unroll
+    for (int u = 0; u < kEdgeUnroll; ++u) {
+      const bool on = e0 + u < deg;
+      pos[u] = on ? begin + e0 + u : -1;
+      const int64_t j = on ? col[pos[u]] : nrow;
+      const float* other = qkvs + j * 4 * DIM;
+      load_row<DIM>(other + DIM, lig, kr[u]);
+      load_row<DIM>(other + 2 * DIM, lig, vr[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < kEdgeUnroll; ++u) {
+      float a[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) a[v] = dot4(q[v], kr[u][v]);
+      head_reduce<DIM, HEAD_DIM>(a);
+      if (pos[u] >= 0) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const float logit = a[v] * scale;
+          const float m_new = fmaxf(m[v], logit);
+          const float corr = expf(m[v] - m_new);
+          float p = expf(logit - m_new);
+          l[v] = l[v] * corr + p;
+          if (alpha_mask != nullptr)
+            p *= alpha_mask[(int64_t)eperm[pos[u]] * HEADS + head_of<DIM, HEAD_DIM>(v, lig)];
+          acc[v] = fma4(p, vr[u][v], scale4(corr, acc[v]));
+          m[v] = m_new;
+        }
+      }
+    }
+  }
+
+  float4 xr[V], ag[V];
+  load_row<DIM>(self + 3 * DIM, lig, xr);
+  float zpart = 0.f;
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const float inv = 1.f / (l[v] + kSoftmaxEps);
+    ag[v] = scale4(inv, acc[v]);
+    const int f = v * LPN + lig;
+    if (valid && f % HEAD_F4 == 0) {
+      m_out[nrow * HEADS + f / HEAD_F4] = m[v];
+      invl_out[nrow * HEADS + f / HEAD_F4] = inv;
+    }
+    if (w_beta != nullptr) {
+      const float4 w1 = ldg4(w_beta + 4 * f), w2 = ldg4(w_beta + DIM + 4 * f), w3 = ldg4(w_beta + 2 * DIM + 4 * f);
+      zpart += dot4(w1, ag[v]) + dot4(w2, xr[v]) + dot4(w3, sub4(ag[v], xr[v]));
+    }
+  }
+  float b = 0.f;
+  if (w_beta != nullptr) {
+    const float z = group_sum<LPN>(zpart);
+    b = 1.f / (1.f + expf(-z));
+  }
+  if (!valid) return;
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const int f = v * LPN + lig;
+    float4 o;
+    if (w_beta != nullptr) o = add4(scale4(b, xr[v]), scale4(1.f - b, ag[v]));
+    else o = add4(ag[v], xr[v]);
+    st4(out + nrow * DIM + 4 * f, o);
+    st4(agg_out + nrow * DIM + 4 * f, ag[v]);
+  }
+  if (lig == 0 && beta_out != nullptr) beta_out[nrow] = b;
+}
+
+// ------------------------------------------------------------ backward, destination pass
+// Per destination i: gate backward (d_agg, d_skip, w_beta partials), delta_h = <d_agg, agg>_h,
+// then over in-edges: alpha (recomputed from saved m, 1/l), d_alpha = <d_agg, v_j>_h,
+// d_logit = alpha (d_alpha*mask - delta), d_query += scale*d_logit*k_j.  Emits per-edge
+// (alpha*mask, scale*d_logit) for the source pass.
+template <int DIM, int HEAD_DIM>
+__global__ void __launch_bounds__(kThreads)
+tconv_bwd_dst_kernel(const float* __restrict__ qkvs, const float* __restrict__ d_out, int64_t num_nodes,
+                     const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                     const int32_t* __restrict__ eperm, const float* __restrict__ w_beta,
+                     const float* __restrict__ alpha_mask, const float* __restrict__ agg,
+                     const float* __restrict__ beta, const float* __restrict__ m_in,
+                     const float* __restrict__ invl_in, float* __restrict__ d_qkvs,
+                     float* __restrict__ d_agg_out, float2* __restrict__ ecoef,
+                     float* __restrict__ wbeta_partial /* [grid][3*DIM] */) {
+  using G = RowGeom<DIM>;
+  constexpr int V = G::V, LPN = G::LPN;
+  constexpr int HEADS = DIM / HEAD_DIM;
+  constexpr int HEAD_F4 = HEAD_DIM / 4;
+  const float scale = rsqrtf((float)HEAD_DIM);
+  const int lane = threadIdx.x & 31;
+  const int lig = lane % LPN;
+  const int warp_in_cta = threadIdx.x >> 5;
+  const int64_t nodes_per_cta = (kThreads / 32) * G::GROUPS;
+
+  float4 dw1[V], dw2[V], dw3[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) { dw1[v] = zero4(); dw2[v] = zero4(); dw3[v] = zero4(); }
+
+  for (int64_t base = blockIdx.x * nodes_per_cta; base < num_nodes; base += (int64_t)gridDim.x * nodes_per_cta) {
+    const int64_t warp_base = base + warp_in_cta * G::GROUPS;
+    if (warp_base >= num_nodes) continue;  // warp-uniform
+    const int64_t node = warp_base + lane / LPN;
+    const bool valid = node < num_nodes;
+    const int64_t nrow = valid ? node : 0;
+    const float* self = qkvs + nrow * 4 * DIM;
+
+    float4 g[V], xr[V], ag[V], dag[V], q[V];
+    load_row<DIM>(d_out + nrow * DIM, lig, g);
+    load_row<DIM>(self + 3 * DIM, lig, xr);
+    load_row<DIM>(agg + nrow * DIM, lig, ag);
+    load_row<DIM>(self, lig, q);
+    if (w_beta != nullptr) {
+      const float b = beta[nrow];
+      float part = 0.f;
+#pragma unroll
+      for (int v = 0; v < V; ++v) part += dot4(g[v], sub4(xr[v], ag[v]));
+      const float dz = group_sum<LPN>(part) * b * (1.f - b);
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const int f = v * LPN + lig;
+        const float4 w1 = ldg4(w_beta + 4 * f), w2 = ldg4(w_beta + DIM + 4 * f), w3 = ldg4(w_beta + 2 * DIM + 4 * f);
+        dag[v] = fma4(dz, add4(w1, w3), scale4(1.f - b, g[v]));
+        const float4 dxr = fma4(dz, sub4(w2, w3), scale4(b, g[v]));
+        if (valid) {
+          st4(d_qkvs + nrow * 4 * DIM + 3 * DIM + 4 * f, dxr);
+          dw1[v] = fma4(dz, ag[v], dw1[v]);
+          dw2[v] = fma4(dz, xr[v], dw2[v]);
+          dw3[v] = fma4(dz, sub4(ag[v], xr[v]), dw3[v]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        dag[v] = g[v];
+        if (valid) st4(d_qkvs + nrow * 4 * DIM + 3 * DIM + 4 * (v * LPN + lig), g[v]);
+      }
+    }
+    float delta[V], mh[V], il[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      delta[v] = dot4(dag[v], ag[v]);
+      const int h = head_of<DIM, HEAD_DIM>(v, lig);
+      mh[v] = m_in[nrow * HEADS + h];
+      il[v] = invl_in[nrow * HEADS + h];
+      if (valid) st4(d_agg_out + nrow * DIM + 4 * (v * LPN + lig), dag[v]);
+    }
+    head_reduce<DIM, HEAD_DIM>(delta);
+
+    const int begin = valid ? rowptr[nrow] : 0;
+    const int deg = valid ? rowptr[nrow + 1] - begin : 0;
+    int deg_max = deg;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) deg_max = max(deg_max, __shfl_xor_sync(0xffffffffu, deg_max, off));
+    float4 dq[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) dq[v] = zero4();
+
+    for (int e0 = 0; e0 < deg_max; e0 += kEdgeUnroll) {
+      float4 kr[kEdgeUnroll][V], vr[kEdgeUnroll][V];
+      int pos[kEdgeUnroll];
+#pragma unroll
+      for (int u = 0; u < kEdgeUnroll; ++u) {
+        const bool on = e0 + u < deg;
+        pos[u] = on ? begin + e0 + u : -1;
+        const int64_t j = on ? col[pos[u]] : nrow;
+        const float* other = qkvs + j * 4 * DIM;
+        load_row<DIM>(other + DIM, lig, kr[u]);
+        load_row<DIM>(other + 2 * DIM, lig, vr[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < kEdgeUnroll; ++u) {
+        float a[V], da[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) { a[v] = dot4(q[v], kr[u][v]); da[v] = dot4(dag[v], vr[u][v]); }
+        head_reduce<DIM, HEAD_DIM>(a);
+        head_reduce<DIM, HEAD_DIM>(da);
+        if (pos[u] >= 0) {
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            const float alpha = expf(a[v] * scale - mh[v]) * il[v];
+            float mask = 1.f;
+            const int h = head_of<DIM, HEAD_DIM>(v, lig);
+            if (alpha_mask != nullptr) mask = alpha_mask[(int64_t)eperm[pos[u]] * HEADS + h];
+            const float dlogit = alpha * (da[v] * mask - delta[v]) * scale;
+            dq[v] = fma4(dlogit, kr[u][v], dq[v]);
+            if ((v * LPN + lig) % HEAD_F4 == 0) ecoef[(int64_t)pos[u] * HEADS + h] = make_float2(alpha * mask, dlogit);
+          }
+        }
+      }
+    }
+    if (valid) {
+#pragma unroll
+      for (int v = 0; v < V; ++v) st4(d_qkvs + nrow * 4 * DIM + 4 * (v * LPN + lig), dq[v]);
+    }
+  }
+
+  if (wbeta_partial != nullptr) {
+    // fixed-order reduction of the per-group partials of this CTA
+    extern __shared__ float dyn[];  // [(kThreads/32)*GROUPS][3*DIM]
+    const int group_in_cta = warp_in_cta * G::GROUPS + lane / LPN;
+    float* mine = dyn + (size_t)group_in_cta * 3 * DIM;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const int f = v * LPN + lig;
+      st4(mine + 4 * f, dw1[v]);
+      st4(mine + DIM + 4 * f, dw2[v]);
+      st4(mine + 2 * DIM + 4 * f, dw3[v]);
+    }
+    __syncthreads();
+    constexpr int NG = (kThreads / 32) * G::GROUPS;
+    for (int i = threadIdx.x; i < 3 * DIM; i += kThreads) {
+      float s = 0.f;
+      for (int gidx = 0; gidx < NG; ++gidx) s += dyn[(size_t)gidx * 3 * DIM + i];
+      wbeta_partial[(int64_t)blockIdx.x * 3 * DIM + i] = s;
+    }
+  }
+}
+
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, int parts, int width,
+                                       float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= width) return;
+  float s = 0.f;
+  for (int p = 0; p < parts; ++p) s += partial[(int64_t)p * width + i];
+  out[i] = s;
+}
+
+// ------------------------------------------------------------------ backward, source pass
+// Per source j over its out-edges (CSC): d_key_j += scale*d_logit_e * q_i, d_value_j +=
+// alpha_e*mask_e * d_agg_i.  One owner group per row, ascending CSC order: deterministic.
+template <int DIM, int HEAD_DIM>
+__global__ void __launch_bounds__(kThreads)
+tconv_bwd_src_kernel(const float* __restrict__ qkvs, int64_t num_nodes, const int32_t* __restrict__ colptr,
+                     const int32_t* __restrict__ row, const int32_t* __restrict__ cpos,
+                     const float* __restrict__ d_agg, const float2* __restrict__ ecoef,
+                     float* __restrict__ d_qkvs) {
+  using G = RowGeom<DIM>;
+  constexpr int V = G::V, LPN = G::LPN;
+  constexpr int HEADS = DIM / HEAD_DIM;
+  const int lane = threadIdx.x & 31;
+  const int lig = lane % LPN;
+  const int64_t node = ((blockIdx.x * (int64_t)kThreads + threadIdx.x) >> 5) * G::GROUPS + lane / LPN;
+  if (node >= num_nodes) return;
+  const int begin = colptr[node], end = colptr[node + 1];
+  float4 dk[V], dv[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) { dk[v] = zero4(); dv[v] = zero4(); }
+  for (int p0 = begin; p0 < end; p0 += kEdgeUnroll) {
+    float4 qr[kEdgeUnroll][V], gr[kEdgeUnroll][V];
+    float2 c[kEdgeUnroll][V];
+#pragma unroll
+    for (int u = 0; u < kEdgeUnroll; ++u) {
+      const bool on = p0 + u < end;
+      const int p = on ? p0 + u : begin;
+      const int64_t i = row[p];
+      const int64_t e = cpos[p];
+      load_row<DIM>(qkvs + i * 4 * DIM, lig, qr[u]);
+      load_row<DIM>(d_agg + i * DIM, lig, gr[u]);
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        c[u][v] = ecoef[e * HEADS + head_of<DIM, HEAD_DIM>(v, lig)];
+        if (!on) c[u][v] = make_float2(0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kEdgeUnroll; ++u) {
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        dk[v] = fma4(c[u][v].y, qr[u][v], dk[v]);
+        dv[v] = fma4(c[u][v].x, gr[u][v], dv[v]);
+      }
+    }
+  }
+  float* drow = d_qkvs + node * 4 * DIM;
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    st4(drow + DIM + 4 * (v * LPN + lig), dk[v]);
+    st4(drow + 2 * DIM + 4 * (v * LPN + lig), dv[v]);
+  }
+}
+
+int dst_pass_grid(int64_t num_nodes, int nodes_per_cta) { return grid_for(num_nodes, nodes_per_cta, 4); }
+
+}  // namespace
+}  // namespace etpgt
+
+using namespace etpgt;
+
+extern "C" int etpgt_tconv_fwd(const float* qkvs, int64_t num_nodes, int dim, int heads,
+                               const int32_t* rowptr, const int32_t* col, const int32_t* eperm,
+                               int64_t num_edges, const float* w_beta, const float* alpha_mask, float* out,
+                               float* agg, float* beta, float* m, float* inv_l, etpgt_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ETPGT_REQUIRE(num_nodes >= 0 && num_edges >= 0, "tconv_fwd: negative size");
+  ETPGT_REQUIRE(qkvs && rowptr && out && agg && m && inv_l, "tconv_fwd: null pointer");
+  ETPGT_REQUIRE(num_edges == 0 || (col && eperm), "tconv_fwd: null edge arrays");
+  ETPGT_REQUIRE(w_beta == nullptr || beta != nullptr, "tconv_fwd: beta output required with w_beta");
+  if (num_nodes == 0) return ETPGT_OK;
+#define CALL(D, C)                                                                               \
+  {                                                                                              \
+    const int64_t npc = (kThreads / 32) * RowGeom<D>::GROUPS;                                    \
+    const int64_t grid = (num_nodes + npc - 1) / npc;                                            \
+    tconv_fwd_kernel<D, C><<<(unsigned)grid, kThreads, 0, stream>>>(qkvs, num_nodes, rowptr, col, eperm, w_beta, \
+                                                                   alpha_mask, out, agg, beta, m, inv_l); \
+  }
+  ETPGT_DISPATCH_DIM_HEADS(dim, heads, CALL)
+#undef CALL
+  ETPGT_CHECK_LAUNCH("tconv_fwd");
+  return ETPGT_OK;
+}
+
+extern "C" size_t etpgt_tconv_bwd_workspace_bytes(int64_t num_nodes, int64_t num_edges, int dim, int heads) {
+  return align_up((size_t)num_nodes * dim * sizeof(float)) +
+         align_up((size_t)(num_edges > 0 ? num_edges : 1) * heads * sizeof(float2)) +
+         align_up((size_t)kNumSMs * 4 * 3 * dim * sizeof(float)) + 256;
+}
+
+extern "C" int etpgt_tconv_bwd(const float* qkvs, const float* d_out, int64_t num_nodes, int dim, int heads,
+                               const int32_t* rowptr, const int32_t* col, const int32_t* eperm,
+                               const int32_t* colptr, const int32_t* row, const int32_t* cpos,
+                               int64_t num_edges, const float* w_beta, const float* alpha_mask,
+                               const float* agg, const float* beta, const float* m, const float* inv_l,
+                               float* d_qkvs, float* d_w_beta, void* ws, size_t ws_bytes,
+                               etpgt_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ETPGT_REQUIRE(num_nodes >= 0 && num_edges >= 0, "tconv_bwd: negative size");
+  ETPGT_REQUIRE(qkvs && d_out && rowptr && colptr && agg && m && inv_l && d_qkvs, "tconv_bwd: null pointer");
+  ETPGT_REQUIRE(w_beta == nullptr || (beta && d_w_beta), "tconv_bwd: beta / d_w_beta required with w_beta");
+  if (ws_bytes < etpgt_tconv_bwd_workspace_bytes(num_nodes, num_edges, dim, heads)) {
+    set_error("tconv_bwd: workspace %zu < %zu", ws_bytes,
+              etpgt_tconv_bwd_workspace_bytes(num_nodes, num_edges, dim, heads));
+    return ETPGT_EWORKSPACE;
+  }
+  if (num_nodes == 0) return ETPGT_OK;
+  Workspace w(ws, ws_bytes);
+  float* d_agg = w.take<float>((size_t)num_nodes * dim);
+  float2* ecoef = w.take<float2>((size_t)(num_edges > 0 ? num_edges : 1) * heads);
+  float* partial = w.take<float>((size_t)kNumSMs * 4 * 3 * dim);
+  int grid_a = 1;
+#define CALL(D, C)                                                                                   \
+  {                                                                                                  \
+    const int npc = (kThreads / 32) * RowGeom<D>::GROUPS;                                            \
+    grid_a = dst_pass_grid(num_nodes, npc);                                                          \
+    const size_t smem = w_beta ? (size_t)npc * 3 * D * sizeof(float) : 0;                            \
+    if (smem > 48 * 1024)                                                                            \
+      cudaFuncSetAttribute(tconv_bwd_dst_kernel<D, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    tconv_bwd_dst_kernel<D, C><<<grid_a, kThreads, smem, stream>>>(                                  \
+        qkvs, d_out, num_nodes, rowptr, col, eperm, w_beta, alpha_mask, agg, beta, m, inv_l, d_qkvs, d_agg, \
+        ecoef, w_beta ? partial : nullptr);                                                          \
+  }
+  ETPGT_DISPATCH_DIM_HEADS(dim, heads, CALL)
+#undef CALL
+  ETPGT_CHECK_LAUNCH("tconv_bwd_dst");
+  if (w_beta != nullptr) {
+    reduce_partials_kernel<<<(3 * dim + 255) / 256, 256, 0, stream>>>(partial, grid_a, 3 * dim, d_w_beta);
+    ETPGT_CHECK_LAUNCH("tconv wbeta reduce");
+  }
+#define CALL(D, C)                                                                                  \
+  {                                                                                                 \
+    const int64_t npc = (kThreads / 32) * RowGeom<D>::GROUPS;                                       \
+    const int64_t grid = (num_nodes + npc - 1) / npc;                                               \
+    tconv_bwd_src_kernel<D, C><<<(unsigned)grid, kThreads, 0, stream>>>(qkvs, num_nodes, colptr, row, cpos, d_agg, \
+                                                                       ecoef, d_qkvs);              \
+  }
+  ETPGT_DISPATCH_DIM_HEADS(dim, heads, CALL)
+#undef CALL
+  ETPGT_CHECK_LAUNCH("tconv_bwd_src");
+  return ETPGT_OK;
+}

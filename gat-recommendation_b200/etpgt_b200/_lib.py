@@ -1,0 +1,126 @@
+"""ctypes binding of libetpgt_b200.so (the C ABI declared in include/etpgt_b200.h).
+
+The library is the product: there is no Python / CPU fallback.  If the shared object is missing
+or a call is made with non-CUDA tensors this module raises immediately.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_double, c_float, c_int, c_int64, c_size_t, c_void_p
+from pathlib import Path
+
+import torch
+
+_LIB_PATH = Path(__file__).resolve().parent / "libetpgt_b200.so"
+
+P, I, L, F, D, Z = c_void_p, c_int, c_int64, c_float, c_double, c_size_t
+
+# name -> (restype, argtypes); mirrors include/etpgt_b200.h one to one
+_PROTOTYPES = {
+    "etpgt_version": (I, []),
+    "etpgt_last_error": (ctypes.c_char_p, []),
+    "etpgt_launch_count": (L, []),
+    "etpgt_reset_launch_count": (None, []),
+    "etpgt_csr_workspace_bytes": (Z, [L, L]),
+    "etpgt_csr_from_coo": (I, [P, P, L, L, P, P, P, P, P, P, P, Z, P]),
+    "etpgt_segment_ptr": (I, [P, L, L, P, P]),
+    "etpgt_embed_pe_fwd": (I, [P, L, P, L, P, I, P, P, I, I, P, P]),
+    "etpgt_embed_pe_bwd_workspace_bytes": (Z, [L, I, I]),
+    "etpgt_embed_pe_bwd": (I, [P, L, P, L, P, I, I, I, L, P, P, P, P, Z, P]),
+    "etpgt_tconv_fwd": (I, [P, L, I, I, P, P, P, L, P, P, P, P, P, P, P, P]),
+    "etpgt_tconv_bwd_workspace_bytes": (Z, [L, L, I, I]),
+    "etpgt_tconv_bwd": (I, [P, P, L, I, I, P, P, P, P, P, P, L, P, P, P, P, P, P, P, P, P, Z, P]),
+    "etpgt_bn_workspace_bytes": (Z, [L, I]),
+    "etpgt_bn_stats": (I, [P, L, I, P, P, Z, P]),
+    "etpgt_bn_finalize": (I, [P, D, I, F, F, P, P, P, P, P]),
+    "etpgt_bn_from_running": (I, [P, P, I, F, P, P, P]),
+    "etpgt_bn_apply": (I, [P, L, I, P, P, P, P, P, I, P, P]),
+    "etpgt_bn_bwd_stats": (I, [P, P, P, L, I, P, P, I, P, P, Z, P]),
+    "etpgt_bn_bwd_apply": (I, [P, P, P, L, I, P, P, P, I, I, P, D, P, P, P, P, P]),
+    "etpgt_readout_fwd": (I, [P, P, L, I, I, P, P, P, P]),
+    "etpgt_readout_bwd": (I, [P, P, P, P, L, L, I, I, P, P, P, P]),
+    "etpgt_sampled_loss_workspace_bytes": (Z, [L, I, I]),
+    "etpgt_sampled_loss_fwd": (I, [P, P, P, P, L, I, I, I, F, F, D, P, P, P, Z, P]),
+    "etpgt_sampled_loss_bwd": (I, [P, P, P, P, L, I, I, I, F, F, D, P, P, L, L, P, P, P, Z, P]),
+    "etpgt_score_topk_workspace_bytes": (Z, [L, L, I, I]),
+    "etpgt_score_topk_f32": (I, [P, P, L, L, I, I, L, P, P, P, Z, P]),
+    "etpgt_topk_merge": (I, [P, P, L, I, I, P, P, P]),
+    "etpgt_topk_metrics": (I, [P, P, L, I, I, P, P]),
+    "etpgt_scatter_rows_workspace_bytes": (Z, [L]),
+    "etpgt_scatter_rows": (I, [P, P, P, L, I, I, L, L, P, P, Z, P]),
+}
+
+_lib = None
+
+
+def exported_symbols() -> list[str]:
+    return sorted(_PROTOTYPES)
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def load():
+    """Loads the shared library once and installs the prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise ImportError(
+            f"{_LIB_PATH} is missing: build it with `python gat-recommendation_b200/build.py` "
+            "(etpgt_b200 has no CPU or PyTorch fallback)"
+        )
+    lib = ctypes.CDLL(str(_LIB_PATH))
+    for name, (restype, argtypes) in _PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError here = header/library mismatch
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().etpgt_last_error().decode()
+
+
+def ptr(t: torch.Tensor | None):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("etpgt_b200 runs on CUDA tensors only (no CPU fallback); got a CPU tensor")
+    if not t.is_contiguous():
+        raise RuntimeError("etpgt_b200 kernels need contiguous tensors")
+    return c_void_p(t.data_ptr())
+
+
+def stream() -> c_void_p:
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def workspace(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def call(name: str, *args):
+    """Calls an int-returning entry point and raises with the library's message on failure."""
+    rc = getattr(load(), name)(*args)
+    if rc != 0:
+        msg = last_error()
+        if "Unknown" in msg:  # mirrors the reference's ValueError for unknown readout / loss kinds
+            raise ValueError(msg)
+        raise RuntimeError(f"{name} failed ({rc}): {msg}")
+
+
+def size(name: str, *args) -> int:
+    return int(getattr(load(), name)(*args))
+
+
+def launch_count() -> int:
+    return int(load().etpgt_launch_count())
+
+
+def reset_launch_count() -> None:
+    load().etpgt_reset_launch_count()

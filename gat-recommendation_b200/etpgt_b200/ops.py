@@ -1,0 +1,380 @@
+"""Host side of the hot path: graph index construction and the autograd Functions that hand
+raw device pointers + the current stream to the C-ABI kernels (include/etpgt_b200.h).
+
+PyTorch is plumbing here (device memory, streams, autograd bookkeeping); all arithmetic on the
+path runs in libetpgt_b200.so, except the dense node projections which are library GEMMs.
+"""
+
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import call, ptr, size, stream, workspace
+
+READOUT_MODES = {"mean": 0, "max": 1, "last": 2, "attention": 3}
+LOSS_MODES = {"bpr": 0, "listwise": 1, "dual": 2}
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"etpgt_b200: {what} must be a CUDA tensor (the B200 path has no CPU fallback)")
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    return t.contiguous() if t.dtype == torch.float32 else t.float().contiguous()
+
+
+def _i64(t: torch.Tensor) -> torch.Tensor:
+    return t.contiguous() if t.dtype == torch.int64 else t.long().contiguous()
+
+
+# ------------------------------------------------------------------------------ graph index
+
+
+class GraphIndex:
+    """Destination-sorted CSR + source-sorted CSC of one batched graph, built once per batch on
+    the device and shared by every conv layer (forward and backward)."""
+
+    __slots__ = ("num_nodes", "num_edges", "rowptr", "col", "eperm", "colptr", "row", "cpos")
+
+    def __init__(self, edge_index: torch.Tensor, num_nodes: int):
+        _require_cuda(edge_index, "edge_index")
+        edge_index = _i64(edge_index)
+        dev = edge_index.device
+        e = int(edge_index.size(1))
+        self.num_nodes, self.num_edges = int(num_nodes), e
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.rowptr = torch.empty(num_nodes + 1, **i32)
+        self.colptr = torch.empty(num_nodes + 1, **i32)
+        self.col = torch.empty(e, **i32)
+        self.eperm = torch.empty(e, **i32)
+        self.row = torch.empty(e, **i32)
+        self.cpos = torch.empty(e, **i32)
+        nbytes = size("etpgt_csr_workspace_bytes", e, num_nodes)
+        ws = workspace(nbytes, dev)
+        call("etpgt_csr_from_coo", ptr(edge_index[0]), ptr(edge_index[1]), e, num_nodes,
+             ptr(self.rowptr), ptr(self.col), ptr(self.eperm), ptr(self.colptr), ptr(self.row), ptr(self.cpos),
+             ptr(ws), ws.numel(), stream())
+
+
+def graph_index_of(batch, edge_index: torch.Tensor, num_nodes: int) -> GraphIndex:
+    """Cached on the batch object so that L layers and the backward pass share one build."""
+    cached = getattr(batch, "_etpgt_index", None)
+    if cached is not None and cached[0] is edge_index and cached[1].num_nodes == num_nodes:
+        return cached[1]
+    index = GraphIndex(edge_index, num_nodes)
+    try:
+        object.__setattr__(batch, "_etpgt_index", (edge_index, index))
+    except Exception:  # exotic batch containers: just rebuild next time
+        pass
+    return index
+
+
+def segment_ptr(batch_vec: torch.Tensor, num_sessions: int) -> torch.Tensor:
+    _require_cuda(batch_vec, "batch")
+    batch_vec = _i64(batch_vec)
+    out = torch.empty(num_sessions + 1, dtype=torch.int32, device=batch_vec.device)
+    call("etpgt_segment_ptr", ptr(batch_vec), batch_vec.numel(), num_sessions, ptr(out), stream())
+    return out
+
+
+# ------------------------------------------------------------------------------ embedding + PE
+
+
+class EmbedPE(torch.autograd.Function):
+    """x0 = table[ids] (+ pe @ w_pe^T + b_pe)   — etpgt/model/graph_transformer.py:140-152."""
+
+    @staticmethod
+    def forward(ctx, ids, table, pe, pe_per_node, w_pe, b_pe, padding_idx):
+        _require_cuda(table, "item_embedding.weight")
+        ids = _i64(ids)
+        table_c = _f32(table)
+        n, dim = ids.numel(), table_c.size(1)
+        out = torch.empty(n, dim, dtype=torch.float32, device=table_c.device)
+        k_pe = 0
+        if pe is not None:
+            pe, w_pe_c, b_pe_c = _f32(pe), _f32(w_pe), _f32(b_pe)
+            k_pe = pe.size(1)
+        else:
+            w_pe_c = b_pe_c = None
+        call("etpgt_embed_pe_fwd", ptr(ids), n, ptr(table_c), table_c.size(0), ptr(pe), int(bool(pe_per_node)),
+             ptr(w_pe_c), ptr(b_pe_c), k_pe, dim, ptr(out), stream())
+        ctx.save_for_backward(ids, pe)
+        ctx.meta = (table_c.size(0), dim, k_pe, int(bool(pe_per_node)), -1 if padding_idx is None else int(padding_idx))
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        ids, pe = ctx.saved_tensors
+        num_items, dim, k_pe, per_node, padding_idx = ctx.meta
+        d_out = _f32(d_out)
+        dev = d_out.device
+        n = ids.numel()
+        d_table = torch.zeros(num_items, dim, dtype=torch.float32, device=dev) if ctx.needs_input_grad[1] else None
+        d_w = d_b = None
+        if pe is not None:
+            d_w = torch.empty(dim, k_pe, dtype=torch.float32, device=dev)
+            d_b = torch.empty(dim, dtype=torch.float32, device=dev)
+        ws = workspace(size("etpgt_embed_pe_bwd_workspace_bytes", n, dim, max(k_pe, 1)), dev)
+        call("etpgt_embed_pe_bwd", ptr(ids), n, ptr(d_out), num_items, ptr(pe), per_node, k_pe, dim, padding_idx,
+             ptr(d_table), ptr(d_w), ptr(d_b), ptr(ws), ws.numel(), stream())
+        return None, d_table, None, None, d_w, d_b, None
+
+
+# ------------------------------------------------------------------------------ TransformerConv
+
+
+class TransformerConvFn(torch.autograd.Function):
+    """Fused attention + aggregation + gate over the CSR (etpgt_tconv_fwd / _bwd)."""
+
+    @staticmethod
+    def forward(ctx, qkvs, w_beta, alpha_mask, index: GraphIndex, heads: int):
+        _require_cuda(qkvs, "node features")
+        qkvs = _f32(qkvs)
+        n, dim = qkvs.size(0), qkvs.size(1) // 4
+        dev = qkvs.device
+        w_beta_c = _f32(w_beta).reshape(-1) if w_beta is not None else None
+        mask_c = _f32(alpha_mask) if alpha_mask is not None else None
+        f32 = dict(dtype=torch.float32, device=dev)
+        out = torch.empty(n, dim, **f32)
+        agg = torch.empty(n, dim, **f32)
+        beta = torch.empty(n, **f32)
+        m = torch.empty(n, heads, **f32)
+        inv_l = torch.empty(n, heads, **f32)
+        call("etpgt_tconv_fwd", ptr(qkvs), n, dim, heads, ptr(index.rowptr), ptr(index.col), ptr(index.eperm),
+             index.num_edges, ptr(w_beta_c), ptr(mask_c), ptr(out), ptr(agg), ptr(beta), ptr(m), ptr(inv_l), stream())
+        ctx.save_for_backward(qkvs, w_beta_c, mask_c, agg, beta, m, inv_l)
+        ctx.index, ctx.heads = index, heads
+        ctx.w_beta_shape = None if w_beta is None else tuple(w_beta.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        qkvs, w_beta, mask, agg, beta, m, inv_l = ctx.saved_tensors
+        index, heads = ctx.index, ctx.heads
+        d_out = _f32(d_out)
+        n, dim = qkvs.size(0), qkvs.size(1) // 4
+        dev = qkvs.device
+        d_qkvs = torch.empty_like(qkvs)
+        d_w_beta = torch.empty(3 * dim, dtype=torch.float32, device=dev) if w_beta is not None else None
+        ws = workspace(size("etpgt_tconv_bwd_workspace_bytes", n, index.num_edges, dim, heads), dev)
+        call("etpgt_tconv_bwd", ptr(qkvs), ptr(d_out), n, dim, heads, ptr(index.rowptr), ptr(index.col),
+             ptr(index.eperm), ptr(index.colptr), ptr(index.row), ptr(index.cpos), index.num_edges, ptr(w_beta),
+             ptr(mask), ptr(agg), ptr(beta), ptr(m), ptr(inv_l), ptr(d_qkvs), ptr(d_w_beta), ptr(ws), ws.numel(),
+             stream())
+        if d_w_beta is not None:
+            d_w_beta = d_w_beta.view(ctx.w_beta_shape)
+        return d_qkvs, d_w_beta, None, None, None
+
+
+# ------------------------------------------------------------------------------ BatchNorm (+res, +relu)
+
+
+def _dist_ready(group) -> bool:
+    return group is not False and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+
+class BatchNormRows(torch.autograd.Function):
+    """BatchNorm1d over all node rows of the (global) batch + residual (+ ReLU).
+    etpgt/model/graph_transformer.py:175-176, gat.py:138-140, graphsage.py:76-77.  Under data
+    parallelism the 2*dim partial sums are all-reduced so statistics cover every rank's nodes."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, bias, residual, running_mean, running_var, training, momentum, eps, relu, group):
+        _require_cuda(x, "node features")
+        x = _f32(x)
+        n, dim = x.shape
+        dev = x.device
+        gamma_c, bias_c = _f32(gamma), _f32(bias)
+        res_c = _f32(residual) if residual is not None else None
+        mean = torch.empty(dim, dtype=torch.float32, device=dev)
+        invstd = torch.empty(dim, dtype=torch.float32, device=dev)
+        count = float(n)
+        if training:
+            sums = torch.empty(2 * dim, dtype=torch.float64, device=dev)
+            ws = workspace(size("etpgt_bn_workspace_bytes", n, dim), dev)
+            call("etpgt_bn_stats", ptr(x), n, dim, ptr(sums), ptr(ws), ws.numel(), stream())
+            if _dist_ready(group):
+                packed = torch.cat([sums, torch.tensor([count], dtype=torch.float64, device=dev)])
+                dist.all_reduce(packed, group=group or None)
+                sums, count = packed[:-1].contiguous(), float(packed[-1].item())
+            if count < 2:
+                raise ValueError("Expected more than 1 value per channel when training")
+            call("etpgt_bn_finalize", ptr(sums), count, dim, float(eps), float(momentum), ptr(mean), ptr(invstd),
+                 ptr(running_mean), ptr(running_var), stream())
+        else:
+            call("etpgt_bn_from_running", ptr(running_mean), ptr(running_var), dim, float(eps), ptr(mean),
+                 ptr(invstd), stream())
+        y = torch.empty_like(x)
+        call("etpgt_bn_apply", ptr(x), n, dim, ptr(mean), ptr(invstd), ptr(gamma_c), ptr(bias_c), ptr(res_c),
+             int(bool(relu)), ptr(y), stream())
+        ctx.save_for_backward(x, y if relu else None, mean, invstd, gamma_c)
+        ctx.meta = (bool(training), bool(relu), count, residual is not None, group)
+        return y
+
+    @staticmethod
+    def backward(ctx, d_y):
+        x, y, mean, invstd, gamma = ctx.saved_tensors
+        training, relu, count, has_res, group = ctx.meta
+        d_y = _f32(d_y)
+        n, dim = x.shape
+        dev = x.device
+        local = torch.empty(2 * dim, dtype=torch.float64, device=dev)
+        ws = workspace(size("etpgt_bn_workspace_bytes", n, dim), dev)
+        call("etpgt_bn_bwd_stats", ptr(x), ptr(y), ptr(d_y), n, dim, ptr(mean), ptr(invstd), int(relu), ptr(local),
+             ptr(ws), ws.numel(), stream())
+        sums = local
+        if training and _dist_ready(group):
+            sums = local.clone()
+            dist.all_reduce(sums, group=group or None)
+        d_x = torch.empty_like(x)
+        d_gamma = torch.empty(dim, dtype=torch.float32, device=dev)
+        d_bias = torch.empty(dim, dtype=torch.float32, device=dev)
+        call("etpgt_bn_bwd_apply", ptr(x), ptr(y), ptr(d_y), n, dim, ptr(mean), ptr(invstd), ptr(gamma), int(relu),
+             int(training), ptr(sums), count, ptr(local), ptr(d_x), ptr(d_gamma), ptr(d_bias), stream())
+        d_res = None
+        if has_res:
+            d_res = d_y if not relu else d_y * (y > 0)
+        return d_x, d_gamma, d_bias, d_res, None, None, None, None, None, None, None
+
+
+# ------------------------------------------------------------------------------ readout
+
+
+class SegmentReadout(torch.autograd.Function):
+    """Session readout over contiguous node ranges — etpgt/model/base.py:136-193."""
+
+    @staticmethod
+    def forward(ctx, x, scores, seg_ptr, mode: int):
+        _require_cuda(x, "node embeddings")
+        x = _f32(x)
+        n, dim = x.shape
+        s = seg_ptr.numel() - 1
+        dev = x.device
+        out = torch.empty(s, dim, dtype=torch.float32, device=dev)
+        aux = None
+        scores_c = None
+        if mode == READOUT_MODES["max"]:
+            aux = torch.empty(s, dim, dtype=torch.int32, device=dev)
+        elif mode == READOUT_MODES["attention"]:
+            aux = torch.empty(n, dtype=torch.float32, device=dev)
+            scores_c = _f32(scores).reshape(-1)
+        call("etpgt_readout_fwd", ptr(x), ptr(seg_ptr), s, dim, mode, ptr(scores_c), ptr(out), ptr(aux), stream())
+        ctx.save_for_backward(x, out, seg_ptr, aux)
+        ctx.mode = mode
+        ctx.scores_shape = None if scores is None else tuple(scores.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        x, out, seg_ptr, aux = ctx.saved_tensors
+        mode = ctx.mode
+        d_out = _f32(d_out)
+        n, dim = x.shape
+        d_x = torch.empty_like(x)
+        d_scores = torch.empty(n, dtype=torch.float32, device=x.device) if mode == READOUT_MODES["attention"] else None
+        call("etpgt_readout_bwd", ptr(x), ptr(out), ptr(d_out), ptr(seg_ptr), n, seg_ptr.numel() - 1, dim, mode,
+             ptr(aux), ptr(d_x), ptr(d_scores), stream())
+        if d_scores is not None:
+            d_scores = d_scores.view(ctx.scores_shape)
+        return d_x, d_scores, None, None
+
+
+# ------------------------------------------------------------------------------ sampled losses
+
+
+class SampledLoss(torch.autograd.Function):
+    """BPR / listwise / dual loss over (target, negatives) — etpgt/train/losses.py:20-164.
+    Returns a device tensor [3] = (total, listwise, bpr); only `[0]` carries gradient."""
+
+    @staticmethod
+    def forward(ctx, sess, table, targets, negatives, mode, alpha, temperature, total_sessions, padding_idx):
+        _require_cuda(sess, "session embeddings")
+        sess_c, table_c = _f32(sess), _f32(table)
+        targets, negatives = _i64(targets), _i64(negatives)
+        b, dim = sess_c.shape
+        if negatives.dim() != 2 or negatives.size(0) != b:
+            raise RuntimeError(f"negative_items must be [batch, num_negatives]; got {tuple(negatives.shape)}")
+        num_neg = negatives.size(1)
+        dev = sess_c.device
+        total = float(total_sessions if total_sessions else b)
+        scores = torch.empty(b, num_neg + 1, dtype=torch.float32, device=dev)
+        losses = torch.empty(3, dtype=torch.float32, device=dev)
+        ws = workspace(size("etpgt_sampled_loss_workspace_bytes", b, num_neg, dim), dev)
+        call("etpgt_sampled_loss_fwd", ptr(sess_c), ptr(table_c), ptr(targets), ptr(negatives), b, num_neg, dim, mode,
+             float(alpha), float(temperature), total, ptr(scores), ptr(losses), ptr(ws), ws.numel(), stream())
+        ctx.save_for_backward(sess_c, table_c, targets, negatives, scores)
+        ctx.meta = (mode, float(alpha), float(temperature), total, -1 if padding_idx is None else int(padding_idx))
+        return losses
+
+    @staticmethod
+    def backward(ctx, d_losses):
+        sess, table, targets, negatives, scores = ctx.saved_tensors
+        mode, alpha, temperature, total, padding_idx = ctx.meta
+        b, dim = sess.shape
+        num_neg = negatives.size(1)
+        dev = sess.device
+        d_loss = _f32(d_losses)[0:1].contiguous()
+        d_sess = torch.empty_like(sess)
+        d_table = torch.zeros_like(table) if ctx.needs_input_grad[1] else None
+        ws = workspace(size("etpgt_sampled_loss_workspace_bytes", b, num_neg, dim), dev)
+        call("etpgt_sampled_loss_bwd", ptr(sess), ptr(table), ptr(targets), ptr(negatives), b, num_neg, dim, mode,
+             alpha, temperature, total, ptr(scores), ptr(d_loss), table.size(0), padding_idx, ptr(d_sess),
+             ptr(d_table), ptr(ws), ws.numel(), stream())
+        return d_sess, d_table, None, None, None, None, None, None, None
+
+
+def sampled_loss(sess, item_embeddings, targets, negatives, kind: str, alpha=0.7, temperature=1.0,
+                 total_sessions=None) -> torch.Tensor:
+    """`item_embeddings` is the nn.Embedding the reference passes around (trainer.py:103)."""
+    weight = item_embeddings.weight if hasattr(item_embeddings, "weight") else item_embeddings
+    padding_idx = getattr(item_embeddings, "padding_idx", None)
+    return SampledLoss.apply(sess, weight, targets, negatives, LOSS_MODES[kind], alpha, temperature,
+                             total_sessions, padding_idx)
+
+
+# ------------------------------------------------------------------------------ scoring / top-k
+
+
+@torch.no_grad()
+def score_topk(sess: torch.Tensor, table: torch.Tensor, k: int, id_base: int = 0):
+    """Top-k item ids by dot product, ties to the lower id — etpgt/model/base.py:59-78."""
+    _require_cuda(sess, "session embeddings")
+    sess_c, table_c = _f32(sess.detach()), _f32(table.detach())
+    b, dim = sess_c.shape
+    items = table_c.size(0)
+    dev = sess_c.device
+    top_val = torch.empty(b, k, dtype=torch.float32, device=dev)
+    top_idx = torch.empty(b, k, dtype=torch.int64, device=dev)
+    ws = workspace(size("etpgt_score_topk_workspace_bytes", b, items, dim, k), dev)
+    call("etpgt_score_topk_f32", ptr(sess_c), ptr(table_c), b, items, dim, k, id_base, ptr(top_val), ptr(top_idx),
+         ptr(ws), ws.numel(), stream())
+    return top_val, top_idx
+
+
+@torch.no_grad()
+def topk_merge(cand_val: torch.Tensor, cand_idx: torch.Tensor, k: int):
+    """Exact merge of per-shard candidate lists [B, parts*k] (score desc, id asc)."""
+    b = cand_val.size(0)
+    parts = cand_val.size(1) // k
+    cand_val, cand_idx = _f32(cand_val), _i64(cand_idx)
+    top_val = torch.empty(b, k, dtype=torch.float32, device=cand_val.device)
+    top_idx = torch.empty(b, k, dtype=torch.int64, device=cand_val.device)
+    call("etpgt_topk_merge", ptr(cand_val), ptr(cand_idx), b, parts, k, ptr(top_val), ptr(top_idx), stream())
+    return top_val, top_idx
+
+
+@torch.no_grad()
+def topk_metrics(top_idx: torch.Tensor, targets: torch.Tensor, k: int, acc: torch.Tensor | None = None):
+    """Adds (#hits@k, sum of 1/log2(pos+2)) into `acc` (double[2]) without leaving the device."""
+    top_idx, targets = _i64(top_idx), _i64(targets)
+    if acc is None:
+        acc = torch.zeros(2, dtype=torch.float64, device=top_idx.device)
+    call("etpgt_topk_metrics", ptr(top_idx), ptr(targets), top_idx.size(0), top_idx.size(1), k, ptr(acc), stream())
+    return acc
+
+
+def launch_count() -> int:
+    return _lib.launch_count()

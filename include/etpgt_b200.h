@@ -1,0 +1,194 @@
+/* etpgt_b200 — C ABI of the B200-native hot path of the `etpgt` session recommender.
+ *
+ * The reference (Axionis47/GAT-Recommendation) is pure Python and has no FFI; its drop-in
+ * boundary is the Python module API of etpgt/model, etpgt/train/losses.py and
+ * etpgt/utils/metrics.py.  These are the entry points a binding for that
+ * path uses; each one names the reference code it replaces.  INTEGRATION.md shows the
+ * ctypes stub.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless it says "host";
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), never
+ *     allocates and never synchronises; scratch comes from `ws` sized by *_workspace_bytes;
+ *   - returns 0, or a negative ETPGT_E* code with a thread-local message in
+ *     etpgt_last_error(); nothing is launched when an argument check fails;
+ *   - API-side indices are int64 (the reference's dtype); internal structures are int32;
+ *   - feature matrices are fp32 row-major with D in {32,64,128,256};
+ *   - no global mutable state, re-entrant, no CPU fallback anywhere.
+ */
+#ifndef ETPGT_B200_H
+#define ETPGT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ETPGT_OK 0
+#define ETPGT_EINVAL (-1)   /* bad argument / unsupported shape */
+#define ETPGT_ECUDA (-2)    /* CUDA runtime error at launch */
+#define ETPGT_EWORKSPACE (-3) /* workspace too small */
+
+typedef void* etpgt_stream_t; /* cudaStream_t */
+
+int etpgt_version(void);
+const char* etpgt_last_error(void);
+/* number of kernel launches issued by this library from the calling thread since the last
+ * reset (bench.py's `gpu_launches`). */
+int64_t etpgt_launch_count(void);
+void etpgt_reset_launch_count(void);
+
+/* ---- index structures ------------------------------------------------------------------
+ * Destination-sorted CSR and source-sorted CSC of an edge list, both stable (ties keep the
+ * original edge order).  Replaces the COO scatter inside PyG's MessagePassing.propagate that
+ * etpgt/model/graph_transformer.py:174, gat.py:137 and graphsage.py:75 reach.
+ *   rowptr[N+1], col[E] (source of the p-th CSR edge), eperm[E] (its original index),
+ *   colptr[N+1], row[E] (destination of the p-th CSC edge), cpos[E] (its CSR position). */
+size_t etpgt_csr_workspace_bytes(int64_t num_edges, int64_t num_nodes);
+int etpgt_csr_from_coo(const int64_t* src, const int64_t* dst, int64_t num_edges, int64_t num_nodes,
+                       int32_t* rowptr, int32_t* col, int32_t* eperm,
+                       int32_t* colptr, int32_t* row, int32_t* cpos,
+                       void* ws, size_t ws_bytes, etpgt_stream_t stream);
+/* ptr[S+1] from a non-decreasing segment-id vector (PyG `batch`): etpgt/model/base.py:146-155. */
+int etpgt_segment_ptr(const int64_t* seg_ids, int64_t n, int64_t num_segments, int32_t* ptr,
+                      etpgt_stream_t stream);
+
+/* ---- a4: item embedding + Laplacian-PE projection -------------------------------------
+ * out[n] = table[ids[n]] (+ pe[pe_row(n)] @ w_pe^T + b_pe);  pe_row(n) = n when
+ * pe_per_node else ids[n].  etpgt/model/graph_transformer.py:140-152,
+ * etpgt/encodings/laplacian_pe.py:170-199.  pe == NULL skips the projection. */
+int etpgt_embed_pe_fwd(const int64_t* ids, int64_t n, const float* table, int64_t num_items,
+                       const float* pe, int pe_per_node, const float* w_pe, const float* b_pe,
+                       int k_pe, int dim, float* out, etpgt_stream_t stream);
+/* Deterministic backward: d_table (dense [num_items, dim], caller-zeroed, rows are ADDED),
+ * d_w_pe [dim,k_pe], d_b_pe [dim] (overwritten; NULL when pe == NULL).  Row padding_idx
+ * (etpgt/model/base.py:36; -1 = none) receives no gradient. */
+size_t etpgt_embed_pe_bwd_workspace_bytes(int64_t n, int dim, int k_pe);
+int etpgt_embed_pe_bwd(const int64_t* ids, int64_t n, const float* d_out, int64_t num_items,
+                       const float* pe, int pe_per_node, int k_pe, int dim, int64_t padding_idx,
+                       float* d_table, float* d_w_pe, float* d_b_pe,
+                       void* ws, size_t ws_bytes, etpgt_stream_t stream);
+
+/* ---- a5: fused TransformerConv ----------------------------------------------------------
+ * qkvs [N, 4*dim] = (query | key | value | skip) projections of x (one GEMM by the caller).
+ * Per destination i and head h: a_e = <q_i,k_j>/sqrt(C); alpha = exp(a_e-m_i)/(sum+1e-16);
+ * agg_i = sum alpha*mask_e*v_j; beta = sigmoid(w_beta . [agg, s, agg-s]); out = beta*s+(1-beta)*agg.
+ * PyG TransformerConv(concat=True, beta=True) as used at graph_transformer.py:73-98,174.
+ * alpha_mask [E, heads] in ORIGINAL edge order (dropout mask already scaled) or NULL.
+ * w_beta == NULL selects beta=False (out = agg + s).
+ * Saved for backward: agg [N,dim], beta [N], m [N,heads], inv_l [N,heads]. */
+int etpgt_tconv_fwd(const float* qkvs, int64_t num_nodes, int dim, int heads,
+                    const int32_t* rowptr, const int32_t* col, const int32_t* eperm, int64_t num_edges,
+                    const float* w_beta, const float* alpha_mask,
+                    float* out, float* agg, float* beta, float* m, float* inv_l,
+                    etpgt_stream_t stream);
+/* Backward, no atomics: a destination pass (d_query, d_skip, per-edge coefficients) then a
+ * source pass over the CSC (d_key, d_value).  d_qkvs [N,4*dim] is overwritten; d_w_beta [3*dim]
+ * overwritten (NULL when w_beta == NULL). */
+size_t etpgt_tconv_bwd_workspace_bytes(int64_t num_nodes, int64_t num_edges, int dim, int heads);
+int etpgt_tconv_bwd(const float* qkvs, const float* d_out, int64_t num_nodes, int dim, int heads,
+                    const int32_t* rowptr, const int32_t* col, const int32_t* eperm,
+                    const int32_t* colptr, const int32_t* row, const int32_t* cpos, int64_t num_edges,
+                    const float* w_beta, const float* alpha_mask,
+                    const float* agg, const float* beta, const float* m, const float* inv_l,
+                    float* d_qkvs, float* d_w_beta,
+                    void* ws, size_t ws_bytes, etpgt_stream_t stream);
+
+/* ---- a6: BatchNorm1d over node rows (+ residual, + ReLU) --------------------------------
+ * graph_transformer.py:175-176, gat.py:138-140, graphsage.py:76-77.
+ * stats: per-feature sums over this rank's rows, double precision: sums[0:dim] = sum x,
+ * sums[dim:2dim] = sum x^2.  Under data parallelism the caller all-reduces `sums` (and the
+ * row count) between stats and finalize so that the whole-batch semantics are kept. */
+size_t etpgt_bn_workspace_bytes(int64_t n, int dim);
+int etpgt_bn_stats(const float* x, int64_t n, int dim, double* sums,
+                   void* ws, size_t ws_bytes, etpgt_stream_t stream);
+/* mean/invstd [dim] from sums and the GLOBAL row count; running stats updated in place
+ * (momentum, unbiased variance) when running_mean != NULL. */
+int etpgt_bn_finalize(const double* sums, double count, int dim, float eps, float momentum,
+                      float* mean, float* invstd, float* running_mean, float* running_var,
+                      etpgt_stream_t stream);
+/* eval mode helper: mean/invstd from the running statistics. */
+int etpgt_bn_from_running(const float* running_mean, const float* running_var, int dim, float eps,
+                          float* mean, float* invstd, etpgt_stream_t stream);
+/* y = (x-mean)*invstd*gamma + bias (+ residual) (then ReLU when relu != 0). */
+int etpgt_bn_apply(const float* x, int64_t n, int dim, const float* mean, const float* invstd,
+                   const float* gamma, const float* bias, const float* residual, int relu,
+                   float* y, etpgt_stream_t stream);
+/* backward step 1: sums[0:dim] = sum g, sums[dim:2dim] = sum g*xhat with g = d_y (masked by
+ * y > 0 when relu).  All-reduced across ranks by the caller in training mode. */
+int etpgt_bn_bwd_stats(const float* x, const float* y, const float* d_y, int64_t n, int dim,
+                       const float* mean, const float* invstd, int relu, double* sums,
+                       void* ws, size_t ws_bytes, etpgt_stream_t stream);
+/* backward step 2: d_x; d_gamma/d_bias [dim] = LOCAL sums (pass the un-reduced sums as
+ * local_sums).  training != 0 uses the batch-statistics formula with the GLOBAL count. */
+int etpgt_bn_bwd_apply(const float* x, const float* y, const float* d_y, int64_t n, int dim,
+                       const float* mean, const float* invstd, const float* gamma, int relu,
+                       int training, const double* sums, double count, const double* local_sums,
+                       float* d_x, float* d_gamma, float* d_bias, etpgt_stream_t stream);
+
+/* ---- a7: session readout (segmented reduction) ------------------------------------------
+ * etpgt/model/base.py:136-193.  mode: 0 mean, 1 max, 2 last, 3 attention (softmax of the
+ * caller-computed per-node `scores` inside each session).  Sessions are the contiguous node
+ * ranges ptr[s]..ptr[s+1].  aux: argmax [S,dim] int32 for max, weights [N] float for attention. */
+#define ETPGT_READOUT_MEAN 0
+#define ETPGT_READOUT_MAX 1
+#define ETPGT_READOUT_LAST 2
+#define ETPGT_READOUT_ATTENTION 3
+int etpgt_readout_fwd(const float* x, const int32_t* ptr, int64_t num_sessions, int dim, int mode,
+                      const float* scores, float* out, void* aux, etpgt_stream_t stream);
+int etpgt_readout_bwd(const float* x, const float* out, const float* d_out, const int32_t* ptr,
+                      int64_t num_nodes, int64_t num_sessions, int dim, int mode, const void* aux,
+                      float* d_x, float* d_scores, etpgt_stream_t stream);
+
+/* ---- a8: sampled BPR / listwise / dual loss ---------------------------------------------
+ * etpgt/train/losses.py:20-164, etpgt/model/base.py:80-113.
+ * losses[3] = (alpha*listwise + (1-alpha)*bpr, listwise, bpr); mode 0 bpr (alpha ignored,
+ * total = bpr), 1 listwise (total = listwise), 2 dual.  The means divide by total_sessions
+ * (the GLOBAL batch under data parallelism).  scores [B, 1+num_neg] is saved for backward. */
+#define ETPGT_LOSS_BPR 0
+#define ETPGT_LOSS_LISTWISE 1
+#define ETPGT_LOSS_DUAL 2
+size_t etpgt_sampled_loss_workspace_bytes(int64_t batch, int num_neg, int dim);
+int etpgt_sampled_loss_fwd(const float* sess, const float* table, const int64_t* targets,
+                           const int64_t* negatives, int64_t batch, int num_neg, int dim,
+                           int mode, float alpha, float temperature, double total_sessions,
+                           float* scores, float* losses, void* ws, size_t ws_bytes,
+                           etpgt_stream_t stream);
+/* d_loss: device scalar (upstream gradient of losses[0]).  d_sess [B,dim] overwritten;
+ * d_table dense [num_items,dim], caller-zeroed, rows ADDED deterministically. */
+int etpgt_sampled_loss_bwd(const float* sess, const float* table, const int64_t* targets,
+                           const int64_t* negatives, int64_t batch, int num_neg, int dim,
+                           int mode, float alpha, float temperature, double total_sessions,
+                           const float* scores, const float* d_loss, int64_t num_items,
+                           int64_t padding_idx, float* d_sess, float* d_table, void* ws, size_t ws_bytes,
+                           etpgt_stream_t stream);
+
+/* ---- a9/a10: full-catalogue scoring with fused top-k and metrics ------------------------
+ * etpgt/model/base.py:59-78, etpgt/utils/metrics.py:6-66.  Scores are never materialised.
+ * Ties go to the lower item id.  id_base offsets the ids of an item-table shard. */
+size_t etpgt_score_topk_workspace_bytes(int64_t batch, int64_t num_items, int dim, int k);
+/* fp32 CUDA-core path (exact reference arithmetic, small batches). */
+int etpgt_score_topk_f32(const float* sess, const float* table, int64_t batch, int64_t num_items,
+                         int dim, int k, int64_t id_base, float* top_val, int64_t* top_idx,
+                         void* ws, size_t ws_bytes, etpgt_stream_t stream);
+/* exact merge of `parts` candidate lists per row ([B, parts*k] values + ids). */
+int etpgt_topk_merge(const float* cand_val, const int64_t* cand_idx, int64_t batch, int parts, int k,
+                     float* top_val, int64_t* top_idx, etpgt_stream_t stream);
+/* hits/ndcg accumulators: out[0] += #hits@k, out[1] += sum 1/log2(pos+2) (double[2], caller-zeroed). */
+int etpgt_topk_metrics(const int64_t* top_idx, const int64_t* targets, int64_t batch, int k_stride,
+                       int k, double* out, etpgt_stream_t stream);
+
+/* ---- generic helper shared by embedding / loss backward ---------------------------------
+ * d_table[key] += sum_{p: keys[p]==key} coef[p] * src[p / src_div]  in ascending p, one writer
+ * per row (deterministic).  coef may be NULL (=1); row skip_key (-1 = none) is left untouched. */
+size_t etpgt_scatter_rows_workspace_bytes(int64_t m);
+int etpgt_scatter_rows(const int64_t* keys, const float* coef, const float* src, int64_t m,
+                       int src_div, int dim, int64_t num_rows, int64_t skip_key, float* d_table,
+                       void* ws, size_t ws_bytes, etpgt_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ETPGT_B200_H */

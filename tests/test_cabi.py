@@ -1,0 +1,114 @@
+"""CPU tests of the drop-in boundary: the C-ABI library builds, loads, and exports every symbol
+that include/etpgt_b200.h declares; the ctypes prototypes cover exactly that set; the host
+package mirrors the reference's module API and state-dict keys.  No compute calls (no GPU)."""
+
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+HEADER = ROOT / "include" / "etpgt_b200.h"
+
+
+def declared_symbols():
+    text = re.sub(r"/\*.*?\*/", "", HEADER.read_text(), flags=re.S)
+    return sorted(set(re.findall(r"\b(etpgt_[a-z0-9_]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from etpgt_b200 import _lib
+
+    if not _lib.lib_path().exists():
+        import importlib.util
+
+        spec = importlib.util.spec_from_file_location("etpgt_build", ROOT / "gat-recommendation_b200" / "build.py")
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.build()
+    return _lib
+
+
+def test_library_exports_every_declared_symbol(lib):
+    handle = ctypes.CDLL(str(lib.lib_path()))
+    names = declared_symbols()
+    assert len(names) >= 30
+    for name in names:
+        assert hasattr(handle, name), f"{name} declared in the header but not exported"
+    assert sorted(lib.exported_symbols()) == names, "ctypes prototypes and header disagree"
+    assert lib.load().etpgt_version() >= 100
+    assert lib.size("etpgt_tconv_bwd_workspace_bytes", 10, 20, 256, 2) > 10 * 256 * 4
+
+
+def test_argument_checks_fail_loudly_without_launching(lib):
+    # unsupported dim: rejected on the host, nothing is launched, message available
+    with pytest.raises(RuntimeError, match="unsupported"):
+        lib.call("etpgt_embed_pe_fwd", None, 4, None, 10, None, 0, None, None, 0, 48, None, None)
+    with pytest.raises(ValueError, match="Unknown readout type"):
+        lib.call("etpgt_readout_fwd", None, None, 1, 32, 9, None, None, None, None)
+
+
+def test_cpu_tensors_are_rejected():
+    from etpgt_b200.model import create_graph_transformer_optimized
+
+    model = create_graph_transformer_optimized(num_items=50, embedding_dim=32, hidden_dim=32, use_laplacian_pe=False)
+
+    class B:
+        x = torch.tensor([1, 2, 3])
+        edge_index = torch.tensor([[0, 1], [1, 2]])
+        batch = torch.tensor([0, 0, 0])
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model(B())
+
+
+def test_module_api_and_state_dict_keys_match_reference():
+    from etpgt_b200.model import (create_gat, create_graph_transformer, create_graph_transformer_optimized,
+                                  create_graphsage)
+    from etpgt_b200.train.losses import BPRLoss, DualLoss, ListwiseLoss, SampledSoftmaxLoss, create_loss_function
+
+    m = create_graph_transformer_optimized(num_items=100, embedding_dim=32, hidden_dim=32)
+    assert (m.use_ffn, m.num_layers, m.num_heads) == (False, 2, 2)       # tests/test_models.py:147-149
+    keys = set(m.state_dict().keys())
+    for layer in (0, 1):
+        for lin in ("key", "query", "value", "skip"):
+            assert f"convs.{layer}.lin_{lin}.weight" in keys and f"convs.{layer}.lin_{lin}.bias" in keys
+        assert f"convs.{layer}.lin_beta.weight" in keys
+        assert f"batch_norms.{layer}.running_var" in keys
+    assert {"item_embedding.weight", "laplacian_pe.projection.weight", "laplacian_pe.projection.bias"} <= keys
+    assert m.item_embedding.padding_idx == 0 and bool((m.item_embedding.weight[0] == 0).all())
+    with pytest.raises(RuntimeError, match="Laplacian PE not precomputed"):
+        m.laplacian_pe(torch.tensor([1, 2]))
+    count = lambda mod: sum(p.numel() for p in mod.parameters())  # noqa: E731
+    kw = dict(num_items=188, embedding_dim=64, hidden_dim=64, num_layers=2, dropout=0.1)
+    # docs/EXPERIMENTS.md:85-88
+    assert count(create_graph_transformer_optimized(**kw, num_heads=2, use_laplacian_pe=False)) == 45952
+    assert count(create_graph_transformer(**kw, num_heads=2, use_laplacian_pe=False, use_ffn=True)) == 112128
+    assert count(create_gat(**kw, num_heads=2)) == 29312
+    assert count(create_graphsage(**kw)) == 28800
+    assert isinstance(create_loss_function("bpr"), BPRLoss)
+    assert isinstance(create_loss_function("listwise"), ListwiseLoss)
+    assert isinstance(create_loss_function("dual"), DualLoss)
+    assert isinstance(create_loss_function("sampled_softmax"), SampledSoftmaxLoss)
+    with pytest.raises(ValueError, match="Unknown loss type"):
+        create_loss_function("nope")
+
+
+def test_golden_state_dicts_load_strictly():
+    from golden_util import Golden
+
+    from etpgt_b200.model import create_gat, create_graph_transformer_optimized, create_graphsage
+
+    for name, factory in (("gt_opt_b32", create_graph_transformer_optimized), ("gat_directed", create_gat),
+                          ("sage_directed", create_graphsage)):
+        g = Golden(name)
+        cfg = g.cfg()
+        model = factory(**cfg)
+        state = g.group("state")
+        pe = state.pop("laplacian_pe._cached_pe", None)
+        missing, unexpected = model.load_state_dict(state, strict=False)
+        assert not unexpected, unexpected
+        assert not missing, missing
