@@ -1,0 +1,423 @@
+#!/usr/bin/env python3
+"""bench.py — the driver-facing benchmark of the etpgt_b200 hot path.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU oracle port, same config
+
+Workload (BASELINE.json configs[1]): graph_transformer_optimized (D=256, L=2, H=2, k_pe=16),
+BPR loss, AdamW(1e-3, 1e-5), session batches drawn from the synthetic RetailRocket-shaped graph
+(etpgt_b200/synth.py).  One step = forward + loss + backward + optimizer over one batch of
+`--batch` sessions per GPU (weak scaling).  Prints ONE JSON line (rank 0).
+
+  value   sessions/s with the batch tensors already resident in HBM;
+  e2e     the same step driven from pinned HOST batch tensors (H2D of x / edge_index / batch /
+          targets / negatives inside the timed region) with the loss read back every step;
+  roofline  the dominant kernel group (fused TransformerConv fwd+bwd) timed alone with CUDA events:
+          algorithmic bytes / time vs the measured HBM peak;
+  cpu_baseline  the oracle port (oracle/model_ref.py, a restatement of the reference's PyTorch/PyG
+          path) on this box's host cores, on a bounded sample of the same workload.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT / "gat-recommendation_b200"))
+sys.path.insert(0, str(ROOT))
+
+METRIC = "train sessions/sec/GPU at 1/2/4/8 B200; TransformerConv edges/sec & HBM GB/s"
+DIM, LAYERS, HEADS, K_PE, NUM_NEG = 256, 2, 2, 16, 5
+NUM_ITEMS = 82_174
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=16384, help="sessions per GPU per step")
+    ap.add_argument("--cpu-batch", type=int, default=1024, help="sessions per step of the CPU sample")
+    ap.add_argument("--rotate", type=int, default=4, help="distinct batches rotated through the timed steps")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------ helpers
+
+
+def peaks() -> dict:
+    path = ROOT / "MEASURED_PEAKS.json"
+    if path.exists():
+        d = json.loads(path.read_text())
+        return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.samples, self.proc = gpu_index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append([f.strip() for f in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+
+    def summary(self) -> dict:
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.samples:
+            try:
+                sm.append(float(row[0])), mx.append(float(row[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, flag in zip(names, row[2:6]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def sample_negatives_host(rng, members, num_items, num_neg):
+    """Host negatives with the reference's acceptance rule (dataloader.py:116-124): uniform in
+    [1, num_items), never a session item, duplicates allowed.  Setup only (the device sampler is the
+    production path once a1-a3 are on the device)."""
+    out = rng.integers(1, num_items, size=(len(members), num_neg))
+    for b, items in enumerate(members):
+        bad = np.isin(out[b], items)
+        while bad.any():
+            out[b, bad] = rng.integers(1, num_items, size=int(bad.sum()))
+            bad = np.isin(out[b], items)
+    return out.astype(np.int64)
+
+
+class HostBatch:
+    """One batch as pinned host tensors, the way the reference's DataLoader hands it over."""
+
+    FIELDS = ("x", "edge_index", "batch", "target", "negatives")
+
+    def __init__(self, arrays: dict, pin: bool):
+        self.t = {k: torch.from_numpy(np.ascontiguousarray(arrays[k])) for k in self.FIELDS}
+        if pin:
+            self.t = {k: v.pin_memory() for k, v in self.t.items()}
+        self.num_graphs = int(arrays["target"].shape[0])
+        self.nodes, self.edges = int(arrays["x"].shape[0]), int(arrays["edge_index"].shape[1])
+
+    def nbytes(self) -> int:
+        return sum(v.numel() * v.element_size() for v in self.t.values())
+
+    def to_device(self, device):
+        return DeviceBatch({k: v.to(device, non_blocking=True) for k, v in self.t.items()}, self.num_graphs)
+
+
+class DeviceBatch:
+    def __init__(self, t: dict, num_graphs: int):
+        self.x, self.edge_index, self.batch = t["x"], t["edge_index"], t["batch"]
+        self.target_item, self.negative_items = t["target"], t["negatives"]
+        self.num_graphs = num_graphs
+
+
+def make_batches(data, edge_keys, first_session, batch, count, seed, pin):
+    from etpgt_b200 import synth
+
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(count):
+        ids = (first_session + i * batch + np.arange(batch)) % data.num_sessions
+        arrays = synth.build_batch(data, ids, edge_keys=edge_keys)
+        arrays["negatives"] = sample_negatives_host(rng, arrays["members"], data.num_items, NUM_NEG)
+        out.append(HostBatch(arrays, pin))
+    return out
+
+
+def cached_pe(num_items):
+    return torch.randn(num_items, K_PE, generator=torch.Generator().manual_seed(7)).abs()
+
+
+# ------------------------------------------------------------------------------ reference arm
+
+
+def oracle_training_steps(data, edge_keys, batch, steps, warmup):
+    """The CPU oracle port of the same step (embedding + PE, 2x TransformerConv/BN/residual, mean
+    readout, BPR, AdamW over every parameter incl. the dense item table) on all host cores."""
+    from oracle import model_ref
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(0)
+    state = {"item_embedding.weight": torch.randn(NUM_ITEMS, DIM, generator=g) * 0.05,
+             "laplacian_pe.projection.weight": torch.randn(DIM, K_PE, generator=g) * 0.1,
+             "laplacian_pe.projection.bias": torch.zeros(DIM), "laplacian_pe._cached_pe": cached_pe(NUM_ITEMS)}
+    state["item_embedding.weight"][0] = 0
+    for layer in range(LAYERS):
+        for lin in ("query", "key", "value", "skip"):
+            state[f"convs.{layer}.lin_{lin}.weight"] = torch.randn(DIM, DIM, generator=g) / DIM ** 0.5
+            state[f"convs.{layer}.lin_{lin}.bias"] = torch.zeros(DIM)
+        state[f"convs.{layer}.lin_beta.weight"] = torch.randn(1, 3 * DIM, generator=g) * 0.05
+        state[f"batch_norms.{layer}.weight"] = torch.ones(DIM)
+        state[f"batch_norms.{layer}.bias"] = torch.zeros(DIM)
+        state[f"batch_norms.{layer}.running_mean"] = torch.zeros(DIM)
+        state[f"batch_norms.{layer}.running_var"] = torch.ones(DIM)
+    params = [k for k in state if "running" not in k and "_cached_pe" not in k]
+    for k in params:
+        state[k].requires_grad_(True)
+    opt = torch.optim.AdamW([state[k] for k in params], lr=1e-3, weight_decay=1e-5)
+    batches = make_batches(data, edge_keys, 0, batch, 2, seed=1, pin=False)
+    times = []
+    for step in range(warmup + steps):
+        hb = batches[step % len(batches)]
+        t0 = time.perf_counter()
+        sess = model_ref.graph_transformer_forward(state, hb.t["x"], hb.t["edge_index"], hb.t["batch"],
+                                                   num_layers=LAYERS, num_heads=HEADS, training=True)
+        loss = model_ref.bpr_loss(sess, state["item_embedding.weight"], hb.t["target"], hb.t["negatives"])
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        loss.item()
+        if step >= warmup:
+            times.append(time.perf_counter() - t0)
+    return batch / (sum(times) / len(times)), sum(times) / len(times)
+
+
+def run_reference(args, rank):
+    from etpgt_b200 import synth
+
+    if rank != 0:
+        return
+    data = synth.generate()
+    edge_keys = synth.sorted_edge_keys(data)
+    steps, warmup = min(args.steps, 5), min(args.warmup, 1)
+    value, sec = oracle_training_steps(data, edge_keys, args.cpu_batch, steps, warmup)
+    cores = os.cpu_count() or 1
+    sample = f"{steps} steps of {args.cpu_batch} sessions (oracle port of the reference PyTorch/PyG path, fp32, CPU)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "sessions/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, data.stats()),
+        "cpu_baseline": {"value": value, "unit": "sessions/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "sessions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(args, stats):
+    return {"workload": "graph_transformer_optimized training step (fwd+BPR+bwd+AdamW), RR-synth sessions",
+            "dim": DIM, "layers": LAYERS, "heads": HEADS, "k_pe": K_PE, "negatives": NUM_NEG,
+            "sessions_per_gpu_per_step": args.batch, "items": stats["items"], "graph_edges": stats["graph_edges"],
+            "graph_nodes": stats["graph_nodes"], "parallelism": f"dp{args.gpus}",
+            "l2_policy": "inputs larger than L2 (rotating batches, 84 MB table, >300 MB activations)"}
+
+
+# ------------------------------------------------------------------------------ B200 arm
+
+
+def run_b200(args, rank, world_size, local_rank):
+    import torch.distributed as dist
+
+    import etpgt_b200
+    from etpgt_b200 import _lib, ops, parallel, synth
+    from etpgt_b200.model import create_graph_transformer_optimized
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the etpgt_b200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    distributed = world_size > 1
+    if distributed:
+        dist.init_process_group("nccl", device_id=device)
+
+    data = synth.generate()
+    edge_keys = synth.sorted_edge_keys(data)
+    first = rank * args.batch * args.rotate
+    host_batches = make_batches(data, edge_keys, first, args.batch, args.rotate, seed=100 + rank, pin=True)
+    dev_batches = [hb.to_device(device) for hb in host_batches]
+
+    torch.manual_seed(0)
+    model = create_graph_transformer_optimized(NUM_ITEMS, DIM, DIM, LAYERS, HEADS, dropout=0.1).to(device)
+    model.laplacian_pe._cached_pe = cached_pe(NUM_ITEMS).to(device)
+    if distributed:
+        parallel.enable_global_batch_norm(model)
+        for p in model.parameters():
+            dist.broadcast(p.data, 0)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-5, fused=True)
+    params = list(model.parameters())
+    total_sessions = args.batch * world_size
+    model.train()
+
+    def step(batch):
+        sess = model(batch)
+        loss = ops.sampled_loss(sess, model.item_embedding, batch.target_item, batch.negative_items, "bpr",
+                                total_sessions=total_sessions)[0]
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        if distributed:
+            parallel.allreduce_gradients(params)
+        opt.step()
+        return loss
+
+    def sync():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for i in range(steps):
+            fn(i)
+        t1.record()
+        sync()
+        ms = torch.tensor([t0.elapsed_time(t1)], device=device)
+        if distributed:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- device-resident timing (value)
+    for i in range(args.warmup):
+        step(dev_batches[i % len(dev_batches)])
+    _lib.reset_launch_count()
+    with ClockSampler(local_rank) as clocks:
+        ms_total = timed(lambda i: step(dev_batches[i % len(dev_batches)]), args.steps)
+    launches = _lib.launch_count()
+    value = total_sessions * args.steps / (ms_total / 1e3)
+
+    # ---- end to end from pinned host batches (e2e)
+    losses = []
+
+    def e2e_step(i):
+        hb = host_batches[i % len(host_batches)]
+        losses.append(float(step(hb.to_device(device)).item()))
+
+    for i in range(min(args.warmup, 3)):
+        e2e_step(i)
+    ms_e2e = timed(e2e_step, args.steps)
+    e2e_value = total_sessions * args.steps / (ms_e2e / 1e3)
+    h2d = int(np.mean([hb.nbytes() for hb in host_batches]))
+
+    out = {
+        "metric": METRIC, "value": value, "unit": "sessions/s", "n_gpus": world_size, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, data.stats()),
+        "e2e": {"value": e2e_value, "unit": "sessions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks.summary(),
+        "final_loss": losses[-1] if losses else None,
+        "batch_shape": {"nodes": host_batches[0].nodes, "edges": host_batches[0].edges},
+    }
+    if rank == 0:
+        out["roofline"] = tconv_roofline(model, dev_batches[0], device)
+        out["edges_per_s_tconv_fwd_bwd"] = out["roofline"].pop("edges_per_s")
+        if world_size == 1 and not args.skip_cpu_baseline:
+            steps = 2
+            v, sec = oracle_training_steps(data, edge_keys, args.cpu_batch, steps, 1)
+            out["cpu_baseline"] = {"value": v, "unit": "sessions/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                   "sample": f"{steps} steps of {args.cpu_batch} sessions (oracle port, fp32 CPU)"}
+        print(json.dumps(out))
+    if distributed:
+        dist.destroy_process_group()
+
+
+def tconv_roofline(model, batch, device, reps=20):
+    """Times the fused TransformerConv forward and backward kernels alone (CUDA events on the
+    launching stream, L2 flushed between repetitions) on the step's own layer-0 tensors."""
+    from etpgt_b200 import _lib, ops
+    from etpgt_b200._lib import call, ptr, size, stream, workspace
+
+    pk = peaks()
+    index = ops.graph_index_of(batch, batch.edge_index, batch.x.numel())
+    n, e = index.num_nodes, index.num_edges
+    with torch.no_grad():
+        x = ops.EmbedPE.apply(batch.x, model.item_embedding.weight, model.laplacian_pe.cached(), False,
+                              model.laplacian_pe.projection.weight, model.laplacian_pe.projection.bias, 0)
+        conv = model.convs[0]
+        qkvs = conv.project(x).contiguous()
+        w_beta = conv.lin_beta.weight.detach().reshape(-1).contiguous()
+    f32 = dict(dtype=torch.float32, device=device)
+    out, agg = torch.empty(n, DIM, **f32), torch.empty(n, DIM, **f32)
+    beta, m, inv_l = torch.empty(n, **f32), torch.empty(n, HEADS, **f32), torch.empty(n, HEADS, **f32)
+    d_out, d_qkvs, d_wb = torch.randn(n, DIM, **f32), torch.empty_like(qkvs), torch.empty(3 * DIM, **f32)
+    ws = workspace(size("etpgt_tconv_bwd_workspace_bytes", n, e, DIM, HEADS), device)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+
+    def fwd():
+        call("etpgt_tconv_fwd", ptr(qkvs), n, DIM, HEADS, ptr(index.rowptr), ptr(index.col), ptr(index.eperm), e,
+             ptr(w_beta), None, ptr(out), ptr(agg), ptr(beta), ptr(m), ptr(inv_l), stream())
+
+    def bwd():
+        call("etpgt_tconv_bwd", ptr(qkvs), ptr(d_out), n, DIM, HEADS, ptr(index.rowptr), ptr(index.col),
+             ptr(index.eperm), ptr(index.colptr), ptr(index.row), ptr(index.cpos), e, ptr(w_beta), None, ptr(agg),
+             ptr(beta), ptr(m), ptr(inv_l), ptr(d_qkvs), ptr(d_wb), ptr(ws), ws.numel(), stream())
+
+    def time_fn(fn):
+        for _ in range(3):
+            fn()
+        total = 0.0
+        for _ in range(reps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            total += a.elapsed_time(b)
+        return total / reps
+
+    ms_f, ms_b = time_fn(fwd), time_fn(bwd)
+    s = 4
+    bytes_f = e * (2 * DIM * s + 4) + n * (4 * DIM * s + HEADS * 8 + 4)
+    bytes_b = e * (4 * DIM * s + 8 + HEADS * 16 + 8) + n * (10 * DIM * s)
+    achieved = (bytes_f + bytes_b) / ((ms_f + ms_b) / 1e3) / 1e9
+    return {"bound": "hbm", "kernel": "tconv_fwd + tconv_bwd_dst + tconv_bwd_src (layer 0)",
+            "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
+            "peak_source": pk["source"], "traffic": None, "ms_fwd": ms_f, "ms_bwd": ms_b,
+            "gbs_fwd": bytes_f / (ms_f / 1e3) / 1e9, "gbs_bwd": bytes_b / (ms_b / 1e3) / 1e9,
+            "nodes": n, "edges": e, "edges_per_s": e / ((ms_f + ms_b) / 1e3)}
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world_size == 1 and args.gpus > 1:
+        # launched without torchrun: N independent ranks are not available; measure one GPU
+        print(f"bench.py: --gpus {args.gpus} without torchrun env; running a single rank", file=sys.stderr)
+    run_b200(args, rank, world_size, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -31,6 +31,11 @@ _PROTOTYPES = {
     "etpgt_tconv_fwd": (I, [P, L, I, I, P, P, P, L, P, P, P, P, P, P, P, P]),
     "etpgt_tconv_bwd_workspace_bytes": (Z, [L, L, I, I]),
     "etpgt_tconv_bwd": (I, [P, P, L, I, I, P, P, P, P, P, P, L, P, P, P, P, P, P, P, P, P, Z, P]),
+    "etpgt_gat_fwd": (I, [P, P, P, L, I, I, P, P, P, F, P, P, P, P, P, P]),
+    "etpgt_gat_bwd_workspace_bytes": (Z, [L, L, I]),
+    "etpgt_gat_bwd": (I, [P, P, P, P, P, L, I, I, P, P, P, P, P, P, L, F, P, P, P, P, P, P, P, P, Z, P]),
+    "etpgt_sage_mean_fwd": (I, [P, L, I, P, P, P, P]),
+    "etpgt_sage_mean_bwd": (I, [P, L, I, P, P, P, P, P]),
     "etpgt_bn_workspace_bytes": (Z, [L, I]),
     "etpgt_bn_stats": (I, [P, L, I, P, P, Z, P]),
     "etpgt_bn_finalize": (I, [P, D, I, F, F, P, P, P, P, P]),

@@ -57,6 +57,59 @@ class TransformerConv(nn.Module):
         return ops.TransformerConvFn.apply(qkvs, w_beta, alpha_mask, index, self.heads)
 
 
+class GATConv(nn.Module):
+    """Drop-in for `torch_geometric.nn.GATConv(in, out, heads, dropout, concat)` as constructed at
+    etpgt/model/gat.py:49-109 (PyG >= 2.5 parameter names: lin, att_src, att_dst, bias)."""
+
+    def __init__(self, in_channels, out_channels, heads=1, concat=True, negative_slope=0.2, dropout=0.0,
+                 add_self_loops=True, bias=True):
+        super().__init__()
+        if not add_self_loops:
+            raise NotImplementedError("etpgt_b200.GATConv implements add_self_loops=True (the reference's use)")
+        self.in_channels, self.out_channels, self.heads = in_channels, out_channels, heads
+        self.concat, self.negative_slope, self.dropout = concat, negative_slope, dropout
+        self.lin = nn.Linear(in_channels, heads * out_channels, bias=False)
+        self.att_src = nn.Parameter(torch.empty(1, heads, out_channels))
+        self.att_dst = nn.Parameter(torch.empty(1, heads, out_channels))
+        self.bias = nn.Parameter(torch.zeros(heads * out_channels if concat else out_channels)) if bias else None
+        nn.init.xavier_uniform_(self.lin.weight)
+        nn.init.xavier_uniform_(self.att_src)
+        nn.init.xavier_uniform_(self.att_dst)
+
+    def forward(self, x, edge_index, mask_edges=None, mask_self=None):
+        index = _as_index(edge_index, x.size(0))
+        n, heads, c = x.size(0), self.heads, self.out_channels
+        h = self.lin(x)
+        hv = h.view(n, heads, c)
+        a_src = (hv * self.att_src).sum(-1)
+        a_dst = (hv * self.att_dst).sum(-1)
+        if mask_edges is None and self.training and self.dropout > 0.0:
+            mask_edges = _alpha_dropout_mask(index.num_edges, heads, self.dropout, True, x)
+            mask_self = _alpha_dropout_mask(n, heads, self.dropout, True, x)
+        agg = ops.GatAggregateFn.apply(h, a_src, a_dst, mask_edges, mask_self, index, heads, self.negative_slope)
+        out = agg if self.concat else agg.view(n, heads, c).mean(dim=1)
+        return out if self.bias is None else out + self.bias
+
+
+class SAGEConv(nn.Module):
+    """Drop-in for `torch_geometric.nn.SAGEConv(in, out, aggr="mean")` (etpgt/model/graphsage.py:43-48):
+    lin_l(mean of in-neighbours) + lin_r(x), lin_l with bias, lin_r without."""
+
+    def __init__(self, in_channels, out_channels, aggr="mean", normalize=False, root_weight=True, project=False,
+                 bias=True):
+        super().__init__()
+        if aggr != "mean" or normalize or project or not root_weight:
+            raise NotImplementedError("etpgt_b200.SAGEConv implements aggr='mean' (the only aggregator the "
+                                      "reference uses, scripts/evaluate_local.py:43)")
+        self.in_channels, self.out_channels, self.aggr = in_channels, out_channels, aggr
+        self.lin_l = nn.Linear(in_channels, out_channels, bias=bias)
+        self.lin_r = nn.Linear(in_channels, out_channels, bias=False)
+
+    def forward(self, x, edge_index):
+        index = _as_index(edge_index, x.size(0))
+        return self.lin_l(ops.SageMeanFn.apply(x, index)) + self.lin_r(x)
+
+
 def batch_norm_rows(bn: nn.BatchNorm1d, x: torch.Tensor, residual: torch.Tensor | None = None,
                     relu: bool = False, group=None) -> torch.Tensor:
     """`bn(x) (+ residual) (-> relu)` with the statistics of an ordinary nn.BatchNorm1d module

@@ -169,6 +169,72 @@ class TransformerConvFn(torch.autograd.Function):
         return d_qkvs, d_w_beta, None, None, None
 
 
+# ------------------------------------------------------------------------------ GAT / GraphSAGE
+
+
+class GatAggregateFn(torch.autograd.Function):
+    """Edge softmax over leaky_relu(a_src[j] + a_dst[i]) and per-head aggregation of h_j, with the
+    PyG self-loop rule (etpgt_gat_fwd / _bwd).  Returns the per-head result [N, heads*C]."""
+
+    @staticmethod
+    def forward(ctx, h, a_src, a_dst, mask_edges, mask_self, index: GraphIndex, heads: int, slope: float):
+        _require_cuda(h, "node features")
+        h, a_src, a_dst = _f32(h), _f32(a_src), _f32(a_dst)
+        n, width = h.shape
+        dev = h.device
+        me = _f32(mask_edges) if mask_edges is not None else None
+        ms = _f32(mask_self) if mask_self is not None else None
+        agg = torch.empty(n, width, dtype=torch.float32, device=dev)
+        m = torch.empty(n, heads, dtype=torch.float32, device=dev)
+        inv_l = torch.empty(n, heads, dtype=torch.float32, device=dev)
+        call("etpgt_gat_fwd", ptr(h), ptr(a_src), ptr(a_dst), n, width, heads, ptr(index.rowptr), ptr(index.col),
+             ptr(index.eperm), float(slope), ptr(me), ptr(ms), ptr(agg), ptr(m), ptr(inv_l), stream())
+        ctx.save_for_backward(h, a_src, a_dst, me, ms, agg, m, inv_l)
+        ctx.index, ctx.heads, ctx.slope = index, heads, float(slope)
+        return agg
+
+    @staticmethod
+    def backward(ctx, d_agg):
+        h, a_src, a_dst, me, ms, agg, m, inv_l = ctx.saved_tensors
+        index, heads = ctx.index, ctx.heads
+        d_agg = _f32(d_agg)
+        n, width = h.shape
+        dev = h.device
+        d_h = torch.empty_like(h)
+        d_a_src = torch.empty_like(a_src)
+        d_a_dst = torch.empty_like(a_dst)
+        ws = workspace(size("etpgt_gat_bwd_workspace_bytes", n, index.num_edges, heads), dev)
+        call("etpgt_gat_bwd", ptr(h), ptr(a_src), ptr(a_dst), ptr(d_agg), ptr(agg), n, width, heads,
+             ptr(index.rowptr), ptr(index.col), ptr(index.eperm), ptr(index.colptr), ptr(index.row), ptr(index.cpos),
+             index.num_edges, ctx.slope, ptr(me), ptr(ms), ptr(m), ptr(inv_l), ptr(d_h), ptr(d_a_src), ptr(d_a_dst),
+             ptr(ws), ws.numel(), stream())
+        return d_h, d_a_src, d_a_dst, None, None, None, None, None
+
+
+class SageMeanFn(torch.autograd.Function):
+    """Mean of in-neighbour rows (0 for isolated nodes) — PyG SAGEConv(aggr='mean') aggregation."""
+
+    @staticmethod
+    def forward(ctx, x, index: GraphIndex):
+        _require_cuda(x, "node features")
+        x = _f32(x)
+        n, dim = x.shape
+        mean = torch.empty_like(x)
+        call("etpgt_sage_mean_fwd", ptr(x), n, dim, ptr(index.rowptr), ptr(index.col), ptr(mean), stream())
+        ctx.index = index
+        return mean
+
+    @staticmethod
+    def backward(ctx, d_mean):
+        index = ctx.index
+        d_mean = _f32(d_mean)
+        n, dim = d_mean.shape
+        d_x = torch.empty_like(d_mean)
+        call("etpgt_sage_mean_bwd", ptr(d_mean), n, dim, ptr(index.rowptr), ptr(index.colptr), ptr(index.row),
+             ptr(d_x), stream())
+        return d_x, None
+
+
 # ------------------------------------------------------------------------------ BatchNorm (+res, +relu)
 
 

@@ -96,6 +96,32 @@ int etpgt_tconv_bwd(const float* qkvs, const float* d_out, int64_t num_nodes, in
                     float* d_qkvs, float* d_w_beta,
                     void* ws, size_t ws_bytes, etpgt_stream_t stream);
 
+/* ---- a12: GAT edge-softmax aggregation and GraphSAGE mean aggregation ---------------------
+ * PyG GATConv(add_self_loops=True) as used at etpgt/model/gat.py:49-109,137: h [N, width] with
+ * width = heads*channels is the projected row, a_src/a_dst [N, heads] the attention scalars;
+ * e = leaky_relu(a_src[j] + a_dst[i]); existing self loops are dropped and one self loop per node
+ * is processed after the real edges; agg [N, width] = per-head sum alpha * h_j (the head mean /
+ * concat + bias stay with the caller).  mask_edges [E, heads] (original edge order) and
+ * mask_self [N, heads] are optional dropout masks (both or neither).  width in {32..1024}. */
+int etpgt_gat_fwd(const float* h, const float* a_src, const float* a_dst, int64_t num_nodes, int width,
+                  int heads, const int32_t* rowptr, const int32_t* col, const int32_t* eperm,
+                  float negative_slope, const float* mask_edges, const float* mask_self,
+                  float* agg, float* m, float* inv_l, etpgt_stream_t stream);
+size_t etpgt_gat_bwd_workspace_bytes(int64_t num_nodes, int64_t num_edges, int heads);
+int etpgt_gat_bwd(const float* h, const float* a_src, const float* a_dst, const float* d_agg,
+                  const float* agg, int64_t num_nodes, int width, int heads,
+                  const int32_t* rowptr, const int32_t* col, const int32_t* eperm,
+                  const int32_t* colptr, const int32_t* row, const int32_t* cpos, int64_t num_edges,
+                  float negative_slope, const float* mask_edges, const float* mask_self,
+                  const float* m, const float* inv_l, float* d_h, float* d_a_src, float* d_a_dst,
+                  void* ws, size_t ws_bytes, etpgt_stream_t stream);
+/* PyG SAGEConv(aggr="mean") neighbour mean (etpgt/model/graphsage.py:43-48,75): mean_i = average of
+ * x_j over in-edges (0 when there are none); backward distributes d_mean_i / indeg(i) to sources. */
+int etpgt_sage_mean_fwd(const float* x, int64_t num_nodes, int dim, const int32_t* rowptr,
+                        const int32_t* col, float* mean, etpgt_stream_t stream);
+int etpgt_sage_mean_bwd(const float* d_mean, int64_t num_nodes, int dim, const int32_t* rowptr,
+                        const int32_t* colptr, const int32_t* row, float* d_x, etpgt_stream_t stream);
+
 /* ---- a6: BatchNorm1d over node rows (+ residual, + ReLU) --------------------------------
  * graph_transformer.py:175-176, gat.py:138-140, graphsage.py:76-77.
  * stats: per-feature sums over this rank's rows, double precision: sums[0:dim] = sum x,

@@ -254,7 +254,7 @@ def test_session_readout(ops, kind, dim):
     assert rel_err(xc.grad, x64.grad) < TOL
     if kind == "attention":
         assert rel_err(awc.grad, aw64.grad) < TOL
-        assert rel_err(abc.grad, ab64.grad) < TOL
+        assert abc.grad.abs().max().item() < 1e-5  # analytically zero: the softmax cancels a shared bias
 
 
 def test_golden_readouts(ops):
