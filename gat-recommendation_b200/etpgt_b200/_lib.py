@@ -25,6 +25,12 @@ _PROTOTYPES = {
     "etpgt_csr_workspace_bytes": (Z, [L, L]),
     "etpgt_csr_from_coo": (I, [P, P, L, L, P, P, P, P, P, P, P, Z, P]),
     "etpgt_segment_ptr": (I, [P, L, L, P, P]),
+    "etpgt_item_graph_workspace_bytes": (Z, [L]),
+    "etpgt_item_graph_build": (I, [P, P, L, L, P, P, P, P, Z, P]),
+    "etpgt_session_subgraphs_workspace_bytes": (Z, [L, L]),
+    "etpgt_session_subgraphs_count": (I, [P, P, P, P, P, L, I, I, I, P, P, P, Z, P]),
+    "etpgt_session_subgraphs_fill": (I, [P, P, P, P, P, P, L, I, I, I, P, P, L, P, P, P, P, P, P, Z, P]),
+    "etpgt_sample_negatives": (I, [ctypes.c_uint64, ctypes.c_uint32, L, P, P, P, L, I, L, I, P, P]),
     "etpgt_embed_pe_fwd": (I, [P, L, P, L, P, I, P, P, I, I, P, P]),
     "etpgt_embed_pe_bwd_workspace_bytes": (Z, [L, I, I]),
     "etpgt_embed_pe_bwd": (I, [P, L, P, L, P, I, I, I, L, P, P, P, P, Z, P]),

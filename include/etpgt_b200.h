@@ -55,6 +55,52 @@ int etpgt_csr_from_coo(const int64_t* src, const int64_t* dst, int64_t num_edges
 int etpgt_segment_ptr(const int64_t* seg_ids, int64_t n, int64_t num_segments, int32_t* ptr,
                       etpgt_stream_t stream);
 
+/* ---- a1-a3: per-batch session subgraphs and negatives on the device ------------------------
+ * Replaces SessionDataset._build_session_subgraph / collate_fn / _sample_negatives
+ * (etpgt/train/dataloader.py:107-202) and create_batch_from_sessions' edge rules
+ * (scripts/pipeline/run_full_pipeline.py:120-166).
+ *
+ * item_graph_build (one-off): lookup structure over the stored edge list (item_i[e], item_j[e]) in
+ * its stored order: gptr[num_items+1] rows keyed by item_i, gcol[E] = item_j sorted inside a row,
+ * gidx[E] = stored row index of that edge. */
+size_t etpgt_item_graph_workspace_bytes(int64_t num_edges);
+int etpgt_item_graph_build(const int64_t* item_i, const int64_t* item_j, int64_t num_edges,
+                           int64_t num_items, int32_t* gptr, int32_t* gcol, int32_t* gidx,
+                           void* ws, size_t ws_bytes, etpgt_stream_t stream);
+/* Sessions are sess_items[sess_ptr[s] : sess_ptr[s+1]] in chronological order (target = last
+ * event).  Only the last max_len events are used (max_len <= 65); context = all but the last;
+ * nodes = sorted unique context items; an edge of the stored list is kept iff both ends are context
+ * items, in stored order and direction.  session_ids [S] (or NULL = 0..S-1) selects the batch's
+ * sessions out of the resident store.  symmetrize appends the reversed copies after the forward
+ * ones; self_loop_if_empty adds one loop per node when no edge was kept.
+ * count: node_ptr / edge_ptr [S+1] (exclusive prefix sums; the caller reads the two totals to size
+ * the outputs).  fill: x [N] item ids, batch [N] session index, edge_src / edge_dst [E] with the
+ * cumulative node offset added (PyG collate layout), target [S]. */
+size_t etpgt_session_subgraphs_workspace_bytes(int64_t num_sessions, int64_t num_edges);
+int etpgt_session_subgraphs_count(const int32_t* gptr, const int32_t* gcol, const int64_t* sess_ptr,
+                                  const int64_t* sess_items, const int64_t* session_ids,
+                                  int64_t num_sessions, int max_len,
+                                  int symmetrize, int self_loop_if_empty,
+                                  int32_t* node_ptr, int32_t* edge_ptr,
+                                  void* ws, size_t ws_bytes, etpgt_stream_t stream);
+int etpgt_session_subgraphs_fill(const int32_t* gptr, const int32_t* gcol, const int32_t* gidx,
+                                 const int64_t* sess_ptr, const int64_t* sess_items,
+                                 const int64_t* session_ids, int64_t num_sessions, int max_len,
+                                 int symmetrize,
+                                 int self_loop_if_empty, const int32_t* node_ptr,
+                                 const int32_t* edge_ptr, int64_t num_edges,
+                                 int64_t* x, int64_t* batch, int64_t* edge_src, int64_t* edge_dst,
+                                 int64_t* target, void* ws, size_t ws_bytes, etpgt_stream_t stream);
+/* out[s, slot] = uniform id in [1, num_items) that is not among the last max_len events of session
+ * s (duplicates between slots allowed).  Philox4x32-10, key = seed, counter = (GLOBAL session index
+ * = session_ids[s], or session_base + s when session_ids is NULL; slot, attempt / 4, step), word attempt % 4, candidate = 1 + ((word * (num_items-1)) >> 32):
+ * identical for any partition of the sessions over GPUs. */
+int etpgt_sample_negatives(uint64_t seed, uint32_t step, int64_t session_base,
+                           const int64_t* sess_ptr, const int64_t* sess_items,
+                           const int64_t* session_ids, int64_t num_sessions,
+                           int max_len, int64_t num_items, int num_neg, int64_t* out,
+                           etpgt_stream_t stream);
+
 /* ---- a4: item embedding + Laplacian-PE projection -------------------------------------
  * out[n] = table[ids[n]] (+ pe[pe_row(n)] @ w_pe^T + b_pe);  pe_row(n) = n when
  * pe_per_node else ids[n].  etpgt/model/graph_transformer.py:140-152,
