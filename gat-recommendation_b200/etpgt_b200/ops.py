@@ -404,16 +404,42 @@ def sampled_loss(sess, item_embeddings, targets, negatives, kind: str, alpha=0.7
 # ------------------------------------------------------------------------------ scoring / top-k
 
 
+def to_bf16(t: torch.Tensor) -> torch.Tensor:
+    """Round-to-nearest-even fp32 -> bf16 copy (etpgt_f32_to_bf16)."""
+    if t.dtype == torch.bfloat16:
+        return t.contiguous()
+    src = _f32(t.detach())
+    dst = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    call("etpgt_f32_to_bf16", ptr(src), ptr(dst), src.numel(), stream())
+    return dst
+
+
+def tensor_core_scoring_supported(dim: int, k: int) -> bool:
+    return dim in (64, 128, 192, 256) and 1 <= k <= 32
+
+
 @torch.no_grad()
-def score_topk(sess: torch.Tensor, table: torch.Tensor, k: int, id_base: int = 0):
-    """Top-k item ids by dot product, ties to the lower id — etpgt/model/base.py:59-78."""
+def score_topk(sess: torch.Tensor, table: torch.Tensor, k: int, id_base: int = 0, precision: str = "fp32"):
+    """Top-k item ids by dot product, ties to the lower id — etpgt/model/base.py:59-78.
+
+    precision "fp32": CUDA-core scorer with the reference's fp32 arithmetic.
+    precision "bf16": tcgen05 tensor-core scorer (bf16 operands, fp32 accumulation in TMEM); `table`
+    may already be a bf16 copy (an evaluation loop converts it once)."""
     _require_cuda(sess, "session embeddings")
-    sess_c, table_c = _f32(sess.detach()), _f32(table.detach())
-    b, dim = sess_c.shape
-    items = table_c.size(0)
-    dev = sess_c.device
+    b, dim = sess.shape
+    items = table.size(0)
+    dev = sess.device
     top_val = torch.empty(b, k, dtype=torch.float32, device=dev)
     top_idx = torch.empty(b, k, dtype=torch.int64, device=dev)
+    if precision == "bf16":
+        sess_h, table_h = to_bf16(sess), to_bf16(table)
+        ws = workspace(size("etpgt_score_topk_bf16_workspace_bytes", b, items, k), dev)
+        call("etpgt_score_topk_bf16", ptr(sess_h), ptr(table_h), b, items, dim, k, id_base, ptr(top_val),
+             ptr(top_idx), ptr(ws), ws.numel(), stream())
+        return top_val, top_idx
+    if precision != "fp32":
+        raise ValueError(f"Unknown scoring precision: {precision}")
+    sess_c, table_c = _f32(sess.detach()), _f32(table.detach())
     ws = workspace(size("etpgt_score_topk_workspace_bytes", b, items, dim, k), dev)
     call("etpgt_score_topk_f32", ptr(sess_c), ptr(table_c), b, items, dim, k, id_base, ptr(top_val), ptr(top_idx),
          ptr(ws), ws.numel(), stream())

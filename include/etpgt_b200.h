@@ -245,6 +245,14 @@ size_t etpgt_score_topk_workspace_bytes(int64_t batch, int64_t num_items, int di
 int etpgt_score_topk_f32(const float* sess, const float* table, int64_t batch, int64_t num_items,
                          int dim, int k, int64_t id_base, float* top_val, int64_t* top_idx,
                          void* ws, size_t ws_bytes, etpgt_stream_t stream);
+/* Tensor-core path: bf16 operands (row-major [rows, dim], 16-byte aligned, dim in {64,128,192,256}),
+ * fp32 accumulation in TMEM, tcgen05.mma fed by TMA, top-k (k <= 32) fused into the TMEM epilogue.
+ * Oracle: fp64 scores of the bf16-rounded operands (oracle/model_ref.predict(bf16_inputs=True)). */
+int etpgt_f32_to_bf16(const float* src, void* dst_bf16, int64_t n, etpgt_stream_t stream);
+size_t etpgt_score_topk_bf16_workspace_bytes(int64_t batch, int64_t num_items, int k);
+int etpgt_score_topk_bf16(const void* sess_bf16, const void* table_bf16, int64_t batch, int64_t num_items,
+                          int dim, int k, int64_t id_base, float* top_val, int64_t* top_idx,
+                          void* ws, size_t ws_bytes, etpgt_stream_t stream);
 /* exact merge of `parts` candidate lists per row ([B, parts*k] values + ids). */
 int etpgt_topk_merge(const float* cand_val, const int64_t* cand_idx, int64_t batch, int parts, int k,
                      float* top_val, int64_t* top_idx, etpgt_stream_t stream);
