@@ -1,0 +1,386 @@
+// Dense node projections on the tensor cores at fp32-grade accuracy ("split-bf16 x3").
+//
+// The per-layer projections of the path are fp32 nn.Linear GEMMs in the reference
+// (TransformerConv lin_query/key/value/skip, PyG via graph_transformer.py:174): [N,256] x [256,1024].
+// fp32 CUDA-core GEMMs were 62 % of the training step (profiles/r01_step_launches.txt).  Here every
+// fp32 operand x is split as x = hi + lo (+ O(2^-18 |x|)), hi = bf16(x), lo = bf16(x - hi), and
+//   C = A_hi B_hi^T + A_hi B_lo^T + A_lo B_hi^T        (fp32 accumulation in TMEM)
+// is issued as three tcgen05.mma per k-step into the same accumulator: ~1e-5 relative error,
+// inside the path's 1e-4 parity bound, at a third of the bf16 tensor rate instead of the fp32
+// CUDA-core rate.  lo == NULL gives a plain bf16 GEMM.
+//
+//   etpgt_split_bf16      fp32 [R,C] -> hi/lo bf16 row-major and/or transposed (K-major operands
+//                         for both the forward and the weight-gradient GEMM) + column sums
+//   etpgt_gemm_bf16x3     C[M,N] = A[M,K] B[N,K]^T (+ bias[N]); persistent warp-specialised
+//                         kernel: TMA ring (A and B k-blocks, SWIZZLE_128B) -> tcgen05.mma
+//                         128x128x16 -> double-buffered TMEM -> epilogue warps -> global;
+//                         optional split-K with a fixed-order reduction (deterministic).
+#include <math.h>
+
+#include "tc_common.cuh"
+
+namespace etpgt {
+namespace {
+
+using namespace tc;
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_N = 128;
+constexpr int kStages = 3;
+constexpr int kAccStages = 2;
+constexpr int kTmemCols = 256;
+constexpr int kThreads = 192;  // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr uint32_t TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB per operand part per k-block
+constexpr uint32_t kInstrDesc = instr_desc_bf16(BLOCK_M, BLOCK_N);
+
+struct __align__(8) GemmBarriers {
+  uint64_t full[kStages];
+  uint64_t empty[kStages];
+  uint64_t acc_full[kAccStages];
+  uint64_t acc_empty[kAccStages];
+  uint32_t tmem_base;
+};
+
+// PARTS = 1: plain bf16 (A_hi, B_hi).  PARTS = 2: split operands, three products.
+template <int PARTS>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                   const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                   int64_t M, int64_t N, int64_t K, int m_tiles, int n_tiles, int split_k, int kb_per_split,
+                   const float* __restrict__ bias, float* __restrict__ C, int64_t ldc,
+                   float* __restrict__ partial /* [split_k][M][N] when split_k > 1 */) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  constexpr uint32_t STAGE_BYTES = 2 * PARTS * TILE_BYTES;  // A parts then B parts
+  GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(smem + kStages * STAGE_BYTES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_kb = (int)((K + BLOCK_K - 1) / BLOCK_K);
+  const int64_t total_units = (int64_t)m_tiles * n_tiles * split_k;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+    for (int s = 0; s < kAccStages; ++s) { mbar_init(&bars->acc_full[s], 1); mbar_init(&bars->acc_empty[s], 4); }
+    fence_barrier_init();
+    tma_prefetch_desc(&map_a_hi);
+    tma_prefetch_desc(&map_b_hi);
+    if (PARTS == 2) { tma_prefetch_desc(&map_a_lo); tma_prefetch_desc(&map_b_lo); }
+  }
+  if (warp == 1) tmem_alloc(&bars->tmem_base, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  // unit -> (split, m_tile, n_tile); n fastest so that co-resident CTAs share the A tile in L2
+  auto decode = [&](int64_t u, int& ks, int& mt, int& nt) {
+    nt = (int)(u % n_tiles);
+    mt = (int)((u / n_tiles) % m_tiles);
+    ks = (int)(u / ((int64_t)n_tiles * m_tiles));
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t u = blockIdx.x; u < total_units; u += gridDim.x) {
+        int ks, mt, nt;
+        decode(u, ks, mt, nt);
+        const int kb0 = ks * kb_per_split;
+        const int kb1 = kb0 + kb_per_split < total_kb ? kb0 + kb_per_split : total_kb;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&bars->empty[stage], phase ^ 1);
+          mbar_expect_tx(&bars->full[stage], STAGE_BYTES);
+          uint8_t* st = smem + stage * STAGE_BYTES;
+          tma_load_2d(&map_a_hi, &bars->full[stage], st, kb * BLOCK_K, mt * BLOCK_M);
+          if (PARTS == 2) tma_load_2d(&map_a_lo, &bars->full[stage], st + TILE_BYTES, kb * BLOCK_K, mt * BLOCK_M);
+          tma_load_2d(&map_b_hi, &bars->full[stage], st + PARTS * TILE_BYTES, kb * BLOCK_K, nt * BLOCK_N);
+          if (PARTS == 2)
+            tma_load_2d(&map_b_lo, &bars->full[stage], st + (PARTS + 1) * TILE_BYTES, kb * BLOCK_K, nt * BLOCK_N);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int t = 0;
+      for (int64_t u = blockIdx.x; u < total_units; u += gridDim.x, ++t) {
+        int ks, mt, nt;
+        decode(u, ks, mt, nt);
+        const int kb0 = ks * kb_per_split;
+        const int kb1 = kb0 + kb_per_split < total_kb ? kb0 + kb_per_split : total_kb;
+        const int acc = t & 1;
+        mbar_wait(&bars->acc_empty[acc], ((uint32_t)(t >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&bars->full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t a_lo = a_hi + TILE_BYTES;
+          const uint32_t b_hi = a_hi + PARTS * TILE_BYTES;
+          const uint32_t b_lo = b_hi + TILE_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+            const uint32_t off = kk * UMMA_K * 2;
+            const uint32_t first = (kb == kb0 && kk == 0) ? 0u : 1u;
+            umma_bf16(tmem_d, make_desc_sw128(a_hi + off), make_desc_sw128(b_hi + off), kInstrDesc, first);
+            if (PARTS == 2) {
+              umma_bf16(tmem_d, make_desc_sw128(a_hi + off), make_desc_sw128(b_lo + off), kInstrDesc, 1u);
+              umma_bf16(tmem_d, make_desc_sw128(a_lo + off), make_desc_sw128(b_hi + off), kInstrDesc, 1u);
+            }
+          }
+          umma_commit(&bars->empty[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&bars->acc_full[acc]);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row_in_tile = quarter * 32 + lane;
+    int t = 0;
+    for (int64_t u = blockIdx.x; u < total_units; u += gridDim.x, ++t) {
+      int ks, mt, nt;
+      decode(u, ks, mt, nt);
+      const int acc = t & 1;
+      mbar_wait(&bars->acc_full[acc], (uint32_t)(t >> 1) & 1);
+      tc_fence_after();
+      const int64_t row = (int64_t)mt * BLOCK_M + row_in_tile;
+      const int64_t col0 = (int64_t)nt * BLOCK_N;
+      float* out = split_k > 1 ? partial + ((int64_t)ks * M + row) * N : C + row * ldc;
+      const bool add_bias = bias != nullptr && split_k == 1;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + (uint32_t)c0, v);
+        if (row < M) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const int64_t col = col0 + c0 + j;
+            if (col + 3 < N) {
+              float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                     __uint_as_float(v[j + 3]));
+              if (add_bias) o = add4(o, ldg4(bias + col));
+              st4(out + col, o);
+            } else {
+              for (int q = 0; q < 4; ++q)
+                if (col + q < N) out[col + q] = __uint_as_float(v[j + q]) + (add_bias ? bias[col + q] : 0.f);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// C[m][n] = bias[n] + sum_s partial[s][m][n], s ascending: deterministic split-K reduction.
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ partial, int split_k, int64_t M, int64_t N,
+                     const float* __restrict__ bias, float* __restrict__ C, int64_t ldc) {
+  const int64_t total4 = M * N / 4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = (4 * i) / N, n = (4 * i) % N;
+    float4 acc = bias != nullptr ? ldg4(bias + n) : zero4();
+    for (int s = 0; s < split_k; ++s) acc = add4(acc, ldg4(partial + ((int64_t)s * M + m) * N + n));
+    st4(C + m * ldc + n, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------ split kernel
+// 64 x 64 fp32 tile per CTA (256 threads): row-major hi/lo written straight from the coalesced
+// read, transposed hi/lo through a padded shared-memory tile, column sums as per-CTA partials.
+constexpr int SPLIT_TILE = 64;
+
+__device__ __forceinline__ void split_one(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+__global__ void __launch_bounds__(256)
+split_bf16_kernel(const float* __restrict__ src, int64_t rows, int64_t cols, int64_t ld_src,
+                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int64_t ld_out,
+                  __nv_bfloat16* __restrict__ hi_t, __nv_bfloat16* __restrict__ lo_t, int64_t ld_t,
+                  float* __restrict__ colsum_partial /* [row_tiles][cols] */) {
+  __shared__ float tile[SPLIT_TILE][SPLIT_TILE + 1];
+  const int64_t r0 = (int64_t)blockIdx.y * SPLIT_TILE, c0 = (int64_t)blockIdx.x * SPLIT_TILE;
+  const int tx = threadIdx.x % SPLIT_TILE, ty = threadIdx.x / SPLIT_TILE;  // 64 x 4
+  for (int rr = ty; rr < SPLIT_TILE; rr += 4) {
+    const int64_t r = r0 + rr, c = c0 + tx;
+    float x = 0.f;
+    if (r < rows && c < cols) {
+      x = src[r * ld_src + c];
+      if (hi != nullptr) {
+        __nv_bfloat16 h, l;
+        split_one(x, h, l);
+        hi[r * ld_out + c] = h;
+        if (lo != nullptr) lo[r * ld_out + c] = l;
+      }
+    }
+    tile[rr][tx] = x;
+  }
+  __syncthreads();
+  if (hi_t != nullptr) {
+    for (int cc = ty; cc < SPLIT_TILE; cc += 4) {
+      const int64_t c = c0 + cc, r = r0 + tx;
+      if (c < cols && r < rows) {
+        __nv_bfloat16 h, l;
+        split_one(tile[tx][cc], h, l);
+        hi_t[c * ld_t + r] = h;
+        if (lo_t != nullptr) lo_t[c * ld_t + r] = l;
+      }
+    }
+  }
+  if (colsum_partial != nullptr && threadIdx.x < SPLIT_TILE) {
+    const int64_t c = c0 + threadIdx.x;
+    if (c < cols) {
+      float s = 0.f;
+      for (int rr = 0; rr < SPLIT_TILE; ++rr) s += tile[rr][threadIdx.x];
+      colsum_partial[(int64_t)blockIdx.y * cols + c] = s;
+    }
+  }
+}
+
+// one warp per output column, lanes stride over the row tiles, fixed butterfly: deterministic
+__global__ void __launch_bounds__(256)
+colsum_reduce_kernel(const float* __restrict__ partial, int64_t parts, int64_t cols, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t c = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (c >= cols) return;
+  float s = 0.f;
+  for (int64_t p = lane; p < parts; p += 32) s += partial[p * cols + c];
+  s = group_sum<32>(s);
+  if (lane == 0) out[c] = s;
+}
+
+struct GemmPlan {
+  int m_tiles, n_tiles, split_k, kb_per_split, grid;
+};
+
+GemmPlan gemm_plan(int64_t M, int64_t N, int64_t K, int want_split) {
+  GemmPlan p;
+  p.m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M);
+  p.n_tiles = (int)((N + BLOCK_N - 1) / BLOCK_N);
+  const int total_kb = (int)((K + BLOCK_K - 1) / BLOCK_K);
+  int split = 1;
+  if (want_split != 1) {
+    // few output tiles and a long K: split K until about two waves of units exist
+    const int64_t tiles = (int64_t)p.m_tiles * p.n_tiles;
+    if (tiles < kNumSMs && total_kb >= 16) {
+      split = (int)((2 * kNumSMs + tiles - 1) / tiles);
+      if (split > total_kb / 8) split = total_kb / 8;
+      if (split < 1) split = 1;
+    }
+    if (want_split > 1) split = want_split;
+  }
+  p.kb_per_split = (total_kb + split - 1) / split;
+  p.split_k = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
+  const int64_t units = (int64_t)p.m_tiles * p.n_tiles * p.split_k;
+  p.grid = (int)(units < kNumSMs ? units : kNumSMs);
+  if (p.grid < 1) p.grid = 1;
+  return p;
+}
+
+}  // namespace
+}  // namespace etpgt
+
+using namespace etpgt;
+
+extern "C" size_t etpgt_split_bf16_workspace_bytes(int64_t rows, int64_t cols) {
+  const int64_t row_tiles = (rows + SPLIT_TILE - 1) / SPLIT_TILE;
+  return align_up((size_t)(row_tiles > 0 ? row_tiles : 1) * cols * sizeof(float)) + 256;
+}
+
+extern "C" int etpgt_split_bf16(const float* src, int64_t rows, int64_t cols, int64_t ld_src, void* hi, void* lo,
+                                int64_t ld_out, void* hi_t, void* lo_t, int64_t ld_t, float* colsum, void* ws,
+                                size_t ws_bytes, etpgt_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ETPGT_REQUIRE(rows >= 0 && cols > 0 && ld_src >= cols, "split_bf16: bad sizes");
+  ETPGT_REQUIRE(hi == nullptr || ld_out >= cols, "split_bf16: ld_out < cols");
+  ETPGT_REQUIRE(hi_t == nullptr || ld_t >= rows, "split_bf16: ld_t < rows");
+  ETPGT_REQUIRE(lo == nullptr || hi != nullptr, "split_bf16: lo without hi");
+  ETPGT_REQUIRE(lo_t == nullptr || hi_t != nullptr, "split_bf16: lo_t without hi_t");
+  if (colsum != nullptr && ws_bytes < etpgt_split_bf16_workspace_bytes(rows, cols)) {
+    set_error("split_bf16: workspace too small");
+    return ETPGT_EWORKSPACE;
+  }
+  const int64_t row_tiles = (rows + SPLIT_TILE - 1) / SPLIT_TILE, col_tiles = (cols + SPLIT_TILE - 1) / SPLIT_TILE;
+  float* partial = colsum != nullptr ? static_cast<float*>(ws) : nullptr;
+  if (rows > 0) {
+    split_bf16_kernel<<<dim3((unsigned)col_tiles, (unsigned)row_tiles), 256, 0, stream>>>(
+        src, rows, cols, ld_src, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), ld_out,
+        static_cast<__nv_bfloat16*>(hi_t), static_cast<__nv_bfloat16*>(lo_t), ld_t, partial);
+    ETPGT_CHECK_LAUNCH("split_bf16");
+  }
+  if (colsum != nullptr) {
+    colsum_reduce_kernel<<<(unsigned)((cols * 32 + 255) / 256), 256, 0, stream>>>(partial, rows > 0 ? row_tiles : 0, cols,
+                                                                                 colsum);
+    ETPGT_CHECK_LAUNCH("colsum_reduce");
+  }
+  return ETPGT_OK;
+}
+
+extern "C" size_t etpgt_gemm_bf16x3_workspace_bytes(int64_t M, int64_t N, int64_t K, int split_k) {
+  const GemmPlan p = gemm_plan(M, N, K, split_k);
+  return (p.split_k > 1 ? align_up((size_t)p.split_k * M * N * sizeof(float)) : 0) + 256;
+}
+
+extern "C" int etpgt_gemm_bf16x3(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int64_t M,
+                                 int64_t N, int64_t K, int64_t lda, int64_t ldb, const float* bias, float* C,
+                                 int64_t ldc, int split_k, void* ws, size_t ws_bytes, etpgt_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ETPGT_REQUIRE(M >= 0 && N > 0 && K > 0 && M < (int64_t(1) << 31) && N < (int64_t(1) << 31) && K < (int64_t(1) << 31),
+                "gemm_bf16x3: bad sizes");
+  ETPGT_REQUIRE(a_hi && b_hi && C && (a_lo == nullptr) == (b_lo == nullptr),
+                "gemm_bf16x3: operands: hi parts required, lo parts both or neither");
+  ETPGT_REQUIRE(lda >= K && ldb >= K && lda % 8 == 0 && ldb % 8 == 0,
+                "gemm_bf16x3: operand pitches must cover K and be multiples of 8 elements (16 bytes)");
+  ETPGT_REQUIRE(N % 4 == 0 && ldc % 4 == 0 && ldc >= N, "gemm_bf16x3: N and ldc must be multiples of 4");
+  ETPGT_REQUIRE((((uintptr_t)a_hi | (uintptr_t)b_hi | (uintptr_t)a_lo | (uintptr_t)b_lo | (uintptr_t)C) & 15) == 0,
+                "gemm_bf16x3: pointers must be 16-byte aligned");
+  if (M == 0) return ETPGT_OK;
+  const GemmPlan p = gemm_plan(M, N, K, split_k);
+  if (ws_bytes < etpgt_gemm_bf16x3_workspace_bytes(M, N, K, split_k)) {
+    set_error("gemm_bf16x3: workspace too small");
+    return ETPGT_EWORKSPACE;
+  }
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  bool ok = make_map_bf16(&ma_hi, a_hi, M, K, lda, BLOCK_M) && make_map_bf16(&mb_hi, b_hi, N, K, ldb, BLOCK_N);
+  if (a_lo != nullptr) ok = ok && make_map_bf16(&ma_lo, a_lo, M, K, lda, BLOCK_M) && make_map_bf16(&mb_lo, b_lo, N, K, ldb, BLOCK_N);
+  else { ma_lo = ma_hi; mb_lo = mb_hi; }
+  if (!ok) {
+    set_error("gemm_bf16x3: cuTensorMapEncodeTiled failed");
+    return ETPGT_ECUDA;
+  }
+  float* partial = p.split_k > 1 ? static_cast<float*>(ws) : nullptr;
+  const int parts = a_lo != nullptr ? 2 : 1;
+  const size_t smem = 1024 + (size_t)kStages * 2 * parts * TILE_BYTES + sizeof(GemmBarriers) + 64;
+  if (parts == 2) {
+    cudaFuncSetAttribute(gemm_bf16x3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    gemm_bf16x3_kernel<2><<<p.grid, kThreads, smem, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, K, p.m_tiles, p.n_tiles,
+                                                             p.split_k, p.kb_per_split, bias, C, ldc, partial);
+  } else {
+    cudaFuncSetAttribute(gemm_bf16x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    gemm_bf16x3_kernel<1><<<p.grid, kThreads, smem, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, K, p.m_tiles, p.n_tiles,
+                                                             p.split_k, p.kb_per_split, bias, C, ldc, partial);
+  }
+  ETPGT_CHECK_LAUNCH("gemm_bf16x3");
+  if (p.split_k > 1) {
+    splitk_reduce_kernel<<<grid_for(M * N / 4, 256 * 2, 8), 256, 0, stream>>>(partial, p.split_k, M, N, bias, C, ldc);
+    ETPGT_CHECK_LAUNCH("splitk_reduce");
+  }
+  return ETPGT_OK;
+}

@@ -37,6 +37,10 @@ _PROTOTYPES = {
     "etpgt_tconv_fwd": (I, [P, L, I, I, P, P, P, L, P, P, P, P, P, P, P, P]),
     "etpgt_tconv_bwd_workspace_bytes": (Z, [L, L, I, I]),
     "etpgt_tconv_bwd": (I, [P, P, L, I, I, P, P, P, P, P, P, L, P, P, P, P, P, P, P, P, P, Z, P]),
+    "etpgt_split_bf16_workspace_bytes": (Z, [L, L]),
+    "etpgt_split_bf16": (I, [P, L, L, L, P, P, L, P, P, L, P, P, Z, P]),
+    "etpgt_gemm_bf16x3_workspace_bytes": (Z, [L, L, L, I]),
+    "etpgt_gemm_bf16x3": (I, [P, P, P, P, L, L, L, L, L, P, P, L, I, P, Z, P]),
     "etpgt_gat_fwd": (I, [P, P, P, L, I, I, P, P, P, F, P, P, P, P, P, P]),
     "etpgt_gat_bwd_workspace_bytes": (Z, [L, L, I]),
     "etpgt_gat_bwd": (I, [P, P, P, P, P, L, I, I, P, P, P, P, P, P, L, F, P, P, P, P, P, P, P, P, Z, P]),

@@ -46,7 +46,7 @@ class TransformerConv(nn.Module):
     def project(self, x: torch.Tensor) -> torch.Tensor:
         weight = torch.cat([self.lin_query.weight, self.lin_key.weight, self.lin_value.weight, self.lin_skip.weight])
         bias = torch.cat([self.lin_query.bias, self.lin_key.bias, self.lin_value.bias, self.lin_skip.bias])
-        return F.linear(x, weight, bias)
+        return ops.linear(x, weight, bias)
 
     def forward(self, x, edge_index, alpha_mask=None):
         index = _as_index(edge_index, x.size(0))

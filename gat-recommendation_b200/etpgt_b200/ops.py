@@ -169,6 +169,87 @@ class TransformerConvFn(torch.autograd.Function):
         return d_qkvs, d_w_beta, None, None, None
 
 
+# ------------------------------------------------------------------------------ dense projections
+
+
+def _split(src: torch.Tensor, rowmajor: bool, transposed: bool, colsum: bool = False):
+    """fp32 [R, C] -> bf16 hi/lo parts (x = hi + lo), row-major and/or transposed, + column sums."""
+    r, c = src.shape
+    dev = src.device
+    bf = dict(dtype=torch.bfloat16, device=dev)
+    hi = lo = hi_t = lo_t = sums = None
+    ld_t = (r + 7) // 8 * 8
+    if rowmajor:
+        hi, lo = torch.empty(r, c, **bf), torch.empty(r, c, **bf)
+    if transposed:
+        hi_t, lo_t = torch.empty(c, ld_t, **bf), torch.empty(c, ld_t, **bf)
+    if colsum:
+        sums = torch.empty(c, dtype=torch.float32, device=dev)
+    ws = workspace(size("etpgt_split_bf16_workspace_bytes", r, c) if colsum else 256, dev)
+    call("etpgt_split_bf16", ptr(src), r, c, c, ptr(hi), ptr(lo), c, ptr(hi_t), ptr(lo_t), ld_t, ptr(sums), ptr(ws),
+         ws.numel(), stream())
+    return hi, lo, hi_t, lo_t, ld_t, sums
+
+
+def _gemm_x3(a_hi, a_lo, b_hi, b_lo, m, n, k, lda, ldb, bias, split_k=1) -> torch.Tensor:
+    out = torch.empty(m, n, dtype=torch.float32, device=a_hi.device)
+    ws = workspace(size("etpgt_gemm_bf16x3_workspace_bytes", m, n, k, split_k), a_hi.device)
+    call("etpgt_gemm_bf16x3", ptr(a_hi), ptr(a_lo), ptr(b_hi), ptr(b_lo), m, n, k, lda, ldb, ptr(bias), ptr(out), n,
+         split_k, ptr(ws), ws.numel(), stream())
+    return out
+
+
+class LinearTensorCore(torch.autograd.Function):
+    """y = x @ W^T + b on the tcgen05 tensor cores with split-bf16 operands (fp32-grade accuracy,
+    etpgt_gemm_bf16x3).  Backward: dX and dW are the same kernel on transposed splits, db is the
+    column sum produced while splitting dY."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        _require_cuda(x, "node features")
+        x, weight = _f32(x), _f32(weight)
+        bias_c = _f32(bias) if bias is not None else None
+        n, k = x.shape
+        n_out = weight.size(0)
+        x_hi, x_lo, _, _, _, _ = _split(x, True, False)
+        w_hi, w_lo, _, _, _, _ = _split(weight, True, False)
+        y = _gemm_x3(x_hi, x_lo, w_hi, w_lo, n, n_out, k, k, k, bias_c)
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, d_y):
+        x, weight = ctx.saved_tensors
+        d_y = _f32(d_y)
+        n, k = x.shape
+        n_out = weight.size(0)
+        need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        g_hi, g_lo, g_hi_t, g_lo_t, ld_t, d_bias = _split(d_y, need_x, need_w, colsum=ctx.has_bias)
+        d_x = d_w = None
+        if need_x:
+            _, _, wt_hi, wt_lo, ld_w, _ = _split(weight, False, True)       # [k, n_out]: B of dX
+            d_x = _gemm_x3(g_hi, g_lo, wt_hi, wt_lo, n, k, n_out, n_out, ld_w, None)
+        if need_w:
+            _, _, xt_hi, xt_lo, ld_x, _ = _split(x, False, True)            # [k, nodes]: B of dW
+            d_w = _gemm_x3(g_hi_t, g_lo_t, xt_hi, xt_lo, n_out, k, n, ld_t, ld_x, None, split_k=0)
+        return d_x, d_w, d_bias
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None) -> torch.Tensor:
+    """Dense projection of the path.  Tensor-core split-bf16 GEMM when the shape allows it
+    (inner and outer widths multiples of 8), else a library fp32 GEMM."""
+    if PROJECTION_BACKEND == "tcgen05" and x.is_cuda and x.size(1) % 8 == 0 and weight.size(0) % 8 == 0 \
+            and x.size(0) > 0:
+        return LinearTensorCore.apply(x, weight, bias)
+    return torch.nn.functional.linear(x, weight, bias)
+
+
+import os as _os  # noqa: E402
+
+PROJECTION_BACKEND = _os.environ.get("ETPGT_PROJECTION", "tcgen05")
+
+
 # ------------------------------------------------------------------------------ GAT / GraphSAGE
 
 

@@ -142,6 +142,27 @@ int etpgt_tconv_bwd(const float* qkvs, const float* d_out, int64_t num_nodes, in
                     float* d_qkvs, float* d_w_beta,
                     void* ws, size_t ws_bytes, etpgt_stream_t stream);
 
+/* ---- a5 (dense part): node projections on the tensor cores, fp32-grade ("split-bf16 x3") ----
+ * Replaces the fp32 nn.Linear GEMMs of TransformerConv (lin_query/key/value/skip,
+ * graph_transformer.py:73-98,174).  x = hi + lo with hi = bf16(x), lo = bf16(x - hi);
+ * C = A_hi B_hi^T + A_hi B_lo^T + A_lo B_hi^T accumulated in fp32 in TMEM (tcgen05.mma), relative
+ * error ~1e-5.  Operands are K-major bf16: A [M,K] (pitch lda), B [N,K] (pitch ldb), pitches
+ * multiples of 8 elements; C fp32 [M,N] (pitch ldc); bias [N] or NULL.  a_lo == b_lo == NULL gives a
+ * plain bf16 GEMM.  split_k: 1 = none, 0 = automatic (few output tiles, long K), >1 = forced; the
+ * split-K partials are reduced in a fixed order (deterministic).
+ *
+ * split_bf16: src fp32 [rows, cols] (pitch ld_src) -> any of: hi/lo row-major [rows, cols] (pitch
+ * ld_out), hi_t/lo_t transposed [cols, rows] (pitch ld_t), colsum [cols] (fp32 column sums). */
+size_t etpgt_split_bf16_workspace_bytes(int64_t rows, int64_t cols);
+int etpgt_split_bf16(const float* src, int64_t rows, int64_t cols, int64_t ld_src,
+                     void* hi, void* lo, int64_t ld_out, void* hi_t, void* lo_t, int64_t ld_t,
+                     float* colsum, void* ws, size_t ws_bytes, etpgt_stream_t stream);
+size_t etpgt_gemm_bf16x3_workspace_bytes(int64_t m, int64_t n, int64_t k, int split_k);
+int etpgt_gemm_bf16x3(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,
+                      int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb,
+                      const float* bias, float* c, int64_t ldc, int split_k,
+                      void* ws, size_t ws_bytes, etpgt_stream_t stream);
+
 /* ---- a12: GAT edge-softmax aggregation and GraphSAGE mean aggregation ---------------------
  * PyG GATConv(add_self_loops=True) as used at etpgt/model/gat.py:49-109,137: h [N, width] with
  * width = heads*channels is the projected row, a_src/a_dst [N, heads] the attention scalars;

@@ -1,0 +1,65 @@
+"""GPU parity tests of the split-bf16 tcgen05 GEMM that carries the dense node projections:
+forward, both backward GEMMs (incl. deterministic split-K) and the bias gradient, against fp64."""
+
+import pytest
+import torch
+
+from golden_util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("m,k,n_out", [(300, 256, 1024), (128, 64, 128), (1, 256, 1024), (1000, 32, 128),
+                                        (4097, 256, 256), (130, 72, 40)])
+def test_linear_tensor_core_forward_backward(m, k, n_out):
+    import etpgt_b200.ops as ops
+
+    g = torch.Generator().manual_seed(m + k)
+    x = torch.randn(m, k, generator=g, dtype=torch.float64)
+    w = torch.randn(n_out, k, generator=g, dtype=torch.float64) / k ** 0.5
+    b = torch.randn(n_out, generator=g, dtype=torch.float64)
+    d_y = torch.randn(m, n_out, generator=g, dtype=torch.float64)
+    x64, w64, b64 = (t.clone().requires_grad_(True) for t in (x, w, b))
+    (x64 @ w64.t() + b64).backward(d_y)
+    xc, wc, bc = (t.float().cuda().requires_grad_(True) for t in (x, w, b))
+    y = ops.LinearTensorCore.apply(xc, wc, bc)
+    y.backward(d_y.float().cuda())
+    torch.cuda.synchronize()
+    assert rel_err(y, x @ w.t() + b) < 3e-5
+    assert rel_err(xc.grad, x64.grad) < 3e-5
+    assert rel_err(wc.grad, w64.grad) < 3e-5
+    assert rel_err(bc.grad, b64.grad) < 3e-5
+
+
+def test_split_k_is_deterministic_and_accurate():
+    import etpgt_b200.ops as ops
+
+    g = torch.Generator().manual_seed(2)
+    m, k, n_out = 20000, 256, 1024            # dW: K = 20000 nodes, 16 output tiles -> split-K
+    x = torch.randn(m, k, generator=g)
+    w = (torch.randn(n_out, k, generator=g) / 16).cuda().requires_grad_(True)
+    d_y = torch.randn(m, n_out, generator=g).cuda()
+    grads = []
+    for _ in range(2):
+        w.grad = None
+        ops.LinearTensorCore.apply(x.cuda(), w, None).backward(d_y)
+        grads.append(w.grad.clone())
+    assert torch.equal(grads[0], grads[1])
+    want = d_y.double().t() @ x.double().cuda()
+    assert rel_err(grads[0], want) < 3e-5
+
+
+def test_plain_bf16_gemm_and_split_parts():
+    import etpgt_b200.ops as ops
+
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(200, 128, generator=g).cuda()
+    w = torch.randn(256, 128, generator=g).cuda()
+    hi, lo, hi_t, lo_t, ld_t, sums = ops._split(x, True, True, colsum=True)
+    assert torch.equal(hi, x.to(torch.bfloat16))
+    assert torch.equal(lo, (x - hi.float()).to(torch.bfloat16))
+    assert torch.equal(hi_t[:, :200], hi.t()) and torch.equal(lo_t[:, :200], lo.t())
+    assert rel_err(sums, x.double().sum(0)) < 1e-5
+    w_hi = w.to(torch.bfloat16)
+    y = ops._gemm_x3(hi, None, w_hi, None, 200, 256, 128, 128, 128, None)
+    assert rel_err(y, hi.double() @ w_hi.double().t()) < 1e-5
