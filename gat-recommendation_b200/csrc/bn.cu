@@ -75,6 +75,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count
                                    float* __restrict__ running_mean, float* __restrict__ running_var) {
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= dim) return;
+  if (count <= 0) count = sums[2 * dim];  // global row count carried (and all-reduced) behind the sums
   const double mu = sums[d] / count;
   double var = sums[dim + d] / count - mu * mu;
   if (var < 0) var = 0;
@@ -134,7 +135,7 @@ bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ y, co
     if (training) {
       const float4 a = ldg4(x + 4 * i);
       const float4 mu = ld4(mean + c);
-      const float inv_n = (float)(1.0 / count);
+      const float inv_n = (float)(1.0 / (count > 0 ? count : sums[2 * dim]));
       const float gs[4] = {(float)sums[c] * inv_n, (float)sums[c + 1] * inv_n, (float)sums[c + 2] * inv_n,
                            (float)sums[c + 3] * inv_n};
       const float gx[4] = {(float)sums[dim + c] * inv_n, (float)sums[dim + c + 1] * inv_n,
@@ -195,7 +196,7 @@ extern "C" int etpgt_bn_stats(const float* x, int64_t n, int dim, double* sums, 
 
 extern "C" int etpgt_bn_finalize(const double* sums, double count, int dim, float eps, float momentum, float* mean,
                                  float* invstd, float* running_mean, float* running_var, etpgt_stream_t stream) {
-  ETPGT_REQUIRE(count >= 1 && dim > 0 && sums && mean && invstd, "bn_finalize: bad arguments");
+  ETPGT_REQUIRE((count >= 1 || count == 0) && dim > 0 && sums && mean && invstd, "bn_finalize: bad arguments");
   bn_finalize_kernel<<<(dim + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
       sums, count, dim, eps, momentum, mean, invstd, running_mean, running_var);
   ETPGT_CHECK_LAUNCH("bn_finalize");
@@ -239,7 +240,7 @@ extern "C" int etpgt_bn_bwd_apply(const float* x, const float* y, const float* d
                                   float* d_x, float* d_gamma, float* d_bias, etpgt_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ETPGT_REQUIRE(dim % 4 == 0 && dim >= 4, "bn_bwd_apply: dim %d must be a multiple of 4", dim);
-  ETPGT_REQUIRE(n >= 0 && d_y && mean && invstd && gamma && d_x && local_sums && (!training || (x && sums && count >= 1)),
+  ETPGT_REQUIRE(n >= 0 && d_y && mean && invstd && gamma && d_x && local_sums && (!training || (x && sums && (count >= 1 || count == 0))),
                 "bn_bwd_apply: bad arguments");
   if (n > 0) {
     const int64_t total4 = n * (dim / 4);

@@ -340,14 +340,16 @@ class BatchNormRows(torch.autograd.Function):
         invstd = torch.empty(dim, dtype=torch.float32, device=dev)
         count = float(n)
         if training:
-            sums = torch.empty(2 * dim, dtype=torch.float64, device=dev)
+            # [sum x | sum x^2 | row count]: under data parallelism the whole vector is all-reduced and
+            # the kernels read the GLOBAL count from its tail (count argument 0) — no host round trip
+            sums = torch.empty(2 * dim + 1, dtype=torch.float64, device=dev)
             ws = workspace(size("etpgt_bn_workspace_bytes", n, dim), dev)
             call("etpgt_bn_stats", ptr(x), n, dim, ptr(sums), ptr(ws), ws.numel(), stream())
             if _dist_ready(group):
-                packed = torch.cat([sums, torch.tensor([count], dtype=torch.float64, device=dev)])
-                dist.all_reduce(packed, group=group or None)
-                sums, count = packed[:-1].contiguous(), float(packed[-1].item())
-            if count < 2:
+                sums[2 * dim:].fill_(count)
+                dist.all_reduce(sums, group=group or None)
+                count = 0.0
+            elif count < 2:
                 raise ValueError("Expected more than 1 value per channel when training")
             call("etpgt_bn_finalize", ptr(sums), count, dim, float(eps), float(momentum), ptr(mean), ptr(invstd),
                  ptr(running_mean), ptr(running_var), stream())
@@ -368,14 +370,15 @@ class BatchNormRows(torch.autograd.Function):
         d_y = _f32(d_y)
         n, dim = x.shape
         dev = x.device
-        local = torch.empty(2 * dim, dtype=torch.float64, device=dev)
+        local = torch.empty(2 * dim + 1, dtype=torch.float64, device=dev)
         ws = workspace(size("etpgt_bn_workspace_bytes", n, dim), dev)
         call("etpgt_bn_bwd_stats", ptr(x), ptr(y), ptr(d_y), n, dim, ptr(mean), ptr(invstd), int(relu), ptr(local),
              ptr(ws), ws.numel(), stream())
         sums = local
         if training and _dist_ready(group):
+            local[2 * dim:].fill_(float(n))
             sums = local.clone()
-            dist.all_reduce(sums, group=group or None)
+            dist.all_reduce(sums, group=group or None)   # count == 0.0: read from the reduced tail
         d_x = torch.empty_like(x)
         d_gamma = torch.empty(dim, dtype=torch.float32, device=dev)
         d_bias = torch.empty(dim, dtype=torch.float32, device=dev)
