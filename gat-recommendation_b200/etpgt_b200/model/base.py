@@ -22,6 +22,7 @@ class BaseRecommendationModel(nn.Module, ABC):
         self.item_embedding = nn.Embedding(num_items, embedding_dim, padding_idx=0)
         nn.init.xavier_uniform_(self.item_embedding.weight[1:])
         self.bn_process_group = None  # set by the data-parallel wrapper
+        self.score_precision = "auto"  # "auto" | "fp32" | "bf16" for predict()
 
     @abstractmethod
     def forward(self, batch):
@@ -33,7 +34,13 @@ class BaseRecommendationModel(nn.Module, ABC):
     def predict(self, session_embeddings: torch.Tensor, k: int = 20) -> torch.Tensor:
         """Top-k item ids per session by dot product against the whole table; the [B, I] score
         matrix is never materialised (fused scoring + top-k kernel)."""
-        _, top = ops.score_topk(session_embeddings, self.get_item_embeddings(), k)
+        precision = self.score_precision
+        if precision == "auto":
+            # small batches: fp32 CUDA-core scorer (the reference's arithmetic); evaluation-sized batches:
+            # tcgen05 bf16 scorer (BASELINE.json: bf16 GEMM within 1e-2, ties to the lower id)
+            big = session_embeddings.size(0) >= 64
+            precision = "bf16" if big and ops.tensor_core_scoring_supported(session_embeddings.size(1), k) else "fp32"
+        _, top = ops.score_topk(session_embeddings, self.get_item_embeddings(), k, precision=precision)
         return top
 
     def compute_loss(self, session_embeddings, target_items, negative_items) -> torch.Tensor:

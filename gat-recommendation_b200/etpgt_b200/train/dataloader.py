@@ -1,0 +1,84 @@
+"""GPU-resident replacement of the reference data loader with the same entry point
+(`create_dataloader(sessions_path, graph_edges_path, batch_size, num_negatives, max_session_length,
+shuffle, num_workers)`, etpgt/train/dataloader.py:205-241).
+
+The reference re-scans the 738k-row edge frame with pandas for every sample and remaps edges in a
+Python loop; here the two CSVs are read ONCE into device arrays (`data.ItemGraph`, `data.SessionStore`)
+and every batch — session subgraphs, PyG-collate layout, targets, Philox negatives — is produced by
+device kernels (`etpgt_session_subgraphs_*`, `etpgt_sample_negatives`).  Iterating yields objects with
+the attributes of the PyG `Batch` the reference trainer consumes (`x, edge_index, batch, ptr,
+target_item, negative_items [B*num_neg], num_graphs`), already on the GPU.
+"""
+
+from __future__ import annotations
+
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from .. import data
+
+
+def load_sessions(sessions_path) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """train.csv / val.csv (columns session_id, timestamp, itemid, ...) -> (session ids in the
+    reference's group order, ptr, items ordered by timestamp inside a session) — dataloader.py:35-40,78-82."""
+    import pandas as pd
+
+    df = pd.read_csv(sessions_path, usecols=["session_id", "timestamp", "itemid"])
+    df = df.sort_values(["session_id", "timestamp"], kind="stable")
+    ids, counts = np.unique(df["session_id"].to_numpy(), return_counts=True)
+    ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    return ids, ptr, df["itemid"].to_numpy().astype(np.int64)
+
+
+class DeviceSessionLoader:
+    """Iterable over GPU-built batches; `len()` = number of batches, `.num_items` as the reference dataset."""
+
+    def __init__(self, sessions_path, graph_edges_path, batch_size=32, num_negatives=5, max_session_length=50,
+                 shuffle=True, seed=0, device="cuda", symmetrize=False, self_loop_if_empty=False,
+                 flatten_negatives=True):
+        import pandas as pd
+
+        self.session_ids, ptr, items = load_sessions(Path(sessions_path))
+        edges = pd.read_csv(graph_edges_path, usecols=["item_i", "item_j"])
+        item_i, item_j = edges["item_i"].to_numpy(), edges["item_j"].to_numpy()
+        # dataloader.py:50-58
+        self.num_items = int(max(items.max(initial=0), item_i.max(initial=0), item_j.max(initial=0))) + 1
+        self.graph = data.ItemGraph(item_i, item_j, self.num_items, device)
+        self.sessions = data.SessionStore(ptr, items, device)
+        self.batch_size, self.num_negatives, self.max_session_length = batch_size, num_negatives, max_session_length
+        self.shuffle, self.seed, self.epoch, self.step = shuffle, seed, 0, 0
+        self.symmetrize, self.self_loop_if_empty = symmetrize, self_loop_if_empty
+        self.flatten_negatives = flatten_negatives
+        self.device = device
+
+    def __len__(self) -> int:
+        return (self.sessions.num_sessions + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self):
+        n = self.sessions.num_sessions
+        if self.shuffle:
+            g = torch.Generator().manual_seed(self.seed + self.epoch)
+            order = torch.randperm(n, generator=g).to(self.device)
+        else:
+            order = torch.arange(n, device=self.device)
+        self.epoch += 1
+        for start in range(0, n, self.batch_size):
+            ids = order[start:start + self.batch_size]
+            batch = data.build_batch(self.graph, self.sessions, ids, self.max_session_length, self.symmetrize,
+                                     self.self_loop_if_empty)
+            neg = data.sample_negatives(self.sessions, ids, self.num_items, self.num_negatives, self.seed, self.step,
+                                        max_len=self.max_session_length)
+            # PyG collate concatenates the per-sample [num_neg] tensors (trainer.py:87-89 reshapes them back)
+            batch.negative_items = neg.reshape(-1) if self.flatten_negatives else neg
+            self.step += 1
+            yield batch
+
+
+def create_dataloader(sessions_path, graph_edges_path, batch_size: int = 32, num_negatives: int = 5,
+                      max_session_length: int = 50, shuffle: bool = True, num_workers: int = 0) -> DeviceSessionLoader:
+    """Same signature as the reference; `num_workers` is accepted and ignored (no host workers: the batch
+    is built on the device)."""
+    del num_workers
+    return DeviceSessionLoader(sessions_path, graph_edges_path, batch_size, num_negatives, max_session_length, shuffle)

@@ -131,3 +131,42 @@ def test_device_batch_trains_end_to_end():
     loss_b.backward()
     assert loss.item() == loss_b.item()
     assert torch.equal(grad_a, model.item_embedding.weight.grad)
+
+
+def test_create_dataloader_reads_reference_csvs(tmp_path):
+    """The reference's on-disk formats (train.csv / graph_edges.csv) -> device batches identical to what
+    the reference SessionDataset + collate_fn produced for the same files (golden fixture)."""
+    import csv
+
+    from etpgt_b200.train.dataloader import create_dataloader
+
+    g = Golden("dataloader")
+    ptr = g.raw["sess_ptr"]
+    with open(tmp_path / "train.csv", "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(["timestamp", "visitorid", "event", "itemid", "transactionid", "session_id"])
+        for s in range(len(ptr) - 1):
+            for t, it in enumerate(g.raw["sess_items"][ptr[s]:ptr[s + 1]]):
+                w.writerow([1000 * s + t, s, "view", int(it), "", s])
+    with open(tmp_path / "graph_edges.csv", "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(["item_i", "item_j", "count", "last_ts", "event_pair_hist"])
+        for i, j in zip(g.raw["item_i"], g.raw["item_j"]):
+            w.writerow([int(i), int(j), 1, 0, "{}"])
+    loader = create_dataloader(tmp_path / "train.csv", tmp_path / "graph_edges.csv", batch_size=40, shuffle=False)
+    assert loader.num_items == int(g.raw["num_items"]) and len(loader) == 1
+    (batch,) = list(loader)
+    assert np.array_equal(batch.x.cpu().numpy(), g.raw["x"])
+    assert np.array_equal(batch.edge_index.cpu().numpy(), g.raw["edge_index"])
+    assert np.array_equal(batch.batch.cpu().numpy(), g.raw["batch"])
+    assert np.array_equal(batch.target_item.cpu().numpy(), g.raw["target"])
+    neg = batch.negative_items.view(40, 5).cpu().numpy()          # trainer.py:87-89
+    for s in range(40):
+        assert not set(neg[s]) & set(g.raw["sess_items"][ptr[s]:ptr[s + 1]][-50:]) and neg[s].min() >= 1
+    # smaller batches partition the same sessions, shuffled epochs differ
+    small = create_dataloader(tmp_path / "train.csv", tmp_path / "graph_edges.csv", batch_size=16, shuffle=True)
+    assert len(small) == 3
+    first = [b.target_item.cpu() for b in small]
+    second = [b.target_item.cpu() for b in small]
+    assert sorted(torch.cat(first).tolist()) == sorted(g.raw["target"].tolist())
+    assert not torch.equal(torch.cat(first), torch.cat(second))

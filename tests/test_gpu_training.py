@@ -1,0 +1,101 @@
+"""GPU parity at the training-loop level: several optimizer steps of the B200 path against the CPU
+oracle from the same initial state, on the two entry-point configurations of the reference
+(BASELINE.json configs[0] = run_full_pipeline: D=64, symmetrised edges, ListwiseLoss, Adam;
+configs[1] = train_baseline: D=256, directed edges, BPR, AdamW), then Recall@10 parity."""
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_state(model):
+    state = {k: (v.detach().double().cpu().clone() if v.is_floating_point() else v.cpu().clone())
+             for k, v in model.state_dict().items()}
+    pe = getattr(getattr(model, "laplacian_pe", None), "_cached_pe", None)
+    if pe is not None:
+        state["laplacian_pe._cached_pe"] = pe.double().cpu()
+    return state
+
+
+def _run(dim, symmetrize, loss_kind, opt_name, use_pe, steps=4, sessions=96):
+    from etpgt_b200 import data, synth
+    from etpgt_b200.model import create_graph_transformer_optimized
+    from etpgt_b200.train.losses import create_loss_function
+    from oracle import model_ref
+
+    d = synth.generate(num_sessions=1200, graph_sessions=900, num_items=400, clusters=16, seed=5)
+    graph = data.ItemGraph(d.item_i, d.item_j, d.num_items)
+    store = data.SessionStore(d.sess_ptr, d.sess_items)
+    torch.manual_seed(1)
+    model = create_graph_transformer_optimized(d.num_items, dim, dim, num_layers=2, num_heads=2, dropout=0.0,
+                                               use_laplacian_pe=use_pe).cuda()
+    if use_pe:
+        model.laplacian_pe._cached_pe = torch.randn(d.num_items, 16, generator=torch.Generator().manual_seed(7)).abs().cuda()
+    state = _oracle_state(model)
+    names = [k for k in state if state[k].is_floating_point() and "running" not in k and "_cached_pe" not in k]
+    for k in names:
+        state[k].requires_grad_(True)
+    make_opt = (lambda ps: torch.optim.Adam(ps, lr=1e-3)) if opt_name == "adam" else \
+               (lambda ps: torch.optim.AdamW(ps, lr=1e-3, weight_decay=1e-5))
+    opt_gpu, opt_cpu = make_opt(model.parameters()), make_opt([state[k] for k in names])
+    loss_fn = create_loss_function(loss_kind)
+    model.train()
+    for step in range(steps):
+        ids = np.arange(step * sessions, (step + 1) * sessions)
+        batch = data.build_batch(graph, store, ids, 50, symmetrize, symmetrize)
+        neg = data.sample_negatives(store, ids, d.num_items, 5, seed=3, step=step)
+        out = loss_fn(model(batch), batch.target_item, neg, model.item_embedding)
+        loss = out[0] if isinstance(out, tuple) else out
+        opt_gpu.zero_grad()
+        loss.backward()
+        opt_gpu.step()
+        # oracle step on the same batch and negatives
+        sess, _, stats = model_ref.graph_transformer_forward(
+            state, batch.x.cpu(), batch.edge_index.cpu(), batch.batch.cpu(), num_layers=2, num_heads=2,
+            training=True, return_nodes=True)
+        table = state["item_embedding.weight"]
+        want = {"bpr": lambda: model_ref.bpr_loss(sess, table, batch.target_item.cpu(), neg.cpu()),
+                "listwise": lambda: model_ref.listwise_loss(sess, table, batch.target_item.cpu(), neg.cpu())}[loss_kind]()
+        opt_cpu.zero_grad()
+        want.backward()
+        state["item_embedding.weight"].grad[0] = 0          # padding_idx row (nn.Embedding semantics)
+        opt_cpu.step()
+        with torch.no_grad():
+            state["item_embedding.weight"][0] = 0
+            for k, v in stats.items():
+                state[k] = v.detach()
+        assert abs(loss.item() - want.item()) < 2e-4 * abs(want.item()), (step, loss.item(), want.item())
+    # after training: evaluation outputs and Recall@10 / top-k still agree.  (Adam divides by |g|, so
+    # elements whose gradient is at rounding-noise level — e.g. the key bias, analytically zero — take
+    # steps of different sign on the two paths; the comparison is therefore on outputs, not raw weights.)
+    model.eval()
+    ids = np.arange(900, 1100)
+    batch = data.build_batch(graph, store, ids, 50, symmetrize, symmetrize)
+    with torch.no_grad():
+        sess_gpu = model(batch)
+        model.score_precision = "fp32"
+        top_gpu = model.predict(sess_gpu, k=10).cpu()
+        model.score_precision = "bf16"          # tensor-core scorer: Recall@10 within 0.1 pt as well
+        top_tc = model.predict(sess_gpu, k=10).cpu()
+    sess_cpu = model_ref.graph_transformer_forward(
+        {k: v.detach() for k, v in state.items()}, batch.x.cpu(), batch.edge_index.cpu(), batch.batch.cpu(),
+        num_layers=2, num_heads=2, training=False)
+    assert (sess_gpu.double().cpu() - sess_cpu).abs().max() <= 2e-3 * sess_cpu.abs().max()
+    _, top_cpu = model_ref.predict(sess_cpu, state["item_embedding.weight"].detach(), 10)
+    recall_gpu = model_ref.recall_at_k(top_gpu, batch.target_item.cpu(), 10)
+    recall_cpu = model_ref.recall_at_k(top_cpu, batch.target_item.cpu(), 10)
+    assert abs(recall_gpu - recall_cpu) <= 0.001 + 1e-9          # BASELINE.json: within 0.1 pt
+    if dim % 64 == 0:
+        recall_tc = model_ref.recall_at_k(top_tc, batch.target_item.cpu(), 10)
+        assert abs(recall_tc - recall_cpu) <= 0.005 + 1e-9       # 200 sessions: one flipped session = 0.5 pt
+    assert (top_gpu == top_cpu).float().mean() > 0.97
+
+
+def test_run_full_pipeline_configuration():
+    _run(dim=64, symmetrize=True, loss_kind="listwise", opt_name="adam", use_pe=False)
+
+
+def test_train_baseline_configuration():
+    _run(dim=256, symmetrize=False, loss_kind="bpr", opt_name="adamw", use_pe=True)
