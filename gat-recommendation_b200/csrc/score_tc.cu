@@ -1,17 +1,31 @@
 // a9: full-catalogue scoring on the 5th-generation tensor cores with a fused top-k epilogue.
 //   scores[b, i] = <S[b, :], E[i, :]>  (bf16 operands, fp32 accumulation in TMEM), top-k per row
 // etpgt/model/base.py:59-78 (`torch.matmul(S, E.t())` + `torch.topk`).  The [B, I] score matrix is
-// never written: the epilogue warps read each 128 x 256 accumulator tile straight out of TMEM and
-// keep per-row k-lists; only [B, parts, k] candidates leave the SM, merged by etpgt_topk_merge.
+// never written.
 //
-// Structure (one CTA = one unit of 128 sessions x a contiguous range of 256-item tiles):
+// GEMM kernel (one CTA = 128 sessions x a contiguous range of 256-item tiles):
 //   warp 0      TMA producer: session tile once (DIM/64 k-blocks of 128x64 bf16, SWIZZLE_128B), then
 //               a ring of item k-blocks (256x64 bf16) with mbarrier full/empty hand-shakes
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128x256x16, kind::f16),
 //               accumulators double-buffered in the 512 TMEM columns
-//   warps 2-5   epilogue, one warp per TMEM lane quarter: tcgen05.ld 32x32b.x32 (lane = session row),
-//               threshold-pruned candidates, register-resident sorted k-list per row
-// Tensor-bound: 2*128*256*DIM flop per tile against DIM/16 MMA instructions of 128 cycles each.
+//   warps 2-5   epilogue, one warp per TMEM lane quarter (lane = session row)
+//
+// Epilogue = "chunk dump".  Measured on B200: with an epilogue that only loads TMEM and takes
+// maxima the pipeline runs at 84 % of the cuBLAS bf16 peak; every form of per-item candidate
+// handling inside the loop (shared-memory k-lists: 3 %, pending buffers: 23 %, register lists with
+// warp-uniform scans: 30 %) was bound by SIMT divergence — the 32 rows of a warp accept candidates
+// at different columns, so each accepted item costs the whole warp an insert.  So the loop keeps,
+// per row, only the K best 32-column CHUNK MAXIMA in a register-resident sorting network (values
+// only, branch-free, all lanes in lockstep), and a lane whose chunk maximum beats its row's
+// threshold dumps that chunk's 32 raw scores (one full 128-byte line) to a per-(row, range) slot
+// buffer in HBM.  K chunk maxima >= thr prove K items >= thr, so thr is a valid lower bound of the
+// row's K-th best score and no chunk holding a top-K item is ever skipped (chunks arrive in
+// ascending id order and the test is a strict '>', so ties keep the lower id).  About
+// K*ln(chunks/K) ~ 100 chunks (12 KB) per row are dumped.
+//
+// Select kernel (one warp per row): filters the dumped scores against the best range threshold and
+// picks the exact top-k by (score desc, id asc).  Rows whose slot buffer overflowed (adversarial
+// score orders) are recomputed exactly by a CUDA-core fallback kernel, so the result is always exact.
 #include <math.h>
 #include <stdlib.h>
 
@@ -24,12 +38,14 @@ using namespace tc;
 
 constexpr int BLOCK_M = 128;   // sessions per CTA (TMEM lanes)
 constexpr int BLOCK_N = 256;   // items per accumulator tile (TMEM columns)
+constexpr int CHUNK = 32;      // columns per tcgen05.ld and per dumped line
 constexpr int kMaxStages = 3;  // ring of item k-blocks
 constexpr int kAccStages = 2;  // TMEM accumulator double buffer
 constexpr int kTmemCols = 512;
 constexpr int kEpilogueWarps = 4;
 constexpr int kThreads = 32 * (2 + kEpilogueWarps);
 constexpr int kMaxKTc = 32;
+constexpr int kPendingMerge = 8;  // chunk maxima a row may have waiting before the warp merges
 constexpr uint32_t A_KBLOCK_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr uint32_t B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;   // 32 KB
 constexpr uint32_t kInstrDesc = instr_desc_bf16(BLOCK_M, BLOCK_N);
@@ -43,91 +59,62 @@ struct __align__(8) Barriers {
   uint32_t tmem_base;
 };
 
-// Per-row candidate list, REGISTER resident and sorted (score desc; equal scores keep arrival =
-// ascending id order), KCAP >= k entries; the row's threshold is the last entry.
-//
-// Inserting straight from the scan would serialise the warp: the 32 rows of a warp accept
-// candidates at different columns, and every accept would drag the whole warp through the insert
-// (first version, shared-memory lists with a k-step rescan per accept: 21 ms for 23,861 x 82,174,
-// 3 % of the tensor peak; pending buffers: 2.6 ms; the rescan's dependent shared-memory loads
-// were still the largest cost).  Now a candidate that beats the row's (possibly stale) threshold
-// is only APPENDED to a small pending buffer in shared memory, and the pending buffers of all 32
-// rows are merged into the register lists together, in lockstep, by a branch-free insertion
-// (compare, then shift everything behind the insertion point) when one of them is about to fill
-// up or the range ends.  The threshold only ever rises, so a stale one admits extra candidates but
-// never loses one; arrival order is ascending id, so strict '>' keeps the lower id on ties.
-constexpr int kPendingCap = 40;  // a whole 32-column chunk always fits after the overflow check
-constexpr int kScanBlock = 4;    // columns per second-level maximum
+// Dump buffers, per (row, range): `cap` slots of 32 scores + the chunk's first column (relative to the
+// range), a slot count (may exceed cap = overflow) and the range's final threshold.
+struct DumpBuffers {
+  float* scores;      // [rows*splits][cap][32]
+  int32_t* chunk_col; // [rows*splits][cap]
+  int32_t* count;     // [rows*splits]
+  float* threshold;   // [rows*splits]
+  int cap;
+};
 
-template <int KCAP>
-struct RowList {
-  float lv[KCAP];
-  int32_t li[KCAP];
-  float* pend_vals;
-  int32_t* pend_idxs;
-  int pending;
-  float thr;
-  __device__ __forceinline__ void init(float* pv, int32_t* pi) {
-    pend_vals = pv; pend_idxs = pi; pending = 0; thr = -INFINITY;
-#pragma unroll
-    for (int t = 0; t < KCAP; ++t) { lv[t] = -INFINITY; li[t] = INT32_MAX; }
+// Work units.  One CTA per SM and one long range per row is the cheapest (every range pays a warm-up
+// while its thresholds rise from -inf), but the number of 128-row tiles is rarely a multiple of 148.
+// So the first `m_full` row tiles (whole waves) each scan the WHOLE catalogue as one unit, and only
+// the remaining row tiles are cut into `tail_splits` item ranges to fill the last wave.
+struct Schedule {
+  int m_full;           // row tiles with a single full-catalogue unit (a multiple of 148, may be 0)
+  int tail_splits;      // item ranges per remaining row tile
+  int tiles_per_split;  // 256-item tiles per tail range
+  int total_tiles;
+  __host__ __device__ int64_t full_rows() const { return (int64_t)m_full * BLOCK_M; }
+  __host__ __device__ int parts_of_row(int64_t row) const { return row < full_rows() ? 1 : tail_splits; }
+  // index of (row, part) in the count / threshold arrays; x cap in the slot arrays
+  __host__ __device__ int64_t part_index(int64_t row, int part) const {
+    return row < full_rows() ? row : full_rows() + (row - full_rows()) * tail_splits + part;
   }
-  __device__ __forceinline__ void append(float v, int32_t id) {
-    pend_vals[pending * BLOCK_M] = v;
-    pend_idxs[pending * BLOCK_M] = id;
-    ++pending;
-  }
-  __device__ __forceinline__ void insert(float v, int32_t id) {
-    bool shifting = false;
-#pragma unroll
-    for (int t = 0; t < KCAP; ++t) {
-      shifting = shifting || v > lv[t];
-      const float ov = lv[t];
-      const int32_t oi = li[t];
-      lv[t] = shifting ? v : ov;
-      li[t] = shifting ? id : oi;
-      v = shifting ? ov : v;
-      id = shifting ? oi : id;
-    }
-    thr = lv[KCAP - 1];
-  }
-  // all 32 lanes of the warp call this together
-  __device__ __forceinline__ void flush() {
-    int most = pending;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) most = max(most, __shfl_xor_sync(0xffffffffu, most, off));
-    for (int p = 0; p < most; ++p) {
-      const bool on = p < pending;
-      const float v = on ? pend_vals[p * BLOCK_M] : -INFINITY;   // -inf never beats any entry
-      const int32_t id = on ? pend_idxs[p * BLOCK_M] : INT32_MAX;
-      insert(v, id);
-    }
-    pending = 0;
+  __host__ __device__ int first_tile(int64_t row, int part) const { return row < full_rows() ? 0 : part * tiles_per_split; }
+  __host__ __device__ int64_t num_parts(int64_t batch) const {
+    const int64_t f = batch < full_rows() ? batch : full_rows();
+    return f + (batch - f) * tail_splits;
   }
 };
 
-template <int NUM_KB, int KCAP>  // DIM / 64, list capacity
+template <int NUM_KB, int KCAP>  // DIM / 64, number of chunk maxima tracked (>= k)
 __global__ void __launch_bounds__(kThreads, 1)
-score_topk_tc_kernel(const __grid_constant__ CUtensorMap map_sess, const __grid_constant__ CUtensorMap map_items,
-                     int64_t batch, int64_t num_items, int k, int stages_and_flags, int tiles_per_split, int splits,
-                     int64_t id_base, float* __restrict__ cand_val, int64_t* __restrict__ cand_idx) {
-  const int stages = stages_and_flags & 255;
-  const bool debug_skip_scan = (stages_and_flags & 256) != 0;
+score_dump_tc_kernel(const __grid_constant__ CUtensorMap map_sess, const __grid_constant__ CUtensorMap map_items,
+                     int64_t batch, int64_t num_items, int stages, Schedule sch, DumpBuffers dump) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;                                   // NUM_KB x 16 KB
   uint8_t* smem_b = smem_a + NUM_KB * A_KBLOCK_BYTES;       // stages x 32 KB
-  float* pend_vals = reinterpret_cast<float*>(smem_b + stages * B_STAGE_BYTES);   // [cap][128]
-  int32_t* pend_idxs = reinterpret_cast<int32_t*>(pend_vals + kPendingCap * BLOCK_M);
-  Barriers* bars = reinterpret_cast<Barriers*>(pend_idxs + kPendingCap * BLOCK_M);
+  float* pend_max = reinterpret_cast<float*>(smem_b + stages * B_STAGE_BYTES);  // [kPendingMerge][128]
+  Barriers* bars = reinterpret_cast<Barriers*>(pend_max + kPendingMerge * BLOCK_M);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int split = blockIdx.x;
-  const int m_tile = blockIdx.y;
-  const int64_t total_tiles = (num_items + BLOCK_N - 1) / BLOCK_N;
-  const int64_t tile_begin = (int64_t)split * tiles_per_split;
-  const int64_t tile_end = tile_begin + tiles_per_split < total_tiles ? tile_begin + tiles_per_split : total_tiles;
+  int m_tile, part;
+  int64_t tile_begin, tile_end;
+  if ((int)blockIdx.x < sch.m_full) {
+    m_tile = blockIdx.x; part = 0; tile_begin = 0; tile_end = sch.total_tiles;
+  } else {
+    const int v = blockIdx.x - sch.m_full;
+    m_tile = sch.m_full + v / sch.tail_splits;
+    part = v % sch.tail_splits;
+    tile_begin = (int64_t)part * sch.tiles_per_split;
+    tile_end = tile_begin + sch.tiles_per_split < sch.total_tiles ? tile_begin + sch.tiles_per_split : sch.total_tiles;
+  }
   const int num_tiles = tile_end > tile_begin ? (int)(tile_end - tile_begin) : 0;
 
   if (threadIdx.x == 0) {
@@ -196,50 +183,74 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap map_sess, const __grid_
     // ===================== epilogue: 4 warps, TMEM lane quarter = warp % 4 =====================
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;       // session row inside the tile == TMEM lane
-    RowList<KCAP> list;
-    list.init(pend_vals + row, pend_idxs + row);
+    const int64_t grow = (int64_t)m_tile * BLOCK_M + row;
+    const bool live = grow < batch;
+    const int64_t pidx = live ? sch.part_index(grow, part) : 0;
+    const int64_t slot0 = pidx * (int64_t)dump.cap;
+    float* my_scores = dump.scores + slot0 * CHUNK;
+    int32_t* my_cols = dump.chunk_col + slot0;
+    float best[KCAP];   // the KCAP largest chunk maxima of this row so far, descending
+#pragma unroll
+    for (int t = 0; t < KCAP; ++t) best[t] = -INFINITY;
+    float thr = -INFINITY;
+    int count = 0, pending = 0;
+    float* my_pending = pend_max + row;  // [kPendingMerge][128], row fastest
     for (int t = 0; t < num_tiles; ++t) {
       const int acc = t & 1;
       const uint32_t acc_phase = (uint32_t)(t >> 1) & 1;
       mbar_wait(&bars->acc_full[acc], acc_phase);
       tc_fence_after();
       const int64_t item0 = (tile_begin + t) * BLOCK_N;
-      const int base = t * BLOCK_N;  // id relative to the first item of this CTA's range
       const int limit = num_items - item0 < BLOCK_N ? (int)(num_items - item0) : BLOCK_N;  // real columns
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-        float v[32];
+      for (int c0 = 0; c0 < BLOCK_N; c0 += CHUNK) {
+        float v[CHUNK];
         {
-          uint32_t raw[32];
+          uint32_t raw[CHUNK];
           tmem_ld_32x32(taddr + (uint32_t)c0, raw);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+          for (int j = 0; j < CHUNK; ++j) v[j] = __uint_as_float(raw[j]);
         }
-        if (limit - c0 < 32) {  // only the table's last tile: columns past the end never qualify
+        if (limit - c0 < CHUNK) {  // only the table's last tile: columns past the end never qualify
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = c0 + j < limit ? v[j] : -INFINITY;
+          for (int j = 0; j < CHUNK; ++j) v[j] = c0 + j < limit ? v[j] : -INFINITY;
         }
-        // two-level maximum; every branch below is warp-uniform (votes), the appends are predicated,
-        // so the scan costs no divergence and the warp only touches the 4-column blocks that hold a
-        // candidate of some row
-        float gmax[32 / kScanBlock];
+        float g[8];
 #pragma unroll
-        for (int g = 0; g < 32 / kScanBlock; ++g)
-          gmax[g] = fmaxf(fmaxf(v[4 * g], v[4 * g + 1]), fmaxf(v[4 * g + 2], v[4 * g + 3]));
-        const float mx = fmaxf(fmaxf(fmaxf(gmax[0], gmax[1]), fmaxf(gmax[2], gmax[3])),
-                               fmaxf(fmaxf(gmax[4], gmax[5]), fmaxf(gmax[6], gmax[7])));
-        if (debug_skip_scan) { if (mx == 123456.75f) list.thr = mx; continue; }  // profiling only (ETPGT_SCORE_DEBUG=1): garbage results
-        if (__any_sync(0xffffffffu, mx > list.thr)) {
-          if (__any_sync(0xffffffffu, list.pending > kPendingCap - 32)) list.flush();  // room for a whole chunk
-          const float thr = list.thr;
+        for (int q = 0; q < 8; ++q) g[q] = fmaxf(fmaxf(v[4 * q], v[4 * q + 1]), fmaxf(v[4 * q + 2], v[4 * q + 3]));
+        const float mx = fmaxf(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])), fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7])));
+        const bool hit = live && mx > thr;
+        if (__any_sync(0xffffffffu, hit)) {  // warp-uniform
+          if (hit) {
+            if (count < dump.cap) {
+              float4* dst = reinterpret_cast<float4*>(my_scores + (int64_t)count * CHUNK);
 #pragma unroll
-          for (int g = 0; g < 32 / kScanBlock; ++g) {
-            if (__any_sync(0xffffffffu, gmax[g] > thr)) {
-#pragma unroll
-              for (int j = g * kScanBlock; j < (g + 1) * kScanBlock; ++j)
-                if (v[j] > thr) list.append(v[j], base + c0 + j);
+              for (int q = 0; q < 8; ++q) __stcs(dst + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+              my_cols[count] = t * BLOCK_N + c0;
             }
+            ++count;
+            my_pending[pending * BLOCK_M] = mx;  // the maximum waits here for the next lockstep merge
+            ++pending;
+          }
+          // Merge the pending chunk maxima of all 32 rows into the sorted lists TOGETHER: one pass of
+          // the sorting network then serves up to 32 rows at once (run per hit it would serve ~1).  The
+          // threshold is a little stale in between, which only dumps a few extra chunks.
+          if (__any_sync(0xffffffffu, pending >= kPendingMerge)) {
+            int most = pending;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) most = max(most, __shfl_xor_sync(0xffffffffu, most, off));
+            for (int p = 0; p < most; ++p) {
+              float x = p < pending ? my_pending[p * BLOCK_M] : -INFINITY;  // -inf passes through unchanged
+#pragma unroll
+              for (int s = 0; s < KCAP; ++s) {
+                const float hi = fmaxf(best[s], x);
+                x = fminf(best[s], x);
+                best[s] = hi;
+              }
+            }
+            pending = 0;
+            thr = best[KCAP - 1];
           }
         }
       }
@@ -247,17 +258,9 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap map_sess, const __grid_
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
     }
-    list.flush();
-    const int64_t grow = (int64_t)m_tile * BLOCK_M + row;
-    if (grow < batch) {
-      const int64_t o = (grow * splits + split) * k;
-#pragma unroll
-      for (int t = 0; t < KCAP; ++t) {
-        if (t < k) {
-          cand_val[o + t] = list.li[t] == INT32_MAX ? -INFINITY : list.lv[t];
-          cand_idx[o + t] = list.li[t] == INT32_MAX ? INT64_MAX : id_base + tile_begin * BLOCK_N + list.li[t];
-        }
-      }
+    if (live) {
+      dump.count[pidx] = count;
+      dump.threshold[pidx] = thr;
     }
   }
   tc_fence_before();
@@ -265,6 +268,163 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap map_sess, const __grid_
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+__device__ __forceinline__ bool better(float v, int64_t i, float bv, int64_t bi) {
+  return v > bv || (v == bv && i < bi);
+}
+
+// One warp per row.  Survivors (scores >= the best range threshold) are collected in shared memory,
+// then k selection passes pick the best remaining candidate by (score desc, id asc).
+constexpr int kSelectWarps = 4;
+constexpr int kSurvivorCap = 512;
+
+__global__ void __launch_bounds__(kSelectWarps * 32)
+score_select_kernel(DumpBuffers dump, int64_t batch, Schedule sch, int k, int64_t id_base,
+                    float* __restrict__ top_val, int64_t* __restrict__ top_idx, int32_t* __restrict__ redo) {
+  __shared__ float s_val[kSelectWarps][kSurvivorCap];
+  __shared__ int32_t s_idx[kSelectWarps][kSurvivorCap];
+  __shared__ int s_count[kSelectWarps];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = blockIdx.x * (int64_t)kSelectWarps + w;
+  if (row >= batch) return;
+  if (lane == 0) s_count[w] = 0;
+  float tau = -INFINITY;
+  bool overflow = false;
+  const int splits = sch.parts_of_row(row);
+  for (int s = 0; s < splits; ++s) {
+    tau = fmaxf(tau, dump.threshold[sch.part_index(row, s)]);
+    overflow = overflow || dump.count[sch.part_index(row, s)] > dump.cap;
+  }
+  __syncwarp();
+  if (!overflow) {
+    for (int s = 0; s < splits; ++s) {
+      const int n = dump.count[sch.part_index(row, s)];
+      const int64_t slot0 = sch.part_index(row, s) * (int64_t)dump.cap;
+      const int range_col0 = sch.first_tile(row, s) * BLOCK_N;
+      // lane j owns column j of every dumped chunk: one coalesced 128-byte line per chunk, eight
+      // independent loads in flight
+      const float* base = dump.scores + slot0 * CHUNK + lane;
+      for (int c0 = 0; c0 < n; c0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = c0 + u < n ? __ldcs(base + (int64_t)(c0 + u) * CHUNK) : -INFINITY;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (v[u] >= tau && v[u] > -INFINITY) {  // -inf marks columns past the end of the table
+            const int pos = atomicAdd(&s_count[w], 1);
+            if (pos < kSurvivorCap) {
+              s_val[w][pos] = v[u];
+              s_idx[w][pos] = range_col0 + dump.chunk_col[slot0 + c0 + u] + lane;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+    overflow = s_count[w] > kSurvivorCap;  // a huge tie at the threshold
+  }
+  if (overflow) {
+    if (lane == 0) redo[row] = 1;
+    return;
+  }
+  if (lane == 0) redo[row] = 0;
+  const int n = s_count[w];
+  float prev_v = INFINITY;
+  int64_t prev_i = -1;
+  for (int t = 0; t < k; ++t) {
+    float bv = -INFINITY;
+    int64_t bi = INT64_MAX;
+    for (int c = lane; c < n; c += 32) {
+      const float v = s_val[w][c];
+      const int64_t i = s_idx[w][c];
+      const bool after_prev = v < prev_v || (v == prev_v && i > prev_i);
+      if (after_prev && better(v, i, bv, bi)) { bv = v; bi = i; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+      const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, off);
+      if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) {
+      top_val[row * k + t] = bv;
+      top_idx[row * k + t] = bi == INT64_MAX ? INT64_MAX : id_base + bi;
+    }
+    prev_v = bv;
+    prev_i = bi;
+  }
+}
+
+// Exact CUDA-core recomputation of the rows flagged in `redo` (slot-buffer or tie overflow): one CTA
+// per row, every thread scores a strided share of the items (fp32 accumulation of the same bf16
+// operands) and keeps a private sorted k-list; lists are merged through shared memory.
+constexpr int kRedoThreads = 256;
+
+__global__ void __launch_bounds__(kRedoThreads)
+score_redo_kernel(const __nv_bfloat16* __restrict__ sess, const __nv_bfloat16* __restrict__ table, int64_t batch,
+                  int64_t num_items, int dim, int k, int64_t id_base, const int32_t* __restrict__ redo,
+                  float* __restrict__ top_val, int64_t* __restrict__ top_idx) {
+  const int64_t row = blockIdx.x;
+  if (row >= batch || redo[row] == 0) return;
+  extern __shared__ float redo_smem[];       // session row [dim], then lists
+  float* s_row = redo_smem;
+  float* l_val = redo_smem + dim;            // [kRedoThreads][k]
+  int32_t* l_idx = reinterpret_cast<int32_t*>(l_val + kRedoThreads * k);
+  for (int d = threadIdx.x; d < dim; d += kRedoThreads) s_row[d] = __bfloat162float(sess[row * dim + d]);
+  float* mv = l_val + threadIdx.x * k;
+  int32_t* mi = l_idx + threadIdx.x * k;
+  for (int t = 0; t < k; ++t) { mv[t] = -INFINITY; mi[t] = INT32_MAX; }
+  __syncthreads();
+  for (int64_t item = threadIdx.x; item < num_items; item += kRedoThreads) {
+    const __nv_bfloat16* e = table + item * dim;
+    float acc = 0.f;
+    for (int d = 0; d < dim; d += 2) {
+      const float2 p = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(e + d));
+      acc = fmaf(s_row[d], p.x, acc);
+      acc = fmaf(s_row[d + 1], p.y, acc);
+    }
+    if (acc > mv[k - 1]) {  // ascending ids per thread: strict '>' keeps the lower id
+      int t = k - 1;
+      while (t > 0 && mv[t - 1] < acc) { mv[t] = mv[t - 1]; mi[t] = mi[t - 1]; --t; }
+      mv[t] = acc;
+      mi[t] = (int32_t)item;
+    }
+  }
+  __syncthreads();
+  // k selection passes over the kRedoThreads*k candidates by (score desc, id asc)
+  __shared__ float r_val[kRedoThreads / 32];
+  __shared__ int32_t r_idx[kRedoThreads / 32];
+  float prev_v = INFINITY;
+  int32_t prev_i = -1;
+  for (int t = 0; t < k; ++t) {
+    float bv = -INFINITY;
+    int32_t bi = INT32_MAX;
+    for (int c = threadIdx.x; c < kRedoThreads * k; c += kRedoThreads) {
+      const float v = l_val[c];
+      const int32_t i = l_idx[c];
+      const bool after_prev = v < prev_v || (v == prev_v && i > prev_i);
+      if (after_prev && (v > bv || (v == bv && i < bi))) { bv = v; bi = i; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+      const int32_t oi = __shfl_xor_sync(0xffffffffu, bi, off);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { r_val[threadIdx.x >> 5] = bv; r_idx[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    bv = r_val[0]; bi = r_idx[0];
+    for (int q = 1; q < kRedoThreads / 32; ++q)
+      if (r_val[q] > bv || (r_val[q] == bv && r_idx[q] < bi)) { bv = r_val[q]; bi = r_idx[q]; }
+    if (threadIdx.x == 0) {
+      top_val[row * k + t] = bv;
+      top_idx[row * k + t] = bi == INT32_MAX ? INT64_MAX : id_base + bi;
+    }
+    prev_v = bv;
+    prev_i = bi;
+    __syncthreads();
   }
 }
 
@@ -280,42 +440,60 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16*
 }
 
 struct TcPlan {
-  int m_tiles, splits, tiles_per_split;
+  Schedule sch;
+  int grid;
+  int cap;
 };
 
-TcPlan tc_plan(int64_t batch, int64_t num_items) {
+TcPlan tc_plan(int64_t batch, int64_t num_items, int k) {
   TcPlan p;
-  p.m_tiles = (int)((batch + BLOCK_M - 1) / BLOCK_M);
-  const int64_t total_tiles = (num_items + BLOCK_N - 1) / BLOCK_N;
-  // One CTA per SM.  Pick the number of item-range splits whose CTA count fills whole waves of the
-  // 148 SMs well, charging each extra split for its per-range warm-up (lists restart empty).
-  int64_t max_splits = total_tiles / 8 > 1 ? total_tiles / 8 : 1;
+  const int m_tiles = (int)((batch + BLOCK_M - 1) / BLOCK_M);
+  const int total_tiles = (int)((num_items + BLOCK_N - 1) / BLOCK_N);
+  // tail ranges stay >= 64 tiles (512 chunks) so that every range's own threshold is tight enough for
+  // the select kernel's survivor buffer
+  int max_splits = total_tiles / 64 > 1 ? total_tiles / 64 : 1;
   if (max_splits > 32) max_splits = 32;
-  int best = 1;
-  double best_score = -1.0;
-  for (int64_t s = 1; s <= max_splits; ++s) {
-    const int64_t per = (total_tiles + s - 1) / s;
-    const int64_t real = (total_tiles + per - 1) / per;
-    const int64_t ctas = real * p.m_tiles;
-    const int64_t waves = (ctas + kNumSMs - 1) / kNumSMs;
-    double eff = (double)ctas / (double)(waves * kNumSMs);
-    const double score = eff - 0.03 * (double)s;
-    if (score > best_score) { best_score = score; best = (int)s; }
+  const int m_full = (m_tiles / kNumSMs) * kNumSMs;   // whole waves: one full-catalogue unit per row tile
+  const int tail = m_tiles - m_full;
+  int splits = 1;
+  if (tail > 0) {
+    // cost model fitted on B200: time ~ waves * (range length + a warm-up worth ~half a full range)
+    double best_cost = 1e30;
+    for (int s = 1; s <= max_splits; ++s) {
+      const int per = (total_tiles + s - 1) / s;
+      const int real = (total_tiles + per - 1) / per;
+      const int waves = (real * tail + kNumSMs - 1) / kNumSMs;
+      const double cost = (double)waves * ((double)per / (double)total_tiles + 0.5);
+      if (cost < best_cost - 1e-9) { best_cost = cost; splits = s; }
+    }
+    if (const char* forced = getenv("ETPGT_SCORE_SPLITS")) {  // tuning knob
+      const int f = atoi(forced);
+      if (f >= 1 && f <= max_splits) splits = f;
+    }
   }
-  if (const char* forced = getenv("ETPGT_SCORE_SPLITS")) {  // tuning knob
+  p.sch.m_full = m_full;
+  p.sch.total_tiles = total_tiles;
+  p.sch.tiles_per_split = (total_tiles + splits - 1) / splits;
+  p.sch.tail_splits = (total_tiles + p.sch.tiles_per_split - 1) / p.sch.tiles_per_split;
+  p.grid = m_full + tail * p.sch.tail_splits;
+  // slots per (row, range): ~ K*(1 + ln(chunks/K)) chunks are expected; 1.6x head-room (sized for the
+  // longest range), overflow is handled exactly by the fallback kernel
+  const double chunks = (double)(m_full > 0 ? total_tiles : p.sch.tiles_per_split) * (BLOCK_N / CHUNK);
+  const int kc = k <= 10 ? 10 : k <= 20 ? 20 : 32;
+  double expect = kc * (1.0 + (chunks > kc ? log(chunks / kc) : 0.0));
+  int cap = (int)(1.6 * expect) + 8;
+  if (cap > (int)chunks) cap = (int)chunks;
+  if (const char* forced = getenv("ETPGT_SCORE_CAP")) {  // test hook: force slot-buffer overflow
     const int f = atoi(forced);
-    if (f >= 1 && f <= max_splits) best = f;
+    if (f >= 1) cap = f;
   }
-  p.tiles_per_split = (int)((total_tiles + best - 1) / best);
-  p.splits = (int)((total_tiles + p.tiles_per_split - 1) / p.tiles_per_split);
+  p.cap = cap < 1 ? 1 : cap;
   return p;
 }
 
-int tc_stages(int, int) { return kMaxStages; }
-
-size_t tc_smem_bytes(int num_kb, int, int stages) {
+size_t tc_smem_bytes(int num_kb, int stages) {
   return 1024 + (size_t)num_kb * A_KBLOCK_BYTES + (size_t)stages * B_STAGE_BYTES +
-         (size_t)kPendingCap * BLOCK_M * 8 + sizeof(Barriers) + 64;
+         (size_t)kPendingMerge * BLOCK_M * sizeof(float) + sizeof(Barriers) + 64;
 }
 
 }  // namespace
@@ -334,9 +512,10 @@ extern "C" int etpgt_f32_to_bf16(const float* src, void* dst, int64_t n, etpgt_s
 
 extern "C" size_t etpgt_score_topk_bf16_workspace_bytes(int64_t batch, int64_t num_items, int k) {
   if (batch <= 0 || num_items <= 0 || k <= 0) return 256;
-  const TcPlan p = tc_plan(batch, num_items);
-  const size_t m = (size_t)batch * p.splits * k;
-  return align_up(m * sizeof(float)) + align_up(m * sizeof(int64_t)) + 256;
+  const TcPlan p = tc_plan(batch, num_items, k);
+  const size_t units = (size_t)p.sch.num_parts(batch);
+  return align_up(units * p.cap * CHUNK * sizeof(float)) + align_up(units * p.cap * sizeof(int32_t)) +
+         2 * align_up(units * sizeof(float)) + 2 * align_up((size_t)batch * sizeof(int32_t)) + 256;
 }
 
 extern "C" int etpgt_score_topk_bf16(const void* sess_bf16, const void* table_bf16, int64_t batch,
@@ -355,11 +534,16 @@ extern "C" int etpgt_score_topk_bf16(const void* sess_bf16, const void* table_bf
     return ETPGT_EWORKSPACE;
   }
   if (batch == 0) return ETPGT_OK;
-  const TcPlan p = tc_plan(batch, num_items);
+  const TcPlan p = tc_plan(batch, num_items, k);
   Workspace w(ws, ws_bytes);
-  const size_t m = (size_t)batch * p.splits * k;
-  float* cand_val = w.take<float>(m);
-  int64_t* cand_idx = w.take<int64_t>(m);
+  const size_t units = (size_t)p.sch.num_parts(batch);
+  DumpBuffers dump;
+  dump.scores = w.take<float>(units * p.cap * CHUNK);
+  dump.chunk_col = w.take<int32_t>(units * p.cap);
+  dump.count = w.take<int32_t>(units);
+  dump.threshold = w.take<float>(units);
+  dump.cap = p.cap;
+  int32_t* redo = w.take<int32_t>(batch);
   CUtensorMap map_sess, map_items;
   if (!make_map_bf16(&map_sess, sess_bf16, batch, dim, dim, BLOCK_M) ||
       !make_map_bf16(&map_items, table_bf16, num_items, dim, dim, BLOCK_N)) {
@@ -367,15 +551,14 @@ extern "C" int etpgt_score_topk_bf16(const void* sess_bf16, const void* table_bf
     return ETPGT_ECUDA;
   }
   const int num_kb = dim / BLOCK_K;
-  const int stages = tc_stages(num_kb, k);
-  const size_t smem = tc_smem_bytes(num_kb, k, stages);
-  const dim3 grid(p.splits, p.m_tiles);
+  const int stages = kMaxStages;
+  const size_t smem = tc_smem_bytes(num_kb, stages);
+  const dim3 grid(p.grid);
 #define LAUNCH2(NKB, KC)                                                                                        \
   {                                                                                                             \
-    cudaFuncSetAttribute(score_topk_tc_kernel<NKB, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    score_topk_tc_kernel<NKB, KC><<<grid, kThreads, smem, stream>>>(map_sess, map_items, batch, num_items, k, stages | (getenv("ETPGT_SCORE_DEBUG") ? 256 : 0), \
-                                                                   p.tiles_per_split, p.splits, id_base, cand_val, \
-                                                                   cand_idx);                                   \
+    cudaFuncSetAttribute(score_dump_tc_kernel<NKB, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    score_dump_tc_kernel<NKB, KC><<<grid, kThreads, smem, stream>>>(map_sess, map_items, batch, num_items, stages, \
+                                                                   p.sch, dump);                               \
   }
 #define LAUNCH(NKB)                    \
   {                                    \
@@ -391,6 +574,16 @@ extern "C" int etpgt_score_topk_bf16(const void* sess_bf16, const void* table_bf
   }
 #undef LAUNCH
 #undef LAUNCH2
-  ETPGT_CHECK_LAUNCH("score_topk_tc");
-  return etpgt_topk_merge(cand_val, cand_idx, batch, p.splits, k, top_val, top_idx, stream_);
+  ETPGT_CHECK_LAUNCH("score_dump_tc");
+  score_select_kernel<<<(unsigned)((batch + kSelectWarps - 1) / kSelectWarps), kSelectWarps * 32, 0, stream>>>(
+      dump, batch, p.sch, k, id_base, top_val, top_idx, redo);
+  ETPGT_CHECK_LAUNCH("score_select");
+  const size_t redo_smem = ((size_t)dim + (size_t)kRedoThreads * k * 2) * sizeof(float);
+  if (redo_smem > 48 * 1024)
+    cudaFuncSetAttribute(score_redo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)redo_smem);
+  score_redo_kernel<<<(unsigned)batch, kRedoThreads, redo_smem, stream>>>(
+      static_cast<const __nv_bfloat16*>(sess_bf16), static_cast<const __nv_bfloat16*>(table_bf16), batch, num_items,
+      dim, k, id_base, redo, top_val, top_idx);
+  ETPGT_CHECK_LAUNCH("score_redo");
+  return ETPGT_OK;
 }

@@ -59,6 +59,29 @@ def test_score_topk_tensor_core_exact_ties():
     assert torch.equal(f32_i.cpu(), want_i)
 
 
+def test_score_topk_tensor_core_overflow_fallback(monkeypatch):
+    """Adversarial score order (every chunk beats the running threshold) and a forced tiny slot buffer:
+    the overflowed rows are recomputed exactly by the CUDA-core fallback kernel."""
+    import etpgt_b200.ops as ops
+
+    g = torch.Generator().manual_seed(3)
+    # scores increase with the item id for the first 100 rows -> every chunk is a new maximum
+    sess = torch.randint(1, 3, (150, 64), generator=g).float()
+    sess[100:] = torch.randint(-2, 3, (50, 64), generator=g).float()
+    table = torch.randint(0, 2, (9000, 64), generator=g).float()
+    table[:, 0] = (torch.arange(9000) // 64).float()          # slowly growing column 0 (exact in bf16)
+    want_v, want_i = _oracle(sess, table, 20)
+    got_v, got_i = ops.score_topk(sess.cuda(), table.cuda(), 20, precision="bf16")
+    assert torch.equal(got_i.cpu(), want_i) and torch.equal(got_v.cpu().double(), want_v)
+    monkeypatch.setenv("ETPGT_SCORE_CAP", "2")       # every row overflows its slot buffer
+    g2 = torch.Generator().manual_seed(4)
+    sess2 = torch.randint(-2, 3, (70, 128), generator=g2).float()
+    table2 = torch.randint(-1, 2, (5000, 128), generator=g2).float()
+    want_v2, want_i2 = _oracle(sess2, table2, 20)
+    got_v2, got_i2 = ops.score_topk(sess2.cuda(), table2.cuda(), 20, precision="bf16")
+    assert torch.equal(got_i2.cpu(), want_i2) and torch.equal(got_v2.cpu().double(), want_v2)
+
+
 def test_bf16_conversion_matches_torch():
     import etpgt_b200.ops as ops
 
