@@ -337,7 +337,7 @@ def run_b200(args, rank, world_size, local_rank):
     }
     if rank == 0:
         out["scoring"] = scoring_roofline(model, device)
-        out["roofline"] = tconv_roofline(model, dev_batches[0], device)
+        out["roofline"] = tconv_roofline(model, dev_batches[0], data, device)
         out["edges_per_s_tconv_fwd_bwd"] = out["roofline"].pop("edges_per_s")
         if world_size == 1 and not args.skip_cpu_baseline:
             steps = 2
@@ -380,21 +380,12 @@ def scoring_roofline(model, device, sessions=23_861, k=20, reps=5):
             "sessions_per_s": sessions / (ms / 1e3)}
 
 
-def tconv_roofline(model, batch, device, reps=20):
-    """Times the fused TransformerConv forward and backward kernels alone (CUDA events on the
-    launching stream, L2 flushed between repetitions) on the step's own layer-0 tensors."""
-    from etpgt_b200 import _lib, ops
+def time_tconv(qkvs, w_beta, index, device, reps=20):
+    """Average CUDA-event time (ms) of the fused TransformerConv forward and backward launches on
+    torch's current stream, L2 flushed between repetitions."""
     from etpgt_b200._lib import call, ptr, size, stream, workspace
 
-    pk = peaks()
-    index = ops.graph_index_of(batch, batch.edge_index, batch.x.numel())
     n, e = index.num_nodes, index.num_edges
-    with torch.no_grad():
-        x = ops.EmbedPE.apply(batch.x, model.item_embedding.weight, model.laplacian_pe.cached(), False,
-                              model.laplacian_pe.projection.weight, model.laplacian_pe.projection.bias, 0)
-        conv = model.convs[0]
-        qkvs = conv.project(x).contiguous()
-        w_beta = conv.lin_beta.weight.detach().reshape(-1).contiguous()
     f32 = dict(dtype=torch.float32, device=device)
     out, agg = torch.empty(n, DIM, **f32), torch.empty(n, DIM, **f32)
     beta, m, inv_l = torch.empty(n, **f32), torch.empty(n, HEADS, **f32), torch.empty(n, HEADS, **f32)
@@ -425,16 +416,60 @@ def tconv_roofline(model, batch, device, reps=20):
             total += a.elapsed_time(b)
         return total / reps
 
-    ms_f, ms_b = time_fn(fwd), time_fn(bwd)
+    return time_fn(fwd), time_fn(bwd)
+
+
+def tconv_bytes(n, e):
+    """Algorithmic bytes of one layer, fp32, D=256."""
     s = 4
-    bytes_f = e * (2 * DIM * s + 4) + n * (4 * DIM * s + HEADS * 8 + 4)
-    bytes_b = e * (4 * DIM * s + 8 + HEADS * 16 + 8) + n * (10 * DIM * s)
+    fwd = e * (2 * DIM * s + 4) + n * (4 * DIM * s + HEADS * 8 + 4)
+    bwd = e * (4 * DIM * s + 8 + HEADS * 16 + 8) + n * (10 * DIM * s)
+    return fwd, bwd
+
+
+def tconv_roofline(model, batch, data, device):
+    """The dominant edge-kernel group timed alone: (a) on the step's own layer-0 tensors (session batch:
+    millions of tiny segments) and (b) on the whole symmetrised co-occurrence graph as ONE graph (power-law
+    rows; the notebook's "whole graph as one session" case)."""
+    from etpgt_b200 import ops
+
+    pk = peaks()
+    index = ops.graph_index_of(batch, batch.edge_index, batch.x.numel())
+    n, e = index.num_nodes, index.num_edges
+    conv = model.convs[0]
+    with torch.no_grad():
+        x = ops.EmbedPE.apply(batch.x, model.item_embedding.weight, model.laplacian_pe.cached(), False,
+                              model.laplacian_pe.projection.weight, model.laplacian_pe.projection.bias, 0)
+        qkvs = conv.project(x).contiguous()
+        w_beta = conv.lin_beta.weight.detach().reshape(-1).contiguous()
+    ms_f, ms_b = time_tconv(qkvs, w_beta, index, device)
+    bytes_f, bytes_b = tconv_bytes(n, e)
     achieved = (bytes_f + bytes_b) / ((ms_f + ms_b) / 1e3) / 1e9
-    return {"bound": "hbm", "kernel": "tconv_fwd + tconv_bwd_dst + tconv_bwd_src (layer 0)",
-            "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-            "peak_source": pk["source"], "traffic": None, "ms_fwd": ms_f, "ms_bwd": ms_b,
-            "gbs_fwd": bytes_f / (ms_f / 1e3) / 1e9, "gbs_bwd": bytes_b / (ms_b / 1e3) / 1e9,
-            "nodes": n, "edges": e, "edges_per_s": e / ((ms_f + ms_b) / 1e3)}
+    traffic = None
+    tfile = ROOT / "profiles" / "tconv_traffic.json"   # dram bytes per launch from the committed ncu capture
+    if tfile.exists():
+        t = json.loads(tfile.read_text())
+        if t.get("nodes") == n and t.get("edges") == e:
+            traffic = t["dram_bytes_fwd_bwd"]
+    out = {"bound": "hbm", "kernel": "tconv_fwd + tconv_bwd_dst + tconv_bwd_src (layer 0, session batch)",
+           "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
+           "peak_source": pk["source"], "traffic": traffic, "ms_fwd": ms_f, "ms_bwd": ms_b,
+           "gbs_fwd": bytes_f / (ms_f / 1e3) / 1e9, "gbs_bwd": bytes_b / (ms_b / 1e3) / 1e9,
+           "nodes": n, "edges": e, "edges_per_s": e / ((ms_f + ms_b) / 1e3)}
+    # (b) the whole graph, both directions of every stored pair
+    src = torch.from_numpy(np.concatenate([data.item_i, data.item_j])).to(device)
+    dst = torch.from_numpy(np.concatenate([data.item_j, data.item_i])).to(device)
+    gindex = ops.GraphIndex(torch.stack([src, dst]), data.num_items)
+    with torch.no_grad():
+        gq = conv.project(model.item_embedding.weight.detach()).contiguous()
+    gf, gb = time_tconv(gq, w_beta, gindex, device, reps=10)
+    gbf, gbb = tconv_bytes(gindex.num_nodes, gindex.num_edges)
+    g_ach = (gbf + gbb) / ((gf + gb) / 1e3) / 1e9
+    out["global_graph"] = {"nodes": gindex.num_nodes, "edges": gindex.num_edges, "ms_fwd": gf, "ms_bwd": gb,
+                           "achieved": g_ach, "frac": g_ach / pk["hbm_gbs"],
+                           "edges_per_s_fwd": gindex.num_edges / (gf / 1e3),
+                           "edges_per_s_fwd_bwd": gindex.num_edges / ((gf + gb) / 1e3)}
+    return out
 
 
 def main():

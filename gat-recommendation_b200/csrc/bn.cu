@@ -62,12 +62,16 @@ __global__ void bn_partial_kernel(const float* __restrict__ x, const float* __re
   }
 }
 
+// one warp per output column: lanes stride over the per-CTA partials, fixed butterfly -> deterministic
 __global__ void bn_reduce_kernel(const double* __restrict__ partial, int parts, int width, double* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (i >= width) return;
   double s = 0;
-  for (int p = 0; p < parts; ++p) s += partial[(int64_t)p * width + i];
-  out[i] = s;
+  for (int p = lane; p < parts; p += 32) s += partial[(int64_t)p * width + i];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (lane == 0) out[i] = s;
 }
 
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, int dim, float eps,
@@ -172,7 +176,7 @@ int launch_partial(const float* x, const float* y, const float* d_y, int64_t n, 
   const size_t smem = (size_t)ty * 2 * dim * sizeof(double);
   bn_partial_kernel<MODE><<<parts, dim3(tx, ty), smem, stream>>>(x, y, d_y, n, dim, mean, invstd, relu, chunk, partial);
   ETPGT_CHECK_LAUNCH("bn_partial");
-  bn_reduce_kernel<<<(2 * dim + 255) / 256, 256, 0, stream>>>(partial, parts, 2 * dim, sums);
+  bn_reduce_kernel<<<(2 * dim * 32 + 255) / 256, 256, 0, stream>>>(partial, parts, 2 * dim, sums);
   ETPGT_CHECK_LAUNCH("bn_reduce");
   return ETPGT_OK;
 }

@@ -96,10 +96,14 @@ pe_wgrad_partial_kernel(const int64_t* __restrict__ ids, int64_t n, const float*
 
 __global__ void pe_wgrad_reduce_kernel(const float* __restrict__ partial, int parts, int dim, int kpe,
                                        float* __restrict__ d_w, float* __restrict__ d_b) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over dim*(kpe+1)
+  // one warp per output (dim*(kpe+1) of them): fixed lane striding + butterfly -> deterministic
+  const int lane = threadIdx.x & 31;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (i >= dim * (kpe + 1)) return;
   float s = 0.f;
-  for (int p = 0; p < parts; ++p) s += partial[(int64_t)p * dim * (kpe + 1) + i];
+  for (int p = lane; p < parts; p += 32) s += partial[(int64_t)p * dim * (kpe + 1) + i];
+  s = group_sum<32>(s);
+  if (lane != 0) return;
   const int d = i / (kpe + 1), k = i % (kpe + 1);
   if (k == kpe) d_b[d] = s; else d_w[d * kpe + k] = s;
 }
@@ -178,7 +182,7 @@ extern "C" int etpgt_embed_pe_bwd(const int64_t* ids, int64_t n, const float* d_
 #undef CALL_K
   ETPGT_CHECK_LAUNCH("pe_wgrad_partial");
   const int total = dim * (k_pe + 1);
-  pe_wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, stream>>>(partial, parts, dim, k_pe, d_w_pe, d_b_pe);
+  pe_wgrad_reduce_kernel<<<(total * 32 + 255) / 256, 256, 0, stream>>>(partial, parts, dim, k_pe, d_w_pe, d_b_pe);
   ETPGT_CHECK_LAUNCH("pe_wgrad_reduce");
   return ETPGT_OK;
 }

@@ -29,8 +29,8 @@ __device__ __forceinline__ void load_row(const float* __restrict__ row, int lig,
 }
 
 // ------------------------------------------------------------------------------- forward
-template <int DIM, int HEAD_DIM>
-__global__ void __launch_bounds__(kThreads)
+template <int DIM, int HEAD_DIM, int UNROLL>
+__global__ void __launch_bounds__(kThreads, UNROLL <= 2 ? 3 : 2)
 tconv_fwd_kernel(const float* __restrict__ qkvs, int64_t num_nodes, const int32_t* __restrict__ rowptr,
                  const int32_t* __restrict__ col, const int32_t* __restrict__ eperm,
                  const float* __restrict__ w_beta, const float* __restrict__ alpha_mask,
@@ -63,11 +63,11 @@ tconv_fwd_kernel(const float* __restrict__ qkvs, int64_t num_nodes, const int32_
 #pragma unroll
   for (int v = 0; v < V; ++v) { m[v] = -INFINITY; l[v] = 0.f; acc[v] = zero4(); }
 
-  for (int e0 = 0; e0 < deg_max; e0 += kEdgeUnroll) {
-    float4 kr[kEdgeUnroll][V], vr[kEdgeUnroll][V];
-    int pos[kEdgeUnroll];
+  for (int e0 = 0; e0 < deg_max; e0 += UNROLL) {
+    float4 kr[UNROLL][V], vr[UNROLL][V];
+    int pos[UNROLL];
 #pragma unroll
-    for (int u = 0; u < kEdgeUnroll; ++u) {
+    for (int u = 0; u < UNROLL; ++u) {
       const bool on = e0 + u < deg;
       pos[u] = on ? begin + e0 + u : -1;
       const int64_t j = on ? col[pos[u]] : nrow;
@@ -76,7 +76,7 @@ tconv_fwd_kernel(const float* __restrict__ qkvs, int64_t num_nodes, const int32_
       load_row<DIM>(other + 2 * DIM, lig, vr[u]);
     }
 #pragma unroll
-    for (int u = 0; u < kEdgeUnroll; ++u) {
+    for (int u = 0; u < UNROLL; ++u) {
       float a[V];
 #pragma unroll
       for (int v = 0; v < V; ++v) a[v] = dot4(q[v], kr[u][v]);
@@ -138,8 +138,8 @@ tconv_fwd_kernel(const float* __restrict__ qkvs, int64_t num_nodes, const int32_
 // then over in-edges: alpha (recomputed from saved m, 1/l), d_alpha = <d_agg, v_j>_h,
 // d_logit = alpha (d_alpha*mask - delta), d_query += scale*d_logit*k_j.  Emits per-edge
 // (alpha*mask, scale*d_logit) for the source pass.
-template <int DIM, int HEAD_DIM>
-__global__ void __launch_bounds__(kThreads)
+template <int DIM, int HEAD_DIM, int UNROLL>
+__global__ void __launch_bounds__(kThreads, 2)
 tconv_bwd_dst_kernel(const float* __restrict__ qkvs, const float* __restrict__ d_out, int64_t num_nodes,
                      const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                      const int32_t* __restrict__ eperm, const float* __restrict__ w_beta,
@@ -158,9 +158,9 @@ tconv_bwd_dst_kernel(const float* __restrict__ qkvs, const float* __restrict__ d
   const int warp_in_cta = threadIdx.x >> 5;
   const int64_t nodes_per_cta = (kThreads / 32) * G::GROUPS;
 
-  float4 dw1[V], dw2[V], dw3[V];
+  float4 dw1[V], dw2[V];  // sum dz*agg, sum dz*skip; the third block is their difference
 #pragma unroll
-  for (int v = 0; v < V; ++v) { dw1[v] = zero4(); dw2[v] = zero4(); dw3[v] = zero4(); }
+  for (int v = 0; v < V; ++v) { dw1[v] = zero4(); dw2[v] = zero4(); }
 
   for (int64_t base = blockIdx.x * nodes_per_cta; base < num_nodes; base += (int64_t)gridDim.x * nodes_per_cta) {
     const int64_t warp_base = base + warp_in_cta * G::GROUPS;
@@ -191,7 +191,7 @@ tconv_bwd_dst_kernel(const float* __restrict__ qkvs, const float* __restrict__ d
           st4(d_qkvs + nrow * 4 * DIM + 3 * DIM + 4 * f, dxr);
           dw1[v] = fma4(dz, ag[v], dw1[v]);
           dw2[v] = fma4(dz, xr[v], dw2[v]);
-          dw3[v] = fma4(dz, sub4(ag[v], xr[v]), dw3[v]);
+
         }
       }
     } else {
@@ -221,11 +221,11 @@ tconv_bwd_dst_kernel(const float* __restrict__ qkvs, const float* __restrict__ d
 #pragma unroll
     for (int v = 0; v < V; ++v) dq[v] = zero4();
 
-    for (int e0 = 0; e0 < deg_max; e0 += kEdgeUnroll) {
-      float4 kr[kEdgeUnroll][V], vr[kEdgeUnroll][V];
-      int pos[kEdgeUnroll];
+    for (int e0 = 0; e0 < deg_max; e0 += UNROLL) {
+      float4 kr[UNROLL][V], vr[UNROLL][V];
+      int pos[UNROLL];
 #pragma unroll
-      for (int u = 0; u < kEdgeUnroll; ++u) {
+      for (int u = 0; u < UNROLL; ++u) {
         const bool on = e0 + u < deg;
         pos[u] = on ? begin + e0 + u : -1;
         const int64_t j = on ? col[pos[u]] : nrow;
@@ -234,7 +234,7 @@ tconv_bwd_dst_kernel(const float* __restrict__ qkvs, const float* __restrict__ d
         load_row<DIM>(other + 2 * DIM, lig, vr[u]);
       }
 #pragma unroll
-      for (int u = 0; u < kEdgeUnroll; ++u) {
+      for (int u = 0; u < UNROLL; ++u) {
         float a[V], da[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) { a[v] = dot4(q[v], kr[u][v]); da[v] = dot4(dag[v], vr[u][v]); }
@@ -270,7 +270,7 @@ tconv_bwd_dst_kernel(const float* __restrict__ qkvs, const float* __restrict__ d
       const int f = v * LPN + lig;
       st4(mine + 4 * f, dw1[v]);
       st4(mine + DIM + 4 * f, dw2[v]);
-      st4(mine + 2 * DIM + 4 * f, dw3[v]);
+      st4(mine + 2 * DIM + 4 * f, sub4(dw1[v], dw2[v]));
     }
     __syncthreads();
     constexpr int NG = (kThreads / 32) * G::GROUPS;
@@ -284,11 +284,14 @@ tconv_bwd_dst_kernel(const float* __restrict__ qkvs, const float* __restrict__ d
 
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, int parts, int width,
                                        float* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per output: lanes stride over the per-CTA partials, fixed butterfly -> deterministic
+  const int lane = threadIdx.x & 31;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (i >= width) return;
   float s = 0.f;
-  for (int p = 0; p < parts; ++p) s += partial[(int64_t)p * width + i];
-  out[i] = s;
+  for (int p = lane; p < parts; p += 32) s += partial[(int64_t)p * width + i];
+  s = group_sum<32>(s);
+  if (lane == 0) out[i] = s;
 }
 
 // ------------------------------------------------------------------ backward, source pass
@@ -362,12 +365,17 @@ extern "C" int etpgt_tconv_fwd(const float* qkvs, int64_t num_nodes, int dim, in
   ETPGT_REQUIRE(num_edges == 0 || (col && eperm), "tconv_fwd: null edge arrays");
   ETPGT_REQUIRE(w_beta == nullptr || beta != nullptr, "tconv_fwd: beta output required with w_beta");
   if (num_nodes == 0) return ETPGT_OK;
+  const bool sparse = num_edges < 8 * num_nodes;  // session batches: short rows -> shallower unroll, more warps
 #define CALL(D, C)                                                                               \
   {                                                                                              \
     const int64_t npc = (kThreads / 32) * RowGeom<D>::GROUPS;                                    \
     const int64_t grid = (num_nodes + npc - 1) / npc;                                            \
-    tconv_fwd_kernel<D, C><<<(unsigned)grid, kThreads, 0, stream>>>(qkvs, num_nodes, rowptr, col, eperm, w_beta, \
-                                                                   alpha_mask, out, agg, beta, m, inv_l); \
+    if (sparse)                                                                                  \
+      tconv_fwd_kernel<D, C, 2><<<(unsigned)grid, kThreads, 0, stream>>>(qkvs, num_nodes, rowptr, col, eperm,   \
+                                                                        w_beta, alpha_mask, out, agg, beta, m, inv_l); \
+    else                                                                                         \
+      tconv_fwd_kernel<D, C, 4><<<(unsigned)grid, kThreads, 0, stream>>>(qkvs, num_nodes, rowptr, col, eperm,   \
+                                                                        w_beta, alpha_mask, out, agg, beta, m, inv_l); \
   }
   ETPGT_DISPATCH_DIM_HEADS(dim, heads, CALL)
 #undef CALL
@@ -398,6 +406,7 @@ extern "C" int etpgt_tconv_bwd(const float* qkvs, const float* d_out, int64_t nu
     return ETPGT_EWORKSPACE;
   }
   if (num_nodes == 0) return ETPGT_OK;
+  const bool sparse = num_edges < 8 * num_nodes;  // session batches: short rows -> shallower unroll, more warps
   Workspace w(ws, ws_bytes);
   float* d_agg = w.take<float>((size_t)num_nodes * dim);
   float2* ecoef = w.take<float2>((size_t)(num_edges > 0 ? num_edges : 1) * heads);
@@ -408,17 +417,20 @@ extern "C" int etpgt_tconv_bwd(const float* qkvs, const float* d_out, int64_t nu
     const int npc = (kThreads / 32) * RowGeom<D>::GROUPS;                                            \
     grid_a = dst_pass_grid(num_nodes, npc);                                                          \
     const size_t smem = w_beta ? (size_t)npc * 3 * D * sizeof(float) : 0;                            \
-    if (smem > 48 * 1024)                                                                            \
-      cudaFuncSetAttribute(tconv_bwd_dst_kernel<D, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    tconv_bwd_dst_kernel<D, C><<<grid_a, kThreads, smem, stream>>>(                                  \
-        qkvs, d_out, num_nodes, rowptr, col, eperm, w_beta, alpha_mask, agg, beta, m, inv_l, d_qkvs, d_agg, \
-        ecoef, w_beta ? partial : nullptr);                                                          \
+    if (sparse)                                                                                      \
+      tconv_bwd_dst_kernel<D, C, 2><<<grid_a, kThreads, smem, stream>>>(                             \
+          qkvs, d_out, num_nodes, rowptr, col, eperm, w_beta, alpha_mask, agg, beta, m, inv_l, d_qkvs, d_agg, \
+          ecoef, w_beta ? partial : nullptr);                                                        \
+    else                                                                                             \
+      tconv_bwd_dst_kernel<D, C, 4><<<grid_a, kThreads, smem, stream>>>(                             \
+          qkvs, d_out, num_nodes, rowptr, col, eperm, w_beta, alpha_mask, agg, beta, m, inv_l, d_qkvs, d_agg, \
+          ecoef, w_beta ? partial : nullptr);                                                        \
   }
   ETPGT_DISPATCH_DIM_HEADS(dim, heads, CALL)
 #undef CALL
   ETPGT_CHECK_LAUNCH("tconv_bwd_dst");
   if (w_beta != nullptr) {
-    reduce_partials_kernel<<<(3 * dim + 255) / 256, 256, 0, stream>>>(partial, grid_a, 3 * dim, d_w_beta);
+    reduce_partials_kernel<<<(3 * dim * 32 + 255) / 256, 256, 0, stream>>>(partial, grid_a, 3 * dim, d_w_beta);
     ETPGT_CHECK_LAUNCH("tconv wbeta reduce");
   }
 #define CALL(D, C)                                                                                  \

@@ -35,8 +35,8 @@ typedef void* etpgt_stream_t; /* cudaStream_t */
 
 int etpgt_version(void);
 const char* etpgt_last_error(void);
-/* number of kernel launches issued by this library from the calling thread since the last
- * reset (bench.py's `gpu_launches`). */
+/* number of kernel launches issued by this library (all threads of the process; autograd runs
+ * backward on worker threads) since the last reset — bench.py's `gpu_launches`. */
 int64_t etpgt_launch_count(void);
 void etpgt_reset_launch_count(void);
 
