@@ -349,7 +349,7 @@ def run_b200(args, rank, world_size, local_rank):
         dist.destroy_process_group()
 
 
-def scoring_roofline(model, device, sessions=23_861, k=20, reps=5):
+def scoring_roofline(model, device, sessions=23_861, k=20, reps=10):
     """Full-catalogue evaluation scoring (BASELINE.json config 4 shape: every validation session
     against the whole item table, top-20) on the tcgen05 kernel: dense flops / time vs the measured
     bf16 tensor peak.  The item table is converted to bf16 once, as an evaluation loop does."""
@@ -359,19 +359,19 @@ def scoring_roofline(model, device, sessions=23_861, k=20, reps=5):
     table = ops.to_bf16(model.item_embedding.weight)
     sess = torch.randn(sessions, DIM, device=device) * 0.1
     sess_h = ops.to_bf16(sess)
-    for _ in range(2):
+    for _ in range(3):
         ops.score_topk(sess_h, table, k, precision="bf16")
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
-    total = 0.0
+    torch.cuda.synchronize()
+    # back-to-back launches between one pair of events: the host side of a call (tensor-map encode,
+    # workspace hand-out) is hidden behind the previous call's kernels, so this is device time.  The
+    # working set (54 MB operands + ~1.5 GB dump buffers) is far larger than L2.
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
     for _ in range(reps):
-        flush.zero_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
         ops.score_topk(sess_h, table, k, precision="bf16")
-        b.record()
-        torch.cuda.synchronize()
-        total += a.elapsed_time(b)
-    ms = total / reps
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
     flops = 2.0 * sessions * NUM_ITEMS * DIM
     achieved = flops / (ms / 1e3) / 1e12
     return {"bound": "tensor", "kernel": "score_topk_tc (tcgen05 bf16 GEMM + fused top-k) + topk_merge",
