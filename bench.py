@@ -243,7 +243,7 @@ def run_b200(args, rank, world_size, local_rank):
     import torch.distributed as dist
 
     import etpgt_b200
-    from etpgt_b200 import _lib, ops, parallel, synth
+    from etpgt_b200 import _lib, ops, optim, parallel, synth
     from etpgt_b200.model import create_graph_transformer_optimized
 
     if not torch.cuda.is_available():
@@ -267,7 +267,7 @@ def run_b200(args, rank, world_size, local_rank):
         parallel.enable_global_batch_norm(model)
         for p in model.parameters():
             dist.broadcast(p.data, 0)
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-5, fused=True)
+    opt = optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-5)   # etpgt_adam_step, table-gradient sink
     params = list(model.parameters())
     total_sessions = args.batch * world_size
     model.train()
@@ -276,7 +276,7 @@ def run_b200(args, rank, world_size, local_rank):
         sess = model(batch)
         loss = ops.sampled_loss(sess, model.item_embedding, batch.target_item, batch.negative_items, "bpr",
                                 total_sessions=total_sessions)[0]
-        opt.zero_grad(set_to_none=True)
+        opt.zero_grad()
         loss.backward()
         if distributed:
             parallel.allreduce_gradients(params)

@@ -13,7 +13,8 @@
 //                         for both the forward and the weight-gradient GEMM) + column sums
 //   etpgt_gemm_bf16x3     C[M,N] = A[M,K] B[N,K]^T (+ bias[N]); persistent warp-specialised
 //                         kernel: TMA ring (A and B k-blocks, SWIZZLE_128B) -> tcgen05.mma
-//                         128x128x16 -> double-buffered TMEM -> epilogue warps -> global;
+//                         128x128x16 -> double-buffered TMEM -> epilogue warps -> swizzled smem
+//                         staging -> TMA tile stores (coalesced 128-byte rows, edges clipped);
 //                         optional split-K with a fixed-order reduction (deterministic).
 #include <math.h>
 
@@ -32,6 +33,9 @@ constexpr int kTmemCols = 256;
 constexpr int kThreads = 192;  // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
 constexpr uint32_t TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB per operand part per k-block
 constexpr uint32_t kInstrDesc = instr_desc_bf16(BLOCK_M, BLOCK_N);
+constexpr int kEpiWarps = 4;
+constexpr uint32_t CD_BOX_BYTES = 32 * 32 * 4;  // one 32-row x 32-column fp32 store box
+constexpr uint32_t CD_BYTES = kEpiWarps * 2 * CD_BOX_BYTES;  // double-buffered per epilogue warp
 
 struct __align__(8) GemmBarriers {
   uint64_t full[kStages];
@@ -46,13 +50,14 @@ template <int PARTS>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                    const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                   const __grid_constant__ CUtensorMap map_c /* C, or the [split_k][M][N] partials */,
                    int64_t M, int64_t N, int64_t K, int m_tiles, int n_tiles, int split_k, int kb_per_split,
-                   const float* __restrict__ bias, float* __restrict__ C, int64_t ldc,
-                   float* __restrict__ partial /* [split_k][M][N] when split_k > 1 */) {
+                   const float* __restrict__ bias, int a_mn, int b_mn) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   constexpr uint32_t STAGE_BYTES = 2 * PARTS * TILE_BYTES;  // A parts then B parts
-  GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(smem + kStages * STAGE_BYTES);
+  uint8_t* smem_cd = smem + kStages * STAGE_BYTES;  // 1024-byte aligned (stage sizes are multiples of 16 KB)
+  GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(smem_cd + CD_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -65,6 +70,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     fence_barrier_init();
     tma_prefetch_desc(&map_a_hi);
     tma_prefetch_desc(&map_b_hi);
+    tma_prefetch_desc(&map_c);
     if (PARTS == 2) { tma_prefetch_desc(&map_a_lo); tma_prefetch_desc(&map_b_lo); }
   }
   if (warp == 1) tmem_alloc(&bars->tmem_base, kTmemCols);
@@ -93,11 +99,20 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
           mbar_wait(&bars->empty[stage], phase ^ 1);
           mbar_expect_tx(&bars->full[stage], STAGE_BYTES);
           uint8_t* st = smem + stage * STAGE_BYTES;
-          tma_load_2d(&map_a_hi, &bars->full[stage], st, kb * BLOCK_K, mt * BLOCK_M);
-          if (PARTS == 2) tma_load_2d(&map_a_lo, &bars->full[stage], st + TILE_BYTES, kb * BLOCK_K, mt * BLOCK_M);
-          tma_load_2d(&map_b_hi, &bars->full[stage], st + PARTS * TILE_BYTES, kb * BLOCK_K, nt * BLOCK_N);
-          if (PARTS == 2)
-            tma_load_2d(&map_b_lo, &bars->full[stage], st + (PARTS + 1) * TILE_BYTES, kb * BLOCK_K, nt * BLOCK_N);
+          // K-major operand: one box of 128 rows x 64 k.  MN-major operand (global [K, MN] row-major):
+          // two stacked boxes of 64 k-rows x 64 mn columns.
+          auto load = [&](const CUtensorMap* map, uint8_t* dst, int mn0, int mn_major) {
+            if (mn_major) {
+              tma_load_2d(map, &bars->full[stage], dst, mn0, kb * BLOCK_K);
+              tma_load_2d(map, &bars->full[stage], dst + TILE_BYTES / 2, mn0 + 64, kb * BLOCK_K);
+            } else {
+              tma_load_2d(map, &bars->full[stage], dst, kb * BLOCK_K, mn0);
+            }
+          };
+          load(&map_a_hi, st, mt * BLOCK_M, a_mn);
+          if (PARTS == 2) load(&map_a_lo, st + TILE_BYTES, mt * BLOCK_M, a_mn);
+          load(&map_b_hi, st + PARTS * TILE_BYTES, nt * BLOCK_N, b_mn);
+          if (PARTS == 2) load(&map_b_lo, st + (PARTS + 1) * TILE_BYTES, nt * BLOCK_N, b_mn);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -107,6 +122,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
       int stage = 0;
       uint32_t phase = 0;
       int t = 0;
+      const uint32_t idesc = kInstrDesc | (a_mn ? 1u << 15 : 0u) | (b_mn ? 1u << 16 : 0u);
       for (int64_t u = blockIdx.x; u < total_units; u += gridDim.x, ++t) {
         int ks, mt, nt;
         decode(u, ks, mt, nt);
@@ -125,12 +141,18 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
           const uint32_t b_lo = b_hi + TILE_BYTES;
 #pragma unroll
           for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
-            const uint32_t off = kk * UMMA_K * 2;
+            // one UMMA_K = 16 step: 32 bytes along a K-major swizzle row, 16 rows (2 KB) of an MN-major tile
+            const uint32_t off_a = a_mn ? kk * UMMA_K * 128 : kk * UMMA_K * 2;
+            const uint32_t off_b = b_mn ? kk * UMMA_K * 128 : kk * UMMA_K * 2;
             const uint32_t first = (kb == kb0 && kk == 0) ? 0u : 1u;
-            umma_bf16(tmem_d, make_desc_sw128(a_hi + off), make_desc_sw128(b_hi + off), kInstrDesc, first);
+            const uint64_t da_hi = a_mn ? make_desc_mn_sw128(a_hi + off_a, TILE_BYTES / 2) : make_desc_sw128(a_hi + off_a);
+            const uint64_t db_hi = b_mn ? make_desc_mn_sw128(b_hi + off_b, TILE_BYTES / 2) : make_desc_sw128(b_hi + off_b);
+            umma_bf16(tmem_d, da_hi, db_hi, idesc, first);
             if (PARTS == 2) {
-              umma_bf16(tmem_d, make_desc_sw128(a_hi + off), make_desc_sw128(b_lo + off), kInstrDesc, 1u);
-              umma_bf16(tmem_d, make_desc_sw128(a_lo + off), make_desc_sw128(b_hi + off), kInstrDesc, 1u);
+              const uint64_t da_lo = a_mn ? make_desc_mn_sw128(a_lo + off_a, TILE_BYTES / 2) : make_desc_sw128(a_lo + off_a);
+              const uint64_t db_lo = b_mn ? make_desc_mn_sw128(b_lo + off_b, TILE_BYTES / 2) : make_desc_sw128(b_lo + off_b);
+              umma_bf16(tmem_d, da_hi, db_lo, idesc, 1u);
+              umma_bf16(tmem_d, da_lo, db_hi, idesc, 1u);
             }
           }
           umma_commit(&bars->empty[stage]);
@@ -140,8 +162,13 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
       }
     }
   } else {
+    // TMEM lane quarter = warp % 4.  Each warp drains its 32 rows x 128 columns in four 32-column
+    // chunks: tcgen05.ld -> (+bias) -> 128B-swizzled staging box -> one TMA store per chunk, so
+    // global memory sees whole 128-byte row segments instead of 32 scattered 16-byte pieces.
     const int quarter = warp & 3;
-    const int row_in_tile = quarter * 32 + lane;
+    uint8_t* my_cd = smem_cd + (warp - 2) * 2 * CD_BOX_BYTES;
+    const bool add_bias = bias != nullptr && split_k == 1;
+    int buf = 0;
     int t = 0;
     for (int64_t u = blockIdx.x; u < total_units; u += gridDim.x, ++t) {
       int ks, mt, nt;
@@ -149,35 +176,41 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
       const int acc = t & 1;
       mbar_wait(&bars->acc_full[acc], (uint32_t)(t >> 1) & 1);
       tc_fence_after();
-      const int64_t row = (int64_t)mt * BLOCK_M + row_in_tile;
-      const int64_t col0 = (int64_t)nt * BLOCK_N;
-      float* out = split_k > 1 ? partial + ((int64_t)ks * M + row) * N : C + row * ldc;
-      const bool add_bias = bias != nullptr && split_k == 1;
+      const int row0 = mt * BLOCK_M + quarter * 32;
+      const int col0 = nt * BLOCK_N;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
         uint32_t v[32];
         tmem_ld_32x32(taddr + (uint32_t)c0, v);
-        if (row < M) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const int64_t col = col0 + c0 + j;
-            if (col + 3 < N) {
-              float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                     __uint_as_float(v[j + 3]));
-              if (add_bias) o = add4(o, ldg4(bias + col));
-              st4(out + col, o);
-            } else {
-              for (int q = 0; q < 4; ++q)
-                if (col + q < N) out[col + q] = __uint_as_float(v[j + q]) + (add_bias ? bias[col + q] : 0.f);
-            }
-          }
+        if (c0 + 32 == BLOCK_N) {  // accumulator fully read: hand the TMEM stage back before storing
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
         }
+        if ((int64_t)col0 + c0 >= N) continue;  // whole chunk past the last column (warp-uniform)
+        // the store issued two chunks ago (same staging box) must have finished reading it
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+        uint8_t* box = my_cd + buf * CD_BOX_BYTES + lane * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                 __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+          const int64_t col = (int64_t)col0 + c0 + 4 * j;
+          if (add_bias && col + 3 < N) o = add4(o, ldg4(bias + col));
+          *reinterpret_cast<float4*>(box + ((j ^ (lane & 7)) << 4)) = o;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&map_c, my_cd + buf * CD_BOX_BYTES, col0 + c0, row0, split_k > 1 ? ks : 0);
+          tma_store_commit();
+        }
+        buf ^= 1;
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
     }
+    if (lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -338,16 +371,17 @@ extern "C" size_t etpgt_gemm_bf16x3_workspace_bytes(int64_t M, int64_t N, int64_
   return (p.split_k > 1 ? align_up((size_t)p.split_k * M * N * sizeof(float)) : 0) + 256;
 }
 
-extern "C" int etpgt_gemm_bf16x3(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int64_t M,
-                                 int64_t N, int64_t K, int64_t lda, int64_t ldb, const float* bias, float* C,
-                                 int64_t ldc, int split_k, void* ws, size_t ws_bytes, etpgt_stream_t stream_) {
+extern "C" int etpgt_gemm_bf16x3_ex(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int64_t M,
+                                    int64_t N, int64_t K, int64_t lda, int64_t ldb, int a_mn_major, int b_mn_major,
+                                    const float* bias, float* C, int64_t ldc, int split_k, void* ws, size_t ws_bytes,
+                                    etpgt_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ETPGT_REQUIRE(M >= 0 && N > 0 && K > 0 && M < (int64_t(1) << 31) && N < (int64_t(1) << 31) && K < (int64_t(1) << 31),
                 "gemm_bf16x3: bad sizes");
   ETPGT_REQUIRE(a_hi && b_hi && C && (a_lo == nullptr) == (b_lo == nullptr),
                 "gemm_bf16x3: operands: hi parts required, lo parts both or neither");
-  ETPGT_REQUIRE(lda >= K && ldb >= K && lda % 8 == 0 && ldb % 8 == 0,
-                "gemm_bf16x3: operand pitches must cover K and be multiples of 8 elements (16 bytes)");
+  ETPGT_REQUIRE(lda >= (a_mn_major ? M : K) && ldb >= (b_mn_major ? N : K) && lda % 8 == 0 && ldb % 8 == 0,
+                "gemm_bf16x3: operand pitches must cover the contiguous extent and be multiples of 8 elements");
   ETPGT_REQUIRE(N % 4 == 0 && ldc % 4 == 0 && ldc >= N, "gemm_bf16x3: N and ldc must be multiples of 4");
   ETPGT_REQUIRE((((uintptr_t)a_hi | (uintptr_t)b_hi | (uintptr_t)a_lo | (uintptr_t)b_lo | (uintptr_t)C) & 15) == 0,
                 "gemm_bf16x3: pointers must be 16-byte aligned");
@@ -358,24 +392,39 @@ extern "C" int etpgt_gemm_bf16x3(const void* a_hi, const void* a_lo, const void*
     return ETPGT_EWORKSPACE;
   }
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-  bool ok = make_map_bf16(&ma_hi, a_hi, M, K, lda, BLOCK_M) && make_map_bf16(&mb_hi, b_hi, N, K, ldb, BLOCK_N);
-  if (a_lo != nullptr) ok = ok && make_map_bf16(&ma_lo, a_lo, M, K, lda, BLOCK_M) && make_map_bf16(&mb_lo, b_lo, N, K, ldb, BLOCK_N);
+  // K-major operand [MN, K]: boxes of 128 rows x 64 k.  MN-major operand [K, MN]: boxes of 64 k-rows x 64 mn.
+  auto map_a = [&](CUtensorMap* m, const void* p) {
+    return a_mn_major ? make_map_bf16(m, p, K, M, lda, 64) : make_map_bf16(m, p, M, K, lda, BLOCK_M);
+  };
+  auto map_b = [&](CUtensorMap* m, const void* p) {
+    return b_mn_major ? make_map_bf16(m, p, K, N, ldb, 64) : make_map_bf16(m, p, N, K, ldb, BLOCK_N);
+  };
+  bool ok = map_a(&ma_hi, a_hi) && map_b(&mb_hi, b_hi);
+  if (a_lo != nullptr) ok = ok && map_a(&ma_lo, a_lo) && map_b(&mb_lo, b_lo);
   else { ma_lo = ma_hi; mb_lo = mb_hi; }
   if (!ok) {
     set_error("gemm_bf16x3: cuTensorMapEncodeTiled failed");
     return ETPGT_ECUDA;
   }
   float* partial = p.split_k > 1 ? static_cast<float*>(ws) : nullptr;
+  CUtensorMap mc;
+  if (!(p.split_k > 1 ? make_map_f32_store(&mc, partial, p.split_k, M, N, N, M * N)
+                      : make_map_f32_store(&mc, C, 1, M, N, ldc, M * ldc))) {
+    set_error("gemm_bf16x3: cuTensorMapEncodeTiled (output) failed");
+    return ETPGT_ECUDA;
+  }
   const int parts = a_lo != nullptr ? 2 : 1;
-  const size_t smem = 1024 + (size_t)kStages * 2 * parts * TILE_BYTES + sizeof(GemmBarriers) + 64;
+  const size_t smem = 1024 + (size_t)kStages * 2 * parts * TILE_BYTES + CD_BYTES + sizeof(GemmBarriers) + 64;
   if (parts == 2) {
     cudaFuncSetAttribute(gemm_bf16x3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    gemm_bf16x3_kernel<2><<<p.grid, kThreads, smem, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, K, p.m_tiles, p.n_tiles,
-                                                             p.split_k, p.kb_per_split, bias, C, ldc, partial);
+    gemm_bf16x3_kernel<2><<<p.grid, kThreads, smem, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, mc, M, N, K, p.m_tiles,
+                                                             p.n_tiles, p.split_k, p.kb_per_split, bias,
+                                                             a_mn_major != 0, b_mn_major != 0);
   } else {
     cudaFuncSetAttribute(gemm_bf16x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    gemm_bf16x3_kernel<1><<<p.grid, kThreads, smem, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, K, p.m_tiles, p.n_tiles,
-                                                             p.split_k, p.kb_per_split, bias, C, ldc, partial);
+    gemm_bf16x3_kernel<1><<<p.grid, kThreads, smem, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, mc, M, N, K, p.m_tiles,
+                                                             p.n_tiles, p.split_k, p.kb_per_split, bias,
+                                                             a_mn_major != 0, b_mn_major != 0);
   }
   ETPGT_CHECK_LAUNCH("gemm_bf16x3");
   if (p.split_k > 1) {
@@ -383,4 +432,11 @@ extern "C" int etpgt_gemm_bf16x3(const void* a_hi, const void* a_lo, const void*
     ETPGT_CHECK_LAUNCH("splitk_reduce");
   }
   return ETPGT_OK;
+}
+
+extern "C" int etpgt_gemm_bf16x3(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int64_t M,
+                                 int64_t N, int64_t K, int64_t lda, int64_t ldb, const float* bias, float* C,
+                                 int64_t ldc, int split_k, void* ws, size_t ws_bytes, etpgt_stream_t stream) {
+  return etpgt_gemm_bf16x3_ex(a_hi, a_lo, b_hi, b_lo, M, N, K, lda, ldb, 0, 0, bias, C, ldc, split_k, ws, ws_bytes,
+                              stream);
 }

@@ -41,6 +41,7 @@ _PROTOTYPES = {
     "etpgt_split_bf16": (I, [P, L, L, L, P, P, L, P, P, L, P, P, Z, P]),
     "etpgt_gemm_bf16x3_workspace_bytes": (Z, [L, L, L, I]),
     "etpgt_gemm_bf16x3": (I, [P, P, P, P, L, L, L, L, L, P, P, L, I, P, Z, P]),
+    "etpgt_gemm_bf16x3_ex": (I, [P, P, P, P, L, L, L, L, L, I, I, P, P, L, I, P, Z, P]),
     "etpgt_gat_fwd": (I, [P, P, P, L, I, I, P, P, P, F, P, P, P, P, P, P]),
     "etpgt_gat_bwd_workspace_bytes": (Z, [L, L, I]),
     "etpgt_gat_bwd": (I, [P, P, P, P, P, L, I, I, P, P, P, P, P, P, L, F, P, P, P, P, P, P, P, P, Z, P]),
@@ -67,6 +68,9 @@ _PROTOTYPES = {
     "etpgt_topk_metrics": (I, [P, P, L, I, I, P, P]),
     "etpgt_scatter_rows_workspace_bytes": (Z, [L]),
     "etpgt_scatter_rows": (I, [P, P, P, L, I, I, L, L, P, P, Z, P]),
+    "etpgt_cooc_graph_workspace_bytes": (Z, [L, I]),
+    "etpgt_cooc_graph_build": (I, [P, P, P, L, L, I, L, L, P, P, P, P, P, P, Z, P]),
+    "etpgt_adam_step": (I, [P, I, D, D, D, D, D, I, L, I, P]),
 }
 
 _lib = None

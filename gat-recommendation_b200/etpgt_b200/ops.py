@@ -26,6 +26,13 @@ def _f32(t: torch.Tensor) -> torch.Tensor:
     return t.contiguous() if t.dtype == torch.float32 else t.float().contiguous()
 
 
+def _grad_sink(table: torch.Tensor):
+    """Persistent gradient buffer of `table` if an etpgt_b200.optim optimizer registered one."""
+    from .optim import grad_sink_for
+
+    return grad_sink_for(table) if table.dtype == torch.float32 and table.is_contiguous() else None
+
+
 def _i64(t: torch.Tensor) -> torch.Tensor:
     return t.contiguous() if t.dtype == torch.int64 else t.long().contiguous()
 
@@ -102,6 +109,7 @@ class EmbedPE(torch.autograd.Function):
         call("etpgt_embed_pe_fwd", ptr(ids), n, ptr(table_c), table_c.size(0), ptr(pe), int(bool(pe_per_node)),
              ptr(w_pe_c), ptr(b_pe_c), k_pe, dim, ptr(out), stream())
         ctx.save_for_backward(ids, pe)
+        ctx.table_ref = table
         ctx.meta = (table_c.size(0), dim, k_pe, int(bool(pe_per_node)), -1 if padding_idx is None else int(padding_idx))
         return out
 
@@ -112,7 +120,10 @@ class EmbedPE(torch.autograd.Function):
         d_out = _f32(d_out)
         dev = d_out.device
         n = ids.numel()
-        d_table = torch.zeros(num_items, dim, dtype=torch.float32, device=dev) if ctx.needs_input_grad[1] else None
+        d_table = sink = None
+        if ctx.needs_input_grad[1]:
+            sink = _grad_sink(ctx.table_ref)   # persistent buffer owned by etpgt_b200.optim: rows are ADDED
+            d_table = sink if sink is not None else torch.zeros(num_items, dim, dtype=torch.float32, device=dev)
         d_w = d_b = None
         if pe is not None:
             d_w = torch.empty(dim, k_pe, dtype=torch.float32, device=dev)
@@ -120,7 +131,7 @@ class EmbedPE(torch.autograd.Function):
         ws = workspace(size("etpgt_embed_pe_bwd_workspace_bytes", n, dim, max(k_pe, 1)), dev)
         call("etpgt_embed_pe_bwd", ptr(ids), n, ptr(d_out), num_items, ptr(pe), per_node, k_pe, dim, padding_idx,
              ptr(d_table), ptr(d_w), ptr(d_b), ptr(ws), ws.numel(), stream())
-        return None, d_table, None, None, d_w, d_b, None
+        return None, (None if sink is not None else d_table), None, None, d_w, d_b, None
 
 
 # ------------------------------------------------------------------------------ TransformerConv
@@ -191,18 +202,22 @@ def _split(src: torch.Tensor, rowmajor: bool, transposed: bool, colsum: bool = F
     return hi, lo, hi_t, lo_t, ld_t, sums
 
 
-def _gemm_x3(a_hi, a_lo, b_hi, b_lo, m, n, k, lda, ldb, bias, split_k=1) -> torch.Tensor:
+def _gemm_x3(a_hi, a_lo, b_hi, b_lo, m, n, k, lda, ldb, bias, split_k=1, a_mn=False, b_mn=False) -> torch.Tensor:
+    """C[m,n] = A B^T (+bias).  a_mn / b_mn: that operand is stored as its transpose ([k, m] / [k, n]
+    row-major) and read MN-major by the tensor cores — no transposed copy is made."""
     out = torch.empty(m, n, dtype=torch.float32, device=a_hi.device)
     ws = workspace(size("etpgt_gemm_bf16x3_workspace_bytes", m, n, k, split_k), a_hi.device)
-    call("etpgt_gemm_bf16x3", ptr(a_hi), ptr(a_lo), ptr(b_hi), ptr(b_lo), m, n, k, lda, ldb, ptr(bias), ptr(out), n,
-         split_k, ptr(ws), ws.numel(), stream())
+    call("etpgt_gemm_bf16x3_ex", ptr(a_hi), ptr(a_lo), ptr(b_hi), ptr(b_lo), m, n, k, lda, ldb, int(a_mn), int(b_mn),
+         ptr(bias), ptr(out), n, split_k, ptr(ws), ws.numel(), stream())
     return out
 
 
 class LinearTensorCore(torch.autograd.Function):
     """y = x @ W^T + b on the tcgen05 tensor cores with split-bf16 operands (fp32-grade accuracy,
-    etpgt_gemm_bf16x3).  Backward: dX and dW are the same kernel on transposed splits, db is the
-    column sum produced while splitting dY."""
+    etpgt_gemm_bf16x3_ex).  The hi/lo splits of x and W made for the forward are kept for the backward,
+    whose two GEMMs read them (and the split of dY) MN-major: dX = dY x W, dW = dY^T x X (K = nodes,
+    deterministic split-K); db is the column sum produced while splitting dY.  Per layer and step:
+    three split passes (x, W, dY) and three GEMMs, no transposed copies."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
@@ -214,25 +229,23 @@ class LinearTensorCore(torch.autograd.Function):
         x_hi, x_lo, _, _, _, _ = _split(x, True, False)
         w_hi, w_lo, _, _, _, _ = _split(weight, True, False)
         y = _gemm_x3(x_hi, x_lo, w_hi, w_lo, n, n_out, k, k, k, bias_c)
-        ctx.save_for_backward(x, weight)
+        ctx.save_for_backward(x_hi, x_lo, w_hi, w_lo)
         ctx.has_bias = bias is not None
         return y
 
     @staticmethod
     def backward(ctx, d_y):
-        x, weight = ctx.saved_tensors
+        x_hi, x_lo, w_hi, w_lo = ctx.saved_tensors
         d_y = _f32(d_y)
-        n, k = x.shape
-        n_out = weight.size(0)
+        n, k = x_hi.shape
+        n_out = w_hi.size(0)
         need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        g_hi, g_lo, g_hi_t, g_lo_t, ld_t, d_bias = _split(d_y, need_x, need_w, colsum=ctx.has_bias)
+        g_hi, g_lo, _, _, _, d_bias = _split(d_y, True, False, colsum=ctx.has_bias)
         d_x = d_w = None
-        if need_x:
-            _, _, wt_hi, wt_lo, ld_w, _ = _split(weight, False, True)       # [k, n_out]: B of dX
-            d_x = _gemm_x3(g_hi, g_lo, wt_hi, wt_lo, n, k, n_out, n_out, ld_w, None)
-        if need_w:
-            _, _, xt_hi, xt_lo, ld_x, _ = _split(x, False, True)            # [k, nodes]: B of dW
-            d_w = _gemm_x3(g_hi_t, g_lo_t, xt_hi, xt_lo, n_out, k, n, ld_t, ld_x, None, split_k=0)
+        if need_x:   # dX[n, k] = dY[n, n_out] x W[n_out, k]: B = W^T given as W, MN-major
+            d_x = _gemm_x3(g_hi, g_lo, w_hi, w_lo, n, k, n_out, n_out, k, None, b_mn=True)
+        if need_w:   # dW[n_out, k] = dY^T x X: both operands given by their row-major [nodes, .] splits
+            d_w = _gemm_x3(g_hi, g_lo, x_hi, x_lo, n_out, k, n, n_out, k, None, split_k=0, a_mn=True, b_mn=True)
         return d_x, d_w, d_bias
 
 
@@ -456,6 +469,7 @@ class SampledLoss(torch.autograd.Function):
         call("etpgt_sampled_loss_fwd", ptr(sess_c), ptr(table_c), ptr(targets), ptr(negatives), b, num_neg, dim, mode,
              float(alpha), float(temperature), total, ptr(scores), ptr(losses), ptr(ws), ws.numel(), stream())
         ctx.save_for_backward(sess_c, table_c, targets, negatives, scores)
+        ctx.table_ref = table
         ctx.meta = (mode, float(alpha), float(temperature), total, -1 if padding_idx is None else int(padding_idx))
         return losses
 
@@ -468,12 +482,15 @@ class SampledLoss(torch.autograd.Function):
         dev = sess.device
         d_loss = _f32(d_losses)[0:1].contiguous()
         d_sess = torch.empty_like(sess)
-        d_table = torch.zeros_like(table) if ctx.needs_input_grad[1] else None
+        d_table = sink = None
+        if ctx.needs_input_grad[1]:
+            sink = _grad_sink(ctx.table_ref)
+            d_table = sink if sink is not None else torch.zeros_like(table)
         ws = workspace(size("etpgt_sampled_loss_workspace_bytes", b, num_neg, dim), dev)
         call("etpgt_sampled_loss_bwd", ptr(sess), ptr(table), ptr(targets), ptr(negatives), b, num_neg, dim, mode,
              alpha, temperature, total, ptr(scores), ptr(d_loss), table.size(0), padding_idx, ptr(d_sess),
              ptr(d_table), ptr(ws), ws.numel(), stream())
-        return d_sess, d_table, None, None, None, None, None, None, None
+        return d_sess, (None if sink is not None else d_table), None, None, None, None, None, None, None
 
 
 def sampled_loss(sess, item_embeddings, targets, negatives, kind: str, alpha=0.7, temperature=1.0,

@@ -1,0 +1,172 @@
+"""Optimizer step of the training loop on the device.
+
+`AdamW` / `Adam` are drop-ins for the `torch.optim.AdamW(model.parameters(), lr, weight_decay)` the
+reference builds at scripts/train/train_baseline.py:252-256 and the `torch.optim.Adam(lr=1e-3)` of
+scripts/pipeline/run_full_pipeline.py:210: same constructor arguments, `step() / zero_grad() /
+state_dict() / load_state_dict()`, same per-parameter state keys (`step`, `exp_avg`, `exp_avg_sq`),
+so `Trainer` (etpgt/train/trainer.py:125-127) and its checkpoints work unchanged.  The arithmetic of
+torch's dense single-tensor update runs as ONE launch of `etpgt_adam_step` over every parameter.
+
+Persistent gradient buffers ("grad sinks"): for large tables (>= `sink_bytes`, i.e. the item embedding)
+the optimizer owns a zero-initialised gradient buffer that the path's backward kernels ACCUMULATE rows
+into directly (ops.EmbedPE / ops.SampledLoss look the buffer up by the table's storage address), and
+the step kernel clears it while it updates the parameter.  That removes, per step, two 84 MB memsets,
+the 3 x 84 MB add that autograd needs to sum the two table gradients, and a separate zero_grad pass.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import weakref
+
+import torch
+
+from . import _lib
+from ._lib import stream
+
+
+class _AdamTensor(ctypes.Structure):
+    _fields_ = [("param", ctypes.c_void_p), ("grad", ctypes.c_void_p), ("exp_avg", ctypes.c_void_p),
+                ("exp_avg_sq", ctypes.c_void_p), ("numel", ctypes.c_int64)]
+
+
+# table storage address -> (weakref to the parameter, gradient buffer, owner optimizer)
+_GRAD_SINKS: dict[int, tuple] = {}
+
+
+def grad_sink_for(table: torch.Tensor):
+    """The persistent gradient buffer registered for `table` (a parameter or its data), or None."""
+    entry = _GRAD_SINKS.get(table.data_ptr())
+    if entry is None:
+        return None
+    ref, buf, owner = entry
+    param = ref()
+    if param is None or param.data_ptr() != table.data_ptr() or buf.shape != table.shape:
+        _GRAD_SINKS.pop(table.data_ptr(), None)
+        return None
+    owner_opt = owner()
+    if owner_opt is not None:
+        owner_opt._dirty = True
+    return buf
+
+
+class _DeviceAdam(torch.optim.Optimizer):
+    _decoupled = True
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, amsgrad=False,
+                 grad_sinks=True, sink_bytes=4 << 20):
+        if amsgrad:
+            raise NotImplementedError("etpgt_b200 optimizers implement amsgrad=False (the reference's setting)")
+        if lr < 0.0 or eps < 0.0 or weight_decay < 0.0 or not 0.0 <= betas[0] < 1.0 or not 0.0 <= betas[1] < 1.0:
+            raise ValueError("Invalid optimizer hyper-parameter")
+        defaults = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay, amsgrad=False)
+        super().__init__(params, defaults)
+        self._dirty = False
+        self._sinks: list[torch.nn.Parameter] = []
+        self._plan_key = None
+        self._plan = None
+        if grad_sinks:
+            for group in self.param_groups:
+                for p in group["params"]:
+                    if p.is_cuda and p.dtype == torch.float32 and p.dim() == 2 and p.is_contiguous() \
+                            and p.numel() * 4 >= sink_bytes:
+                        self._install_sink(p)
+
+    # ------------------------------------------------------------------ gradient sinks
+    def _install_sink(self, p):
+        buf = torch.zeros_like(p)
+        p.grad = buf
+        _GRAD_SINKS[p.data_ptr()] = (weakref.ref(p), buf, weakref.ref(self))
+        self._sinks.append(p)
+
+    def _is_sink(self, p) -> bool:
+        entry = _GRAD_SINKS.get(p.data_ptr())
+        return entry is not None and entry[0]() is p and p.grad is entry[1]
+
+    def zero_grad(self, set_to_none: bool = True):
+        """torch semantics, except that sink gradients stay allocated (they are already zero after a
+        step; they are cleared here only if a backward ran since)."""
+        for group in self.param_groups:
+            for p in group["params"]:
+                if self._is_sink(p):
+                    if self._dirty:
+                        p.grad.zero_()
+                elif p.grad is not None:
+                    if set_to_none:
+                        p.grad = None
+                    else:
+                        p.grad.detach_()
+                        p.grad.zero_()
+        self._dirty = False
+
+    # ------------------------------------------------------------------ the step
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for group in self.param_groups:
+            todo: dict[int, list] = {}
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                if not p.is_cuda:
+                    raise RuntimeError("etpgt_b200 optimizers run on CUDA parameters only (no CPU fallback)")
+                if p.grad.is_sparse or p.dtype != torch.float32:
+                    raise RuntimeError("etpgt_b200 optimizers need dense fp32 parameters and gradients")
+                state = self.state[p]
+                if len(state) == 0:
+                    state["step"] = torch.tensor(0.0)
+                    state["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    state["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                state["step"] += 1
+                todo.setdefault(int(state["step"].item()), []).append(p)
+            for step_no, plist in todo.items():
+                self._launch(group, step_no, plist)
+        self._dirty = False
+        return loss
+
+    def _launch(self, group, step_no, plist):
+        grads = [p.grad if p.grad.is_contiguous() else p.grad.contiguous() for p in plist]
+        key = tuple((p.data_ptr(), g.data_ptr()) for p, g in zip(plist, grads))
+        if key != self._plan_key:
+            plain, sinks = [], []
+            for p, g in zip(plist, grads):
+                if not p.is_contiguous():
+                    raise RuntimeError("etpgt_b200 optimizers need contiguous parameters")
+                st = self.state[p]
+                entry = _AdamTensor(p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(),
+                                    st["exp_avg_sq"].data_ptr(), p.numel())
+                (sinks if self._is_sink(p) else plain).append(entry)
+            self._plan_key = key
+            self._plan = ((_AdamTensor * max(len(plain), 1))(*plain), len(plain),
+                          (_AdamTensor * max(len(sinks), 1))(*sinks), len(sinks))
+        arr_plain, n_plain, arr_sink, n_sink = self._plan
+        beta1, beta2 = group["betas"]
+        common = (float(group["lr"]), float(beta1), float(beta2), float(group["eps"]), float(group["weight_decay"]),
+                  int(self._decoupled), int(step_no))
+        # the sink gradients are cleared by the kernel (zero_grad flag); the others are released by
+        # zero_grad(set_to_none=True) as usual
+        if n_plain:
+            _lib.call("etpgt_adam_step", arr_plain, n_plain, *common, 0, stream())
+        if n_sink:
+            _lib.call("etpgt_adam_step", arr_sink, n_sink, *common, 1, stream())
+
+
+class AdamW(_DeviceAdam):
+    """torch.optim.AdamW semantics (decoupled weight decay, default 1e-2) on `etpgt_adam_step`."""
+
+    _decoupled = True
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, amsgrad=False, **kw):
+        super().__init__(params, lr, betas, eps, weight_decay, amsgrad, **kw)
+
+
+class Adam(_DeviceAdam):
+    """torch.optim.Adam semantics (L2 weight decay added to the gradient, default 0)."""
+
+    _decoupled = False
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, amsgrad=False, **kw):
+        super().__init__(params, lr, betas, eps, weight_decay, amsgrad, **kw)

@@ -162,6 +162,16 @@ int etpgt_gemm_bf16x3(const void* a_hi, const void* a_lo, const void* b_hi, cons
                       int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb,
                       const float* bias, float* c, int64_t ldc, int split_k,
                       void* ws, size_t ws_bytes, etpgt_stream_t stream);
+/* The same with either operand stored MN-major, i.e. as the transpose: a_mn_major != 0 means A is
+ * given as [K, M] row-major (pitch lda >= M), b_mn_major != 0 means B is given as [K, N] row-major
+ * (pitch ldb >= N).  This is what the two backward GEMMs of a Linear layer need without any
+ * transposed copies: dX[nodes,in] = dY[nodes,out] (K-major) x W[out,in] (B MN-major), and
+ * dW[out,in] = dY[nodes,out] (A MN-major) x X[nodes,in] (B MN-major), K = nodes. */
+int etpgt_gemm_bf16x3_ex(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,
+                         int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb,
+                         int a_mn_major, int b_mn_major,
+                         const float* bias, float* c, int64_t ldc, int split_k,
+                         void* ws, size_t ws_bytes, etpgt_stream_t stream);
 
 /* ---- a12: GAT edge-softmax aggregation and GraphSAGE mean aggregation ---------------------
  * PyG GATConv(add_self_loops=True) as used at etpgt/model/gat.py:49-109,137: h [N, width] with
@@ -288,6 +298,42 @@ size_t etpgt_scatter_rows_workspace_bytes(int64_t m);
 int etpgt_scatter_rows(const int64_t* keys, const float* coef, const float* src, int64_t m,
                        int src_div, int dim, int64_t num_rows, int64_t skip_key, float* d_table,
                        void* ws, size_t ws_bytes, etpgt_stream_t stream);
+
+/* ---- a11 / §8(f1): the optimizer step ------------------------------------------------------
+ * torch.optim.AdamW (scripts/train/train_baseline.py:252-256, stepped at etpgt/train/trainer.py:127)
+ * and torch.optim.Adam (scripts/pipeline/run_full_pipeline.py:210) over a list of fp32 tensors in ONE
+ * launch (chunks of <= 48 tensors).  `tensors` is a HOST array, read during the call.  decoupled != 0:
+ * AdamW (p *= 1 - lr*wd); 0: Adam with L2 (g += wd*p).  `step` is the 1-based step count shared by
+ * the listed tensors (bias corrections are computed from it in double, as torch does on the host).
+ * zero_grad != 0 also clears every listed gradient (persistent gradient buffers that the next
+ * backward accumulates into).  Dense semantics: every element of every tensor is updated. */
+typedef struct etpgt_adam_tensor {
+  float* param;
+  float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t numel;
+} etpgt_adam_tensor;
+int etpgt_adam_step(const etpgt_adam_tensor* tensors, int count, double lr, double beta1, double beta2,
+                    double eps, double weight_decay, int decoupled, int64_t step, int zero_grad,
+                    etpgt_stream_t stream);
+
+/* ---- §8(f3): co-occurrence graph construction ----------------------------------------------
+ * scripts/data/04_build_graph.py:25-127 (`build_co_event_graph`): sessions are
+ * sess_items[sess_ptr[s] : sess_ptr[s+1]] in timestamp order (the reference's groupby + sort); every
+ * pair of events at most `window` steps apart adds one co-occurrence to the undirected edge
+ * (min item, max item); count = co-occurrences, last_ts = max(0, timestamps of the event holding the
+ * smaller item id) (timestamps / last_ts may both be NULL).  Edges come out ordered by count
+ * descending, ties by first emission (the stable order of the reference's dict; pandas' default sort
+ * leaves ties unspecified).  Outputs hold `capacity` entries; *num_edges (device scalar) receives the
+ * true edge count (<= num_events * window) and at most `capacity` edges are written.  The per-edge
+ * `event_pair_hist` of the reference is not produced (unused by the training path). */
+size_t etpgt_cooc_graph_workspace_bytes(int64_t num_events, int window);
+int etpgt_cooc_graph_build(const int64_t* sess_ptr, const int64_t* sess_items, const int64_t* timestamps,
+                           int64_t num_sessions, int64_t num_events, int window, int64_t num_items,
+                           int64_t capacity, int64_t* item_i, int64_t* item_j, int64_t* count,
+                           int64_t* last_ts, int64_t* num_edges, void* ws, size_t ws_bytes,
+                           etpgt_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -55,7 +55,7 @@ def test_plain_bf16_gemm_and_split_parts():
     g = torch.Generator().manual_seed(4)
     x = torch.randn(200, 128, generator=g).cuda()
     w = torch.randn(256, 128, generator=g).cuda()
-    hi, lo, hi_t, lo_t, ld_t, sums = ops._split(x, True, True, colsum=True)
+    hi, lo, hi_t, lo_t, ld_t, sums = ops._split(x, True, True, colsum=True)   # transposed outputs stay in the ABI
     assert torch.equal(hi, x.to(torch.bfloat16))
     assert torch.equal(lo, (x - hi.float()).to(torch.bfloat16))
     assert torch.equal(hi_t[:, :200], hi.t()) and torch.equal(lo_t[:, :200], lo.t())
@@ -63,3 +63,26 @@ def test_plain_bf16_gemm_and_split_parts():
     w_hi = w.to(torch.bfloat16)
     y = ops._gemm_x3(hi, None, w_hi, None, 200, 256, 128, 128, 128, None)
     assert rel_err(y, hi.double() @ w_hi.double().t()) < 1e-5
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("m,n,k", [(128, 128, 64), (304, 264, 1000), (1024, 256, 5000), (72, 40, 136)])
+def test_mn_major_operands(a_mn, b_mn, m, n, k):
+    """Operands stored as their transposes ([K, M] / [K, N] row-major) are read MN-major: same result
+    as the K-major GEMM on explicitly transposed copies (split-bf16 x3, then plain bf16)."""
+    import etpgt_b200.ops as ops
+
+    g = torch.Generator().manual_seed(m + n + k)
+    a = torch.randn(m, k, generator=g).cuda()
+    b = torch.randn(n, k, generator=g).cuda()
+    want = a.double() @ b.double().t()
+    a_src = a.t().contiguous() if a_mn else a          # what the caller holds
+    b_src = b.t().contiguous() if b_mn else b
+    a_hi, a_lo, _, _, _, _ = ops._split(a_src, True, False)
+    b_hi, b_lo, _, _, _, _ = ops._split(b_src, True, False)
+    got = ops._gemm_x3(a_hi, a_lo, b_hi, b_lo, m, n, k, a_src.size(1), b_src.size(1), None, a_mn=a_mn, b_mn=b_mn)
+    assert rel_err(got, want) < 3e-5
+    plain = ops._gemm_x3(a_hi, None, b_hi, None, m, n, k, a_src.size(1), b_src.size(1), None, a_mn=a_mn, b_mn=b_mn)
+    a_r = a_hi.double().t() if a_mn else a_hi.double()
+    b_r = b_hi.double().t() if b_mn else b_hi.double()
+    assert rel_err(plain, a_r @ b_r.t()) < 1e-5
