@@ -11,6 +11,7 @@
 //
 // HBM-bound.  Algorithmic bytes (fp32): forward 2*DIM*4 per edge + 4*DIM*4 per node
 // (q, skip in; out, agg out); backward 4*DIM*4 per edge + 10*DIM*4 per node.
+#include <cuda_bf16.h>
 #include <math.h>
 
 #include "common.cuh"
@@ -26,6 +27,28 @@ template <int DIM>
 __device__ __forceinline__ void load_row(const float* __restrict__ row, int lig, float4 (&dst)[RowGeom<DIM>::V]) {
 #pragma unroll
   for (int v = 0; v < RowGeom<DIM>::V; ++v) dst[v] = ldg4(row + 4 * (v * RowGeom<DIM>::LPN + lig));
+}
+
+// Gradient row store: fp32 (d_qkvs) or, for the tensor-core projection backward, already split as
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi) (what etpgt_split_bf16 would produce from the fp32
+// row) so that the [N, 4*DIM] gradient never makes a second trip through HBM.
+__device__ __forceinline__ uint2 pack_bf16x4(float a, float b, float c, float d) {
+  __nv_bfloat162 p0 = __floats2bfloat162_rn(a, b), p1 = __floats2bfloat162_rn(c, d);
+  uint2 r;
+  r.x = *reinterpret_cast<uint32_t*>(&p0);
+  r.y = *reinterpret_cast<uint32_t*>(&p1);
+  return r;
+}
+__device__ __forceinline__ void store_grad4(float* __restrict__ d_f32, __nv_bfloat16* __restrict__ d_hi,
+                                            __nv_bfloat16* __restrict__ d_lo, int64_t offset, float4 g) {
+  if (d_hi != nullptr) {
+    const float hx = __bfloat162float(__float2bfloat16_rn(g.x)), hy = __bfloat162float(__float2bfloat16_rn(g.y));
+    const float hz = __bfloat162float(__float2bfloat16_rn(g.z)), hw = __bfloat162float(__float2bfloat16_rn(g.w));
+    *reinterpret_cast<uint2*>(d_hi + offset) = pack_bf16x4(hx, hy, hz, hw);
+    *reinterpret_cast<uint2*>(d_lo + offset) = pack_bf16x4(g.x - hx, g.y - hy, g.z - hz, g.w - hw);
+  } else {
+    st4(d_f32 + offset, g);
+  }
 }
 
 // ------------------------------------------------------------------------------- forward
@@ -138,7 +161,7 @@ tconv_fwd_kernel(const float* __restrict__ qkvs, int64_t num_nodes, const int32_
 // then over in-edges: alpha (recomputed from saved m, 1/l), d_alpha = <d_agg, v_j>_h,
 // d_logit = alpha (d_alpha*mask - delta), d_query += scale*d_logit*k_j.  Emits per-edge
 // (alpha*mask, scale*d_logit) for the source pass.
-template <int DIM, int HEAD_DIM, int UNROLL>
+template <int DIM, int HEAD_DIM, int UNROLL, bool COLSUM>
 __global__ void __launch_bounds__(kThreads, 2)
 tconv_bwd_dst_kernel(const float* __restrict__ qkvs, const float* __restrict__ d_out, int64_t num_nodes,
                      const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
@@ -146,8 +169,10 @@ tconv_bwd_dst_kernel(const float* __restrict__ qkvs, const float* __restrict__ d
                      const float* __restrict__ alpha_mask, const float* __restrict__ agg,
                      const float* __restrict__ beta, const float* __restrict__ m_in,
                      const float* __restrict__ invl_in, float* __restrict__ d_qkvs,
+                     __nv_bfloat16* __restrict__ d_hi, __nv_bfloat16* __restrict__ d_lo,
                      float* __restrict__ d_agg_out, float2* __restrict__ ecoef,
-                     float* __restrict__ wbeta_partial /* [grid][3*DIM] */) {
+                     float* __restrict__ partial /* [grid][(w_beta ? 3 : 0) + (COLSUM ? 2 : 0)][DIM] */) {
+  constexpr bool want_colsum = COLSUM;
   using G = RowGeom<DIM>;
   constexpr int V = G::V, LPN = G::LPN;
   constexpr int HEADS = DIM / HEAD_DIM;
@@ -159,8 +184,9 @@ tconv_bwd_dst_kernel(const float* __restrict__ qkvs, const float* __restrict__ d
   const int64_t nodes_per_cta = (kThreads / 32) * G::GROUPS;
 
   float4 dw1[V], dw2[V];  // sum dz*agg, sum dz*skip; the third block is their difference
+  float4 cq[V], cs[V];    // column sums of d_query / d_skip over this CTA's nodes (bias gradients)
 #pragma unroll
-  for (int v = 0; v < V; ++v) { dw1[v] = zero4(); dw2[v] = zero4(); }
+  for (int v = 0; v < V; ++v) { dw1[v] = zero4(); dw2[v] = zero4(); cq[v] = zero4(); cs[v] = zero4(); }
 
   for (int64_t base = blockIdx.x * nodes_per_cta; base < num_nodes; base += (int64_t)gridDim.x * nodes_per_cta) {
     const int64_t warp_base = base + warp_in_cta * G::GROUPS;
@@ -188,17 +214,20 @@ tconv_bwd_dst_kernel(const float* __restrict__ qkvs, const float* __restrict__ d
         dag[v] = fma4(dz, add4(w1, w3), scale4(1.f - b, g[v]));
         const float4 dxr = fma4(dz, sub4(w2, w3), scale4(b, g[v]));
         if (valid) {
-          st4(d_qkvs + nrow * 4 * DIM + 3 * DIM + 4 * f, dxr);
+          store_grad4(d_qkvs, d_hi, d_lo, nrow * 4 * DIM + 3 * DIM + 4 * f, dxr);
           dw1[v] = fma4(dz, ag[v], dw1[v]);
           dw2[v] = fma4(dz, xr[v], dw2[v]);
-
+          if (COLSUM) cs[v] = add4(cs[v], dxr);
         }
       }
     } else {
 #pragma unroll
       for (int v = 0; v < V; ++v) {
         dag[v] = g[v];
-        if (valid) st4(d_qkvs + nrow * 4 * DIM + 3 * DIM + 4 * (v * LPN + lig), g[v]);
+        if (valid) {
+          store_grad4(d_qkvs, d_hi, d_lo, nrow * 4 * DIM + 3 * DIM + 4 * (v * LPN + lig), g[v]);
+          if (COLSUM) cs[v] = add4(cs[v], g[v]);
+        }
       }
     }
     float delta[V], mh[V], il[V];
@@ -256,34 +285,49 @@ tconv_bwd_dst_kernel(const float* __restrict__ qkvs, const float* __restrict__ d
     }
     if (valid) {
 #pragma unroll
-      for (int v = 0; v < V; ++v) st4(d_qkvs + nrow * 4 * DIM + 4 * (v * LPN + lig), dq[v]);
+      for (int v = 0; v < V; ++v) {
+        store_grad4(d_qkvs, d_hi, d_lo, nrow * 4 * DIM + 4 * (v * LPN + lig), dq[v]);
+        if (COLSUM) cq[v] = add4(cq[v], dq[v]);
+      }
     }
   }
 
-  if (wbeta_partial != nullptr) {
-    // fixed-order reduction of the per-group partials of this CTA
-    extern __shared__ float dyn[];  // [(kThreads/32)*GROUPS][3*DIM]
+  const int wb = w_beta != nullptr ? 3 : 0, width = (wb + (want_colsum ? 2 : 0)) * DIM;
+  if (width > 0) {
+    // fixed-order reduction of the per-group partials of this CTA:
+    // [dz*agg | dz*skip | difference] (w_beta gradient) then [sum d_query | sum d_skip] (bias gradients)
+    extern __shared__ float dyn[];  // [(kThreads/32)*GROUPS][width]
     const int group_in_cta = warp_in_cta * G::GROUPS + lane / LPN;
-    float* mine = dyn + (size_t)group_in_cta * 3 * DIM;
+    float* mine = dyn + (size_t)group_in_cta * width;
 #pragma unroll
     for (int v = 0; v < V; ++v) {
       const int f = v * LPN + lig;
-      st4(mine + 4 * f, dw1[v]);
-      st4(mine + DIM + 4 * f, dw2[v]);
-      st4(mine + 2 * DIM + 4 * f, sub4(dw1[v], dw2[v]));
+      if (wb) {
+        st4(mine + 4 * f, dw1[v]);
+        st4(mine + DIM + 4 * f, dw2[v]);
+        st4(mine + 2 * DIM + 4 * f, sub4(dw1[v], dw2[v]));
+      }
+      if (want_colsum) {
+        st4(mine + wb * DIM + 4 * f, cq[v]);
+        st4(mine + (wb + 1) * DIM + 4 * f, cs[v]);
+      }
     }
     __syncthreads();
     constexpr int NG = (kThreads / 32) * G::GROUPS;
-    for (int i = threadIdx.x; i < 3 * DIM; i += kThreads) {
+    for (int i = threadIdx.x; i < width; i += kThreads) {
       float s = 0.f;
-      for (int gidx = 0; gidx < NG; ++gidx) s += dyn[(size_t)gidx * 3 * DIM + i];
-      wbeta_partial[(int64_t)blockIdx.x * 3 * DIM + i] = s;
+      for (int gidx = 0; gidx < NG; ++gidx) s += dyn[(size_t)gidx * width + i];
+      partial[(int64_t)blockIdx.x * width + i] = s;
     }
   }
 }
 
-__global__ void reduce_partials_kernel(const float* __restrict__ partial, int parts, int width,
-                                       float* __restrict__ out) {
+// Column i of the per-CTA partials goes to out_a[i] when i < width_a, else to
+// out_b[off_b0 + (i - width_a)] for the first `dim` of them and out_b[off_b1 + ...] for the next `dim`
+// (the two bias-gradient blocks of a pass sit at different offsets of the [4*dim] bias gradient).
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, int parts, int width, int width_a,
+                                       float* __restrict__ out_a, float* __restrict__ out_b, int dim, int off_b0,
+                                       int off_b1) {
   // one warp per output: lanes stride over the per-CTA partials, fixed butterfly -> deterministic
   const int lane = threadIdx.x & 31;
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -291,7 +335,10 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int pa
   float s = 0.f;
   for (int p = lane; p < parts; p += 32) s += partial[(int64_t)p * width + i];
   s = group_sum<32>(s);
-  if (lane == 0) out[i] = s;
+  if (lane != 0) return;
+  if (i < width_a) out_a[i] = s;
+  else if (i - width_a < dim) out_b[off_b0 + (i - width_a)] = s;
+  else out_b[off_b1 + (i - width_a - dim)] = s;
 }
 
 // ------------------------------------------------------------------ backward, source pass
@@ -302,15 +349,18 @@ __global__ void __launch_bounds__(kThreads)
 tconv_bwd_src_kernel(const float* __restrict__ qkvs, int64_t num_nodes, const int32_t* __restrict__ colptr,
                      const int32_t* __restrict__ row, const int32_t* __restrict__ cpos,
                      const float* __restrict__ d_agg, const float2* __restrict__ ecoef,
-                     float* __restrict__ d_qkvs) {
+                     float* __restrict__ d_qkvs, __nv_bfloat16* __restrict__ d_hi, __nv_bfloat16* __restrict__ d_lo,
+                     float* __restrict__ colsum_partial /* [grid][2*DIM] or NULL */) {
   using G = RowGeom<DIM>;
   constexpr int V = G::V, LPN = G::LPN;
   constexpr int HEADS = DIM / HEAD_DIM;
   const int lane = threadIdx.x & 31;
   const int lig = lane % LPN;
-  const int64_t node = ((blockIdx.x * (int64_t)kThreads + threadIdx.x) >> 5) * G::GROUPS + lane / LPN;
-  if (node >= num_nodes) return;
-  const int begin = colptr[node], end = colptr[node + 1];
+  const int64_t node_raw = ((blockIdx.x * (int64_t)kThreads + threadIdx.x) >> 5) * G::GROUPS + lane / LPN;
+  const bool valid = node_raw < num_nodes;
+  if (!valid && colsum_partial == nullptr) return;
+  const int64_t node = valid ? node_raw : 0;
+  const int begin = valid ? colptr[node] : 0, end = valid ? colptr[node + 1] : 0;
   float4 dk[V], dv[V];
 #pragma unroll
   for (int v = 0; v < V; ++v) { dk[v] = zero4(); dv[v] = zero4(); }
@@ -340,11 +390,30 @@ tconv_bwd_src_kernel(const float* __restrict__ qkvs, int64_t num_nodes, const in
       }
     }
   }
-  float* drow = d_qkvs + node * 4 * DIM;
+  if (valid) {
 #pragma unroll
-  for (int v = 0; v < V; ++v) {
-    st4(drow + DIM + 4 * (v * LPN + lig), dk[v]);
-    st4(drow + 2 * DIM + 4 * (v * LPN + lig), dv[v]);
+    for (int v = 0; v < V; ++v) {
+      store_grad4(d_qkvs, d_hi, d_lo, node * 4 * DIM + DIM + 4 * (v * LPN + lig), dk[v]);
+      store_grad4(d_qkvs, d_hi, d_lo, node * 4 * DIM + 2 * DIM + 4 * (v * LPN + lig), dv[v]);
+    }
+  }
+  if (colsum_partial != nullptr) {
+    // column sums of d_key / d_value over this CTA's rows, groups added in a fixed order
+    extern __shared__ float dyn[];  // [(kThreads/32)*GROUPS][2*DIM]
+    const int group_in_cta = (threadIdx.x >> 5) * G::GROUPS + lane / LPN;
+    float* mine = dyn + (size_t)group_in_cta * 2 * DIM;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      st4(mine + 4 * (v * LPN + lig), dk[v]);          // zero for rows past the end
+      st4(mine + DIM + 4 * (v * LPN + lig), dv[v]);
+    }
+    __syncthreads();
+    constexpr int NG = (kThreads / 32) * G::GROUPS;
+    for (int i = threadIdx.x; i < 2 * DIM; i += kThreads) {
+      float s = 0.f;
+      for (int gidx = 0; gidx < NG; ++gidx) s += dyn[(size_t)gidx * 2 * DIM + i];
+      colsum_partial[(int64_t)blockIdx.x * 2 * DIM + i] = s;
+    }
   }
 }
 
@@ -384,9 +453,85 @@ extern "C" int etpgt_tconv_fwd(const float* qkvs, int64_t num_nodes, int dim, in
 }
 
 extern "C" size_t etpgt_tconv_bwd_workspace_bytes(int64_t num_nodes, int64_t num_edges, int dim, int heads) {
+  const int64_t npc = (kThreads / 32) * (32 / (dim / 4 < 32 ? dim / 4 : 32));
+  const int64_t src_ctas = (num_nodes + npc - 1) / npc + 1;
   return align_up((size_t)num_nodes * dim * sizeof(float)) +
          align_up((size_t)(num_edges > 0 ? num_edges : 1) * heads * sizeof(float2)) +
-         align_up((size_t)kNumSMs * 4 * 3 * dim * sizeof(float)) + 256;
+         align_up((size_t)kNumSMs * 4 * 5 * dim * sizeof(float)) +
+         align_up((size_t)src_ctas * 2 * dim * sizeof(float)) + 256;
+}
+
+extern "C" int etpgt_tconv_bwd_split(const float* qkvs, const float* d_out, int64_t num_nodes, int dim, int heads,
+                                     const int32_t* rowptr, const int32_t* col, const int32_t* eperm,
+                                     const int32_t* colptr, const int32_t* row, const int32_t* cpos,
+                                     int64_t num_edges, const float* w_beta, const float* alpha_mask,
+                                     const float* agg, const float* beta, const float* m, const float* inv_l,
+                                     float* d_qkvs, void* d_hi_, void* d_lo_, float* d_colsum, float* d_w_beta,
+                                     void* ws, size_t ws_bytes, etpgt_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  __nv_bfloat16* d_hi = static_cast<__nv_bfloat16*>(d_hi_);
+  __nv_bfloat16* d_lo = static_cast<__nv_bfloat16*>(d_lo_);
+  ETPGT_REQUIRE(num_nodes >= 0 && num_edges >= 0, "tconv_bwd: negative size");
+  ETPGT_REQUIRE(qkvs && d_out && rowptr && colptr && agg && m && inv_l, "tconv_bwd: null pointer");
+  ETPGT_REQUIRE((d_hi != nullptr) == (d_lo != nullptr) && (d_hi != nullptr || d_qkvs != nullptr),
+                "tconv_bwd: gradient output required: fp32 d_qkvs, or both bf16 parts d_hi / d_lo");
+  ETPGT_REQUIRE(w_beta == nullptr || (beta && d_w_beta), "tconv_bwd: beta / d_w_beta required with w_beta");
+  if (ws_bytes < etpgt_tconv_bwd_workspace_bytes(num_nodes, num_edges, dim, heads)) {
+    set_error("tconv_bwd: workspace %zu < %zu", ws_bytes,
+              etpgt_tconv_bwd_workspace_bytes(num_nodes, num_edges, dim, heads));
+    return ETPGT_EWORKSPACE;
+  }
+  if (num_nodes == 0) {
+    if (d_colsum != nullptr) cudaMemsetAsync(d_colsum, 0, (size_t)4 * dim * sizeof(float), stream);
+    if (d_w_beta != nullptr) cudaMemsetAsync(d_w_beta, 0, (size_t)3 * dim * sizeof(float), stream);
+    return ETPGT_OK;
+  }
+  const bool sparse = num_edges < 8 * num_nodes;  // session batches: short rows -> shallower unroll, more warps
+  const int want_colsum = d_colsum != nullptr;
+  const int width_a = w_beta ? 3 * dim : 0;
+  const int width = width_a + (want_colsum ? 2 * dim : 0);
+  Workspace w(ws, ws_bytes);
+  float* d_agg = w.take<float>((size_t)num_nodes * dim);
+  float2* ecoef = w.take<float2>((size_t)(num_edges > 0 ? num_edges : 1) * heads);
+  float* partial = w.take<float>((size_t)kNumSMs * 4 * 5 * dim);
+  int grid_a = 1;
+#define CALL(D, C)                                                                                   \
+  {                                                                                                  \
+    const int npc = (kThreads / 32) * RowGeom<D>::GROUPS;                                            \
+    grid_a = dst_pass_grid(num_nodes, npc);                                                          \
+    const size_t smem = (size_t)npc * width * sizeof(float);                                         \
+    auto kern = sparse ? (want_colsum ? tconv_bwd_dst_kernel<D, C, 2, true> : tconv_bwd_dst_kernel<D, C, 2, false>) \
+                       : (want_colsum ? tconv_bwd_dst_kernel<D, C, 4, true> : tconv_bwd_dst_kernel<D, C, 4, false>); \
+    kern<<<grid_a, kThreads, smem, stream>>>(qkvs, d_out, num_nodes, rowptr, col, eperm, w_beta, alpha_mask, agg,    \
+                                             beta, m, inv_l, d_qkvs, d_hi, d_lo, d_agg, ecoef, partial);            \
+  }
+  ETPGT_DISPATCH_DIM_HEADS(dim, heads, CALL)
+#undef CALL
+  ETPGT_CHECK_LAUNCH("tconv_bwd_dst");
+  if (width > 0) {  // d_w_beta [3*dim]; bias gradients of query -> d_colsum[0:dim], skip -> d_colsum[3*dim:4*dim]
+    reduce_partials_kernel<<<(width * 32 + 255) / 256, 256, 0, stream>>>(partial, grid_a, width, width_a, d_w_beta,
+                                                                        d_colsum, dim, 0, 3 * dim);
+    ETPGT_CHECK_LAUNCH("tconv dst partial reduce");
+  }
+  float* src_partial = want_colsum ? w.take<float>((size_t)((num_nodes + 7) / 8 + 1) * 2 * dim) : nullptr;
+  int64_t grid_src = 1;
+#define CALL(D, C)                                                                                  \
+  {                                                                                                 \
+    const int64_t npc = (kThreads / 32) * RowGeom<D>::GROUPS;                                       \
+    grid_src = (num_nodes + npc - 1) / npc;                                                         \
+    const size_t smem = want_colsum ? (size_t)npc * 2 * D * sizeof(float) : 0;                      \
+    tconv_bwd_src_kernel<D, C><<<(unsigned)grid_src, kThreads, smem, stream>>>(                     \
+        qkvs, num_nodes, colptr, row, cpos, d_agg, ecoef, d_qkvs, d_hi, d_lo, src_partial);         \
+  }
+  ETPGT_DISPATCH_DIM_HEADS(dim, heads, CALL)
+#undef CALL
+  ETPGT_CHECK_LAUNCH("tconv_bwd_src");
+  if (want_colsum) {  // key -> d_colsum[dim:2*dim], value -> d_colsum[2*dim:3*dim]
+    reduce_partials_kernel<<<(2 * dim * 32 + 255) / 256, 256, 0, stream>>>(src_partial, (int)grid_src, 2 * dim, 0,
+                                                                          nullptr, d_colsum, dim, dim, 2 * dim);
+    ETPGT_CHECK_LAUNCH("tconv src colsum reduce");
+  }
+  return ETPGT_OK;
 }
 
 extern "C" int etpgt_tconv_bwd(const float* qkvs, const float* d_out, int64_t num_nodes, int dim, int heads,
@@ -395,53 +540,9 @@ extern "C" int etpgt_tconv_bwd(const float* qkvs, const float* d_out, int64_t nu
                                int64_t num_edges, const float* w_beta, const float* alpha_mask,
                                const float* agg, const float* beta, const float* m, const float* inv_l,
                                float* d_qkvs, float* d_w_beta, void* ws, size_t ws_bytes,
-                               etpgt_stream_t stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  ETPGT_REQUIRE(num_nodes >= 0 && num_edges >= 0, "tconv_bwd: negative size");
-  ETPGT_REQUIRE(qkvs && d_out && rowptr && colptr && agg && m && inv_l && d_qkvs, "tconv_bwd: null pointer");
-  ETPGT_REQUIRE(w_beta == nullptr || (beta && d_w_beta), "tconv_bwd: beta / d_w_beta required with w_beta");
-  if (ws_bytes < etpgt_tconv_bwd_workspace_bytes(num_nodes, num_edges, dim, heads)) {
-    set_error("tconv_bwd: workspace %zu < %zu", ws_bytes,
-              etpgt_tconv_bwd_workspace_bytes(num_nodes, num_edges, dim, heads));
-    return ETPGT_EWORKSPACE;
-  }
-  if (num_nodes == 0) return ETPGT_OK;
-  const bool sparse = num_edges < 8 * num_nodes;  // session batches: short rows -> shallower unroll, more warps
-  Workspace w(ws, ws_bytes);
-  float* d_agg = w.take<float>((size_t)num_nodes * dim);
-  float2* ecoef = w.take<float2>((size_t)(num_edges > 0 ? num_edges : 1) * heads);
-  float* partial = w.take<float>((size_t)kNumSMs * 4 * 3 * dim);
-  int grid_a = 1;
-#define CALL(D, C)                                                                                   \
-  {                                                                                                  \
-    const int npc = (kThreads / 32) * RowGeom<D>::GROUPS;                                            \
-    grid_a = dst_pass_grid(num_nodes, npc);                                                          \
-    const size_t smem = w_beta ? (size_t)npc * 3 * D * sizeof(float) : 0;                            \
-    if (sparse)                                                                                      \
-      tconv_bwd_dst_kernel<D, C, 2><<<grid_a, kThreads, smem, stream>>>(                             \
-          qkvs, d_out, num_nodes, rowptr, col, eperm, w_beta, alpha_mask, agg, beta, m, inv_l, d_qkvs, d_agg, \
-          ecoef, w_beta ? partial : nullptr);                                                        \
-    else                                                                                             \
-      tconv_bwd_dst_kernel<D, C, 4><<<grid_a, kThreads, smem, stream>>>(                             \
-          qkvs, d_out, num_nodes, rowptr, col, eperm, w_beta, alpha_mask, agg, beta, m, inv_l, d_qkvs, d_agg, \
-          ecoef, w_beta ? partial : nullptr);                                                        \
-  }
-  ETPGT_DISPATCH_DIM_HEADS(dim, heads, CALL)
-#undef CALL
-  ETPGT_CHECK_LAUNCH("tconv_bwd_dst");
-  if (w_beta != nullptr) {
-    reduce_partials_kernel<<<(3 * dim * 32 + 255) / 256, 256, 0, stream>>>(partial, grid_a, 3 * dim, d_w_beta);
-    ETPGT_CHECK_LAUNCH("tconv wbeta reduce");
-  }
-#define CALL(D, C)                                                                                  \
-  {                                                                                                 \
-    const int64_t npc = (kThreads / 32) * RowGeom<D>::GROUPS;                                       \
-    const int64_t grid = (num_nodes + npc - 1) / npc;                                               \
-    tconv_bwd_src_kernel<D, C><<<(unsigned)grid, kThreads, 0, stream>>>(qkvs, num_nodes, colptr, row, cpos, d_agg, \
-                                                                       ecoef, d_qkvs);              \
-  }
-  ETPGT_DISPATCH_DIM_HEADS(dim, heads, CALL)
-#undef CALL
-  ETPGT_CHECK_LAUNCH("tconv_bwd_src");
-  return ETPGT_OK;
+                               etpgt_stream_t stream) {
+  ETPGT_REQUIRE(d_qkvs != nullptr, "tconv_bwd: null d_qkvs");
+  return etpgt_tconv_bwd_split(qkvs, d_out, num_nodes, dim, heads, rowptr, col, eperm, colptr, row, cpos, num_edges,
+                               w_beta, alpha_mask, agg, beta, m, inv_l, d_qkvs, nullptr, nullptr, nullptr, d_w_beta,
+                               ws, ws_bytes, stream);
 }

@@ -37,6 +37,7 @@ _PROTOTYPES = {
     "etpgt_tconv_fwd": (I, [P, L, I, I, P, P, P, L, P, P, P, P, P, P, P, P]),
     "etpgt_tconv_bwd_workspace_bytes": (Z, [L, L, I, I]),
     "etpgt_tconv_bwd": (I, [P, P, L, I, I, P, P, P, P, P, P, L, P, P, P, P, P, P, P, P, P, Z, P]),
+    "etpgt_tconv_bwd_split": (I, [P, P, L, I, I, P, P, P, P, P, P, L, P, P, P, P, P, P, P, P, P, P, P, P, Z, P]),
     "etpgt_split_bf16_workspace_bytes": (Z, [L, L]),
     "etpgt_split_bf16": (I, [P, L, L, L, P, P, L, P, P, L, P, P, Z, P]),
     "etpgt_gemm_bf16x3_workspace_bytes": (Z, [L, L, L, I]),

@@ -109,3 +109,28 @@ def sample_negatives(sessions: SessionStore, session_ids, num_items: int, num_ne
     call("etpgt_sample_negatives", int(seed) & (2 ** 64 - 1), int(step) & 0xFFFFFFFF, int(session_base),
          ptr(sessions.ptr), ptr(sessions.items), ptr(ids), b, max_len, num_items, num_neg, ptr(out), stream())
     return out
+
+
+def build_co_event_graph(sess_ptr, sess_items, timestamps=None, window: int = 5, num_items: int | None = None,
+                         device="cuda"):
+    """The co-occurrence graph of scripts/data/04_build_graph.py:25-127 built on the device
+    (`etpgt_cooc_graph_build`): sessions given as ptr / items (/ timestamps) in time order.  Returns
+    device tensors (item_i, item_j, count, last_ts) ordered by count descending (ties: first emission) —
+    the rows of graph_edges.csv minus the unused event_pair_hist column."""
+    ptr_d, items_d = _dev_i64(sess_ptr, device), _dev_i64(sess_items, device)
+    ts_d = None if timestamps is None else _dev_i64(timestamps, device)
+    s, t = ptr_d.numel() - 1, items_d.numel()
+    if num_items is None:
+        num_items = int(items_d.max().item()) + 1 if t else 1
+    cap = max(t * window, 1)
+    i64 = dict(dtype=torch.int64, device=ptr_d.device)
+    item_i, item_j, count = torch.empty(cap, **i64), torch.empty(cap, **i64), torch.empty(cap, **i64)
+    last_ts = torch.empty(cap, **i64) if ts_d is not None else None
+    num_edges = torch.zeros(1, **i64)
+    ws = workspace(size("etpgt_cooc_graph_workspace_bytes", t, window), ptr_d.device)
+    call("etpgt_cooc_graph_build", ptr(ptr_d), ptr(items_d), ptr(ts_d), s, t, window, num_items, cap, ptr(item_i),
+         ptr(item_j), ptr(count), ptr(last_ts), ptr(num_edges), ptr(ws), ws.numel(), stream())
+    e = int(num_edges.item())          # the one host read of this one-off build
+    out = [item_i[:e].clone(), item_j[:e].clone(), count[:e].clone()]
+    out.append(last_ts[:e].clone() if last_ts is not None else None)
+    return tuple(out)

@@ -43,17 +43,24 @@ class TransformerConv(nn.Module):
         self.lin_skip = nn.Linear(in_channels, width)
         self.lin_beta = nn.Linear(3 * width, 1, bias=False) if beta else None
 
-    def project(self, x: torch.Tensor) -> torch.Tensor:
+    def fused_parameters(self):
         weight = torch.cat([self.lin_query.weight, self.lin_key.weight, self.lin_value.weight, self.lin_skip.weight])
         bias = torch.cat([self.lin_query.bias, self.lin_key.bias, self.lin_value.bias, self.lin_skip.bias])
+        return weight, bias
+
+    def project(self, x: torch.Tensor) -> torch.Tensor:
+        weight, bias = self.fused_parameters()
         return ops.linear(x, weight, bias)
 
     def forward(self, x, edge_index, alpha_mask=None):
         index = _as_index(edge_index, x.size(0))
         if alpha_mask is None:
             alpha_mask = _alpha_dropout_mask(index.num_edges, self.heads, self.dropout, self.training, x)
-        qkvs = self.project(x)
         w_beta = None if self.lin_beta is None else self.lin_beta.weight
+        if ops.fused_conv_supported(x, self.in_channels, 4 * self.heads * self.out_channels):
+            weight, bias = self.fused_parameters()
+            return ops.TransformerConvLayer.apply(x, weight, bias, w_beta, alpha_mask, index, self.heads)
+        qkvs = self.project(x)
         return ops.TransformerConvFn.apply(qkvs, w_beta, alpha_mask, index, self.heads)
 
 

@@ -249,6 +249,73 @@ class LinearTensorCore(torch.autograd.Function):
         return d_x, d_w, d_bias
 
 
+class TransformerConvLayer(torch.autograd.Function):
+    """One whole TransformerConv layer (etpgt/model/graph_transformer.py:73-98,174): the fused
+    query|key|value|skip projection on the tensor cores, then the fused attention / aggregation / gate
+    kernel.  Joining the two lets the backward edge kernels write the projection gradient d(qkvs) directly
+    as split-bf16 tensor-core operands together with its column sums (the bias gradient)
+    (etpgt_tconv_bwd_split): the [N, 4*dim] fp32 gradient and its split pass never exist."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, w_beta, alpha_mask, index: GraphIndex, heads: int):
+        _require_cuda(x, "node features")
+        x, weight, bias_c = _f32(x), _f32(weight), _f32(bias)
+        n, k = x.shape
+        width = weight.size(0)
+        dim = width // 4
+        dev = x.device
+        x_hi, x_lo, _, _, _, _ = _split(x, True, False)
+        w_hi, w_lo, _, _, _, _ = _split(weight, True, False)
+        qkvs = _gemm_x3(x_hi, x_lo, w_hi, w_lo, n, width, k, k, k, bias_c)
+        w_beta_c = _f32(w_beta).reshape(-1) if w_beta is not None else None
+        mask_c = _f32(alpha_mask) if alpha_mask is not None else None
+        f32 = dict(dtype=torch.float32, device=dev)
+        out, agg = torch.empty(n, dim, **f32), torch.empty(n, dim, **f32)
+        beta, m, inv_l = torch.empty(n, **f32), torch.empty(n, heads, **f32), torch.empty(n, heads, **f32)
+        call("etpgt_tconv_fwd", ptr(qkvs), n, dim, heads, ptr(index.rowptr), ptr(index.col), ptr(index.eperm),
+             index.num_edges, ptr(w_beta_c), ptr(mask_c), ptr(out), ptr(agg), ptr(beta), ptr(m), ptr(inv_l), stream())
+        ctx.save_for_backward(x_hi, x_lo, w_hi, w_lo, qkvs, w_beta_c, mask_c, agg, beta, m, inv_l)
+        ctx.index, ctx.heads = index, heads
+        ctx.w_beta_shape = None if w_beta is None else tuple(w_beta.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        x_hi, x_lo, w_hi, w_lo, qkvs, w_beta, mask, agg, beta, m, inv_l = ctx.saved_tensors
+        index, heads = ctx.index, ctx.heads
+        d_out = _f32(d_out)
+        n, k = x_hi.shape
+        width = w_hi.size(0)
+        dim = width // 4
+        dev = d_out.device
+        g_hi = torch.empty(n, width, dtype=torch.bfloat16, device=dev)
+        g_lo = torch.empty(n, width, dtype=torch.bfloat16, device=dev)
+        d_bias = torch.empty(width, dtype=torch.float32, device=dev)
+        d_w_beta = torch.empty(3 * dim, dtype=torch.float32, device=dev) if w_beta is not None else None
+        ws = workspace(size("etpgt_tconv_bwd_workspace_bytes", n, index.num_edges, dim, heads), dev)
+        call("etpgt_tconv_bwd_split", ptr(qkvs), ptr(d_out), n, dim, heads, ptr(index.rowptr), ptr(index.col),
+             ptr(index.eperm), ptr(index.colptr), ptr(index.row), ptr(index.cpos), index.num_edges, ptr(w_beta),
+             ptr(mask), ptr(agg), ptr(beta), ptr(m), ptr(inv_l), None, ptr(g_hi), ptr(g_lo), ptr(d_bias),
+             ptr(d_w_beta), ptr(ws), ws.numel(), stream())
+        d_x = d_w = None
+        if ctx.needs_input_grad[0]:
+            d_x = _gemm_x3(g_hi, g_lo, w_hi, w_lo, n, k, width, width, k, None, b_mn=True)
+        if ctx.needs_input_grad[1]:
+            d_w = _gemm_x3(g_hi, g_lo, x_hi, x_lo, width, k, n, width, k, None, split_k=0, a_mn=True, b_mn=True)
+        if d_w_beta is not None:
+            d_w_beta = d_w_beta.view(ctx.w_beta_shape)
+        return d_x, d_w, d_bias, d_w_beta, None, None, None
+
+
+def fused_conv_supported(x: torch.Tensor, in_channels: int, width: int) -> bool:
+    return PROJECTION_BACKEND == "tcgen05" and x.is_cuda and x.size(0) > 0 and in_channels % 8 == 0 and \
+        width % 32 == 0 and supported_dim(width // 4)
+
+
+def supported_dim(dim: int) -> bool:
+    return dim in (32, 64, 128, 256)
+
+
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None) -> torch.Tensor:
     """Dense projection of the path.  Tensor-core split-bf16 GEMM when the shape allows it
     (inner and outer widths multiples of 8), else a library fp32 GEMM."""

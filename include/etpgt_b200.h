@@ -142,6 +142,19 @@ int etpgt_tconv_bwd(const float* qkvs, const float* d_out, int64_t num_nodes, in
                     float* d_qkvs, float* d_w_beta,
                     void* ws, size_t ws_bytes, etpgt_stream_t stream);
 
+/* The same backward for the tensor-core projection path: instead of (or next to) the fp32 d_qkvs the
+ * gradient rows are written already split as bf16 pairs d_hi + d_lo = d_qkvs (hi = bf16(x),
+ * lo = bf16(x - hi), exactly what etpgt_split_bf16 would produce), and d_colsum [4*dim] receives the
+ * column sums of d_qkvs (the gradient of the fused query|key|value|skip bias), reduced in a fixed
+ * order.  d_qkvs may be NULL when d_hi / d_lo are given; d_colsum may be NULL. */
+int etpgt_tconv_bwd_split(const float* qkvs, const float* d_out, int64_t num_nodes, int dim, int heads,
+                          const int32_t* rowptr, const int32_t* col, const int32_t* eperm,
+                          const int32_t* colptr, const int32_t* row, const int32_t* cpos, int64_t num_edges,
+                          const float* w_beta, const float* alpha_mask,
+                          const float* agg, const float* beta, const float* m, const float* inv_l,
+                          float* d_qkvs, void* d_hi, void* d_lo, float* d_colsum, float* d_w_beta,
+                          void* ws, size_t ws_bytes, etpgt_stream_t stream);
+
 /* ---- a5 (dense part): node projections on the tensor cores, fp32-grade ("split-bf16 x3") ----
  * Replaces the fp32 nn.Linear GEMMs of TransformerConv (lin_query/key/value/skip,
  * graph_transformer.py:73-98,174).  x = hi + lo with hi = bf16(x), lo = bf16(x - hi);

@@ -13,6 +13,11 @@ is compared BIT-EXACTLY with the CUDA path.
                                 counter-based Philox stream (the reference's own mt19937 stream
                                 is worker-order dependent).
   * `merge_topk`              — exact (score desc, id asc) merge of per-shard candidates.
+  * `co_event_graph`          — scripts/data/04_build_graph.py:25-127 (`build_co_event_graph`), the
+                                step before the path: window-5 pair counts, last
+                                timestamp, edges ordered by count descending with ties in dict-insertion
+                                (first emission) order.  Pinned against the reference function itself
+                                through tests/golden/co_event_graph.npz.
 """
 
 from __future__ import annotations
@@ -158,3 +163,32 @@ def merge_topk(values: np.ndarray, ids: np.ndarray, k: int):
         order = np.lexsort((ids[b], -values[b].astype(np.float64)))[:k]
         out_v[b], out_i[b] = values[b][order], ids[b][order]
     return out_v, out_i
+
+
+def co_event_graph(sess_ptr, sess_items, timestamps=None, window: int = 5):
+    """scripts/data/04_build_graph.py:41-101 on sessions already grouped and time-sorted.
+    Returns (item_i, item_j, count, last_ts) int64 arrays, count-descending, ties by first emission
+    (a STABLE sort of the reference's dict order; pandas' default quicksort leaves ties unspecified)."""
+    edges: dict[tuple[int, int], list[int]] = {}
+    sess_ptr = np.asarray(sess_ptr)
+    sess_items = np.asarray(sess_items)
+    for s in range(len(sess_ptr) - 1):
+        lo, hi = int(sess_ptr[s]), int(sess_ptr[s + 1])
+        for i in range(lo, hi):
+            for j in range(i + 1, min(i + window + 1, hi)):
+                a, b = int(sess_items[i]), int(sess_items[j])
+                if a > b:                                   # 04_build_graph.py:64-71
+                    a, b = b, a
+                    ts = int(timestamps[j]) if timestamps is not None else 0
+                else:
+                    ts = int(timestamps[i]) if timestamps is not None else 0
+                rec = edges.setdefault((a, b), [0, 0])
+                rec[0] += 1
+                rec[1] = max(rec[1], ts)
+    keys = list(edges)
+    order = sorted(range(len(keys)), key=lambda r: -edges[keys[r]][0])   # stable
+    item_i = np.asarray([keys[r][0] for r in order], dtype=np.int64)
+    item_j = np.asarray([keys[r][1] for r in order], dtype=np.int64)
+    count = np.asarray([edges[keys[r]][0] for r in order], dtype=np.int64)
+    last_ts = np.asarray([edges[keys[r]][1] for r in order], dtype=np.int64)
+    return item_i, item_j, count, last_ts

@@ -242,8 +242,47 @@ def dataloader_case():
     print(f"wrote dataloader.npz: N={batch.x.numel()} E={batch.edge_index.size(1)}")
 
 
+def co_event_graph_case():
+    """Runs the reference's own `build_co_event_graph` (scripts/data/04_build_graph.py:25-127, loaded by
+    file path) on a small session frame with repeated items, equal items inside the window (self pairs),
+    sessions shorter than the window and one long session; pins row f3."""
+    import importlib.util
+
+    import pandas as pd
+
+    spec = importlib.util.spec_from_file_location("ref_build_graph", "/root/reference/scripts/data/04_build_graph.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rng = np.random.default_rng(11)
+    rows, ptr, items, stamps = [], [0], [], []
+    for s in range(300):
+        length = int(rng.integers(1, 12)) if s != 17 else 70
+        its = rng.integers(1, 40, size=length)
+        ts = np.sort(rng.integers(1_000, 2_000_000, size=length)) + s          # strictly per-session sorted
+        ts = ts + np.arange(length)                                               # no equal timestamps
+        for t, it in zip(ts, its):
+            rows.append({"session_id": s, "timestamp": int(t), "itemid": int(it),
+                         "event": ["view", "addtocart", "transaction"][int(rng.integers(0, 3))]})
+        items += [int(i) for i in its]
+        stamps += [int(t) for t in ts]
+        ptr.append(len(items))
+    df = pd.DataFrame(rows).sample(frac=1.0, random_state=3).reset_index(drop=True)   # shuffled rows
+    edges_df, stats = mod.build_co_event_graph(df, window=5)
+    np.savez_compressed(
+        OUT / "co_event_graph.npz", sess_ptr=np.asarray(ptr), sess_items=np.asarray(items),
+        timestamps=np.asarray(stamps), window=np.asarray(5),
+        item_i=edges_df["item_i"].to_numpy(), item_j=edges_df["item_j"].to_numpy(),
+        count=edges_df["count"].to_numpy(), last_ts=edges_df["last_ts"].to_numpy(),
+        num_nodes=np.asarray(stats["num_nodes"]), num_edges=np.asarray(stats["num_edges"]))
+    print(f"wrote co_event_graph.npz: {stats['num_edges']} edges, {stats['num_nodes']} nodes")
+
+
 if __name__ == "__main__":
     OUT.mkdir(parents=True, exist_ok=True)
+    if "--only-co-event" in sys.argv:
+        co_event_graph_case()
+        raise SystemExit(0)
     model_cases()
     loss_readout_metric_cases()
     dataloader_case()
+    co_event_graph_case()

@@ -170,3 +170,45 @@ def test_create_dataloader_reads_reference_csvs(tmp_path):
     second = [b.target_item.cpu() for b in small]
     assert sorted(torch.cat(first).tolist()) == sorted(g.raw["target"].tolist())
     assert not torch.equal(torch.cat(first), torch.cat(second))
+
+
+@pytest.mark.parametrize("window", [1, 5, 7])
+def test_co_event_graph_device_builder_is_bit_exact(window):
+    """etpgt_cooc_graph_build vs oracle/graph_ref.co_event_graph (pinned to the reference function by
+    tests/golden/co_event_graph.npz): identical rows in identical order."""
+    from golden_util import GOLDEN
+    from etpgt_b200 import data
+    from oracle import graph_ref
+
+    g = dict(np.load(GOLDEN / "co_event_graph.npz"))
+    want = graph_ref.co_event_graph(g["sess_ptr"], g["sess_items"], g["timestamps"], window)
+    got = data.build_co_event_graph(g["sess_ptr"], g["sess_items"], g["timestamps"], window)
+    for a, b in zip(got, want):
+        assert np.array_equal(a.cpu().numpy(), b)
+    if window == 5:   # and therefore the reference's own edge set
+        ref = {(int(a), int(b)): (int(c), int(t)) for a, b, c, t in zip(g["item_i"], g["item_j"], g["count"], g["last_ts"])}
+        mine = {(int(a), int(b)): (int(c), int(t)) for a, b, c, t in zip(*[x.cpu().numpy() for x in got])}
+        assert mine == ref
+    no_ts = data.build_co_event_graph(g["sess_ptr"], g["sess_items"], None, window)
+    assert no_ts[3] is None and all(np.array_equal(a.cpu().numpy(), b) for a, b in zip(no_ts[:3], want[:3]))
+
+
+def test_co_event_graph_edge_cases_and_synthetic_scale():
+    from etpgt_b200 import data, synth
+    from oracle import graph_ref
+
+    # no sessions / single-event sessions -> no edges
+    for ptr, items in (([0], []), ([0, 1, 2], [3, 4])):
+        got = data.build_co_event_graph(np.asarray(ptr), np.asarray(items, dtype=np.int64), None, 5, num_items=8)
+        assert got[0].numel() == 0
+    # a session of one repeated item -> one self edge with all the pairs
+    got = data.build_co_event_graph(np.asarray([0, 4]), np.asarray([6, 6, 6, 6]), np.asarray([5, 6, 7, 8]), 2, num_items=8)
+    assert [t.tolist() for t in got] == [[6], [6], [5], [7]]
+    # the synthetic RetailRocket-shaped generator builds its graph with the same rule (numpy path)
+    d = synth.generate(num_sessions=3000, graph_sessions=2200, num_items=900, clusters=30, seed=2)
+    ptr = d.sess_ptr[: 2200 + 1]
+    items = d.sess_items[: ptr[-1]]
+    i, j, c, _ = data.build_co_event_graph(ptr, items, None, 5, num_items=d.num_items)
+    want = graph_ref.co_event_graph(ptr, items, None, 5)
+    assert np.array_equal(i.cpu().numpy(), want[0]) and np.array_equal(j.cpu().numpy(), want[1])
+    assert np.array_equal(c.cpu().numpy(), want[2])

@@ -182,6 +182,56 @@ def test_tconv_backward_is_deterministic(ops):
         assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("n,e,dim,heads,beta,hub", [(257, 1500, 256, 2, True, False), (300, 4000, 256, 2, True, True),
+                                                    (100, 700, 64, 2, False, False), (33, 200, 32, 4, True, False),
+                                                    (5, 0, 128, 1, True, False)])
+def test_tconv_backward_split_outputs(ops, n, e, dim, heads, beta, hub):
+    """etpgt_tconv_bwd_split: the bf16 hi/lo gradient rows are bit-identical to splitting the fp32
+    gradient of the plain backward, and the fused column sums are the bias gradient."""
+    from etpgt_b200._lib import call, ptr, size, stream, workspace
+
+    rng = np.random.default_rng(n + e)
+    g = torch.Generator().manual_seed(dim + heads)
+    index = ops.GraphIndex(torch.from_numpy(random_graph(rng, n, e, hub=hub)).cuda(), n)
+    qkvs = torch.randn(n, 4 * dim, generator=g).cuda()
+    w_beta = (torch.randn(3 * dim, generator=g) * 0.2).cuda() if beta else None
+    d_out = torch.randn(n, dim, generator=g).cuda()
+    f32 = dict(dtype=torch.float32, device="cuda")
+    out, agg = torch.empty(n, dim, **f32), torch.empty(n, dim, **f32)
+    bt, m, inv_l = torch.empty(n, **f32), torch.empty(n, heads, **f32), torch.empty(n, heads, **f32)
+    call("etpgt_tconv_fwd", ptr(qkvs), n, dim, heads, ptr(index.rowptr), ptr(index.col), ptr(index.eperm),
+         index.num_edges, ptr(w_beta), None, ptr(out), ptr(agg), ptr(bt), ptr(m), ptr(inv_l), stream())
+    ws = workspace(size("etpgt_tconv_bwd_workspace_bytes", n, index.num_edges, dim, heads), "cuda")
+
+    def bwd(d_qkvs, hi, lo, colsum):
+        d_wb = torch.empty(3 * dim, **f32) if beta else None
+        call("etpgt_tconv_bwd_split", ptr(qkvs), ptr(d_out), n, dim, heads, ptr(index.rowptr), ptr(index.col),
+             ptr(index.eperm), ptr(index.colptr), ptr(index.row), ptr(index.cpos), index.num_edges, ptr(w_beta), None,
+             ptr(agg), ptr(bt), ptr(m), ptr(inv_l), ptr(d_qkvs), ptr(hi), ptr(lo), ptr(colsum), ptr(d_wb), ptr(ws),
+             ws.numel(), stream())
+        return d_wb
+
+    d_plain = torch.empty(n, 4 * dim, **f32)
+    wb_plain = bwd(d_plain, None, None, None)
+    hi = torch.empty(n, 4 * dim, dtype=torch.bfloat16, device="cuda")
+    lo = torch.empty_like(hi)
+    colsum = torch.full((4 * dim,), float("nan"), **f32)
+    wb_split = bwd(None, hi, lo, colsum)
+    want_hi = d_plain.to(torch.bfloat16)
+    assert torch.equal(hi, want_hi)
+    assert torch.equal(lo, (d_plain - want_hi.float()).to(torch.bfloat16))
+    assert rel_err(colsum, d_plain.double().sum(0)) < 1e-5
+    if beta:
+        assert torch.equal(wb_plain, wb_split)
+    # both at once, and run-to-run determinism of the fused sums
+    d_both, colsum2 = torch.empty(n, 4 * dim, **f32), torch.empty(4 * dim, **f32)
+    hi2, lo2 = torch.empty_like(hi), torch.empty_like(hi)
+    bwd(d_both, hi2, lo2, colsum2)
+    assert torch.equal(colsum, colsum2) and torch.equal(hi, hi2) and torch.equal(lo, lo2)
+    with pytest.raises(RuntimeError, match="gradient output required"):
+        bwd(None, None, None, None)
+
+
 # ------------------------------------------------------------------------------ BatchNorm
 
 

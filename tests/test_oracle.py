@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from golden_util import Golden, rel_err
+from golden_util import GOLDEN as GOLDEN_DIR, Golden, rel_err
 from oracle import graph_ref, model_ref
 
 GT_CASES = ["gt_opt_dummy", "gt_opt_dummy_nope", "gt_opt_b32", "gt_opt_b32_dual", "gt_opt_directed",
@@ -184,3 +184,22 @@ def test_csr_from_coo_is_stable():
     assert c["colptr"].tolist() == [0, 2, 4, 7, 7]
     assert c["cpos"].tolist() == [3, 6, 0, 5, 1, 2, 4]
     assert c["row"].tolist() == [1, 2, 0, 1, 0, 1, 1]
+
+
+def test_co_event_graph_restatement_matches_reference_function():
+    """oracle/graph_ref.co_event_graph vs the reference's build_co_event_graph
+    (scripts/data/04_build_graph.py:25-127) run by oracle/make_golden.py: same edge set, counts and
+    last timestamps; both count-descending (the reference's order inside equal counts is pandas'
+    unstable quicksort, so ties are compared as sets)."""
+    g = dict(np.load(GOLDEN_DIR / "co_event_graph.npz"))
+    i, j, c, t = graph_ref.co_event_graph(g["sess_ptr"], g["sess_items"], g["timestamps"], int(g["window"]))
+    assert len(i) == int(g["num_edges"]) == len(g["item_i"])
+    want = {(int(a), int(b)): (int(cc), int(tt)) for a, b, cc, tt in zip(g["item_i"], g["item_j"], g["count"], g["last_ts"])}
+    got = {(int(a), int(b)): (int(cc), int(tt)) for a, b, cc, tt in zip(i, j, c, t)}
+    assert got == want
+    assert (np.diff(c) <= 0).all() and (np.diff(g["count"]) <= 0).all()
+    assert np.array_equal(c, g["count"])                       # the count column itself is identical
+    assert len(set(i) | set(j)) == int(g["num_nodes"])
+    # without timestamps the structure is unchanged
+    i2, j2, c2, _ = graph_ref.co_event_graph(g["sess_ptr"], g["sess_items"], None, int(g["window"]))
+    assert np.array_equal(i, i2) and np.array_equal(j, j2) and np.array_equal(c, c2)
