@@ -11,11 +11,12 @@
 namespace etpgt {
 namespace {
 
-constexpr int kRowsPerCta = 256;
+constexpr int kRowsPerCta = 64;   // small chunks: enough CTAs (<= 8 per SM) to cover the HBM latency
+constexpr int kRowUnroll = 4;     // independent row loads in flight per thread
 
 int stat_parts(int64_t n) {
   int64_t parts = (n + kRowsPerCta - 1) / kRowsPerCta;
-  if (parts > 4 * kNumSMs) parts = 4 * kNumSMs;
+  if (parts > 8 * kNumSMs) parts = 8 * kNumSMs;
   return parts < 1 ? 1 : (int)parts;
 }
 
@@ -34,20 +35,38 @@ __global__ void bn_partial_kernel(const float* __restrict__ x, const float* __re
   double s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0};
   float4 mu = zero4(), is = zero4();
   if (MODE == 1) { mu = ld4(mean + 4 * tx); is = ld4(invstd + 4 * tx); }
-  for (int64_t r = begin + ty; r < end; r += blockDim.y) {
-    const float4 a = ldg4(x + r * dim + 4 * tx);
-    if (MODE == 0) {
-      s0[0] += a.x; s0[1] += a.y; s0[2] += a.z; s0[3] += a.w;
-      s1[0] += (double)a.x * a.x; s1[1] += (double)a.y * a.y; s1[2] += (double)a.z * a.z; s1[3] += (double)a.w * a.w;
-    } else {
-      float4 g = ldg4(d_y + r * dim + 4 * tx);
-      if (relu) {
-        const float4 o = ldg4(y + r * dim + 4 * tx);
-        g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f; g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
+  for (int64_t r0 = begin + ty; r0 < end; r0 += (int64_t)kRowUnroll * blockDim.y) {
+    float4 a[kRowUnroll], g[kRowUnroll], o[kRowUnroll];
+    bool on[kRowUnroll];
+#pragma unroll
+    for (int u = 0; u < kRowUnroll; ++u) {   // all loads of the unrolled rows are issued before any use
+      const int64_t r = r0 + (int64_t)u * blockDim.y;
+      on[u] = r < end;
+      const int64_t rr = on[u] ? r : begin;
+      a[u] = ldg4(x + rr * dim + 4 * tx);
+      if (MODE == 1) {
+        g[u] = ldg4(d_y + rr * dim + 4 * tx);
+        if (relu) o[u] = ldg4(y + rr * dim + 4 * tx);
       }
-      s0[0] += g.x; s0[1] += g.y; s0[2] += g.z; s0[3] += g.w;
-      s1[0] += (double)g.x * ((a.x - mu.x) * is.x); s1[1] += (double)g.y * ((a.y - mu.y) * is.y);
-      s1[2] += (double)g.z * ((a.z - mu.z) * is.z); s1[3] += (double)g.w * ((a.w - mu.w) * is.w);
+    }
+#pragma unroll
+    for (int u = 0; u < kRowUnroll; ++u) {
+      if (!on[u]) continue;
+      const float4 av = a[u];
+      if (MODE == 0) {
+        s0[0] += av.x; s0[1] += av.y; s0[2] += av.z; s0[3] += av.w;
+        s1[0] += (double)av.x * av.x; s1[1] += (double)av.y * av.y; s1[2] += (double)av.z * av.z;
+        s1[3] += (double)av.w * av.w;
+      } else {
+        float4 gv = g[u];
+        if (relu) {
+          gv.x = o[u].x > 0.f ? gv.x : 0.f; gv.y = o[u].y > 0.f ? gv.y : 0.f;
+          gv.z = o[u].z > 0.f ? gv.z : 0.f; gv.w = o[u].w > 0.f ? gv.w : 0.f;
+        }
+        s0[0] += gv.x; s0[1] += gv.y; s0[2] += gv.z; s0[3] += gv.w;
+        s1[0] += (double)gv.x * ((av.x - mu.x) * is.x); s1[1] += (double)gv.y * ((av.y - mu.y) * is.y);
+        s1[2] += (double)gv.z * ((av.z - mu.z) * is.z); s1[3] += (double)gv.w * ((av.w - mu.w) * is.w);
+      }
     }
   }
   double* mine = sm + (size_t)ty * 2 * dim;

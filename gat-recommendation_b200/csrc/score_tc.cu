@@ -38,14 +38,16 @@ using namespace tc;
 
 constexpr int BLOCK_M = 128;   // sessions per CTA (TMEM lanes)
 constexpr int BLOCK_N = 256;   // items per accumulator tile (TMEM columns)
-constexpr int CHUNK = 32;      // columns per tcgen05.ld and per dumped line
+constexpr int CHUNK = 32;      // columns per tcgen05.ld
+constexpr int DUMPW = 16;      // columns per dumped piece (64 bytes)
 constexpr int kMaxStages = 3;  // ring of item k-blocks
 constexpr int kAccStages = 2;  // TMEM accumulator double buffer
 constexpr int kTmemCols = 512;
 constexpr int kEpilogueWarps = 4;
 constexpr int kThreads = 32 * (2 + kEpilogueWarps);
 constexpr int kMaxKTc = 32;
-constexpr int kPendingMerge = 8;  // chunk maxima a row may have waiting before the warp merges
+constexpr int kPendingMerge = 10;  // capacity: maxima a row may have waiting (merge threshold - 1 + pieces per chunk)
+constexpr int kDefaultPendingMerge = 8;
 constexpr uint32_t A_KBLOCK_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr uint32_t B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;   // 32 KB
 constexpr uint32_t kInstrDesc = instr_desc_bf16(BLOCK_M, BLOCK_N);
@@ -94,7 +96,8 @@ struct Schedule {
 template <int NUM_KB, int KCAP>  // DIM / 64, number of chunk maxima tracked (>= k)
 __global__ void __launch_bounds__(kThreads, 1)
 score_dump_tc_kernel(const __grid_constant__ CUtensorMap map_sess, const __grid_constant__ CUtensorMap map_items,
-                     int64_t batch, int64_t num_items, int stages, Schedule sch, DumpBuffers dump) {
+                     int64_t batch, int64_t num_items, int stages, Schedule sch, DumpBuffers dump,
+                     int pending_merge /* <= kPendingMerge */) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;                                   // NUM_KB x 16 KB
@@ -187,14 +190,14 @@ score_dump_tc_kernel(const __grid_constant__ CUtensorMap map_sess, const __grid_
     const bool live = grow < batch;
     const int64_t pidx = live ? sch.part_index(grow, part) : 0;
     const int64_t slot0 = pidx * (int64_t)dump.cap;
-    float* my_scores = dump.scores + slot0 * CHUNK;
+    float* my_scores = dump.scores + slot0 * DUMPW;
     int32_t* my_cols = dump.chunk_col + slot0;
     float best[KCAP];   // the KCAP largest chunk maxima of this row so far, descending
 #pragma unroll
     for (int t = 0; t < KCAP; ++t) best[t] = -INFINITY;
     float thr = -INFINITY;
     int count = 0, pending = 0;
-    float* my_pending = pend_max + row;  // [kPendingMerge][128], row fastest
+    const uint32_t my_pending = smem_u32(pend_max + row);  // [kPendingMerge][128], row fastest (shared-space address)
     for (int t = 0; t < num_tiles; ++t) {
       const int acc = t & 1;
       const uint32_t acc_phase = (uint32_t)(t >> 1) & 1;
@@ -219,29 +222,44 @@ score_dump_tc_kernel(const __grid_constant__ CUtensorMap map_sess, const __grid_
         float g[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) g[q] = fmaxf(fmaxf(v[4 * q], v[4 * q + 1]), fmaxf(v[4 * q + 2], v[4 * q + 3]));
-        const float mx = fmaxf(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])), fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7])));
-        const bool hit = live && mx > thr;
-        if (__any_sync(0xffffffffu, hit)) {  // warp-uniform
-          if (hit) {
-            if (count < dump.cap) {
-              float4* dst = reinterpret_cast<float4*>(my_scores + (int64_t)count * CHUNK);
+        // dump granularity = DUMPW (16) columns: one 64-byte piece per hit instead of the whole 128-byte
+        // chunk — a third less dump traffic and half the store instructions on the divergent path
+        float mx[CHUNK / DUMPW];
+        bool hit[CHUNK / DUMPW];
+        bool any_hit = false;
 #pragma unroll
-              for (int q = 0; q < 8; ++q) __stcs(dst + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
-              my_cols[count] = t * BLOCK_N + c0;
+        for (int h = 0; h < CHUNK / DUMPW; ++h) {
+          mx[h] = fmaxf(fmaxf(g[4 * h], g[4 * h + 1]), fmaxf(g[4 * h + 2], g[4 * h + 3]));
+          hit[h] = live && mx[h] > thr;
+          any_hit = any_hit || hit[h];
+        }
+        if (__any_sync(0xffffffffu, any_hit)) {  // warp-uniform
+#pragma unroll
+          for (int h = 0; h < CHUNK / DUMPW; ++h) {
+            if (hit[h]) {
+              const int slot = count++;
+              st_shared_f32(my_pending + pending * BLOCK_M * sizeof(float), mx[h]);  // waits for the lockstep merge
+              ++pending;
+              if (slot < dump.cap) {
+                my_cols[slot] = t * BLOCK_N + c0 + h * DUMPW;
+                float4* dst = reinterpret_cast<float4*>(my_scores + (int64_t)slot * DUMPW);
+#pragma unroll
+                for (int q = 0; q < DUMPW / 4; ++q) {
+                  const int j = h * DUMPW + 4 * q;
+                  __stcs(dst + q, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                }
+              }
             }
-            ++count;
-            my_pending[pending * BLOCK_M] = mx;  // the maximum waits here for the next lockstep merge
-            ++pending;
           }
           // Merge the pending chunk maxima of all 32 rows into the sorted lists TOGETHER: one pass of
           // the sorting network then serves up to 32 rows at once (run per hit it would serve ~1).  The
           // threshold is a little stale in between, which only dumps a few extra chunks.
-          if (__any_sync(0xffffffffu, pending >= kPendingMerge)) {
+          if (__any_sync(0xffffffffu, pending >= pending_merge)) {
             int most = pending;
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) most = max(most, __shfl_xor_sync(0xffffffffu, most, off));
             for (int p = 0; p < most; ++p) {
-              float x = p < pending ? my_pending[p * BLOCK_M] : -INFINITY;  // -inf passes through unchanged
+              float x = p < pending ? ld_shared_f32(my_pending + p * BLOCK_M * sizeof(float)) : -INFINITY;  // -inf: no-op
 #pragma unroll
               for (int s = 0; s < KCAP; ++s) {
                 const float hi = fmaxf(best[s], x);
@@ -275,16 +293,30 @@ __device__ __forceinline__ bool better(float v, int64_t i, float bv, int64_t bi)
   return v > bv || (v == bv && i < bi);
 }
 
-// One warp per row.  Survivors (scores >= the best range threshold) are collected in shared memory,
-// then k selection passes pick the best remaining candidate by (score desc, id asc).
+// (score, column) packed so that an unsigned 64-bit comparison orders candidates by score descending,
+// then column ascending: high word = order-preserving image of the float (-0.0 canonicalised to +0.0,
+// like the oracle's comparison), low word = ~column.  0 is never a valid key.
+__device__ __forceinline__ uint64_t candidate_key(float v, int32_t col) {
+  uint32_t f = __float_as_uint(v + 0.0f);
+  f = (f & 0x80000000u) ? ~f : (f | 0x80000000u);
+  return ((uint64_t)f << 32) | (uint64_t)(0xFFFFFFFFu - (uint32_t)col);
+}
+__device__ __forceinline__ void decode_key(uint64_t key, float& v, int64_t& col) {
+  if (key == 0) { v = -INFINITY; col = 0; return; }
+  const uint32_t f = (uint32_t)(key >> 32);
+  v = __uint_as_float((f & 0x80000000u) ? (f ^ 0x80000000u) : ~f);
+  col = (int64_t)(0xFFFFFFFFu - (uint32_t)key);
+}
+
+// One warp per row.  Survivors (scores >= the best range threshold) are collected in shared memory as
+// packed keys, then sorted (bitonic network over 64 keys; selection passes when there are more).
 constexpr int kSelectWarps = 4;
 constexpr int kSurvivorCap = 512;
 
 __global__ void __launch_bounds__(kSelectWarps * 32)
 score_select_kernel(DumpBuffers dump, int64_t batch, Schedule sch, int k, int64_t id_base,
                     float* __restrict__ top_val, int64_t* __restrict__ top_idx, int32_t* __restrict__ redo) {
-  __shared__ float s_val[kSelectWarps][kSurvivorCap];
-  __shared__ int32_t s_idx[kSelectWarps][kSurvivorCap];
+  __shared__ uint64_t s_key[kSelectWarps][kSurvivorCap];  // (orderable score, ~column): larger = better
   __shared__ int s_count[kSelectWarps];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = blockIdx.x * (int64_t)kSelectWarps + w;
@@ -303,20 +335,30 @@ score_select_kernel(DumpBuffers dump, int64_t batch, Schedule sch, int k, int64_
       const int n = dump.count[sch.part_index(row, s)];
       const int64_t slot0 = sch.part_index(row, s) * (int64_t)dump.cap;
       const int range_col0 = sch.first_tile(row, s) * BLOCK_N;
-      // lane j owns column j of every dumped chunk: one coalesced 128-byte line per chunk, eight
-      // independent loads in flight
-      const float* base = dump.scores + slot0 * CHUNK + lane;
-      for (int c0 = 0; c0 < n; c0 += 8) {
-        float v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = c0 + u < n ? __ldcs(base + (int64_t)(c0 + u) * CHUNK) : -INFINITY;
+      // 128-bit loads: DUMPW/4 lanes cover one dumped piece, a warp load covers 128/DUMPW pieces, eight
+      // independent loads in flight per lane (4 KB per warp and iteration)
+      constexpr int LPP = DUMPW / 4;            // lanes per piece
+      constexpr int PPL = 32 / LPP;             // pieces per warp load
+      const int sub = lane / LPP, quad = lane % LPP;
+      const float4* base = reinterpret_cast<const float4*>(dump.scores + slot0 * DUMPW) + quad;
+      for (int c0 = 0; c0 < n; c0 += 8 * PPL) {
+        float4 v[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          if (v[u] >= tau && v[u] > -INFINITY) {  // -inf marks columns past the end of the table
-            const int pos = atomicAdd(&s_count[w], 1);
-            if (pos < kSurvivorCap) {
-              s_val[w][pos] = v[u];
-              s_idx[w][pos] = range_col0 + dump.chunk_col[slot0 + c0 + u] + lane;
+          const int piece = c0 + PPL * u + sub;
+          v[u] = piece < n ? __ldcs(base + (int64_t)piece * LPP) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float e4[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+          for (int comp = 0; comp < 4; ++comp) {
+            if (e4[comp] >= tau && e4[comp] > -INFINITY) {  // -inf marks columns past the end of the table
+              const int pos = atomicAdd(&s_count[w], 1);
+              if (pos < kSurvivorCap) {
+                s_key[w][pos] = candidate_key(
+                    e4[comp], range_col0 + dump.chunk_col[slot0 + c0 + PPL * u + sub] + 4 * quad + comp);
+              }
             }
           }
         }
@@ -331,29 +373,54 @@ score_select_kernel(DumpBuffers dump, int64_t batch, Schedule sch, int k, int64_
   }
   if (lane == 0) redo[row] = 0;
   const int n = s_count[w];
-  float prev_v = INFINITY;
-  int64_t prev_i = -1;
-  for (int t = 0; t < k; ++t) {
-    float bv = -INFINITY;
-    int64_t bi = INT64_MAX;
-    for (int c = lane; c < n; c += 32) {
-      const float v = s_val[w][c];
-      const int64_t i = s_idx[w][c];
-      const bool after_prev = v < prev_v || (v == prev_v && i > prev_i);
-      if (after_prev && better(v, i, bv, bi)) { bv = v; bi = i; }
-    }
+  uint64_t mine = 0;   // lane t ends up with the t-th best candidate (0 = none)
+  if (n <= 64) {
+    // the usual case (a few dozen survivors): bitonic sort of 64 keys, two per lane, descending
+    uint64_t k0 = lane < n ? s_key[w][lane] : 0, k1 = lane + 32 < n ? s_key[w][lane + 32] : 0;
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
-      const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, off);
-      if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    for (int size = 2; size <= 64; size <<= 1) {
+#pragma unroll
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        if (stride == 32) {          // partner of element i (< 32) is i + 32: the lane's own second key
+          const uint64_t hi = k0 > k1 ? k0 : k1, lo = k0 > k1 ? k1 : k0;   // size == 64: descending everywhere
+          k0 = hi; k1 = lo;
+        } else {
+          // element index e0 = lane, e1 = lane + 32; direction of the bitonic block containing the element
+          const uint64_t p0 = __shfl_xor_sync(0xffffffffu, k0, stride), p1 = __shfl_xor_sync(0xffffffffu, k1, stride);
+          const bool lower = (lane & stride) == 0;                       // this lane holds the lower index of the pair
+          const bool desc0 = size == 64 || ((lane & size) == 0);        // block direction (final merge: descending)
+          const bool desc1 = size == 64 || (((lane + 32) & size) == 0);
+          const bool take_max0 = lower == desc0, take_max1 = lower == desc1;
+          k0 = take_max0 ? (k0 > p0 ? k0 : p0) : (k0 < p0 ? k0 : p0);
+          k1 = take_max1 ? (k1 > p1 ? k1 : p1) : (k1 < p1 ? k1 : p1);
+        }
+      }
     }
-    if (lane == 0) {
-      top_val[row * k + t] = bv;
-      top_idx[row * k + t] = bi == INT64_MAX ? INT64_MAX : id_base + bi;
+    mine = k0;                       // ranks 0..31 are the first keys of lanes 0..31 (k <= 32)
+  } else {
+    // many survivors (large ties at the threshold): k selection passes over the shared-memory list
+    uint64_t prev = ~uint64_t(0);
+    for (int t = 0; t < k; ++t) {
+      uint64_t best = 0;
+      for (int c = lane; c < n; c += 32) {
+        const uint64_t key = s_key[w][c];
+        if (key < prev && key > best) best = key;
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const uint64_t o = __shfl_xor_sync(0xffffffffu, best, off);
+        best = o > best ? o : best;
+      }
+      if (lane == t) mine = best;
+      prev = best;
     }
-    prev_v = bv;
-    prev_i = bi;
+  }
+  if (lane < k) {   // one coalesced store of the row's k results
+    float v;
+    int64_t col;
+    decode_key(mine, v, col);
+    top_val[row * k + lane] = v;
+    top_idx[row * k + lane] = mine == 0 ? INT64_MAX : id_base + col;
   }
 }
 
@@ -366,9 +433,19 @@ __global__ void __launch_bounds__(kRedoThreads)
 score_redo_kernel(const __nv_bfloat16* __restrict__ sess, const __nv_bfloat16* __restrict__ table, int64_t batch,
                   int64_t num_items, int dim, int k, int64_t id_base, const int32_t* __restrict__ redo,
                   float* __restrict__ top_val, int64_t* __restrict__ top_idx) {
-  const int64_t row = blockIdx.x;
-  if (row >= batch || redo[row] == 0) return;
   extern __shared__ float redo_smem[];       // session row [dim], then lists
+  // a small persistent grid; the flags of kRedoThreads rows are read at once, so rows that need no
+  // recomputation (normally all of them) cost one coalesced load per 256 rows
+  __shared__ int32_t s_flag[kRedoThreads];
+  for (int64_t row0 = (int64_t)blockIdx.x * kRedoThreads; row0 < batch; row0 += (int64_t)gridDim.x * kRedoThreads) {
+  const int32_t mine = row0 + threadIdx.x < batch ? redo[row0 + threadIdx.x] : 0;
+  if (__syncthreads_or(mine) == 0) continue;  // CTA-uniform
+  s_flag[threadIdx.x] = mine;
+  __syncthreads();
+  for (int rr = 0; rr < kRedoThreads; ++rr) {
+  if (s_flag[rr] == 0) continue;              // CTA-uniform
+  const int64_t row = row0 + rr;
+  __syncthreads();                           // the previous row's lists are no longer read
   float* s_row = redo_smem;
   float* l_val = redo_smem + dim;            // [kRedoThreads][k]
   int32_t* l_idx = reinterpret_cast<int32_t*>(l_val + kRedoThreads * k);
@@ -426,6 +503,9 @@ score_redo_kernel(const __nv_bfloat16* __restrict__ sess, const __nv_bfloat16* _
     prev_i = bi;
     __syncthreads();
   }
+  }
+  __syncthreads();                           // s_flag is rewritten by the next block of rows
+  }
 }
 
 __global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n4) {
@@ -478,7 +558,7 @@ TcPlan tc_plan(int64_t batch, int64_t num_items, int k) {
   p.grid = m_full + tail * p.sch.tail_splits;
   // slots per (row, range): ~ K*(1 + ln(chunks/K)) chunks are expected; 1.6x head-room (sized for the
   // longest range), overflow is handled exactly by the fallback kernel
-  const double chunks = (double)(m_full > 0 ? total_tiles : p.sch.tiles_per_split) * (BLOCK_N / CHUNK);
+  const double chunks = (double)(m_full > 0 ? total_tiles : p.sch.tiles_per_split) * (BLOCK_N / DUMPW);
   const int kc = k <= 10 ? 10 : k <= 20 ? 20 : 32;
   double expect = kc * (1.0 + (chunks > kc ? log(chunks / kc) : 0.0));
   int cap = (int)(1.6 * expect) + 8;
@@ -514,7 +594,7 @@ extern "C" size_t etpgt_score_topk_bf16_workspace_bytes(int64_t batch, int64_t n
   if (batch <= 0 || num_items <= 0 || k <= 0) return 256;
   const TcPlan p = tc_plan(batch, num_items, k);
   const size_t units = (size_t)p.sch.num_parts(batch);
-  return align_up(units * p.cap * CHUNK * sizeof(float)) + align_up(units * p.cap * sizeof(int32_t)) +
+  return align_up(units * p.cap * DUMPW * sizeof(float)) + align_up(units * p.cap * sizeof(int32_t)) +
          2 * align_up(units * sizeof(float)) + 2 * align_up((size_t)batch * sizeof(int32_t)) + 256;
 }
 
@@ -538,7 +618,7 @@ extern "C" int etpgt_score_topk_bf16(const void* sess_bf16, const void* table_bf
   Workspace w(ws, ws_bytes);
   const size_t units = (size_t)p.sch.num_parts(batch);
   DumpBuffers dump;
-  dump.scores = w.take<float>(units * p.cap * CHUNK);
+  dump.scores = w.take<float>(units * p.cap * DUMPW);
   dump.chunk_col = w.take<int32_t>(units * p.cap);
   dump.count = w.take<int32_t>(units);
   dump.threshold = w.take<float>(units);
@@ -552,13 +632,18 @@ extern "C" int etpgt_score_topk_bf16(const void* sess_bf16, const void* table_bf
   }
   const int num_kb = dim / BLOCK_K;
   const int stages = kMaxStages;
+  int pending_merge = kDefaultPendingMerge;
+  if (const char* forced = getenv("ETPGT_SCORE_PENDING")) {  // tuning knob
+    const int f = atoi(forced);
+    if (f >= 1 && f <= kPendingMerge + 1 - CHUNK / DUMPW) pending_merge = f;
+  }
   const size_t smem = tc_smem_bytes(num_kb, stages);
   const dim3 grid(p.grid);
 #define LAUNCH2(NKB, KC)                                                                                        \
   {                                                                                                             \
     cudaFuncSetAttribute(score_dump_tc_kernel<NKB, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     score_dump_tc_kernel<NKB, KC><<<grid, kThreads, smem, stream>>>(map_sess, map_items, batch, num_items, stages, \
-                                                                   p.sch, dump);                               \
+                                                                   p.sch, dump, pending_merge);                \
   }
 #define LAUNCH(NKB)                    \
   {                                    \
@@ -581,7 +666,9 @@ extern "C" int etpgt_score_topk_bf16(const void* sess_bf16, const void* table_bf
   const size_t redo_smem = ((size_t)dim + (size_t)kRedoThreads * k * 2) * sizeof(float);
   if (redo_smem > 48 * 1024)
     cudaFuncSetAttribute(score_redo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)redo_smem);
-  score_redo_kernel<<<(unsigned)batch, kRedoThreads, redo_smem, stream>>>(
+  const int64_t redo_blocks = (batch + kRedoThreads - 1) / kRedoThreads;
+  const unsigned redo_grid = (unsigned)(redo_blocks < 2 * kNumSMs ? redo_blocks : 2 * kNumSMs);
+  score_redo_kernel<<<redo_grid, kRedoThreads, redo_smem, stream>>>(
       static_cast<const __nv_bfloat16*>(sess_bf16), static_cast<const __nv_bfloat16*>(table_bf16), batch, num_items,
       dim, k, id_base, redo, top_val, top_idx);
   ETPGT_CHECK_LAUNCH("score_redo");
