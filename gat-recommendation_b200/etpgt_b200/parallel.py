@@ -57,16 +57,17 @@ def allreduce_gradients(params, group=None) -> None:
     for p in params:
         if p.grad is None:
             continue
-        (large if p.grad.numel() * p.grad.element_size() >= (4 << 20) else small).append(p.grad)
+        (large if p.grad.numel() * p.grad.element_size() >= (4 << 20) else small).append(p)
     if small:
-        flat = torch.cat([g.reshape(-1) for g in small])
+        flat = torch.cat([p.grad.reshape(-1) for p in small])
         dist.all_reduce(flat, group=group)
         offset = 0
-        for g in small:
-            g.copy_(flat[offset:offset + g.numel()].view_as(g))
-            offset += g.numel()
-    for g in large:
-        dist.all_reduce(g, group=group)
+        for p in small:   # rebind .grad to its slice of the reduced buffer: no copy back
+            n = p.grad.numel()
+            p.grad = flat[offset:offset + n].view_as(p.grad)
+            offset += n
+    for p in large:
+        dist.all_reduce(p.grad, group=group)
 
 
 @torch.no_grad()
