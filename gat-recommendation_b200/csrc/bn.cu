@@ -6,6 +6,8 @@
 // reduction: stats (per-CTA column sums in double, fixed-order second stage) -> [caller may
 // all-reduce 2*dim doubles across ranks] -> finalize -> apply.  Streaming, HBM-bound:
 // stats reads N*dim*4 B; apply reads 2 rows and writes 1 per node.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace etpgt {
@@ -27,6 +29,7 @@ template <int MODE>
 __global__ void bn_partial_kernel(const float* __restrict__ x, const float* __restrict__ y,
                                   const float* __restrict__ d_y, int64_t n, int dim,
                                   const float* __restrict__ mean, const float* __restrict__ invstd, int relu,
+                                  uint32_t drop_threshold, float keep_scale, uint64_t drop_seed,
                                   int64_t chunk, double* __restrict__ partial /* [grid][2][dim] */) {
   extern __shared__ double sm[];  // [blockDim.y][2][dim]
   const int tx = threadIdx.x, ty = threadIdx.y;
@@ -59,6 +62,10 @@ __global__ void bn_partial_kernel(const float* __restrict__ x, const float* __re
         s1[3] += (double)av.w * av.w;
       } else {
         float4 gv = g[u];
+        if (drop_threshold != 0) {   // the layer output was dropout(...): its gradient passes the same mask
+          const int64_t r = r0 + (int64_t)u * blockDim.y;
+          gv = mul4(gv, dropout_factors4(drop_seed, (uint64_t)(r * (dim / 4) + tx), drop_threshold, keep_scale));
+        }
         if (relu) {
           gv.x = o[u].x > 0.f ? gv.x : 0.f; gv.y = o[u].y > 0.f ? gv.y : 0.f;
           gv.z = o[u].z > 0.f ? gv.z : 0.f; gv.w = o[u].w > 0.f ? gv.w : 0.f;
@@ -122,7 +129,9 @@ __global__ void bn_from_running_kernel(const float* __restrict__ rm, const float
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const float* __restrict__ x, int64_t total4, int dim4, const float* __restrict__ mean,
                 const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ bias,
-                const float* __restrict__ residual, int relu, float* __restrict__ y) {
+                const float* __restrict__ residual, int relu, uint32_t drop_threshold, float keep_scale,
+                uint64_t drop_seed, float* __restrict__ y, __nv_bfloat16* __restrict__ y_hi,
+                __nv_bfloat16* __restrict__ y_lo) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % dim4) * 4;
     const float4 a = ldg4(x + 4 * i);
@@ -134,7 +143,18 @@ bn_apply_kernel(const float* __restrict__ x, int64_t total4, int dim4, const flo
     o.w = (a.w - mu.w) * is.w * ga.w + be.w;
     if (residual != nullptr) o = add4(o, ldg4(residual + 4 * i));
     if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    if (drop_threshold != 0) o = mul4(o, dropout_factors4(drop_seed, (uint64_t)i, drop_threshold, keep_scale));
     st4(y + 4 * i, o);
+    if (y_hi != nullptr) {   // the next layer's projection operand, split for the tensor cores (x = hi + lo)
+      const __nv_bfloat162 h0 = __floats2bfloat162_rn(o.x, o.y), h1 = __floats2bfloat162_rn(o.z, o.w);
+      const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+      const __nv_bfloat162 l0 = __floats2bfloat162_rn(o.x - f0.x, o.y - f0.y), l1 = __floats2bfloat162_rn(o.z - f1.x, o.w - f1.y);
+      uint2 ph, pl;
+      ph.x = *reinterpret_cast<const uint32_t*>(&h0); ph.y = *reinterpret_cast<const uint32_t*>(&h1);
+      pl.x = *reinterpret_cast<const uint32_t*>(&l0); pl.y = *reinterpret_cast<const uint32_t*>(&l1);
+      *reinterpret_cast<uint2*>(y_hi + 4 * i) = ph;
+      *reinterpret_cast<uint2*>(y_lo + 4 * i) = pl;
+    }
   }
 }
 
@@ -144,15 +164,18 @@ __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ d_y,
                     int64_t total4, int dim, const float* __restrict__ mean, const float* __restrict__ invstd,
                     const float* __restrict__ gamma, int relu, int training, const double* __restrict__ sums,
-                    double count, float* __restrict__ d_x) {
+                    double count, uint32_t drop_threshold, float keep_scale, uint64_t drop_seed,
+                    float* __restrict__ d_x, float* __restrict__ d_res) {
   const int dim4 = dim / 4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % dim4) * 4;
     float4 g = ldg4(d_y + 4 * i);
+    if (drop_threshold != 0) g = mul4(g, dropout_factors4(drop_seed, (uint64_t)i, drop_threshold, keep_scale));
     if (relu) {
       const float4 o = ldg4(y + 4 * i);
       g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f; g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
     }
+    if (d_res != nullptr) st4(d_res + 4 * i, g);   // gradient of the residual branch (same mask, same ReLU gate)
     const float4 is = ld4(invstd + c), ga = ld4(gamma + c);
     float4 r;
     if (training) {
@@ -184,7 +207,8 @@ __global__ void bn_param_grad_kernel(const double* __restrict__ local_sums, int 
 
 template <int MODE>
 int launch_partial(const float* x, const float* y, const float* d_y, int64_t n, int dim, const float* mean,
-                   const float* invstd, int relu, double* sums, void* ws, size_t ws_bytes, cudaStream_t stream) {
+                   const float* invstd, int relu, uint32_t drop_threshold, float keep_scale, uint64_t drop_seed,
+                   double* sums, void* ws, size_t ws_bytes, cudaStream_t stream) {
   const int parts = stat_parts(n);
   const size_t need = align_up((size_t)parts * 2 * dim * sizeof(double));
   if (ws_bytes < need) { set_error("bn: workspace %zu < %zu", ws_bytes, need); return ETPGT_EWORKSPACE; }
@@ -193,7 +217,8 @@ int launch_partial(const float* x, const float* y, const float* d_y, int64_t n, 
   const int tx = dim / 4;
   const int ty = 256 / tx > 0 ? 256 / tx : 1;
   const size_t smem = (size_t)ty * 2 * dim * sizeof(double);
-  bn_partial_kernel<MODE><<<parts, dim3(tx, ty), smem, stream>>>(x, y, d_y, n, dim, mean, invstd, relu, chunk, partial);
+  bn_partial_kernel<MODE><<<parts, dim3(tx, ty), smem, stream>>>(x, y, d_y, n, dim, mean, invstd, relu, drop_threshold,
+                                                                 keep_scale, drop_seed, chunk, partial);
   ETPGT_CHECK_LAUNCH("bn_partial");
   bn_reduce_kernel<<<(2 * dim * 32 + 255) / 256, 256, 0, stream>>>(partial, parts, 2 * dim, sums);
   ETPGT_CHECK_LAUNCH("bn_reduce");
@@ -213,7 +238,7 @@ extern "C" int etpgt_bn_stats(const float* x, int64_t n, int dim, double* sums, 
                               etpgt_stream_t stream) {
   ETPGT_REQUIRE(dim % 4 == 0 && dim >= 4 && dim <= 1024, "bn_stats: dim %d must be a multiple of 4 <= 1024", dim);
   ETPGT_REQUIRE(n >= 0 && x && sums, "bn_stats: bad arguments");
-  return launch_partial<0>(x, nullptr, nullptr, n, dim, nullptr, nullptr, 0, sums, ws, ws_bytes,
+  return launch_partial<0>(x, nullptr, nullptr, n, dim, nullptr, nullptr, 0, 0u, 1.f, 0ull, sums, ws, ws_bytes,
                            static_cast<cudaStream_t>(stream));
 }
 
@@ -235,40 +260,76 @@ extern "C" int etpgt_bn_from_running(const float* running_mean, const float* run
   return ETPGT_OK;
 }
 
-extern "C" int etpgt_bn_apply(const float* x, int64_t n, int dim, const float* mean, const float* invstd,
-                              const float* gamma, const float* bias, const float* residual, int relu, float* y,
-                              etpgt_stream_t stream) {
+// p -> (threshold = p * 2^32, scale = 1 / (1 - p)); p == 0 disables the mask
+static bool dropout_params(double p, uint32_t* threshold, float* keep_scale) {
+  if (!(p >= 0.0 && p < 1.0)) return false;
+  const double t = p * 4294967296.0;
+  *threshold = p > 0.0 ? (uint32_t)(t < 1.0 ? 1.0 : (t > 4294967295.0 ? 4294967295.0 : t)) : 0u;
+  *keep_scale = (float)(1.0 / (1.0 - p));
+  return true;
+}
+
+extern "C" int etpgt_bn_apply_ex(const float* x, int64_t n, int dim, const float* mean, const float* invstd,
+                                 const float* gamma, const float* bias, const float* residual, int relu,
+                                 double drop_p, uint64_t drop_seed, float* y, void* y_hi, void* y_lo,
+                                 etpgt_stream_t stream) {
   ETPGT_REQUIRE(dim % 4 == 0 && dim >= 4, "bn_apply: dim %d must be a multiple of 4", dim);
   ETPGT_REQUIRE(n >= 0 && x && mean && invstd && gamma && bias && y, "bn_apply: bad arguments");
+  ETPGT_REQUIRE((y_hi == nullptr) == (y_lo == nullptr), "bn_apply: split outputs come in pairs");
+  uint32_t threshold;
+  float keep_scale;
+  ETPGT_REQUIRE(dropout_params(drop_p, &threshold, &keep_scale), "bn_apply: dropout p must be in [0, 1)");
   if (n == 0) return ETPGT_OK;
   const int64_t total4 = n * (dim / 4);
   bn_apply_kernel<<<grid_for(total4, 256 * 4, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, total4, dim / 4, mean, invstd, gamma, bias, residual, relu, y);
+      x, total4, dim / 4, mean, invstd, gamma, bias, residual, relu, threshold, keep_scale, drop_seed, y,
+      static_cast<__nv_bfloat16*>(y_hi), static_cast<__nv_bfloat16*>(y_lo));
   ETPGT_CHECK_LAUNCH("bn_apply");
   return ETPGT_OK;
+}
+
+extern "C" int etpgt_bn_apply(const float* x, int64_t n, int dim, const float* mean, const float* invstd,
+                              const float* gamma, const float* bias, const float* residual, int relu, float* y,
+                              etpgt_stream_t stream) {
+  return etpgt_bn_apply_ex(x, n, dim, mean, invstd, gamma, bias, residual, relu, 0.0, 0, y, nullptr, nullptr, stream);
+}
+
+extern "C" int etpgt_bn_bwd_stats_ex(const float* x, const float* y, const float* d_y, int64_t n, int dim,
+                                     const float* mean, const float* invstd, int relu, double drop_p,
+                                     uint64_t drop_seed, double* sums, void* ws, size_t ws_bytes,
+                                     etpgt_stream_t stream) {
+  ETPGT_REQUIRE(dim % 4 == 0 && dim >= 4 && dim <= 1024, "bn_bwd_stats: dim %d must be a multiple of 4 <= 1024", dim);
+  ETPGT_REQUIRE(n >= 0 && x && d_y && mean && invstd && sums && (!relu || y), "bn_bwd_stats: bad arguments");
+  uint32_t threshold;
+  float keep_scale;
+  ETPGT_REQUIRE(dropout_params(drop_p, &threshold, &keep_scale), "bn_bwd_stats: dropout p must be in [0, 1)");
+  return launch_partial<1>(x, y, d_y, n, dim, mean, invstd, relu, threshold, keep_scale, drop_seed, sums, ws, ws_bytes,
+                           static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int etpgt_bn_bwd_stats(const float* x, const float* y, const float* d_y, int64_t n, int dim,
                                   const float* mean, const float* invstd, int relu, double* sums, void* ws,
                                   size_t ws_bytes, etpgt_stream_t stream) {
-  ETPGT_REQUIRE(dim % 4 == 0 && dim >= 4 && dim <= 1024, "bn_bwd_stats: dim %d must be a multiple of 4 <= 1024", dim);
-  ETPGT_REQUIRE(n >= 0 && x && d_y && mean && invstd && sums && (!relu || y), "bn_bwd_stats: bad arguments");
-  return launch_partial<1>(x, y, d_y, n, dim, mean, invstd, relu, sums, ws, ws_bytes,
-                           static_cast<cudaStream_t>(stream));
+  return etpgt_bn_bwd_stats_ex(x, y, d_y, n, dim, mean, invstd, relu, 0.0, 0, sums, ws, ws_bytes, stream);
 }
 
-extern "C" int etpgt_bn_bwd_apply(const float* x, const float* y, const float* d_y, int64_t n, int dim,
-                                  const float* mean, const float* invstd, const float* gamma, int relu,
-                                  int training, const double* sums, double count, const double* local_sums,
-                                  float* d_x, float* d_gamma, float* d_bias, etpgt_stream_t stream_) {
+extern "C" int etpgt_bn_bwd_apply_ex(const float* x, const float* y, const float* d_y, int64_t n, int dim,
+                                     const float* mean, const float* invstd, const float* gamma, int relu,
+                                     int training, const double* sums, double count, const double* local_sums,
+                                     double drop_p, uint64_t drop_seed, float* d_x, float* d_res, float* d_gamma,
+                                     float* d_bias, etpgt_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ETPGT_REQUIRE(dim % 4 == 0 && dim >= 4, "bn_bwd_apply: dim %d must be a multiple of 4", dim);
   ETPGT_REQUIRE(n >= 0 && d_y && mean && invstd && gamma && d_x && local_sums && (!training || (x && sums && (count >= 1 || count == 0))),
                 "bn_bwd_apply: bad arguments");
+  uint32_t threshold;
+  float keep_scale;
+  ETPGT_REQUIRE(dropout_params(drop_p, &threshold, &keep_scale), "bn_bwd_apply: dropout p must be in [0, 1)");
   if (n > 0) {
     const int64_t total4 = n * (dim / 4);
     bn_bwd_apply_kernel<<<grid_for(total4, 256 * 4, 8), 256, 0, stream>>>(x, y, d_y, total4, dim, mean, invstd, gamma,
-                                                                         relu, training, sums, count, d_x);
+                                                                         relu, training, sums, count, threshold,
+                                                                         keep_scale, drop_seed, d_x, d_res);
     ETPGT_CHECK_LAUNCH("bn_bwd_apply");
   }
   if (d_gamma != nullptr && d_bias != nullptr) {
@@ -276,4 +337,12 @@ extern "C" int etpgt_bn_bwd_apply(const float* x, const float* y, const float* d
     ETPGT_CHECK_LAUNCH("bn_param_grad");
   }
   return ETPGT_OK;
+}
+
+extern "C" int etpgt_bn_bwd_apply(const float* x, const float* y, const float* d_y, int64_t n, int dim,
+                                  const float* mean, const float* invstd, const float* gamma, int relu,
+                                  int training, const double* sums, double count, const double* local_sums,
+                                  float* d_x, float* d_gamma, float* d_bias, etpgt_stream_t stream) {
+  return etpgt_bn_bwd_apply_ex(x, y, d_y, n, dim, mean, invstd, gamma, relu, training, sums, count, local_sums, 0.0, 0,
+                               d_x, nullptr, d_gamma, d_bias, stream);
 }

@@ -141,6 +141,34 @@ __device__ __forceinline__ int head_of(int v, int lane_in_group) {
   return (v * RowGeom<DIM>::LPN + lane_in_group) / (HEAD_DIM / 4);
 }
 
+// ---------------------------------------------------------------------------- Philox4x32-10
+// Counter-based generator (Random123): the negative sampler (subgraph.cu) and the fused dropout of
+// the BatchNorm epilogue (bn.cu) draw from it, keyed by (seed, element index), so a mask never has
+// to be stored: forward and backward regenerate the same bits.
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+  const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+  c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+}
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+// Inverted-dropout factors of the four floats of float4 number `i4` of a tensor: 0 with probability
+// p, else 1/(1-p).  threshold = p * 2^32 (host side); word w keeps its element iff w >= threshold.
+__device__ __forceinline__ float4 dropout_factors4(uint64_t seed, uint64_t i4, uint32_t threshold, float keep_scale) {
+  uint32_t c[4] = {(uint32_t)i4, (uint32_t)(i4 >> 32), 0x44524F50u /* "DROP" */, 0u};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  return make_float4(c[0] >= threshold ? keep_scale : 0.f, c[1] >= threshold ? keep_scale : 0.f,
+                     c[2] >= threshold ? keep_scale : 0.f, c[3] >= threshold ? keep_scale : 0.f);
+}
+__device__ __forceinline__ float4 mul4(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+
 }  // namespace etpgt
 
 // Dispatch over the supported (dim, heads) pairs.  HEAD_DIM = dim / heads must be a power of

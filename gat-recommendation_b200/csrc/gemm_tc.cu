@@ -52,7 +52,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                    const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                    const __grid_constant__ CUtensorMap map_c /* C, or the [split_k][M][N] partials */,
                    int64_t M, int64_t N, int64_t K, int m_tiles, int n_tiles, int split_k, int kb_per_split,
-                   const float* __restrict__ bias, int a_mn, int b_mn) {
+                   const float* __restrict__ bias, int a_mn, int b_mn, int accumulate) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   constexpr uint32_t STAGE_BYTES = 2 * PARTS * TILE_BYTES;  // A parts then B parts
@@ -204,7 +204,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_3d(&map_c, my_cd + buf * CD_BOX_BYTES, col0 + c0, row0, split_k > 1 ? ks : 0);
+          if (accumulate && split_k == 1) tma_reduce_add_3d(&map_c, my_cd + buf * CD_BOX_BYTES, col0 + c0, row0, 0);
+          else tma_store_3d(&map_c, my_cd + buf * CD_BOX_BYTES, col0 + c0, row0, split_k > 1 ? ks : 0);
           tma_store_commit();
         }
         buf ^= 1;
@@ -223,11 +224,12 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
 // C[m][n] = bias[n] + sum_s partial[s][m][n], s ascending: deterministic split-K reduction.
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ partial, int split_k, int64_t M, int64_t N,
-                     const float* __restrict__ bias, float* __restrict__ C, int64_t ldc) {
+                     const float* __restrict__ bias, float* __restrict__ C, int64_t ldc, int accumulate) {
   const int64_t total4 = M * N / 4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t m = (4 * i) / N, n = (4 * i) % N;
     float4 acc = bias != nullptr ? ldg4(bias + n) : zero4();
+    if (accumulate) acc = add4(acc, ld4(C + m * ldc + n));
     for (int s = 0; s < split_k; ++s) acc = add4(acc, ldg4(partial + ((int64_t)s * M + m) * N + n));
     st4(C + m * ldc + n, acc);
   }
@@ -373,8 +375,8 @@ extern "C" size_t etpgt_gemm_bf16x3_workspace_bytes(int64_t M, int64_t N, int64_
 
 extern "C" int etpgt_gemm_bf16x3_ex(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int64_t M,
                                     int64_t N, int64_t K, int64_t lda, int64_t ldb, int a_mn_major, int b_mn_major,
-                                    const float* bias, float* C, int64_t ldc, int split_k, void* ws, size_t ws_bytes,
-                                    etpgt_stream_t stream_) {
+                                    const float* bias, int accumulate, float* C, int64_t ldc, int split_k, void* ws,
+                                    size_t ws_bytes, etpgt_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ETPGT_REQUIRE(M >= 0 && N > 0 && K > 0 && M < (int64_t(1) << 31) && N < (int64_t(1) << 31) && K < (int64_t(1) << 31),
                 "gemm_bf16x3: bad sizes");
@@ -419,16 +421,17 @@ extern "C" int etpgt_gemm_bf16x3_ex(const void* a_hi, const void* a_lo, const vo
     cudaFuncSetAttribute(gemm_bf16x3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     gemm_bf16x3_kernel<2><<<p.grid, kThreads, smem, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, mc, M, N, K, p.m_tiles,
                                                              p.n_tiles, p.split_k, p.kb_per_split, bias,
-                                                             a_mn_major != 0, b_mn_major != 0);
+                                                             a_mn_major != 0, b_mn_major != 0, accumulate != 0);
   } else {
     cudaFuncSetAttribute(gemm_bf16x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     gemm_bf16x3_kernel<1><<<p.grid, kThreads, smem, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, mc, M, N, K, p.m_tiles,
                                                              p.n_tiles, p.split_k, p.kb_per_split, bias,
-                                                             a_mn_major != 0, b_mn_major != 0);
+                                                             a_mn_major != 0, b_mn_major != 0, accumulate != 0);
   }
   ETPGT_CHECK_LAUNCH("gemm_bf16x3");
   if (p.split_k > 1) {
-    splitk_reduce_kernel<<<grid_for(M * N / 4, 256 * 2, 8), 256, 0, stream>>>(partial, p.split_k, M, N, bias, C, ldc);
+    splitk_reduce_kernel<<<grid_for(M * N / 4, 256 * 2, 8), 256, 0, stream>>>(partial, p.split_k, M, N, bias, C, ldc,
+                                                                              accumulate != 0);
     ETPGT_CHECK_LAUNCH("splitk_reduce");
   }
   return ETPGT_OK;
@@ -437,6 +440,6 @@ extern "C" int etpgt_gemm_bf16x3_ex(const void* a_hi, const void* a_lo, const vo
 extern "C" int etpgt_gemm_bf16x3(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int64_t M,
                                  int64_t N, int64_t K, int64_t lda, int64_t ldb, const float* bias, float* C,
                                  int64_t ldc, int split_k, void* ws, size_t ws_bytes, etpgt_stream_t stream) {
-  return etpgt_gemm_bf16x3_ex(a_hi, a_lo, b_hi, b_lo, M, N, K, lda, ldb, 0, 0, bias, C, ldc, split_k, ws, ws_bytes,
+  return etpgt_gemm_bf16x3_ex(a_hi, a_lo, b_hi, b_lo, M, N, K, lda, ldb, 0, 0, bias, 0, C, ldc, split_k, ws, ws_bytes,
                               stream);
 }

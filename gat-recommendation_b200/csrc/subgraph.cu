@@ -183,21 +183,7 @@ session_subgraph_kernel(const int32_t* __restrict__ gptr, const int32_t* __restr
 __global__ void set_zero_kernel(int32_t* p) { *p = 0; }
 
 // ---------------------------------------------------------------------------- Philox sampler
-__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
-  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
-  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
-  const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
-  c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
-}
-
-__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    philox_round(c, k0, k1);
-    k0 += 0x9E3779B9u;
-    k1 += 0xBB67AE85u;
-  }
-}
+// (philox4x32_10 lives in common.cuh)
 
 // One thread per (session, slot).  Stream definition: oracle/graph_ref.sample_negatives.
 __global__ void __launch_bounds__(kThreads)

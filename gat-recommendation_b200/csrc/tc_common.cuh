@@ -66,6 +66,12 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void*
                ::"l"((uint64_t)map), "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+// the same tile, ADDED element-wise to global memory (fp32 add in the L2, type from the tensor map)
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, const void* smem, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"((uint64_t)map), "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // at most PENDING of this thread's bulk groups still have to READ their shared-memory source
 template <int PENDING>

@@ -42,7 +42,7 @@ _PROTOTYPES = {
     "etpgt_split_bf16": (I, [P, L, L, L, P, P, L, P, P, L, P, P, Z, P]),
     "etpgt_gemm_bf16x3_workspace_bytes": (Z, [L, L, L, I]),
     "etpgt_gemm_bf16x3": (I, [P, P, P, P, L, L, L, L, L, P, P, L, I, P, Z, P]),
-    "etpgt_gemm_bf16x3_ex": (I, [P, P, P, P, L, L, L, L, L, I, I, P, P, L, I, P, Z, P]),
+    "etpgt_gemm_bf16x3_ex": (I, [P, P, P, P, L, L, L, L, L, I, I, P, I, P, L, I, P, Z, P]),
     "etpgt_gat_fwd": (I, [P, P, P, L, I, I, P, P, P, F, P, P, P, P, P, P]),
     "etpgt_gat_bwd_workspace_bytes": (Z, [L, L, I]),
     "etpgt_gat_bwd": (I, [P, P, P, P, P, L, I, I, P, P, P, P, P, P, L, F, P, P, P, P, P, P, P, P, Z, P]),
@@ -53,6 +53,9 @@ _PROTOTYPES = {
     "etpgt_bn_finalize": (I, [P, D, I, F, F, P, P, P, P, P]),
     "etpgt_bn_from_running": (I, [P, P, I, F, P, P, P]),
     "etpgt_bn_apply": (I, [P, L, I, P, P, P, P, P, I, P, P]),
+    "etpgt_bn_apply_ex": (I, [P, L, I, P, P, P, P, P, I, D, ctypes.c_uint64, P, P, P, P]),
+    "etpgt_bn_bwd_stats_ex": (I, [P, P, P, L, I, P, P, I, D, ctypes.c_uint64, P, P, Z, P]),
+    "etpgt_bn_bwd_apply_ex": (I, [P, P, P, L, I, P, P, P, I, I, P, D, P, D, ctypes.c_uint64, P, P, P, P, P]),
     "etpgt_bn_bwd_stats": (I, [P, P, P, L, I, P, P, I, P, P, Z, P]),
     "etpgt_bn_bwd_apply": (I, [P, P, P, L, I, P, P, P, I, I, P, D, P, P, P, P, P]),
     "etpgt_readout_fwd": (I, [P, P, L, I, I, P, P, P, P]),

@@ -7,7 +7,7 @@ import torch.nn as nn
 
 from .. import ops
 from ..encodings.laplacian_pe import LaplacianPECached
-from ..nn import TransformerConv, batch_norm_rows
+from ..nn import TransformerConv, batch_norm_rows, fused_layer_supported, transformer_layer
 from .base import BaseRecommendationModel, SessionReadout
 
 
@@ -46,9 +46,16 @@ class GraphTransformer(BaseRecommendationModel):
             w_pe, b_pe = self.laplacian_pe.projection.weight, self.laplacian_pe.projection.bias
         x = ops.EmbedPE.apply(ids, self.item_embedding.weight, pe, per_node, w_pe, b_pe,
                               self.item_embedding.padding_idx)
+        split = None   # bf16 hi/lo split of x, produced by the previous fused layer for this layer's GEMM
         for layer, (conv, bn) in enumerate(zip(self.convs, self.batch_norms)):
-            x = batch_norm_rows(bn, conv(x, index), residual=x, group=self.bn_process_group)
-            x = self.dropout_layer(x)
+            if fused_layer_supported(conv, bn, x):
+                drop_p = self.dropout_layer.p if self.training else 0.0
+                want_split = not self.use_ffn and layer + 1 < len(self.convs)
+                x, split = transformer_layer(conv, bn, x, split, index, drop_p, self.bn_process_group, want_split)
+            else:
+                x = batch_norm_rows(bn, conv(x, index), residual=x, group=self.bn_process_group)
+                x = self.dropout_layer(x)
+                split = None
             if self.use_ffn:
                 x = x + self.ffns[layer](x)
         return self.readout(x, batch.batch, self._num_sessions(batch))

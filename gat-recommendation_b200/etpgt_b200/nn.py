@@ -127,3 +127,28 @@ def batch_norm_rows(bn: nn.BatchNorm1d, x: torch.Tensor, residual: torch.Tensor 
     momentum = 0.1 if bn.momentum is None else bn.momentum
     return ops.BatchNormRows.apply(x, bn.weight, bn.bias, residual, bn.running_mean, bn.running_var, training,
                                    momentum, bn.eps, relu, group)
+
+
+def transformer_layer(conv: TransformerConv, bn: nn.BatchNorm1d, x: torch.Tensor, x_split, index, drop_p: float,
+                      group=None, want_split: bool = False):
+    """dropout(bn(conv(x)) + x) as ONE fused autograd node (ops.TransformerLayer); returns (y, split of
+    y or None).  Parameters / buffers of `conv` and `bn` are used and updated in place, so state dicts
+    stay those of the reference."""
+    training = bn.training or not bn.track_running_stats
+    if training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    momentum = 0.1 if bn.momentum is None else bn.momentum
+    alpha_mask = _alpha_dropout_mask(index.num_edges, conv.heads, conv.dropout, conv.training, x)
+    weight, bias = conv.fused_parameters()
+    w_beta = None if conv.lin_beta is None else conv.lin_beta.weight
+    seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if drop_p > 0.0 else 0   # torch's CPU generator
+    y, y_hi, y_lo = ops.TransformerLayer.apply(
+        x, x_split, weight, bias, w_beta, alpha_mask, index, conv.heads, bn.weight, bn.bias, bn.running_mean,
+        bn.running_var, training, momentum, bn.eps, group, drop_p, seed, want_split)
+    return y, ((y_hi, y_lo) if want_split else None)
+
+
+def fused_layer_supported(conv: TransformerConv, bn: nn.BatchNorm1d, x: torch.Tensor) -> bool:
+    width = 4 * conv.heads * conv.out_channels
+    return ops.FUSED_LAYER and isinstance(conv, TransformerConv) and bn.affine and bn.track_running_stats and \
+        x.size(1) == conv.heads * conv.out_channels and ops.fused_conv_supported(x, conv.in_channels, width)

@@ -202,13 +202,15 @@ def _split(src: torch.Tensor, rowmajor: bool, transposed: bool, colsum: bool = F
     return hi, lo, hi_t, lo_t, ld_t, sums
 
 
-def _gemm_x3(a_hi, a_lo, b_hi, b_lo, m, n, k, lda, ldb, bias, split_k=1, a_mn=False, b_mn=False) -> torch.Tensor:
+def _gemm_x3(a_hi, a_lo, b_hi, b_lo, m, n, k, lda, ldb, bias, split_k=1, a_mn=False, b_mn=False,
+             accumulate_into=None) -> torch.Tensor:
     """C[m,n] = A B^T (+bias).  a_mn / b_mn: that operand is stored as its transpose ([k, m] / [k, n]
-    row-major) and read MN-major by the tensor cores — no transposed copy is made."""
-    out = torch.empty(m, n, dtype=torch.float32, device=a_hi.device)
+    row-major) and read MN-major by the tensor cores — no transposed copy is made.  accumulate_into: an
+    existing fp32 [m, n] tensor the product is ADDED to (TMA reduce-add) and that is returned."""
+    out = accumulate_into if accumulate_into is not None else torch.empty(m, n, dtype=torch.float32, device=a_hi.device)
     ws = workspace(size("etpgt_gemm_bf16x3_workspace_bytes", m, n, k, split_k), a_hi.device)
     call("etpgt_gemm_bf16x3_ex", ptr(a_hi), ptr(a_lo), ptr(b_hi), ptr(b_lo), m, n, k, lda, ldb, int(a_mn), int(b_mn),
-         ptr(bias), ptr(out), n, split_k, ptr(ws), ws.numel(), stream())
+         ptr(bias), int(accumulate_into is not None), ptr(out), n, split_k, ptr(ws), ws.numel(), stream())
     return out
 
 
@@ -307,6 +309,124 @@ class TransformerConvLayer(torch.autograd.Function):
         return d_x, d_w, d_bias, d_w_beta, None, None, None
 
 
+class TransformerLayer(torch.autograd.Function):
+    """One whole layer of the optimized GraphTransformer (etpgt/model/graph_transformer.py:172-177):
+
+        y = dropout_p( BatchNorm1d( TransformerConv(x, edges) ) + x )
+
+    Forward: split(x) [skipped when the previous layer already produced it] -> projection GEMM ->
+    fused conv -> BN statistics (all-reduced under data parallelism) -> one apply kernel doing affine +
+    residual + Philox dropout and, when asked, the bf16 split of y for the next layer.
+    Backward: BN statistics / apply with the regenerated dropout mask (also emitting the residual
+    branch's gradient), the edge kernels writing split-bf16 d(qkvs) + bias column sums, then
+    dX = d_res + dQKVS x W (accumulated by the GEMM's TMA reduce-add) and dW (split-K).
+    No dropout mask, no fp32 d(qkvs), no autograd add for the residual ever touch HBM."""
+
+    @staticmethod
+    def forward(ctx, x, x_split, weight, bias, w_beta, alpha_mask, index: GraphIndex, heads, gamma, bn_bias,
+                running_mean, running_var, training, momentum, eps, group, drop_p, drop_seed, want_split):
+        _require_cuda(x, "node features")
+        x, weight, bias_c = _f32(x), _f32(weight), _f32(bias)
+        n, k = x.shape
+        width = weight.size(0)
+        dim = width // 4
+        dev = x.device
+        if x_split is None:
+            x_hi, x_lo, _, _, _, _ = _split(x, True, False)
+        else:
+            x_hi, x_lo = x_split
+        w_hi, w_lo, _, _, _, _ = _split(weight, True, False)
+        qkvs = _gemm_x3(x_hi, x_lo, w_hi, w_lo, n, width, k, k, k, bias_c)
+        w_beta_c = _f32(w_beta).reshape(-1) if w_beta is not None else None
+        mask_c = _f32(alpha_mask) if alpha_mask is not None else None
+        f32 = dict(dtype=torch.float32, device=dev)
+        conv_out, agg = torch.empty(n, dim, **f32), torch.empty(n, dim, **f32)
+        beta, m, inv_l = torch.empty(n, **f32), torch.empty(n, heads, **f32), torch.empty(n, heads, **f32)
+        call("etpgt_tconv_fwd", ptr(qkvs), n, dim, heads, ptr(index.rowptr), ptr(index.col), ptr(index.eperm),
+             index.num_edges, ptr(w_beta_c), ptr(mask_c), ptr(conv_out), ptr(agg), ptr(beta), ptr(m), ptr(inv_l),
+             stream())
+        gamma_c, bn_bias_c = _f32(gamma), _f32(bn_bias)
+        mean, invstd = torch.empty(dim, **f32), torch.empty(dim, **f32)
+        count = float(n)
+        if training:
+            sums = torch.empty(2 * dim + 1, dtype=torch.float64, device=dev)
+            ws = workspace(size("etpgt_bn_workspace_bytes", n, dim), dev)
+            call("etpgt_bn_stats", ptr(conv_out), n, dim, ptr(sums), ptr(ws), ws.numel(), stream())
+            if _dist_ready(group):
+                sums[2 * dim:].fill_(count)
+                dist.all_reduce(sums, group=group or None)
+                count = 0.0
+            elif count < 2:
+                raise ValueError("Expected more than 1 value per channel when training")
+            call("etpgt_bn_finalize", ptr(sums), count, dim, float(eps), float(momentum), ptr(mean), ptr(invstd),
+                 ptr(running_mean), ptr(running_var), stream())
+        else:
+            call("etpgt_bn_from_running", ptr(running_mean), ptr(running_var), dim, float(eps), ptr(mean),
+                 ptr(invstd), stream())
+        y = torch.empty(n, dim, **f32)
+        y_hi = y_lo = None
+        if want_split:
+            y_hi = torch.empty(n, dim, dtype=torch.bfloat16, device=dev)
+            y_lo = torch.empty(n, dim, dtype=torch.bfloat16, device=dev)
+        call("etpgt_bn_apply_ex", ptr(conv_out), n, dim, ptr(mean), ptr(invstd), ptr(gamma_c), ptr(bn_bias_c), ptr(x),
+             0, float(drop_p), int(drop_seed), ptr(y), ptr(y_hi), ptr(y_lo), stream())
+        ctx.save_for_backward(x_hi, x_lo, w_hi, w_lo, qkvs, w_beta_c, mask_c, agg, beta, m, inv_l, conv_out, mean,
+                              invstd, gamma_c)
+        ctx.index, ctx.heads = index, heads
+        ctx.meta = (bool(training), count, group, float(drop_p), int(drop_seed))
+        ctx.w_beta_shape = None if w_beta is None else tuple(w_beta.shape)
+        if want_split:
+            ctx.mark_non_differentiable(y_hi, y_lo)
+        return y, y_hi, y_lo
+
+    @staticmethod
+    def backward(ctx, d_y, _d_hi, _d_lo):
+        (x_hi, x_lo, w_hi, w_lo, qkvs, w_beta, mask, agg, beta, m, inv_l, conv_out, mean, invstd,
+         gamma) = ctx.saved_tensors
+        index, heads = ctx.index, ctx.heads
+        training, count, group, drop_p, drop_seed = ctx.meta
+        d_y = _f32(d_y)
+        n, k = x_hi.shape
+        width = w_hi.size(0)
+        dim = width // 4
+        dev = d_y.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        # BatchNorm backward (the dropout mask is regenerated from the seed)
+        local = torch.empty(2 * dim + 1, dtype=torch.float64, device=dev)
+        ws = workspace(size("etpgt_bn_workspace_bytes", n, dim), dev)
+        call("etpgt_bn_bwd_stats_ex", ptr(conv_out), None, ptr(d_y), n, dim, ptr(mean), ptr(invstd), 0, drop_p,
+             drop_seed, ptr(local), ptr(ws), ws.numel(), stream())
+        sums = local
+        if training and _dist_ready(group):
+            local[2 * dim:].fill_(float(n))
+            sums = local.clone()
+            dist.all_reduce(sums, group=group or None)
+        d_conv, d_res = torch.empty(n, dim, **f32), torch.empty(n, dim, **f32)
+        d_gamma, d_bn_bias = torch.empty(dim, **f32), torch.empty(dim, **f32)
+        call("etpgt_bn_bwd_apply_ex", ptr(conv_out), None, ptr(d_y), n, dim, ptr(mean), ptr(invstd), ptr(gamma), 0,
+             int(training), ptr(sums), count, ptr(local), drop_p, drop_seed, ptr(d_conv), ptr(d_res), ptr(d_gamma),
+             ptr(d_bn_bias), stream())
+        # conv backward: split-bf16 d(qkvs) + its column sums (the fused bias gradient)
+        g_hi = torch.empty(n, width, dtype=torch.bfloat16, device=dev)
+        g_lo = torch.empty(n, width, dtype=torch.bfloat16, device=dev)
+        d_bias = torch.empty(width, **f32)
+        d_w_beta = torch.empty(3 * dim, **f32) if w_beta is not None else None
+        ws = workspace(size("etpgt_tconv_bwd_workspace_bytes", n, index.num_edges, dim, heads), dev)
+        call("etpgt_tconv_bwd_split", ptr(qkvs), ptr(d_conv), n, dim, heads, ptr(index.rowptr), ptr(index.col),
+             ptr(index.eperm), ptr(index.colptr), ptr(index.row), ptr(index.cpos), index.num_edges, ptr(w_beta),
+             ptr(mask), ptr(agg), ptr(beta), ptr(m), ptr(inv_l), None, ptr(g_hi), ptr(g_lo), ptr(d_bias),
+             ptr(d_w_beta), ptr(ws), ws.numel(), stream())
+        d_x = d_w = None
+        if ctx.needs_input_grad[0]:   # residual branch + projection branch, summed by the GEMM epilogue
+            d_x = _gemm_x3(g_hi, g_lo, w_hi, w_lo, n, k, width, width, k, None, b_mn=True, accumulate_into=d_res)
+        if ctx.needs_input_grad[2]:
+            d_w = _gemm_x3(g_hi, g_lo, x_hi, x_lo, width, k, n, width, k, None, split_k=0, a_mn=True, b_mn=True)
+        if d_w_beta is not None:
+            d_w_beta = d_w_beta.view(ctx.w_beta_shape)
+        return (d_x, None, d_w, d_bias, d_w_beta, None, None, None, d_gamma, d_bn_bias, None, None, None, None, None,
+                None, None, None, None)
+
+
 def fused_conv_supported(x: torch.Tensor, in_channels: int, width: int) -> bool:
     return PROJECTION_BACKEND == "tcgen05" and x.is_cuda and x.size(0) > 0 and in_channels % 8 == 0 and \
         width % 32 == 0 and supported_dim(width // 4)
@@ -328,6 +448,7 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None) -> 
 import os as _os  # noqa: E402
 
 PROJECTION_BACKEND = _os.environ.get("ETPGT_PROJECTION", "tcgen05")
+FUSED_LAYER = _os.environ.get("ETPGT_FUSED_LAYER", "1") != "0"   # ops.TransformerLayer (conv + BN + residual + dropout)
 
 
 # ------------------------------------------------------------------------------ GAT / GraphSAGE

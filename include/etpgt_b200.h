@@ -179,11 +179,14 @@ int etpgt_gemm_bf16x3(const void* a_hi, const void* a_lo, const void* b_hi, cons
  * given as [K, M] row-major (pitch lda >= M), b_mn_major != 0 means B is given as [K, N] row-major
  * (pitch ldb >= N).  This is what the two backward GEMMs of a Linear layer need without any
  * transposed copies: dX[nodes,in] = dY[nodes,out] (K-major) x W[out,in] (B MN-major), and
- * dW[out,in] = dY[nodes,out] (A MN-major) x X[nodes,in] (B MN-major), K = nodes. */
+ * dW[out,in] = dY[nodes,out] (A MN-major) x X[nodes,in] (B MN-major), K = nodes.
+ * accumulate != 0: C += A B^T (+ bias) — the tiles are added to C by the TMA unit
+ * (cp.reduce.async.bulk.tensor .add, one add per element: deterministic), which is how the residual
+ * branch's gradient is merged into dX without a separate add pass. */
 int etpgt_gemm_bf16x3_ex(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,
                          int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb,
                          int a_mn_major, int b_mn_major,
-                         const float* bias, float* c, int64_t ldc, int split_k,
+                         const float* bias, int accumulate, float* c, int64_t ldc, int split_k,
                          void* ws, size_t ws_bytes, etpgt_stream_t stream);
 
 /* ---- a12: GAT edge-softmax aggregation and GraphSAGE mean aggregation ---------------------
@@ -232,6 +235,15 @@ int etpgt_bn_from_running(const float* running_mean, const float* running_var, i
 int etpgt_bn_apply(const float* x, int64_t n, int dim, const float* mean, const float* invstd,
                    const float* gamma, const float* bias, const float* residual, int relu,
                    float* y, etpgt_stream_t stream);
+/* The same with the layer's dropout fused in (etpgt/model/graph_transformer.py:176-177
+ * `x = self.dropout_layer(x)`): y = dropout_p(bn(x) + residual) with a counter-based Philox4x32-10
+ * mask keyed by (drop_seed, element index) that the backward entry points regenerate, so no mask is
+ * stored; drop_p == 0 disables it.  y_hi / y_lo (both or neither): y also written split as bf16
+ * pairs (y = hi + lo), the operand format of the next layer's tensor-core projection. */
+int etpgt_bn_apply_ex(const float* x, int64_t n, int dim, const float* mean, const float* invstd,
+                      const float* gamma, const float* bias, const float* residual, int relu,
+                      double drop_p, uint64_t drop_seed, float* y, void* y_hi, void* y_lo,
+                      etpgt_stream_t stream);
 /* backward step 1: sums[0:dim] = sum g, sums[dim:2dim] = sum g*xhat with g = d_y (masked by
  * y > 0 when relu).  All-reduced across ranks by the caller in training mode. */
 int etpgt_bn_bwd_stats(const float* x, const float* y, const float* d_y, int64_t n, int dim,
@@ -243,6 +255,18 @@ int etpgt_bn_bwd_apply(const float* x, const float* y, const float* d_y, int64_t
                        const float* mean, const float* invstd, const float* gamma, int relu,
                        int training, const double* sums, double count, const double* local_sums,
                        float* d_x, float* d_gamma, float* d_bias, etpgt_stream_t stream);
+
+/* Backward of etpgt_bn_apply_ex: g = d_y * dropout mask (* [y > 0] with relu); d_res (optional)
+ * receives g, the gradient of the residual branch. */
+int etpgt_bn_bwd_stats_ex(const float* x, const float* y, const float* d_y, int64_t n, int dim,
+                          const float* mean, const float* invstd, int relu, double drop_p,
+                          uint64_t drop_seed, double* sums, void* ws, size_t ws_bytes,
+                          etpgt_stream_t stream);
+int etpgt_bn_bwd_apply_ex(const float* x, const float* y, const float* d_y, int64_t n, int dim,
+                          const float* mean, const float* invstd, const float* gamma, int relu,
+                          int training, const double* sums, double count, const double* local_sums,
+                          double drop_p, uint64_t drop_seed, float* d_x, float* d_res,
+                          float* d_gamma, float* d_bias, etpgt_stream_t stream);
 
 /* ---- a7: session readout (segmented reduction) ------------------------------------------
  * etpgt/model/base.py:136-193.  mode: 0 mean, 1 max, 2 last, 3 attention (softmax of the

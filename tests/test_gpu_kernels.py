@@ -445,3 +445,69 @@ def test_topk_merge_and_metrics(ops):
     assert compute_recall_at_k(preds, tg, 5) == pytest.approx(2 / 3)
     assert compute_recall_at_k(preds, tg, 2) == pytest.approx(1 / 3)
     assert compute_ndcg_at_k(preds, tg, 5) == pytest.approx(g.raw["met/ndcg5"].item(), abs=1e-6)
+
+
+# ------------------------------------------------------------------------------ fused dropout in the BN epilogue
+
+
+@pytest.mark.parametrize("p,relu,res", [(0.1, False, True), (0.5, True, False), (0.9, False, True)])
+def test_batch_norm_fused_dropout_forward_backward(ops, p, relu, res):
+    """etpgt_bn_apply_ex / _bwd_stats_ex / _bwd_apply_ex: y = dropout_p(relu?(bn(x) + residual)).  The
+    Philox mask is never stored: it is recovered here from y / y(p=0) and every backward quantity is
+    recomputed with it in fp64."""
+    from etpgt_b200._lib import call, ptr, size, stream, workspace
+
+    n, dim, seed = 3000, 256, 123456789
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(n, dim, generator=g).cuda()
+    r = torch.randn(n, dim, generator=g).cuda() if res else None
+    gamma, bias = (torch.rand(dim, generator=g) + 0.5).cuda(), torch.randn(dim, generator=g).cuda()
+    mean, invstd = x.mean(0), 1.0 / (x.var(0, unbiased=False) + 1e-5).sqrt()
+    d_y = torch.randn(n, dim, generator=g).cuda()
+
+    def apply(pp, split=False):
+        y = torch.empty_like(x)
+        hi = torch.empty(n, dim, dtype=torch.bfloat16, device="cuda") if split else None
+        lo = torch.empty_like(hi) if split else None
+        call("etpgt_bn_apply_ex", ptr(x), n, dim, ptr(mean), ptr(invstd), ptr(gamma), ptr(bias), ptr(r), int(relu),
+             float(pp), seed, ptr(y), ptr(hi), ptr(lo), stream())
+        return y, hi, lo
+
+    y0, _, _ = apply(0.0)
+    y, hi, lo = apply(p, split=True)
+    want0 = (x.double() - mean.double()) * invstd.double() * gamma.double() + bias.double()
+    if res:
+        want0 = want0 + r.double()
+    if relu:
+        want0 = want0.clamp_min(0)
+    assert rel_err(y0, want0) < 1e-5
+    keep = 1.0 / (1.0 - p)
+    nz = y0 != 0
+    factor = torch.where(nz, y / torch.where(nz, y0, torch.ones_like(y0)), torch.full_like(y0, float("nan")))
+    kept = (factor - keep).abs() < 1e-5 * keep
+    dropped = factor == 0
+    assert bool((kept | dropped | ~nz).all())                       # every element is 0 or y0 / (1 - p)
+    frac = dropped[nz].float().mean().item()
+    assert abs(frac - p) < 5 * (p * (1 - p) / nz.sum().item()) ** 0.5 + 1e-3
+    y2, _, _ = apply(p)
+    assert torch.equal(y, y2)                                        # same seed -> same mask
+    assert torch.equal(hi, y.to(torch.bfloat16)) and torch.equal(lo, (y - hi.float()).to(torch.bfloat16))
+    # backward with the regenerated mask (where y0 == 0 the mask is unobservable: only ReLU zeros, whose
+    # gradient is gated off anyway)
+    mask = torch.where(dropped, torch.zeros_like(y0), torch.full_like(y0, keep)).double()
+    gate = (y0 > 0).double() if relu else torch.ones_like(mask)
+    gtrue = d_y.double() * mask * gate
+    xhat = (x.double() - mean.double()) * invstd.double()
+    sums = torch.empty(2 * dim + 1, dtype=torch.float64, device="cuda")
+    ws = workspace(size("etpgt_bn_workspace_bytes", n, dim), "cuda")
+    call("etpgt_bn_bwd_stats_ex", ptr(x), ptr(y), ptr(d_y), n, dim, ptr(mean), ptr(invstd), int(relu), float(p), seed,
+         ptr(sums), ptr(ws), ws.numel(), stream())
+    assert rel_err(sums[:dim], gtrue.sum(0)) < 1e-6 and rel_err(sums[dim:2 * dim], (gtrue * xhat).sum(0)) < 1e-6
+    d_x, d_res = torch.empty_like(x), torch.empty_like(x)
+    d_gamma, d_bias = torch.empty(dim, device="cuda"), torch.empty(dim, device="cuda")
+    call("etpgt_bn_bwd_apply_ex", ptr(x), ptr(y), ptr(d_y), n, dim, ptr(mean), ptr(invstd), ptr(gamma), int(relu), 1,
+         ptr(sums), float(n), ptr(sums), float(p), seed, ptr(d_x), ptr(d_res), ptr(d_gamma), ptr(d_bias), stream())
+    assert rel_err(d_res, gtrue) < 1e-6
+    want_dx = gamma.double() * invstd.double() * (gtrue - gtrue.mean(0) - xhat * (gtrue * xhat).mean(0))
+    assert rel_err(d_x, want_dx) < 1e-5
+    assert rel_err(d_bias, gtrue.sum(0)) < 1e-5 and rel_err(d_gamma, (gtrue * xhat).sum(0)) < 1e-5

@@ -135,3 +135,71 @@ def test_training_dropout_is_applied_and_finite():
     loss = model.compute_loss(a, g.tensor("target").cuda(), g.tensor("negatives").cuda())
     loss.backward()
     assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
+
+
+def test_fused_layer_equals_unfused_layer_bit_for_bit():
+    """ops.TransformerLayer (conv + BN + residual + dropout in one autograd node, split hand-over between
+    layers, residual gradient accumulated by the GEMM's TMA reduce-add) against the same kernels driven
+    as separate autograd nodes: identical outputs, gradients and running statistics (p = 0)."""
+    import numpy as np
+
+    import etpgt_b200.ops as ops
+    from etpgt_b200 import data, synth
+    from etpgt_b200.model import create_graph_transformer_optimized
+
+    d = synth.generate(num_sessions=900, graph_sessions=700, num_items=500, clusters=16, seed=5)
+    graph = data.ItemGraph(d.item_i, d.item_j, d.num_items)
+    store = data.SessionStore(d.sess_ptr, d.sess_items)
+    ids = np.arange(300)
+    results = []
+    for fused in (True, False):
+        ops.FUSED_LAYER = fused
+        try:
+            torch.manual_seed(3)
+            model = create_graph_transformer_optimized(d.num_items, 256, 256, dropout=0.0).cuda()
+            model.laplacian_pe._cached_pe = torch.randn(d.num_items, 16, generator=torch.Generator().manual_seed(7)).abs().cuda()
+            model.train()
+            batch = data.build_batch(graph, store, ids, 50, True, True)
+            neg = data.sample_negatives(store, ids, d.num_items, 5, seed=3, step=0)
+            out = model(batch)
+            model.compute_loss(out, batch.target_item, neg).backward()
+            results.append((out.detach().clone(), {k: p.grad.clone() for k, p in model.named_parameters()},
+                            {k: v.clone() for k, v in model.state_dict().items() if "running" in k}))
+        finally:
+            ops.FUSED_LAYER = True
+    (o1, g1, r1), (o2, g2, r2) = results
+    assert torch.equal(o1, o2)
+    for k in g1:
+        assert torch.equal(g1[k], g2[k]), k
+    for k in r1:
+        assert torch.equal(r1[k], r2[k]), k
+
+
+def test_fused_layer_training_mode_dropout_statistics():
+    """With dropout 0.5 the fused layer zeroes about half of every layer's outputs, is reproducible under
+    torch.manual_seed, and still back-propagates finite gradients to every parameter."""
+    import numpy as np
+
+    from etpgt_b200 import data, synth
+    from etpgt_b200.model import create_graph_transformer_optimized
+
+    d = synth.generate(num_sessions=900, graph_sessions=700, num_items=500, clusters=16, seed=5)
+    graph = data.ItemGraph(d.item_i, d.item_j, d.num_items)
+    store = data.SessionStore(d.sess_ptr, d.sess_items)
+    batch = data.build_batch(graph, store, np.arange(400), 50, True, True)
+    torch.manual_seed(3)
+    model = create_graph_transformer_optimized(d.num_items, 256, 256, dropout=0.5, readout_type="last").cuda()
+    model.laplacian_pe._cached_pe = torch.randn(d.num_items, 16).abs().cuda()
+    model.train()
+    torch.manual_seed(11)
+    a = model(batch)
+    torch.manual_seed(11)
+    b = model(batch)
+    assert torch.equal(a, b)
+    zero_frac = (a == 0).float().mean().item()          # "last" readout = rows of the last layer's output
+    assert 0.45 < zero_frac < 0.55
+    a.square().mean().backward()
+    for name, p in model.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), name
+    model.eval()
+    assert (model(batch) == 0).float().mean().item() < 0.01

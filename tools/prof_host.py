@@ -12,7 +12,7 @@ ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT / "gat-recommendation_b200"))
 sys.path.insert(0, str(ROOT))
 import bench  # noqa: E402
-from etpgt_b200 import ops, synth  # noqa: E402
+from etpgt_b200 import ops, optim, synth  # noqa: E402
 from etpgt_b200.model import create_graph_transformer_optimized  # noqa: E402
 
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
@@ -23,14 +23,14 @@ hb = bench.make_batches(data, keys, 0, batch, 2, seed=1, pin=True)
 db = [h.to_device(dev) for h in hb]
 model = create_graph_transformer_optimized(bench.NUM_ITEMS, 256, 256, 2, 2, dropout=0.1).to(dev)
 model.laplacian_pe._cached_pe = bench.cached_pe(bench.NUM_ITEMS).to(dev)
-opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-5, fused=True)
+opt = optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-5)
 model.train()
 
 
 def step(b):
     sess = model(b)
     loss = ops.sampled_loss(sess, model.item_embedding, b.target_item, b.negative_items, "bpr")[0]
-    opt.zero_grad(set_to_none=True)
+    opt.zero_grad()
     loss.backward()
     opt.step()
 
@@ -51,4 +51,4 @@ for i in range(20):
 torch.cuda.synchronize()
 pr.disable()
 st = pstats.Stats(pr)
-st.sort_stats("tottime").print_stats(22)
+st.sort_stats("tottime").print_stats(40)
