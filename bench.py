@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--cpu-batch", type=int, default=1024, help="sessions per step of the CPU sample")
     ap.add_argument("--rotate", type=int, default=4, help="distinct batches rotated through the timed steps")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--sweep-batch", type=int, default=65536,
+                    help="extra device-resident measurement at this batch size (rank 0, 1 GPU; 0 = off)")
     return ap.parse_args()
 
 
@@ -273,6 +275,7 @@ def run_b200(args, rank, world_size, local_rank):
     model.train()
 
     def step(batch):
+        nonlocal total_sessions
         sess = model(batch)
         loss = ops.sampled_loss(sess, model.item_embedding, batch.target_item, batch.negative_items, "bpr",
                                 total_sessions=total_sessions)[0]
@@ -377,9 +380,25 @@ def run_b200(args, rank, world_size, local_rank):
         "final_loss": losses[-1] if losses else None,
         "batch_shape": {"nodes": host_batches[0].nodes, "edges": host_batches[0].edges},
     }
+    if rank == 0 and world_size == 1 and args.sweep_batch > args.batch:
+        # the step at 16,384 sessions is close to host-launch-bound (about 60 launches in ~2 ms); the same
+        # step at a larger batch shows what the kernels sustain when the device is the limit
+        big = [hb.to_device(device) for hb in make_batches(data, edge_keys, 0, args.sweep_batch, 2, seed=7, pin=False)]
+        total_sessions = args.sweep_batch
+        for i in range(3):
+            step(big[i % 2])
+        sweep_steps = max(args.steps // 2, 4)
+        ms_big = timed(lambda i: step(big[i % 2]), sweep_steps)
+        out["batch_sweep"] = [{"sessions_per_step": args.sweep_batch, "ms_per_step": ms_big / sweep_steps,
+                               "value": args.sweep_batch * sweep_steps / (ms_big / 1e3), "unit": "sessions/s",
+                               "nodes": big[0].x.numel(), "edges": big[0].edge_index.size(1)}]
+        total_sessions = args.batch * world_size
+        del big
     if rank == 0:
         out["scoring"] = scoring_roofline(model, device)
         out["roofline"] = tconv_roofline(model, dev_batches[0], data, device)
+        if world_size == 1:
+            out["baseline_models"] = baseline_models(dev_batches, device)
         out["edges_per_s_tconv_fwd_bwd"] = out["roofline"].pop("edges_per_s")
         if world_size == 1 and not args.skip_cpu_baseline:
             steps = 2
@@ -389,6 +408,43 @@ def run_b200(args, rank, world_size, local_rank):
         print(json.dumps(out))
     if distributed:
         dist.destroy_process_group()
+
+
+def baseline_models(dev_batches, device, steps=10):
+    """BASELINE.json configs[2]: the GAT and GraphSAGE baselines (scripts/evaluate_local.py:33-58 shapes:
+    3 layers, GAT with 4 averaged heads) on the same session batches: training-step sessions/s with the
+    edge-softmax / mean-aggregation kernels, BPR loss and the device optimizer."""
+    from etpgt_b200 import ops, optim
+    from etpgt_b200.model import create_gat, create_graphsage
+
+    out = {}
+    sessions = dev_batches[0].num_graphs
+    for name, make in (("gat_l3_h4", lambda: create_gat(NUM_ITEMS, DIM, DIM, 3, 4, dropout=0.1)),
+                       ("graphsage_l3_mean", lambda: create_graphsage(NUM_ITEMS, DIM, DIM, 3, dropout=0.1))):
+        torch.manual_seed(0)
+        model = make().to(device)
+        opt = optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-5)
+        model.train()
+
+        def step(batch):
+            loss = ops.sampled_loss(model(batch), model.item_embedding, batch.target_item, batch.negative_items, "bpr")[0]
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+
+        for i in range(4):
+            step(dev_batches[i % len(dev_batches)])
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(steps):
+            step(dev_batches[i % len(dev_batches)])
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / steps
+        out[name] = {"ms_per_step": ms, "value": sessions / (ms / 1e3), "unit": "sessions/s"}
+        del model, opt
+    return out
 
 
 def scoring_roofline(model, device, sessions=23_861, k=20, reps=10):

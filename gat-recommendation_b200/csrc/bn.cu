@@ -205,6 +205,20 @@ __global__ void bn_param_grad_kernel(const double* __restrict__ local_sums, int 
   d_gamma[d] = (float)local_sums[dim + d];
 }
 
+// out[i] = 0 with probability p, else 1/(1-p): the inverted-dropout mask over attention coefficients
+// (PyG TransformerConv / GATConv `F.dropout(alpha, p)`), for every layer of a forward pass at once.
+__global__ void __launch_bounds__(256)
+dropout_mask_kernel(uint64_t seed, int64_t n4, int64_t n, uint32_t threshold, float keep_scale, float* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 f = dropout_factors4(seed, (uint64_t)i, threshold, keep_scale);
+    if (4 * i + 3 < n) st4(out + 4 * i, f);
+    else {
+      const float e[4] = {f.x, f.y, f.z, f.w};
+      for (int c = 0; c < 4 && 4 * i + c < n; ++c) out[4 * i + c] = e[c];
+    }
+  }
+}
+
 template <int MODE>
 int launch_partial(const float* x, const float* y, const float* d_y, int64_t n, int dim, const float* mean,
                    const float* invstd, int relu, uint32_t drop_threshold, float keep_scale, uint64_t drop_seed,
@@ -267,6 +281,19 @@ static bool dropout_params(double p, uint32_t* threshold, float* keep_scale) {
   *threshold = p > 0.0 ? (uint32_t)(t < 1.0 ? 1.0 : (t > 4294967295.0 ? 4294967295.0 : t)) : 0u;
   *keep_scale = (float)(1.0 / (1.0 - p));
   return true;
+}
+
+extern "C" int etpgt_dropout_mask(uint64_t seed, double p, int64_t n, float* out, etpgt_stream_t stream) {
+  uint32_t threshold;
+  float keep_scale;
+  ETPGT_REQUIRE(dropout_params(p, &threshold, &keep_scale), "dropout_mask: p must be in [0, 1)");
+  ETPGT_REQUIRE(n >= 0 && (n == 0 || out != nullptr) && ((uintptr_t)out & 15) == 0, "dropout_mask: bad arguments");
+  if (n == 0) return ETPGT_OK;
+  const int64_t n4 = (n + 3) / 4;
+  dropout_mask_kernel<<<grid_for(n4, 256 * 4, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(seed, n4, n, threshold,
+                                                                                           keep_scale, out);
+  ETPGT_CHECK_LAUNCH("dropout_mask");
+  return ETPGT_OK;
 }
 
 extern "C" int etpgt_bn_apply_ex(const float* x, int64_t n, int dim, const float* mean, const float* invstd,

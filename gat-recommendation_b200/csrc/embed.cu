@@ -44,10 +44,32 @@ embed_pe_fwd_kernel(const int64_t* __restrict__ ids, int64_t n, const float* __r
       const float* prow = pe + (pe_per_node ? node : id) * (int64_t)k_pe;
 #pragma unroll
       for (int v = 0; v < G::V; ++v) acc[v] = add4(acc[v], ld4(bias + 4 * (v * G::LPN + lig)));
-      for (int k = 0; k < k_pe; ++k) {
-        const float p = __ldg(prow + k);
+      if ((k_pe & 3) == 0 && (k_pe >> 2) <= G::LPN) {
+        // the PE row is loaded ONCE (lane j of the group holds floats 4j..4j+3, in flight together with
+        // the table row) and broadcast by shuffles; a scalar load per k would serialise k_pe HBM round trips
+        const int quads = k_pe >> 2;
+        const float4 mine = lig < quads ? ldg4(prow + 4 * lig) : zero4();
+        const unsigned gmask = G::LPN == 32 ? 0xffffffffu : (((1u << (G::LPN % 32)) - 1u) << ((lane / G::LPN) * G::LPN));
+        const int src0 = (lane / G::LPN) * G::LPN;
+        for (int j = 0; j < quads; ++j) {
+          const float p0 = __shfl_sync(gmask, mine.x, src0 + j), p1 = __shfl_sync(gmask, mine.y, src0 + j);
+          const float p2 = __shfl_sync(gmask, mine.z, src0 + j), p3 = __shfl_sync(gmask, mine.w, src0 + j);
+          const float* w = wt + (size_t)(4 * j) * DIM;
 #pragma unroll
-        for (int v = 0; v < G::V; ++v) acc[v] = fma4(p, ld4(wt + k * DIM + 4 * (v * G::LPN + lig)), acc[v]);
+          for (int v = 0; v < G::V; ++v) {
+            const int c = 4 * (v * G::LPN + lig);
+            acc[v] = fma4(p0, ld4(w + c), acc[v]);
+            acc[v] = fma4(p1, ld4(w + DIM + c), acc[v]);
+            acc[v] = fma4(p2, ld4(w + 2 * DIM + c), acc[v]);
+            acc[v] = fma4(p3, ld4(w + 3 * DIM + c), acc[v]);
+          }
+        }
+      } else {
+        for (int k = 0; k < k_pe; ++k) {
+          const float p = __ldg(prow + k);
+#pragma unroll
+          for (int v = 0; v < G::V; ++v) acc[v] = fma4(p, ld4(wt + k * DIM + 4 * (v * G::LPN + lig)), acc[v]);
+        }
       }
     }
     float* orow = out + node * DIM;
@@ -82,11 +104,18 @@ pe_wgrad_partial_kernel(const int64_t* __restrict__ ids, int64_t n, const float*
       pe_tile[r][k] = pe[prow * KPE + k];
     }
     __syncthreads();
-    for (int r = 0; r < rows; ++r) {
-      const float g = d_out[(base + r) * DIM + d];
+    for (int r0 = 0; r0 < rows; r0 += 8) {   // eight independent row loads in flight per thread
+      float g[8];
 #pragma unroll
-      for (int k = 0; k < KPE; ++k) acc[k] = fmaf(g, pe_tile[r][k], acc[k]);
-      acc[KPE] += g;
+      for (int u = 0; u < 8; ++u) g[u] = r0 + u < rows ? d_out[(base + r0 + u) * DIM + d] : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (r0 + u < rows) {
+#pragma unroll
+          for (int k = 0; k < KPE; ++k) acc[k] = fmaf(g[u], pe_tile[r0 + u][k], acc[k]);
+          acc[KPE] += g[u];
+        }
+      }
     }
   }
   float* dst = partial + ((int64_t)blockIdx.x * DIM + d) * (KPE + 1);
@@ -109,8 +138,8 @@ __global__ void pe_wgrad_reduce_kernel(const float* __restrict__ partial, int pa
 }
 
 int wgrad_parts(int64_t n) {
-  int64_t parts = (n + 255) / 256;
-  if (parts > 2 * kNumSMs) parts = 2 * kNumSMs;
+  int64_t parts = (n + 63) / 64;
+  if (parts > 6 * kNumSMs) parts = 6 * kNumSMs;
   return parts < 1 ? 1 : (int)parts;
 }
 

@@ -53,6 +53,7 @@ _PROTOTYPES = {
     "etpgt_bn_finalize": (I, [P, D, I, F, F, P, P, P, P, P]),
     "etpgt_bn_from_running": (I, [P, P, I, F, P, P, P]),
     "etpgt_bn_apply": (I, [P, L, I, P, P, P, P, P, I, P, P]),
+    "etpgt_dropout_mask": (I, [ctypes.c_uint64, D, L, P, P]),
     "etpgt_bn_apply_ex": (I, [P, L, I, P, P, P, P, P, I, D, ctypes.c_uint64, P, P, P, P]),
     "etpgt_bn_bwd_stats_ex": (I, [P, P, P, L, I, P, P, I, D, ctypes.c_uint64, P, P, Z, P]),
     "etpgt_bn_bwd_apply_ex": (I, [P, P, P, L, I, P, P, P, I, I, P, D, P, D, ctypes.c_uint64, P, P, P, P, P]),

@@ -20,7 +20,7 @@ def _alpha_dropout_mask(num_edges: int, heads: int, p: float, training: bool, li
     """Inverted-dropout mask over the attention weights, in original edge order."""
     if not training or p <= 0.0:
         return None
-    return F.dropout(torch.ones(num_edges, heads, dtype=torch.float32, device=like.device), p=p, training=True)
+    return ops.dropout_mask(num_edges * heads, p, like.device).view(num_edges, heads)
 
 
 class TransformerConv(nn.Module):
@@ -43,7 +43,33 @@ class TransformerConv(nn.Module):
         self.lin_skip = nn.Linear(in_channels, width)
         self.lin_beta = nn.Linear(3 * width, 1, bias=False) if beta else None
 
+    def _fused(self, name: str):
+        """query | key | value | skip `name` ("weight" / "bias") as ONE tensor without copying: the four
+        parameters are re-homed (once per device move) as consecutive row blocks of a single buffer, and
+        ops.FusedRows presents that buffer to autograd as a function of the four parameters, so state
+        dicts, optimizers and checkpoints keep seeing four ordinary parameters."""
+        parts = [getattr(lin, name) for lin in (self.lin_query, self.lin_key, self.lin_value, self.lin_skip)]
+        cache = self.__dict__.setdefault("_fused_store", {})
+        store = cache.get(name)
+        offset, aliased = 0, store is not None
+        if aliased:
+            for p in parts:
+                aliased = aliased and p.data_ptr() == store.data_ptr() + offset * store.element_size() \
+                    and p.device == store.device and p.dtype == store.dtype
+                offset += p.numel()
+        if not aliased:
+            with torch.no_grad():
+                store = torch.cat([p.detach() for p in parts]).contiguous()
+                row = 0
+                for p in parts:
+                    p.data = store[row:row + p.size(0)]
+                    row += p.size(0)
+            cache[name] = store
+        return ops.FusedRows.apply(store, *parts)
+
     def fused_parameters(self):
+        if self.lin_query.weight.is_cuda and torch.is_grad_enabled():
+            return self._fused("weight"), self._fused("bias")
         weight = torch.cat([self.lin_query.weight, self.lin_key.weight, self.lin_value.weight, self.lin_skip.weight])
         bias = torch.cat([self.lin_query.bias, self.lin_key.bias, self.lin_value.bias, self.lin_skip.bias])
         return weight, bias
@@ -86,7 +112,7 @@ class GATConv(nn.Module):
     def forward(self, x, edge_index, mask_edges=None, mask_self=None):
         index = _as_index(edge_index, x.size(0))
         n, heads, c = x.size(0), self.heads, self.out_channels
-        h = self.lin(x)
+        h = ops.linear(x, self.lin.weight, None)      # tcgen05 split-bf16 GEMM (fp32-grade)
         hv = h.view(n, heads, c)
         a_src = (hv * self.att_src).sum(-1)
         a_dst = (hv * self.att_dst).sum(-1)
@@ -114,7 +140,8 @@ class SAGEConv(nn.Module):
 
     def forward(self, x, edge_index):
         index = _as_index(edge_index, x.size(0))
-        return self.lin_l(ops.SageMeanFn.apply(x, index)) + self.lin_r(x)
+        mean = ops.SageMeanFn.apply(x, index)
+        return ops.linear(mean, self.lin_l.weight, self.lin_l.bias) + ops.linear(x, self.lin_r.weight, None)
 
 
 def batch_norm_rows(bn: nn.BatchNorm1d, x: torch.Tensor, residual: torch.Tensor | None = None,

@@ -375,6 +375,7 @@ class TransformerLayer(torch.autograd.Function):
         ctx.index, ctx.heads = index, heads
         ctx.meta = (bool(training), count, group, float(drop_p), int(drop_seed))
         ctx.w_beta_shape = None if w_beta is None else tuple(w_beta.shape)
+        ctx.set_materialize_grads(False)   # no zero-filled "gradients" for the two bf16 hand-over outputs
         if want_split:
             ctx.mark_non_differentiable(y_hi, y_lo)
         return y, y_hi, y_lo
@@ -385,8 +386,10 @@ class TransformerLayer(torch.autograd.Function):
          gamma) = ctx.saved_tensors
         index, heads = ctx.index, ctx.heads
         training, count, group, drop_p, drop_seed = ctx.meta
-        d_y = _f32(d_y)
         n, k = x_hi.shape
+        if d_y is None:   # the layer output was not used downstream
+            d_y = torch.zeros(n, w_hi.size(0) // 4, dtype=torch.float32, device=x_hi.device)
+        d_y = _f32(d_y)
         width = w_hi.size(0)
         dim = width // 4
         dev = d_y.device
@@ -425,6 +428,35 @@ class TransformerLayer(torch.autograd.Function):
             d_w_beta = d_w_beta.view(ctx.w_beta_shape)
         return (d_x, None, d_w, d_bias, d_w_beta, None, None, None, d_gamma, d_bn_bias, None, None, None, None, None,
                 None, None, None, None)
+
+
+def dropout_mask(n: int, p: float, device, seed: int | None = None) -> torch.Tensor:
+    """[n] floats, 0 with probability p else 1/(1-p) (etpgt_dropout_mask); the seed comes from torch's
+    CPU generator unless given, so torch.manual_seed makes runs reproducible."""
+    if seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    out = torch.empty(n, dtype=torch.float32, device=device)
+    call("etpgt_dropout_mask", int(seed), float(p), n, ptr(out), stream())
+    return out
+
+
+class FusedRows(torch.autograd.Function):
+    """The row-concatenation of parameters that already ARE consecutive row blocks of one buffer
+    (nn.TransformerConv.fused_parameters): forward is a view, backward hands each parameter its row
+    block of the fused gradient as a view.  No kernel on either side (torch.cat would copy twice)."""
+
+    @staticmethod
+    def forward(ctx, fused, *parts):
+        ctx.rows = [p.size(0) for p in parts]
+        return fused.view_as(fused)
+
+    @staticmethod
+    def backward(ctx, d_fused):
+        grads, row = [], 0
+        for r in ctx.rows:
+            grads.append(d_fused[row:row + r])
+            row += r
+        return (None, *grads)
 
 
 def fused_conv_supported(x: torch.Tensor, in_channels: int, width: int) -> bool:

@@ -244,6 +244,10 @@ int etpgt_bn_apply_ex(const float* x, int64_t n, int dim, const float* mean, con
                       const float* gamma, const float* bias, const float* residual, int relu,
                       double drop_p, uint64_t drop_seed, float* y, void* y_hi, void* y_lo,
                       etpgt_stream_t stream);
+/* out[i] = 0 with probability p, else 1/(1-p) (Philox4x32-10 keyed by (seed, i / 4)): the attention
+ * dropout masks (`alpha_mask` of etpgt_tconv_fwd, `mask_edges` / `mask_self` of etpgt_gat_fwd) of all
+ * layers of one forward pass in a single launch.  out must be 16-byte aligned. */
+int etpgt_dropout_mask(uint64_t seed, double p, int64_t n, float* out, etpgt_stream_t stream);
 /* backward step 1: sums[0:dim] = sum g, sums[dim:2dim] = sum g*xhat with g = d_y (masked by
  * y > 0 when relu).  All-reduced across ranks by the caller in training mode. */
 int etpgt_bn_bwd_stats(const float* x, const float* y, const float* d_y, int64_t n, int dim,
