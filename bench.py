@@ -7,7 +7,9 @@
 Workload (BASELINE.json configs[1]): graph_transformer_optimized (D=256, L=2, H=2, k_pe=16),
 BPR loss, AdamW(1e-3, 1e-5), session batches drawn from the synthetic RetailRocket-shaped graph
 (etpgt_b200/synth.py).  One step = forward + loss + backward + optimizer over one batch of
-`--batch` sessions per GPU (weak scaling).  Prints ONE JSON line (rank 0).
+`--batch` sessions per GPU (weak scaling; default 32,768 — the smallest power of two at which the step
+is device-bound rather than bound by the ~1.9 ms the host needs to launch it; `batch_sweep` reports
+16,384 and 65,536 as well).  Prints ONE JSON line (rank 0).
 
   value   sessions/s with the batch tensors already resident in HBM;
   e2e     the same step driven from pinned HOST batch tensors (H2D of x / edge_index / batch /
@@ -47,12 +49,12 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=16384, help="sessions per GPU per step")
+    ap.add_argument("--batch", type=int, default=32768, help="sessions per GPU per step")
     ap.add_argument("--cpu-batch", type=int, default=1024, help="sessions per step of the CPU sample")
     ap.add_argument("--rotate", type=int, default=4, help="distinct batches rotated through the timed steps")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
-    ap.add_argument("--sweep-batch", type=int, default=65536,
-                    help="extra device-resident measurement at this batch size (rank 0, 1 GPU; 0 = off)")
+    ap.add_argument("--sweep-batches", type=str, default="16384,65536",
+                    help="extra device-resident measurements at these batch sizes (rank 0, 1 GPU; '' = off)")
     return ap.parse_args()
 
 
@@ -328,7 +330,11 @@ def run_b200(args, rank, world_size, local_rank):
             losses.append(float(loss_host[pending["slot"] ^ 1][0]))
             pending["loss_event"] = None
 
+    e2e_marks = []
+
     def e2e_step(i):
+        if os.environ.get("ETPGT_BENCH_DEBUG"):
+            e2e_marks.append(time.perf_counter())
         if pending["batch"] is None:
             prefetch(i)
         batch, ready = pending["batch"], pending["ready"]
@@ -354,7 +360,9 @@ def run_b200(args, rank, world_size, local_rank):
         launches = _lib.launch_count()
         value = total_sessions * args.steps / (ms_total / 1e3)
         # ---- end to end from pinned host batches (e2e)
-        for i in range(max(min(args.warmup, 3), 1)):
+        # the warm-up visits every rotating batch on the copy stream too (its allocator pool must have seen
+        # every shape before the clock starts, exactly as for the device-resident loop above)
+        for i in range(max(args.warmup, len(host_batches) + 1)):
             e2e_step(i)
         drain_loss()
         pending["batch"] = None
@@ -365,6 +373,9 @@ def run_b200(args, rank, world_size, local_rank):
                 drain_loss()              # the last loss is read inside the timed region too
 
         ms_e2e = timed(e2e_all, args.steps)
+        if e2e_marks and rank == 0:
+            gaps = np.diff(np.asarray(e2e_marks[-args.steps:])) * 1e3
+            print("e2e host gaps between steps (ms):", np.round(gaps, 2).tolist(), file=sys.stderr)
         e2e_value = total_sessions * args.steps / (ms_e2e / 1e3)
     h2d = int(np.mean([hb.nbytes() for hb in host_batches]))
 
@@ -380,20 +391,25 @@ def run_b200(args, rank, world_size, local_rank):
         "final_loss": losses[-1] if losses else None,
         "batch_shape": {"nodes": host_batches[0].nodes, "edges": host_batches[0].edges},
     }
-    if rank == 0 and world_size == 1 and args.sweep_batch > args.batch:
-        # the step at 16,384 sessions is close to host-launch-bound (about 60 launches in ~2 ms); the same
-        # step at a larger batch shows what the kernels sustain when the device is the limit
-        big = [hb.to_device(device) for hb in make_batches(data, edge_keys, 0, args.sweep_batch, 2, seed=7, pin=False)]
-        total_sessions = args.sweep_batch
-        for i in range(3):
-            step(big[i % 2])
-        sweep_steps = max(args.steps // 2, 4)
-        ms_big = timed(lambda i: step(big[i % 2]), sweep_steps)
-        out["batch_sweep"] = [{"sessions_per_step": args.sweep_batch, "ms_per_step": ms_big / sweep_steps,
-                               "value": args.sweep_batch * sweep_steps / (ms_big / 1e3), "unit": "sessions/s",
-                               "nodes": big[0].x.numel(), "edges": big[0].edge_index.size(1)}]
+    if rank == 0 and world_size == 1 and args.sweep_batches:
+        # The step costs the host about 1.9 ms (some 60 launches driven through Python / autograd), so small
+        # batches are host-launch-bound and noisy; the sweep shows the same step on either side of the
+        # default batch.
+        out["batch_sweep"] = []
+        for sweep in [int(v) for v in args.sweep_batches.split(",") if v]:
+            if sweep == args.batch:
+                continue
+            big = [hb.to_device(device) for hb in make_batches(data, edge_keys, 0, sweep, 2, seed=7, pin=False)]
+            total_sessions = sweep
+            for i in range(3):
+                step(big[i % 2])
+            sweep_steps = max(args.steps // 2, 4)
+            ms_big = timed(lambda i: step(big[i % 2]), sweep_steps)
+            out["batch_sweep"].append({"sessions_per_step": sweep, "ms_per_step": ms_big / sweep_steps,
+                                       "value": sweep * sweep_steps / (ms_big / 1e3), "unit": "sessions/s",
+                                       "nodes": big[0].x.numel(), "edges": big[0].edge_index.size(1)})
+            del big
         total_sessions = args.batch * world_size
-        del big
     if rank == 0:
         out["scoring"] = scoring_roofline(model, device)
         out["roofline"] = tconv_roofline(model, dev_batches[0], data, device)

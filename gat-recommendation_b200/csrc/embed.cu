@@ -34,47 +34,64 @@ embed_pe_fwd_kernel(const int64_t* __restrict__ ids, int64_t n, const float* __r
   const int lig = lane % G::LPN;
   const int64_t groups_per_cta = (kThreads / 32) * G::GROUPS;
   const int64_t group0 = blockIdx.x * groups_per_cta + (threadIdx.x >> 5) * G::GROUPS + lane / G::LPN;
-  for (int64_t node = group0; node < n; node += (int64_t)gridDim.x * groups_per_cta) {
-    const int64_t id = ids[node];
-    const float* trow = table + id * DIM;
-    float4 acc[G::V];
+  const int64_t stride = (int64_t)gridDim.x * groups_per_cta;
+  const unsigned gmask = G::LPN == 32 ? 0xffffffffu : (((1u << (G::LPN % 32)) - 1u) << ((lane / G::LPN) * G::LPN));
+  const int src0 = (lane / G::LPN) * G::LPN;
+  const bool quad_pe = pe != nullptr && (k_pe & 3) == 0 && (k_pe >> 2) <= G::LPN;
+  const int quads = k_pe >> 2;
+  // two nodes per group and iteration: both id loads, then both table rows and PE rows are in flight
+  // together (the chain id -> row is two dependent HBM round trips)
+  for (int64_t node0 = group0; node0 < n; node0 += 2 * stride) {
+    int64_t node[2] = {node0, node0 + stride};
+    bool on[2] = {true, node[1] < n};
+    int64_t id[2];
 #pragma unroll
-    for (int v = 0; v < G::V; ++v) acc[v] = ldg4(trow + 4 * (v * G::LPN + lig));
-    if (pe != nullptr) {
-      const float* prow = pe + (pe_per_node ? node : id) * (int64_t)k_pe;
+    for (int u = 0; u < 2; ++u) id[u] = on[u] ? ids[node[u]] : 0;
+    float4 acc[2][G::V], mine[2];
 #pragma unroll
-      for (int v = 0; v < G::V; ++v) acc[v] = add4(acc[v], ld4(bias + 4 * (v * G::LPN + lig)));
-      if ((k_pe & 3) == 0 && (k_pe >> 2) <= G::LPN) {
-        // the PE row is loaded ONCE (lane j of the group holds floats 4j..4j+3, in flight together with
-        // the table row) and broadcast by shuffles; a scalar load per k would serialise k_pe HBM round trips
-        const int quads = k_pe >> 2;
-        const float4 mine = lig < quads ? ldg4(prow + 4 * lig) : zero4();
-        const unsigned gmask = G::LPN == 32 ? 0xffffffffu : (((1u << (G::LPN % 32)) - 1u) << ((lane / G::LPN) * G::LPN));
-        const int src0 = (lane / G::LPN) * G::LPN;
-        for (int j = 0; j < quads; ++j) {
-          const float p0 = __shfl_sync(gmask, mine.x, src0 + j), p1 = __shfl_sync(gmask, mine.y, src0 + j);
-          const float p2 = __shfl_sync(gmask, mine.z, src0 + j), p3 = __shfl_sync(gmask, mine.w, src0 + j);
-          const float* w = wt + (size_t)(4 * j) * DIM;
+    for (int u = 0; u < 2; ++u) {
+      const float* trow = table + id[u] * DIM;
 #pragma unroll
-          for (int v = 0; v < G::V; ++v) {
-            const int c = 4 * (v * G::LPN + lig);
-            acc[v] = fma4(p0, ld4(w + c), acc[v]);
-            acc[v] = fma4(p1, ld4(w + DIM + c), acc[v]);
-            acc[v] = fma4(p2, ld4(w + 2 * DIM + c), acc[v]);
-            acc[v] = fma4(p3, ld4(w + 3 * DIM + c), acc[v]);
+      for (int v = 0; v < G::V; ++v) acc[u][v] = ldg4(trow + 4 * (v * G::LPN + lig));
+      mine[u] = zero4();
+      if (quad_pe && lig < quads) mine[u] = ldg4(pe + (pe_per_node ? node[u] : id[u]) * (int64_t)k_pe + 4 * lig);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (pe != nullptr) {
+#pragma unroll
+        for (int v = 0; v < G::V; ++v) acc[u][v] = add4(acc[u][v], ld4(bias + 4 * (v * G::LPN + lig)));
+        if (quad_pe) {
+          // the PE row was loaded ONCE (lane j of the group holds floats 4j..4j+3) and is broadcast by
+          // shuffles; a scalar load per k would serialise k_pe HBM round trips
+          for (int j = 0; j < quads; ++j) {
+            const float p0 = __shfl_sync(gmask, mine[u].x, src0 + j), p1 = __shfl_sync(gmask, mine[u].y, src0 + j);
+            const float p2 = __shfl_sync(gmask, mine[u].z, src0 + j), p3 = __shfl_sync(gmask, mine[u].w, src0 + j);
+            const float* w = wt + (size_t)(4 * j) * DIM;
+#pragma unroll
+            for (int v = 0; v < G::V; ++v) {
+              const int c = 4 * (v * G::LPN + lig);
+              acc[u][v] = fma4(p0, ld4(w + c), acc[u][v]);
+              acc[u][v] = fma4(p1, ld4(w + DIM + c), acc[u][v]);
+              acc[u][v] = fma4(p2, ld4(w + 2 * DIM + c), acc[u][v]);
+              acc[u][v] = fma4(p3, ld4(w + 3 * DIM + c), acc[u][v]);
+            }
+          }
+        } else {
+          const float* prow = pe + (pe_per_node ? node[u] : id[u]) * (int64_t)k_pe;
+          for (int k = 0; k < k_pe; ++k) {
+            const float p = __ldg(prow + k);
+#pragma unroll
+            for (int v = 0; v < G::V; ++v) acc[u][v] = fma4(p, ld4(wt + k * DIM + 4 * (v * G::LPN + lig)), acc[u][v]);
           }
         }
-      } else {
-        for (int k = 0; k < k_pe; ++k) {
-          const float p = __ldg(prow + k);
+      }
+      if (on[u]) {
+        float* orow = out + node[u] * DIM;
 #pragma unroll
-          for (int v = 0; v < G::V; ++v) acc[v] = fma4(p, ld4(wt + k * DIM + 4 * (v * G::LPN + lig)), acc[v]);
-        }
+        for (int v = 0; v < G::V; ++v) st4(orow + 4 * (v * G::LPN + lig), acc[u][v]);
       }
     }
-    float* orow = out + node * DIM;
-#pragma unroll
-    for (int v = 0; v < G::V; ++v) st4(orow + 4 * (v * G::LPN + lig), acc[v]);
   }
 }
 
@@ -123,23 +140,38 @@ pe_wgrad_partial_kernel(const int64_t* __restrict__ ids, int64_t n, const float*
   for (int k = 0; k <= KPE; ++k) dst[k] = acc[k];
 }
 
-__global__ void pe_wgrad_reduce_kernel(const float* __restrict__ partial, int parts, int dim, int kpe,
-                                       float* __restrict__ d_w, float* __restrict__ d_b) {
-  // one warp per output (dim*(kpe+1) of them): fixed lane striding + butterfly -> deterministic
-  const int lane = threadIdx.x & 31;
-  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (i >= dim * (kpe + 1)) return;
+__global__ void __launch_bounds__(256)
+pe_wgrad_reduce_kernel(const float* __restrict__ partial, int parts, int dim, int kpe,
+                       float* __restrict__ d_w, float* __restrict__ d_b) {
+  // A CTA owns 32 consecutive outputs (of dim*(kpe+1)): lane = output, so every load is a coalesced
+  // 128-byte segment; warp w adds parts w, w+8, ...; the eight warp sums are added in warp order.
+  __shared__ float warp_sum[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int total = dim * (kpe + 1);
+  const int i = blockIdx.x * 32 + lane;
   float s = 0.f;
-  for (int p = lane; p < parts; p += 32) s += partial[(int64_t)p * dim * (kpe + 1) + i];
-  s = group_sum<32>(s);
-  if (lane != 0) return;
+  if (i < total) {
+    int p = w;
+    for (; p + 24 < parts; p += 32) {
+      const float a = partial[(int64_t)p * total + i], b = partial[(int64_t)(p + 8) * total + i];
+      const float c = partial[(int64_t)(p + 16) * total + i], e = partial[(int64_t)(p + 24) * total + i];
+      s += a; s += b; s += c; s += e;
+    }
+    for (; p < parts; p += 8) s += partial[(int64_t)p * total + i];
+  }
+  warp_sum[w][lane] = s;
+  __syncthreads();
+  if (w != 0 || i >= total) return;
+  float t = 0.f;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) t += warp_sum[q][lane];
   const int d = i / (kpe + 1), k = i % (kpe + 1);
-  if (k == kpe) d_b[d] = s; else d_w[d * kpe + k] = s;
+  if (k == kpe) d_b[d] = t; else d_w[d * kpe + k] = t;
 }
 
 int wgrad_parts(int64_t n) {
   int64_t parts = (n + 63) / 64;
-  if (parts > 6 * kNumSMs) parts = 6 * kNumSMs;
+  if (parts > 4 * kNumSMs) parts = 4 * kNumSMs;
   return parts < 1 ? 1 : (int)parts;
 }
 
@@ -211,7 +243,7 @@ extern "C" int etpgt_embed_pe_bwd(const int64_t* ids, int64_t n, const float* d_
 #undef CALL_K
   ETPGT_CHECK_LAUNCH("pe_wgrad_partial");
   const int total = dim * (k_pe + 1);
-  pe_wgrad_reduce_kernel<<<(total * 32 + 255) / 256, 256, 0, stream>>>(partial, parts, dim, k_pe, d_w_pe, d_b_pe);
+  pe_wgrad_reduce_kernel<<<(total + 31) / 32, 256, 0, stream>>>(partial, parts, dim, k_pe, d_w_pe, d_b_pe);
   ETPGT_CHECK_LAUNCH("pe_wgrad_reduce");
   return ETPGT_OK;
 }

@@ -360,8 +360,8 @@ reduce_partials_kernel(const float* __restrict__ partial, int parts, int width, 
 // ------------------------------------------------------------------ backward, source pass
 // Per source j over its out-edges (CSC): d_key_j += scale*d_logit_e * q_i, d_value_j +=
 // alpha_e*mask_e * d_agg_i.  One owner group per row, ascending CSC order: deterministic.
-template <int DIM, int HEAD_DIM>
-__global__ void __launch_bounds__(kThreads)
+template <int DIM, int HEAD_DIM, bool COLSUM>
+__global__ void __launch_bounds__(kThreads, COLSUM ? 3 : 4)
 tconv_bwd_src_kernel(const float* __restrict__ qkvs, int64_t num_nodes, const int32_t* __restrict__ colptr,
                      const int32_t* __restrict__ row, const int32_t* __restrict__ cpos,
                      const float* __restrict__ d_agg, const float2* __restrict__ ecoef,
@@ -372,56 +372,61 @@ tconv_bwd_src_kernel(const float* __restrict__ qkvs, int64_t num_nodes, const in
   constexpr int HEADS = DIM / HEAD_DIM;
   const int lane = threadIdx.x & 31;
   const int lig = lane % LPN;
-  const int64_t node_raw = ((blockIdx.x * (int64_t)kThreads + threadIdx.x) >> 5) * G::GROUPS + lane / LPN;
-  const bool valid = node_raw < num_nodes;
-  if (!valid && colsum_partial == nullptr) return;
-  const int64_t node = valid ? node_raw : 0;
-  const int begin = valid ? colptr[node] : 0, end = valid ? colptr[node + 1] : 0;
-  float4 dk[V], dv[V];
+  const int64_t nodes_per_cta = (kThreads / 32) * G::GROUPS;
+  float4 ck[V], cv[V];   // column sums of d_key / d_value over this CTA's rows (bias gradients)
 #pragma unroll
-  for (int v = 0; v < V; ++v) { dk[v] = zero4(); dv[v] = zero4(); }
-  for (int p0 = begin; p0 < end; p0 += kEdgeUnroll) {
-    float4 qr[kEdgeUnroll][V], gr[kEdgeUnroll][V];
-    float2 c[kEdgeUnroll][V];
+  for (int v = 0; v < V; ++v) { ck[v] = zero4(); cv[v] = zero4(); }
+  // grid-stride over node groups: with the column sums wanted the grid is capped (a few CTAs per SM), so
+  // that only a few hundred per-CTA partials have to be reduced afterwards
+  for (int64_t base = blockIdx.x * nodes_per_cta; base < num_nodes; base += (int64_t)gridDim.x * nodes_per_cta) {
+    const int64_t node = base + (threadIdx.x >> 5) * G::GROUPS + lane / LPN;
+    if (node >= num_nodes) continue;
+    const int begin = colptr[node], end = colptr[node + 1];
+    float4 dk[V], dv[V];
 #pragma unroll
-    for (int u = 0; u < kEdgeUnroll; ++u) {
-      const bool on = p0 + u < end;
-      const int p = on ? p0 + u : begin;
-      const int64_t i = row[p];
-      const int64_t e = cpos[p];
-      load_row<DIM>(qkvs + i * 4 * DIM, lig, qr[u]);
-      load_row<DIM>(d_agg + i * DIM, lig, gr[u]);
+    for (int v = 0; v < V; ++v) { dk[v] = zero4(); dv[v] = zero4(); }
+    for (int p0 = begin; p0 < end; p0 += kEdgeUnroll) {
+      float4 qr[kEdgeUnroll][V], gr[kEdgeUnroll][V];
+      float2 c[kEdgeUnroll][V];
 #pragma unroll
-      for (int v = 0; v < V; ++v) {
-        c[u][v] = ecoef[e * HEADS + head_of<DIM, HEAD_DIM>(v, lig)];
-        if (!on) c[u][v] = make_float2(0.f, 0.f);
+      for (int u = 0; u < kEdgeUnroll; ++u) {
+        const bool on = p0 + u < end;
+        const int p = on ? p0 + u : begin;
+        const int64_t i = row[p];
+        const int64_t e = cpos[p];
+        load_row<DIM>(qkvs + i * 4 * DIM, lig, qr[u]);
+        load_row<DIM>(d_agg + i * DIM, lig, gr[u]);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          c[u][v] = ecoef[e * HEADS + head_of<DIM, HEAD_DIM>(v, lig)];
+          if (!on) c[u][v] = make_float2(0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kEdgeUnroll; ++u) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          dk[v] = fma4(c[u][v].y, qr[u][v], dk[v]);
+          dv[v] = fma4(c[u][v].x, gr[u][v], dv[v]);
+        }
       }
     }
-#pragma unroll
-    for (int u = 0; u < kEdgeUnroll; ++u) {
-#pragma unroll
-      for (int v = 0; v < V; ++v) {
-        dk[v] = fma4(c[u][v].y, qr[u][v], dk[v]);
-        dv[v] = fma4(c[u][v].x, gr[u][v], dv[v]);
-      }
-    }
-  }
-  if (valid) {
 #pragma unroll
     for (int v = 0; v < V; ++v) {
       store_grad4(d_qkvs, d_hi, d_lo, node * 4 * DIM + DIM + 4 * (v * LPN + lig), dk[v]);
       store_grad4(d_qkvs, d_hi, d_lo, node * 4 * DIM + 2 * DIM + 4 * (v * LPN + lig), dv[v]);
+      if (COLSUM) { ck[v] = add4(ck[v], dk[v]); cv[v] = add4(cv[v], dv[v]); }
     }
   }
-  if (colsum_partial != nullptr) {
-    // column sums of d_key / d_value over this CTA's rows, groups added in a fixed order
+  if (COLSUM) {
+    // groups added in a fixed order -> deterministic
     extern __shared__ float dyn[];  // [(kThreads/32)*GROUPS][2*DIM]
     const int group_in_cta = (threadIdx.x >> 5) * G::GROUPS + lane / LPN;
     float* mine = dyn + (size_t)group_in_cta * 2 * DIM;
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-      st4(mine + 4 * (v * LPN + lig), dk[v]);          // zero for rows past the end
-      st4(mine + DIM + 4 * (v * LPN + lig), dv[v]);
+      st4(mine + 4 * (v * LPN + lig), ck[v]);
+      st4(mine + DIM + 4 * (v * LPN + lig), cv[v]);
     }
     __syncthreads();
     constexpr int NG = (kThreads / 32) * G::GROUPS;
@@ -469,8 +474,7 @@ extern "C" int etpgt_tconv_fwd(const float* qkvs, int64_t num_nodes, int dim, in
 }
 
 extern "C" size_t etpgt_tconv_bwd_workspace_bytes(int64_t num_nodes, int64_t num_edges, int dim, int heads) {
-  const int64_t npc = (kThreads / 32) * (32 / (dim / 4 < 32 ? dim / 4 : 32));
-  const int64_t src_ctas = (num_nodes + npc - 1) / npc + 1;
+  const int64_t src_ctas = 8 * kNumSMs;  // the source pass runs a capped, persistent grid when it sums columns
   return align_up((size_t)num_nodes * dim * sizeof(float)) +
          align_up((size_t)(num_edges > 0 ? num_edges : 1) * heads * sizeof(float2)) +
          align_up((size_t)kNumSMs * 4 * 5 * dim * sizeof(float)) +
@@ -529,15 +533,17 @@ extern "C" int etpgt_tconv_bwd_split(const float* qkvs, const float* d_out, int6
                                                                  dim, 0, 3 * dim);
     ETPGT_CHECK_LAUNCH("tconv dst partial reduce");
   }
-  float* src_partial = want_colsum ? w.take<float>((size_t)((num_nodes + 7) / 8 + 1) * 2 * dim) : nullptr;
+  float* src_partial = want_colsum ? w.take<float>((size_t)8 * kNumSMs * 2 * dim) : nullptr;
   int64_t grid_src = 1;
 #define CALL(D, C)                                                                                  \
   {                                                                                                 \
     const int64_t npc = (kThreads / 32) * RowGeom<D>::GROUPS;                                       \
     grid_src = (num_nodes + npc - 1) / npc;                                                         \
+    if (want_colsum && grid_src > 8 * kNumSMs) grid_src = 8 * kNumSMs;                              \
     const size_t smem = want_colsum ? (size_t)npc * 2 * D * sizeof(float) : 0;                      \
-    tconv_bwd_src_kernel<D, C><<<(unsigned)grid_src, kThreads, smem, stream>>>(                     \
-        qkvs, num_nodes, colptr, row, cpos, d_agg, ecoef, d_qkvs, d_hi, d_lo, src_partial);         \
+    auto kern = want_colsum ? tconv_bwd_src_kernel<D, C, true> : tconv_bwd_src_kernel<D, C, false>; \
+    kern<<<(unsigned)grid_src, kThreads, smem, stream>>>(qkvs, num_nodes, colptr, row, cpos, d_agg, ecoef, d_qkvs, \
+                                                         d_hi, d_lo, src_partial);                  \
   }
   ETPGT_DISPATCH_DIM_HEADS(dim, heads, CALL)
 #undef CALL

@@ -36,6 +36,15 @@ class GraphTransformer(BaseRecommendationModel):
         return nn.Sequential(nn.Linear(hidden_dim, inner), nn.GELU(), nn.Dropout(self.dropout),
                              nn.Linear(inner, hidden_dim), nn.Dropout(self.dropout))
 
+    @staticmethod
+    def _ffn(ffn: nn.Sequential, x):
+        """Linear -> GELU -> Dropout -> Linear -> Dropout (graph_transformer.py:109-124) with both dense
+        layers on the tcgen05 split-bf16 GEMM; the module (and its state-dict keys ffns.{l}.{0,3}) is the
+        reference's nn.Sequential."""
+        lin1, act, drop1, lin2, drop2 = ffn
+        h = drop1(act(ops.linear(x, lin1.weight, lin1.bias)))
+        return drop2(ops.linear(h, lin2.weight, lin2.bias))
+
     def forward(self, batch):
         ids, index = self._graph(batch)
         pe = w_pe = b_pe = None
@@ -57,7 +66,7 @@ class GraphTransformer(BaseRecommendationModel):
                 x = self.dropout_layer(x)
                 split = None
             if self.use_ffn:
-                x = x + self.ffns[layer](x)
+                x = x + self._ffn(self.ffns[layer], x)
         return self.readout(x, batch.batch, self._num_sessions(batch))
 
 
