@@ -218,7 +218,7 @@ def run_reference(args, rank):
         return
     data = synth.generate()
     edge_keys = synth.sorted_edge_keys(data)
-    steps, warmup = min(args.steps, 5), min(args.warmup, 1)
+    steps, warmup = min(args.steps, 50), min(args.warmup, 5)   # 1,024-session steps: ~0.2-0.4 s each on the host cores
     value, sec = oracle_training_steps(data, edge_keys, args.cpu_batch, steps, warmup)
     cores = os.cpu_count() or 1
     sample = f"{steps} steps of {args.cpu_batch} sessions (oracle port of the reference PyTorch/PyG path, fp32, CPU)"
