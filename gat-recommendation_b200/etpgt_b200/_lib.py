@@ -46,6 +46,11 @@ _PROTOTYPES = {
     "etpgt_gat_fwd": (I, [P, P, P, L, I, I, P, P, P, F, P, P, P, P, P, P]),
     "etpgt_gat_bwd_workspace_bytes": (Z, [L, L, I]),
     "etpgt_gat_bwd": (I, [P, P, P, P, P, L, I, I, P, P, P, P, P, P, L, F, P, P, P, P, P, P, P, P, Z, P]),
+    "etpgt_gat_aux_workspace_bytes": (Z, [L, I]),
+    "etpgt_gat_scores_fwd": (I, [P, P, P, L, I, I, P, P, P]),
+    "etpgt_gat_scores_bwd": (I, [P, P, P, P, P, L, I, I, P, P, P, P, Z, P]),
+    "etpgt_head_mean_fwd": (I, [P, P, L, I, I, P, P]),
+    "etpgt_head_mean_bwd": (I, [P, L, I, I, P, P, P, Z, P]),
     "etpgt_sage_mean_fwd": (I, [P, L, I, P, P, P, P]),
     "etpgt_sage_mean_bwd": (I, [P, L, I, P, P, P, P, P]),
     "etpgt_bn_workspace_bytes": (Z, [L, I]),

@@ -34,9 +34,8 @@ class GAT(BaseRecommendationModel):
         last = len(self.convs) - 1
         for layer, (conv, bn) in enumerate(zip(self.convs, self.batch_norms)):
             # BN, then ReLU + dropout on every layer but the last (gat.py:136-141)
-            x = batch_norm_rows(bn, conv(x, index), relu=layer < last, group=self.bn_process_group)
-            if layer < last:
-                x = self.dropout_layer(x)
+            drop_p = self.dropout_layer.p if (self.training and layer < last) else 0.0
+            x = batch_norm_rows(bn, conv(x, index), relu=layer < last, group=self.bn_process_group, drop_p=drop_p)
         return self.readout(x, batch.batch, self._num_sessions(batch))
 
 

@@ -27,7 +27,8 @@ class GraphSAGE(BaseRecommendationModel):
                               self.item_embedding.padding_idx)
         for conv, bn in zip(self.convs, self.batch_norms):
             # BN -> ReLU -> dropout on every layer (graphsage.py:74-78)
-            x = self.dropout_layer(batch_norm_rows(bn, conv(x, index), relu=True, group=self.bn_process_group))
+            x = batch_norm_rows(bn, conv(x, index), relu=True, group=self.bn_process_group,
+                                drop_p=self.dropout_layer.p if self.training else 0.0)   # BN + ReLU + dropout, one kernel
         return self.readout(x, batch.batch, self._num_sessions(batch))
 
 

@@ -113,12 +113,17 @@ class GATConv(nn.Module):
         index = _as_index(edge_index, x.size(0))
         n, heads, c = x.size(0), self.heads, self.out_channels
         h = ops.linear(x, self.lin.weight, None)      # tcgen05 split-bf16 GEMM (fp32-grade)
+        if mask_edges is None and self.training and self.dropout > 0.0:
+            masks = ops.dropout_mask((index.num_edges + n) * heads, self.dropout, x.device)   # one launch for both
+            mask_edges = masks[: index.num_edges * heads].view(index.num_edges, heads)
+            mask_self = masks[index.num_edges * heads:].view(n, heads)
+        if not self.concat and c % 4 == 0 and h.size(1) <= 1024:
+            # attention scalars, edge softmax + aggregation, head mean + bias: one autograd node
+            return ops.GatConvFn.apply(h, self.att_src, self.att_dst, self.bias, mask_edges, mask_self, index, heads,
+                                       self.negative_slope)
         hv = h.view(n, heads, c)
         a_src = (hv * self.att_src).sum(-1)
         a_dst = (hv * self.att_dst).sum(-1)
-        if mask_edges is None and self.training and self.dropout > 0.0:
-            mask_edges = _alpha_dropout_mask(index.num_edges, heads, self.dropout, True, x)
-            mask_self = _alpha_dropout_mask(n, heads, self.dropout, True, x)
         agg = ops.GatAggregateFn.apply(h, a_src, a_dst, mask_edges, mask_self, index, heads, self.negative_slope)
         out = agg if self.concat else agg.view(n, heads, c).mean(dim=1)
         return out if self.bias is None else out + self.bias
@@ -145,15 +150,17 @@ class SAGEConv(nn.Module):
 
 
 def batch_norm_rows(bn: nn.BatchNorm1d, x: torch.Tensor, residual: torch.Tensor | None = None,
-                    relu: bool = False, group=None) -> torch.Tensor:
-    """`bn(x) (+ residual) (-> relu)` with the statistics of an ordinary nn.BatchNorm1d module
-    (its parameters / buffers are used and updated in place, so state dicts stay compatible)."""
+                    relu: bool = False, group=None, drop_p: float = 0.0) -> torch.Tensor:
+    """`bn(x) (+ residual) (-> relu) (-> dropout_p)` with the statistics of an ordinary nn.BatchNorm1d
+    module (its parameters / buffers are used and updated in place, so state dicts stay compatible).
+    drop_p > 0 fuses the layer's nn.Dropout into the same kernel (Philox mask, seed from torch's CPU RNG)."""
     training = bn.training or not bn.track_running_stats
     if training and bn.track_running_stats and bn.num_batches_tracked is not None:
         bn.num_batches_tracked.add_(1)
     momentum = 0.1 if bn.momentum is None else bn.momentum
+    seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if drop_p > 0.0 else 0
     return ops.BatchNormRows.apply(x, bn.weight, bn.bias, residual, bn.running_mean, bn.running_var, training,
-                                   momentum, bn.eps, relu, group)
+                                   momentum, bn.eps, relu, group, float(drop_p), seed)
 
 
 def transformer_layer(conv: TransformerConv, bn: nn.BatchNorm1d, x: torch.Tensor, x_split, index, drop_p: float,

@@ -525,6 +525,62 @@ class GatAggregateFn(torch.autograd.Function):
         return d_h, d_a_src, d_a_dst, None, None, None, None, None
 
 
+class GatConvFn(torch.autograd.Function):
+    """Everything of PyG GATConv(concat=False) after the projection as one autograd node: attention
+    scalars (etpgt_gat_scores_fwd), edge softmax + aggregation (etpgt_gat_fwd), head mean + bias
+    (etpgt_head_mean_fwd), and the matching backward chain — etpgt/model/gat.py:49-109,137."""
+
+    @staticmethod
+    def forward(ctx, h, att_src, att_dst, bias, mask_edges, mask_self, index: GraphIndex, heads: int, slope: float):
+        _require_cuda(h, "node features")
+        h = _f32(h)
+        n, width = h.shape
+        c = width // heads
+        dev = h.device
+        att_s, att_d = _f32(att_src).reshape(-1), _f32(att_dst).reshape(-1)
+        bias_c = _f32(bias) if bias is not None else None
+        me = _f32(mask_edges) if mask_edges is not None else None
+        ms = _f32(mask_self) if mask_self is not None else None
+        f32 = dict(dtype=torch.float32, device=dev)
+        a_src, a_dst = torch.empty(n, heads, **f32), torch.empty(n, heads, **f32)
+        call("etpgt_gat_scores_fwd", ptr(h), ptr(att_s), ptr(att_d), n, width, heads, ptr(a_src), ptr(a_dst), stream())
+        agg = torch.empty(n, width, **f32)
+        m, inv_l = torch.empty(n, heads, **f32), torch.empty(n, heads, **f32)
+        call("etpgt_gat_fwd", ptr(h), ptr(a_src), ptr(a_dst), n, width, heads, ptr(index.rowptr), ptr(index.col),
+             ptr(index.eperm), float(slope), ptr(me), ptr(ms), ptr(agg), ptr(m), ptr(inv_l), stream())
+        out = torch.empty(n, c, **f32)
+        call("etpgt_head_mean_fwd", ptr(agg), ptr(bias_c), n, heads, c, ptr(out), stream())
+        ctx.save_for_backward(h, att_s, att_d, a_src, a_dst, me, ms, agg, m, inv_l)
+        ctx.index, ctx.heads, ctx.slope = index, heads, float(slope)
+        ctx.shapes = (tuple(att_src.shape), tuple(att_dst.shape), bias is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        h, att_s, att_d, a_src, a_dst, me, ms, agg, m, inv_l = ctx.saved_tensors
+        index, heads = ctx.index, ctx.heads
+        d_out = _f32(d_out)
+        n, width = h.shape
+        c = width // heads
+        dev = h.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        d_agg = torch.empty(n, width, **f32)
+        d_bias = torch.empty(c, **f32) if ctx.shapes[2] else None
+        ws = workspace(size("etpgt_gat_aux_workspace_bytes", n, width), dev)
+        call("etpgt_head_mean_bwd", ptr(d_out), n, heads, c, ptr(d_agg), ptr(d_bias), ptr(ws), ws.numel(), stream())
+        d_h = torch.empty_like(h)
+        d_a_src, d_a_dst = torch.empty_like(a_src), torch.empty_like(a_dst)
+        ws2 = workspace(size("etpgt_gat_bwd_workspace_bytes", n, index.num_edges, heads), dev)
+        call("etpgt_gat_bwd", ptr(h), ptr(a_src), ptr(a_dst), ptr(d_agg), ptr(agg), n, width, heads,
+             ptr(index.rowptr), ptr(index.col), ptr(index.eperm), ptr(index.colptr), ptr(index.row), ptr(index.cpos),
+             index.num_edges, ctx.slope, ptr(me), ptr(ms), ptr(m), ptr(inv_l), ptr(d_h), ptr(d_a_src), ptr(d_a_dst),
+             ptr(ws2), ws2.numel(), stream())
+        d_att_s, d_att_d = torch.empty(width, **f32), torch.empty(width, **f32)
+        call("etpgt_gat_scores_bwd", ptr(h), ptr(att_s), ptr(att_d), ptr(d_a_src), ptr(d_a_dst), n, width, heads,
+             ptr(d_h), ptr(d_att_s), ptr(d_att_d), ptr(ws), ws.numel(), stream())
+        return (d_h, d_att_s.view(ctx.shapes[0]), d_att_d.view(ctx.shapes[1]), d_bias, None, None, None, None, None)
+
+
 class SageMeanFn(torch.autograd.Function):
     """Mean of in-neighbour rows (0 for isolated nodes) — PyG SAGEConv(aggr='mean') aggregation."""
 
@@ -562,7 +618,8 @@ class BatchNormRows(torch.autograd.Function):
     parallelism the 2*dim partial sums are all-reduced so statistics cover every rank's nodes."""
 
     @staticmethod
-    def forward(ctx, x, gamma, bias, residual, running_mean, running_var, training, momentum, eps, relu, group):
+    def forward(ctx, x, gamma, bias, residual, running_mean, running_var, training, momentum, eps, relu, group,
+                drop_p=0.0, drop_seed=0):
         _require_cuda(x, "node features")
         x = _f32(x)
         n, dim = x.shape
@@ -590,23 +647,24 @@ class BatchNormRows(torch.autograd.Function):
             call("etpgt_bn_from_running", ptr(running_mean), ptr(running_var), dim, float(eps), ptr(mean),
                  ptr(invstd), stream())
         y = torch.empty_like(x)
-        call("etpgt_bn_apply", ptr(x), n, dim, ptr(mean), ptr(invstd), ptr(gamma_c), ptr(bias_c), ptr(res_c),
-             int(bool(relu)), ptr(y), stream())
+        # (+ the layer's dropout, Philox mask regenerated in backward: gat.py:139-141, graphsage.py:77-78)
+        call("etpgt_bn_apply_ex", ptr(x), n, dim, ptr(mean), ptr(invstd), ptr(gamma_c), ptr(bias_c), ptr(res_c),
+             int(bool(relu)), float(drop_p), int(drop_seed), ptr(y), None, None, stream())
         ctx.save_for_backward(x, y if relu else None, mean, invstd, gamma_c)
-        ctx.meta = (bool(training), bool(relu), count, residual is not None, group)
+        ctx.meta = (bool(training), bool(relu), count, residual is not None, group, float(drop_p), int(drop_seed))
         return y
 
     @staticmethod
     def backward(ctx, d_y):
         x, y, mean, invstd, gamma = ctx.saved_tensors
-        training, relu, count, has_res, group = ctx.meta
+        training, relu, count, has_res, group, drop_p, drop_seed = ctx.meta
         d_y = _f32(d_y)
         n, dim = x.shape
         dev = x.device
         local = torch.empty(2 * dim + 1, dtype=torch.float64, device=dev)
         ws = workspace(size("etpgt_bn_workspace_bytes", n, dim), dev)
-        call("etpgt_bn_bwd_stats", ptr(x), ptr(y), ptr(d_y), n, dim, ptr(mean), ptr(invstd), int(relu), ptr(local),
-             ptr(ws), ws.numel(), stream())
+        call("etpgt_bn_bwd_stats_ex", ptr(x), ptr(y), ptr(d_y), n, dim, ptr(mean), ptr(invstd), int(relu), drop_p,
+             drop_seed, ptr(local), ptr(ws), ws.numel(), stream())
         sums = local
         if training and _dist_ready(group):
             local[2 * dim:].fill_(float(n))
@@ -615,12 +673,14 @@ class BatchNormRows(torch.autograd.Function):
         d_x = torch.empty_like(x)
         d_gamma = torch.empty(dim, dtype=torch.float32, device=dev)
         d_bias = torch.empty(dim, dtype=torch.float32, device=dev)
-        call("etpgt_bn_bwd_apply", ptr(x), ptr(y), ptr(d_y), n, dim, ptr(mean), ptr(invstd), ptr(gamma), int(relu),
-             int(training), ptr(sums), count, ptr(local), ptr(d_x), ptr(d_gamma), ptr(d_bias), stream())
-        d_res = None
-        if has_res:
-            d_res = d_y if not relu else d_y * (y > 0)
-        return d_x, d_gamma, d_bias, d_res, None, None, None, None, None, None, None
+        # the residual branch's gradient (d_y through the dropout mask and the ReLU gate) comes out of the same pass
+        d_res = torch.empty_like(x) if has_res and (relu or drop_p > 0.0) else None
+        call("etpgt_bn_bwd_apply_ex", ptr(x), ptr(y), ptr(d_y), n, dim, ptr(mean), ptr(invstd), ptr(gamma), int(relu),
+             int(training), ptr(sums), count, ptr(local), drop_p, drop_seed, ptr(d_x), ptr(d_res), ptr(d_gamma),
+             ptr(d_bias), stream())
+        if has_res and d_res is None:
+            d_res = d_y
+        return d_x, d_gamma, d_bias, d_res, None, None, None, None, None, None, None, None, None
 
 
 # ------------------------------------------------------------------------------ readout

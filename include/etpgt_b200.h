@@ -208,6 +208,24 @@ int etpgt_gat_bwd(const float* h, const float* a_src, const float* a_dst, const 
                   float negative_slope, const float* mask_edges, const float* mask_self,
                   const float* m, const float* inv_l, float* d_h, float* d_a_src, float* d_a_dst,
                   void* ws, size_t ws_bytes, etpgt_stream_t stream);
+/* The node-wise parts of GATConv around the edge kernels, each one streaming pass (in PyTorch a dozen
+ * element-wise / reduction launches over [N, heads*channels]):
+ *   scores:    a_src[n,h] = <h[n,h,:], att_src[h,:]>, a_dst likewise (att_* are [heads*channels]);
+ *   scores bwd: d_h (in/out) += d_a_src (x) att_src + d_a_dst (x) att_dst; d_att_src / d_att_dst [heads*channels]
+ *              overwritten (deterministic column sums);
+ *   head mean: out[n,:] = mean_h agg[n,h,:] + bias (bias [channels] or NULL) — concat=False, gat.py:92-107;
+ *   head mean bwd: d_agg[n,h,:] = d_out[n,:] / heads, d_bias = column sums of d_out (or NULL).
+ * One workspace size serves both backward calls. */
+size_t etpgt_gat_aux_workspace_bytes(int64_t num_nodes, int width);
+int etpgt_gat_scores_fwd(const float* h, const float* att_src, const float* att_dst, int64_t num_nodes,
+                         int width, int heads, float* a_src, float* a_dst, etpgt_stream_t stream);
+int etpgt_gat_scores_bwd(const float* h, const float* att_src, const float* att_dst, const float* d_a_src,
+                         const float* d_a_dst, int64_t num_nodes, int width, int heads, float* d_h,
+                         float* d_att_src, float* d_att_dst, void* ws, size_t ws_bytes, etpgt_stream_t stream);
+int etpgt_head_mean_fwd(const float* agg, const float* bias, int64_t num_nodes, int heads, int channels,
+                        float* out, etpgt_stream_t stream);
+int etpgt_head_mean_bwd(const float* d_out, int64_t num_nodes, int heads, int channels, float* d_agg,
+                        float* d_bias, void* ws, size_t ws_bytes, etpgt_stream_t stream);
 /* PyG SAGEConv(aggr="mean") neighbour mean (etpgt/model/graphsage.py:43-48,75): mean_i = average of
  * x_j over in-edges (0 when there are none); backward distributes d_mean_i / indeg(i) to sources. */
 int etpgt_sage_mean_fwd(const float* x, int64_t num_nodes, int dim, const int32_t* rowptr,

@@ -511,3 +511,49 @@ def test_batch_norm_fused_dropout_forward_backward(ops, p, relu, res):
     want_dx = gamma.double() * invstd.double() * (gtrue - gtrue.mean(0) - xhat * (gtrue * xhat).mean(0))
     assert rel_err(d_x, want_dx) < 1e-5
     assert rel_err(d_bias, gtrue.sum(0)) < 1e-5 and rel_err(d_gamma, (gtrue * xhat).sum(0)) < 1e-5
+
+
+# ------------------------------------------------------------------------------ GAT node-wise kernels
+
+
+@pytest.mark.parametrize("n,heads,c", [(500, 4, 256), (77, 2, 64), (1, 1, 32), (300, 8, 128)])
+def test_gat_scores_and_head_mean_kernels(ops, n, heads, c):
+    """etpgt_gat_scores_fwd/_bwd and etpgt_head_mean_fwd/_bwd against the PyTorch expressions of PyG GATConv
+    ((h * att).sum(-1), mean over heads + bias) in fp64."""
+    from etpgt_b200._lib import call, ptr, size, stream, workspace
+
+    g = torch.Generator().manual_seed(n + c)
+    width = heads * c
+    h = torch.randn(n, width, generator=g)
+    att_s, att_d = torch.randn(width, generator=g), torch.randn(width, generator=g)
+    hc, sc, dc = h.cuda(), att_s.cuda(), att_d.cuda()
+    a_src, a_dst = torch.empty(n, heads, device="cuda"), torch.empty(n, heads, device="cuda")
+    call("etpgt_gat_scores_fwd", ptr(hc), ptr(sc), ptr(dc), n, width, heads, ptr(a_src), ptr(a_dst), stream())
+    hv = h.double().view(n, heads, c)
+    assert rel_err(a_src, (hv * att_s.double().view(heads, c)).sum(-1)) < 1e-5
+    assert rel_err(a_dst, (hv * att_d.double().view(heads, c)).sum(-1)) < 1e-5
+    d_as, d_ad = torch.randn(n, heads, generator=g), torch.randn(n, heads, generator=g)
+    d_h0 = torch.randn(n, width, generator=g)
+    d_h = d_h0.clone().cuda()
+    d_as_c, d_ad_c = d_as.cuda(), d_ad.cuda()          # keep the device copies alive across the call
+    d_att_s, d_att_d = torch.empty(width, device="cuda"), torch.empty(width, device="cuda")
+    ws = workspace(size("etpgt_gat_aux_workspace_bytes", n, width), "cuda")
+    call("etpgt_gat_scores_bwd", ptr(hc), ptr(sc), ptr(dc), ptr(d_as_c), ptr(d_ad_c), n, width, heads,
+         ptr(d_h), ptr(d_att_s), ptr(d_att_d), ptr(ws), ws.numel(), stream())
+    want_dh = d_h0.double().view(n, heads, c) + d_as.double().unsqueeze(-1) * att_s.double().view(heads, c) \
+        + d_ad.double().unsqueeze(-1) * att_d.double().view(heads, c)
+    assert rel_err(d_h, want_dh.reshape(n, width)) < 1e-5
+    assert rel_err(d_att_s, (d_as.double().unsqueeze(-1) * hv).sum(0).reshape(-1)) < 1e-5
+    assert rel_err(d_att_d, (d_ad.double().unsqueeze(-1) * hv).sum(0).reshape(-1)) < 1e-5
+    # head mean + bias
+    bias = torch.randn(c, generator=g)
+    out = torch.empty(n, c, device="cuda")
+    bias_c = bias.cuda()
+    call("etpgt_head_mean_fwd", ptr(hc), ptr(bias_c), n, heads, c, ptr(out), stream())
+    assert rel_err(out, hv.mean(1) + bias.double()) < 1e-5
+    d_out = torch.randn(n, c, generator=g)
+    d_agg, d_bias = torch.empty(n, width, device="cuda"), torch.empty(c, device="cuda")
+    d_out_c = d_out.cuda()
+    call("etpgt_head_mean_bwd", ptr(d_out_c), n, heads, c, ptr(d_agg), ptr(d_bias), ptr(ws), ws.numel(), stream())
+    assert rel_err(d_agg, (d_out.double() / heads).unsqueeze(1).expand(n, heads, c).reshape(n, width)) < 1e-6
+    assert rel_err(d_bias, d_out.double().sum(0)) < 1e-5
