@@ -320,9 +320,12 @@ def run_b200(args, rank, world_size, local_rank):
         hb = host_batches[i % len(host_batches)]
         with torch.cuda.stream(copy_stream):
             batch = hb.to_device(device)
+            # the batch's graph index (CSR + CSC, two radix sorts) depends on edge_index only: built behind
+            # the copy on the same side stream, it overlaps the previous step like the copy does
+            index = ops.graph_index_of(batch, batch.edge_index, batch.x.numel())
             ready = torch.cuda.Event()
             ready.record(copy_stream)
-        pending["batch"], pending["ready"] = batch, ready
+        pending["batch"], pending["ready"], pending["index"] = batch, ready, index
 
     def drain_loss():
         if pending["loss_event"] is not None:
@@ -339,7 +342,9 @@ def run_b200(args, rank, world_size, local_rank):
             prefetch(i)
         batch, ready = pending["batch"], pending["ready"]
         torch.cuda.current_stream().wait_event(ready)
-        for t in (batch.x, batch.edge_index, batch.batch, batch.target_item, batch.negative_items):
+        index = pending["index"]
+        for t in (batch.x, batch.edge_index, batch.batch, batch.target_item, batch.negative_items, index.rowptr,
+                  index.col, index.eperm, index.colptr, index.row, index.cpos):
             t.record_stream(torch.cuda.current_stream())
         prefetch(i + 1)
         loss = step(batch)

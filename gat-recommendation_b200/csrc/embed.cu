@@ -39,53 +39,72 @@ embed_pe_fwd_kernel(const int64_t* __restrict__ ids, int64_t n, const float* __r
   const int src0 = (lane / G::LPN) * G::LPN;
   const bool quad_pe = pe != nullptr && (k_pe & 3) == 0 && (k_pe >> 2) <= G::LPN;
   const int quads = k_pe >> 2;
-  // two nodes per group and iteration: both id loads, then both table rows and PE rows are in flight
-  // together (the chain id -> row is two dependent HBM round trips)
-  for (int64_t node0 = group0; node0 < n; node0 += 2 * stride) {
-    int64_t node[2] = {node0, node0 + stride};
-    bool on[2] = {true, node[1] < n};
-    int64_t id[2];
+  // NB nodes per group and iteration: all id loads, then all table rows and PE rows are in flight together
+  // (the chain id -> row is two dependent HBM round trips), and every W_pe^T float4 read from shared
+  // memory is applied to NB nodes (the projection is shared-memory-bandwidth bound otherwise: 32 LDS.128 per
+  // node and lane).
+  constexpr int NB = 4;
+  for (int64_t node0 = group0; node0 < n; node0 += NB * stride) {
+    int64_t node[NB], id[NB];
+    bool on[NB];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) id[u] = on[u] ? ids[node[u]] : 0;
-    float4 acc[2][G::V], mine[2];
+    for (int u = 0; u < NB; ++u) {
+      node[u] = node0 + u * stride;
+      on[u] = node[u] < n;
+      id[u] = on[u] ? ids[node[u]] : 0;
+    }
+    float4 acc[NB][G::V], mine[NB];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < NB; ++u) {
       const float* trow = table + id[u] * DIM;
 #pragma unroll
       for (int v = 0; v < G::V; ++v) acc[u][v] = ldg4(trow + 4 * (v * G::LPN + lig));
       mine[u] = zero4();
-      if (quad_pe && lig < quads) mine[u] = ldg4(pe + (pe_per_node ? node[u] : id[u]) * (int64_t)k_pe + 4 * lig);
+      if (quad_pe && lig < quads && on[u]) mine[u] = ldg4(pe + (pe_per_node ? node[u] : id[u]) * (int64_t)k_pe + 4 * lig);
     }
+    if (pe != nullptr) {
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (pe != nullptr) {
+      for (int v = 0; v < G::V; ++v) {
+        const float4 b = ld4(bias + 4 * (v * G::LPN + lig));
 #pragma unroll
-        for (int v = 0; v < G::V; ++v) acc[u][v] = add4(acc[u][v], ld4(bias + 4 * (v * G::LPN + lig)));
-        if (quad_pe) {
-          // the PE row was loaded ONCE (lane j of the group holds floats 4j..4j+3) and is broadcast by
-          // shuffles; a scalar load per k would serialise k_pe HBM round trips
-          for (int j = 0; j < quads; ++j) {
-            const float p0 = __shfl_sync(gmask, mine[u].x, src0 + j), p1 = __shfl_sync(gmask, mine[u].y, src0 + j);
-            const float p2 = __shfl_sync(gmask, mine[u].z, src0 + j), p3 = __shfl_sync(gmask, mine[u].w, src0 + j);
-            const float* w = wt + (size_t)(4 * j) * DIM;
+        for (int u = 0; u < NB; ++u) acc[u][v] = add4(acc[u][v], b);
+      }
+      if (quad_pe) {
+        for (int j = 0; j < quads; ++j) {
+          float p[NB][4];
 #pragma unroll
-            for (int v = 0; v < G::V; ++v) {
-              const int c = 4 * (v * G::LPN + lig);
-              acc[u][v] = fma4(p0, ld4(w + c), acc[u][v]);
-              acc[u][v] = fma4(p1, ld4(w + DIM + c), acc[u][v]);
-              acc[u][v] = fma4(p2, ld4(w + 2 * DIM + c), acc[u][v]);
-              acc[u][v] = fma4(p3, ld4(w + 3 * DIM + c), acc[u][v]);
+          for (int u = 0; u < NB; ++u) {   // the PE row was loaded once (lane j holds floats 4j..4j+3): broadcast
+            p[u][0] = __shfl_sync(gmask, mine[u].x, src0 + j);
+            p[u][1] = __shfl_sync(gmask, mine[u].y, src0 + j);
+            p[u][2] = __shfl_sync(gmask, mine[u].z, src0 + j);
+            p[u][3] = __shfl_sync(gmask, mine[u].w, src0 + j);
+          }
+          const float* w = wt + (size_t)(4 * j) * DIM;
+#pragma unroll
+          for (int v = 0; v < G::V; ++v) {
+            const int c = 4 * (v * G::LPN + lig);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 wq = ld4(w + q * DIM + c);
+#pragma unroll
+              for (int u = 0; u < NB; ++u) acc[u][v] = fma4(p[u][q], wq, acc[u][v]);
             }
           }
-        } else {
-          const float* prow = pe + (pe_per_node ? node[u] : id[u]) * (int64_t)k_pe;
-          for (int k = 0; k < k_pe; ++k) {
-            const float p = __ldg(prow + k);
+        }
+      } else {
 #pragma unroll
-            for (int v = 0; v < G::V; ++v) acc[u][v] = fma4(p, ld4(wt + k * DIM + 4 * (v * G::LPN + lig)), acc[u][v]);
+        for (int u = 0; u < NB; ++u) {
+          const float* prow = pe + (pe_per_node ? node[u] : id[u]) * (int64_t)k_pe;
+          for (int k = 0; k < k_pe && on[u]; ++k) {
+            const float pk = __ldg(prow + k);
+#pragma unroll
+            for (int v = 0; v < G::V; ++v) acc[u][v] = fma4(pk, ld4(wt + k * DIM + 4 * (v * G::LPN + lig)), acc[u][v]);
           }
         }
       }
+    }
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
       if (on[u]) {
         float* orow = out + node[u] * DIM;
 #pragma unroll

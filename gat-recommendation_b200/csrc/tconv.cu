@@ -162,7 +162,7 @@ tconv_fwd_kernel(const float* __restrict__ qkvs, int64_t num_nodes, const int32_
 // d_logit = alpha (d_alpha*mask - delta), d_query += scale*d_logit*k_j.  Emits per-edge
 // (alpha*mask, scale*d_logit) for the source pass.
 template <int DIM, int HEAD_DIM, int UNROLL, bool COLSUM>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, UNROLL <= 2 ? 3 : 2)
 tconv_bwd_dst_kernel(const float* __restrict__ qkvs, const float* __restrict__ d_out, int64_t num_nodes,
                      const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                      const int32_t* __restrict__ eperm, const float* __restrict__ w_beta,
@@ -172,7 +172,6 @@ tconv_bwd_dst_kernel(const float* __restrict__ qkvs, const float* __restrict__ d
                      __nv_bfloat16* __restrict__ d_hi, __nv_bfloat16* __restrict__ d_lo,
                      float* __restrict__ d_agg_out, float2* __restrict__ ecoef,
                      float* __restrict__ partial /* [grid][(w_beta ? 3 : 0) + (COLSUM ? 2 : 0)][DIM] */) {
-  constexpr bool want_colsum = COLSUM;
   using G = RowGeom<DIM>;
   constexpr int V = G::V, LPN = G::LPN;
   constexpr int HEADS = DIM / HEAD_DIM;
@@ -183,10 +182,19 @@ tconv_bwd_dst_kernel(const float* __restrict__ qkvs, const float* __restrict__ d
   const int warp_in_cta = threadIdx.x >> 5;
   const int64_t nodes_per_cta = (kThreads / 32) * G::GROUPS;
 
-  float4 dw1[V], dw2[V];  // sum dz*agg, sum dz*skip; the third block is their difference
-  float4 cq[V], cs[V];    // column sums of d_query / d_skip over this CTA's nodes (bias gradients)
+  // Per-group running sums live in shared memory (each lane owns its own float4 slots, so no
+  // synchronisation is needed until the final cross-group reduction): [sum dz*agg | sum dz*skip | (their
+  // difference, formed at the end)] for the w_beta gradient, then [sum d_query | sum d_skip] for the bias
+  // gradients.  Keeping them out of registers lets three CTAs share an SM instead of two.
+  extern __shared__ float dyn[];  // [(kThreads/32)*GROUPS][width]
+  const int wb = w_beta != nullptr ? 3 : 0, width = (wb + (COLSUM ? 2 : 0)) * DIM;
+  float* mine = dyn + (size_t)(warp_in_cta * G::GROUPS + lane / LPN) * width;
 #pragma unroll
-  for (int v = 0; v < V; ++v) { dw1[v] = zero4(); dw2[v] = zero4(); cq[v] = zero4(); cs[v] = zero4(); }
+  for (int v = 0; v < V; ++v) {
+    const int f = v * LPN + lig;
+    if (wb) { st4(mine + 4 * f, zero4()); st4(mine + DIM + 4 * f, zero4()); }
+    if (COLSUM) { st4(mine + wb * DIM + 4 * f, zero4()); st4(mine + (wb + 1) * DIM + 4 * f, zero4()); }
+  }
 
   for (int64_t base = blockIdx.x * nodes_per_cta; base < num_nodes; base += (int64_t)gridDim.x * nodes_per_cta) {
     const int64_t warp_base = base + warp_in_cta * G::GROUPS;
@@ -215,9 +223,9 @@ tconv_bwd_dst_kernel(const float* __restrict__ qkvs, const float* __restrict__ d
         const float4 dxr = fma4(dz, sub4(w2, w3), scale4(b, g[v]));
         if (valid) {
           store_grad4(d_qkvs, d_hi, d_lo, nrow * 4 * DIM + 3 * DIM + 4 * f, dxr);
-          dw1[v] = fma4(dz, ag[v], dw1[v]);
-          dw2[v] = fma4(dz, xr[v], dw2[v]);
-          if (COLSUM) cs[v] = add4(cs[v], dxr);
+          st4(mine + 4 * f, fma4(dz, ag[v], ld4(mine + 4 * f)));
+          st4(mine + DIM + 4 * f, fma4(dz, xr[v], ld4(mine + DIM + 4 * f)));
+          if (COLSUM) st4(mine + (wb + 1) * DIM + 4 * f, add4(ld4(mine + (wb + 1) * DIM + 4 * f), dxr));
         }
       }
     } else {
@@ -226,7 +234,10 @@ tconv_bwd_dst_kernel(const float* __restrict__ qkvs, const float* __restrict__ d
         dag[v] = g[v];
         if (valid) {
           store_grad4(d_qkvs, d_hi, d_lo, nrow * 4 * DIM + 3 * DIM + 4 * (v * LPN + lig), g[v]);
-          if (COLSUM) cs[v] = add4(cs[v], g[v]);
+          if (COLSUM) {
+            float* slot = mine + (wb + 1) * DIM + 4 * (v * LPN + lig);
+            st4(slot, add4(ld4(slot), g[v]));
+          }
         }
       }
     }
@@ -287,29 +298,21 @@ tconv_bwd_dst_kernel(const float* __restrict__ qkvs, const float* __restrict__ d
 #pragma unroll
       for (int v = 0; v < V; ++v) {
         store_grad4(d_qkvs, d_hi, d_lo, nrow * 4 * DIM + 4 * (v * LPN + lig), dq[v]);
-        if (COLSUM) cq[v] = add4(cq[v], dq[v]);
+        if (COLSUM) {
+          float* slot = mine + wb * DIM + 4 * (v * LPN + lig);
+          st4(slot, add4(ld4(slot), dq[v]));
+        }
       }
     }
   }
 
-  const int wb = w_beta != nullptr ? 3 : 0, width = (wb + (want_colsum ? 2 : 0)) * DIM;
   if (width > 0) {
-    // fixed-order reduction of the per-group partials of this CTA:
-    // [dz*agg | dz*skip | difference] (w_beta gradient) then [sum d_query | sum d_skip] (bias gradients)
-    extern __shared__ float dyn[];  // [(kThreads/32)*GROUPS][width]
-    const int group_in_cta = warp_in_cta * G::GROUPS + lane / LPN;
-    float* mine = dyn + (size_t)group_in_cta * width;
+    // fixed-order reduction of the per-group sums of this CTA
+    if (wb) {
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-      const int f = v * LPN + lig;
-      if (wb) {
-        st4(mine + 4 * f, dw1[v]);
-        st4(mine + DIM + 4 * f, dw2[v]);
-        st4(mine + 2 * DIM + 4 * f, sub4(dw1[v], dw2[v]));
-      }
-      if (want_colsum) {
-        st4(mine + wb * DIM + 4 * f, cq[v]);
-        st4(mine + (wb + 1) * DIM + 4 * f, cs[v]);
+      for (int v = 0; v < V; ++v) {
+        const int f = v * LPN + lig;
+        st4(mine + 2 * DIM + 4 * f, sub4(ld4(mine + 4 * f), ld4(mine + DIM + 4 * f)));
       }
     }
     __syncthreads();
@@ -438,7 +441,11 @@ tconv_bwd_src_kernel(const float* __restrict__ qkvs, int64_t num_nodes, const in
   }
 }
 
-int dst_pass_grid(int64_t num_nodes, int nodes_per_cta) { return grid_for(num_nodes, nodes_per_cta, 4); }
+// persistent destination pass: as many CTAs as are resident (3 per SM for the sparse variant, 2 for the
+// dense one, which then runs two even waves)
+int dst_pass_grid(int64_t num_nodes, int nodes_per_cta, bool sparse) {
+  return grid_for(num_nodes, nodes_per_cta, sparse ? 3 : 4);
+}
 
 }  // namespace
 }  // namespace etpgt
@@ -518,7 +525,7 @@ extern "C" int etpgt_tconv_bwd_split(const float* qkvs, const float* d_out, int6
 #define CALL(D, C)                                                                                   \
   {                                                                                                  \
     const int npc = (kThreads / 32) * RowGeom<D>::GROUPS;                                            \
-    grid_a = dst_pass_grid(num_nodes, npc);                                                          \
+    grid_a = dst_pass_grid(num_nodes, npc, sparse);                                                        \
     const size_t smem = (size_t)npc * width * sizeof(float);                                         \
     auto kern = sparse ? (want_colsum ? tconv_bwd_dst_kernel<D, C, 2, true> : tconv_bwd_dst_kernel<D, C, 2, false>) \
                        : (want_colsum ? tconv_bwd_dst_kernel<D, C, 4, true> : tconv_bwd_dst_kernel<D, C, 4, false>); \

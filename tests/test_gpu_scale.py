@@ -226,3 +226,29 @@ def test_training_steps_at_1m_items(big):
         losses.append(loss.item())
     assert all(math.isfinite(v) for v in losses) and losses[-1] < losses[0]
     assert model.item_embedding.weight.grad.abs().sum().item() == 0     # sink cleared by the step kernel
+
+
+def test_co_event_graph_at_retailrocket_scale():
+    """The device builder over the 120,436 training sessions of the RR-synth generator (BASELINE.json's
+    82k-item / 738k-edge shape) against the generator's own numpy construction (np.unique over the window-5
+    pair keys): same edge set, and the device rows are count-descending."""
+    from etpgt_b200 import data, synth
+
+    d = synth.generate()
+    graph_sessions = 120_436
+    ptr = d.sess_ptr[: graph_sessions + 1]
+    items = d.sess_items[: ptr[-1]]
+    item_i, item_j, count, _ = data.build_co_event_graph(ptr, items, None, 5, num_items=d.num_items)
+    stats = d.stats()
+    assert item_i.numel() == stats["graph_edges"] == len(d.item_i)
+    got = (item_i * d.num_items + item_j).cpu().numpy()
+    want = d.item_i.astype(np.int64) * d.num_items + d.item_j.astype(np.int64)
+    assert np.array_equal(np.sort(got), np.sort(want))
+    c = count.cpu().numpy()
+    assert (np.diff(c) <= 0).all() and c.min() >= 1
+    assert bool((item_i <= item_j).all())
+    assert len(np.unique(np.concatenate([item_i.cpu().numpy(), item_j.cpu().numpy()]))) == stats["graph_nodes"]
+    # total co-occurrences = number of in-session pairs at distance <= 5
+    lens = np.diff(ptr)
+    pairs = sum(int(np.maximum(lens - k, 0).sum()) for k in range(1, 6))
+    assert int(c.sum()) == pairs
