@@ -575,6 +575,14 @@ def tconv_roofline(model, batch, data, device):
            "peak_source": pk["source"], "traffic": traffic, "ms_fwd": ms_f, "ms_bwd": ms_b,
            "gbs_fwd": bytes_f / (ms_f / 1e3) / 1e9, "gbs_bwd": bytes_b / (ms_b / 1e3) / 1e9,
            "nodes": n, "edges": e, "edges_per_s": e / ((ms_f + ms_b) / 1e3)}
+    if traffic:
+        # what actually crossed the HBM interface (ncu): below the algorithmic bytes because the neighbour rows
+        # of a session are adjacent and are served by L1 / L2 — which is also how `frac` can exceed 1
+        out["achieved_dram"] = traffic / ((ms_f + ms_b) / 1e3) / 1e9
+        out["frac_dram"] = out["achieved_dram"] / pk["hbm_gbs"]
+        out["note"] = ("achieved = algorithmic bytes / time; measured DRAM traffic is lower (L1/L2 reuse of "
+                       "neighbour rows), see achieved_dram / frac_dram; global_graph is the same kernel group on a "
+                       "working set larger than L2")
     # (b) the whole graph, both directions of every stored pair
     src = torch.from_numpy(np.concatenate([data.item_i, data.item_j])).to(device)
     dst = torch.from_numpy(np.concatenate([data.item_j, data.item_i])).to(device)
