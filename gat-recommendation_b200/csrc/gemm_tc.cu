@@ -28,8 +28,8 @@ using namespace tc;
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_N = 128;
 constexpr int kStages = 3;
-constexpr int kAccStages = 2;
-constexpr int kTmemCols = 256;
+constexpr int kAccStages = 4;   // 4 x 128 fp32 columns = all 512 TMEM columns: the MMA thread may run 4 tiles ahead
+constexpr int kTmemCols = 512;
 constexpr int kThreads = 192;  // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
 constexpr uint32_t TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB per operand part per k-block
 constexpr uint32_t kInstrDesc = instr_desc_bf16(BLOCK_M, BLOCK_N);
@@ -128,8 +128,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         decode(u, ks, mt, nt);
         const int kb0 = ks * kb_per_split;
         const int kb1 = kb0 + kb_per_split < total_kb ? kb0 + kb_per_split : total_kb;
-        const int acc = t & 1;
-        mbar_wait(&bars->acc_empty[acc], ((uint32_t)(t >> 1) & 1) ^ 1);
+        const int acc = t % kAccStages;
+        mbar_wait(&bars->acc_empty[acc], ((uint32_t)(t / kAccStages) & 1) ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -173,14 +173,21 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     for (int64_t u = blockIdx.x; u < total_units; u += gridDim.x, ++t) {
       int ks, mt, nt;
       decode(u, ks, mt, nt);
-      const int acc = t & 1;
-      mbar_wait(&bars->acc_full[acc], (uint32_t)(t >> 1) & 1);
+      const int acc = t % kAccStages;
+      mbar_wait(&bars->acc_full[acc], (uint32_t)(t / kAccStages) & 1);
       tc_fence_after();
       const int row0 = mt * BLOCK_M + quarter * 32;
       const int col0 = nt * BLOCK_N;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        // the chunk's 32 bias values are requested BEFORE the TMEM load so that both latencies overlap
+        float4 bv[8];
+        const bool bias_on = add_bias && (int64_t)col0 + c0 + 32 <= N;
+        if (bias_on) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bv[j] = ldg4(bias + col0 + c0 + 4 * j);
+        }
         uint32_t v[32];
         tmem_ld_32x32(taddr + (uint32_t)c0, v);
         if (c0 + 32 == BLOCK_N) {  // accumulator fully read: hand the TMEM stage back before storing
@@ -198,7 +205,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
           float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
                                  __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
           const int64_t col = (int64_t)col0 + c0 + 4 * j;
-          if (add_bias && col + 3 < N) o = add4(o, ldg4(bias + col));
+          if (bias_on) o = add4(o, bv[j]);
+          else if (add_bias && col + 3 < N) o = add4(o, ldg4(bias + col));   // ragged last chunk
           *reinterpret_cast<float4*>(box + ((j ^ (lane & 7)) << 4)) = o;
         }
         fence_proxy_async_smem();
