@@ -13,10 +13,11 @@
 //                         for both the forward and the weight-gradient GEMM) + column sums
 //   etpgt_gemm_bf16x3     C[M,N] = A[M,K] B[N,K]^T (+ bias[N]); persistent warp-specialised
 //                         kernel: TMA ring (A and B k-blocks, SWIZZLE_128B) -> tcgen05.mma
-//                         128x128x16 -> double-buffered TMEM -> epilogue warps -> swizzled smem
+//                         128x128x16 or 128x256x16 -> multi-stage TMEM -> epilogue warps -> swizzled smem
 //                         staging -> TMA tile stores (coalesced 128-byte rows, edges clipped);
 //                         optional split-K with a fixed-order reduction (deterministic).
 #include <math.h>
+#include <stdlib.h>
 
 #include "tc_common.cuh"
 
@@ -26,27 +27,32 @@ namespace {
 using namespace tc;
 
 constexpr int BLOCK_M = 128;
-constexpr int BLOCK_N = 128;
-constexpr int kStages = 3;
-constexpr int kAccStages = 4;   // 4 x 128 fp32 columns = all 512 TMEM columns: the MMA thread may run 4 tiles ahead
-constexpr int kTmemCols = 512;
+// Output tiles are 128 x BN with BN = 128 or 256 (template parameter, chosen per call by gemm_plan).  The
+// GEMMs of a layer are bound by L2 -> shared-memory bandwidth (~1.6 GB in ~145 us each with 128 x 128
+// tiles = 11 TB/s at 50 % tensor-pipe activity); BN = 256 raises the flops per operand byte by a third and
+// pays off for the forward projection (short K) and the split-K weight gradient; the long-K dX GEMM keeps
+// BN = 128 (three 64 KB stages pipeline better than two 96 KB ones, and its tile count fills the SMs evenly).
+constexpr int kTmemCols = 512;  // all of TMEM: 512 / BN accumulator stages
 constexpr int kThreads = 192;  // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
-constexpr uint32_t TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB per operand part per k-block
-constexpr uint32_t kInstrDesc = instr_desc_bf16(BLOCK_M, BLOCK_N);
+constexpr uint32_t TILE_BYTES = BLOCK_M * BLOCK_K * 2;    // A: 16 KB per operand part per k-block
+constexpr uint32_t MN_BOX_BYTES = 64 * BLOCK_K * 2;       // one 64(k) x 64(mn) box of an MN-major operand
+template <int PARTS, int BN> struct StageCount {          // ring depth that fits 227 KB next to the store boxes
+  static constexpr int value = PARTS == 2 ? (BN == 256 ? 2 : 3) : 4;
+};
 constexpr int kEpiWarps = 4;
 constexpr uint32_t CD_BOX_BYTES = 32 * 32 * 4;  // one 32-row x 32-column fp32 store box
 constexpr uint32_t CD_BYTES = kEpiWarps * 2 * CD_BOX_BYTES;  // double-buffered per epilogue warp
 
 struct __align__(8) GemmBarriers {
-  uint64_t full[kStages];
-  uint64_t empty[kStages];
-  uint64_t acc_full[kAccStages];
-  uint64_t acc_empty[kAccStages];
+  uint64_t full[4];
+  uint64_t empty[4];
+  uint64_t acc_full[4];
+  uint64_t acc_empty[4];
   uint32_t tmem_base;
 };
 
 // PARTS = 1: plain bf16 (A_hi, B_hi).  PARTS = 2: split operands, three products.
-template <int PARTS>
+template <int PARTS, int BLOCK_N>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                    const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -55,7 +61,11 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                    const float* __restrict__ bias, int a_mn, int b_mn, int accumulate) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  constexpr uint32_t STAGE_BYTES = 2 * PARTS * TILE_BYTES;  // A parts then B parts
+  constexpr int kStages = StageCount<PARTS, BLOCK_N>::value;
+  constexpr int kAccStages = kTmemCols / BLOCK_N;
+  constexpr uint32_t B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;  // B: 16 / 32 KB per operand part per k-block
+  constexpr uint32_t kInstrDesc = instr_desc_bf16(BLOCK_M, BLOCK_N);
+  constexpr uint32_t STAGE_BYTES = PARTS * (TILE_BYTES + B_TILE_BYTES);  // A parts then B parts
   uint8_t* smem_cd = smem + kStages * STAGE_BYTES;  // 1024-byte aligned (stage sizes are multiples of 16 KB)
   GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(smem_cd + CD_BYTES);
 
@@ -65,8 +75,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
   const int64_t total_units = (int64_t)m_tiles * n_tiles * split_k;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
-    for (int s = 0; s < kAccStages; ++s) { mbar_init(&bars->acc_full[s], 1); mbar_init(&bars->acc_empty[s], 4); }
+    for (int s = 0; s < 4; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+    for (int s = 0; s < 4; ++s) { mbar_init(&bars->acc_full[s], 1); mbar_init(&bars->acc_empty[s], 4); }
     fence_barrier_init();
     tma_prefetch_desc(&map_a_hi);
     tma_prefetch_desc(&map_b_hi);
@@ -99,20 +109,20 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
           mbar_wait(&bars->empty[stage], phase ^ 1);
           mbar_expect_tx(&bars->full[stage], STAGE_BYTES);
           uint8_t* st = smem + stage * STAGE_BYTES;
-          // K-major operand: one box of 128 rows x 64 k.  MN-major operand (global [K, MN] row-major):
-          // two stacked boxes of 64 k-rows x 64 mn columns.
-          auto load = [&](const CUtensorMap* map, uint8_t* dst, int mn0, int mn_major) {
+          // K-major operand: one box of `rows` rows x 64 k.  MN-major operand (global [K, MN] row-major):
+          // rows / 64 stacked boxes of 64 k-rows x 64 mn columns.
+          auto load = [&](const CUtensorMap* map, uint8_t* dst, int mn0, int mn_major, int rows) {
             if (mn_major) {
-              tma_load_2d(map, &bars->full[stage], dst, mn0, kb * BLOCK_K);
-              tma_load_2d(map, &bars->full[stage], dst + TILE_BYTES / 2, mn0 + 64, kb * BLOCK_K);
+              for (int b = 0; b < rows / 64; ++b)
+                tma_load_2d(map, &bars->full[stage], dst + b * MN_BOX_BYTES, mn0 + 64 * b, kb * BLOCK_K);
             } else {
               tma_load_2d(map, &bars->full[stage], dst, kb * BLOCK_K, mn0);
             }
           };
-          load(&map_a_hi, st, mt * BLOCK_M, a_mn);
-          if (PARTS == 2) load(&map_a_lo, st + TILE_BYTES, mt * BLOCK_M, a_mn);
-          load(&map_b_hi, st + PARTS * TILE_BYTES, nt * BLOCK_N, b_mn);
-          if (PARTS == 2) load(&map_b_lo, st + (PARTS + 1) * TILE_BYTES, nt * BLOCK_N, b_mn);
+          load(&map_a_hi, st, mt * BLOCK_M, a_mn, BLOCK_M);
+          if (PARTS == 2) load(&map_a_lo, st + TILE_BYTES, mt * BLOCK_M, a_mn, BLOCK_M);
+          load(&map_b_hi, st + PARTS * TILE_BYTES, nt * BLOCK_N, b_mn, BLOCK_N);
+          if (PARTS == 2) load(&map_b_lo, st + PARTS * TILE_BYTES + B_TILE_BYTES, nt * BLOCK_N, b_mn, BLOCK_N);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -138,19 +148,19 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
           const uint32_t a_hi = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t a_lo = a_hi + TILE_BYTES;
           const uint32_t b_hi = a_hi + PARTS * TILE_BYTES;
-          const uint32_t b_lo = b_hi + TILE_BYTES;
+          const uint32_t b_lo = b_hi + B_TILE_BYTES;
 #pragma unroll
           for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
             // one UMMA_K = 16 step: 32 bytes along a K-major swizzle row, 16 rows (2 KB) of an MN-major tile
             const uint32_t off_a = a_mn ? kk * UMMA_K * 128 : kk * UMMA_K * 2;
             const uint32_t off_b = b_mn ? kk * UMMA_K * 128 : kk * UMMA_K * 2;
             const uint32_t first = (kb == kb0 && kk == 0) ? 0u : 1u;
-            const uint64_t da_hi = a_mn ? make_desc_mn_sw128(a_hi + off_a, TILE_BYTES / 2) : make_desc_sw128(a_hi + off_a);
-            const uint64_t db_hi = b_mn ? make_desc_mn_sw128(b_hi + off_b, TILE_BYTES / 2) : make_desc_sw128(b_hi + off_b);
+            const uint64_t da_hi = a_mn ? make_desc_mn_sw128(a_hi + off_a, MN_BOX_BYTES) : make_desc_sw128(a_hi + off_a);
+            const uint64_t db_hi = b_mn ? make_desc_mn_sw128(b_hi + off_b, MN_BOX_BYTES) : make_desc_sw128(b_hi + off_b);
             umma_bf16(tmem_d, da_hi, db_hi, idesc, first);
             if (PARTS == 2) {
-              const uint64_t da_lo = a_mn ? make_desc_mn_sw128(a_lo + off_a, TILE_BYTES / 2) : make_desc_sw128(a_lo + off_a);
-              const uint64_t db_lo = b_mn ? make_desc_mn_sw128(b_lo + off_b, TILE_BYTES / 2) : make_desc_sw128(b_lo + off_b);
+              const uint64_t da_lo = a_mn ? make_desc_mn_sw128(a_lo + off_a, MN_BOX_BYTES) : make_desc_sw128(a_lo + off_a);
+              const uint64_t db_lo = b_mn ? make_desc_mn_sw128(b_lo + off_b, MN_BOX_BYTES) : make_desc_sw128(b_lo + off_b);
               umma_bf16(tmem_d, da_hi, db_lo, idesc, 1u);
               umma_bf16(tmem_d, da_lo, db_hi, idesc, 1u);
             }
@@ -310,13 +320,20 @@ colsum_reduce_kernel(const float* __restrict__ partial, int64_t parts, int64_t c
 }
 
 struct GemmPlan {
-  int m_tiles, n_tiles, split_k, kb_per_split, grid;
+  int m_tiles, n_tiles, split_k, kb_per_split, grid, block_n;
 };
 
 GemmPlan gemm_plan(int64_t M, int64_t N, int64_t K, int want_split) {
   GemmPlan p;
+  // 128 x 256 tiles for the short-K forward projection and for split-K problems (the weight gradient);
+  // 128 x 128 otherwise (see the note at the top); ETPGT_GEMM_BN=128|256 overrides for tuning
+  p.block_n = (N > 128 && (K <= 512 || want_split != 1)) ? 256 : 128;
+  if (const char* forced = getenv("ETPGT_GEMM_BN")) {
+    const int f = atoi(forced);
+    if (f == 128 || f == 256) p.block_n = f;
+  }
   p.m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M);
-  p.n_tiles = (int)((N + BLOCK_N - 1) / BLOCK_N);
+  p.n_tiles = (int)((N + p.block_n - 1) / p.block_n);
   const int total_kb = (int)((K + BLOCK_K - 1) / BLOCK_K);
   int split = 1;
   if (want_split != 1) {
@@ -402,12 +419,12 @@ extern "C" int etpgt_gemm_bf16x3_ex(const void* a_hi, const void* a_lo, const vo
     return ETPGT_EWORKSPACE;
   }
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-  // K-major operand [MN, K]: boxes of 128 rows x 64 k.  MN-major operand [K, MN]: boxes of 64 k-rows x 64 mn.
-  auto map_a = [&](CUtensorMap* m, const void* p) {
-    return a_mn_major ? make_map_bf16(m, p, K, M, lda, 64) : make_map_bf16(m, p, M, K, lda, BLOCK_M);
+  // K-major operand [MN, K]: boxes of 128 (A) / BN (B) rows x 64 k.  MN-major operand [K, MN]: boxes of 64 k-rows x 64 mn.
+  auto map_a = [&](CUtensorMap* m, const void* ptr_) {
+    return a_mn_major ? make_map_bf16(m, ptr_, K, M, lda, 64) : make_map_bf16(m, ptr_, M, K, lda, BLOCK_M);
   };
-  auto map_b = [&](CUtensorMap* m, const void* p) {
-    return b_mn_major ? make_map_bf16(m, p, K, N, ldb, 64) : make_map_bf16(m, p, N, K, ldb, BLOCK_N);
+  auto map_b = [&](CUtensorMap* m, const void* ptr_) {
+    return b_mn_major ? make_map_bf16(m, ptr_, K, N, ldb, 64) : make_map_bf16(m, ptr_, N, K, ldb, p.block_n);
   };
   bool ok = map_a(&ma_hi, a_hi) && map_b(&mb_hi, b_hi);
   if (a_lo != nullptr) ok = ok && map_a(&ma_lo, a_lo) && map_b(&mb_lo, b_lo);
@@ -424,18 +441,21 @@ extern "C" int etpgt_gemm_bf16x3_ex(const void* a_hi, const void* a_lo, const vo
     return ETPGT_ECUDA;
   }
   const int parts = a_lo != nullptr ? 2 : 1;
-  const size_t smem = 1024 + (size_t)kStages * 2 * parts * TILE_BYTES + CD_BYTES + sizeof(GemmBarriers) + 64;
-  if (parts == 2) {
-    cudaFuncSetAttribute(gemm_bf16x3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    gemm_bf16x3_kernel<2><<<p.grid, kThreads, smem, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, mc, M, N, K, p.m_tiles,
-                                                             p.n_tiles, p.split_k, p.kb_per_split, bias,
-                                                             a_mn_major != 0, b_mn_major != 0, accumulate != 0);
-  } else {
-    cudaFuncSetAttribute(gemm_bf16x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    gemm_bf16x3_kernel<1><<<p.grid, kThreads, smem, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, mc, M, N, K, p.m_tiles,
-                                                             p.n_tiles, p.split_k, p.kb_per_split, bias,
-                                                             a_mn_major != 0, b_mn_major != 0, accumulate != 0);
+#define LAUNCH(PARTS_, BN_)                                                                                       \
+  {                                                                                                               \
+    const size_t smem = 1024 + (size_t)StageCount<PARTS_, BN_>::value * PARTS_ * (TILE_BYTES + BN_ * BLOCK_K * 2) + \
+                        CD_BYTES + sizeof(GemmBarriers) + 64;                                                     \
+    cudaFuncSetAttribute(gemm_bf16x3_kernel<PARTS_, BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    gemm_bf16x3_kernel<PARTS_, BN_><<<p.grid, kThreads, smem, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, mc, M, N, K,   \
+                                                                       p.m_tiles, p.n_tiles, p.split_k,           \
+                                                                       p.kb_per_split, bias, a_mn_major != 0,     \
+                                                                       b_mn_major != 0, accumulate != 0);         \
   }
+  if (parts == 2 && p.block_n == 256) LAUNCH(2, 256)
+  else if (parts == 2) LAUNCH(2, 128)
+  else if (p.block_n == 256) LAUNCH(1, 256)
+  else LAUNCH(1, 128)
+#undef LAUNCH
   ETPGT_CHECK_LAUNCH("gemm_bf16x3");
   if (p.split_k > 1) {
     splitk_reduce_kernel<<<grid_for(M * N / 4, 256 * 2, 8), 256, 0, stream>>>(partial, p.split_k, M, N, bias, C, ldc,
