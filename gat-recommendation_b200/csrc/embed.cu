@@ -230,7 +230,16 @@ extern "C" size_t etpgt_embed_pe_bwd_workspace_bytes(int64_t n, int dim, int k_p
 extern "C" int etpgt_embed_pe_bwd(const int64_t* ids, int64_t n, const float* d_out, int64_t num_items,
                                   const float* pe, int pe_per_node, int k_pe, int dim, int64_t padding_idx,
                                   float* d_table, float* d_w_pe, float* d_b_pe, void* ws, size_t ws_bytes,
-                                  etpgt_stream_t stream_) {
+                                  etpgt_stream_t stream) {
+  return etpgt_embed_pe_bwd_planned(ids, n, d_out, num_items, pe, pe_per_node, k_pe, dim, padding_idx, nullptr,
+                                    nullptr, d_table, d_w_pe, d_b_pe, ws, ws_bytes, stream);
+}
+
+extern "C" int etpgt_embed_pe_bwd_planned(const int64_t* ids, int64_t n, const float* d_out, int64_t num_items,
+                                          const float* pe, int pe_per_node, int k_pe, int dim,
+                                          int64_t padding_idx, const int32_t* plan_sorted_key,
+                                          const int32_t* plan_perm, float* d_table, float* d_w_pe, float* d_b_pe,
+                                          void* ws, size_t ws_bytes, etpgt_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ETPGT_REQUIRE(supported_dim(dim), "embed_pe_bwd: unsupported dim %d", dim);
   ETPGT_REQUIRE(pe == nullptr || k_pe == 8 || k_pe == 16 || k_pe == 32,
@@ -240,8 +249,12 @@ extern "C" int etpgt_embed_pe_bwd(const int64_t* ids, int64_t n, const float* d_
     return ETPGT_EWORKSPACE;
   }
   if (d_table != nullptr && n > 0) {
-    int rc = etpgt_scatter_rows(ids, nullptr, d_out, n, 1, dim, num_items, padding_idx, d_table, ws,
-                                etpgt_scatter_rows_workspace_bytes(n), stream_);
+    // the sort of the node ids may come from a per-batch scatter plan (etpgt_scatter_plan over `ids`)
+    int rc = plan_sorted_key != nullptr
+                 ? etpgt_scatter_rows_planned(plan_sorted_key, plan_perm, nullptr, d_out, n, 1, dim, padding_idx,
+                                              d_table, stream_)
+                 : etpgt_scatter_rows(ids, nullptr, d_out, n, 1, dim, num_items, padding_idx, d_table, ws,
+                                      etpgt_scatter_rows_workspace_bytes(n), stream_);
     if (rc != ETPGT_OK) return rc;
   }
   if (pe == nullptr) return ETPGT_OK;

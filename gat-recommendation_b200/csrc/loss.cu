@@ -183,12 +183,13 @@ extern "C" int etpgt_sampled_loss_fwd(const float* sess, const float* table, con
   return ETPGT_OK;
 }
 
-extern "C" int etpgt_sampled_loss_bwd(const float* sess, const float* table, const int64_t* targets,
-                                      const int64_t* negatives, int64_t batch, int num_neg, int dim, int mode,
-                                      float alpha, float temperature, double total_sessions, const float* scores,
-                                      const float* d_loss, int64_t num_items, int64_t padding_idx,
-                                      float* d_sess, float* d_table,
-                                      void* ws, size_t ws_bytes, etpgt_stream_t stream_) {
+extern "C" int etpgt_sampled_loss_bwd_planned(const float* sess, const float* table, const int64_t* targets,
+                                              const int64_t* negatives, int64_t batch, int num_neg, int dim,
+                                              int mode, float alpha, float temperature, double total_sessions,
+                                              const float* scores, const float* d_loss, int64_t num_items,
+                                              int64_t padding_idx, const int32_t* plan_sorted_key,
+                                              const int32_t* plan_perm, float* d_sess, float* d_table, void* ws,
+                                              size_t ws_bytes, etpgt_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc = check_loss_args("sampled_loss_bwd", batch, num_neg, dim, mode, temperature, total_sessions);
   if (rc != ETPGT_OK) return rc;
@@ -215,8 +216,22 @@ extern "C" int etpgt_sampled_loss_bwd(const float* sess, const float* table, con
   ETPGT_CHECK_LAUNCH("loss_bwd");
   if (d_table != nullptr) {
     // the padding row keeps a zero gradient (nn.Embedding(padding_idx=0), base.py:36)
+    if (plan_sorted_key != nullptr)   // keys [b][0] = target, [b][1 + c] = negative c: sorted once per batch
+      return etpgt_scatter_rows_planned(plan_sorted_key, plan_perm, coef, sess, m, num_neg + 1, dim, padding_idx,
+                                        d_table, stream_);
     return etpgt_scatter_rows(keys, coef, sess, m, num_neg + 1, dim, num_items, padding_idx, d_table,
                               static_cast<char*>(ws) + w.used, ws_bytes - w.used, stream_);
   }
   return ETPGT_OK;
+}
+
+extern "C" int etpgt_sampled_loss_bwd(const float* sess, const float* table, const int64_t* targets,
+                                      const int64_t* negatives, int64_t batch, int num_neg, int dim, int mode,
+                                      float alpha, float temperature, double total_sessions, const float* scores,
+                                      const float* d_loss, int64_t num_items, int64_t padding_idx,
+                                      float* d_sess, float* d_table,
+                                      void* ws, size_t ws_bytes, etpgt_stream_t stream) {
+  return etpgt_sampled_loss_bwd_planned(sess, table, targets, negatives, batch, num_neg, dim, mode, alpha, temperature,
+                                        total_sessions, scores, d_loss, num_items, padding_idx, nullptr, nullptr,
+                                        d_sess, d_table, ws, ws_bytes, stream);
 }

@@ -76,6 +76,59 @@ extern "C" size_t etpgt_scatter_rows_workspace_bytes(int64_t m) {
   return 4 * align_up(n * sizeof(int32_t)) + align_up(sort_temp_bytes(n)) + 256;
 }
 
+// The sort of a scatter depends on the keys only, and the keys of both scatters of a training step (the
+// batch's node ids; its targets + negatives) are known as soon as the batch exists.  So the sort can be
+// made ONCE per batch, next to the CSR / CSC index ("scatter plan"), off the critical path of the step.
+extern "C" size_t etpgt_scatter_plan_workspace_bytes(int64_t m) {
+  int64_t n = m > 0 ? m : 1;
+  return 2 * align_up(n * sizeof(int32_t)) + align_up(sort_temp_bytes(n)) + 256;
+}
+
+extern "C" int etpgt_scatter_plan(const int64_t* keys, int64_t m, int64_t num_rows, int32_t* sorted_key,
+                                  int32_t* perm, void* ws, size_t ws_bytes, etpgt_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ETPGT_REQUIRE(m >= 0 && m < (int64_t(1) << 31) && num_rows >= 1 && num_rows < (int64_t(1) << 31),
+                "scatter_plan: bad size");
+  if (m == 0) return ETPGT_OK;
+  ETPGT_REQUIRE(keys && sorted_key && perm, "scatter_plan: null pointer");
+  if (ws_bytes < etpgt_scatter_plan_workspace_bytes(m)) {
+    set_error("scatter_plan: workspace %zu < %zu", ws_bytes, etpgt_scatter_plan_workspace_bytes(m));
+    return ETPGT_EWORKSPACE;
+  }
+  Workspace w(ws, ws_bytes);
+  int32_t* key_a = w.take<int32_t>(m);
+  int32_t* iota = w.take<int32_t>(m);
+  size_t temp_bytes = sort_temp_bytes(m);
+  void* temp = w.take<char>(temp_bytes);
+  narrow_keys_iota_kernel<<<grid_for(m, kThreads, 8), kThreads, 0, stream>>>(keys, key_a, iota, m);
+  ETPGT_CHECK_LAUNCH("scatter_plan narrow");
+  cudaError_t err = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, key_a, sorted_key, iota, perm,
+                                                    static_cast<int>(m), 0, key_bits(num_rows), stream);
+  if (err != cudaSuccess) { set_error("scatter_plan sort: %s", cudaGetErrorString(err)); return ETPGT_ECUDA; }
+  count_launch(4);
+  return ETPGT_OK;
+}
+
+extern "C" int etpgt_scatter_rows_planned(const int32_t* sorted_key, const int32_t* perm, const float* coef,
+                                          const float* src, int64_t m, int src_div, int dim, int64_t skip_key,
+                                          float* d_table, etpgt_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ETPGT_REQUIRE(supported_dim(dim), "scatter_rows: unsupported dim %d", dim);
+  ETPGT_REQUIRE(m >= 0 && m < (int64_t(1) << 31) && src_div >= 1, "scatter_rows: bad size");
+  if (m == 0) return ETPGT_OK;
+  ETPGT_REQUIRE(sorted_key && perm && src && d_table, "scatter_rows_planned: null pointer");
+#define CALL(D)                                                                                         \
+  {                                                                                                     \
+    const int64_t gpc = (kThreads / 32) * RowGeom<D>::GROUPS;                                           \
+    segment_rows_add_kernel<D><<<grid_for(m, (int)gpc, 8), kThreads, 0, stream>>>(sorted_key, perm, coef, src, m, \
+                                                                                 src_div, (int)skip_key, d_table); \
+  }
+  ETPGT_DISPATCH_DIM(dim, CALL)
+#undef CALL
+  ETPGT_CHECK_LAUNCH("segment_rows_add");
+  return ETPGT_OK;
+}
+
 extern "C" int etpgt_scatter_rows(const int64_t* keys, const float* coef, const float* src, int64_t m,
                                   int src_div, int dim, int64_t num_rows, int64_t skip_key, float* d_table,
                                   void* ws, size_t ws_bytes, etpgt_stream_t stream_) {

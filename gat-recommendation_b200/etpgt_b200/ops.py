@@ -7,6 +7,8 @@ path runs in libetpgt_b200.so, except the dense node projections which are libra
 
 from __future__ import annotations
 
+import weakref
+
 import torch
 import torch.distributed as dist
 
@@ -87,6 +89,108 @@ def segment_ptr(batch_vec: torch.Tensor, num_sessions: int) -> torch.Tensor:
     return out
 
 
+# ------------------------------------------------------------------------------ scatter plans
+
+
+class ScatterPlan:
+    """Stable sort of the keys of one row scatter (`etpgt_scatter_plan`): `sorted_key [m]`, `perm [m]`.
+    The keys of both table-gradient scatters of a step — the batch's node ids (embedding backward) and
+    [target | negatives] per session (loss backward) — are inputs of the batch, so their sorts are batch
+    preparation (the device-side counterpart of the reference's collate, dataloader.py:157-202), not part
+    of the step's dependent chain."""
+
+    __slots__ = ("m", "sorted_key", "perm")
+
+    def __init__(self, keys: torch.Tensor, num_rows: int):
+        _require_cuda(keys, "scatter keys")
+        keys = _i64(keys).reshape(-1)
+        self.m = int(keys.numel())
+        dev = keys.device
+        self.sorted_key = torch.empty(self.m, dtype=torch.int32, device=dev)
+        self.perm = torch.empty(self.m, dtype=torch.int32, device=dev)
+        ws = workspace(size("etpgt_scatter_plan_workspace_bytes", self.m), dev)
+        call("etpgt_scatter_plan", ptr(keys), self.m, int(num_rows), ptr(self.sorted_key), ptr(self.perm),
+             ptr(ws), ws.numel(), stream())
+
+
+# Plans are found again by the identity of the key tensors' memory: (data_ptr, numel) of the tensors the plan
+# was made from, valid while those tensors are alive and unmodified (weak references + version counters).
+_PLANS: dict = {}
+
+
+def _plan_key(*tensors):
+    return tuple((t.data_ptr(), t.numel()) for t in tensors)
+
+
+def _register_plan(plan: ScatterPlan, *tensors) -> None:
+    key = _plan_key(*tensors)
+
+    def drop(_ref, key=key):
+        _PLANS.pop(key, None)
+
+    _PLANS[key] = (plan, tuple(weakref.ref(t, drop) for t in tensors), tuple(t._version for t in tensors))
+
+
+def _find_plan(*tensors):
+    if not _PLANS:
+        return None
+    entry = _PLANS.get(_plan_key(*tensors))
+    if entry is None:
+        return None
+    plan, refs, versions = entry
+    for t, ref, version in zip(tensors, refs, versions):
+        base = ref()
+        # a view of the planned tensor (e.g. the trainer's negative_items.view(B, -1), trainer.py:87-89)
+        # shares its version counter
+        if base is None or base.device != t.device or t._version != version:
+            return None
+    return plan
+
+
+class PreparedBatch:
+    """What `prepare_batch` built: the graph index and the two scatter plans (for `record_stream`
+    bookkeeping when preparation runs on a side stream)."""
+
+    __slots__ = ("index", "plan_nodes", "plan_loss", "loss_keys")
+
+    def tensors(self):
+        out = [self.index.rowptr, self.index.col, self.index.eperm, self.index.colptr, self.index.row,
+               self.index.cpos]
+        for plan in (self.plan_nodes, self.plan_loss):
+            if plan is not None:
+                out += [plan.sorted_key, plan.perm]
+        if self.loss_keys is not None:
+            out.append(self.loss_keys)
+        return out
+
+
+def prepare_batch(batch, num_items: int | None = None) -> PreparedBatch:
+    """Integer preparation of one batch on the current stream: CSR / CSC index of `batch.edge_index` and, when
+    the table size is given, the scatter plans of `batch.x` and of `batch.target_item | batch.negative_items`.
+    Everything here depends on the batch's inputs only, so a loader (or a side stream one step ahead) runs
+    it off the training step's critical path; the model and the loss find the results again through the
+    batch object / the key tensors.  Without this call the step builds the same things inline."""
+    prepared = PreparedBatch()
+    prepared.index = graph_index_of(batch, batch.edge_index, batch.x.numel())
+    prepared.plan_nodes = prepared.plan_loss = prepared.loss_keys = None
+    if num_items is not None:
+        prepared.plan_nodes = ScatterPlan(batch.x, num_items)
+        _register_plan(prepared.plan_nodes, batch.x)
+        targets = getattr(batch, "target_item", None)
+        negatives = getattr(batch, "negative_items", None)
+        if targets is not None and negatives is not None and targets.numel() > 0:
+            b = targets.numel()
+            # keys [b][0] = target, [b][1 + c] = negative c (the layout etpgt_sampled_loss_bwd scatters in)
+            prepared.loss_keys = torch.cat([_i64(targets).reshape(b, 1), _i64(negatives).reshape(b, -1)], dim=1)
+            prepared.plan_loss = ScatterPlan(prepared.loss_keys, num_items)
+            _register_plan(prepared.plan_loss, targets, negatives)
+    try:
+        object.__setattr__(batch, "_etpgt_prepared", prepared)   # keeps the plans alive with the batch
+    except Exception:
+        pass
+    return prepared
+
+
 # ------------------------------------------------------------------------------ embedding + PE
 
 
@@ -110,6 +214,7 @@ class EmbedPE(torch.autograd.Function):
              ptr(w_pe_c), ptr(b_pe_c), k_pe, dim, ptr(out), stream())
         ctx.save_for_backward(ids, pe)
         ctx.table_ref = table
+        ctx.plan = _find_plan(ids)          # per-batch sort of the node ids, if prepare_batch made one
         ctx.meta = (table_c.size(0), dim, k_pe, int(bool(pe_per_node)), -1 if padding_idx is None else int(padding_idx))
         return out
 
@@ -129,7 +234,9 @@ class EmbedPE(torch.autograd.Function):
             d_w = torch.empty(dim, k_pe, dtype=torch.float32, device=dev)
             d_b = torch.empty(dim, dtype=torch.float32, device=dev)
         ws = workspace(size("etpgt_embed_pe_bwd_workspace_bytes", n, dim, max(k_pe, 1)), dev)
-        call("etpgt_embed_pe_bwd", ptr(ids), n, ptr(d_out), num_items, ptr(pe), per_node, k_pe, dim, padding_idx,
+        plan = ctx.plan if d_table is not None and ctx.plan is not None and ctx.plan.m == n else None
+        call("etpgt_embed_pe_bwd_planned", ptr(ids), n, ptr(d_out), num_items, ptr(pe), per_node, k_pe, dim,
+             padding_idx, ptr(plan.sorted_key) if plan else None, ptr(plan.perm) if plan else None,
              ptr(d_table), ptr(d_w), ptr(d_b), ptr(ws), ws.numel(), stream())
         return None, (None if sink is not None else d_table), None, None, d_w, d_b, None
 
@@ -750,6 +857,7 @@ class SampledLoss(torch.autograd.Function):
              float(alpha), float(temperature), total, ptr(scores), ptr(losses), ptr(ws), ws.numel(), stream())
         ctx.save_for_backward(sess_c, table_c, targets, negatives, scores)
         ctx.table_ref = table
+        ctx.plan = _find_plan(targets, negatives)
         ctx.meta = (mode, float(alpha), float(temperature), total, -1 if padding_idx is None else int(padding_idx))
         return losses
 
@@ -767,8 +875,10 @@ class SampledLoss(torch.autograd.Function):
             sink = _grad_sink(ctx.table_ref)
             d_table = sink if sink is not None else torch.zeros_like(table)
         ws = workspace(size("etpgt_sampled_loss_workspace_bytes", b, num_neg, dim), dev)
-        call("etpgt_sampled_loss_bwd", ptr(sess), ptr(table), ptr(targets), ptr(negatives), b, num_neg, dim, mode,
-             alpha, temperature, total, ptr(scores), ptr(d_loss), table.size(0), padding_idx, ptr(d_sess),
+        plan = ctx.plan if d_table is not None and ctx.plan is not None and ctx.plan.m == b * (num_neg + 1) else None
+        call("etpgt_sampled_loss_bwd_planned", ptr(sess), ptr(table), ptr(targets), ptr(negatives), b, num_neg, dim,
+             mode, alpha, temperature, total, ptr(scores), ptr(d_loss), table.size(0), padding_idx,
+             ptr(plan.sorted_key) if plan else None, ptr(plan.perm) if plan else None, ptr(d_sess),
              ptr(d_table), ptr(ws), ws.numel(), stream())
         return d_sess, (None if sink is not None else d_table), None, None, None, None, None, None, None
 

@@ -17,7 +17,7 @@ from pathlib import Path
 import numpy as np
 import torch
 
-from .. import data
+from .. import data, ops
 
 
 def load_sessions(sessions_path) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
@@ -72,6 +72,8 @@ class DeviceSessionLoader:
                                         max_len=self.max_session_length)
             # PyG collate concatenates the per-sample [num_neg] tensors (trainer.py:87-89 reshapes them back)
             batch.negative_items = neg.reshape(-1) if self.flatten_negatives else neg
+            # the rest of "collate": CSR / CSC index and the sorts of the two table-gradient scatters
+            ops.prepare_batch(batch, self.num_items)
             self.step += 1
             yield batch
 

@@ -394,6 +394,30 @@ int etpgt_cooc_graph_build(const int64_t* sess_ptr, const int64_t* sess_items, c
                            int64_t* last_ts, int64_t* num_edges, void* ws, size_t ws_bytes,
                            etpgt_stream_t stream);
 
+/* Scatter plans: the sort of a scatter depends on its keys only, and the keys of both scatters of a
+ * training step (the batch's node ids for the embedding backward; [target | negatives] per session for the
+ * loss backward) are fixed once the batch exists.  etpgt_scatter_plan sorts them once per batch (next to
+ * the CSR / CSC index, off the step's critical path): sorted_key [m], perm [m] (stable).  The *_planned
+ * entry points then only run the owner-per-row accumulation.  Loss keys are laid out
+ * [b][0] = target, [b][1 + c] = negative c. */
+size_t etpgt_scatter_plan_workspace_bytes(int64_t m);
+int etpgt_scatter_plan(const int64_t* keys, int64_t m, int64_t num_rows, int32_t* sorted_key, int32_t* perm,
+                       void* ws, size_t ws_bytes, etpgt_stream_t stream);
+int etpgt_scatter_rows_planned(const int32_t* sorted_key, const int32_t* perm, const float* coef,
+                               const float* src, int64_t m, int src_div, int dim, int64_t skip_key,
+                               float* d_table, etpgt_stream_t stream);
+int etpgt_embed_pe_bwd_planned(const int64_t* ids, int64_t n, const float* d_out, int64_t num_items,
+                               const float* pe, int pe_per_node, int k_pe, int dim, int64_t padding_idx,
+                               const int32_t* plan_sorted_key, const int32_t* plan_perm, float* d_table,
+                               float* d_w_pe, float* d_b_pe, void* ws, size_t ws_bytes, etpgt_stream_t stream);
+int etpgt_sampled_loss_bwd_planned(const float* sess, const float* table, const int64_t* targets,
+                                   const int64_t* negatives, int64_t batch, int num_neg, int dim,
+                                   int mode, float alpha, float temperature, double total_sessions,
+                                   const float* scores, const float* d_loss, int64_t num_items,
+                                   int64_t padding_idx, const int32_t* plan_sorted_key,
+                                   const int32_t* plan_perm, float* d_sess, float* d_table, void* ws,
+                                   size_t ws_bytes, etpgt_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

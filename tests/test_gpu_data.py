@@ -212,3 +212,66 @@ def test_co_event_graph_edge_cases_and_synthetic_scale():
     want = graph_ref.co_event_graph(ptr, items, None, 5)
     assert np.array_equal(i.cpu().numpy(), want[0]) and np.array_equal(j.cpu().numpy(), want[1])
     assert np.array_equal(c.cpu().numpy(), want[2])
+
+
+def test_scatter_plans_give_bit_identical_table_gradients():
+    """ops.prepare_batch (index + the two scatter plans, made on a side stream one step ahead) must not change
+    a single bit of the step: same loss, same table gradient, same dense gradients as the inline path; the
+    plan of the loss keys is found again through the trainer's `negative_items.view(B, -1)` (trainer.py:87-89),
+    and a modified key tensor invalidates its plan."""
+    from etpgt_b200 import data, ops, synth
+    from etpgt_b200.model import create_graph_transformer_optimized
+
+    d = synth.generate(num_sessions=800, graph_sessions=600, num_items=500, clusters=20, seed=3)
+    graph = data.ItemGraph(d.item_i, d.item_j, d.num_items)
+    store = data.SessionStore(d.sess_ptr, d.sess_items)
+    ids = np.arange(100, 420)
+    torch.manual_seed(0)
+    model = create_graph_transformer_optimized(d.num_items, 64, 64, dropout=0.0, laplacian_k=8).cuda()
+    model.laplacian_pe._cached_pe = torch.randn(d.num_items, 8, device="cuda").abs()
+    model.train()
+
+    def run(prepare, loss_kind):
+        batch = data.build_batch(graph, store, ids)
+        batch.negative_items = data.sample_negatives(store, ids, d.num_items, 5, seed=1, step=0).reshape(-1)
+        if prepare:
+            side = torch.cuda.Stream()
+            with torch.cuda.stream(side):
+                prepared = ops.prepare_batch(batch, d.num_items)
+            torch.cuda.current_stream().wait_stream(side)
+            assert prepared.plan_nodes.m == batch.x.numel() and prepared.plan_loss.m == len(ids) * 6
+            key = prepared.plan_loss.sorted_key.cpu().numpy()
+            assert np.array_equal(key, np.sort(prepared.loss_keys.cpu().numpy().reshape(-1), kind="stable"))
+            perm = prepared.plan_loss.perm.cpu().numpy()    # stable: equal keys keep ascending position
+            assert np.array_equal(perm, np.argsort(prepared.loss_keys.cpu().numpy().reshape(-1), kind="stable"))
+        model.zero_grad()
+        for bn in model.batch_norms:
+            bn.reset_running_stats()
+        launches = ops.launch_count()
+        sess = model(batch)
+        loss = ops.sampled_loss(sess, model.item_embedding, batch.target_item,
+                                batch.negative_items.view(len(ids), -1), loss_kind)[0]
+        loss.backward()
+        grads = {k: p.grad.clone() for k, p in model.named_parameters()}
+        return loss.item(), grads, ops.launch_count() - launches
+
+    for kind in ("bpr", "dual"):
+        loss_a, grads_a, launches_a = run(False, kind)
+        loss_b, grads_b, launches_b = run(True, kind)
+        assert loss_a == loss_b
+        for k in grads_a:
+            assert torch.equal(grads_a[k], grads_b[k]), k
+        # inline path: CSR build + two scatter sorts inside the step; prepared path: none of them
+        assert launches_b < launches_a - 8, (launches_a, launches_b)
+
+    # a key tensor modified after planning must not be served by the stale plan
+    batch = data.build_batch(graph, store, ids)
+    batch.negative_items = data.sample_negatives(store, ids, d.num_items, 5, seed=1, step=0)
+    ops.prepare_batch(batch, d.num_items)
+    assert ops._find_plan(batch.target_item, batch.negative_items) is not None
+    assert ops._find_plan(batch.x) is not None
+    batch.negative_items[0, 0] = 1
+    assert ops._find_plan(batch.target_item, batch.negative_items) is None
+    x_key = ops._plan_key(batch.x)
+    del batch
+    assert x_key not in ops._PLANS          # plans die with their key tensors
