@@ -85,6 +85,9 @@ _PROTOTYPES = {
     "etpgt_sampled_loss_bwd_planned": (I, [P, P, P, P, L, I, I, I, F, F, D, P, P, L, L, P, P, P, P, P, Z, P]),
     "etpgt_cooc_graph_workspace_bytes": (Z, [L, I]),
     "etpgt_cooc_graph_build": (I, [P, P, P, L, L, I, L, L, P, P, P, P, P, P, Z, P]),
+    "etpgt_gt_step_arena_bytes": (Z, [P]),
+    "etpgt_gt_step_num_phases": (I, [P]),
+    "etpgt_gt_step_run": (I, [P, I, I, P]),
     "etpgt_adam_step": (I, [P, I, D, D, D, D, D, I, L, I, P]),
 }
 

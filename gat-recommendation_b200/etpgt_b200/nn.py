@@ -48,6 +48,11 @@ class TransformerConv(nn.Module):
         parameters are re-homed (once per device move) as consecutive row blocks of a single buffer, and
         ops.FusedRows presents that buffer to autograd as a function of the four parameters, so state
         dicts, optimizers and checkpoints keep seeing four ordinary parameters."""
+        store, parts = self.fused_store(name)
+        return ops.FusedRows.apply(store, *parts)
+
+    def fused_store(self, name: str):
+        """(the single buffer holding query | key | value | skip `name`, the four parameters aliasing it)."""
         parts = [getattr(lin, name) for lin in (self.lin_query, self.lin_key, self.lin_value, self.lin_skip)]
         cache = self.__dict__.setdefault("_fused_store", {})
         store = cache.get(name)
@@ -65,7 +70,7 @@ class TransformerConv(nn.Module):
                     p.data = store[row:row + p.size(0)]
                     row += p.size(0)
             cache[name] = store
-        return ops.FusedRows.apply(store, *parts)
+        return store, parts
 
     def fused_parameters(self):
         if self.lin_query.weight.is_cuda and torch.is_grad_enabled():

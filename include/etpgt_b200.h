@@ -418,6 +418,82 @@ int etpgt_sampled_loss_bwd_planned(const float* sess, const float* table, const 
                                    const int32_t* plan_perm, float* d_sess, float* d_table, void* ws,
                                    size_t ws_bytes, etpgt_stream_t stream);
 
+/* ---- a11: step driver --------------------------------------------------------------------------
+ * One host call for the whole training step of graph_transformer_optimized — what Trainer.train_epoch
+ * (etpgt/train/trainer.py:95-127) runs between `optimizer.zero_grad()` and `optimizer.step()`:
+ * model(batch) (etpgt/model/graph_transformer.py:126-182, use_ffn=False), the sampled loss
+ * (etpgt/train/losses.py) and the backward pass.  It launches exactly the entry points above, in the order and
+ * with the arguments of the per-operator path, out of one caller-provided arena; results are bit-identical to
+ * calling them one by one.
+ *
+ * All pointers are device pointers except the descriptor itself (host).  Gradient outputs are OVERWRITTEN,
+ * except d_table whose rows are ADDED (caller-zeroed, or the optimizer's persistent gradient buffer).
+ * layer[l].weight / bias are the query|key|value|skip blocks as one [4*dim, dim] / [4*dim] buffer.
+ * Dropout: attention-weight masks from (alpha_seed, alpha_p), layer dropout from (drop_seed, drop_p), both
+ * Philox4x32-10 as in etpgt_dropout_mask / etpgt_bn_apply_ex; ignored when training == 0.
+ * plan_* (optional): etpgt_scatter_plan of `ids` and of the [target | negatives] keys.
+ *
+ * Phases (data parallelism): the step is cut at the BatchNorm statistics exchanges into 2*layers+1 phases;
+ * run [phase_begin, phase_end) per call.  bn_sums is [2*layers][2*dim+1] doubles: row l = forward sums of
+ * layer l (complete after phase l), row layers+l = backward sums of layer l (complete after phase
+ * 2*layers-1-l ... i.e. just before the phase that consumes them).  With distributed != 0 the caller
+ * all-reduces the row a phase produced before running the next phase (the row's last element carries the
+ * row count); with distributed == 0 run all phases in one call. */
+#define ETPGT_GT_MAX_LAYERS 4
+typedef struct etpgt_gt_layer {
+  const float* weight;       /* [4*dim, dim] */
+  const float* bias;         /* [4*dim] */
+  const float* w_beta;       /* [3*dim] or NULL (beta=False) */
+  const float* bn_weight;    /* [dim] */
+  const float* bn_bias;      /* [dim] */
+  float* running_mean;       /* [dim], updated in training */
+  float* running_var;        /* [dim] */
+  int64_t* num_batches_tracked; /* scalar, +1 in training (may be NULL) */
+  float* d_weight;           /* [4*dim, dim] */
+  float* d_bias;             /* [4*dim] */
+  float* d_w_beta;           /* [3*dim] or NULL */
+  float* d_bn_weight;        /* [dim] */
+  float* d_bn_bias;          /* [dim] */
+  double momentum, eps;
+  uint64_t alpha_seed, drop_seed;
+} etpgt_gt_layer_t;
+
+typedef struct etpgt_gt_step {
+  int64_t struct_bytes;      /* sizeof(etpgt_gt_step_t): guards against header / binding drift */
+  /* batch (PyG collate layout) and its index (etpgt_csr_from_coo) */
+  int64_t num_nodes, num_edges, num_sessions;
+  const int64_t* ids;        /* [N] item id per node */
+  const int64_t* batch_vec;  /* [N] session index per node, non-decreasing */
+  const int32_t *rowptr, *col, *eperm, *colptr, *row, *cpos;
+  const int64_t* targets;    /* [B] */
+  const int64_t* negatives;  /* [B, num_neg] */
+  const int32_t *plan_nodes_key, *plan_nodes_perm, *plan_loss_key, *plan_loss_perm; /* or NULL */
+  /* model */
+  int64_t num_items, padding_idx;
+  int32_t dim, heads, num_layers, k_pe, num_neg, readout_mode, loss_mode;
+  int32_t training, backward, distributed;
+  float alpha, temperature;
+  double total_sessions, alpha_p, drop_p;
+  const float* table;        /* [num_items, dim] */
+  const float* pe;           /* [num_items, k_pe] cached Laplacian PE or NULL */
+  const float* w_pe;         /* [dim, k_pe] */
+  const float* b_pe;         /* [dim] */
+  float* d_table;            /* [num_items, dim] rows ADDED */
+  float* d_w_pe;             /* [dim, k_pe] */
+  float* d_b_pe;             /* [dim] */
+  etpgt_gt_layer_t layer[ETPGT_GT_MAX_LAYERS];
+  /* outputs / exchange */
+  float* sess;               /* [B, dim] session embeddings */
+  float* losses;             /* [3] (total, listwise, bpr) */
+  double* bn_sums;           /* [2*layers][2*dim+1] */
+  void* arena;
+  size_t arena_bytes;        /* >= etpgt_gt_step_arena_bytes */
+} etpgt_gt_step_t;
+
+size_t etpgt_gt_step_arena_bytes(const etpgt_gt_step_t* step);
+int etpgt_gt_step_num_phases(const etpgt_gt_step_t* step);
+int etpgt_gt_step_run(const etpgt_gt_step_t* step, int phase_begin, int phase_end, etpgt_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,202 @@
+"""The C++ step driver (etpgt_gt_step_run, §8 a11) against the per-operator autograd path: same kernels, same
+order, same arguments => every output must be BIT-identical — loss components, session embeddings, every
+parameter gradient (incl. the item table), BatchNorm running statistics and counters — with dropout (same
+torch seed), every driven readout and loss, 1-3 layers, with and without Laplacian PE, with and without
+prepared scatter plans, run as one call or phase by phase.  The autograd path itself is checked against the
+fp64 oracle in tests/test_gpu_models.py / test_gpu_training.py; one oracle check of the driver is repeated
+here."""
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(dim=64, layers=2, heads=2, dropout=0.1, readout="mean", pe=True, sessions=300, seed=3):
+    from etpgt_b200 import data, synth
+    from etpgt_b200.model import create_graph_transformer_optimized
+
+    d = synth.generate(num_sessions=800, graph_sessions=600, num_items=500, clusters=20, seed=seed)
+    graph = data.ItemGraph(d.item_i, d.item_j, d.num_items)
+    store = data.SessionStore(d.sess_ptr, d.sess_items)
+    ids = np.arange(50, 50 + sessions)
+
+    def make_batch():
+        batch = data.build_batch(graph, store, ids)
+        batch.negative_items = data.sample_negatives(store, ids, d.num_items, 5, seed=1, step=0).reshape(-1)
+        return batch
+
+    torch.manual_seed(0)
+    model = create_graph_transformer_optimized(d.num_items, dim, dim, num_layers=layers, num_heads=heads,
+                                               dropout=dropout, readout_type=readout, use_laplacian_pe=pe,
+                                               laplacian_k=8).cuda()
+    if pe:
+        model.laplacian_pe._cached_pe = torch.randn(d.num_items, 8, device="cuda").abs()
+    model.train()
+    return d, model, make_batch
+
+
+def _snapshot(model):
+    out = {k: p.grad.clone() for k, p in model.named_parameters()}
+    for l, bn in enumerate(model.batch_norms):
+        out[f"rm{l}"], out[f"rv{l}"] = bn.running_mean.clone(), bn.running_var.clone()
+        out[f"nbt{l}"] = bn.num_batches_tracked.clone()
+    return out
+
+
+def _reset(model):
+    model.zero_grad(set_to_none=True)
+    for bn in model.batch_norms:
+        bn.reset_running_stats()
+
+
+def _autograd_step(model, batch, loss_kind, seed):
+    from etpgt_b200 import ops
+
+    _reset(model)
+    torch.manual_seed(seed)
+    sess = model(batch)
+    losses = ops.sampled_loss(sess, model.item_embedding, batch.target_item,
+                              batch.negative_items.view(batch.target_item.numel(), -1), loss_kind)
+    losses[0].backward()
+    return losses.detach().clone(), sess.detach().clone(), _snapshot(model)
+
+
+def _driver_step(model, batch, loss_kind, seed, phase_by_phase=False):
+    from etpgt_b200 import _lib
+    from etpgt_b200.train.step import FusedTrainStep
+
+    _reset(model)
+    torch.manual_seed(seed)
+    step = FusedTrainStep(model, loss_kind)
+    if phase_by_phase:
+        # single-GPU run of the data-parallel control flow: one call per phase, no exchange in between
+        calls = []
+        real = _lib.call
+
+        def spy(name, *args):
+            if name == "etpgt_gt_step_run":
+                desc, lo, hi, stream = args
+                for p in range(lo, hi):
+                    calls.append(p)
+                    real(name, desc, p, p + 1, stream)
+                return
+            return real(name, *args)
+
+        import etpgt_b200.train.step as step_mod
+        step_mod._lib.call, saved = spy, step_mod._lib.call
+        try:
+            losses = step(batch)
+        finally:
+            step_mod._lib.call = saved
+        assert calls == list(range(2 * len(model.convs) + 1))
+    else:
+        losses = step(batch)
+    return losses.clone(), step.session_embeddings.clone(), _snapshot(model)
+
+
+def _assert_identical(a, b):
+    (la, sa, ga), (lb, sb, gb) = a, b
+    assert torch.equal(la, lb), (la, lb)
+    assert torch.equal(sa, sb)
+    assert ga.keys() == gb.keys()
+    for k in ga:
+        assert torch.equal(ga[k], gb[k]), k
+
+
+@pytest.mark.parametrize("dim,layers,heads,dropout,readout,pe,loss", [
+    (64, 2, 2, 0.0, "mean", True, "bpr"),
+    (64, 2, 2, 0.1, "mean", True, "dual"),
+    (256, 2, 2, 0.1, "mean", True, "bpr"),
+    (128, 3, 4, 0.1, "max", False, "listwise"),
+    (32, 1, 1, 0.2, "last", True, "bpr"),
+])
+def test_driver_is_bit_identical_to_the_autograd_path(dim, layers, heads, dropout, readout, pe, loss):
+    from etpgt_b200 import ops
+
+    d, model, make_batch = _setup(dim, layers, heads, dropout, readout, pe)
+    want = _autograd_step(model, make_batch(), loss, seed=11)
+    launches = ops.launch_count()
+    got = _driver_step(model, make_batch(), loss, seed=11)
+    driver_launches = ops.launch_count() - launches
+    _assert_identical(want, got)
+    assert driver_launches > 30          # the library's kernels ran (nothing else can have produced this)
+    # prepared batch (index + scatter plans made ahead): still the same bits
+    batch = make_batch()
+    ops.prepare_batch(batch, d.num_items)
+    _assert_identical(want, _driver_step(model, batch, loss, seed=11))
+    # the data-parallel control flow (one call per phase)
+    _assert_identical(want, _driver_step(model, make_batch(), loss, seed=11, phase_by_phase=True))
+
+
+def test_driver_matches_the_fp64_oracle():
+    from oracle import model_ref
+
+    d, model, make_batch = _setup(dim=64, dropout=0.0)
+    batch = make_batch()
+    state = {k: (v.detach().double().cpu() if v.is_floating_point() else v.cpu()) for k, v in model.state_dict().items()}
+    state["laplacian_pe._cached_pe"] = model.laplacian_pe._cached_pe.double().cpu()
+    losses, sess, grads = _driver_step(model, batch, "bpr", seed=0)
+    want = model_ref.graph_transformer_forward(state, batch.x.cpu(), batch.edge_index.cpu(), batch.batch.cpu(),
+                                               num_layers=2, num_heads=2, training=True)
+    negatives = batch.negative_items.view(batch.target_item.numel(), -1).cpu()
+    want_loss = model_ref.bpr_loss(want, state["item_embedding.weight"], batch.target_item.cpu(), negatives)
+    assert (sess.double().cpu() - want).abs().max().item() <= 1e-4 * want.abs().max().item()
+    assert abs(losses[0].item() - want_loss.item()) <= 1e-4 * abs(want_loss.item())
+    assert losses[2].item() == losses[0].item()      # bpr mode: total = bpr component
+
+
+def test_driver_gradient_semantics_and_training_loop():
+    """.grad is set when None and accumulated otherwise (torch semantics); with the device optimizer the table
+    gradient goes to its persistent buffer; a short training run equals the autograd run bit for bit."""
+    from etpgt_b200 import ops, optim
+    from etpgt_b200.train.step import FusedTrainStep
+
+    d, model, make_batch = _setup(dim=64, dropout=0.0)
+    batch = make_batch()
+    step = FusedTrainStep(model, "bpr")
+    _reset(model)
+    step(batch)
+    once = {k: p.grad.clone() for k, p in model.named_parameters()}
+    step(batch)                                   # no zero_grad in between: gradients accumulate
+    for k, p in model.named_parameters():
+        assert torch.allclose(p.grad, 2 * once[k], rtol=1e-6, atol=1e-12), k
+
+    def train(use_driver):
+        torch.manual_seed(0)
+        d2, m, mk = _setup(dim=64, dropout=0.1)
+        opt = optim.AdamW(m.parameters(), lr=1e-3, weight_decay=1e-5)
+        fused = FusedTrainStep(m, "bpr") if use_driver else None
+        out = []
+        torch.manual_seed(5)
+        for _ in range(4):
+            b = mk()
+            opt.zero_grad()
+            if use_driver:
+                loss = fused(b)[0]
+            else:
+                loss = ops.sampled_loss(m(b), m.item_embedding, b.target_item, b.negative_items.view(-1, 5), "bpr")[0]
+                loss.backward()
+            opt.step()
+            out.append(loss.item())
+        return out, {k: v.clone() for k, v in m.state_dict().items()}
+
+    losses_a, state_a = train(False)
+    losses_b, state_b = train(True)
+    assert losses_a == losses_b
+    for k in state_a:
+        assert torch.equal(state_a[k], state_b[k]), k
+
+
+def test_driver_rejects_what_it_does_not_cover():
+    from etpgt_b200.model import create_gat, create_graph_transformer
+    from etpgt_b200.train.step import FusedTrainStep
+
+    assert not FusedTrainStep.supported(create_graph_transformer(50, 64, 64).cuda())       # FFN variant
+    assert not FusedTrainStep.supported(create_gat(50, 64, 64).cuda())
+    with pytest.raises(NotImplementedError):
+        FusedTrainStep(create_graph_transformer(50, 64, 64, use_ffn=False, readout_type="attention").cuda())
+    d, model, make_batch = _setup(dim=64)
+    with pytest.raises(ValueError, match="Unknown loss type"):
+        FusedTrainStep(model, "hinge")
