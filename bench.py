@@ -254,6 +254,7 @@ def run_b200(args, rank, world_size, local_rank):
     import etpgt_b200
     from etpgt_b200 import _lib, ops, optim, parallel, synth
     from etpgt_b200.model import create_graph_transformer_optimized
+    from etpgt_b200.train.step import FusedTrainStep
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the etpgt_b200 path has no CPU fallback")
@@ -282,15 +283,24 @@ def run_b200(args, rank, world_size, local_rank):
     total_sessions = args.batch * world_size
     model.train()
 
+    # forward + BPR loss + backward through the C++ step driver (etpgt_gt_step_run: the same kernels as the
+    # per-operator autograd path, bit-identical results, one host call); ETPGT_BENCH_AUTOGRAD=1 times that path
+    fused = None if os.environ.get("ETPGT_BENCH_AUTOGRAD") else FusedTrainStep(model, "bpr")
+
     def step(batch):
         nonlocal total_sessions
-        sess = model(batch)
-        loss = ops.sampled_loss(sess, model.item_embedding, batch.target_item, batch.negative_items, "bpr",
-                                total_sessions=total_sessions)[0]
         opt.zero_grad()
-        loss.backward()
-        if distributed:
-            parallel.allreduce_gradients(params)
+        if fused is not None:
+            loss = fused(batch, total_sessions=total_sessions)[0]
+            if distributed:
+                fused.allreduce_gradients()
+        else:
+            sess = model(batch)
+            loss = ops.sampled_loss(sess, model.item_embedding, batch.target_item, batch.negative_items, "bpr",
+                                    total_sessions=total_sessions)[0]
+            loss.backward()
+            if distributed:
+                parallel.allreduce_gradients(params)
         opt.step()
         return loss
 
@@ -301,12 +311,16 @@ def run_b200(args, rank, world_size, local_rank):
 
     def timed(fn, steps):
         sync()
+        mallocs = torch.cuda.memory_stats(device).get("num_device_alloc", 0)
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record()
         for i in range(steps):
             fn(i)
         t1.record()
         sync()
+        mallocs = torch.cuda.memory_stats(device).get("num_device_alloc", 0) - mallocs
+        if mallocs and rank == 0:   # a cudaMalloc inside the timed region means the warm-up was too short
+            print(f"bench.py: {mallocs} device allocations inside a timed region", file=sys.stderr)
         ms = torch.tensor([t0.elapsed_time(t1)], device=device)
         if distributed:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -392,7 +406,7 @@ def run_b200(args, rank, world_size, local_rank):
     with ClockSampler(local_rank) as clocks:
         # ---- device-resident timing (value); the warm-up visits every rotating batch so that the
         # caching allocator has seen every shape before the clock starts
-        for i in range(max(args.warmup, len(dev_batches) + 1)):
+        for i in range(max(args.warmup, 2 * len(dev_batches) + 1)):
             value_step(i)
         pending["batch"] = None
         _lib.reset_launch_count()
@@ -403,7 +417,7 @@ def run_b200(args, rank, world_size, local_rank):
         # ---- end to end from pinned host batches (e2e)
         # the warm-up visits every rotating batch on the copy stream too (its allocator pool must have seen
         # every shape before the clock starts, exactly as for the device-resident loop above)
-        for i in range(max(args.warmup, len(host_batches) + 1)):
+        for i in range(max(args.warmup, 2 * len(host_batches) + 1)):
             e2e_step(i)
         drain_loss()
         pending["batch"] = None

@@ -20,6 +20,19 @@ __global__ void narrow_keys_iota_kernel(const int64_t* __restrict__ key64, int32
   }
 }
 
+// keys of the loss scatter: [s][0] = target of session s, [s][1 + c] = its negative c
+__global__ void narrow_loss_keys_iota_kernel(const int64_t* __restrict__ targets, const int64_t* __restrict__ negatives,
+                                             int64_t batch, int num_neg, int32_t* __restrict__ key32,
+                                             int32_t* __restrict__ iota) {
+  const int64_t n = batch * (num_neg + 1);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = i / (num_neg + 1);
+    const int c = static_cast<int>(i - s * (num_neg + 1));
+    key32[i] = static_cast<int32_t>(c == 0 ? targets[s] : negatives[s * num_neg + c - 1]);
+    iota[i] = static_cast<int32_t>(i);
+  }
+}
+
 template <int DIM>
 __global__ void __launch_bounds__(kThreads)
 segment_rows_add_kernel(const int32_t* __restrict__ sorted_key, const int32_t* __restrict__ perm,
@@ -84,8 +97,26 @@ extern "C" size_t etpgt_scatter_plan_workspace_bytes(int64_t m) {
   return 2 * align_up(n * sizeof(int32_t)) + align_up(sort_temp_bytes(n)) + 256;
 }
 
+static int scatter_plan_impl(const int64_t* keys, const int64_t* negatives, int64_t batch, int num_neg, int64_t m,
+                             int64_t num_rows, int32_t* sorted_key, int32_t* perm, void* ws, size_t ws_bytes,
+                             etpgt_stream_t stream_);
+
 extern "C" int etpgt_scatter_plan(const int64_t* keys, int64_t m, int64_t num_rows, int32_t* sorted_key,
-                                  int32_t* perm, void* ws, size_t ws_bytes, etpgt_stream_t stream_) {
+                                  int32_t* perm, void* ws, size_t ws_bytes, etpgt_stream_t stream) {
+  return scatter_plan_impl(keys, nullptr, 0, 0, m, num_rows, sorted_key, perm, ws, ws_bytes, stream);
+}
+
+extern "C" int etpgt_scatter_plan_loss(const int64_t* targets, const int64_t* negatives, int64_t batch, int num_neg,
+                                       int64_t num_rows, int32_t* sorted_key, int32_t* perm, void* ws,
+                                       size_t ws_bytes, etpgt_stream_t stream) {
+  ETPGT_REQUIRE(batch >= 0 && num_neg >= 1 && negatives != nullptr, "scatter_plan_loss: bad arguments");
+  return scatter_plan_impl(targets, negatives, batch, num_neg, batch * (num_neg + 1), num_rows, sorted_key, perm, ws,
+                           ws_bytes, stream);
+}
+
+static int scatter_plan_impl(const int64_t* keys, const int64_t* negatives, int64_t batch, int num_neg, int64_t m,
+                             int64_t num_rows, int32_t* sorted_key, int32_t* perm, void* ws, size_t ws_bytes,
+                             etpgt_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ETPGT_REQUIRE(m >= 0 && m < (int64_t(1) << 31) && num_rows >= 1 && num_rows < (int64_t(1) << 31),
                 "scatter_plan: bad size");
@@ -100,7 +131,11 @@ extern "C" int etpgt_scatter_plan(const int64_t* keys, int64_t m, int64_t num_ro
   int32_t* iota = w.take<int32_t>(m);
   size_t temp_bytes = sort_temp_bytes(m);
   void* temp = w.take<char>(temp_bytes);
-  narrow_keys_iota_kernel<<<grid_for(m, kThreads, 8), kThreads, 0, stream>>>(keys, key_a, iota, m);
+  if (negatives != nullptr)
+    narrow_loss_keys_iota_kernel<<<grid_for(m, kThreads, 8), kThreads, 0, stream>>>(keys, negatives, batch, num_neg,
+                                                                                  key_a, iota);
+  else
+    narrow_keys_iota_kernel<<<grid_for(m, kThreads, 8), kThreads, 0, stream>>>(keys, key_a, iota, m);
   ETPGT_CHECK_LAUNCH("scatter_plan narrow");
   cudaError_t err = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, key_a, sorted_key, iota, perm,
                                                     static_cast<int>(m), 0, key_bits(num_rows), stream);

@@ -48,24 +48,37 @@ class GraphIndex:
 
     __slots__ = ("num_nodes", "num_edges", "rowptr", "col", "eperm", "colptr", "row", "cpos")
 
-    def __init__(self, edge_index: torch.Tensor, num_nodes: int):
+    def __init__(self, edge_index: torch.Tensor, num_nodes: int, out: torch.Tensor | None = None,
+                 ws: torch.Tensor | None = None):
+        """`out` (optional): an int32 buffer of at least `GraphIndex.out_elems(num_nodes, num_edges)` elements the
+        six arrays are carved from; `ws`: a byte workspace of at least etpgt_csr_workspace_bytes."""
         _require_cuda(edge_index, "edge_index")
         edge_index = _i64(edge_index)
         dev = edge_index.device
         e = int(edge_index.size(1))
-        self.num_nodes, self.num_edges = int(num_nodes), e
-        i32 = dict(dtype=torch.int32, device=dev)
-        self.rowptr = torch.empty(num_nodes + 1, **i32)
-        self.colptr = torch.empty(num_nodes + 1, **i32)
-        self.col = torch.empty(e, **i32)
-        self.eperm = torch.empty(e, **i32)
-        self.row = torch.empty(e, **i32)
-        self.cpos = torch.empty(e, **i32)
-        nbytes = size("etpgt_csr_workspace_bytes", e, num_nodes)
-        ws = workspace(nbytes, dev)
+        num_nodes = int(num_nodes)
+        self.num_nodes, self.num_edges = num_nodes, e
+        if out is None:
+            out = torch.empty(self.out_elems(num_nodes, e), dtype=torch.int32, device=dev)
+        o1 = _pad64(num_nodes + 1)
+        o2, oe = 2 * o1, _pad64(e)
+        self.rowptr, self.colptr = out[:num_nodes + 1], out[o1:o1 + num_nodes + 1]
+        self.col, self.eperm = out[o2:o2 + e], out[o2 + oe:o2 + oe + e]
+        self.row, self.cpos = out[o2 + 2 * oe:o2 + 2 * oe + e], out[o2 + 3 * oe:o2 + 3 * oe + e]
+        if ws is None:
+            ws = workspace(size("etpgt_csr_workspace_bytes", e, num_nodes), dev)
         call("etpgt_csr_from_coo", ptr(edge_index[0]), ptr(edge_index[1]), e, num_nodes,
              ptr(self.rowptr), ptr(self.col), ptr(self.eperm), ptr(self.colptr), ptr(self.row), ptr(self.cpos),
              ptr(ws), ws.numel(), stream())
+
+    @staticmethod
+    def out_elems(num_nodes: int, num_edges: int) -> int:
+        return 2 * _pad64(num_nodes + 1) + 4 * _pad64(num_edges)
+
+
+def _pad64(n: int) -> int:
+    """int32 element counts rounded to 256 bytes, so that every array carved from one buffer stays aligned."""
+    return (int(n) + 63) // 64 * 64
 
 
 def graph_index_of(batch, edge_index: torch.Tensor, num_nodes: int) -> GraphIndex:
@@ -101,16 +114,31 @@ class ScatterPlan:
 
     __slots__ = ("m", "sorted_key", "perm")
 
-    def __init__(self, keys: torch.Tensor, num_rows: int):
+    def __init__(self, keys: torch.Tensor, num_rows: int, negatives: torch.Tensor | None = None,
+                 out: torch.Tensor | None = None, ws: torch.Tensor | None = None):
+        """keys [m] — or, with `negatives` [B, num_neg], keys = targets [B] and the plan covers the loss layout
+        [b][0] = target, [b][1 + c] = negative c.  `out`: int32 buffer of >= 2 * _pad64(m) elements."""
         _require_cuda(keys, "scatter keys")
         keys = _i64(keys).reshape(-1)
-        self.m = int(keys.numel())
         dev = keys.device
-        self.sorted_key = torch.empty(self.m, dtype=torch.int32, device=dev)
-        self.perm = torch.empty(self.m, dtype=torch.int32, device=dev)
-        ws = workspace(size("etpgt_scatter_plan_workspace_bytes", self.m), dev)
-        call("etpgt_scatter_plan", ptr(keys), self.m, int(num_rows), ptr(self.sorted_key), ptr(self.perm),
-             ptr(ws), ws.numel(), stream())
+        if negatives is not None:
+            negatives = _i64(negatives)
+            b = int(keys.numel())
+            num_neg = negatives.numel() // max(b, 1)
+            self.m = b * (num_neg + 1)
+        else:
+            self.m = int(keys.numel())
+        if out is None:
+            out = torch.empty(2 * _pad64(self.m), dtype=torch.int32, device=dev)
+        self.sorted_key, self.perm = out[:self.m], out[_pad64(self.m):_pad64(self.m) + self.m]
+        if ws is None:
+            ws = workspace(size("etpgt_scatter_plan_workspace_bytes", self.m), dev)
+        if negatives is not None:
+            call("etpgt_scatter_plan_loss", ptr(keys), ptr(negatives), b, num_neg, int(num_rows),
+                 ptr(self.sorted_key), ptr(self.perm), ptr(ws), ws.numel(), stream())
+        else:
+            call("etpgt_scatter_plan", ptr(keys), self.m, int(num_rows), ptr(self.sorted_key), ptr(self.perm),
+                 ptr(ws), ws.numel(), stream())
 
 
 # Plans are found again by the identity of the key tensors' memory: (data_ptr, numel) of the tensors the plan
@@ -148,20 +176,13 @@ def _find_plan(*tensors):
 
 
 class PreparedBatch:
-    """What `prepare_batch` built: the graph index and the two scatter plans (for `record_stream`
-    bookkeeping when preparation runs on a side stream)."""
+    """What `prepare_batch` built: the graph index and the two scatter plans, all carved from ONE int32 buffer
+    (`tensors()` lists what a caller must `record_stream` when preparation runs on a side stream)."""
 
-    __slots__ = ("index", "plan_nodes", "plan_loss", "loss_keys")
+    __slots__ = ("index", "plan_nodes", "plan_loss", "buffer", "scratch")
 
     def tensors(self):
-        out = [self.index.rowptr, self.index.col, self.index.eperm, self.index.colptr, self.index.row,
-               self.index.cpos]
-        for plan in (self.plan_nodes, self.plan_loss):
-            if plan is not None:
-                out += [plan.sorted_key, plan.perm]
-        if self.loss_keys is not None:
-            out.append(self.loss_keys)
-        return out
+        return [self.buffer, self.scratch]
 
 
 def prepare_batch(batch, num_items: int | None = None) -> PreparedBatch:
@@ -169,20 +190,36 @@ def prepare_batch(batch, num_items: int | None = None) -> PreparedBatch:
     the table size is given, the scatter plans of `batch.x` and of `batch.target_item | batch.negative_items`.
     Everything here depends on the batch's inputs only, so a loader (or a side stream one step ahead) runs
     it off the training step's critical path; the model and the loss find the results again through the
-    batch object / the key tensors.  Without this call the step builds the same things inline."""
+    batch object / the key tensors.  Without this call the step builds the same things inline.
+    Host cost: two allocations and three library calls."""
     prepared = PreparedBatch()
-    prepared.index = graph_index_of(batch, batch.edge_index, batch.x.numel())
-    prepared.plan_nodes = prepared.plan_loss = prepared.loss_keys = None
+    edge_index, ids = batch.edge_index, batch.x
+    _require_cuda(ids, "batch.x")
+    n, e = int(ids.numel()), int(edge_index.size(1))
+    targets = getattr(batch, "target_item", None) if num_items is not None else None
+    negatives = getattr(batch, "negative_items", None) if num_items is not None else None
+    plan_loss = targets is not None and negatives is not None and targets.numel() > 0
+    m_loss = int(targets.numel() + negatives.numel()) if plan_loss else 0
+    elems_index = GraphIndex.out_elems(n, e)
+    elems_nodes = 2 * _pad64(n) if num_items is not None else 0
+    dev = ids.device
+    prepared.buffer = torch.empty(elems_index + elems_nodes + 2 * _pad64(m_loss), dtype=torch.int32, device=dev)
+    nbytes = size("etpgt_csr_workspace_bytes", e, n)
     if num_items is not None:
-        prepared.plan_nodes = ScatterPlan(batch.x, num_items)
-        _register_plan(prepared.plan_nodes, batch.x)
-        targets = getattr(batch, "target_item", None)
-        negatives = getattr(batch, "negative_items", None)
-        if targets is not None and negatives is not None and targets.numel() > 0:
-            b = targets.numel()
-            # keys [b][0] = target, [b][1 + c] = negative c (the layout etpgt_sampled_loss_bwd scatters in)
-            prepared.loss_keys = torch.cat([_i64(targets).reshape(b, 1), _i64(negatives).reshape(b, -1)], dim=1)
-            prepared.plan_loss = ScatterPlan(prepared.loss_keys, num_items)
+        nbytes = max(nbytes, size("etpgt_scatter_plan_workspace_bytes", max(n, m_loss)))
+    prepared.scratch = workspace(nbytes, dev)          # the three calls run back to back on one stream
+    prepared.index = GraphIndex(edge_index, n, out=prepared.buffer, ws=prepared.scratch)
+    try:
+        object.__setattr__(batch, "_etpgt_index", (edge_index, prepared.index))
+    except Exception:
+        pass
+    prepared.plan_nodes = prepared.plan_loss = None
+    if num_items is not None:
+        prepared.plan_nodes = ScatterPlan(ids, num_items, out=prepared.buffer[elems_index:], ws=prepared.scratch)
+        _register_plan(prepared.plan_nodes, ids)
+        if plan_loss:
+            prepared.plan_loss = ScatterPlan(targets, num_items, negatives=negatives,
+                                             out=prepared.buffer[elems_index + elems_nodes:], ws=prepared.scratch)
             _register_plan(prepared.plan_loss, targets, negatives)
     try:
         object.__setattr__(batch, "_etpgt_prepared", prepared)   # keeps the plans alive with the batch

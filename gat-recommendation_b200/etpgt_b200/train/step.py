@@ -74,6 +74,7 @@ class FusedTrainStep:
         self.model, self.loss, self.alpha, self.temperature = model, loss, float(alpha), float(temperature)
         self.session_embeddings = None      # [B, dim] of the last call (detached)
         self._flat = None
+        self._arena, self._arena_stream = None, None
         self._views: list[tuple[torch.nn.Parameter, torch.Tensor]] = []
         self._flat_key = None
         self._desc = _GtStep()
@@ -254,8 +255,16 @@ class FusedTrainStep:
         if arena_bytes == 0:
             msg = _lib.last_error()
             raise (ValueError if msg.startswith(("Unknown", "Expected")) else RuntimeError)(msg)
-        arena = torch.empty(arena_bytes, dtype=torch.uint8, device=dev)
-        d.arena, d.arena_bytes = arena.data_ptr(), arena_bytes
+        # the arena persists across steps (grown with head-room when a larger batch arrives): batches differ in
+        # size, and a fresh GB-sized allocation per step would keep the caching allocator splitting and
+        # re-growing its blocks.  It belongs to the stream that used it last.
+        raw_stream = stream().value
+        if self._arena is None or self._arena.numel() < arena_bytes or self._arena_stream != raw_stream \
+                or self._arena.device != dev:
+            self._arena = None
+            self._arena = torch.empty(arena_bytes + arena_bytes // 8, dtype=torch.uint8, device=dev)
+            self._arena_stream = raw_stream
+        d.arena, d.arena_bytes = self._arena.data_ptr(), self._arena.numel()
 
         phases = 2 * layers + 1
         if not distributed:

@@ -403,6 +403,10 @@ int etpgt_cooc_graph_build(const int64_t* sess_ptr, const int64_t* sess_items, c
 size_t etpgt_scatter_plan_workspace_bytes(int64_t m);
 int etpgt_scatter_plan(const int64_t* keys, int64_t m, int64_t num_rows, int32_t* sorted_key, int32_t* perm,
                        void* ws, size_t ws_bytes, etpgt_stream_t stream);
+/* the plan of the loss scatter straight from targets [B] and negatives [B, num_neg] (m = B * (1 + num_neg)) */
+int etpgt_scatter_plan_loss(const int64_t* targets, const int64_t* negatives, int64_t batch, int num_neg,
+                            int64_t num_rows, int32_t* sorted_key, int32_t* perm, void* ws, size_t ws_bytes,
+                            etpgt_stream_t stream);
 int etpgt_scatter_rows_planned(const int32_t* sorted_key, const int32_t* perm, const float* coef,
                                const float* src, int64_t m, int src_div, int dim, int64_t skip_key,
                                float* d_table, etpgt_stream_t stream);

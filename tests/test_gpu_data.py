@@ -240,10 +240,14 @@ def test_scatter_plans_give_bit_identical_table_gradients():
                 prepared = ops.prepare_batch(batch, d.num_items)
             torch.cuda.current_stream().wait_stream(side)
             assert prepared.plan_nodes.m == batch.x.numel() and prepared.plan_loss.m == len(ids) * 6
-            key = prepared.plan_loss.sorted_key.cpu().numpy()
-            assert np.array_equal(key, np.sort(prepared.loss_keys.cpu().numpy().reshape(-1), kind="stable"))
+            # loss keys: [b][0] = target, [b][1 + c] = negative c
+            loss_keys = torch.cat([batch.target_item.view(-1, 1), batch.negative_items.view(len(ids), -1)], 1)
+            loss_keys = loss_keys.cpu().numpy().reshape(-1)
+            assert np.array_equal(prepared.plan_loss.sorted_key.cpu().numpy(), np.sort(loss_keys, kind="stable"))
             perm = prepared.plan_loss.perm.cpu().numpy()    # stable: equal keys keep ascending position
-            assert np.array_equal(perm, np.argsort(prepared.loss_keys.cpu().numpy().reshape(-1), kind="stable"))
+            assert np.array_equal(perm, np.argsort(loss_keys, kind="stable"))
+            node_keys = batch.x.cpu().numpy()
+            assert np.array_equal(prepared.plan_nodes.perm.cpu().numpy(), np.argsort(node_keys, kind="stable"))
         model.zero_grad()
         for bn in model.batch_norms:
             bn.reset_running_stats()

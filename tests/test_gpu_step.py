@@ -200,3 +200,71 @@ def test_driver_rejects_what_it_does_not_cover():
     d, model, make_batch = _setup(dim=64)
     with pytest.raises(ValueError, match="Unknown loss type"):
         FusedTrainStep(model, "hinge")
+
+
+def test_trainer_mirrors_the_reference_loop(tmp_path):
+    """etpgt_b200.train.trainer.Trainer (the reference's Trainer API, trainer.py:17-251): the driver-backed
+    epoch equals the per-operator epoch bit for bit; evaluate() equals the oracle's Recall / NDCG on the same
+    predictions; checkpoints, history and early stopping behave as in the reference."""
+    import json
+
+    from etpgt_b200 import data, optim, synth
+    from etpgt_b200.model import create_graph_transformer_optimized
+    from etpgt_b200.train.losses import create_loss_function
+    from etpgt_b200.train.trainer import Trainer
+    from oracle import model_ref
+
+    d = synth.generate(num_sessions=800, graph_sessions=600, num_items=500, clusters=20, seed=3)
+    graph = data.ItemGraph(d.item_i, d.item_j, d.num_items)
+    store = data.SessionStore(d.sess_ptr, d.sess_items)
+
+    def loader(first, count, size=64):
+        out = []
+        for i in range(count):
+            ids = np.arange(first + i * size, first + (i + 1) * size)
+            batch = data.build_batch(graph, store, ids)
+            batch.negative_items = data.sample_negatives(store, ids, d.num_items, 5, seed=1, step=i).reshape(-1)
+            out.append(batch)
+        return out
+
+    def run(use_driver, out_dir, loss_type):
+        torch.manual_seed(0)
+        model = create_graph_transformer_optimized(d.num_items, 64, 64, dropout=0.1, laplacian_k=8).cuda()
+        model.laplacian_pe._cached_pe = torch.randn(d.num_items, 8, device="cuda").abs()
+        opt = optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-5)
+        loss_fn = None if loss_type is None else create_loss_function(loss_type)
+        trainer = Trainer(model, loader(0, 4), loader(600, 2), opt, output_dir=out_dir, max_epochs=3, patience=1,
+                          k_values=[10, 20], loss_fn=loss_fn)
+        assert (trainer._driver is not None)
+        if not use_driver:
+            trainer._driver = None
+        torch.manual_seed(9)
+        history = trainer.train()
+        return trainer, history
+
+    for loss_type in (None, "dual"):
+        a, hist_a = run(True, tmp_path / f"a_{loss_type}", loss_type)
+        b, hist_b = run(False, tmp_path / f"b_{loss_type}", loss_type)
+        assert hist_a == hist_b and len(hist_a["train_loss"]) >= 1
+        for (k, v), (_, w) in zip(a.model.state_dict().items(), b.model.state_dict().items()):
+            assert torch.equal(v, w), k
+    # evaluate(): device-side counters == the oracle's metrics on the gathered predictions
+    metrics = a.evaluate()
+    preds, targets = [], []
+    a.model.eval()
+    with torch.no_grad():
+        for batch in a.val_loader:
+            preds.append(a.model.predict(a.model(batch), k=20).cpu())
+            targets.append(batch.target_item.cpu())
+    preds, targets = torch.cat(preds), torch.cat(targets)
+    for k in (10, 20):
+        assert metrics[f"recall@{k}"] == pytest.approx(model_ref.recall_at_k(preds[:, :k], targets, k))
+        assert metrics[f"ndcg@{k}"] == pytest.approx(model_ref.ndcg_at_k(preds[:, :k], targets, k))
+    # artefacts of the reference loop
+    out = tmp_path / "a_dual"
+    assert (out / "checkpoint_latest.pt").exists() and (out / "history.json").exists()
+    saved = json.loads((out / "history.json").read_text())
+    assert saved == hist_a and set(saved) == {"train_loss", "val_metrics"}
+    ckpt = torch.load(out / "checkpoint_latest.pt", weights_only=False)
+    assert set(ckpt) == {"epoch", "model_state_dict", "optimizer_state_dict", "best_val_metric", "history"}
+    assert a.patience_counter <= a.patience and len(hist_a["val_metrics"]) == len(hist_a["train_loss"])

@@ -22,6 +22,7 @@ sys.path.insert(0, str(ROOT / "gat-recommendation_b200"))
 
 from etpgt_b200 import data, ops, optim, parallel, synth  # noqa: E402
 from etpgt_b200.model import create_graph_transformer_optimized  # noqa: E402
+from etpgt_b200.train.step import FusedTrainStep  # noqa: E402
 
 
 def main():
@@ -45,8 +46,12 @@ def main():
         return model, optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-5)
 
     def train(model, opt, dp):
+        """The data-parallel replica trains through the C++ step driver (phase by phase, BatchNorm sums
+        all-reduced in between, flat gradient all-reduce); the single-process reference through the
+        per-operator autograd path."""
         model.train()
         first_grads = None
+        fused = FusedTrainStep(model, "bpr") if dp else None
         for step in range(steps):
             ids = np.arange(step * global_batch, (step + 1) * global_batch)
             if dp:
@@ -55,12 +60,16 @@ def main():
                 ids = ids[cuts[rank]:cuts[rank + 1]]
             batch = data.build_batch(graph, store, ids, 50, False, False)
             neg = data.sample_negatives(store, ids, d.num_items, 5, seed=3, step=step)
-            loss = ops.sampled_loss(model(batch), model.item_embedding, batch.target_item, neg, "bpr",
-                                    total_sessions=global_batch)[0]
             opt.zero_grad()
-            loss.backward()
             if dp:
-                parallel.allreduce_gradients(list(model.parameters()))
+                batch.negative_items = neg
+                ops.prepare_batch(batch, d.num_items)
+                loss = fused(batch, batch.target_item, neg, total_sessions=global_batch)[0]
+                fused.allreduce_gradients()
+            else:
+                loss = ops.sampled_loss(model(batch), model.item_embedding, batch.target_item, neg, "bpr",
+                                        total_sessions=global_batch)[0]
+                loss.backward()
             if step == 0:
                 first_grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
             opt.step()

@@ -36,6 +36,17 @@ def step(b):
     opt.step()
 
 
+from etpgt_b200.train.step import FusedTrainStep  # noqa: E402
+
+fused = FusedTrainStep(model, "bpr")
+
+
+def step_driver(b):
+    opt.zero_grad()
+    fused(b, total_sessions=B)
+    opt.step()
+
+
 def run(name, fn, steps=20, reset=None):
     for rep in range(3):
         if reset:
@@ -58,6 +69,7 @@ run("a cached index, inline sorts", lambda i: step(db[i % 4]))
 run("b prepare inline (compute stream)", lambda i: (lambda bt: (ops.prepare_batch(bt, bench.NUM_ITEMS), step(bt)))(db[i % 4].fresh()))
 run("b' index inline, no plans", lambda i: step(db[i % 4].fresh()))
 
+run("d driver, cached index, inline sorts", lambda i: step_driver(db[i % 4]))
 state = {"p": None, "ev": []}
 
 
@@ -80,7 +92,7 @@ def piped(k, record=True):
             npr = ops.prepare_batch(nb, bench.NUM_ITEMS)
             nev = torch.cuda.Event(); nev.record(side)
         state["p"] = (nb, npr, nev)
-        step(bt)
+        (step_driver if DRIVER else step)(bt)
         if k:
             e = torch.cuda.Event(); e.record(); state["ev"].append(e)
             if len(state["ev"]) > k:
@@ -92,15 +104,20 @@ def reset():
     state["p"], state["ev"] = None, []
 
 
-for k in (1, 2, 0):
+DRIVER = False
+for k in (1, 2):
     run(f"c side stream, host <= {k} ahead", piped(k), reset=reset)
+DRIVER = True
+for k in (1, 2):
+    run(f"e driver + side stream, host <= {k} ahead", piped(k), reset=reset)
 run("a again", lambda i: step(db[i % 4]))
+run("d again", lambda i: step_driver(db[i % 4]))
 
 if len(sys.argv) > 2:
     import cProfile
     import pstats
     reset()
-    fn = piped(2)
+    fn = lambda i: step_driver(db[i % 4])
     for i in range(6):
         fn(i)
     torch.cuda.synchronize()
