@@ -476,8 +476,8 @@ def run_b200(args, rank, world_size, local_rank):
             out["baseline_models"] = baseline_models(dev_batches, device)
         out["edges_per_s_tconv_fwd_bwd"] = out["roofline"].pop("edges_per_s")
         if world_size == 1 and not args.skip_cpu_baseline:
-            steps = 2
-            v, sec = oracle_training_steps(data, edge_keys, args.cpu_batch, steps, 1)
+            steps = 60      # about 10-20 s of host work: 1,024-session steps take 0.1-0.3 s on 8-32 cores
+            v, sec = oracle_training_steps(data, edge_keys, args.cpu_batch, steps, 2)
             out["cpu_baseline"] = {"value": v, "unit": "sessions/s", "cores": os.cpu_count() or 1, "kind": "port",
                                    "sample": f"{steps} steps of {args.cpu_batch} sessions (oracle port, fp32 CPU)"}
         print(json.dumps(out))

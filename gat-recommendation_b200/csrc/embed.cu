@@ -5,6 +5,8 @@
 // Gather-bound: per node one table row (DIM*4 B, 128-bit loads, a lane group per row), one PE
 // row (k_pe*4 B, broadcast) and one output row.  w_pe^T (k_pe x DIM) and b_pe are staged once
 // per CTA in shared memory so the projection costs no global traffic.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace etpgt {
@@ -17,7 +19,8 @@ template <int DIM>
 __global__ void __launch_bounds__(kThreads)
 embed_pe_fwd_kernel(const int64_t* __restrict__ ids, int64_t n, const float* __restrict__ table,
                     const float* __restrict__ pe, int pe_per_node, const float* __restrict__ w_pe,
-                    const float* __restrict__ b_pe, int k_pe, float* __restrict__ out) {
+                    const float* __restrict__ b_pe, int k_pe, float* __restrict__ out,
+                    __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
   using G = RowGeom<DIM>;
   extern __shared__ float smem[];  // w^T [k_pe][DIM] then bias [DIM]
   float* wt = smem;
@@ -109,6 +112,22 @@ embed_pe_fwd_kernel(const int64_t* __restrict__ ids, int64_t n, const float* __r
         float* orow = out + node[u] * DIM;
 #pragma unroll
         for (int v = 0; v < G::V; ++v) st4(orow + 4 * (v * G::LPN + lig), acc[u][v]);
+        if (out_hi != nullptr) {   // the first layer's projection operand, split for the tensor cores (x = hi + lo)
+#pragma unroll
+          for (int v = 0; v < G::V; ++v) {
+            const float4 o = acc[u][v];
+            const __nv_bfloat162 h0 = __floats2bfloat162_rn(o.x, o.y), h1 = __floats2bfloat162_rn(o.z, o.w);
+            const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+            const __nv_bfloat162 l0 = __floats2bfloat162_rn(o.x - f0.x, o.y - f0.y),
+                                 l1 = __floats2bfloat162_rn(o.z - f1.x, o.w - f1.y);
+            uint2 ph, pl;
+            ph.x = *reinterpret_cast<const uint32_t*>(&h0); ph.y = *reinterpret_cast<const uint32_t*>(&h1);
+            pl.x = *reinterpret_cast<const uint32_t*>(&l0); pl.y = *reinterpret_cast<const uint32_t*>(&l1);
+            const int64_t at = node[u] * DIM + 4 * (v * G::LPN + lig);
+            *reinterpret_cast<uint2*>(out_hi + at) = ph;
+            *reinterpret_cast<uint2*>(out_lo + at) = pl;
+          }
+        }
       }
     }
   }
@@ -201,8 +220,17 @@ using namespace etpgt;
 
 extern "C" int etpgt_embed_pe_fwd(const int64_t* ids, int64_t n, const float* table, int64_t num_items,
                                   const float* pe, int pe_per_node, const float* w_pe, const float* b_pe,
-                                  int k_pe, int dim, float* out, etpgt_stream_t stream_) {
+                                  int k_pe, int dim, float* out, etpgt_stream_t stream) {
+  return etpgt_embed_pe_fwd_split(ids, n, table, num_items, pe, pe_per_node, w_pe, b_pe, k_pe, dim, out, nullptr,
+                                  nullptr, stream);
+}
+
+extern "C" int etpgt_embed_pe_fwd_split(const int64_t* ids, int64_t n, const float* table, int64_t num_items,
+                                        const float* pe, int pe_per_node, const float* w_pe, const float* b_pe,
+                                        int k_pe, int dim, float* out, void* out_hi, void* out_lo,
+                                        etpgt_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ETPGT_REQUIRE((out_hi == nullptr) == (out_lo == nullptr), "embed_pe_fwd: out_hi and out_lo come together");
   ETPGT_REQUIRE(supported_dim(dim), "embed_pe_fwd: unsupported dim %d", dim);
   ETPGT_REQUIRE(n >= 0 && num_items > 0, "embed_pe_fwd: bad size");
   ETPGT_REQUIRE(pe == nullptr || (w_pe && b_pe && k_pe >= 1 && k_pe <= kMaxKpe), "embed_pe_fwd: bad PE arguments");
@@ -214,7 +242,8 @@ extern "C" int etpgt_embed_pe_fwd(const int64_t* ids, int64_t n, const float* ta
       cudaFuncSetAttribute(embed_pe_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     const int64_t gpc = (kThreads / 32) * RowGeom<D>::GROUPS;                                       \
     embed_pe_fwd_kernel<D><<<grid_for(n, (int)gpc * 4, 8), kThreads, smem, stream>>>(                \
-        ids, n, table, pe, pe_per_node, w_pe, b_pe, k_pe, out);                                     \
+        ids, n, table, pe, pe_per_node, w_pe, b_pe, k_pe, out, static_cast<__nv_bfloat16*>(out_hi), \
+        static_cast<__nv_bfloat16*>(out_lo));                                                       \
   }
   ETPGT_DISPATCH_DIM(dim, CALL)
 #undef CALL

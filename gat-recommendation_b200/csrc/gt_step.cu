@@ -199,9 +199,7 @@ extern "C" int etpgt_gt_step_run(const etpgt_gt_step_t* sp, int phase_begin, int
     const etpgt_gt_layer_t& P = s.layer[l];
     const LayerBuffers& B = lay.layer[l];
     const float* x = l == 0 ? lay.x0 : lay.layer[l - 1].y;
-    if (l == 0)
-      TRY(etpgt_split_bf16(x, n, dim, dim, B.x_hi, B.x_lo, dim, nullptr, nullptr, (n + 7) / 8 * 8, nullptr,
-                           lay.scratch, 256, stream_));
+    (void)x;   // layer 0: the embedding kernel wrote the split of x0; layer > 0: the previous BatchNorm apply did
     TRY(etpgt_split_bf16(P.weight, width, dim, dim, B.w_hi, B.w_lo, dim, nullptr, nullptr, (width + 7) / 8 * 8,
                          nullptr, lay.scratch, 256, stream_));
     TRY(etpgt_gemm_bf16x3_ex(B.x_hi, B.x_lo, B.w_hi, B.w_lo, n, width, dim, dim, dim, 0, 0, P.bias, 0, B.qkvs, width,
@@ -271,8 +269,8 @@ extern "C" int etpgt_gt_step_run(const etpgt_gt_step_t* sp, int phase_begin, int
 
   for (int p = phase_begin; p < phase_end; ++p) {
     if (p == 0) {
-      TRY(etpgt_embed_pe_fwd(s.ids, n, s.table, s.num_items, s.pe, 0, s.w_pe, s.b_pe, s.pe ? s.k_pe : 0, dim, lay.x0,
-                             stream_));
+      TRY(etpgt_embed_pe_fwd_split(s.ids, n, s.table, s.num_items, s.pe, 0, s.w_pe, s.b_pe, s.pe ? s.k_pe : 0, dim,
+                                   lay.x0, lay.layer[0].x_hi, lay.layer[0].x_lo, stream_));
       if (s.training) {
         static_assert(ETPGT_GT_MAX_LAYERS == 4, "bump_counters_kernel takes four counters");
         int64_t* c[4] = {nullptr, nullptr, nullptr, nullptr};

@@ -32,6 +32,7 @@ _PROTOTYPES = {
     "etpgt_session_subgraphs_fill": (I, [P, P, P, P, P, P, L, I, I, I, P, P, L, P, P, P, P, P, P, Z, P]),
     "etpgt_sample_negatives": (I, [ctypes.c_uint64, ctypes.c_uint32, L, P, P, P, L, I, L, I, P, P]),
     "etpgt_embed_pe_fwd": (I, [P, L, P, L, P, I, P, P, I, I, P, P]),
+    "etpgt_embed_pe_fwd_split": (I, [P, L, P, L, P, I, P, P, I, I, P, P, P, P]),
     "etpgt_embed_pe_bwd_workspace_bytes": (Z, [L, I, I]),
     "etpgt_embed_pe_bwd": (I, [P, L, P, L, P, I, I, I, L, P, P, P, P, Z, P]),
     "etpgt_tconv_fwd": (I, [P, L, I, I, P, P, P, L, P, P, P, P, P, P, P, P]),

@@ -53,9 +53,18 @@ class GraphTransformer(BaseRecommendationModel):
             given = getattr(batch, "laplacian_pe", None)
             pe, per_node = (given, True) if given is not None else (self.laplacian_pe.cached(), False)
             w_pe, b_pe = self.laplacian_pe.projection.weight, self.laplacian_pe.projection.bias
-        x = ops.EmbedPE.apply(ids, self.item_embedding.weight, pe, per_node, w_pe, b_pe,
-                              self.item_embedding.padding_idx)
-        split = None   # bf16 hi/lo split of x, produced by the previous fused layer for this layer's GEMM
+        # bf16 hi/lo split of x for the fused layer's GEMM: written by the embedding kernel for the first layer
+        # and by the previous fused layer's BatchNorm apply after that
+        split = None
+        if ids.numel() > 0 and ops.FUSED_LAYER and ops.fused_conv_supported(
+                self.item_embedding.weight, self.embedding_dim, 4 * self.hidden_dim) and \
+                self.embedding_dim == self.hidden_dim:
+            x, hi, lo = ops.EmbedPE.apply(ids, self.item_embedding.weight, pe, per_node, w_pe, b_pe,
+                                          self.item_embedding.padding_idx, True)
+            split = (hi, lo)
+        else:
+            x = ops.EmbedPE.apply(ids, self.item_embedding.weight, pe, per_node, w_pe, b_pe,
+                                  self.item_embedding.padding_idx)
         for layer, (conv, bn) in enumerate(zip(self.convs, self.batch_norms)):
             if fused_layer_supported(conv, bn, x):
                 drop_p = self.dropout_layer.p if self.training else 0.0

@@ -235,7 +235,9 @@ class EmbedPE(torch.autograd.Function):
     """x0 = table[ids] (+ pe @ w_pe^T + b_pe)   — etpgt/model/graph_transformer.py:140-152."""
 
     @staticmethod
-    def forward(ctx, ids, table, pe, pe_per_node, w_pe, b_pe, padding_idx):
+    def forward(ctx, ids, table, pe, pe_per_node, w_pe, b_pe, padding_idx, want_split=False):
+        """want_split: also return the bf16 hi/lo split of x0 (non-differentiable), the operand format of the
+        first layer's tensor-core projection — (x0, hi, lo) instead of x0."""
         _require_cuda(table, "item_embedding.weight")
         ids = _i64(ids)
         table_c = _f32(table)
@@ -247,16 +249,24 @@ class EmbedPE(torch.autograd.Function):
             k_pe = pe.size(1)
         else:
             w_pe_c = b_pe_c = None
-        call("etpgt_embed_pe_fwd", ptr(ids), n, ptr(table_c), table_c.size(0), ptr(pe), int(bool(pe_per_node)),
-             ptr(w_pe_c), ptr(b_pe_c), k_pe, dim, ptr(out), stream())
+        hi = lo = None
+        if want_split:
+            hi = torch.empty(n, dim, dtype=torch.bfloat16, device=table_c.device)
+            lo = torch.empty(n, dim, dtype=torch.bfloat16, device=table_c.device)
+        call("etpgt_embed_pe_fwd_split", ptr(ids), n, ptr(table_c), table_c.size(0), ptr(pe), int(bool(pe_per_node)),
+             ptr(w_pe_c), ptr(b_pe_c), k_pe, dim, ptr(out), ptr(hi), ptr(lo), stream())
         ctx.save_for_backward(ids, pe)
         ctx.table_ref = table
         ctx.plan = _find_plan(ids)          # per-batch sort of the node ids, if prepare_batch made one
         ctx.meta = (table_c.size(0), dim, k_pe, int(bool(pe_per_node)), -1 if padding_idx is None else int(padding_idx))
+        if want_split:
+            ctx.set_materialize_grads(False)
+            ctx.mark_non_differentiable(hi, lo)
+            return out, hi, lo
         return out
 
     @staticmethod
-    def backward(ctx, d_out):
+    def backward(ctx, d_out, *_unused):
         ids, pe = ctx.saved_tensors
         num_items, dim, k_pe, per_node, padding_idx = ctx.meta
         d_out = _f32(d_out)
@@ -275,7 +285,7 @@ class EmbedPE(torch.autograd.Function):
         call("etpgt_embed_pe_bwd_planned", ptr(ids), n, ptr(d_out), num_items, ptr(pe), per_node, k_pe, dim,
              padding_idx, ptr(plan.sorted_key) if plan else None, ptr(plan.perm) if plan else None,
              ptr(d_table), ptr(d_w), ptr(d_b), ptr(ws), ws.numel(), stream())
-        return None, (None if sink is not None else d_table), None, None, d_w, d_b, None
+        return None, (None if sink is not None else d_table), None, None, d_w, d_b, None, None
 
 
 # ------------------------------------------------------------------------------ TransformerConv

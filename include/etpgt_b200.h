@@ -108,6 +108,12 @@ int etpgt_sample_negatives(uint64_t seed, uint32_t step, int64_t session_base,
 int etpgt_embed_pe_fwd(const int64_t* ids, int64_t n, const float* table, int64_t num_items,
                        const float* pe, int pe_per_node, const float* w_pe, const float* b_pe,
                        int k_pe, int dim, float* out, etpgt_stream_t stream);
+/* The same, also writing out split as bf16 pairs out = out_hi + out_lo (hi = bf16(x), lo = bf16(x - hi), exactly
+ * what etpgt_split_bf16 produces): the operand format of the first layer's tensor-core projection, so that
+ * layer needs no split pass.  out_hi / out_lo [n, dim] bf16, both or neither. */
+int etpgt_embed_pe_fwd_split(const int64_t* ids, int64_t n, const float* table, int64_t num_items,
+                             const float* pe, int pe_per_node, const float* w_pe, const float* b_pe,
+                             int k_pe, int dim, float* out, void* out_hi, void* out_lo, etpgt_stream_t stream);
 /* Deterministic backward: d_table (dense [num_items, dim], caller-zeroed, rows are ADDED),
  * d_w_pe [dim,k_pe], d_b_pe [dim] (overwritten; NULL when pe == NULL).  Row padding_idx
  * (etpgt/model/base.py:36; -1 = none) receives no gradient. */
