@@ -11,8 +11,10 @@
 //
 // Data parallelism: BatchNorm needs whole-batch statistics, i.e. an all-reduce of 2*dim+1 doubles between the
 // statistics kernel and the apply kernel of every layer, forward and backward.  The step is therefore cut into
-// 2*layers+1 phases at exactly those points; the caller runs [phase_begin, phase_end) per call and all-reduces
-// the exchanged rows of `bn_sums` in between (one call with all phases on a single GPU).
+// phases at exactly those points; the caller runs [phase_begin, phase_end) per call and all-reduces the exchanged
+// rows of `bn_sums` in between (one call with all phases on a single GPU).  One more cut follows the last table-
+// gradient kernel: phase 2*layers+1 (weight gradient of layer 0, PE projection gradient) touches neither the table
+// gradient nor anything a collective needs, so the table's all-reduce can run underneath it.  2*layers+2 phases.
 #include "common.cuh"
 
 namespace etpgt {
@@ -167,14 +169,14 @@ extern "C" size_t etpgt_gt_step_arena_bytes(const etpgt_gt_step_t* s) {
 
 extern "C" int etpgt_gt_step_num_phases(const etpgt_gt_step_t* s) {
   if (check(s) != ETPGT_OK) return 0;
-  return 2 * s->num_layers + 1;
+  return 2 * s->num_layers + 2;
 }
 
 extern "C" int etpgt_gt_step_run(const etpgt_gt_step_t* sp, int phase_begin, int phase_end, etpgt_stream_t stream_) {
   TRY(check(sp));
   const etpgt_gt_step_t& s = *sp;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const int L = s.num_layers, phases = 2 * L + 1;
+  const int L = s.num_layers, phases = 2 * L + 2;
   ETPGT_REQUIRE(phase_begin >= 0 && phase_end <= phases && phase_begin < phase_end, "gt_step: bad phase range [%d, %d)",
                 phase_begin, phase_end);
   ETPGT_REQUIRE(s.arena != nullptr && s.arena_bytes >= etpgt_gt_step_arena_bytes(sp), "gt_step: arena %zu < %zu",
@@ -259,9 +261,15 @@ extern "C" int etpgt_gt_step_run(const etpgt_gt_step_t* sp, int phase_begin, int
     TRY(etpgt_tconv_bwd_split(B.qkvs, B.d_conv, n, dim, heads, s.rowptr, s.col, s.eperm, s.colptr, s.row, s.cpos, e,
                               P.w_beta, B.alpha_mask, B.agg, B.beta, B.m, B.inv_l, nullptr, B.g_hi, B.g_lo, P.d_bias,
                               P.d_w_beta, lay.scratch, etpgt_tconv_bwd_workspace_bytes(n, e, dim, heads), stream_));
-    // dX = d_res + dQKVS x W (residual branch merged by the GEMM's TMA reduce-add); dW = dQKVS^T x X (split-K)
+    // dX = d_res + dQKVS x W (residual branch merged by the GEMM's TMA reduce-add)
     TRY(etpgt_gemm_bf16x3_ex(B.g_hi, B.g_lo, B.w_hi, B.w_lo, n, dim, width, width, dim, 0, 1, nullptr, 1, B.d_res, dim,
                              1, lay.scratch, etpgt_gemm_bf16x3_workspace_bytes(n, dim, width, 1), stream_));
+    return ETPGT_OK;
+  };
+  // ---- backward: weight gradient of layer l, dW = dQKVS^T x X (split-K over the nodes)
+  auto layer_backward_w = [&](int l) -> int {
+    const etpgt_gt_layer_t& P = s.layer[l];
+    const LayerBuffers& B = lay.layer[l];
     TRY(etpgt_gemm_bf16x3_ex(B.g_hi, B.g_lo, B.x_hi, B.x_lo, width, dim, n, width, dim, 1, 1, nullptr, 0, P.d_weight,
                              dim, 0, lay.scratch, etpgt_gemm_bf16x3_workspace_bytes(width, dim, n, 0), stream_));
     return ETPGT_OK;
@@ -302,17 +310,26 @@ extern "C" int etpgt_gt_step_run(const etpgt_gt_step_t* sp, int phase_begin, int
                               lay.d_last, nullptr, stream_));
         TRY(layer_backward_a(L - 1));
       }
-    } else if (s.backward) {
+    } else if (s.backward && p <= 2 * L) {
       const int l = 2 * L - p;   // p = L+1 .. 2L  ->  l = L-1 .. 0
       TRY(layer_backward_b(l));
       if (l > 0) {
+        TRY(layer_backward_w(l));
         TRY(layer_backward_a(l - 1));
       } else {
-        TRY(etpgt_embed_pe_bwd_planned(s.ids, n, lay.layer[0].d_res, s.num_items, s.pe, 0, s.pe ? s.k_pe : 0, dim,
-                                       s.padding_idx, s.plan_nodes_key, s.plan_nodes_perm, s.d_table, s.d_w_pe,
-                                       s.d_b_pe, lay.scratch,
+        // the table gradient is complete as early as possible: its rows need dX of layer 0 only, so the
+        // scatter runs before that layer's weight gradient and the caller can start the table's all-reduce
+        // while the last phase computes
+        TRY(etpgt_embed_pe_bwd_planned(s.ids, n, lay.layer[0].d_res, s.num_items, nullptr, 0, 0, dim, s.padding_idx,
+                                       s.plan_nodes_key, s.plan_nodes_perm, s.d_table, nullptr, nullptr, lay.scratch,
                                        etpgt_embed_pe_bwd_workspace_bytes(n, dim, s.k_pe > 0 ? s.k_pe : 1), stream_));
       }
+    } else if (s.backward) {   // p == 2L+1: what no collective waits for
+      TRY(layer_backward_w(0));
+      if (s.pe != nullptr)
+        TRY(etpgt_embed_pe_bwd_planned(s.ids, n, lay.layer[0].d_res, s.num_items, s.pe, 0, s.k_pe, dim, s.padding_idx,
+                                       nullptr, nullptr, nullptr, s.d_w_pe, s.d_b_pe, lay.scratch,
+                                       etpgt_embed_pe_bwd_workspace_bytes(n, dim, s.k_pe), stream_));
     }
   }
   return ETPGT_OK;

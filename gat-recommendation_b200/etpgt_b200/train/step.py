@@ -75,6 +75,7 @@ class FusedTrainStep:
         self.session_embeddings = None      # [B, dim] of the last call (detached)
         self._flat = None
         self._arena, self._arena_stream = None, None
+        self._table_work = None
         self._views: list[tuple[torch.nn.Parameter, torch.Tensor]] = []
         self._flat_key = None
         self._desc = _GtStep()
@@ -266,7 +267,8 @@ class FusedTrainStep:
             self._arena_stream = raw_stream
         d.arena, d.arena_bytes = self._arena.data_ptr(), self._arena.numel()
 
-        phases = 2 * layers + 1
+        phases = 2 * layers + 2
+        self._table_work = None
         if not distributed:
             _lib.call("etpgt_gt_step_run", ctypes.byref(d), 0, phases, stream())
         else:
@@ -274,11 +276,15 @@ class FusedTrainStep:
             last = phases if backward else layers + 1
             for phase in range(last):
                 _lib.call("etpgt_gt_step_run", ctypes.byref(d), phase, phase + 1, stream())
-                if phase < last - 1:
+                if phase < min(last - 1, 2 * layers):
                     # phase p < layers produced the forward sums of layer p; phase layers + j the backward sums
                     # of layer layers - 1 - j
                     row = phase if phase < layers else layers + (2 * layers - 1 - phase)
                     dist.all_reduce(bn_sums[row], group=group)
+                elif phase == 2 * layers:
+                    # the table gradient is complete: its all-reduce (the step's largest message) runs on NCCL's
+                    # stream underneath the last phase; allreduce_gradients() joins it
+                    self._table_work = dist.all_reduce(sink, group=group, async_op=True)
         if backward:
             for p, view in self._views:
                 p.grad = view
@@ -292,4 +298,8 @@ class FusedTrainStep:
         if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
             return
         dist.all_reduce(self._flat, group=group)
-        dist.all_reduce(self.model.item_embedding.weight.grad, group=group)
+        if self._table_work is not None:      # started by __call__ underneath the last phase
+            self._table_work.wait()
+            self._table_work = None
+        else:
+            dist.all_reduce(self.model.item_embedding.weight.grad, group=group)

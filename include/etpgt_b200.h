@@ -443,12 +443,13 @@ int etpgt_sampled_loss_bwd_planned(const float* sess, const float* table, const 
  * Philox4x32-10 as in etpgt_dropout_mask / etpgt_bn_apply_ex; ignored when training == 0.
  * plan_* (optional): etpgt_scatter_plan of `ids` and of the [target | negatives] keys.
  *
- * Phases (data parallelism): the step is cut at the BatchNorm statistics exchanges into 2*layers+1 phases;
- * run [phase_begin, phase_end) per call.  bn_sums is [2*layers][2*dim+1] doubles: row l = forward sums of
- * layer l (complete after phase l), row layers+l = backward sums of layer l (complete after phase
- * 2*layers-1-l ... i.e. just before the phase that consumes them).  With distributed != 0 the caller
- * all-reduces the row a phase produced before running the next phase (the row's last element carries the
- * row count); with distributed == 0 run all phases in one call. */
+ * Phases (data parallelism): the step is cut at the BatchNorm statistics exchanges, and once more after the last
+ * kernel that adds to d_table, into 2*layers+2 phases; run [phase_begin, phase_end) per call.  bn_sums is
+ * [2*layers][2*dim+1] doubles: row l = forward sums of layer l (produced by phase l), row layers+l = backward
+ * sums of layer l (produced by phase 2*layers-1-l).  With distributed != 0 the caller all-reduces the row a
+ * phase produced before running the next phase (the row's last element carries the row count); d_table is
+ * complete after phase 2*layers, so its all-reduce can overlap phase 2*layers+1 (weight gradient of layer 0 and
+ * the PE projection gradient).  With distributed == 0 run all phases in one call. */
 #define ETPGT_GT_MAX_LAYERS 4
 typedef struct etpgt_gt_layer {
   const float* weight;       /* [4*dim, dim] */

@@ -90,7 +90,7 @@ def _driver_step(model, batch, loss_kind, seed, phase_by_phase=False):
             losses = step(batch)
         finally:
             step_mod._lib.call = saved
-        assert calls == list(range(2 * len(model.convs) + 1))
+        assert calls == list(range(2 * len(model.convs) + 2))
     else:
         losses = step(batch)
     return losses.clone(), step.session_embeddings.clone(), _snapshot(model)
