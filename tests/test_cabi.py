@@ -112,3 +112,37 @@ def test_golden_state_dicts_load_strictly():
         missing, unexpected = model.load_state_dict(state, strict=False)
         assert not unexpected, unexpected
         assert not missing, missing
+
+
+def test_step_descriptor_layout_matches_the_header(tmp_path):
+    """etpgt_gt_step_t / etpgt_gt_layer_t are passed by address from ctypes: every field of the ctypes mirror
+    (etpgt_b200/train/step.py) must sit at the offset the C compiler gives it in include/etpgt_b200.h."""
+    import subprocess
+
+    from etpgt_b200.train import step
+
+    def fields(struct):
+        return [name for name, _ in struct._fields_]
+
+    lines = ['#include <stddef.h>', '#include <stdio.h>', f'#include "{HEADER}"', "int main(void) {"]
+    for cname, struct in (("etpgt_gt_layer_t", step._GtLayer), ("etpgt_gt_step_t", step._GtStep)):
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for f in fields(struct):
+            lines.append(f'  printf("{cname}.{f} %zu\\n", offsetof({cname}, {f}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c11", str(src), "-o", str(exe)], check=True)
+    got = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True,
+                                                       text=True).stdout.splitlines())
+    for cname, struct in (("etpgt_gt_layer_t", step._GtLayer), ("etpgt_gt_step_t", step._GtStep)):
+        assert int(got[cname]) == ctypes.sizeof(struct)
+        for f in fields(struct):
+            assert int(got[f"{cname}.{f}"]) == getattr(struct, f).offset, f"{cname}.{f}"
+    # and the header declares no field the mirror lacks
+    text = re.sub(r"/\*.*?\*/", "", HEADER.read_text(), flags=re.S)
+    body = text[text.index("typedef struct etpgt_gt_step {"):text.index("} etpgt_gt_step_t;")]
+    declared = set(re.findall(r"[\s\*,](\w+)\s*(?:\[\w+\])?\s*[;,]", body))
+    assert declared == set(fields(step._GtStep)), declared ^ set(fields(step._GtStep))
+    assert step.MAX_LAYERS == int(re.search(r"#define ETPGT_GT_MAX_LAYERS (\d+)", text).group(1))
