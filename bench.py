@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument("--cpu-batch", type=int, default=1024, help="sessions per step of the CPU sample")
     ap.add_argument("--rotate", type=int, default=4, help="distinct batches rotated through the timed steps")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--step-only", action="store_true",
+                    help="only the training-step measurements (for profiler runs): no sweep, rooflines or baselines")
     ap.add_argument("--sweep-batches", type=str, default="16384,65536",
                     help="extra device-resident measurements at these batch sizes (rank 0, 1 GPU; '' = off)")
     return ap.parse_args()
@@ -446,6 +448,12 @@ def run_b200(args, rank, world_size, local_rank):
         "final_loss": losses[-1] if losses else None,
         "batch_shape": {"nodes": host_batches[0].nodes, "edges": host_batches[0].edges},
     }
+    if args.step_only:
+        if rank == 0:
+            print(json.dumps(out))
+        if distributed:
+            dist.destroy_process_group()
+        return
     if rank == 0 and world_size == 1 and args.sweep_batches:
         # The step costs the host about 1.9 ms (some 60 launches driven through Python / autograd), so small
         # batches are host-launch-bound and noisy; the sweep shows the same step on either side of the
@@ -458,7 +466,7 @@ def run_b200(args, rank, world_size, local_rank):
             total_sessions = sweep
             big_source = resident(big)
             pending["batch"] = None
-            for i in range(3):
+            for i in range(5):
                 value_step(i, big_source)
             pending["batch"] = None
             sweep_steps = max(args.steps // 2, 4)

@@ -25,12 +25,15 @@ int stat_parts(int64_t n) {
 // blockDim = (dim/4 lanes-x, rows-y): thread (tx, ty) strides over rows ty, ty+RY, ... of the
 // CTA's chunk and owns columns 4*tx..4*tx+3.  MODE 0: sum x, sum x^2.  MODE 1 (backward):
 // sum g, sum g*xhat with g = d_y * (relu ? y > 0 : 1).
-template <int MODE>
-__global__ void bn_partial_kernel(const float* __restrict__ x, const float* __restrict__ y,
-                                  const float* __restrict__ d_y, int64_t n, int dim,
-                                  const float* __restrict__ mean, const float* __restrict__ invstd, int relu,
-                                  uint32_t drop_threshold, float keep_scale, uint64_t drop_seed,
-                                  int64_t chunk, double* __restrict__ partial /* [grid][2][dim] */) {
+// RELU is a template parameter so that the plain-BatchNorm instance carries no registers for the y rows
+// (three resident CTAs per SM instead of two).
+template <int MODE, bool RELU>
+__global__ void __launch_bounds__(256, RELU ? 2 : 3)
+bn_partial_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                  const float* __restrict__ d_y, int64_t n, int dim,
+                  const float* __restrict__ mean, const float* __restrict__ invstd,
+                  uint32_t drop_threshold, float keep_scale, uint64_t drop_seed,
+                  int64_t chunk, double* __restrict__ partial /* [grid][2][dim] */) {
   extern __shared__ double sm[];  // [blockDim.y][2][dim]
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int64_t begin = blockIdx.x * chunk;
@@ -39,7 +42,7 @@ __global__ void bn_partial_kernel(const float* __restrict__ x, const float* __re
   float4 mu = zero4(), is = zero4();
   if (MODE == 1) { mu = ld4(mean + 4 * tx); is = ld4(invstd + 4 * tx); }
   for (int64_t r0 = begin + ty; r0 < end; r0 += (int64_t)kRowUnroll * blockDim.y) {
-    float4 a[kRowUnroll], g[kRowUnroll], o[kRowUnroll];
+    float4 a[kRowUnroll], g[kRowUnroll], o[RELU ? kRowUnroll : 1];
     bool on[kRowUnroll];
 #pragma unroll
     for (int u = 0; u < kRowUnroll; ++u) {   // all loads of the unrolled rows are issued before any use
@@ -49,7 +52,7 @@ __global__ void bn_partial_kernel(const float* __restrict__ x, const float* __re
       a[u] = ldg4(x + rr * dim + 4 * tx);
       if (MODE == 1) {
         g[u] = ldg4(d_y + rr * dim + 4 * tx);
-        if (relu) o[u] = ldg4(y + rr * dim + 4 * tx);
+        if (RELU) o[u] = ldg4(y + rr * dim + 4 * tx);
       }
     }
 #pragma unroll
@@ -66,7 +69,7 @@ __global__ void bn_partial_kernel(const float* __restrict__ x, const float* __re
           const int64_t r = r0 + (int64_t)u * blockDim.y;
           gv = mul4(gv, dropout_factors4(drop_seed, (uint64_t)(r * (dim / 4) + tx), drop_threshold, keep_scale));
         }
-        if (relu) {
+        if (RELU) {
           gv.x = o[u].x > 0.f ? gv.x : 0.f; gv.y = o[u].y > 0.f ? gv.y : 0.f;
           gv.z = o[u].z > 0.f ? gv.z : 0.f; gv.w = o[u].w > 0.f ? gv.w : 0.f;
         }
@@ -160,40 +163,70 @@ bn_apply_kernel(const float* __restrict__ x, int64_t total4, int dim4, const flo
 
 // d_x = gamma*invstd*(g - sum_g/count - xhat*sum_gxhat/count)   (training)
 //     = gamma*invstd*g                                         (eval)
-__global__ void __launch_bounds__(256)
+// FIXED_COLS: the grid stride is a multiple of the row length, so a thread keeps the same four columns for its
+// whole loop and the per-column coefficients (incl. the double -> float conversions of the sums) are formed once,
+// in registers; UNROLL independent elements are loaded before any is used.
+template <bool FIXED_COLS, bool RELU, int UNROLL>
+__global__ void __launch_bounds__(256, 3)
 bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ d_y,
                     int64_t total4, int dim, const float* __restrict__ mean, const float* __restrict__ invstd,
-                    const float* __restrict__ gamma, int relu, int training, const double* __restrict__ sums,
+                    const float* __restrict__ gamma, int training, const double* __restrict__ sums,
                     double count, uint32_t drop_threshold, float keep_scale, uint64_t drop_seed,
                     float* __restrict__ d_x, float* __restrict__ d_res) {
   const int dim4 = dim / 4;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % dim4) * 4;
-    float4 g = ldg4(d_y + 4 * i);
-    if (drop_threshold != 0) g = mul4(g, dropout_factors4(drop_seed, (uint64_t)i, drop_threshold, keep_scale));
-    if (relu) {
-      const float4 o = ldg4(y + 4 * i);
-      g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f; g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
-    }
-    if (d_res != nullptr) st4(d_res + 4 * i, g);   // gradient of the residual branch (same mask, same ReLU gate)
-    const float4 is = ld4(invstd + c), ga = ld4(gamma + c);
-    float4 r;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t first = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  float4 is, gi, mu, gs, gx;   // invstd, gamma * invstd, mean, sum_g / count, sum_gxhat / count of this thread's columns
+  auto coefficients = [&](int c) {
+    is = ld4(invstd + c);
+    const float4 ga = ld4(gamma + c);
+    gi = make_float4(ga.x * is.x, ga.y * is.y, ga.z * is.z, ga.w * is.w);
+    mu = gs = gx = zero4();
     if (training) {
-      const float4 a = ldg4(x + 4 * i);
-      const float4 mu = ld4(mean + c);
+      mu = ld4(mean + c);
       const float inv_n = (float)(1.0 / (count > 0 ? count : sums[2 * dim]));
-      const float gs[4] = {(float)sums[c] * inv_n, (float)sums[c + 1] * inv_n, (float)sums[c + 2] * inv_n,
-                           (float)sums[c + 3] * inv_n};
-      const float gx[4] = {(float)sums[dim + c] * inv_n, (float)sums[dim + c + 1] * inv_n,
-                           (float)sums[dim + c + 2] * inv_n, (float)sums[dim + c + 3] * inv_n};
-      r.x = ga.x * is.x * (g.x - gs[0] - (a.x - mu.x) * is.x * gx[0]);
-      r.y = ga.y * is.y * (g.y - gs[1] - (a.y - mu.y) * is.y * gx[1]);
-      r.z = ga.z * is.z * (g.z - gs[2] - (a.z - mu.z) * is.z * gx[2]);
-      r.w = ga.w * is.w * (g.w - gs[3] - (a.w - mu.w) * is.w * gx[3]);
-    } else {
-      r.x = ga.x * is.x * g.x; r.y = ga.y * is.y * g.y; r.z = ga.z * is.z * g.z; r.w = ga.w * is.w * g.w;
+      gs = make_float4((float)sums[c] * inv_n, (float)sums[c + 1] * inv_n, (float)sums[c + 2] * inv_n,
+                       (float)sums[c + 3] * inv_n);
+      gx = make_float4((float)sums[dim + c] * inv_n, (float)sums[dim + c + 1] * inv_n,
+                       (float)sums[dim + c + 2] * inv_n, (float)sums[dim + c + 3] * inv_n);
     }
-    st4(d_x + 4 * i, r);
+  };
+  if (FIXED_COLS) coefficients((int)(first % dim4) * 4);
+  for (int64_t i0 = first; i0 < total4; i0 += UNROLL * stride) {
+    float4 g[UNROLL], a[UNROLL], o[RELU ? UNROLL : 1];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < total4) {
+        g[u] = ldg4(d_y + 4 * i);
+        if (training) a[u] = ldg4(x + 4 * i);
+        if (RELU) o[u] = ldg4(y + 4 * i);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i >= total4) break;
+      if (!FIXED_COLS) coefficients((int)(i % dim4) * 4);
+      float4 gv = g[u];
+      if (drop_threshold != 0) gv = mul4(gv, dropout_factors4(drop_seed, (uint64_t)i, drop_threshold, keep_scale));
+      if (RELU) {
+        gv.x = o[u].x > 0.f ? gv.x : 0.f; gv.y = o[u].y > 0.f ? gv.y : 0.f;
+        gv.z = o[u].z > 0.f ? gv.z : 0.f; gv.w = o[u].w > 0.f ? gv.w : 0.f;
+      }
+      if (d_res != nullptr) st4(d_res + 4 * i, gv);   // gradient of the residual branch (same mask, same ReLU gate)
+      float4 r;
+      if (training) {
+        const float4 av = a[u];
+        r.x = gi.x * (gv.x - gs.x - (av.x - mu.x) * is.x * gx.x);
+        r.y = gi.y * (gv.y - gs.y - (av.y - mu.y) * is.y * gx.y);
+        r.z = gi.z * (gv.z - gs.z - (av.z - mu.z) * is.z * gx.z);
+        r.w = gi.w * (gv.w - gs.w - (av.w - mu.w) * is.w * gx.w);
+      } else {
+        r.x = gi.x * gv.x; r.y = gi.y * gv.y; r.z = gi.z * gv.z; r.w = gi.w * gv.w;
+      }
+      st4(d_x + 4 * i, r);
+    }
   }
 }
 
@@ -231,8 +264,9 @@ int launch_partial(const float* x, const float* y, const float* d_y, int64_t n, 
   const int tx = dim / 4;
   const int ty = 256 / tx > 0 ? 256 / tx : 1;
   const size_t smem = (size_t)ty * 2 * dim * sizeof(double);
-  bn_partial_kernel<MODE><<<parts, dim3(tx, ty), smem, stream>>>(x, y, d_y, n, dim, mean, invstd, relu, drop_threshold,
-                                                                 keep_scale, drop_seed, chunk, partial);
+  auto kern = (MODE == 1 && relu) ? bn_partial_kernel<MODE, true> : bn_partial_kernel<MODE, false>;
+  kern<<<parts, dim3(tx, ty), smem, stream>>>(x, y, d_y, n, dim, mean, invstd, drop_threshold, keep_scale, drop_seed,
+                                              chunk, partial);
   ETPGT_CHECK_LAUNCH("bn_partial");
   bn_reduce_kernel<<<(2 * dim * 32 + 255) / 256, 256, 0, stream>>>(partial, parts, 2 * dim, sums);
   ETPGT_CHECK_LAUNCH("bn_reduce");
@@ -354,9 +388,13 @@ extern "C" int etpgt_bn_bwd_apply_ex(const float* x, const float* y, const float
   ETPGT_REQUIRE(dropout_params(drop_p, &threshold, &keep_scale), "bn_bwd_apply: dropout p must be in [0, 1)");
   if (n > 0) {
     const int64_t total4 = n * (dim / 4);
-    bn_bwd_apply_kernel<<<grid_for(total4, 256 * 4, 8), 256, 0, stream>>>(x, y, d_y, total4, dim, mean, invstd, gamma,
-                                                                         relu, training, sums, count, threshold,
-                                                                         keep_scale, drop_seed, d_x, d_res);
+    const int grid = grid_for(total4, 256 * 4, 6);
+    const bool fixed = ((int64_t)grid * 256) % (dim / 4) == 0;
+    // (two elements, i.e. four to six 16-byte loads, in flight per thread)
+    auto kern = relu ? (fixed ? bn_bwd_apply_kernel<true, true, 2> : bn_bwd_apply_kernel<false, true, 2>)
+                     : (fixed ? bn_bwd_apply_kernel<true, false, 2> : bn_bwd_apply_kernel<false, false, 2>);
+    kern<<<grid, 256, 0, stream>>>(x, y, d_y, total4, dim, mean, invstd, gamma, training, sums, count, threshold,
+                                   keep_scale, drop_seed, d_x, d_res);
     ETPGT_CHECK_LAUNCH("bn_bwd_apply");
   }
   if (d_gamma != nullptr && d_bias != nullptr) {

@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(DIM)
 pe_wgrad_partial_kernel(const int64_t* __restrict__ ids, int64_t n, const float* __restrict__ d_out,
                         const float* __restrict__ pe, int pe_per_node, int64_t chunk,
                         float* __restrict__ partial /* [grid][DIM][KPE+1] */) {
-  constexpr int TILE = 32;
+  constexpr int TILE = 64;
   __shared__ float pe_tile[TILE][KPE];
   const int d = threadIdx.x;
   const int64_t begin = blockIdx.x * chunk;
@@ -178,38 +178,42 @@ pe_wgrad_partial_kernel(const int64_t* __restrict__ ids, int64_t n, const float*
   for (int k = 0; k <= KPE; ++k) dst[k] = acc[k];
 }
 
-__global__ void __launch_bounds__(256)
+constexpr int kWgradReduceWarps = 32;
+__global__ void __launch_bounds__(kWgradReduceWarps * 32)
 pe_wgrad_reduce_kernel(const float* __restrict__ partial, int parts, int dim, int kpe,
                        float* __restrict__ d_w, float* __restrict__ d_b) {
   // A CTA owns 32 consecutive outputs (of dim*(kpe+1)): lane = output, so every load is a coalesced
-  // 128-byte segment; warp w adds parts w, w+8, ...; the eight warp sums are added in warp order.
-  __shared__ float warp_sum[8][32];
+  // 128-byte segment; warp w adds parts w, w+32, ... with eight loads in flight; the 32 warp sums are added
+  // in warp order (fixed order -> deterministic).
+  __shared__ float warp_sum[kWgradReduceWarps][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int total = dim * (kpe + 1);
   const int i = blockIdx.x * 32 + lane;
   float s = 0.f;
   if (i < total) {
     int p = w;
-    for (; p + 24 < parts; p += 32) {
-      const float a = partial[(int64_t)p * total + i], b = partial[(int64_t)(p + 8) * total + i];
-      const float c = partial[(int64_t)(p + 16) * total + i], e = partial[(int64_t)(p + 24) * total + i];
-      s += a; s += b; s += c; s += e;
+    for (; p + 7 * kWgradReduceWarps < parts; p += 8 * kWgradReduceWarps) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = partial[(int64_t)(p + kWgradReduceWarps * u) * total + i];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += v[u];
     }
-    for (; p < parts; p += 8) s += partial[(int64_t)p * total + i];
+    for (; p < parts; p += kWgradReduceWarps) s += partial[(int64_t)p * total + i];
   }
   warp_sum[w][lane] = s;
   __syncthreads();
   if (w != 0 || i >= total) return;
   float t = 0.f;
 #pragma unroll
-  for (int q = 0; q < 8; ++q) t += warp_sum[q][lane];
+  for (int q = 0; q < kWgradReduceWarps; ++q) t += warp_sum[q][lane];
   const int d = i / (kpe + 1), k = i % (kpe + 1);
   if (k == kpe) d_b[d] = t; else d_w[d * kpe + k] = t;
 }
 
 int wgrad_parts(int64_t n) {
   int64_t parts = (n + 63) / 64;
-  if (parts > 4 * kNumSMs) parts = 4 * kNumSMs;
+  if (parts > 8 * kNumSMs) parts = 8 * kNumSMs;
   return parts < 1 ? 1 : (int)parts;
 }
 
@@ -304,7 +308,8 @@ extern "C" int etpgt_embed_pe_bwd_planned(const int64_t* ids, int64_t n, const f
 #undef CALL_K
   ETPGT_CHECK_LAUNCH("pe_wgrad_partial");
   const int total = dim * (k_pe + 1);
-  pe_wgrad_reduce_kernel<<<(total + 31) / 32, 256, 0, stream>>>(partial, parts, dim, k_pe, d_w_pe, d_b_pe);
+  pe_wgrad_reduce_kernel<<<(total + 31) / 32, kWgradReduceWarps * 32, 0, stream>>>(partial, parts, dim, k_pe, d_w_pe,
+                                                                                 d_b_pe);
   ETPGT_CHECK_LAUNCH("pe_wgrad_reduce");
   return ETPGT_OK;
 }

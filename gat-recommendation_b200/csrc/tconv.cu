@@ -328,33 +328,34 @@ tconv_bwd_dst_kernel(const float* __restrict__ qkvs, const float* __restrict__ d
 // Column i of the per-CTA partials goes to out_a[i] when i < width_a, else to
 // out_b[off_b0 + (i - width_a)] for the first `dim` of them and out_b[off_b1 + ...] for the next `dim`
 // (the two bias-gradient blocks of a pass sit at different offsets of the [4*dim] bias gradient).
-__global__ void __launch_bounds__(256)
+constexpr int kReduceWarps = 32;
+__global__ void __launch_bounds__(kReduceWarps * 32)
 reduce_partials_kernel(const float* __restrict__ partial, int parts, int width, int width_a,
                        float* __restrict__ out_a, float* __restrict__ out_b, int dim, int off_b0, int off_b1) {
   // A CTA owns 32 consecutive columns: lane = column (every load is one coalesced 128-byte row
-  // segment), warp w adds parts w, w+8, ... with eight loads in flight, the eight warp sums are then
-  // added in warp order -> deterministic.
-  __shared__ float warp_sum[8][32];
+  // segment), warp w adds parts w, w+32, ... with eight loads in flight (up to 1,184 partials: five
+  // dependent rounds per warp), the 32 warp sums are then added in warp order -> deterministic.
+  __shared__ float warp_sum[kReduceWarps][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + lane;
   float s = 0.f;
   if (i < width) {
     int p = w;
-    for (; p + 56 < parts; p += 64) {
+    for (; p + 7 * kReduceWarps < parts; p += 8 * kReduceWarps) {
       float v[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = partial[(int64_t)(p + 8 * u) * width + i];
+      for (int u = 0; u < 8; ++u) v[u] = partial[(int64_t)(p + kReduceWarps * u) * width + i];
 #pragma unroll
       for (int u = 0; u < 8; ++u) s += v[u];
     }
-    for (; p < parts; p += 8) s += partial[(int64_t)p * width + i];
+    for (; p < parts; p += kReduceWarps) s += partial[(int64_t)p * width + i];
   }
   warp_sum[w][lane] = s;
   __syncthreads();
   if (w != 0 || i >= width) return;
   float t = 0.f;
 #pragma unroll
-  for (int q = 0; q < 8; ++q) t += warp_sum[q][lane];
+  for (int q = 0; q < kReduceWarps; ++q) t += warp_sum[q][lane];
   if (i < width_a) out_a[i] = t;
   else if (i - width_a < dim) out_b[off_b0 + (i - width_a)] = t;
   else out_b[off_b1 + (i - width_a - dim)] = t;
@@ -536,7 +537,7 @@ extern "C" int etpgt_tconv_bwd_split(const float* qkvs, const float* d_out, int6
 #undef CALL
   ETPGT_CHECK_LAUNCH("tconv_bwd_dst");
   if (width > 0) {  // d_w_beta [3*dim]; bias gradients of query -> d_colsum[0:dim], skip -> d_colsum[3*dim:4*dim]
-    reduce_partials_kernel<<<(width + 31) / 32, 256, 0, stream>>>(partial, grid_a, width, width_a, d_w_beta, d_colsum,
+    reduce_partials_kernel<<<(width + 31) / 32, kReduceWarps * 32, 0, stream>>>(partial, grid_a, width, width_a, d_w_beta, d_colsum,
                                                                  dim, 0, 3 * dim);
     ETPGT_CHECK_LAUNCH("tconv dst partial reduce");
   }
@@ -556,7 +557,7 @@ extern "C" int etpgt_tconv_bwd_split(const float* qkvs, const float* d_out, int6
 #undef CALL
   ETPGT_CHECK_LAUNCH("tconv_bwd_src");
   if (want_colsum) {  // key -> d_colsum[dim:2*dim], value -> d_colsum[2*dim:3*dim]
-    reduce_partials_kernel<<<(2 * dim + 31) / 32, 256, 0, stream>>>(src_partial, (int)grid_src, 2 * dim, 0, nullptr,
+    reduce_partials_kernel<<<(2 * dim + 31) / 32, kReduceWarps * 32, 0, stream>>>(src_partial, (int)grid_src, 2 * dim, 0, nullptr,
                                                                    d_colsum, dim, dim, 2 * dim);
     ETPGT_CHECK_LAUNCH("tconv src colsum reduce");
   }
