@@ -81,6 +81,8 @@ _PROTOTYPES = {
     "etpgt_scatter_rows": (I, [P, P, P, L, I, I, L, L, P, P, Z, P]),
     "etpgt_scatter_plan_workspace_bytes": (Z, [L]),
     "etpgt_scatter_plan": (I, [P, L, L, P, P, P, Z, P]),
+    "etpgt_batch_prepare_workspace_bytes": (Z, [L, L, L]),
+    "etpgt_batch_prepare": (I, [P, P, L, L, P, P, P, L, I, L, P, P, P, P, P, P, P, P, P, P, P, Z, P]),
     "etpgt_scatter_plan_loss": (I, [P, P, L, I, L, P, P, P, Z, P]),
     "etpgt_scatter_rows_planned": (I, [P, P, P, P, L, I, I, L, P, P]),
     "etpgt_embed_pe_bwd_planned": (I, [P, L, P, L, P, I, I, I, L, P, P, P, P, P, P, Z, P]),

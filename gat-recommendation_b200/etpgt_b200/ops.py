@@ -49,9 +49,10 @@ class GraphIndex:
     __slots__ = ("num_nodes", "num_edges", "rowptr", "col", "eperm", "colptr", "row", "cpos")
 
     def __init__(self, edge_index: torch.Tensor, num_nodes: int, out: torch.Tensor | None = None,
-                 ws: torch.Tensor | None = None):
+                 ws: torch.Tensor | None = None, build: bool = True):
         """`out` (optional): an int32 buffer of at least `GraphIndex.out_elems(num_nodes, num_edges)` elements the
-        six arrays are carved from; `ws`: a byte workspace of at least etpgt_csr_workspace_bytes."""
+        six arrays are carved from; `ws`: a byte workspace of at least etpgt_csr_workspace_bytes; build=False
+        only carves the arrays (the caller fills them, see prepare_batch)."""
         _require_cuda(edge_index, "edge_index")
         edge_index = _i64(edge_index)
         dev = edge_index.device
@@ -65,6 +66,8 @@ class GraphIndex:
         self.rowptr, self.colptr = out[:num_nodes + 1], out[o1:o1 + num_nodes + 1]
         self.col, self.eperm = out[o2:o2 + e], out[o2 + oe:o2 + oe + e]
         self.row, self.cpos = out[o2 + 2 * oe:o2 + 2 * oe + e], out[o2 + 3 * oe:o2 + 3 * oe + e]
+        if not build:
+            return
         if ws is None:
             ws = workspace(size("etpgt_csr_workspace_bytes", e, num_nodes), dev)
         call("etpgt_csr_from_coo", ptr(edge_index[0]), ptr(edge_index[1]), e, num_nodes,
@@ -115,9 +118,10 @@ class ScatterPlan:
     __slots__ = ("m", "sorted_key", "perm")
 
     def __init__(self, keys: torch.Tensor, num_rows: int, negatives: torch.Tensor | None = None,
-                 out: torch.Tensor | None = None, ws: torch.Tensor | None = None):
+                 out: torch.Tensor | None = None, ws: torch.Tensor | None = None, build: bool = True):
         """keys [m] — or, with `negatives` [B, num_neg], keys = targets [B] and the plan covers the loss layout
-        [b][0] = target, [b][1 + c] = negative c.  `out`: int32 buffer of >= 2 * _pad64(m) elements."""
+        [b][0] = target, [b][1 + c] = negative c.  `out`: int32 buffer of >= 2 * _pad64(m) elements; build=False
+        only carves the two arrays (the caller fills them, see prepare_batch)."""
         _require_cuda(keys, "scatter keys")
         keys = _i64(keys).reshape(-1)
         dev = keys.device
@@ -131,6 +135,8 @@ class ScatterPlan:
         if out is None:
             out = torch.empty(2 * _pad64(self.m), dtype=torch.int32, device=dev)
         self.sorted_key, self.perm = out[:self.m], out[_pad64(self.m):_pad64(self.m) + self.m]
+        if not build:
+            return
         if ws is None:
             ws = workspace(size("etpgt_scatter_plan_workspace_bytes", self.m), dev)
         if negatives is not None:
@@ -191,37 +197,47 @@ def prepare_batch(batch, num_items: int | None = None) -> PreparedBatch:
     Everything here depends on the batch's inputs only, so a loader (or a side stream one step ahead) runs
     it off the training step's critical path; the model and the loss find the results again through the
     batch object / the key tensors.  Without this call the step builds the same things inline.
-    Host cost: two allocations and three library calls."""
+    Host cost: two allocations and one library call."""
     prepared = PreparedBatch()
     edge_index, ids = batch.edge_index, batch.x
     _require_cuda(ids, "batch.x")
     n, e = int(ids.numel()), int(edge_index.size(1))
-    targets = getattr(batch, "target_item", None) if num_items is not None else None
-    negatives = getattr(batch, "negative_items", None) if num_items is not None else None
-    plan_loss = targets is not None and negatives is not None and targets.numel() > 0
-    m_loss = int(targets.numel() + negatives.numel()) if plan_loss else 0
-    elems_index = GraphIndex.out_elems(n, e)
-    elems_nodes = 2 * _pad64(n) if num_items is not None else 0
     dev = ids.device
-    prepared.buffer = torch.empty(elems_index + elems_nodes + 2 * _pad64(m_loss), dtype=torch.int32, device=dev)
-    nbytes = size("etpgt_csr_workspace_bytes", e, n)
-    if num_items is not None:
-        nbytes = max(nbytes, size("etpgt_scatter_plan_workspace_bytes", max(n, m_loss)))
-    prepared.scratch = workspace(nbytes, dev)          # the three calls run back to back on one stream
-    prepared.index = GraphIndex(edge_index, n, out=prepared.buffer, ws=prepared.scratch)
-    try:
-        object.__setattr__(batch, "_etpgt_index", (edge_index, prepared.index))
-    except Exception:
-        pass
     prepared.plan_nodes = prepared.plan_loss = None
-    if num_items is not None:
-        prepared.plan_nodes = ScatterPlan(ids, num_items, out=prepared.buffer[elems_index:], ws=prepared.scratch)
-        _register_plan(prepared.plan_nodes, ids)
+    if num_items is None or n == 0:      # the index alone
+        prepared.buffer = torch.empty(GraphIndex.out_elems(n, e), dtype=torch.int32, device=dev)
+        prepared.scratch = workspace(size("etpgt_csr_workspace_bytes", e, n), dev)
+        prepared.index = GraphIndex(edge_index, n, out=prepared.buffer, ws=prepared.scratch)
+    else:
+        # index + both scatter plans from ONE library call (etpgt_batch_prepare: the destination sort and the two
+        # plan sorts are a single segmented radix sort), outputs carved from one buffer
+        edge_index, ids = _i64(edge_index), _i64(ids)
+        targets, negatives = getattr(batch, "target_item", None), getattr(batch, "negative_items", None)
+        plan_loss = targets is not None and negatives is not None and targets.numel() > 0
+        b = int(targets.numel()) if plan_loss else 0
+        num_neg = int(negatives.numel()) // b if plan_loss else 0
+        m_loss = b * (num_neg + 1)
         if plan_loss:
-            prepared.plan_loss = ScatterPlan(targets, num_items, negatives=negatives,
-                                             out=prepared.buffer[elems_index + elems_nodes:], ws=prepared.scratch)
-            _register_plan(prepared.plan_loss, targets, negatives)
+            targets, negatives = _i64(targets), _i64(negatives)
+        elems_index, elems_nodes = GraphIndex.out_elems(n, e), 2 * _pad64(n)
+        prepared.buffer = torch.empty(elems_index + elems_nodes + 2 * _pad64(m_loss), dtype=torch.int32, device=dev)
+        prepared.scratch = workspace(size("etpgt_batch_prepare_workspace_bytes", e, n, m_loss), dev)
+        index = prepared.index = GraphIndex(edge_index, n, out=prepared.buffer, build=False)
+        nodes = prepared.plan_nodes = ScatterPlan(ids, num_items, out=prepared.buffer[elems_index:], build=False)
+        loss = None
+        if plan_loss:
+            loss = prepared.plan_loss = ScatterPlan(targets, num_items, negatives=negatives,
+                                                    out=prepared.buffer[elems_index + elems_nodes:], build=False)
+        call("etpgt_batch_prepare", ptr(edge_index[0]), ptr(edge_index[1]), e, n, ptr(ids),
+             ptr(targets) if plan_loss else None, ptr(negatives) if plan_loss else None, b, num_neg, int(num_items),
+             ptr(index.rowptr), ptr(index.col), ptr(index.eperm), ptr(index.colptr), ptr(index.row), ptr(index.cpos),
+             ptr(nodes.sorted_key), ptr(nodes.perm), ptr(loss.sorted_key) if loss else None,
+             ptr(loss.perm) if loss else None, ptr(prepared.scratch), prepared.scratch.numel(), stream())
+        _register_plan(nodes, batch.x)
+        if loss is not None:
+            _register_plan(loss, batch.target_item, batch.negative_items)
     try:
+        object.__setattr__(batch, "_etpgt_index", (batch.edge_index, prepared.index))
         object.__setattr__(batch, "_etpgt_prepared", prepared)   # keeps the plans alive with the batch
     except Exception:
         pass

@@ -416,6 +416,17 @@ int etpgt_scatter_plan_loss(const int64_t* targets, const int64_t* negatives, in
 int etpgt_scatter_rows_planned(const int32_t* sorted_key, const int32_t* perm, const float* coef,
                                const float* src, int64_t m, int src_div, int dim, int64_t skip_key,
                                float* d_table, etpgt_stream_t stream);
+/* Batch preparation in one call: etpgt_csr_from_coo of (src, dst) plus the scatter plans of `ids` [N] (rows of
+ * num_items) and of the loss keys ([b][0] = targets[b], [b][1 + c] = negatives[b][c]; targets == NULL skips that
+ * plan), with identical outputs — but the destination sort and the two plan sorts run as ONE segmented radix sort
+ * (the segment number rides above the key bits), so the call costs two sorts instead of four. */
+size_t etpgt_batch_prepare_workspace_bytes(int64_t num_edges, int64_t num_nodes, int64_t num_loss_keys);
+int etpgt_batch_prepare(const int64_t* src, const int64_t* dst, int64_t num_edges, int64_t num_nodes,
+                        const int64_t* ids, const int64_t* targets, const int64_t* negatives,
+                        int64_t num_sessions, int num_neg, int64_t num_items, int32_t* rowptr, int32_t* col,
+                        int32_t* eperm, int32_t* colptr, int32_t* row, int32_t* cpos, int32_t* nodes_key,
+                        int32_t* nodes_perm, int32_t* loss_key, int32_t* loss_perm, void* ws, size_t ws_bytes,
+                        etpgt_stream_t stream);
 int etpgt_embed_pe_bwd_planned(const int64_t* ids, int64_t n, const float* d_out, int64_t num_items,
                                const float* pe, int pe_per_node, int k_pe, int dim, int64_t padding_idx,
                                const int32_t* plan_sorted_key, const int32_t* plan_perm, float* d_table,

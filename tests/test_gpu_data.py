@@ -279,3 +279,41 @@ def test_scatter_plans_give_bit_identical_table_gradients():
     x_key = ops._plan_key(batch.x)
     del batch
     assert x_key not in ops._PLANS          # plans die with their key tensors
+
+
+@pytest.mark.parametrize("with_loss,edges", [(True, True), (False, True), (True, False)])
+def test_batch_prepare_equals_the_separate_builds(with_loss, edges):
+    """etpgt_batch_prepare (one segmented sort for the destination order and both scatter plans) must produce
+    exactly what etpgt_csr_from_coo + etpgt_scatter_plan + etpgt_scatter_plan_loss produce one by one."""
+    from etpgt_b200 import ops
+
+    g = torch.Generator().manual_seed(4)
+    n, e, b, items = 3001, (7919 if edges else 0), 257, 70000      # item ids need more bits than node ids
+    edge_index = torch.randint(0, n, (2, e), generator=g).cuda()
+    edge_index[1, : e // 3] = 5                                        # a hub destination, many ties
+
+    class Batch:
+        pass
+
+    batch = Batch()
+    batch.x = torch.randint(1, items, (n,), generator=g).cuda()
+    batch.edge_index = edge_index
+    if with_loss:
+        batch.target_item = torch.randint(1, items, (b,), generator=g).cuda()
+        batch.negative_items = torch.randint(1, items, (b * 5,), generator=g).cuda()
+    prepared = ops.prepare_batch(batch, items)
+    index = ops.GraphIndex(edge_index, n)
+    for name in ("rowptr", "col", "eperm", "colptr", "row", "cpos"):
+        assert torch.equal(getattr(prepared.index, name), getattr(index, name)), name
+    nodes = ops.ScatterPlan(batch.x, items)
+    assert torch.equal(prepared.plan_nodes.sorted_key, nodes.sorted_key)
+    assert torch.equal(prepared.plan_nodes.perm, nodes.perm)
+    if with_loss:
+        loss = ops.ScatterPlan(batch.target_item, items, negatives=batch.negative_items)
+        assert torch.equal(prepared.plan_loss.sorted_key, loss.sorted_key)
+        assert torch.equal(prepared.plan_loss.perm, loss.perm)
+        keys = torch.cat([batch.target_item.view(-1, 1), batch.negative_items.view(b, 5)], 1).reshape(-1)
+        want = torch.sort(keys, stable=True)
+        assert torch.equal(loss.sorted_key.long(), want.values) and torch.equal(loss.perm.long(), want.indices)
+    else:
+        assert prepared.plan_loss is None
