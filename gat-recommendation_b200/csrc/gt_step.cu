@@ -182,9 +182,10 @@ extern "C" int etpgt_gt_step_run(const etpgt_gt_step_t* sp, int phase_begin, int
   ETPGT_REQUIRE(s.arena != nullptr && s.arena_bytes >= etpgt_gt_step_arena_bytes(sp), "gt_step: arena %zu < %zu",
                 s.arena_bytes, etpgt_gt_step_arena_bytes(sp));
   ETPGT_REQUIRE((reinterpret_cast<uintptr_t>(s.arena) & 255) == 0, "gt_step: arena must be 256-byte aligned");
-  ETPGT_REQUIRE(s.ids && s.batch_vec && s.rowptr && s.col && s.eperm && s.colptr && s.row && s.cpos && s.targets &&
-                    s.negatives && s.table && s.bn_sums && s.sess && s.losses,
+  ETPGT_REQUIRE(s.ids && s.batch_vec && s.rowptr && s.colptr && s.targets && s.negatives && s.table && s.bn_sums &&
+                    s.sess && s.losses,
                 "gt_step: null pointer in the descriptor");
+  ETPGT_REQUIRE(s.num_edges == 0 || (s.col && s.eperm && s.row && s.cpos), "gt_step: null edge arrays");
   const Layout lay = carve(s, s.arena);
   const int64_t n = s.num_nodes, e = s.num_edges, b = s.num_sessions;
   const int dim = s.dim, width = 4 * s.dim, heads = s.heads;

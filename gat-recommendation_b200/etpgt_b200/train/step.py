@@ -60,6 +60,19 @@ class _GtStep(ctypes.Structure):
            ("arena_bytes", c_size_t)])
 
 
+def exchange_row(phase: int, layers: int) -> int | None:
+    """Row of `bn_sums` that `phase` of the step driver produces and the next phase consumes (to be all-reduced in
+    between under data parallelism), or None for phases that produce no BatchNorm statistics.  Phases 0..layers-1
+    produce the forward sums of layers 0..layers-1 (rows 0..layers-1); phase layers+j (j = 0..layers-1) produces
+    the backward sums of layer layers-1-j (row 2*layers-1-j); phases 2*layers and 2*layers+1 produce none (the
+    table gradient is complete after phase 2*layers).  Mirrors csrc/gt_step.cu."""
+    if 0 <= phase < layers:
+        return phase
+    if layers <= phase < 2 * layers:
+        return layers + (2 * layers - 1 - phase)
+    return None
+
+
 def _addr(t: torch.Tensor | None):
     return None if t is None else t.data_ptr()
 
@@ -276,10 +289,8 @@ class FusedTrainStep:
             last = phases if backward else layers + 1
             for phase in range(last):
                 _lib.call("etpgt_gt_step_run", ctypes.byref(d), phase, phase + 1, stream())
-                if phase < min(last - 1, 2 * layers):
-                    # phase p < layers produced the forward sums of layer p; phase layers + j the backward sums
-                    # of layer layers - 1 - j
-                    row = phase if phase < layers else layers + (2 * layers - 1 - phase)
+                row = exchange_row(phase, layers)
+                if row is not None and phase < last - 1:
                     dist.all_reduce(bn_sums[row], group=group)
                 elif phase == 2 * layers:
                     # the table gradient is complete: its all-reduce (the step's largest message) runs on NCCL's

@@ -146,3 +146,18 @@ def test_step_descriptor_layout_matches_the_header(tmp_path):
     declared = set(re.findall(r"[\s\*,](\w+)\s*(?:\[\w+\])?\s*[;,]", body))
     assert declared == set(fields(step._GtStep)), declared ^ set(fields(step._GtStep))
     assert step.MAX_LAYERS == int(re.search(r"#define ETPGT_GT_MAX_LAYERS (\d+)", text).group(1))
+
+
+def test_step_phase_exchange_rows():
+    """Host-side control flow of the data-parallel step (etpgt_b200/train/step.py): which BatchNorm exchange row
+    each driver phase produces.  Forward rows in layer order, backward rows from the last layer down, none for the
+    two trailing phases; every row exactly once."""
+    from etpgt_b200.train.step import exchange_row
+
+    for layers in (1, 2, 3, 4):
+        rows = [exchange_row(p, layers) for p in range(2 * layers + 2)]
+        assert rows[:layers] == list(range(layers))
+        assert rows[layers:2 * layers] == [layers + l for l in reversed(range(layers))]
+        assert rows[2 * layers:] == [None, None]
+        assert sorted(r for r in rows if r is not None) == list(range(2 * layers))
+    assert exchange_row(-1, 2) is None and exchange_row(99, 2) is None

@@ -268,3 +268,50 @@ def test_trainer_mirrors_the_reference_loop(tmp_path):
     ckpt = torch.load(out / "checkpoint_latest.pt", weights_only=False)
     assert set(ckpt) == {"epoch", "model_state_dict", "optimizer_state_dict", "best_val_metric", "history"}
     assert a.patience_counter <= a.patience and len(hist_a["val_metrics"]) == len(hist_a["train_loss"])
+
+
+def test_driver_edge_cases_match_the_autograd_path():
+    """Ragged and degenerate batches (the shapes the reference's collate can produce): no edge at all, a single
+    session, one-node sessions, a session without edges next to dense ones, an odd number of negatives."""
+    from etpgt_b200.model import create_graph_transformer_optimized
+
+    class Batch:
+        pass
+
+    def make(sizes, edge_prob, num_neg, seed):
+        rng = np.random.default_rng(seed)
+        ids, src, dst, bvec, off = [], [], [], [], 0
+        for s, n in enumerate(sizes):
+            ids.append(np.sort(rng.choice(np.arange(1, 300), size=n, replace=False)))
+            pairs = [(a, b) for a in range(n) for b in range(a, n) if rng.random() < edge_prob[s % len(edge_prob)]]
+            src += [off + a for a, _ in pairs]
+            dst += [off + b for _, b in pairs]
+            bvec += [s] * int(n)
+            off += int(n)
+        b = Batch()
+        b.x = torch.from_numpy(np.concatenate(ids)).cuda()
+        b.edge_index = torch.tensor([src, dst], dtype=torch.long).reshape(2, -1).cuda()
+        b.batch = torch.tensor(bvec, dtype=torch.long).cuda()
+        b.num_graphs = len(sizes)
+        b.target_item = torch.from_numpy(rng.integers(1, 300, size=len(sizes))).cuda()
+        b.negative_items = torch.from_numpy(rng.integers(1, 300, size=len(sizes) * num_neg)).cuda()
+        return b
+
+    torch.manual_seed(0)
+    model = create_graph_transformer_optimized(300, 64, 64, dropout=0.1, laplacian_k=8).cuda()
+    model.laplacian_pe._cached_pe = torch.randn(300, 8, device="cuda").abs()
+    model.train()
+    cases = [
+        ([3, 5, 2, 7], [0.0], 5, 1),                 # no edges anywhere
+        ([6], [0.6], 5, 2),                          # one session
+        ([1, 1, 4, 1], [1.0], 3, 3),                 # one-node sessions (self loops only), 3 negatives
+        ([5, 4, 9, 2, 8], [0.0, 0.9], 1, 4),         # edgeless sessions between dense ones, a single negative
+    ]
+    for sizes, prob, num_neg, seed in cases:
+        batch = make(sizes, prob, num_neg, seed)
+        want = _autograd_step(model, batch, "dual", seed=21)
+        _assert_identical(want, _driver_step(model, make(sizes, prob, num_neg, seed), "dual", seed=21))
+        prepared = make(sizes, prob, num_neg, seed)
+        from etpgt_b200 import ops
+        ops.prepare_batch(prepared, 300)
+        _assert_identical(want, _driver_step(model, prepared, "dual", seed=21))
