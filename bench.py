@@ -6,10 +6,11 @@
 
 Workload (BASELINE.json configs[1]): graph_transformer_optimized (D=256, L=2, H=2, k_pe=16),
 BPR loss, AdamW(1e-3, 1e-5), session batches drawn from the synthetic RetailRocket-shaped graph
-(etpgt_b200/synth.py).  One step = forward + loss + backward + optimizer over one batch of
-`--batch` sessions per GPU (weak scaling; default 32,768 — the smallest power of two at which the step
-is device-bound rather than bound by the ~1.9 ms the host needs to launch it; `batch_sweep` reports
-16,384 and 65,536 as well).  Prints ONE JSON line (rank 0).
+(etpgt_b200/synth.py).  One step = optimizer.zero_grad() + forward + loss + backward (the C++ step driver,
+etpgt_gt_step_run, through etpgt_b200.train.step.FusedTrainStep) + gradient all-reduce (N > 1) + optimizer step
+over one batch of `--batch` sessions per GPU (weak scaling; default 32,768; `batch_sweep` reports 16,384 and
+65,536 as well).  Every step also prepares its batch (CSR + CSC index, scatter plans: etpgt_batch_prepare) inside the
+timed region, one step ahead on a side stream.  Prints ONE JSON line (rank 0).
 
   value   sessions/s with the batch tensors already resident in HBM;
   e2e     the same step driven from pinned HOST batch tensors (H2D of x / edge_index / batch /

@@ -56,9 +56,8 @@ class GraphTransformer(BaseRecommendationModel):
         # bf16 hi/lo split of x for the fused layer's GEMM: written by the embedding kernel for the first layer
         # and by the previous fused layer's BatchNorm apply after that
         split = None
-        if ids.numel() > 0 and ops.FUSED_LAYER and ops.fused_conv_supported(
-                self.item_embedding.weight, self.embedding_dim, 4 * self.hidden_dim) and \
-                self.embedding_dim == self.hidden_dim:
+        if ids.numel() > 0 and ops.embed_split_supported(self.item_embedding.weight, self.embedding_dim,
+                                                         self.hidden_dim):
             x, hi, lo = ops.EmbedPE.apply(ids, self.item_embedding.weight, pe, per_node, w_pe, b_pe,
                                           self.item_embedding.padding_idx, True)
             split = (hi, lo)

@@ -638,6 +638,12 @@ def supported_dim(dim: int) -> bool:
     return dim in (32, 64, 128, 256)
 
 
+def embed_split_supported(table: torch.Tensor, embedding_dim: int, hidden_dim: int) -> bool:
+    """Whether the embedding kernel should also write x0 as the bf16 operand pair of the first fused layer (the
+    conditions under which that layer takes the tensor-core projection path for an [N, embedding_dim] input)."""
+    return FUSED_LAYER and embedding_dim == hidden_dim and fused_conv_supported(table, embedding_dim, 4 * hidden_dim)
+
+
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None) -> torch.Tensor:
     """Dense projection of the path.  Tensor-core split-bf16 GEMM when the shape allows it
     (inner and outer widths multiples of 8), else a library fp32 GEMM."""
