@@ -281,6 +281,8 @@ class FusedTrainStep:
         d.arena, d.arena_bytes = self._arena.data_ptr(), self._arena.numel()
 
         phases = 2 * layers + 2
+        if self._table_work is not None:     # a previous step's table all-reduce nobody joined
+            self._table_work.wait()
         self._table_work = None
         if not distributed:
             _lib.call("etpgt_gt_step_run", ctypes.byref(d), 0, phases, stream())
@@ -305,7 +307,9 @@ class FusedTrainStep:
         return losses
 
     def allreduce_gradients(self, group=None) -> None:
-        """Data parallelism: sums the dense gradients (one flat buffer) and the table gradient across ranks."""
+        """Data parallelism: sums the dense gradients (one flat buffer) and the table gradient across ranks.
+        Call it between the step and `optimizer.step()`: the table's all-reduce was started underneath the
+        step's last phase and is joined here."""
         if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
             return
         dist.all_reduce(self._flat, group=group)
