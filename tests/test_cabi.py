@@ -161,3 +161,23 @@ def test_step_phase_exchange_rows():
         assert rows[2 * layers:] == [None, None]
         assert sorted(r for r in rows if r is not None) == list(range(2 * layers))
     assert exchange_row(-1, 2) is None and exchange_row(99, 2) is None
+
+
+def test_step_driver_support_matrix_on_cpu_models():
+    """Which (model, loss) pairs the trainer sends through the C++ step driver — decided on the host without
+    touching a GPU: CPU-resident models are never driven (the driver has no CPU fallback), nor are the FFN variant,
+    the attention readout, GAT / GraphSAGE."""
+    from etpgt_b200.model import (create_gat, create_graph_transformer, create_graph_transformer_optimized,
+                                  create_graphsage)
+    from etpgt_b200.train.step import FusedTrainStep
+
+    reason = FusedTrainStep.unsupported_reason
+    assert "CUDA" in reason(create_graph_transformer_optimized(50, 64, 64))
+    assert "use_ffn" in reason(create_graph_transformer(50, 64, 64))
+    assert "readout" in reason(create_graph_transformer_optimized(50, 64, 64, readout_type="attention"))
+    assert "GraphTransformer" in reason(create_gat(50, 64, 64))
+    assert "GraphTransformer" in reason(create_graphsage(50, 64, 64))
+    assert "hidden_dim" in reason(create_graph_transformer_optimized(50, 48, 48)) or \
+        "embedding_dim" in reason(create_graph_transformer_optimized(50, 48, 48))
+    with pytest.raises(NotImplementedError):
+        FusedTrainStep(create_graph_transformer_optimized(50, 64, 64))     # CPU parameters
