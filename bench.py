@@ -56,6 +56,8 @@ def parse_args():
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--step-only", action="store_true",
                     help="only the training-step measurements (for profiler runs): no sweep, rooflines or baselines")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: gradient / BatchNorm exchange over peer memory (this library's kernels) or NCCL all-reduces")
     ap.add_argument("--sweep-batches", type=str, default="16384,65536",
                     help="extra device-resident measurements at these batch sizes (rank 0, 1 GPU; '' = off)")
     return ap.parse_args()
@@ -245,6 +247,7 @@ def workload_config(args, stats):
             "dim": DIM, "layers": LAYERS, "heads": HEADS, "k_pe": K_PE, "negatives": NUM_NEG,
             "sessions_per_gpu_per_step": args.batch, "items": stats["items"], "graph_edges": stats["graph_edges"],
             "graph_nodes": stats["graph_nodes"], "parallelism": f"dp{args.gpus}",
+            "exchange": (args.exchange if args.gpus > 1 else "none"),
             "l2_policy": "inputs larger than L2 (rotating batches, 84 MB table, >300 MB activations)"}
 
 
@@ -277,10 +280,11 @@ def run_b200(args, rank, world_size, local_rank):
     torch.manual_seed(0)
     model = create_graph_transformer_optimized(NUM_ITEMS, DIM, DIM, LAYERS, HEADS, dropout=0.1).to(device)
     model.laplacian_pe._cached_pe = cached_pe(NUM_ITEMS).to(device)
+    peer = None
     if distributed:
-        parallel.enable_global_batch_norm(model)
-        for p in model.parameters():
-            dist.broadcast(p.data, 0)
+        # before the optimizer: with the peer exchange the item table and its gradient buffer move into this rank's
+        # peer region (parallel.PeerDataParallel); parameters are broadcast from rank 0
+        peer = parallel.enable_data_parallel(model, exchange=args.exchange)
     opt = optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-5)   # etpgt_adam_step, table-gradient sink
     params = list(model.parameters())
     total_sessions = args.batch * world_size
@@ -295,8 +299,8 @@ def run_b200(args, rank, world_size, local_rank):
         opt.zero_grad()
         if fused is not None:
             loss = fused(batch, total_sessions=total_sessions)[0]
-            if distributed:
-                fused.allreduce_gradients()
+            if distributed and peer is None:
+                fused.allreduce_gradients()      # NCCL variant; the peer exchange is part of opt.step()
         else:
             sess = model(batch)
             loss = ops.sampled_loss(sess, model.item_embedding, batch.target_item, batch.negative_items, "bpr",

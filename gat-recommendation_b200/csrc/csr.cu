@@ -49,6 +49,20 @@ __global__ void gather_i32_kernel(const int32_t* __restrict__ values, const int3
     out[p] = values[index[p]];
 }
 
+// flag |= 1 when any id of the three lists lies outside [0, num_rows): the device-side counterpart of the
+// IndexError nn.Embedding raises in the reference (item ids index the table and its gradient buffer raw)
+__global__ void ids_check_kernel(const int64_t* __restrict__ a, int64_t na, const int64_t* __restrict__ b,
+                                 int64_t nb, const int64_t* __restrict__ c, int64_t nc, int64_t num_rows,
+                                 int32_t* __restrict__ flag) {
+  bool bad = false;
+  const int64_t total = na + nb + nc;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t id = i < na ? a[i] : (i < na + nb ? b[i - na] : c[i - na - nb]);
+    bad = bad || id < 0 || id >= num_rows;
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
 // Batch preparation, one sort for three: element i of the combined array is edge i keyed by its destination
 // (segment 0), node i - E keyed by its item id (segment 1), or loss key i - E - N (segment 2); the segment
 // number sits above the value bits, so ONE stable radix sort orders all three at once (small sorts are bound by
@@ -252,5 +266,18 @@ extern "C" int etpgt_segment_ptr(const int64_t* seg_ids, int64_t n, int64_t num_
   ETPGT_REQUIRE(n >= 0 && num_segments >= 0 && n < (int64_t(1) << 31), "segment_ptr: bad size");
   boundaries_kernel<int64_t><<<grid_for(n + 1, kThreads, 8), kThreads, 0, stream>>>(seg_ids, n, num_segments, ptr);
   ETPGT_CHECK_LAUNCH("boundaries(segment_ptr)");
+  return ETPGT_OK;
+}
+
+extern "C" int etpgt_ids_check(const int64_t* a, int64_t na, const int64_t* b, int64_t nb, const int64_t* c,
+                               int64_t nc, int64_t num_rows, int32_t* flag, etpgt_stream_t stream) {
+  ETPGT_REQUIRE(na >= 0 && nb >= 0 && nc >= 0 && (na == 0 || a) && (nb == 0 || b) && (nc == 0 || c) && flag &&
+                    num_rows >= 0,
+                "ids_check: bad arguments");
+  const int64_t total = na + nb + nc;
+  if (total == 0) return ETPGT_OK;
+  ids_check_kernel<<<grid_for(total, kThreads * 4, 4), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      a, na, b, nb, c, nc, num_rows, flag);
+  ETPGT_CHECK_LAUNCH("ids_check");
   return ETPGT_OK;
 }

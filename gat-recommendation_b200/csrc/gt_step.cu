@@ -215,6 +215,8 @@ extern "C" int etpgt_gt_step_run(const etpgt_gt_step_t* sp, int phase_begin, int
       if (s.distributed) {
         fill_tail_kernel<<<1, 32, 0, stream>>>(fwd_sums(l) + 2 * dim, (double)n, nullptr, 0.f);
         ETPGT_CHECK_LAUNCH("gt_step count");
+        // peer memory: the exchange is one kernel of this stream instead of a phase cut + host collective
+        if (s.comm) TRY(etpgt_comm_allreduce_f64(s.comm, fwd_sums(l), fwd_sums(l), sums_len, stream_));
       }
     }
     return ETPGT_OK;
@@ -245,8 +247,12 @@ extern "C" int etpgt_gt_step_run(const etpgt_gt_step_t* sp, int phase_begin, int
     if (s.training && s.distributed) {
       fill_tail_kernel<<<1, 32, 0, stream>>>(B.local + 2 * dim, (double)n, nullptr, 0.f);
       ETPGT_CHECK_LAUNCH("gt_step count");
-      copy_doubles_kernel<<<(sums_len + 255) / 256, 256, 0, stream>>>(bwd_sums(l), B.local, sums_len);
-      ETPGT_CHECK_LAUNCH("gt_step sums copy");
+      if (s.comm) {
+        TRY(etpgt_comm_allreduce_f64(s.comm, B.local, bwd_sums(l), sums_len, stream_));
+      } else {
+        copy_doubles_kernel<<<(sums_len + 255) / 256, 256, 0, stream>>>(bwd_sums(l), B.local, sums_len);
+        ETPGT_CHECK_LAUNCH("gt_step sums copy");
+      }
     }
     return ETPGT_OK;
   };

@@ -15,7 +15,7 @@
 //
 // HBM-bound: 4 reads + 3 (4 with zero_grad) writes of 4 bytes per element; float4 accesses, chunked
 // multi-tensor launch (one CTA = one 4,096-element chunk of one tensor).
-#include "common.cuh"
+#include "peer.cuh"
 
 namespace etpgt {
 namespace {
@@ -96,6 +96,70 @@ adam_step_kernel(const __grid_constant__ AdamArgs a, const AdamScalars s) {
   }
 }
 
+// Data parallelism over peer memory: reduce-scatter + AdamW + all-gather of the item table as ONE kernel.
+// Rank `c.rank` owns the float4 range [begin4, end4) of the [rows, dim] table.  Per element it
+//   * pulls that element of every rank's gradient buffer over NVLink and adds them in rank order (the
+//     reduce-scatter; deterministic, so any owner would compute the same sum),
+//   * applies the dense AdamW / Adam update with its own moments (only the owner keeps them current),
+//   * pushes the new parameter value into every rank's copy of the table (the all-gather).
+// Inbound (gradients) and outbound (parameters) traffic use opposite NVLink directions and overlap.
+// The caller brackets the kernel with two communicator barriers: gradients complete before, every copy of
+// the table complete (and every gradient buffer free to be cleared) after.
+struct DpTableArgs {
+  size_t param_offset, grad_offset;   // byte offsets of the table / its gradient inside every region
+  float *exp_avg, *exp_avg_sq;        // this rank's moments, [rows, dim] (only the owned rows are touched)
+  int64_t begin4, end4;
+};
+
+__global__ void __launch_bounds__(kThreads)
+dp_adam_table_kernel(const __grid_constant__ CommView c, const DpTableArgs a, const AdamScalars s) {
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  float4* __restrict__ m4 = reinterpret_cast<float4*>(a.exp_avg);
+  float4* __restrict__ v4 = reinterpret_cast<float4*>(a.exp_avg_sq);
+  const float4* p_own = reinterpret_cast<const float4*>(c.base[c.rank] + a.param_offset);
+  for (int64_t i = a.begin4 + blockIdx.x * (int64_t)kThreads + threadIdx.x; i < a.end4; i += stride) {
+    float4 g[kMaxRanks];
+#pragma unroll
+    for (int r = 0; r < kMaxRanks; ++r)
+      if (r < c.world) g[r] = __ldcg(reinterpret_cast<const float4*>(c.base[r] + a.grad_offset) + i);
+    float4 P = p_own[i], M = m4[i], V = v4[i];
+    float4 G = g[0];
+#pragma unroll
+    for (int r = 1; r < kMaxRanks; ++r)
+      if (r < c.world) G = add4(G, g[r]);
+    adam_one(P.x, G.x, M.x, V.x, s);
+    adam_one(P.y, G.y, M.y, V.y, s);
+    adam_one(P.z, G.z, M.z, V.z, s);
+    adam_one(P.w, G.w, M.w, V.w, s);
+#pragma unroll
+    for (int r = 0; r < kMaxRanks; ++r)
+      if (r < c.world) reinterpret_cast<float4*>(c.base[r] + a.param_offset)[i] = P;
+    m4[i] = M;
+    v4[i] = V;
+  }
+  __threadfence_system();   // the pushed rows are visible to the peers before this rank enters the barrier
+}
+
+bool fill_scalars(AdamScalars& s, double lr, double beta1, double beta2, double eps, double weight_decay,
+                  int decoupled, int64_t step, int zero_grad) {
+  // hyper-parameters arrive as doubles (Python floats in torch) and are rounded to fp32 only where
+  // torch rounds them: 1 - beta is formed in double first
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
+  s.decay = (float)(decoupled ? 1.0 - lr * weight_decay : weight_decay);
+  s.one_minus_b1 = (float)(1.0 - beta1);
+  s.b2 = (float)beta2;
+  s.one_minus_b2 = (float)(1.0 - beta2);
+  s.step_size = (float)(lr / bc1);
+  s.bc2_sqrt = (float)sqrt(bc2);
+  s.b1 = (float)beta1;
+  s.lerp_low = (1.0 - beta1) < 0.5;
+  s.eps = (float)eps;
+  s.decoupled = decoupled != 0;
+  s.zero_grad = zero_grad != 0;
+  return true;
+}
+
 }  // namespace
 }  // namespace etpgt
 
@@ -117,21 +181,7 @@ extern "C" int etpgt_adam_step(const etpgt_adam_tensor* tensors, int count, doub
   for (int i = 0; i < count; ++i)
     ETPGT_REQUIRE(tensors[i].numel < (int64_t(1) << 40), "adam_step: tensor %d too large", i);
   AdamScalars s;
-  // hyper-parameters arrive as doubles (Python floats in torch) and are rounded to fp32 only where
-  // torch rounds them: 1 - beta is formed in double first
-  const double bc1 = 1.0 - pow(beta1, (double)step);
-  const double bc2 = 1.0 - pow(beta2, (double)step);
-  s.decay = (float)(decoupled ? 1.0 - lr * weight_decay : weight_decay);
-  s.one_minus_b1 = (float)(1.0 - beta1);
-  s.b2 = (float)beta2;
-  s.one_minus_b2 = (float)(1.0 - beta2);
-  s.step_size = (float)(lr / bc1);
-  s.bc2_sqrt = (float)sqrt(bc2);
-  s.b1 = (float)beta1;
-  s.lerp_low = (1.0 - beta1) < 0.5;
-  s.eps = (float)eps;
-  s.decoupled = decoupled != 0;
-  s.zero_grad = zero_grad != 0;
+  fill_scalars(s, lr, beta1, beta2, eps, weight_decay, decoupled, step, zero_grad);
   int done = 0;
   while (done < count) {
     AdamArgs a;
@@ -156,5 +206,37 @@ extern "C" int etpgt_adam_step(const etpgt_adam_tensor* tensors, int count, doub
     adam_step_kernel<<<blocks, kThreads, 0, stream>>>(a, s);
     ETPGT_CHECK_LAUNCH("adam_step");
   }
+  return ETPGT_OK;
+}
+
+extern "C" int etpgt_dp_adam_table(const etpgt_comm_t* comm, size_t param_offset, size_t grad_offset, float* exp_avg,
+                                   float* exp_avg_sq, int64_t rows, int dim, int64_t row_begin, int64_t row_end,
+                                   double lr, double beta1, double beta2, double eps, double weight_decay,
+                                   int decoupled, int64_t step, etpgt_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ETPGT_REQUIRE(comm != nullptr, "dp_adam_table: null communicator");
+  const CommView c = comm_view(comm);
+  for (int r = 0; r < c.world; ++r) ETPGT_REQUIRE(c.base[r] != nullptr, "dp_adam_table: communicator not connected");
+  ETPGT_REQUIRE(rows >= 0 && dim >= 4 && dim % 4 == 0 && row_begin >= 0 && row_begin <= row_end && row_end <= rows,
+                "dp_adam_table: bad shape (rows %lld, dim %d, shard [%lld, %lld))", (long long)rows, dim,
+                (long long)row_begin, (long long)row_end);
+  ETPGT_REQUIRE(param_offset % 16 == 0 && grad_offset % 16 == 0 && exp_avg && exp_avg_sq &&
+                    (((uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0,
+                "dp_adam_table: buffers must be 16-byte aligned");
+  ETPGT_REQUIRE(step >= 1 && beta1 >= 0.0 && beta1 < 1.0 && beta2 >= 0.0 && beta2 < 1.0 && eps >= 0.0 && lr >= 0.0 &&
+                    weight_decay >= 0.0,
+                "dp_adam_table: hyper-parameters out of range");
+  if (row_begin == row_end) return ETPGT_OK;
+  AdamScalars s;
+  fill_scalars(s, lr, beta1, beta2, eps, weight_decay, decoupled, step, 0);
+  DpTableArgs a;
+  a.param_offset = param_offset;
+  a.grad_offset = grad_offset;
+  a.exp_avg = exp_avg;
+  a.exp_avg_sq = exp_avg_sq;
+  a.begin4 = row_begin * (dim / 4);
+  a.end4 = row_end * (dim / 4);
+  dp_adam_table_kernel<<<grid_for(a.end4 - a.begin4, kThreads * 2, 8), kThreads, 0, stream>>>(c, a, s);
+  ETPGT_CHECK_LAUNCH("dp_adam_table");
   return ETPGT_OK;
 }

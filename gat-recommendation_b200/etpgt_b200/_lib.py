@@ -93,6 +93,20 @@ _PROTOTYPES = {
     "etpgt_gt_step_num_phases": (I, [P]),
     "etpgt_gt_step_run": (I, [P, I, I, P]),
     "etpgt_adam_step": (I, [P, I, D, D, D, D, D, I, L, I, P]),
+    "etpgt_ids_check": (I, [P, L, P, L, P, L, L, P, P]),
+    "etpgt_comm_control_bytes": (Z, []),
+    "etpgt_comm_create": (I, [I, I, Z, P]),
+    "etpgt_comm_ipc_handle": (I, [P, P]),
+    "etpgt_comm_connect_ipc": (I, [P, P]),
+    "etpgt_comm_connect_ptrs": (I, [P, P]),
+    "etpgt_comm_region": (P, [P, I]),
+    "etpgt_comm_set_timeout": (I, [P, D]),
+    "etpgt_comm_destroy": (I, [P]),
+    "etpgt_comm_barrier": (I, [P, P]),
+    "etpgt_comm_allreduce_f64": (I, [P, P, P, I, P]),
+    "etpgt_comm_sum_f32": (I, [P, Z, L, P, P]),
+    "etpgt_comm_status": (I, [P, P]),
+    "etpgt_dp_adam_table": (I, [P, Z, Z, P, P, L, I, L, L, D, D, D, D, D, I, L, P]),
 }
 
 _lib = None

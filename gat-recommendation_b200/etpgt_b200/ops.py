@@ -236,12 +236,39 @@ def prepare_batch(batch, num_items: int | None = None) -> PreparedBatch:
         _register_plan(nodes, batch.x)
         if loss is not None:
             _register_plan(loss, batch.target_item, batch.negative_items)
+        # ids index the table (and its gradient buffer) raw: flag anything outside [0, num_items)
+        call("etpgt_ids_check", ptr(ids), n, ptr(targets) if plan_loss else None, b,
+             ptr(negatives) if plan_loss else None, b * num_neg, int(num_items), ptr(_bad_ids_flag(dev)), stream())
     try:
         object.__setattr__(batch, "_etpgt_index", (batch.edge_index, prepared.index))
         object.__setattr__(batch, "_etpgt_prepared", prepared)   # keeps the plans alive with the batch
     except Exception:
         pass
     return prepared
+
+
+_BAD_IDS: dict = {}
+
+
+def _bad_ids_flag(device) -> torch.Tensor:
+    """Sticky device flag (int32[1]) set by etpgt_ids_check when a prepared batch held an item id outside the
+    table."""
+    key = torch.device(device).index or 0
+    flag = _BAD_IDS.get(key)
+    if flag is None:
+        flag = _BAD_IDS[key] = torch.zeros(1, dtype=torch.int32, device=device)
+    return flag
+
+
+def check_item_ids(device="cuda") -> None:
+    """Raises IndexError (what the reference's nn.Embedding raises, etpgt/model/base.py:36) if any batch prepared
+    on `device` since the last call held an item id outside [0, num_items).  One host read; trainers call it once
+    per epoch, loaders validate their CSV ids up front."""
+    flag = _BAD_IDS.get(torch.device(device).index or 0)
+    if flag is not None and int(flag.item()):
+        flag.zero_()
+        raise IndexError("index out of range in self: a batch holds item ids outside [0, num_items) "
+                         "(e.g. a validation file with items the model was not sized for)")
 
 
 # ------------------------------------------------------------------------------ embedding + PE

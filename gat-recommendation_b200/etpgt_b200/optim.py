@@ -12,6 +12,11 @@ the optimizer owns a zero-initialised gradient buffer that the path's backward k
 into directly (ops.EmbedPE / ops.SampledLoss look the buffer up by the table's storage address), and
 the step kernel clears it while it updates the parameter.  That removes, per step, two 84 MB memsets,
 the 3 x 84 MB add that autograd needs to sum the two table gradients, and a separate zero_grad pass.
+
+Data parallelism over peer memory (`parallel.PeerDataParallel`, created BEFORE the optimizer): the sink is the
+gradient buffer inside this rank's peer region, and `step()` runs the whole gradient exchange itself —
+barrier, dense-gradient sum over the peers, the table's reduce-scatter + AdamW + all-gather as one kernel
+(`etpgt_dp_adam_table`), barrier — so no `allreduce_gradients` call and no NCCL collective is on the step.
 """
 
 from __future__ import annotations
@@ -45,6 +50,16 @@ def grad_sink_for(table: torch.Tensor):
         _GRAD_SINKS.pop(table.data_ptr(), None)
         return None
     owner_opt = owner()
+    if param.grad is None:
+        # `model.zero_grad()` / `table.grad = None` detached the buffer: its contents were "cleared" by that call,
+        # and the next backward must find it attached again or the table would silently stop training
+        if owner_opt is None or owner_opt._dirty:
+            buf.zero_()
+        param.grad = buf
+    elif param.grad is not buf:
+        # somebody installed a gradient of their own: accumulate there through autograd, not into the sink
+        _GRAD_SINKS.pop(table.data_ptr(), None)
+        return None
     if owner_opt is not None:
         owner_opt._dirty = True
     return buf
@@ -65,6 +80,7 @@ class _DeviceAdam(torch.optim.Optimizer):
         self._sinks: list[torch.nn.Parameter] = []
         self._plan_key = None
         self._plan = None
+        self._peer = None          # parallel.PeerDataParallel owning the item table, if any
         if grad_sinks:
             for group in self.param_groups:
                 for p in group["params"]:
@@ -74,7 +90,13 @@ class _DeviceAdam(torch.optim.Optimizer):
 
     # ------------------------------------------------------------------ gradient sinks
     def _install_sink(self, p):
-        buf = torch.zeros_like(p)
+        from .parallel import peer_for
+
+        peer = peer_for(p)
+        if peer is not None:       # the gradient buffer inside the peer region: the other ranks read it
+            buf, self._peer = peer.table_grad, peer
+        else:
+            buf = torch.zeros_like(p)
         p.grad = buf
         _GRAD_SINKS[p.data_ptr()] = (weakref.ref(p), buf, weakref.ref(self))
         self._sinks.append(p)
@@ -127,9 +149,40 @@ class _DeviceAdam(torch.optim.Optimizer):
         self._dirty = False
         return loss
 
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._plan_key = None      # the moment tensors were replaced: the cached launch plan holds freed pointers
+
+    def add_param_group(self, param_group):
+        super().add_param_group(param_group)
+        self._plan_key = None
+
     def _launch(self, group, step_no, plist):
+        beta1, beta2 = group["betas"]
+        peer = self._peer
+        if peer is not None and peer.world > 1:
+            # data parallelism over peer memory: the gradient exchange is part of the step
+            reduced = peer.exchange_dense()
+            rest = []
+            for p in plist:
+                if p.data_ptr() == peer.table.data_ptr():
+                    st = self.state[p]
+                    peer.update_table(st["exp_avg"], st["exp_avg_sq"], group["lr"], beta1, beta2, group["eps"],
+                                      group["weight_decay"], self._decoupled, step_no)
+                else:
+                    rest.append(p)
+            peer.end_exchange()
+            plist = rest
+            if not plist:
+                return
+            if not reduced:    # gradients from the per-operator autograd path: not in the peer region
+                from .parallel import allreduce_gradients
+
+                allreduce_gradients(plist, group=peer.group)
         grads = [p.grad if p.grad.is_contiguous() else p.grad.contiguous() for p in plist]
-        key = tuple((p.data_ptr(), g.data_ptr()) for p, g in zip(plist, grads))
+        # the plan holds raw pointers of the moments too: load_state_dict / restore-best replace those tensors
+        key = tuple((p.data_ptr(), g.data_ptr(), self.state[p]["exp_avg"].data_ptr(),
+                     self.state[p]["exp_avg_sq"].data_ptr()) for p, g in zip(plist, grads))
         if key != self._plan_key:
             plain, sinks = [], []
             for p, g in zip(plist, grads):
@@ -143,7 +196,6 @@ class _DeviceAdam(torch.optim.Optimizer):
             self._plan = ((_AdamTensor * max(len(plain), 1))(*plain), len(plain),
                           (_AdamTensor * max(len(sinks), 1))(*sinks), len(sinks))
         arr_plain, n_plain, arr_sink, n_sink = self._plan
-        beta1, beta2 = group["betas"]
         common = (float(group["lr"]), float(beta1), float(beta2), float(group["eps"]), float(group["weight_decay"]),
                   int(self._decoupled), int(step_no))
         # the sink gradients are cleared by the kernel (zero_grad flag); the others are released by

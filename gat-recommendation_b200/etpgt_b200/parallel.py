@@ -3,10 +3,15 @@
 
   * sessions are independent graph components -> contiguous session ranges per rank, balanced by
     a (nodes + edges)-like cost prefix sum, no data-path collective for the graph kernels;
-  * the only couplings are (a) BatchNorm statistics — all-reduced inside ops.BatchNormRows
-    (2*dim doubles per layer and direction) so whole-batch semantics are kept, (b) the loss mean
-    over the GLOBAL batch, (c) the parameter gradients — two flat all-reduces (dense parameters,
-    item table);
+  * the only couplings are (a) BatchNorm statistics (2*dim+1 doubles per layer and direction, so
+    whole-batch semantics are kept), (b) the loss mean over the GLOBAL batch, (c) the parameter
+    gradients (dense parameters, item table).  With `enable_data_parallel(model)` (PeerDataParallel) all
+    three run as kernels of this library over peer memory — every rank maps every peer's region (CUDA IPC)
+    and the BatchNorm sums, the dense-gradient sum and the table's reduce-scatter + AdamW + all-gather are
+    loads / stores over NVLink ordered by system-scope flags (csrc/peer.cu, csrc/optim.cu), the training step
+    stays ONE host call.  `enable_global_batch_norm` + `allreduce_gradients` is the plain NCCL variant
+    (all-reduces between the phases of the step driver, replicated optimizer), kept as the comparison point
+    and for the per-operator autograd path;
   * evaluation shards the item table by contiguous id ranges: every rank scores all sessions
     against its shard with the fused top-k kernel, candidates are all-gathered and merged exactly
     (score desc, id asc), so the result is identical for any GPU count.
@@ -14,9 +19,15 @@
 
 from __future__ import annotations
 
+import ctypes
+import weakref
+
 import numpy as np
 import torch
 import torch.distributed as dist
+
+from . import _lib
+from ._lib import stream
 
 
 def world() -> tuple[int, int]:
@@ -105,3 +116,251 @@ def sharded_predict(model, session_embeddings: torch.Tensor, k: int = 20, group=
     cand_v = torch.cat([v[mine] for v in vals], dim=1).contiguous()
     cand_i = torch.cat([i[mine] for i in idxs], dim=1).contiguous()
     return ops.topk_merge(cand_v, cand_i, k)[1]
+
+
+# ------------------------------------------------------------------------------ peer memory
+
+
+class _RawDeviceMemory:
+    """`nbytes` of device memory at `address` for torch.as_tensor (CUDA array interface); `owner` is kept alive."""
+
+    def __init__(self, address: int, nbytes: int, owner):
+        self.owner = owner
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(address), False),
+                                         "version": 2}
+
+
+class PeerComm:
+    """One rank's end of the peer-memory communicator (include/etpgt_b200.h, `etpgt_comm_*`): a device region
+    that every peer maps, a barrier, a small fp64 all-reduce and a sum over the peers' fp32 buffers.
+
+    `PeerComm(region_bytes, group=...)` is collective over the torch.distributed group (handles travel through
+    `all_gather_object`; the data path never touches torch.distributed).  `PeerComm.local_group(world, bytes)`
+    builds `world` ranks inside ONE process on the current device (plain pointers, no IPC) — every kernel
+    behaves as across GPUs, which is how the single-GPU tests cover the protocol."""
+
+    def __init__(self, region_bytes: int, group=None, rank: int | None = None, world: int | None = None,
+                 connect: bool = True):
+        if rank is None:
+            if dist.is_available() and dist.is_initialized():
+                rank, world = dist.get_rank(group), dist.get_world_size(group)
+            else:
+                rank, world = 0, 1
+        self.rank, self.world, self.group = int(rank), int(world), group
+        self.control_bytes = int(_lib.size("etpgt_comm_control_bytes"))
+        self.region_bytes = max(int(region_bytes), self.control_bytes)
+        handle = ctypes.c_void_p()
+        _lib.call("etpgt_comm_create", self.rank, self.world, self.region_bytes, ctypes.byref(handle))
+        self.handle = handle
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self._finalizer = weakref.finalize(self, _lib.load().etpgt_comm_destroy, handle)
+        if connect:
+            self._connect_ipc()
+
+    def _connect_ipc(self) -> None:
+        if self.world == 1:
+            return
+        mine = (ctypes.c_ubyte * 64)()
+        _lib.call("etpgt_comm_ipc_handle", self.handle, mine)
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, bytes(mine), group=self.group)
+        _lib.call("etpgt_comm_connect_ipc", self.handle, b"".join(gathered))
+        dist.barrier(group=self.group)      # every rank has mapped every region before anyone writes to a peer
+
+    @classmethod
+    def local_group(cls, world: int, region_bytes: int) -> list["PeerComm"]:
+        comms = [cls(region_bytes, rank=r, world=world, connect=False) for r in range(world)]
+        bases = (ctypes.c_void_p * world)(*[c.base(c.rank) for c in comms])
+        for c in comms:
+            _lib.call("etpgt_comm_connect_ptrs", c.handle, bases)
+        return comms
+
+    def base(self, rank: int | None = None) -> int:
+        """Address (in this process) of `rank`'s region."""
+        return int(_lib.load().etpgt_comm_region(self.handle, self.rank if rank is None else rank) or 0)
+
+    def tensor(self, offset: int, shape, dtype=torch.float32, rank: int | None = None) -> torch.Tensor:
+        """A tensor over [offset, offset + bytes) of `rank`'s region (default: this rank's own)."""
+        shape = tuple(int(v) for v in (shape if isinstance(shape, (tuple, list, torch.Size)) else (shape,)))
+        nbytes = int(np.prod(shape, dtype=np.int64)) * torch.empty(0, dtype=dtype).element_size()
+        if offset < self.control_bytes or offset % 256 or offset + nbytes > self.region_bytes:
+            raise ValueError(f"peer region: [{offset}, {offset + nbytes}) is outside the caller's part of the region")
+        raw = torch.as_tensor(_RawDeviceMemory(self.base(rank) + offset, max(nbytes, 1), self), device=self.device)
+        return raw[:nbytes].view(dtype).view(shape)
+
+    def barrier(self) -> None:
+        _lib.call("etpgt_comm_barrier", self.handle, stream())
+
+    def allreduce_f64(self, inp: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        out = inp if out is None else out
+        _lib.call("etpgt_comm_allreduce_f64", self.handle, _lib.ptr(inp), _lib.ptr(out), inp.numel(), stream())
+        return out
+
+    def sum_f32(self, offset: int, numel: int, out: torch.Tensor) -> torch.Tensor:
+        _lib.call("etpgt_comm_sum_f32", self.handle, int(offset), int(numel), _lib.ptr(out), stream())
+        return out
+
+    def set_timeout(self, seconds: float) -> None:
+        _lib.call("etpgt_comm_set_timeout", self.handle, float(seconds))
+
+    def status(self) -> int:
+        """0, or the code of a wait that gave up (1 barrier, 2 all-reduce).  Synchronises the device."""
+        value = ctypes.c_int(0)
+        _lib.call("etpgt_comm_status", self.handle, ctypes.byref(value))
+        return int(value.value)
+
+    def check(self) -> None:
+        code = self.status()
+        if code:
+            raise RuntimeError(f"etpgt_b200 peer communicator: a wait for a peer timed out (code {code}); "
+                               "results of this step are invalid")
+
+
+# item table storage address -> weak reference to the PeerDataParallel that owns it
+_PEERS: dict[int, "weakref.ReferenceType[PeerDataParallel]"] = {}
+
+
+def peer_for(table: torch.Tensor):
+    """The PeerDataParallel whose region holds `table` (a parameter or its data), or None."""
+    ref = _PEERS.get(table.data_ptr())
+    peer = ref() if ref is not None else None
+    if peer is None or peer.table.data_ptr() != table.data_ptr():
+        return None
+    return peer
+
+
+def _align(n: int, a: int = 256) -> int:
+    return (int(n) + a - 1) // a * a
+
+
+class PeerDataParallel:
+    """Data-parallel state of one model replica with the exchanges over peer memory.
+
+    Re-homes the item table into this rank's region (peers WRITE updated rows into it), and places the table's
+    gradient buffer and the flat dense-gradient buffer of the step driver there as well (peers READ them).
+    Create it BEFORE the optimizer (etpgt_b200.optim picks the region's gradient buffer up as its sink) and do
+    not move the model afterwards.  Per step:
+
+        losses = fused(batch, total_sessions=global_batch)   # ONE host call; BatchNorm sums exchanged in-kernel
+        optimizer.step()    # barrier | dense-gradient sum | table reduce-scatter+AdamW+all-gather | barrier
+
+    Every rank owns the contiguous row range `item_shard(num_items, rank, world)` of the table: it keeps those
+    rows' AdamW moments current (`gather_optimizer_state` collects them for a checkpoint)."""
+
+    def __init__(self, model, group=None, comm: PeerComm | None = None, broadcast: bool = True):
+        table = model.item_embedding.weight
+        if not table.is_cuda or table.dtype != torch.float32:
+            raise RuntimeError("PeerDataParallel needs a CUDA fp32 model (no CPU fallback)")
+        self.dense = [p for p in model.parameters() if p is not table]
+        dense_numel = sum(p.numel() for p in self.dense)
+        control = int(_lib.size("etpgt_comm_control_bytes"))
+        self.flat_offset = control
+        self.grad_offset = self.flat_offset + _align(4 * dense_numel)
+        self.param_offset = self.grad_offset + _align(4 * table.numel())
+        total = self.param_offset + _align(4 * table.numel())
+        self.comm = comm if comm is not None else PeerComm(total, group=group)
+        if self.comm.region_bytes < total:
+            raise ValueError(f"peer region of {self.comm.region_bytes} bytes < {total} needed for this model")
+        self.rank, self.world, self.group = self.comm.rank, self.comm.world, group
+        self.table = self.comm.tensor(self.param_offset, table.shape)
+        with torch.no_grad():
+            self.table.copy_(table.data)
+            table.data = self.table
+        self.table_grad = self.comm.tensor(self.grad_offset, table.shape).zero_()
+        self.flat = self.comm.tensor(self.flat_offset, (max(dense_numel, 1),)).zero_()
+        self.flat_reduced = torch.zeros(max(dense_numel, 1), dtype=torch.float32, device=table.device)
+        self.flat_numel = 0            # elements of `flat` the step driver fills (set by FusedTrainStep)
+        self.flat_dirty = False        # the driver wrote local gradients that are not summed yet
+        self.rows = item_shard(table.size(0), self.rank, self.world)
+        self.num_items, self.dim = int(table.size(0)), int(table.size(1))
+        _PEERS[self.table.data_ptr()] = weakref.ref(self)
+        model._etpgt_peer = self
+        ready = dist.is_available() and dist.is_initialized()
+        if ready and self.world > 1:
+            model.bn_process_group = group if group is not None else dist.group.WORLD
+            if broadcast:
+                for t in list(model.parameters()) + list(model.buffers()):
+                    dist.broadcast(t.data, dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        torch.cuda.current_stream().synchronize()
+        if ready and self.world > 1:
+            dist.barrier(group=group)
+
+    # ------------------------------------------------------------------ the exchanges
+    def exchange_dense(self) -> bool:
+        """Dense gradients: barrier (every rank's backward is complete), then flat_reduced = sum over ranks of
+        their flat buffers, in rank order.  The parameters' .grad are views of flat_reduced.  Returns False when
+        the step driver did not fill the flat buffer (per-operator autograd path: the caller reduces those
+        gradients through torch.distributed)."""
+        if getattr(self, "_entered", False):     # allreduce_gradients() already ran for this step
+            return self._reduced
+        self.comm.barrier()
+        self._reduced = bool(self.flat_dirty and self.flat_numel)
+        if self._reduced:
+            self.comm.sum_f32(self.flat_offset, self.flat_numel, self.flat_reduced)
+        self.flat_dirty = False
+        self._entered = True
+        return self._reduced
+
+    def update_table(self, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, decoupled, step) -> None:
+        """Reduce-scatter + AdamW + all-gather of the table (etpgt_dp_adam_table) between two barriers, then the
+        local gradient buffer is cleared (every peer has read its rows by then)."""
+        if not getattr(self, "_entered", False):
+            self.comm.barrier()
+        lo, hi = self.rows
+        _lib.call("etpgt_dp_adam_table", self.comm.handle, self.param_offset, self.grad_offset, _lib.ptr(exp_avg),
+                  _lib.ptr(exp_avg_sq), self.num_items, self.dim, lo, hi, float(lr), float(beta1), float(beta2),
+                  float(eps), float(weight_decay), int(decoupled), int(step), stream())
+        self.comm.barrier()
+        self.table_grad.zero_()
+
+    def end_exchange(self) -> None:
+        """The optimizer step that consumed this exchange is queued: the next exchange_dense() starts a new one."""
+        self._entered = False
+
+    def reduced_table_gradient(self) -> torch.Tensor:
+        """The summed table gradient as a fresh tensor (diagnostics / tests; the training path never forms it)."""
+        out = torch.empty(self.num_items, self.dim, dtype=torch.float32, device=self.table.device)
+        self.comm.barrier()
+        self.comm.sum_f32(self.grad_offset, self.num_items * self.dim, out)
+        self.comm.barrier()
+        return out
+
+    def gather_optimizer_state(self, optimizer) -> None:
+        """Collects the table's AdamW moments (each rank keeps only its own rows current) into the full tensors
+        of every rank's optimizer state, so that `optimizer.state_dict()` is a complete checkpoint.  Collective."""
+        if self.world == 1 or not (dist.is_available() and dist.is_initialized()):
+            return
+        state = optimizer.state.get(_parameter_of(optimizer, self.table))
+        if not state:
+            return
+        per = (self.num_items + self.world - 1) // self.world
+        for name in ("exp_avg", "exp_avg_sq"):
+            full = state[name]
+            padded = torch.zeros(per * self.world, self.dim, dtype=full.dtype, device=full.device)
+            lo, hi = self.rows
+            dist.all_gather_into_tensor(padded, torch.nn.functional.pad(full[lo:hi], (0, 0, 0, per - (hi - lo))),
+                                        group=self.group)
+            full.copy_(padded[: self.num_items])
+
+
+def _parameter_of(optimizer, data: torch.Tensor):
+    for group in optimizer.param_groups:
+        for p in group["params"]:
+            if p.data_ptr() == data.data_ptr():
+                return p
+    return None
+
+
+def enable_data_parallel(model, group=None, exchange: str = "peer", broadcast: bool = True):
+    """Makes `model` one replica of a session-batch data-parallel job.  exchange="peer": the exchanges run over
+    peer memory (returns the PeerDataParallel); exchange="nccl": BatchNorm sums and gradients go through
+    torch.distributed all-reduces (returns None).  Call before creating the optimizer."""
+    if exchange == "peer":
+        return PeerDataParallel(model, group=group, broadcast=broadcast)
+    if exchange != "nccl":
+        raise ValueError(f"Unknown exchange: {exchange}")
+    enable_global_batch_norm(model, group)
+    if broadcast and dist.is_available() and dist.is_initialized():
+        for t in list(model.parameters()) + list(model.buffers()):
+            dist.broadcast(t.data, dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    return None

@@ -56,7 +56,7 @@ class _GtStep(ctypes.Structure):
         + [("total_sessions", c_double), ("alpha_p", c_double), ("drop_p", c_double)]
         + [(name, c_void_p) for name in ("table", "pe", "w_pe", "b_pe", "d_table", "d_w_pe", "d_b_pe")]
         + [("layer", _GtLayer * MAX_LAYERS)]
-        + [("sess", c_void_p), ("losses", c_void_p), ("bn_sums", c_void_p), ("arena", c_void_p),
+        + [("sess", c_void_p), ("losses", c_void_p), ("bn_sums", c_void_p), ("comm", c_void_p), ("arena", c_void_p),
            ("arena_bytes", c_size_t)])
 
 
@@ -143,19 +143,31 @@ class FusedTrainStep:
         """One persistent flat fp32 buffer for every dense gradient (the driver's kernels OVERWRITE it); each
         parameter's .grad is a view of its slice, so the data-parallel all-reduce is one call on the buffer."""
         blocks = self._dense_parameters()
-        key = tuple(p.data_ptr() for block in blocks for p in block)
+        peer = self._peer()
+        key = tuple(p.data_ptr() for block in blocks for p in block) + (id(peer),)
         if key != self._flat_key:
             dev = self.model.item_embedding.weight.device
             total = sum(p.numel() for block in blocks for p in block)
-            self._flat = torch.zeros(total, dtype=torch.float32, device=dev)
+            if peer is not None:
+                # peer-memory data parallelism: the driver writes this rank's gradients into the peer region (the
+                # other ranks read them); the parameters' .grad are views of the buffer that receives the SUM
+                self._flat, shown = peer.flat[:total], peer.flat_reduced
+                peer.flat_numel = total
+            else:
+                self._flat = shown = torch.zeros(total, dtype=torch.float32, device=dev)
             self._views, self._block_ptr, offset = [], [], 0
             for block in blocks:
                 self._block_ptr.append(self._flat.data_ptr() + 4 * offset)
                 for p in block:
-                    self._views.append((p, self._flat[offset:offset + p.numel()].view_as(p)))
+                    self._views.append((p, shown[offset:offset + p.numel()].view_as(p)))
                     offset += p.numel()
             self._flat_key = key
         return self._block_ptr
+
+    def _peer(self):
+        """The PeerDataParallel of the model when its exchanges run over peer memory (world > 1), else None."""
+        peer = getattr(self.model, "_etpgt_peer", None)
+        return peer if peer is not None and peer.world > 1 else None
 
     # ------------------------------------------------------------------ the step
     def __call__(self, batch, target_items=None, negative_items=None, total_sessions=None, backward: bool = True):
@@ -175,7 +187,8 @@ class FusedTrainStep:
         n, dim = ids.numel(), model.hidden_dim
         index = ops.graph_index_of(batch, edge_index, n)
         training = model.training
-        distributed = training and ops._dist_ready(model.bn_process_group)
+        peer = self._peer()
+        distributed = training and (peer is not None or ops._dist_ready(model.bn_process_group))
         layers = len(model.convs)
         dev = ids.device
         table = model.item_embedding.weight
@@ -225,6 +238,9 @@ class FusedTrainStep:
             # gradients that were not cleared since the last backward: torch accumulates into them
             carried = [(p, p.grad.clone() if p.grad.data_ptr() == view.data_ptr() else p.grad)
                        for p, view in self._views if p.grad is not None]
+            if carried and peer is not None:
+                raise RuntimeError("FusedTrainStep under peer-memory data parallelism: gradients of the previous "
+                                   "step are still set; call optimizer.zero_grad() before every step")
             sink = ops._grad_sink(table)
             if sink is None:
                 if table.grad is None:
@@ -263,6 +279,7 @@ class FusedTrainStep:
         losses = torch.empty(3, dtype=torch.float32, device=dev)
         bn_sums = torch.empty(2 * layers, 2 * dim + 1, dtype=torch.float64, device=dev)
         d.sess, d.losses, d.bn_sums = sess.data_ptr(), losses.data_ptr(), bn_sums.data_ptr()
+        d.comm = peer.comm.handle if (peer is not None and distributed) else None
         lib = _lib.load()
         d.arena, d.arena_bytes = None, 0
         arena_bytes = int(lib.etpgt_gt_step_arena_bytes(ctypes.byref(d)))
@@ -284,8 +301,11 @@ class FusedTrainStep:
         if self._table_work is not None:     # a previous step's table all-reduce nobody joined
             self._table_work.wait()
         self._table_work = None
-        if not distributed:
+        if not distributed or peer is not None:
+            # one host call; under peer-memory data parallelism the driver exchanges the BatchNorm sums itself
             _lib.call("etpgt_gt_step_run", ctypes.byref(d), 0, phases, stream())
+            if peer is not None and backward:
+                peer.flat_dirty = True
         else:
             group = model.bn_process_group or None
             last = phases if backward else layers + 1
@@ -310,6 +330,12 @@ class FusedTrainStep:
         """Data parallelism: sums the dense gradients (one flat buffer) and the table gradient across ranks.
         Call it between the step and `optimizer.step()`: the table's all-reduce was started underneath the
         step's last phase and is joined here."""
+        peer = self._peer()
+        if peer is not None:
+            # barrier + dense-gradient sum over the peers (the .grad views then show the global-batch gradient);
+            # the table's reduce-scatter + update + all-gather is one kernel inside optimizer.step()
+            peer.exchange_dense()
+            return
         if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
             return
         dist.all_reduce(self._flat, group=group)

@@ -416,6 +416,13 @@ int etpgt_scatter_plan_loss(const int64_t* targets, const int64_t* negatives, in
 int etpgt_scatter_rows_planned(const int32_t* sorted_key, const int32_t* perm, const float* coef,
                                const float* src, int64_t m, int src_div, int dim, int64_t skip_key,
                                float* d_table, etpgt_stream_t stream);
+/* Item ids index the table and its gradient buffer raw (the reference's nn.Embedding raises IndexError for
+ * an id >= num_items, etpgt/model/base.py:36).  *flag |= 1 (device int32, caller-zeroed, sticky) when any id of
+ * up to three lists (node ids, targets, negatives; NULL / 0 to skip) lies outside [0, num_rows).  Asynchronous:
+ * the host reads the flag when it wants to (ops.prepare_batch runs the check per batch on the preparation stream,
+ * the trainer reads the flag once per epoch). */
+int etpgt_ids_check(const int64_t* a, int64_t na, const int64_t* b, int64_t nb, const int64_t* c, int64_t nc,
+                    int64_t num_rows, int32_t* flag, etpgt_stream_t stream);
 /* Batch preparation in one call: etpgt_csr_from_coo of (src, dst) plus the scatter plans of `ids` [N] (rows of
  * num_items) and of the loss keys ([b][0] = targets[b], [b][1 + c] = negatives[b][c]; targets == NULL skips that
  * plan), with identical outputs — but the destination sort and the two plan sorts run as ONE segmented radix sort
@@ -439,6 +446,53 @@ int etpgt_sampled_loss_bwd_planned(const float* sess, const float* table, const 
                                    const int32_t* plan_perm, float* d_sess, float* d_table, void* ws,
                                    size_t ws_bytes, etpgt_stream_t stream);
 
+/* ---- (e) multi-GPU: peer-memory communicator ----------------------------------------------------
+ * Session-batch data parallelism over one NVSwitch box (the reference trains on one GPU,
+ * etpgt/train/trainer.py:69-131).  One process per GPU; every rank owns one device *region* (cudaMalloc,
+ * zeroed control block of etpgt_comm_control_bytes() at its start, the rest is the caller's: gradient and
+ * parameter buffers that peers read / write) and maps the regions of all peers — over CUDA IPC
+ * (etpgt_comm_ipc_handle on every rank, handles exchanged by the host, etpgt_comm_connect_ipc), or by plain
+ * pointers when several ranks live in one process (etpgt_comm_connect_ptrs).  The kernels below move data
+ * with ordinary loads / stores over NVLink and order it with system-scope flags; every cross-rank sum runs in
+ * rank order on every rank, so replicas stay bit-identical.  All ranks must issue the same sequence of
+ * communicator calls, each on ONE stream.  A wait that sees no peer for the time-out (default 30 s) gives
+ * up and records it in the status word (etpgt_comm_status) instead of hanging the GPU; later waits of that rank
+ * return at once.
+ *   barrier        everything this rank issued before is complete and visible to its peers, and vice versa
+ *   allreduce_f64  out[i] = sum_r in_r[i], count <= 520 doubles (BatchNorm statistics), ONE single-CTA kernel
+ *                  (in == out allowed)
+ *   sum_f32        out[i] = sum_r region_r[offset + 4*i]: the dense-gradient exchange (callers bracket it
+ *                  with barriers: sources complete before, sources reusable after) */
+#define ETPGT_MAX_RANKS 8
+#define ETPGT_IPC_HANDLE_BYTES 64
+typedef struct etpgt_comm etpgt_comm_t;
+size_t etpgt_comm_control_bytes(void);
+int etpgt_comm_create(int rank, int world, size_t region_bytes, etpgt_comm_t** out);
+int etpgt_comm_ipc_handle(const etpgt_comm_t* comm, unsigned char* handle /* [ETPGT_IPC_HANDLE_BYTES] */);
+int etpgt_comm_connect_ipc(etpgt_comm_t* comm, const unsigned char* handles /* [world][ETPGT_IPC_HANDLE_BYTES] */);
+int etpgt_comm_connect_ptrs(etpgt_comm_t* comm, void* const* bases /* [world] */);
+void* etpgt_comm_region(const etpgt_comm_t* comm, int rank);
+int etpgt_comm_set_timeout(etpgt_comm_t* comm, double seconds);
+int etpgt_comm_destroy(etpgt_comm_t* comm);
+int etpgt_comm_barrier(const etpgt_comm_t* comm, etpgt_stream_t stream);
+int etpgt_comm_allreduce_f64(const etpgt_comm_t* comm, const double* in, double* out, int count,
+                             etpgt_stream_t stream);
+int etpgt_comm_sum_f32(const etpgt_comm_t* comm, size_t offset, int64_t numel, float* out, etpgt_stream_t stream);
+int etpgt_comm_status(const etpgt_comm_t* comm, int* status);
+/* The item table under data parallelism: reduce-scatter of its gradient + dense AdamW / Adam + all-gather of
+ * the updated rows as ONE kernel over peer memory (replaces an 84 MB / 1 GB NCCL all-reduce followed by a
+ * replicated optimizer pass; reference semantics: dense decoupled decay over every row,
+ * scripts/train/train_baseline.py:252-256).  The table [rows, dim] lives at param_offset and its gradient at
+ * grad_offset of EVERY rank's region.  This rank owns rows [row_begin, row_end): it sums those rows of all
+ * ranks' gradients (rank order), updates them with its moments exp_avg / exp_avg_sq ([rows, dim], only the
+ * owned rows are read and written) and stores the new values into every rank's table.  Arithmetic and
+ * hyper-parameters as etpgt_adam_step.  Bracket with etpgt_comm_barrier: gradients complete before; all
+ * tables complete and all gradient buffers free to be cleared after. */
+int etpgt_dp_adam_table(const etpgt_comm_t* comm, size_t param_offset, size_t grad_offset, float* exp_avg,
+                        float* exp_avg_sq, int64_t rows, int dim, int64_t row_begin, int64_t row_end, double lr,
+                        double beta1, double beta2, double eps, double weight_decay, int decoupled, int64_t step,
+                        etpgt_stream_t stream);
+
 /* ---- a11: step driver --------------------------------------------------------------------------
  * One host call for the whole training step of graph_transformer_optimized — what Trainer.train_epoch
  * (etpgt/train/trainer.py:95-127) runs between `optimizer.zero_grad()` and `optimizer.step()`:
@@ -460,7 +514,9 @@ int etpgt_sampled_loss_bwd_planned(const float* sess, const float* table, const 
  * sums of layer l (produced by phase 2*layers-1-l).  With distributed != 0 the caller all-reduces the row a
  * phase produced before running the next phase (the row's last element carries the row count); d_table is
  * complete after phase 2*layers, so its all-reduce can overlap phase 2*layers+1 (weight gradient of layer 0 and
- * the PE projection gradient).  With distributed == 0 run all phases in one call. */
+ * the PE projection gradient).  With distributed == 0 run all phases in one call.
+ * With distributed != 0 AND comm != NULL the driver exchanges the rows itself (etpgt_comm_allreduce_f64 between
+ * the statistics kernel and the apply kernel): no cuts are needed, run all phases in one call. */
 #define ETPGT_GT_MAX_LAYERS 4
 typedef struct etpgt_gt_layer {
   const float* weight;       /* [4*dim, dim] */
@@ -508,6 +564,7 @@ typedef struct etpgt_gt_step {
   float* sess;               /* [B, dim] session embeddings */
   float* losses;             /* [3] (total, listwise, bpr) */
   double* bn_sums;           /* [2*layers][2*dim+1] */
+  const etpgt_comm_t* comm;  /* peer-memory communicator for the BatchNorm exchange, or NULL */
   void* arena;
   size_t arena_bytes;        /* >= etpgt_gt_step_arena_bytes */
 } etpgt_gt_step_t;

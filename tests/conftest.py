@@ -2,8 +2,16 @@
 package directory) on sys.path.  Tests marked `gpu` are the CUDA parity tests proper and are
 skipped automatically when no device is visible."""
 
+import os
 import sys
 from pathlib import Path
+
+# tests/test_gpu_peer.py runs several data-parallel ranks inside ONE process: while rank 0's exchange kernel spins
+# on the device waiting for rank 1, the host must stay free to launch rank 1's kernels.  With lazy module loading
+# the first launch of a not-yet-loaded kernel can wait for the device to go idle — a deadlock until the exchange
+# times out — so the test process loads modules eagerly.  (One process per GPU, the production layout, has no such
+# coupling.)  Must be set before the CUDA driver is initialised.
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 
 import pytest
 

@@ -1,6 +1,10 @@
 """Data-parallel parity check on real GPUs (run under torchrun, any world size >= 1):
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/check_dp.py
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/check_dp.py [peer|nccl]
+
+`peer` (default): BatchNorm sums, dense gradients and the table's reduce-scatter + AdamW + all-gather run as this
+library's kernels over peer memory (parallel.PeerDataParallel); `nccl`: torch.distributed all-reduces between the
+phases of the step driver and a replicated optimizer.
 
 Every rank trains on its contiguous share of the same global session batches (global BatchNorm
 statistics, loss divided by the global batch, gradient all-reduce, device optimizer with the
@@ -27,6 +31,7 @@ from etpgt_b200.train.step import FusedTrainStep  # noqa: E402
 
 def main():
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    exchange = sys.argv[1] if len(sys.argv) > 1 else "peer"
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
@@ -40,7 +45,7 @@ def main():
         model = create_graph_transformer_optimized(d.num_items, 256, 256, dropout=0.0).cuda()
         model.laplacian_pe._cached_pe = torch.randn(d.num_items, 16, generator=torch.Generator().manual_seed(7)).abs().cuda()
         if dp:
-            parallel.enable_global_batch_norm(model)
+            peer = parallel.enable_data_parallel(model, exchange=exchange)     # before the optimizer
         else:
             model.bn_process_group = False
         return model, optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-5)
@@ -72,7 +77,12 @@ def main():
                 loss.backward()
             if step == 0:
                 first_grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+                peer = getattr(model, "_etpgt_peer", None)
+                if dp and peer is not None:    # the summed table gradient is never formed on the training path
+                    first_grads["item_embedding.weight"] = peer.reduced_table_gradient()
             opt.step()
+        if dp and getattr(model, "_etpgt_peer", None) is not None:
+            model._etpgt_peer.comm.check()
         return model, first_grads, loss.item()
 
     def eval_sessions(model):
@@ -103,6 +113,7 @@ def main():
             if err > 1e-5:
                 ok = False
                 print(f"MISMATCH grad {name}: {err:.3e}")
+        print(f"exchange = {exchange}")
         print(f"dp{world} vs single process: step-0 gradient, worst difference / largest gradient = {worst:.3e}")
         # (b) after `steps` optimizer steps: outputs agree (raw weights are not compared: Adam turns
         # rounding-level gradient elements into +-lr steps of arbitrary sign on either path)
