@@ -158,6 +158,73 @@ topk_metrics_kernel(const int64_t* __restrict__ top_idx, const int64_t* __restri
   if (threadIdx.x == 0) { out[0] += red[0][0]; out[1] += red[1][0]; }
 }
 
+// Item-sharded evaluation: the candidates of shard p for ALL sessions arrive as one packed block
+// (val [rows_total, k] f32 | idx [rows_total, k] i64) per rank, gathered rank-major by ONE collective; this merges
+// the rows [row_begin, row_begin + rows) straight out of that layout (no transposes / concatenations in between)
+// and, when targets are given, notes where each target sits in the merged list (-1: not in the top-k).
+__global__ void __launch_bounds__(kThreads)
+topk_merge_parts_kernel(const char* __restrict__ parts, int num_parts, size_t part_stride, size_t idx_offset, int k,
+                        int64_t row_begin, int64_t rows, float* __restrict__ top_val, int64_t* __restrict__ top_idx,
+                        const int64_t* __restrict__ targets, int32_t* __restrict__ hit_pos) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (blockIdx.x * (int64_t)kThreads + threadIdx.x) >> 5;
+  if (row >= rows) return;
+  const int64_t src = (row_begin + row) * k;
+  const int m = num_parts * k;
+  const int64_t target = targets != nullptr ? targets[row] : kNoId;
+  int found = -1;
+  float prev_v = INFINITY;
+  int64_t prev_i = -1;
+  for (int t = 0; t < k; ++t) {
+    float bv = -INFINITY;
+    int64_t bi = kNoId;
+    for (int c = lane; c < m; c += 32) {
+      const char* part = parts + (size_t)(c / k) * part_stride;
+      const float v = reinterpret_cast<const float*>(part)[src + c % k];
+      const int64_t i = reinterpret_cast<const int64_t*>(part + idx_offset)[src + c % k];
+      const bool after_prev = v < prev_v || (v == prev_v && i > prev_i);
+      if (after_prev && better(v, i, bv, bi)) { bv = v; bi = i; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+      const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, off);
+      if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { top_val[row * k + t] = bv; top_idx[row * k + t] = bi; }
+    if (found < 0 && bi == target) found = t;   // first match: metrics.py:49 argmax
+    prev_v = bv;
+    prev_i = bi;
+  }
+  if (lane == 0 && hit_pos != nullptr) hit_pos[row] = found;
+}
+
+// hit_pos[b] = position of the target in the top-k (-1: missed) -> acc[0] += #hits within k, acc[1] += sum of
+// 1/log2(pos + 2) over them (etpgt/utils/metrics.py:6-66); one CTA, fixed order: deterministic.
+__global__ void __launch_bounds__(1024)
+hit_metrics_kernel(const int32_t* __restrict__ hit_pos, int64_t batch, int k, double* __restrict__ out) {
+  __shared__ double red[2][1024];
+  double hits = 0, gain = 0;
+  for (int64_t b = threadIdx.x; b < batch; b += 1024) {
+    const int p = hit_pos[b];
+    if (p >= 0 && p < k) {
+      hits += 1.0;
+      gain += 1.0 / log2((double)p + 2.0);
+    }
+  }
+  red[0][threadIdx.x] = hits;
+  red[1][threadIdx.x] = gain;
+  __syncthreads();
+  for (int off = 512; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) {
+      red[0][threadIdx.x] += red[0][threadIdx.x + off];
+      red[1][threadIdx.x] += red[1][threadIdx.x + off];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { out[0] += red[0][0]; out[1] += red[1][0]; }
+}
+
 struct ScorePlan {
   int parts;
   int64_t chunk;
@@ -248,5 +315,33 @@ extern "C" int etpgt_topk_metrics(const int64_t* top_idx, const int64_t* targets
   ETPGT_REQUIRE(batch >= 0 && k >= 1 && k <= k_stride, "topk_metrics: bad sizes");
   topk_metrics_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(top_idx, targets, batch, k_stride, k, out);
   ETPGT_CHECK_LAUNCH("topk_metrics");
+  return ETPGT_OK;
+}
+
+extern "C" int etpgt_topk_merge_parts(const void* parts, int num_parts, size_t part_stride, size_t idx_offset,
+                                      int64_t rows_total, int k, int64_t row_begin, int64_t rows, float* top_val,
+                                      int64_t* top_idx, const int64_t* targets, int32_t* hit_pos,
+                                      etpgt_stream_t stream) {
+  ETPGT_REQUIRE(num_parts >= 1 && num_parts <= 64 && k >= 1 && k <= kMaxK, "topk_merge_parts: bad sizes (k <= %d)", kMaxK);
+  ETPGT_REQUIRE(rows >= 0 && row_begin >= 0 && row_begin + rows <= rows_total, "topk_merge_parts: bad row range");
+  ETPGT_REQUIRE(idx_offset % 8 == 0 && part_stride % 8 == 0 && idx_offset >= (size_t)rows_total * k * sizeof(float) &&
+                    part_stride >= idx_offset + (size_t)rows_total * k * sizeof(int64_t),
+                "topk_merge_parts: bad part layout");
+  ETPGT_REQUIRE(rows == 0 || (parts && top_val && top_idx), "topk_merge_parts: null pointer");
+  ETPGT_REQUIRE((targets == nullptr) == (hit_pos == nullptr), "topk_merge_parts: targets and hit_pos come together");
+  if (rows == 0) return ETPGT_OK;
+  const int64_t warps_per_cta = kThreads / 32;
+  topk_merge_parts_kernel<<<(unsigned)((rows + warps_per_cta - 1) / warps_per_cta), kThreads, 0,
+                            static_cast<cudaStream_t>(stream)>>>(static_cast<const char*>(parts), num_parts,
+                                                                 part_stride, idx_offset, k, row_begin, rows, top_val,
+                                                                 top_idx, targets, hit_pos);
+  ETPGT_CHECK_LAUNCH("topk_merge_parts");
+  return ETPGT_OK;
+}
+
+extern "C" int etpgt_hit_metrics(const int32_t* hit_pos, int64_t batch, int k, double* out, etpgt_stream_t stream) {
+  ETPGT_REQUIRE(batch >= 0 && k >= 1 && out && (batch == 0 || hit_pos), "hit_metrics: bad arguments");
+  hit_metrics_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(hit_pos, batch, k, out);
+  ETPGT_CHECK_LAUNCH("hit_metrics");
   return ETPGT_OK;
 }

@@ -93,6 +93,8 @@ _PROTOTYPES = {
     "etpgt_gt_step_num_phases": (I, [P]),
     "etpgt_gt_step_run": (I, [P, I, I, P]),
     "etpgt_adam_step": (I, [P, I, D, D, D, D, D, I, L, I, P]),
+    "etpgt_topk_merge_parts": (I, [P, I, Z, Z, L, I, L, L, P, P, P, P, P]),
+    "etpgt_hit_metrics": (I, [P, L, I, P, P]),
     "etpgt_ids_check": (I, [P, L, P, L, P, L, L, P, P]),
     "etpgt_comm_control_bytes": (Z, []),
     "etpgt_comm_create": (I, [I, I, Z, P]),

@@ -81,12 +81,15 @@ class _DeviceAdam(torch.optim.Optimizer):
         self._plan_key = None
         self._plan = None
         self._peer = None          # parallel.PeerDataParallel owning the item table, if any
-        if grad_sinks:
-            for group in self.param_groups:
-                for p in group["params"]:
-                    if p.is_cuda and p.dtype == torch.float32 and p.dim() == 2 and p.is_contiguous() \
-                            and p.numel() * 4 >= sink_bytes:
-                        self._install_sink(p)
+        from .parallel import peer_for
+
+        for group in self.param_groups:
+            for p in group["params"]:
+                if not (p.is_cuda and p.dtype == torch.float32 and p.dim() == 2 and p.is_contiguous()):
+                    continue
+                # a table that lives in a peer region (data parallelism) always uses the region's gradient buffer
+                if peer_for(p) is not None or (grad_sinks and p.numel() * 4 >= sink_bytes):
+                    self._install_sink(p)
 
     # ------------------------------------------------------------------ gradient sinks
     def _install_sink(self, p):

@@ -355,6 +355,17 @@ int etpgt_topk_merge(const float* cand_val, const int64_t* cand_idx, int64_t bat
 /* hits/ndcg accumulators: out[0] += #hits@k, out[1] += sum 1/log2(pos+2) (double[2], caller-zeroed). */
 int etpgt_topk_metrics(const int64_t* top_idx, const int64_t* targets, int64_t batch, int k_stride,
                        int k, double* out, etpgt_stream_t stream);
+/* Item-sharded evaluation: every rank scores ALL sessions against its contiguous id range and
+ * packs its candidates as one block (val [rows_total, k] f32 at offset 0, idx [rows_total, k] i64 at idx_offset);
+ * ONE all-gather lays the blocks out rank-major (part p at parts + p * part_stride).  This merges rows
+ * [row_begin, row_begin + rows) out of that layout exactly (score desc, id asc).  With targets [rows] it also
+ * writes hit_pos[r] = position of targets[r] in the merged top-k or -1 — the input of etpgt_hit_metrics, which
+ * adds (#hits within k, sum of 1/log2(pos+2)) to out[0], out[1] (etpgt/utils/metrics.py:6-66) without the
+ * [rows, k] id matrix being read again. */
+int etpgt_topk_merge_parts(const void* parts, int num_parts, size_t part_stride, size_t idx_offset,
+                           int64_t rows_total, int k, int64_t row_begin, int64_t rows, float* top_val,
+                           int64_t* top_idx, const int64_t* targets, int32_t* hit_pos, etpgt_stream_t stream);
+int etpgt_hit_metrics(const int32_t* hit_pos, int64_t batch, int k, double* out, etpgt_stream_t stream);
 
 /* ---- generic helper shared by embedding / loss backward ---------------------------------
  * d_table[key] += sum_{p: keys[p]==key} coef[p] * src[p / src_div]  in ascending p, one writer

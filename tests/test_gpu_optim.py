@@ -2,6 +2,8 @@
 (oracle/optim_ref.py, itself pinned to torch.optim in tests/test_optim_oracle.py) and against
 torch.optim.AdamW / Adam in fp32 on the same device; gradient-sink behaviour of etpgt_b200.optim."""
 
+import copy
+
 import numpy as np
 import pytest
 import torch
@@ -124,3 +126,68 @@ def test_gradient_sink_zero_grad_discards_unstepped_gradient():
     assert table.grad.abs().sum().item() == 2 * 99 * 256
     opt.zero_grad()
     assert table.grad is not None and table.grad.abs().sum().item() == 0
+
+
+def test_step_after_load_state_dict_uses_the_loaded_moments():
+    """The cached launch plan holds raw pointers of the moment tensors; `load_state_dict` replaces those tensors
+    (resume, restore-best) while parameter and gradient pointers stay the same.  The step after a load must read
+    and update the LOADED moments (not the freed old buffers): compared against torch.optim.AdamW doing the same."""
+    from etpgt_b200 import optim
+
+    shapes = [(3000, 256), (4097,), (5,)]
+    init = _params(shapes, 2)
+    mine = [torch.nn.Parameter(p.clone().cuda()) for p in init]
+    ref = [torch.nn.Parameter(p.clone().cuda()) for p in init]
+    opt_m = optim.AdamW(mine, lr=1e-3, weight_decay=1e-5)
+    opt_t = torch.optim.AdamW(ref, lr=1e-3, weight_decay=1e-5)
+
+    def set_grads(seed):
+        for p, q, g in zip(mine, ref, _params(shapes, seed)):
+            if p.grad is None:
+                p.grad = g.clone().cuda()
+            else:
+                p.grad.copy_(g.cuda())          # same gradient storage every step, as the sink / flat views are
+            q.grad = g.clone().cuda()
+
+    for seed in (20, 21):
+        set_grads(seed)
+        opt_m.step()
+        opt_t.step()
+    saved = copy.deepcopy(opt_t.state_dict())    # state_dict() returns references to the live state tensors
+    for seed in (22, 23):                       # both move on ...
+        set_grads(seed)
+        opt_m.step()
+        opt_t.step()
+    opt_m.load_state_dict(copy.deepcopy(saved))   # ... and are put back to the state after step 2
+    opt_t.load_state_dict(copy.deepcopy(saved))
+    for p, q in zip(mine, ref):
+        p.data.copy_(q.data)
+    old = [opt_m.state[p]["exp_avg"] for p in mine]
+    set_grads(24)
+    opt_m.step()
+    opt_t.step()
+    for p, q, o in zip(mine, ref, old):
+        scale = q.detach().abs().max().item()
+        assert (p.detach() - q.detach()).abs().max().item() <= TOL * scale
+        st_m, st_t = opt_m.state[p], opt_t.state[q]
+        assert st_m["exp_avg"] is o              # the loaded tensor is the one that was updated
+        assert (st_m["exp_avg"] - st_t["exp_avg"]).abs().max().item() <= TOL * st_t["exp_avg"].abs().max().item()
+        assert int(st_m["step"].item()) == 3
+
+
+def test_gradient_sink_survives_module_zero_grad():
+    """`model.zero_grad()` (set_to_none=True) detaches the persistent buffer from `.grad`; the next backward must
+    find it attached again and start from zero — otherwise the table would silently stop training."""
+    from etpgt_b200 import ops, optim
+
+    table = torch.nn.Parameter(torch.randn(8192, 256, device="cuda"))
+    opt = optim.AdamW([table], lr=1e-2, grad_sinks=True)
+    ids = torch.arange(1, 100, device="cuda")
+    ops.EmbedPE.apply(ids, table, None, False, None, None, 0).sum().backward()
+    table.grad = None                          # what nn.Module.zero_grad() does: the unstepped rows are discarded
+    ops.EmbedPE.apply(ids, table, None, False, None, None, 0).sum().backward()
+    assert table.grad is not None and table.grad.abs().sum().item() == 99 * 256
+    before = table.detach().clone()
+    opt.step()
+    assert (table.detach() - before)[1:100].abs().min().item() > 0      # the touched rows moved
+    assert table.grad.abs().sum().item() == 0
