@@ -316,19 +316,24 @@ def run_b200(args, rank, world_size, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    step_stats = {}
+
+    def timed(fn, steps, label="value"):
         sync()
         mallocs = torch.cuda.memory_stats(device).get("num_device_alloc", 0)
-        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0.record()
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        marks[0].record()
         for i in range(steps):
             fn(i)
-        t1.record()
+            marks[i + 1].record()
         sync()
         mallocs = torch.cuda.memory_stats(device).get("num_device_alloc", 0) - mallocs
         if mallocs and rank == 0:   # a cudaMalloc inside the timed region means the warm-up was too short
-            print(f"bench.py: {mallocs} device allocations inside a timed region", file=sys.stderr)
-        ms = torch.tensor([t0.elapsed_time(t1)], device=device)
+            print(f"bench.py: {mallocs} device allocations inside the timed region '{label}'", file=sys.stderr)
+        per_step = [marks[i].elapsed_time(marks[i + 1]) for i in range(steps)]
+        step_stats[label] = {"min": min(per_step), "median": float(np.median(per_step)), "max": max(per_step),
+                             "device_allocations": int(mallocs)}
+        ms = torch.tensor([marks[0].elapsed_time(marks[-1])], device=device)
         if distributed:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
@@ -434,7 +439,7 @@ def run_b200(args, rank, world_size, local_rank):
             if i == args.steps - 1:
                 drain_loss()              # the last loss is read inside the timed region too
 
-        ms_e2e = timed(e2e_all, args.steps)
+        ms_e2e = timed(e2e_all, args.steps, "e2e")
         if e2e_marks and rank == 0:
             gaps = np.diff(np.asarray(e2e_marks[-args.steps:])) * 1e3
             print("e2e host gaps between steps (ms):", np.round(gaps, 2).tolist(), file=sys.stderr)
@@ -449,6 +454,7 @@ def run_b200(args, rank, world_size, local_rank):
         "e2e": {"value": e2e_value, "unit": "sessions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
+        "step_ms": step_stats,      # device time between the ends of consecutive steps (rank 0)
         "clocks": clocks.summary(),
         "final_loss": losses[-1] if losses else None,
         "batch_shape": {"nodes": host_batches[0].nodes, "edges": host_batches[0].edges},
@@ -475,7 +481,7 @@ def run_b200(args, rank, world_size, local_rank):
                 value_step(i, big_source)
             pending["batch"] = None
             sweep_steps = max(args.steps // 2, 4)
-            ms_big = timed(lambda i: value_step(i, big_source), sweep_steps)
+            ms_big = timed(lambda i: value_step(i, big_source), sweep_steps, f"sweep_{sweep}")
             pending["batch"] = None
             out["batch_sweep"].append({"sessions_per_step": sweep, "ms_per_step": ms_big / sweep_steps,
                                        "value": sweep * sweep_steps / (ms_big / 1e3), "unit": "sessions/s",

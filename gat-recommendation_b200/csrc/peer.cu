@@ -43,17 +43,17 @@ __device__ __forceinline__ CommControl* control(const CommView& c, int r) {
 
 // One CTA, one thread per rank: "everything this rank issued before me is done" -> every peer; then wait for
 // the same statement from every peer.  Kernel boundaries order it against the neighbouring kernels.
-__global__ void comm_barrier_kernel(const __grid_constant__ CommView c) {
+__global__ void comm_barrier_kernel(const __grid_constant__ CommView c, int channel) {
   CommControl* me = control(c, c.rank);
   __shared__ unsigned long long epoch_s;
-  if (threadIdx.x == 0) epoch_s = ++me->bar_epoch;
+  if (threadIdx.x == 0) epoch_s = ++me->bar_epoch[channel];
   __syncthreads();
   const unsigned long long epoch = epoch_s;
   const int p = threadIdx.x;
   if (p < c.world) {
     __threadfence_system();
-    st_release_sys(&control(c, p)->bar_flag[c.rank], epoch);
-    wait_flag(&me->bar_flag[p], epoch, c.timeout_ns, &me->status, 1u);
+    st_release_sys(&control(c, p)->bar_flag[channel][c.rank], epoch);
+    wait_flag(&me->bar_flag[channel][p], epoch, c.timeout_ns, &me->status, 1u);
   }
 }
 
@@ -211,9 +211,10 @@ extern "C" int etpgt_comm_destroy(etpgt_comm_t* comm) {
   return ETPGT_OK;
 }
 
-extern "C" int etpgt_comm_barrier(const etpgt_comm_t* comm, etpgt_stream_t stream) {
+extern "C" int etpgt_comm_barrier(const etpgt_comm_t* comm, int channel, etpgt_stream_t stream) {
   ETPGT_REQUIRE(comm && connected(comm), "comm_barrier: communicator not connected");
-  comm_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(comm_view(comm));
+  ETPGT_REQUIRE(channel >= 0 && channel < kBarChannels, "comm_barrier: channel %d must be 0..%d", channel, kBarChannels - 1);
+  comm_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(comm_view(comm), channel);
   ETPGT_CHECK_LAUNCH("comm_barrier");
   return ETPGT_OK;
 }

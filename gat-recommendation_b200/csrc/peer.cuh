@@ -9,18 +9,19 @@
 namespace etpgt {
 
 constexpr int kMaxRanks = ETPGT_MAX_RANKS;
+constexpr int kBarChannels = 4;    // independent barrier sequences (one per stream that synchronises)
 constexpr int kArSlots = 8;        // ring of exchange slots of the small all-reduce
 constexpr int kArMaxCount = 520;   // doubles per contribution (BatchNorm: 2*256 + 1)
 
 // Start of every region.  Flags are written by PEERS (system-scope release stores) and polled locally;
 // the counters are only touched by this rank's own kernels, so that a captured CUDA graph replays correctly.
 struct CommControl {
-  unsigned long long bar_flag[kMaxRanks];             // bar_flag[r] = last barrier epoch rank r has reached
+  unsigned long long bar_flag[kBarChannels][kMaxRanks];   // [c][r] = last barrier epoch of channel c rank r reached
   unsigned long long ar_flag[kArSlots][kMaxRanks];    // ar_flag[s][r] = sequence number of r's data in slot s
-  unsigned long long bar_epoch;                       // barriers this rank has entered
+  unsigned long long bar_epoch[kBarChannels];         // barriers this rank has entered, per channel
   unsigned long long ar_seq;                          // small all-reduces this rank has entered
   unsigned int status;                                // != 0: a wait timed out (see etpgt_comm_status)
-  unsigned int pad_[63];
+  unsigned int pad_[61];
   double ar_slot[kArSlots][kMaxRanks][kArMaxCount];   // ar_slot[s][r] = contribution of rank r
 };
 

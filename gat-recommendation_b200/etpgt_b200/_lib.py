@@ -104,7 +104,7 @@ _PROTOTYPES = {
     "etpgt_comm_region": (P, [P, I]),
     "etpgt_comm_set_timeout": (I, [P, D]),
     "etpgt_comm_destroy": (I, [P]),
-    "etpgt_comm_barrier": (I, [P, P]),
+    "etpgt_comm_barrier": (I, [P, I, P]),
     "etpgt_comm_allreduce_f64": (I, [P, P, P, I, P]),
     "etpgt_comm_sum_f32": (I, [P, Z, L, P, P]),
     "etpgt_comm_status": (I, [P, P]),

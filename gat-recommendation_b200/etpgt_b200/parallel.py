@@ -188,8 +188,8 @@ class PeerComm:
         raw = torch.as_tensor(_RawDeviceMemory(self.base(rank) + offset, max(nbytes, 1), self), device=self.device)
         return raw[:nbytes].view(dtype).view(shape)
 
-    def barrier(self) -> None:
-        _lib.call("etpgt_comm_barrier", self.handle, stream())
+    def barrier(self, channel: int = 0) -> None:
+        _lib.call("etpgt_comm_barrier", self.handle, int(channel), stream())
 
     def allreduce_f64(self, inp: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         out = inp if out is None else out

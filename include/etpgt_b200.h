@@ -466,10 +466,13 @@ int etpgt_sampled_loss_bwd_planned(const float* sess, const float* table, const 
  * pointers when several ranks live in one process (etpgt_comm_connect_ptrs).  The kernels below move data
  * with ordinary loads / stores over NVLink and order it with system-scope flags; every cross-rank sum runs in
  * rank order on every rank, so replicas stay bit-identical.  All ranks must issue the same sequence of
- * communicator calls, each on ONE stream.  A wait that sees no peer for the time-out (default 30 s) gives
+ * communicator calls (per barrier channel; the small all-reduce has one sequence), each sequence on ONE
+ * stream.  A wait that sees no peer for the time-out (default 30 s) gives
  * up and records it in the status word (etpgt_comm_status) instead of hanging the GPU; later waits of that rank
  * return at once.
- *   barrier        everything this rank issued before is complete and visible to its peers, and vice versa
+ *   barrier        everything this rank issued before (on that stream) is complete and visible to its peers, and
+ *                  vice versa; `channel` 0..3 selects an independent barrier sequence, one per stream that
+ *                  synchronises (all ranks use the same channel for the same purpose)
  *   allreduce_f64  out[i] = sum_r in_r[i], count <= 520 doubles (BatchNorm statistics), ONE single-CTA kernel
  *                  (in == out allowed)
  *   sum_f32        out[i] = sum_r region_r[offset + 4*i]: the dense-gradient exchange (callers bracket it
@@ -485,7 +488,7 @@ int etpgt_comm_connect_ptrs(etpgt_comm_t* comm, void* const* bases /* [world] */
 void* etpgt_comm_region(const etpgt_comm_t* comm, int rank);
 int etpgt_comm_set_timeout(etpgt_comm_t* comm, double seconds);
 int etpgt_comm_destroy(etpgt_comm_t* comm);
-int etpgt_comm_barrier(const etpgt_comm_t* comm, etpgt_stream_t stream);
+int etpgt_comm_barrier(const etpgt_comm_t* comm, int channel, etpgt_stream_t stream);
 int etpgt_comm_allreduce_f64(const etpgt_comm_t* comm, const double* in, double* out, int count,
                              etpgt_stream_t stream);
 int etpgt_comm_sum_f32(const etpgt_comm_t* comm, size_t offset, int64_t numel, float* out, etpgt_stream_t stream);

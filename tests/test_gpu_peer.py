@@ -335,7 +335,7 @@ def _two_gpu_worker(rank, world, port, out):
         fused = FusedTrainStep(model, "bpr")
         ok, notes = True, []
         for step in range(3):
-            ids = np.arange(step * global_batch, (step + 1) * global_batch)
+            ids = np.arange(step * global_batch, (step + 1) * global_batch) % d.num_sessions
             cost = (d.sess_ptr[ids + 1] - d.sess_ptr[ids]).astype(np.float64)
             cuts = parallel.partition_sessions(cost, world)
             opt.zero_grad()
