@@ -46,7 +46,7 @@ class GraphIndex:
     """Destination-sorted CSR + source-sorted CSC of one batched graph, built once per batch on
     the device and shared by every conv layer (forward and backward)."""
 
-    __slots__ = ("num_nodes", "num_edges", "rowptr", "col", "eperm", "colptr", "row", "cpos")
+    __slots__ = ("num_nodes", "num_edges", "rowptr", "col", "eperm", "colptr", "row", "cpos", "slot", "generation")
 
     def __init__(self, edge_index: torch.Tensor, num_nodes: int, out: torch.Tensor | None = None,
                  ws: torch.Tensor | None = None, build: bool = True):
@@ -59,6 +59,7 @@ class GraphIndex:
         e = int(edge_index.size(1))
         num_nodes = int(num_nodes)
         self.num_nodes, self.num_edges = num_nodes, e
+        self.slot, self.generation = None, 0      # set by prepare_batch when the arrays live in a BatchPreparer slot
         if out is None:
             out = torch.empty(self.out_elems(num_nodes, e), dtype=torch.int32, device=dev)
         o1 = _pad64(num_nodes + 1)
@@ -87,7 +88,7 @@ def _pad64(n: int) -> int:
 def graph_index_of(batch, edge_index: torch.Tensor, num_nodes: int) -> GraphIndex:
     """Cached on the batch object so that L layers and the backward pass share one build."""
     cached = getattr(batch, "_etpgt_index", None)
-    if cached is not None and cached[0] is edge_index and cached[1].num_nodes == num_nodes:
+    if cached is not None and cached[0] is edge_index and cached[1].num_nodes == num_nodes and _slot_valid(cached[1]):
         return cached[1]
     index = GraphIndex(edge_index, num_nodes)
     try:
@@ -95,6 +96,11 @@ def graph_index_of(batch, edge_index: torch.Tensor, num_nodes: int) -> GraphInde
     except Exception:  # exotic batch containers: just rebuild next time
         pass
     return index
+
+
+def _slot_valid(obj) -> bool:
+    """An index / plan carved from a BatchPreparer slot is valid until that slot is refilled."""
+    return obj.slot is None or obj.slot.generation == obj.generation
 
 
 def segment_ptr(batch_vec: torch.Tensor, num_sessions: int) -> torch.Tensor:
@@ -115,7 +121,7 @@ class ScatterPlan:
     preparation (the device-side counterpart of the reference's collate, dataloader.py:157-202), not part
     of the step's dependent chain."""
 
-    __slots__ = ("m", "sorted_key", "perm")
+    __slots__ = ("m", "sorted_key", "perm", "slot", "generation")
 
     def __init__(self, keys: torch.Tensor, num_rows: int, negatives: torch.Tensor | None = None,
                  out: torch.Tensor | None = None, ws: torch.Tensor | None = None, build: bool = True):
@@ -125,6 +131,7 @@ class ScatterPlan:
         _require_cuda(keys, "scatter keys")
         keys = _i64(keys).reshape(-1)
         dev = keys.device
+        self.slot, self.generation = None, 0
         if negatives is not None:
             negatives = _i64(negatives)
             b = int(keys.numel())
@@ -178,35 +185,90 @@ def _find_plan(*tensors):
         # shares its version counter
         if base is None or base.device != t.device or t._version != version:
             return None
-    return plan
+    return plan if _slot_valid(plan) else None
 
 
 class PreparedBatch:
     """What `prepare_batch` built: the graph index and the two scatter plans, all carved from ONE int32 buffer
     (`tensors()` lists what a caller must `record_stream` when preparation runs on a side stream)."""
 
-    __slots__ = ("index", "plan_nodes", "plan_loss", "buffer", "scratch")
+    __slots__ = ("index", "plan_nodes", "plan_loss", "buffer", "scratch", "slot")
 
     def tensors(self):
         return [self.buffer, self.scratch]
 
+    def release(self) -> None:
+        """Call on the stream that consumed the batch, after its last kernel is queued: the pool slot behind this
+        preparation may then be refilled once that stream gets here (no-op without a pool)."""
+        if getattr(self, "slot", None) is not None:
+            self.slot.free.record()
+            self.slot.busy = False
 
-def prepare_batch(batch, num_items: int | None = None) -> PreparedBatch:
+
+class _PrepareSlot:
+    __slots__ = ("buffer", "scratch", "free", "busy", "generation")
+
+
+class BatchPreparer:
+    """Ring of reusable preparation buffers for a loader that prepares batches ahead of the training step on a side
+    stream: `prepare_batch(batch, num_items, pool=...)` fills the next slot instead of allocating, after making
+    its stream wait (on the device, no host sync) for the step that last consumed that slot —
+    `prepared.release()`, called by the consumer.  A slot that was never released is left alone and replaced by a
+    fresh one; slots grow (with head-room) when a larger batch arrives, so a steady loop allocates nothing."""
+
+    def __init__(self, depth: int = 4):
+        self.depth, self.slots, self.next = int(depth), [], 0
+
+    def acquire(self, elems: int, scratch_bytes: int, device) -> _PrepareSlot:
+        if len(self.slots) < self.depth:
+            self.slots.append(None)
+        i = self.next % self.depth
+        self.next += 1
+        slot = self.slots[i]
+        if slot is not None and (slot.busy or slot.buffer.numel() < elems or slot.scratch.numel() < scratch_bytes
+                                 or slot.buffer.device != torch.device(device)):
+            if slot.busy:      # its consumer never released it: it may still be in use
+                slot = None
+            else:              # too small: the consumer is done with it once `free` has passed
+                torch.cuda.current_stream().wait_event(slot.free)
+                slot = None
+        if slot is None:
+            slot = _PrepareSlot()
+            slot.buffer = torch.empty(elems + elems // 8, dtype=torch.int32, device=device)
+            slot.scratch = workspace(scratch_bytes + scratch_bytes // 8, device)
+            slot.free = torch.cuda.Event()
+            slot.generation = 0
+            self.slots[i] = slot
+        else:
+            torch.cuda.current_stream().wait_event(slot.free)
+        slot.busy = True
+        slot.generation += 1      # indexes / plans carved from the previous filling are no longer valid
+        return slot
+
+
+def prepare_batch(batch, num_items: int | None = None, pool: "BatchPreparer | None" = None) -> PreparedBatch:
     """Integer preparation of one batch on the current stream: CSR / CSC index of `batch.edge_index` and, when
     the table size is given, the scatter plans of `batch.x` and of `batch.target_item | batch.negative_items`.
     Everything here depends on the batch's inputs only, so a loader (or a side stream one step ahead) runs
     it off the training step's critical path; the model and the loss find the results again through the
     batch object / the key tensors.  Without this call the step builds the same things inline.
-    Host cost: two allocations and one library call."""
+    Host cost: two allocations (none with a `pool`) and one library call."""
     prepared = PreparedBatch()
     edge_index, ids = batch.edge_index, batch.x
     _require_cuda(ids, "batch.x")
     n, e = int(ids.numel()), int(edge_index.size(1))
     dev = ids.device
     prepared.plan_nodes = prepared.plan_loss = None
+    prepared.slot = None
+
+    def buffers(elems: int, scratch_bytes: int):
+        if pool is None:
+            return torch.empty(elems, dtype=torch.int32, device=dev), workspace(scratch_bytes, dev)
+        prepared.slot = pool.acquire(elems, scratch_bytes, dev)
+        return prepared.slot.buffer[:elems], prepared.slot.scratch
+
     if num_items is None or n == 0:      # the index alone
-        prepared.buffer = torch.empty(GraphIndex.out_elems(n, e), dtype=torch.int32, device=dev)
-        prepared.scratch = workspace(size("etpgt_csr_workspace_bytes", e, n), dev)
+        prepared.buffer, prepared.scratch = buffers(GraphIndex.out_elems(n, e), size("etpgt_csr_workspace_bytes", e, n))
         prepared.index = GraphIndex(edge_index, n, out=prepared.buffer, ws=prepared.scratch)
     else:
         # index + both scatter plans from ONE library call (etpgt_batch_prepare: the destination sort and the two
@@ -220,8 +282,8 @@ def prepare_batch(batch, num_items: int | None = None) -> PreparedBatch:
         if plan_loss:
             targets, negatives = _i64(targets), _i64(negatives)
         elems_index, elems_nodes = GraphIndex.out_elems(n, e), 2 * _pad64(n)
-        prepared.buffer = torch.empty(elems_index + elems_nodes + 2 * _pad64(m_loss), dtype=torch.int32, device=dev)
-        prepared.scratch = workspace(size("etpgt_batch_prepare_workspace_bytes", e, n, m_loss), dev)
+        prepared.buffer, prepared.scratch = buffers(elems_index + elems_nodes + 2 * _pad64(m_loss),
+                                                    size("etpgt_batch_prepare_workspace_bytes", e, n, m_loss))
         index = prepared.index = GraphIndex(edge_index, n, out=prepared.buffer, build=False)
         nodes = prepared.plan_nodes = ScatterPlan(ids, num_items, out=prepared.buffer[elems_index:], build=False)
         loss = None
@@ -239,6 +301,10 @@ def prepare_batch(batch, num_items: int | None = None) -> PreparedBatch:
         # ids index the table (and its gradient buffer) raw: flag anything outside [0, num_items)
         call("etpgt_ids_check", ptr(ids), n, ptr(targets) if plan_loss else None, b,
              ptr(negatives) if plan_loss else None, b * num_neg, int(num_items), ptr(_bad_ids_flag(dev)), stream())
+    if prepared.slot is not None:
+        for obj in (prepared.index, prepared.plan_nodes, prepared.plan_loss):
+            if obj is not None:
+                obj.slot, obj.generation = prepared.slot, prepared.slot.generation
     try:
         object.__setattr__(batch, "_etpgt_index", (batch.edge_index, prepared.index))
         object.__setattr__(batch, "_etpgt_prepared", prepared)   # keeps the plans alive with the batch
@@ -1006,18 +1072,26 @@ def tensor_core_scoring_supported(dim: int, k: int) -> bool:
 
 
 @torch.no_grad()
-def score_topk(sess: torch.Tensor, table: torch.Tensor, k: int, id_base: int = 0, precision: str = "fp32"):
+def score_topk(sess: torch.Tensor, table: torch.Tensor, k: int, id_base: int = 0, precision: str = "fp32",
+               out: tuple | None = None):
     """Top-k item ids by dot product, ties to the lower id — etpgt/model/base.py:59-78.
 
     precision "fp32": CUDA-core scorer with the reference's fp32 arithmetic.
     precision "bf16": tcgen05 tensor-core scorer (bf16 operands, fp32 accumulation in TMEM); `table`
-    may already be a bf16 copy (an evaluation loop converts it once)."""
+    may already be a bf16 copy (an evaluation loop converts it once).
+    out: (top_val [B, k] f32, top_idx [B, k] i64) to write into (contiguous), else fresh tensors."""
     _require_cuda(sess, "session embeddings")
     b, dim = sess.shape
     items = table.size(0)
     dev = sess.device
-    top_val = torch.empty(b, k, dtype=torch.float32, device=dev)
-    top_idx = torch.empty(b, k, dtype=torch.int64, device=dev)
+    if out is not None:
+        top_val, top_idx = out
+        if tuple(top_val.shape) != (b, k) or tuple(top_idx.shape) != (b, k) or top_val.dtype != torch.float32 \
+                or top_idx.dtype != torch.int64:
+            raise RuntimeError("score_topk: `out` must be (float32 [B, k], int64 [B, k])")
+    else:
+        top_val = torch.empty(b, k, dtype=torch.float32, device=dev)
+        top_idx = torch.empty(b, k, dtype=torch.int64, device=dev)
     if precision == "bf16":
         sess_h, table_h = to_bf16(sess), to_bf16(table)
         ws = workspace(size("etpgt_score_topk_bf16_workspace_bytes", b, items, k), dev)
@@ -1057,3 +1131,29 @@ def topk_metrics(top_idx: torch.Tensor, targets: torch.Tensor, k: int, acc: torc
 
 def launch_count() -> int:
     return _lib.launch_count()
+
+
+@torch.no_grad()
+def topk_merge_parts(parts: torch.Tensor, num_parts: int, part_stride: int, idx_offset: int, rows_total: int, k: int,
+                     row_begin: int, rows: int, targets: torch.Tensor | None = None):
+    """Exact merge of item-sharded candidates out of the rank-major layout one all-gather leaves them in
+    (etpgt_topk_merge_parts).  Returns (top_val, top_idx, hit_pos or None)."""
+    dev = parts.device
+    top_val = torch.empty(rows, k, dtype=torch.float32, device=dev)
+    top_idx = torch.empty(rows, k, dtype=torch.int64, device=dev)
+    hit_pos = None
+    if targets is not None:
+        targets = _i64(targets)
+        hit_pos = torch.empty(rows, dtype=torch.int32, device=dev)
+    call("etpgt_topk_merge_parts", ptr(parts), int(num_parts), int(part_stride), int(idx_offset), int(rows_total), int(k),
+         int(row_begin), int(rows), ptr(top_val), ptr(top_idx), ptr(targets), ptr(hit_pos), stream())
+    return top_val, top_idx, hit_pos
+
+
+@torch.no_grad()
+def hit_metrics(hit_pos: torch.Tensor, k: int, acc: torch.Tensor | None = None):
+    """Adds (#targets found within the first k positions, sum of 1/log2(pos+2)) into `acc` (double[2])."""
+    if acc is None:
+        acc = torch.zeros(2, dtype=torch.float64, device=hit_pos.device)
+    call("etpgt_hit_metrics", ptr(hit_pos), hit_pos.numel(), int(k), ptr(acc), stream())
+    return acc

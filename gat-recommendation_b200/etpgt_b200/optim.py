@@ -104,6 +104,21 @@ class _DeviceAdam(torch.optim.Optimizer):
         _GRAD_SINKS[p.data_ptr()] = (weakref.ref(p), buf, weakref.ref(self))
         self._sinks.append(p)
 
+    def attach_peer(self, peer) -> None:
+        """Moves the item table's gradient sink into the peer region of `peer` (parallel.PeerDataParallel created
+        AFTER this optimizer, e.g. by Trainer(process_group=...)): the table's storage address changed when it was
+        re-homed, so the old registration is dropped and the region's gradient buffer takes over."""
+        for group in self.param_groups:
+            for p in group["params"]:
+                if p.data_ptr() != peer.table.data_ptr():
+                    continue
+                for key, entry in list(_GRAD_SINKS.items()):
+                    if entry[0]() is p:
+                        _GRAD_SINKS.pop(key, None)
+                self._sinks = [q for q in self._sinks if q is not p]
+                self._install_sink(p)
+        self._plan_key = None
+
     def _is_sink(self, p) -> bool:
         entry = _GRAD_SINKS.get(p.data_ptr())
         return entry is not None and entry[0]() is p and p.grad is entry[1]

@@ -81,41 +81,89 @@ def allreduce_gradients(params, group=None) -> None:
         dist.all_reduce(p.grad, group=group)
 
 
+_GATHER_INDEX: dict = {}
+
+
+def _compact_index(counts: tuple, device) -> torch.Tensor:
+    """Row indices that drop the padding of an all-gather of max(counts)-row blocks (cached per counts tuple)."""
+    key = (counts, str(device))
+    idx = _GATHER_INDEX.get(key)
+    if idx is None:
+        width = max(counts)
+        idx = torch.from_numpy(np.concatenate([r * width + np.arange(c) for r, c in enumerate(counts)])).to(device)
+        if len(_GATHER_INDEX) > 64:
+            _GATHER_INDEX.clear()
+        _GATHER_INDEX[key] = idx
+    return idx
+
+
 @torch.no_grad()
-def sharded_predict(model, session_embeddings: torch.Tensor, k: int = 20, group=None) -> torch.Tensor:
-    """Item-sharded full-catalogue top-k: all-gather the session vectors, score the local id range,
-    all-gather (value, id) candidates, exact merge.  Returns the top-k ids of THIS rank's sessions."""
+def sharded_predict(model, session_embeddings: torch.Tensor, k: int = 20, group=None, counts=None, targets=None,
+                    precision: str = "auto"):
+    """Item-sharded full-catalogue top-k: one all-gather of the session vectors, ONE scoring
+    call of this rank's contiguous id range for all sessions (fused top-k), one all-gather of the packed
+    (value, id) candidates, one exact merge kernel that reads the gathered layout directly.  Returns the top-k ids
+    of THIS rank's sessions — identical to single-GPU scoring for any GPU count; with `targets` [B] returns
+    (ids, hit_pos) where hit_pos[b] is the position of the target in the top-k or -1 (input of ops.hit_metrics).
+
+    counts: every rank's session count (host ints), when the caller knows them (a sharding loader does);
+    otherwise they are exchanged, which costs one host read."""
     from . import ops
 
     rank, size = world()
     table = model.get_item_embeddings()
+    b_local, width = session_embeddings.shape
+    dev = session_embeddings.device
+    if precision == "auto":
+        precision = getattr(model, "score_precision", "auto")
     if size == 1:
-        return ops.score_topk(session_embeddings, table, k)[1]
-    counts = [torch.zeros(1, dtype=torch.int64, device=session_embeddings.device) for _ in range(size)]
-    dist.all_gather(counts, torch.tensor([session_embeddings.size(0)], device=session_embeddings.device), group=group)
-    counts = [int(c.item()) for c in counts]
-    width = session_embeddings.size(1)
-    padded = torch.zeros(max(counts), width, dtype=torch.float32, device=session_embeddings.device)
-    padded[: session_embeddings.size(0)] = session_embeddings
-    gathered = [torch.empty_like(padded) for _ in range(size)]
-    dist.all_gather(gathered, padded, group=group)
-    everyone = torch.cat([g[:c] for g, c in zip(gathered, counts)])
+        if precision == "auto":
+            precision = "bf16" if b_local >= 64 and ops.tensor_core_scoring_supported(width, k) else "fp32"
+        top = ops.score_topk(session_embeddings, table, k, precision=precision)[1]
+        if targets is None:
+            return top
+        hit = torch.full((b_local,), -1, dtype=torch.int32, device=dev)
+        match = top == ops._i64(targets).view(-1, 1)
+        found = match.any(dim=1)
+        hit[found] = match.float().argmax(dim=1)[found].int()
+        return top, hit
+    if counts is None:
+        mine = torch.tensor([b_local], dtype=torch.int64, device=dev)
+        everyone_counts = torch.empty(size, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(everyone_counts, mine, group=group)
+        counts = everyone_counts.tolist()
+    counts = tuple(int(c) for c in counts)
+    total, widest = sum(counts), max(counts)
+    send = ops._f32(session_embeddings)
+    if b_local != widest:
+        padded = torch.zeros(widest, width, dtype=torch.float32, device=dev)
+        padded[:b_local] = send
+        send = padded
+    gathered = torch.empty(size * widest, width, dtype=torch.float32, device=dev)
+    dist.all_gather_into_tensor(gathered, send, group=group)
+    everyone = gathered if total == size * widest else gathered.index_select(0, _compact_index(counts, dev))
+    if precision == "auto":
+        precision = "bf16" if total >= 64 and ops.tensor_core_scoring_supported(width, k) else "fp32"
+    # this rank's candidates for ALL sessions, packed as one block: val [total, k] f32 | idx [total, k] i64
     lo, hi = item_shard(table.size(0), rank, size)
     kk = min(k, hi - lo)
-    val, idx = ops.score_topk(everyone, table[lo:hi], kk, id_base=lo)
-    if kk < k:  # tiny shard: pad with sentinels that lose every comparison
-        pad_v = torch.full((val.size(0), k - kk), float("-inf"), device=val.device)
-        pad_i = torch.full((val.size(0), k - kk), torch.iinfo(torch.int64).max, device=val.device)
-        val, idx = torch.cat([val, pad_v], 1), torch.cat([idx, pad_i], 1)
-    vals = [torch.empty_like(val) for _ in range(size)]
-    idxs = [torch.empty_like(idx) for _ in range(size)]
-    dist.all_gather(vals, val, group=group)
-    dist.all_gather(idxs, idx, group=group)
+    val_bytes = _align(total * k * 4)
+    block = torch.empty(val_bytes + total * k * 8, dtype=torch.uint8, device=dev)
+    val = block[: total * k * 4].view(torch.float32).view(total, k)
+    idx = block[val_bytes:].view(torch.int64).view(total, k)
+    if kk == k:
+        ops.score_topk(everyone, table[lo:hi], k, id_base=lo, precision=precision, out=(val, idx))
+    else:   # a shard with fewer than k items: pad with sentinels that lose every comparison
+        val.fill_(float("-inf"))
+        idx.fill_(torch.iinfo(torch.int64).max)
+        if kk > 0:
+            v, i = ops.score_topk(everyone, table[lo:hi], kk, id_base=lo, precision=precision)
+            val[:, :kk], idx[:, :kk] = v, i
+    parts = torch.empty(size * block.numel(), dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(parts, block, group=group)
     start = sum(counts[:rank])
-    mine = slice(start, start + counts[rank])
-    cand_v = torch.cat([v[mine] for v in vals], dim=1).contiguous()
-    cand_i = torch.cat([i[mine] for i in idxs], dim=1).contiguous()
-    return ops.topk_merge(cand_v, cand_i, k)[1]
+    _, top, hit = ops.topk_merge_parts(parts, size, block.numel(), val_bytes, total, k, start, b_local, targets)
+    return top if targets is None else (top, hit)
 
 
 # ------------------------------------------------------------------------------ peer memory

@@ -37,23 +37,29 @@ class SyntheticData:
                 "len_mean": float(lens.mean()), "len_median": float(np.median(lens)), "len_max": int(lens.max())}
 
 
-def session_lengths(rng, count: int) -> np.ndarray:
-    """min 3, median 4, mean ~5.5, tail into the hundreds."""
+def session_lengths(rng, count: int, law: str = "retailrocket") -> np.ndarray:
+    """"retailrocket": min 3, median 4, mean ~5.5, tail into the hundreds (docs/DATA_PIPELINE.md:127-134);
+    "yoochoose": min 3 after the length filter, mean ~4, median 3."""
+    if law == "yoochoose":
+        tail = rng.pareto(2.2, size=count) * 1.7
+        return np.minimum(3 + np.floor(tail).astype(np.int64), 200)
     tail = rng.pareto(1.9, size=count) * 2.65
     return np.minimum(3 + np.floor(tail).astype(np.int64), 417)
 
 
 def generate(num_sessions: int = 167_705, graph_sessions: int | None = 120_436, num_items: int = 82_174,
              clusters: int = 1600, p_local: float = 0.94, a_local: float = 0.4, a_global: float = 0.5,
-             a_cluster: float = 0.5, revisit: float = 0.34, window: int = 5, seed: int = 42) -> SyntheticData:
+             a_cluster: float = 0.5, revisit: float = 0.34, window: int = 5, seed: int = 42,
+             length_law: str = "retailrocket", build_graph: bool = True) -> SyntheticData:
     """Default sizes approximate RR-synth (docs/DATA_PIPELINE.md:127-134,289-291: 82,173 graph nodes,
     737,716 undirected edges, degree ~18) from 120,436 train + 23,861 val + 23,408 test sessions; the
     co-occurrence graph is built from the first `graph_sessions` (train) sessions only, as the
     reference's pipeline does.  Sessions browse one of `clusters` item groups (power-law inside the
     group) with probability p_local and the whole catalogue otherwise; that locality is what makes
-    co-occurrence pairs repeat the way real sessions do.  `stats()` reports what was achieved."""
+    co-occurrence pairs repeat the way real sessions do.  `stats()` reports what was achieved.
+    `generate_scaled()` is the 1M-item / 20M-edge configuration (BASELINE.json configs[4])."""
     rng = np.random.default_rng(seed)
-    lens = session_lengths(rng, num_sessions)
+    lens = session_lengths(rng, num_sessions, length_law)
     ptr = np.concatenate([[0], np.cumsum(lens)])
     total = int(ptr[-1])
     n = num_items - 1
@@ -76,6 +82,9 @@ def generate(num_sessions: int = 167_705, graph_sessions: int | None = 120_436, 
     src_pos = np.arange(total) - 1 - back
     for _ in range(3):  # resolve short chains of revisits-of-revisits
         items = np.where(redo, items[np.maximum(src_pos, 0)], items)
+    if not build_graph:   # the caller builds the co-occurrence graph on the device (data.build_co_event_graph)
+        empty = np.zeros(0, dtype=np.int64)
+        return SyntheticData(num_items, empty, empty, ptr, items)
     # window co-occurrence pairs over the graph (train) sessions, canonical order, counted
     upto = total if graph_sessions is None else int(ptr[min(graph_sessions, num_sessions)])
     keys = []
@@ -136,3 +145,14 @@ def sorted_edge_keys(data: SyntheticData) -> tuple:
     keys = data.item_i * data.num_items + data.item_j
     order = np.argsort(keys, kind="stable")
     return keys[order], order
+
+
+def generate_scaled(num_sessions: int = 8_000_000, num_items: int = 1_000_000, seed: int = 43,
+                    build_graph: bool = False) -> SyntheticData:
+    """BASELINE.json configs[4] / SURVEY.md section 8d config 5: 1,000,000 items, Yoochoose-shaped sessions
+    (~8M sessions, mean length ~4, min 3) whose window-5 co-occurrence graph has ~20M undirected edges (average
+    degree ~40, power-law).  By default only the sessions are generated here; the graph is built from them on the
+    device (etpgt_cooc_graph_build), which is the path a 1M-item data set needs anyway."""
+    return generate(num_sessions=num_sessions, graph_sessions=None, num_items=num_items, clusters=12_500, p_local=0.9,
+                    a_local=0.7, a_global=0.8, a_cluster=0.6, revisit=0.25, seed=seed, length_law="yoochoose",
+                    build_graph=build_graph)

@@ -37,7 +37,7 @@ class DeviceSessionLoader:
 
     def __init__(self, sessions_path, graph_edges_path, batch_size=32, num_negatives=5, max_session_length=50,
                  shuffle=True, seed=0, device="cuda", symmetrize=False, self_loop_if_empty=False,
-                 flatten_negatives=True):
+                 flatten_negatives=True, rank: int = 0, world_size: int = 1):
         import pandas as pd
 
         self.session_ids, ptr, items = load_sessions(Path(sessions_path))
@@ -45,6 +45,11 @@ class DeviceSessionLoader:
         item_i, item_j = edges["item_i"].to_numpy(), edges["item_j"].to_numpy()
         # dataloader.py:50-58
         self.num_items = int(max(items.max(initial=0), item_i.max(initial=0), item_j.max(initial=0))) + 1
+        if min(items.min(initial=0), item_i.min(initial=0), item_j.min(initial=0)) < 0:
+            raise IndexError("index out of range in self: negative item id in the session / edge files")
+        self._lengths = np.minimum(np.diff(ptr), max_session_length).astype(np.float64)   # per-session cost
+        self.rank, self.world_size = int(rank), int(world_size)
+        self._pool = ops.BatchPreparer()
         self.graph = data.ItemGraph(item_i, item_j, self.num_items, device)
         self.sessions = data.SessionStore(ptr, items, device)
         self.batch_size, self.num_negatives, self.max_session_length = batch_size, num_negatives, max_session_length
@@ -56,31 +61,56 @@ class DeviceSessionLoader:
     def __len__(self) -> int:
         return (self.sessions.num_sessions + self.batch_size - 1) // self.batch_size
 
+    def _share(self, ids: np.ndarray):
+        """This rank's contiguous share of one global batch (balanced by session length), every rank's session
+        count, and whether the batch is replicated: a global batch too small to give every rank two sessions is
+        processed WHOLE by every rank with total_sessions = B * world — the sums every rank contributes are then
+        identical, so losses, BatchNorm statistics and gradients equal those of the single batch."""
+        from .. import parallel
+
+        world = self.world_size
+        if world == 1:
+            return ids, (len(ids),), False
+        if len(ids) < 2 * world:
+            return ids, (len(ids),) * world, True
+        cuts = parallel.partition_sessions(self._lengths[ids], world)
+        cuts = np.maximum.accumulate(np.maximum(cuts, 2 * np.arange(world + 1)))   # >= 2 sessions for every rank
+        cuts = np.minimum(cuts, len(ids) - 2 * (world - np.arange(world + 1)))
+        counts = tuple(int(c) for c in np.diff(cuts))
+        return ids[cuts[self.rank]:cuts[self.rank + 1]], counts, False
+
     def __iter__(self):
         n = self.sessions.num_sessions
-        if self.shuffle:
-            g = torch.Generator().manual_seed(self.seed + self.epoch)
-            order = torch.randperm(n, generator=g).to(self.device)
+        if self.shuffle:    # the same permutation on every rank (seeded CPU generator)
+            order = torch.randperm(n, generator=torch.Generator().manual_seed(self.seed + self.epoch)).numpy()
         else:
-            order = torch.arange(n, device=self.device)
+            order = np.arange(n)
         self.epoch += 1
         for start in range(0, n, self.batch_size):
-            ids = order[start:start + self.batch_size]
+            whole = order[start:start + self.batch_size]
+            mine, counts, replicated = self._share(whole)
+            ids = torch.from_numpy(np.ascontiguousarray(mine)).to(self.device)
             batch = data.build_batch(self.graph, self.sessions, ids, self.max_session_length, self.symmetrize,
                                      self.self_loop_if_empty)
             neg = data.sample_negatives(self.sessions, ids, self.num_items, self.num_negatives, self.seed, self.step,
                                         max_len=self.max_session_length)
             # PyG collate concatenates the per-sample [num_neg] tensors (trainer.py:87-89 reshapes them back)
             batch.negative_items = neg.reshape(-1) if self.flatten_negatives else neg
+            # data parallelism: the global batch this share belongs to
+            batch.total_sessions = len(whole) * (self.world_size if replicated else 1)
+            batch.rank_sessions, batch.replicated = counts, replicated
             # the rest of "collate": CSR / CSC index and the sorts of the two table-gradient scatters
-            ops.prepare_batch(batch, self.num_items)
+            batch.prepared = ops.prepare_batch(batch, self.num_items, pool=self._pool)
             self.step += 1
             yield batch
 
 
 def create_dataloader(sessions_path, graph_edges_path, batch_size: int = 32, num_negatives: int = 5,
-                      max_session_length: int = 50, shuffle: bool = True, num_workers: int = 0) -> DeviceSessionLoader:
+                      max_session_length: int = 50, shuffle: bool = True, num_workers: int = 0,
+                      rank: int = 0, world_size: int = 1) -> DeviceSessionLoader:
     """Same signature as the reference; `num_workers` is accepted and ignored (no host workers: the batch
-    is built on the device)."""
+    is built on the device).  rank / world_size (data parallelism): every rank iterates the same global batches
+    and builds only its contiguous share of each."""
     del num_workers
-    return DeviceSessionLoader(sessions_path, graph_edges_path, batch_size, num_negatives, max_session_length, shuffle)
+    return DeviceSessionLoader(sessions_path, graph_edges_path, batch_size, num_negatives, max_session_length, shuffle,
+                               rank=rank, world_size=world_size)

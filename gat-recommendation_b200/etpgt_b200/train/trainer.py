@@ -9,7 +9,13 @@ What differs is where the work runs:
     trainer.py:130-133);
   * evaluation keeps predictions on the device: fused scoring + top-k, hit / NDCG counters accumulated by
     `etpgt_topk_metrics`, one read-back per evaluation (the reference copies every batch's top-k to the host,
-    trainer.py:158-159).
+    trainer.py:158-159);
+  * `process_group=` (not in the reference, which is single-GPU) makes this trainer one rank of a session-batch
+    data-parallel job: loaders hand every rank its share of each global batch (`create_dataloader(..., rank,
+    world_size)`), BatchNorm statistics / gradients / the item-table update are exchanged over peer memory
+    (`exchange="peer"`, parallel.PeerDataParallel) or NCCL (`exchange="nccl"`), the loss is the global-batch mean,
+    evaluation scores item shards (`parallel.sharded_predict`) and sums the counters over the ranks; rank 0 writes
+    the checkpoints.
 """
 
 from __future__ import annotations
@@ -19,8 +25,9 @@ import logging
 from pathlib import Path
 
 import torch
+import torch.distributed as dist
 
-from .. import ops
+from .. import ops, parallel
 from .losses import BPRLoss, DualLoss, ListwiseLoss
 from .step import FusedTrainStep
 
@@ -43,7 +50,7 @@ def _driver_for(model, loss_fn):
 class Trainer:
     def __init__(self, model, train_loader, val_loader, optimizer, device: str = "cuda",
                  output_dir: Path | str = "outputs", max_epochs: int = 100, patience: int = 10, eval_every: int = 1,
-                 k_values: list[int] | None = None, loss_fn=None):
+                 k_values: list[int] | None = None, loss_fn=None, process_group=None, exchange: str = "peer"):
         self.model = model.to(device)
         self.train_loader, self.val_loader, self.optimizer = train_loader, val_loader, optimizer
         self.device = device
@@ -56,21 +63,57 @@ class Trainer:
         self.best_val_metric = 0.0
         self.patience_counter = 0
         self.history = {"train_loss": [], "val_metrics": []}
+        # data parallelism: process_group=True (the default group) or a torch.distributed group
+        self._group, self._world, self._rank, self._peer = None, 1, 0, None
+        if process_group is not None and process_group is not False:
+            if not (dist.is_available() and dist.is_initialized()):
+                raise RuntimeError("Trainer(process_group=...) needs an initialised torch.distributed")
+            self._group = None if process_group is True else process_group
+            self._world, self._rank = dist.get_world_size(self._group), dist.get_rank(self._group)
+        if self._world > 1:
+            ours = hasattr(optimizer, "attach_peer")
+            if exchange == "peer" and not ours:
+                logger.warning("exchange='peer' needs an etpgt_b200.optim optimizer; using NCCL all-reduces")
+                exchange = "nccl"
+            self._peer = parallel.enable_data_parallel(self.model, self._group, exchange)
+            if self._peer is not None:
+                optimizer.attach_peer(self._peer)      # the table moved into the peer region after the optimizer was built
         self._driver = _driver_for(self.model, loss_fn)
 
     # ------------------------------------------------------------------ one step
+    def _total_sessions(self, batch, batch_size: int) -> int:
+        """Sessions of the GLOBAL batch this rank's share belongs to (the loss is its mean)."""
+        if self._world == 1:
+            return batch_size
+        total = getattr(batch, "total_sessions", None)
+        if total is None:       # a loader that does not say: one collective + host read per step
+            t = torch.tensor([batch_size], dtype=torch.int64, device=self.device)
+            dist.all_reduce(t, group=self._group)
+            total = int(t.item())
+        return int(total)
+
     def _loss_and_backward(self, batch) -> torch.Tensor:
+        """Backward of this rank's share of the global-batch loss; returns that share (its sum over the ranks is the
+        global-batch mean loss).  Gradients are reduced here (NCCL exchange) or inside optimizer.step() (peer)."""
         batch_size = batch.target_item.shape[0]
         negatives = batch.negative_items.view(batch_size, -1)        # trainer.py:86-89
+        total = self._total_sessions(batch, batch_size)
         if self._driver is not None and getattr(batch, "laplacian_pe", None) is None:
-            return self._driver(batch, batch.target_item, negatives)[0]
+            loss = self._driver(batch, batch.target_item, negatives, total_sessions=total)[0]
+            if self._world > 1 and self._peer is None:
+                self._driver.allreduce_gradients(self._group)
+            return loss
         sess = self.model(batch)
         if self.loss_fn is not None:
             out = self.loss_fn(sess, batch.target_item, negatives, self.model.item_embedding)
             loss = out[0] if isinstance(out, tuple) else out         # DualLoss returns (loss, parts)
         else:
             loss = self.model.compute_loss(sess, batch.target_item, negatives)
+        if total != batch_size:
+            loss = loss * (batch_size / total)       # mean over the local share -> share of the global mean
         loss.backward()
+        if self._world > 1 and self._peer is None:
+            parallel.allreduce_gradients(list(self.model.parameters()), self._group)
         return loss.detach()
 
     def train_epoch(self) -> float:
@@ -82,8 +125,16 @@ class Trainer:
             self.optimizer.zero_grad()
             loss = self._loss_and_backward(batch)
             self.optimizer.step()
+            prepared = getattr(batch, "prepared", None)
+            if prepared is not None:
+                prepared.release()        # the loader may refill that preparation slot once the step has run
             total += loss
             steps += 1
+        if self._world > 1:
+            dist.all_reduce(total, group=self._group)
+        if self._peer is not None:
+            self._peer.comm.check()
+        ops.check_item_ids(self.device)       # IndexError if a batch held an id outside the table (one read per epoch)
         return float(total.item()) / max(steps, 1)
 
     # ------------------------------------------------------------------ evaluation
@@ -91,23 +142,43 @@ class Trainer:
     def evaluate(self) -> dict:
         self.model.eval()
         k_max = max(self.k_values)
-        acc = {k: torch.zeros(2, dtype=torch.float64, device=self.device) for k in self.k_values}
+        # [hits, ndcg] per k, then the session count: ONE tensor, so that data parallelism sums it in one collective
+        acc = torch.zeros(2 * len(self.k_values) + 1, dtype=torch.float64, device=self.device)
         sessions = 0
         for batch in self.val_loader:
             batch = batch.to(self.device)
-            top = self.model.predict(self.model(batch), k=k_max)
-            for k in self.k_values:
-                ops.topk_metrics(top, batch.target_item, k, acc[k])
+            sess = self.model(batch)
+            if self._world > 1:
+                # item-sharded scoring: every rank scores all sessions of the global batch against its id range
+                _, hit = parallel.sharded_predict(self.model, sess, k=k_max, group=self._group,
+                                                  counts=getattr(batch, "rank_sessions", None),
+                                                  targets=batch.target_item)
+                if getattr(batch, "replicated", False) and self._rank != 0:
+                    continue                   # every rank holds the same sessions: counted once
+                for j, k in enumerate(self.k_values):
+                    ops.hit_metrics(hit, k, acc[2 * j:2 * j + 2])
+            else:
+                top = self.model.predict(sess, k=k_max)
+                for j, k in enumerate(self.k_values):
+                    ops.topk_metrics(top, batch.target_item, k, acc[2 * j:2 * j + 2])
             sessions += int(batch.target_item.shape[0])
+        acc[-1] = sessions
+        if self._world > 1:
+            dist.all_reduce(acc, group=self._group)
+        values = acc.tolist()
+        sessions = values[-1]
         metrics = {}
-        for k in self.k_values:
-            hits, ndcg = acc[k].tolist()
-            metrics[f"recall@{k}"] = hits / sessions if sessions else 0.0
-            metrics[f"ndcg@{k}"] = ndcg / sessions if sessions else 0.0
+        for j, k in enumerate(self.k_values):
+            metrics[f"recall@{k}"] = values[2 * j] / sessions if sessions else 0.0
+            metrics[f"ndcg@{k}"] = values[2 * j + 1] / sessions if sessions else 0.0
         return metrics
 
     # ------------------------------------------------------------------ checkpoints and the outer loop
     def save_checkpoint(self, is_best: bool = False) -> None:
+        if self._peer is not None:      # every rank keeps only its own rows' moments current: collect them
+            self._peer.gather_optimizer_state(self.optimizer)
+        if self._rank != 0:
+            return
         checkpoint = {"epoch": self.current_epoch, "model_state_dict": self.model.state_dict(),
                       "optimizer_state_dict": self.optimizer.state_dict(),
                       "best_val_metric": self.best_val_metric, "history": self.history}
@@ -138,6 +209,7 @@ class Trainer:
             if self.patience_counter >= self.patience:
                 logger.info("Early stopping at epoch %d", epoch)
                 break
-        with open(self.output_dir / "history.json", "w") as f:
-            json.dump(self.history, f, indent=2)
+        if self._rank == 0:
+            with open(self.output_dir / "history.json", "w") as f:
+                json.dump(self.history, f, indent=2)
         return self.history

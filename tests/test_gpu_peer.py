@@ -13,6 +13,7 @@ against torch.optim and the fp64 oracle in tests/test_gpu_optim.py); the single-
 
 import os
 import socket
+from pathlib import Path
 
 import numpy as np
 import pytest
@@ -368,7 +369,52 @@ def _two_gpu_worker(rank, world, port, out):
             sess = model(batch_of(np.arange(600 + 50 * rank, 650 + 50 * rank), 9))
             top = parallel.sharded_predict(model, sess, k=20)
             single_top = ops.score_topk(sess, model.get_item_embeddings(), 20)[1]
-        out[rank] = (ok, same, bool(torch.equal(top, single_top)), notes)
+        # the Trainer as one rank of a data-parallel job (process_group=True) vs. a single-process Trainer on the whole
+        # batches: same epoch loss (global-batch mean), same Recall / NDCG (item-sharded scoring, counters summed)
+        import tempfile
+
+        from etpgt_b200.train.trainer import Trainer
+
+        def loaders(shard):
+            def make_list(first, count, size, base_step):
+                batches = []
+                for i in range(count):
+                    ids = np.arange(first + i * size, first + (i + 1) * size)
+                    mine, counts = ids, (size,)
+                    if shard:
+                        cost = (d.sess_ptr[ids + 1] - d.sess_ptr[ids]).astype(np.float64)
+                        cuts = parallel.partition_sessions(cost, world)
+                        mine, counts = ids[cuts[rank]:cuts[rank + 1]], tuple(int(c) for c in np.diff(cuts))
+                    b = batch_of(mine, base_step + i)
+                    b.negative_items = b.negative_items.reshape(-1)
+                    b.total_sessions, b.rank_sessions, b.replicated = size, counts, False
+                    batches.append(b)
+                return batches
+            return make_list(0, 3, 128, 100), make_list(600, 2, 64, 200)
+
+        def run_trainer(dp):
+            m = make()
+            m.dropout_layer.p = 0.0
+            o = optim.AdamW(m.parameters(), lr=1e-3, weight_decay=1e-5)      # created BEFORE the trainer re-homes the table
+            train_l, val_l = loaders(dp)
+            with tempfile.TemporaryDirectory() as tmp:
+                t = Trainer(m, train_l, val_l, o, output_dir=Path(tmp) / f"r{rank}", max_epochs=2, patience=5,
+                            k_values=[10, 20], process_group=True if dp else None)
+                hist = t.train()
+                wrote = (Path(tmp) / f"r{rank}" / "checkpoint_latest.pt").exists()
+            return hist, wrote
+
+        hist_dp, wrote = run_trainer(True)
+        trainer_ok = wrote == (rank == 0)
+        if rank == 0:
+            hist_single, _ = run_trainer(False)
+            for a, b in zip(hist_dp["train_loss"], hist_single["train_loss"]):
+                trainer_ok = trainer_ok and abs(a - b) <= 1e-4 * abs(b)
+            for ma, mb in zip(hist_dp["val_metrics"], hist_single["val_metrics"]):
+                for key in mb:
+                    trainer_ok = trainer_ok and abs(ma[key] - mb[key]) <= 0.02
+            notes.append(f"trainer dp {hist_dp} single {hist_single}")
+        out[rank] = (ok and trainer_ok, same, bool(torch.equal(top, single_top)), notes)
     finally:
         dist.destroy_process_group()
 

@@ -61,3 +61,32 @@ def test_world_size_two_gloo():
     out = manager.dict()
     mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
     assert dict(out) == {0: True, 1: True}
+
+
+def test_loader_shares_cover_every_global_batch_exactly_once():
+    """Host logic of the sharding loader (DeviceSessionLoader._share): contiguous shares balanced by session
+    length, at least two sessions per rank, tiny batches replicated on every rank."""
+    from etpgt_b200.train.dataloader import DeviceSessionLoader
+
+    rng = np.random.default_rng(0)
+    lengths = rng.integers(2, 50, size=1000).astype(np.float64)
+    for world in (2, 3, 8):
+        for size in (5, 16, 17, 64, 333):
+            ids = rng.permutation(1000)[:size]
+            shares, counts_seen = [], None
+            for rank in range(world):
+                loader = DeviceSessionLoader.__new__(DeviceSessionLoader)
+                loader._lengths, loader.rank, loader.world_size = lengths, rank, world
+                mine, counts, replicated = loader._share(ids)
+                assert counts_seen in (None, counts)
+                counts_seen = counts
+                assert len(mine) == counts[rank]
+                shares.append((mine, replicated))
+            if size < 2 * world:
+                assert all(rep and np.array_equal(m, ids) for m, rep in shares)
+            else:
+                assert not any(rep for _, rep in shares)
+                assert np.array_equal(np.concatenate([m for m, _ in shares]), ids)
+                assert min(len(m) for m, _ in shares) >= 2
+                cost = [lengths[m].sum() for m, _ in shares]
+                assert max(cost) - min(cost) <= 2 * lengths.max() + 1e-9 or size < 4 * world
