@@ -341,3 +341,89 @@ extern "C" int etpgt_gt_step_run(const etpgt_gt_step_t* sp, int phase_begin, int
   }
   return ETPGT_OK;
 }
+
+// ---- the same step as ONE CUDA graph launch -------------------------------------------------------------------
+// At small batches (the reference trains at 32 sessions per step, params.yaml:6) every kernel of the step runs for a
+// few microseconds and the step time is the ~55 launch gaps, not the work.  The driver's launches are therefore
+// captured from the caller's stream (relaxed mode: nothing else of the process is disturbed), the captured graph
+// UPDATES the executable graph kept in `cache` (same topology step after step; only kernel arguments, grids and — for
+// the density-dependent kernel variants — functions change, which cudaGraphExecUpdate applies in place), and the
+// step runs as one graph launch: dependent kernels start back to back without a launch round trip each.  When the
+// topology did change (another model, dropout switched on) the executable graph is rebuilt.  Same kernels, same
+// arguments, same order: results are bit-identical to etpgt_gt_step_run.
+struct etpgt_graph {
+  cudaGraphExec_t exec = nullptr;
+  long long launches = 0, rebuilds = 0;
+};
+
+extern "C" int etpgt_graph_create(etpgt_graph_t** out) {
+  ETPGT_REQUIRE(out != nullptr, "graph_create: null output");
+  *out = new etpgt_graph();
+  return ETPGT_OK;
+}
+
+extern "C" int etpgt_graph_destroy(etpgt_graph_t* g) {
+  if (g == nullptr) return ETPGT_OK;
+  if (g->exec) cudaGraphExecDestroy(g->exec);
+  (void)cudaGetLastError();
+  delete g;
+  return ETPGT_OK;
+}
+
+extern "C" int64_t etpgt_graph_rebuilds(const etpgt_graph_t* g) { return g ? g->rebuilds : 0; }
+
+extern "C" int etpgt_gt_step_run_graph(const etpgt_gt_step_t* sp, int phase_begin, int phase_end, etpgt_graph_t* cache,
+                                       etpgt_stream_t stream_) {
+  ETPGT_REQUIRE(cache != nullptr, "gt_step_run_graph: null graph cache");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ETPGT_REQUIRE(stream != nullptr, "gt_step_run_graph: the legacy default stream cannot be captured; run on a stream");
+  TRY(check(sp));   // argument errors before a capture is open
+  cudaError_t e = cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed);
+  if (e != cudaSuccess) {
+    set_error("gt_step_run_graph: cudaStreamBeginCapture: %s", cudaGetErrorString(e));
+    return ETPGT_ECUDA;
+  }
+  const int rc = etpgt_gt_step_run(sp, phase_begin, phase_end, stream_);
+  cudaGraph_t graph = nullptr;
+  e = cudaStreamEndCapture(stream, &graph);
+  if (rc != ETPGT_OK) {
+    if (graph) cudaGraphDestroy(graph);
+    (void)cudaGetLastError();
+    return rc;
+  }
+  if (e != cudaSuccess || graph == nullptr) {
+    set_error("gt_step_run_graph: cudaStreamEndCapture: %s", cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return ETPGT_ECUDA;
+  }
+  bool ready = false;
+  if (cache->exec != nullptr) {
+    cudaGraphExecUpdateResultInfo info;
+    if (cudaGraphExecUpdate(cache->exec, graph, &info) == cudaSuccess) {
+      ready = true;
+    } else {
+      (void)cudaGetLastError();
+      cudaGraphExecDestroy(cache->exec);
+      cache->exec = nullptr;
+    }
+  }
+  if (!ready) {
+    e = cudaGraphInstantiate(&cache->exec, graph, 0);
+    if (e != cudaSuccess) {
+      set_error("gt_step_run_graph: cudaGraphInstantiate: %s", cudaGetErrorString(e));
+      cudaGraphDestroy(graph);
+      cache->exec = nullptr;
+      (void)cudaGetLastError();
+      return ETPGT_ECUDA;
+    }
+    ++cache->rebuilds;
+  }
+  cudaGraphDestroy(graph);
+  e = cudaGraphLaunch(cache->exec, stream);
+  if (e != cudaSuccess) {
+    set_error("gt_step_run_graph: cudaGraphLaunch: %s", cudaGetErrorString(e));
+    return ETPGT_ECUDA;
+  }
+  ++cache->launches;
+  return ETPGT_OK;
+}

@@ -92,6 +92,10 @@ _PROTOTYPES = {
     "etpgt_gt_step_arena_bytes": (Z, [P]),
     "etpgt_gt_step_num_phases": (I, [P]),
     "etpgt_gt_step_run": (I, [P, I, I, P]),
+    "etpgt_graph_create": (I, [P]),
+    "etpgt_graph_destroy": (I, [P]),
+    "etpgt_graph_rebuilds": (L, [P]),
+    "etpgt_gt_step_run_graph": (I, [P, I, I, P, P]),
     "etpgt_adam_step": (I, [P, I, D, D, D, D, D, I, L, I, P]),
     "etpgt_topk_merge_parts": (I, [P, I, Z, Z, L, I, L, L, P, P, P, P, P]),
     "etpgt_hit_metrics": (I, [P, L, I, P, P]),

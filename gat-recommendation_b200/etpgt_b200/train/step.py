@@ -22,6 +22,7 @@ Configurations the driver does not cover (FFN, attention readout, per-node PE, e
 from __future__ import annotations
 
 import ctypes
+import weakref
 from ctypes import c_double, c_float, c_int32, c_int64, c_size_t, c_uint64, c_void_p
 
 import torch
@@ -78,7 +79,14 @@ def _addr(t: torch.Tensor | None):
 
 
 class FusedTrainStep:
-    def __init__(self, model: GraphTransformer, loss: str = "bpr", alpha: float = 0.7, temperature: float = 1.0):
+    # batches up to this many nodes run as ONE CUDA graph launch (graph="auto"): below it the step is bound by the
+    # gaps between its ~55 microsecond kernels, above it by the kernels themselves
+    GRAPH_MAX_NODES = 24_576
+
+    def __init__(self, model: GraphTransformer, loss: str = "bpr", alpha: float = 0.7, temperature: float = 1.0,
+                 graph: bool | str = "auto"):
+        """graph: True / False / "auto" — run the step's launches as one CUDA graph (etpgt_gt_step_run_graph;
+        bit-identical results).  "auto": for batches of at most GRAPH_MAX_NODES nodes."""
         why = self.unsupported_reason(model)
         if why:
             raise NotImplementedError(f"FusedTrainStep: {why}")
@@ -93,6 +101,8 @@ class FusedTrainStep:
         self._flat_key = None
         self._desc = _GtStep()
         self._desc.struct_bytes = ctypes.sizeof(_GtStep)
+        self.graph = graph
+        self._graph_cache, self._graph_stream = None, None
 
     # ------------------------------------------------------------------ what the driver covers
     @staticmethod
@@ -303,7 +313,10 @@ class FusedTrainStep:
         self._table_work = None
         if not distributed or peer is not None:
             # one host call; under peer-memory data parallelism the driver exchanges the BatchNorm sums itself
-            _lib.call("etpgt_gt_step_run", ctypes.byref(d), 0, phases, stream())
+            if self.graph is True or (self.graph == "auto" and n <= self.GRAPH_MAX_NODES):
+                self._run_graph(phases)
+            else:
+                _lib.call("etpgt_gt_step_run", ctypes.byref(d), 0, phases, stream())
             if peer is not None and backward:
                 peer.flat_dirty = True
         else:
@@ -325,6 +338,30 @@ class FusedTrainStep:
                 p.grad += old
         self.session_embeddings = sess
         return losses
+
+    def _run_graph(self, phases: int) -> None:
+        """All phases as one CUDA graph launch.  The legacy default stream cannot be captured, so from there the step
+        runs on a stream of its own, ordered after and before the caller's stream."""
+        if self._graph_cache is None:
+            handle = ctypes.c_void_p()
+            _lib.call("etpgt_graph_create", ctypes.byref(handle))
+            self._graph_cache = handle
+            self._graph_finalizer = weakref.finalize(self, _lib.load().etpgt_graph_destroy, handle)
+        cur = torch.cuda.current_stream()
+        if cur.cuda_stream != 0:
+            _lib.call("etpgt_gt_step_run_graph", ctypes.byref(self._desc), 0, phases, self._graph_cache, stream())
+            return
+        if self._graph_stream is None or self._graph_stream.device != cur.device:
+            self._graph_stream = torch.cuda.Stream(device=cur.device)
+        side = self._graph_stream
+        side.wait_stream(cur)
+        _lib.call("etpgt_gt_step_run_graph", ctypes.byref(self._desc), 0, phases, self._graph_cache,
+                  ctypes.c_void_p(side.cuda_stream))
+        cur.wait_stream(side)
+
+    def graph_rebuilds(self) -> int:
+        """Instantiations of the executable graph so far (1 in a steady loop; every other step only updates it)."""
+        return 0 if self._graph_cache is None else int(_lib.load().etpgt_graph_rebuilds(self._graph_cache))
 
     def allreduce_gradients(self, group=None) -> None:
         """Data parallelism: sums the dense gradients (one flat buffer) and the table gradient across ranks.

@@ -587,6 +587,19 @@ size_t etpgt_gt_step_arena_bytes(const etpgt_gt_step_t* step);
 int etpgt_gt_step_num_phases(const etpgt_gt_step_t* step);
 int etpgt_gt_step_run(const etpgt_gt_step_t* step, int phase_begin, int phase_end, etpgt_stream_t stream);
 
+/* The same phases as ONE CUDA graph launch, for small batches (the reference trains at 32 sessions per step,
+ * params.yaml:6) where the step is bound by the ~55 launch gaps between microsecond kernels: the driver's launches
+ * are captured from `stream` (which must not be the legacy default stream), the capture updates the executable
+ * graph kept in `cache` in place (kernel arguments / grids / variants change from batch to batch, the topology does
+ * not; it is rebuilt when it does) and is launched once.  Bit-identical to etpgt_gt_step_run.  A cache belongs to
+ * one model / stream; etpgt_graph_rebuilds counts instantiations (1 in a steady loop). */
+typedef struct etpgt_graph etpgt_graph_t;
+int etpgt_graph_create(etpgt_graph_t** out);
+int etpgt_graph_destroy(etpgt_graph_t* cache);
+int64_t etpgt_graph_rebuilds(const etpgt_graph_t* cache);
+int etpgt_gt_step_run_graph(const etpgt_gt_step_t* step, int phase_begin, int phase_end, etpgt_graph_t* cache,
+                            etpgt_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -315,3 +315,46 @@ def test_driver_edge_cases_match_the_autograd_path():
         from etpgt_b200 import ops
         ops.prepare_batch(prepared, 300)
         _assert_identical(want, _driver_step(model, prepared, "dual", seed=21))
+
+
+@pytest.mark.parametrize("on_side_stream", [False, True])
+def test_graph_launch_is_bit_identical_and_only_updates_its_graph(on_side_stream):
+    """etpgt_gt_step_run_graph: the step's launches captured and run as ONE CUDA graph launch — same bits as the
+    plain driver for batches of different sizes (the executable graph is updated in place, not rebuilt), from the
+    legacy default stream (the step moves to a stream of its own) and from a side stream."""
+    from etpgt_b200 import data, ops, synth
+    from etpgt_b200.model import create_graph_transformer_optimized
+    from etpgt_b200.train.step import FusedTrainStep
+
+    d = synth.generate(num_sessions=800, graph_sessions=600, num_items=500, clusters=20, seed=3)
+    graph = data.ItemGraph(d.item_i, d.item_j, d.num_items)
+    store = data.SessionStore(d.sess_ptr, d.sess_items)
+    torch.manual_seed(0)
+    model = create_graph_transformer_optimized(d.num_items, 64, 64, dropout=0.1, laplacian_k=8).cuda()
+    model.laplacian_pe._cached_pe = torch.randn(d.num_items, 8, device="cuda").abs()
+    model.train()
+
+    def batch_of(first, count):
+        ids = np.arange(first, first + count)
+        batch = data.build_batch(graph, store, ids)
+        batch.negative_items = data.sample_negatives(store, ids, d.num_items, 5, seed=1, step=first)
+        ops.prepare_batch(batch, d.num_items)
+        return batch
+
+    plain, graphed = FusedTrainStep(model, "dual", graph=False), FusedTrainStep(model, "dual", graph=True)
+    stream = torch.cuda.Stream() if on_side_stream else torch.cuda.current_stream()
+    for first, count in [(0, 32), (100, 257), (400, 32), (40, 300), (500, 2)]:
+        results = []
+        for step in (plain, graphed):
+            _reset(model)
+            torch.manual_seed(5)
+            torch.cuda.synchronize()
+            with torch.cuda.stream(stream):
+                losses = step(batch_of(first, count))
+            torch.cuda.synchronize()
+            results.append((losses.clone(), step.session_embeddings.clone(), _snapshot(model)))
+        _assert_identical(*results)
+    assert graphed.graph_rebuilds() == 1 and plain.graph_rebuilds() == 0
+    # "auto" graphs small batches only
+    auto = FusedTrainStep(model, "bpr")
+    assert auto.graph == "auto" and auto.GRAPH_MAX_NODES > 1000
