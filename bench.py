@@ -798,9 +798,10 @@ def scoring_roofline(model, device, num_items, sessions=23_861, k=20, reps=10):
             "sessions_per_s": sessions / (ms / 1e3)}
 
 
-def time_tconv(qkvs, w_beta, index, device, reps=20):
+def time_tconv(qkvs, w_beta, index, device, reps=20, hubs=True):
     """Average CUDA-event time (ms) of the fused TransformerConv forward and backward launches on
-    torch's current stream, L2 flushed between repetitions."""
+    torch's current stream, L2 flushed between repetitions.  hubs: rows of more than 256 edges go through the
+    hub-row kernels (the product path whenever a graph has such rows); False times the plain row kernels."""
     from etpgt_b200._lib import call, ptr, size, stream, workspace
 
     n, e = index.num_nodes, index.num_edges
@@ -809,16 +810,21 @@ def time_tconv(qkvs, w_beta, index, device, reps=20):
     beta, m, inv_l = torch.empty(n, **f32), torch.empty(n, HEADS, **f32), torch.empty(n, HEADS, **f32)
     d_out, d_qkvs, d_wb = torch.randn(n, DIM, **f32), torch.empty_like(qkvs), torch.empty(3 * DIM, **f32)
     ws = workspace(size("etpgt_tconv_bwd_workspace_bytes", n, e, DIM, HEADS), device)
+    plan = index.hub_plan() if hubs else None
+    hub_ws = workspace(size("etpgt_tconv_hub_workspace_bytes", e, DIM), device) if plan is not None else None
+    hub_bytes = hub_ws.numel() if hub_ws is not None else 0
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
 
     def fwd():
-        call("etpgt_tconv_fwd", ptr(qkvs), n, DIM, HEADS, ptr(index.rowptr), ptr(index.col), ptr(index.eperm), e,
-             ptr(w_beta), None, ptr(out), ptr(agg), ptr(beta), ptr(m), ptr(inv_l), stream())
+        call("etpgt_tconv_fwd_hub", ptr(qkvs), n, DIM, HEADS, ptr(index.rowptr), ptr(index.col), ptr(index.eperm), e,
+             ptr(w_beta), None, ptr(out), ptr(agg), ptr(beta), ptr(m), ptr(inv_l), ptr(plan), ptr(hub_ws), hub_bytes,
+             stream())
 
     def bwd():
-        call("etpgt_tconv_bwd", ptr(qkvs), ptr(d_out), n, DIM, HEADS, ptr(index.rowptr), ptr(index.col),
+        call("etpgt_tconv_bwd_split_hub", ptr(qkvs), ptr(d_out), n, DIM, HEADS, ptr(index.rowptr), ptr(index.col),
              ptr(index.eperm), ptr(index.colptr), ptr(index.row), ptr(index.cpos), e, ptr(w_beta), None, ptr(agg),
-             ptr(beta), ptr(m), ptr(inv_l), ptr(d_qkvs), ptr(d_wb), ptr(ws), ws.numel(), stream())
+             ptr(beta), ptr(m), ptr(inv_l), ptr(d_qkvs), None, None, None, ptr(d_wb), ptr(ws), ws.numel(), ptr(plan),
+             ptr(hub_ws), hub_bytes, stream())
 
     return _time_launches(fwd, flush, reps), _time_launches(bwd, flush, reps)
 
@@ -900,7 +906,27 @@ def tconv_roofline(model, batch, data, device, num_items, global_graph=True):
     out["global_graph"] = {"nodes": gindex.num_nodes, "edges": gindex.num_edges, "ms_fwd": gf, "ms_bwd": gb,
                            "achieved": g_ach, "frac": g_ach / pk["hbm_gbs"],
                            "edges_per_s_fwd": gindex.num_edges / (gf / 1e3),
-                           "edges_per_s_fwd_bwd": gindex.num_edges / ((gf + gb) / 1e3)}
+                           "edges_per_s_fwd_bwd": gindex.num_edges / ((gf + gb) / 1e3),
+                           "max_degree": int(torch.diff(gindex.rowptr).max().item()),
+                           "hub_rows": gindex.hub_plan() is not None}
+    # (c) the same node / edge counts with the popularity law of the reference's generator (zipf(1.5) weights,
+    # scripts/data/00_generate_synthetic_data.py:53): rows of 10,000+ edges, cut into chunks by the hub-row kernels;
+    # `serial_rows` is the same graph through the plain row kernels (one lane group per row)
+    zi, zj = load_synth().zipf_graph(data.num_items, len(data.item_i))
+    zsrc = torch.from_numpy(np.concatenate([zi, zj])).to(device)
+    zdst = torch.from_numpy(np.concatenate([zj, zi])).to(device)
+    zindex = ops.GraphIndex(torch.stack([zsrc, zdst]), data.num_items)
+    zf, zb = time_tconv(gq, w_beta, zindex, device, reps=10)
+    sf, sb = time_tconv(gq, w_beta, zindex, device, reps=3, hubs=False)
+    zbf, zbb = tconv_bytes(zindex.num_nodes, zindex.num_edges)
+    z_ach = (zbf + zbb) / ((zf + zb) / 1e3) / 1e9
+    counts = zindex.hub_plan()[:16].view(torch.int32).tolist() if zindex.hub_plan() is not None else [0, 0, 0, 0]
+    out["zipf_graph"] = {"nodes": zindex.num_nodes, "edges": zindex.num_edges, "ms_fwd": zf, "ms_bwd": zb,
+                         "achieved": z_ach, "frac": z_ach / pk["hbm_gbs"], "vs_global_graph": z_ach / g_ach,
+                         "max_degree": int(torch.diff(zindex.rowptr).max().item()),
+                         "hub_destinations": counts[0], "hub_chunks": counts[1],
+                         "serial_rows": {"ms_fwd": sf, "ms_bwd": sb,
+                                         "achieved": (zbf + zbb) / ((sf + sb) / 1e3) / 1e9}}
     return out
 
 

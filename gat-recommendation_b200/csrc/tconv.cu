@@ -14,42 +14,18 @@
 #include <cuda_bf16.h>
 #include <math.h>
 
-#include "common.cuh"
+#include <limits.h>
+
+#include "tconv.cuh"
+
+#define TRY_RC(expr)                   \
+  do {                                 \
+    int rc__ = (expr);                 \
+    if (rc__ != ETPGT_OK) return rc__; \
+  } while (0)
 
 namespace etpgt {
 namespace {
-
-constexpr int kThreads = 256;
-constexpr int kEdgeUnroll = 4;
-constexpr float kSoftmaxEps = 1e-16f;  // PyG utils.softmax: p / (sum + 1e-16)
-
-template <int DIM>
-__device__ __forceinline__ void load_row(const float* __restrict__ row, int lig, float4 (&dst)[RowGeom<DIM>::V]) {
-#pragma unroll
-  for (int v = 0; v < RowGeom<DIM>::V; ++v) dst[v] = ldg4(row + 4 * (v * RowGeom<DIM>::LPN + lig));
-}
-
-// Gradient row store: fp32 (d_qkvs) or, for the tensor-core projection backward, already split as
-// x = hi + lo with hi = bf16(x), lo = bf16(x - hi) (what etpgt_split_bf16 would produce from the fp32
-// row) so that the [N, 4*DIM] gradient never makes a second trip through HBM.
-__device__ __forceinline__ uint2 pack_bf16x4(float a, float b, float c, float d) {
-  __nv_bfloat162 p0 = __floats2bfloat162_rn(a, b), p1 = __floats2bfloat162_rn(c, d);
-  uint2 r;
-  r.x = *reinterpret_cast<uint32_t*>(&p0);
-  r.y = *reinterpret_cast<uint32_t*>(&p1);
-  return r;
-}
-__device__ __forceinline__ void store_grad4(float* __restrict__ d_f32, __nv_bfloat16* __restrict__ d_hi,
-                                            __nv_bfloat16* __restrict__ d_lo, int64_t offset, float4 g) {
-  if (d_hi != nullptr) {
-    const float hx = __bfloat162float(__float2bfloat16_rn(g.x)), hy = __bfloat162float(__float2bfloat16_rn(g.y));
-    const float hz = __bfloat162float(__float2bfloat16_rn(g.z)), hw = __bfloat162float(__float2bfloat16_rn(g.w));
-    *reinterpret_cast<uint2*>(d_hi + offset) = pack_bf16x4(hx, hy, hz, hw);
-    *reinterpret_cast<uint2*>(d_lo + offset) = pack_bf16x4(g.x - hx, g.y - hy, g.z - hz, g.w - hw);
-  } else {
-    st4(d_f32 + offset, g);
-  }
-}
 
 // ------------------------------------------------------------------------------- forward
 template <int DIM, int HEAD_DIM, int UNROLL>
@@ -58,12 +34,9 @@ tconv_fwd_kernel(const float* __restrict__ qkvs, int64_t num_nodes, const int32_
                  const int32_t* __restrict__ col, const int32_t* __restrict__ eperm,
                  const float* __restrict__ w_beta, const float* __restrict__ alpha_mask,
                  float* __restrict__ out, float* __restrict__ agg_out, float* __restrict__ beta_out,
-                 float* __restrict__ m_out, float* __restrict__ invl_out) {
+                 float* __restrict__ m_out, float* __restrict__ invl_out, int hub_threshold) {
   using G = RowGeom<DIM>;
   constexpr int V = G::V, LPN = G::LPN;
-  constexpr int HEADS = DIM / HEAD_DIM;
-  constexpr int HEAD_F4 = HEAD_DIM / 4;
-  const float scale = rsqrtf((float)HEAD_DIM);
   const int lane = threadIdx.x & 31;
   const int lig = lane % LPN;
   const int64_t warp_global = (blockIdx.x * (int64_t)kThreads + threadIdx.x) >> 5;
@@ -76,7 +49,9 @@ tconv_fwd_kernel(const float* __restrict__ qkvs, int64_t num_nodes, const int32_
   float4 q[V];
   load_row<DIM>(self, lig, q);
   const int begin = valid ? rowptr[nrow] : 0;
-  const int deg = valid ? rowptr[nrow + 1] - begin : 0;
+  int deg = valid ? rowptr[nrow + 1] - begin : 0;
+  const bool hub = deg > hub_threshold;   // cut into chunks by the hub kernels (tconv_hub.cu), skipped here
+  if (hub) deg = 0;
   int deg_max = deg;
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) deg_max = max(deg_max, __shfl_xor_sync(0xffffffffu, deg_max, off));
@@ -85,75 +60,9 @@ tconv_fwd_kernel(const float* __restrict__ qkvs, int64_t num_nodes, const int32_
   float4 acc[V];
 #pragma unroll
   for (int v = 0; v < V; ++v) { m[v] = -INFINITY; l[v] = 0.f; acc[v] = zero4(); }
-
-  for (int e0 = 0; e0 < deg_max; e0 += UNROLL) {
-    float4 kr[UNROLL][V], vr[UNROLL][V];
-    int pos[UNROLL];
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const bool on = e0 + u < deg;
-      pos[u] = on ? begin + e0 + u : -1;
-      const int64_t j = on ? col[pos[u]] : nrow;
-      const float* other = qkvs + j * 4 * DIM;
-      load_row<DIM>(other + DIM, lig, kr[u]);
-      load_row<DIM>(other + 2 * DIM, lig, vr[u]);
-    }
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      float a[V];
-#pragma unroll
-      for (int v = 0; v < V; ++v) a[v] = dot4(q[v], kr[u][v]);
-      head_reduce<DIM, HEAD_DIM>(a);
-      if (pos[u] >= 0) {
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-          const float logit = a[v] * scale;
-          const float m_new = fmaxf(m[v], logit);
-          const float corr = expf(m[v] - m_new);
-          float p = expf(logit - m_new);
-          l[v] = l[v] * corr + p;
-          if (alpha_mask != nullptr)
-            p *= alpha_mask[(int64_t)eperm[pos[u]] * HEADS + head_of<DIM, HEAD_DIM>(v, lig)];
-          acc[v] = fma4(p, vr[u][v], scale4(corr, acc[v]));
-          m[v] = m_new;
-        }
-      }
-    }
-  }
-
-  float4 xr[V], ag[V];
-  load_row<DIM>(self + 3 * DIM, lig, xr);
-  float zpart = 0.f;
-#pragma unroll
-  for (int v = 0; v < V; ++v) {
-    const float inv = 1.f / (l[v] + kSoftmaxEps);
-    ag[v] = scale4(inv, acc[v]);
-    const int f = v * LPN + lig;
-    if (valid && f % HEAD_F4 == 0) {
-      m_out[nrow * HEADS + f / HEAD_F4] = m[v];
-      invl_out[nrow * HEADS + f / HEAD_F4] = inv;
-    }
-    if (w_beta != nullptr) {
-      const float4 w1 = ldg4(w_beta + 4 * f), w2 = ldg4(w_beta + DIM + 4 * f), w3 = ldg4(w_beta + 2 * DIM + 4 * f);
-      zpart += dot4(w1, ag[v]) + dot4(w2, xr[v]) + dot4(w3, sub4(ag[v], xr[v]));
-    }
-  }
-  float b = 0.f;
-  if (w_beta != nullptr) {
-    const float z = group_sum<LPN>(zpart);
-    b = 1.f / (1.f + expf(-z));
-  }
-  if (!valid) return;
-#pragma unroll
-  for (int v = 0; v < V; ++v) {
-    const int f = v * LPN + lig;
-    float4 o;
-    if (w_beta != nullptr) o = add4(scale4(b, xr[v]), scale4(1.f - b, ag[v]));
-    else o = add4(ag[v], xr[v]);
-    st4(out + nrow * DIM + 4 * f, o);
-    st4(agg_out + nrow * DIM + 4 * f, ag[v]);
-  }
-  if (lig == 0 && beta_out != nullptr) beta_out[nrow] = b;
+  fwd_edges<DIM, HEAD_DIM, UNROLL>(qkvs, q, col, eperm, alpha_mask, begin, deg, deg_max, nrow, lig, m, l, acc);
+  fwd_epilogue<DIM, HEAD_DIM>(self, valid && !hub, nrow, lig, m, l, acc, w_beta, out, agg_out, beta_out, m_out,
+                              invl_out);
 }
 
 // ------------------------------------------------------------ backward, destination pass
@@ -171,12 +80,11 @@ tconv_bwd_dst_kernel(const float* __restrict__ qkvs, const float* __restrict__ d
                      const float* __restrict__ invl_in, float* __restrict__ d_qkvs,
                      __nv_bfloat16* __restrict__ d_hi, __nv_bfloat16* __restrict__ d_lo,
                      float* __restrict__ d_agg_out, float2* __restrict__ ecoef,
-                     float* __restrict__ partial /* [grid][(w_beta ? 3 : 0) + (COLSUM ? 2 : 0)][DIM] */) {
+                     float* __restrict__ partial /* [grid][(w_beta ? 3 : 0) + (COLSUM ? 2 : 0)][DIM] */,
+                     int hub_threshold) {
   using G = RowGeom<DIM>;
   constexpr int V = G::V, LPN = G::LPN;
   constexpr int HEADS = DIM / HEAD_DIM;
-  constexpr int HEAD_F4 = HEAD_DIM / 4;
-  const float scale = rsqrtf((float)HEAD_DIM);
   const int lane = threadIdx.x & 31;
   const int lig = lane % LPN;
   const int warp_in_cta = threadIdx.x >> 5;
@@ -253,48 +161,18 @@ tconv_bwd_dst_kernel(const float* __restrict__ qkvs, const float* __restrict__ d
     head_reduce<DIM, HEAD_DIM>(delta);
 
     const int begin = valid ? rowptr[nrow] : 0;
-    const int deg = valid ? rowptr[nrow + 1] - begin : 0;
+    int deg = valid ? rowptr[nrow + 1] - begin : 0;
+    const bool hub = deg > hub_threshold;   // edges, d_query and its column sums: the hub kernels (tconv_hub.cu)
+    if (hub) deg = 0;
     int deg_max = deg;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) deg_max = max(deg_max, __shfl_xor_sync(0xffffffffu, deg_max, off));
     float4 dq[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) dq[v] = zero4();
-
-    for (int e0 = 0; e0 < deg_max; e0 += UNROLL) {
-      float4 kr[UNROLL][V], vr[UNROLL][V];
-      int pos[UNROLL];
-#pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        const bool on = e0 + u < deg;
-        pos[u] = on ? begin + e0 + u : -1;
-        const int64_t j = on ? col[pos[u]] : nrow;
-        const float* other = qkvs + j * 4 * DIM;
-        load_row<DIM>(other + DIM, lig, kr[u]);
-        load_row<DIM>(other + 2 * DIM, lig, vr[u]);
-      }
-#pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        float a[V], da[V];
-#pragma unroll
-        for (int v = 0; v < V; ++v) { a[v] = dot4(q[v], kr[u][v]); da[v] = dot4(dag[v], vr[u][v]); }
-        head_reduce<DIM, HEAD_DIM>(a);
-        head_reduce<DIM, HEAD_DIM>(da);
-        if (pos[u] >= 0) {
-#pragma unroll
-          for (int v = 0; v < V; ++v) {
-            const float alpha = expf(a[v] * scale - mh[v]) * il[v];
-            float mask = 1.f;
-            const int h = head_of<DIM, HEAD_DIM>(v, lig);
-            if (alpha_mask != nullptr) mask = alpha_mask[(int64_t)eperm[pos[u]] * HEADS + h];
-            const float dlogit = alpha * (da[v] * mask - delta[v]) * scale;
-            dq[v] = fma4(dlogit, kr[u][v], dq[v]);
-            if ((v * LPN + lig) % HEAD_F4 == 0) ecoef[(int64_t)pos[u] * HEADS + h] = make_float2(alpha * mask, dlogit);
-          }
-        }
-      }
-    }
-    if (valid) {
+    bwd_dst_edges<DIM, HEAD_DIM, UNROLL>(qkvs, q, dag, delta, mh, il, col, eperm, alpha_mask, begin, deg, deg_max, nrow,
+                                         lig, ecoef, dq);
+    if (valid && !hub) {
 #pragma unroll
       for (int v = 0; v < V; ++v) {
         store_grad4(d_qkvs, d_hi, d_lo, nrow * 4 * DIM + 4 * (v * LPN + lig), dq[v]);
@@ -370,10 +248,9 @@ tconv_bwd_src_kernel(const float* __restrict__ qkvs, int64_t num_nodes, const in
                      const int32_t* __restrict__ row, const int32_t* __restrict__ cpos,
                      const float* __restrict__ d_agg, const float2* __restrict__ ecoef,
                      float* __restrict__ d_qkvs, __nv_bfloat16* __restrict__ d_hi, __nv_bfloat16* __restrict__ d_lo,
-                     float* __restrict__ colsum_partial /* [grid][2*DIM] or NULL */) {
+                     float* __restrict__ colsum_partial /* [grid][2*DIM] or NULL */, int hub_threshold) {
   using G = RowGeom<DIM>;
   constexpr int V = G::V, LPN = G::LPN;
-  constexpr int HEADS = DIM / HEAD_DIM;
   const int lane = threadIdx.x & 31;
   const int lig = lane % LPN;
   const int64_t nodes_per_cta = (kThreads / 32) * G::GROUPS;
@@ -386,35 +263,11 @@ tconv_bwd_src_kernel(const float* __restrict__ qkvs, int64_t num_nodes, const in
     const int64_t node = base + (threadIdx.x >> 5) * G::GROUPS + lane / LPN;
     if (node >= num_nodes) continue;
     const int begin = colptr[node], end = colptr[node + 1];
+    if (end - begin > hub_threshold) continue;   // a hub source: tconv_hub.cu
     float4 dk[V], dv[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) { dk[v] = zero4(); dv[v] = zero4(); }
-    for (int p0 = begin; p0 < end; p0 += kEdgeUnroll) {
-      float4 qr[kEdgeUnroll][V], gr[kEdgeUnroll][V];
-      float2 c[kEdgeUnroll][V];
-#pragma unroll
-      for (int u = 0; u < kEdgeUnroll; ++u) {
-        const bool on = p0 + u < end;
-        const int p = on ? p0 + u : begin;
-        const int64_t i = row[p];
-        const int64_t e = cpos[p];
-        load_row<DIM>(qkvs + i * 4 * DIM, lig, qr[u]);
-        load_row<DIM>(d_agg + i * DIM, lig, gr[u]);
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-          c[u][v] = ecoef[e * HEADS + head_of<DIM, HEAD_DIM>(v, lig)];
-          if (!on) c[u][v] = make_float2(0.f, 0.f);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < kEdgeUnroll; ++u) {
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-          dk[v] = fma4(c[u][v].y, qr[u][v], dk[v]);
-          dv[v] = fma4(c[u][v].x, gr[u][v], dv[v]);
-        }
-      }
-    }
+    bwd_src_edges<DIM, HEAD_DIM>(qkvs, d_agg, ecoef, row, cpos, begin, end, lig, dk, dv);
 #pragma unroll
     for (int v = 0; v < V; ++v) {
       store_grad4(d_qkvs, d_hi, d_lo, node * 4 * DIM + DIM + 4 * (v * LPN + lig), dk[v]);
@@ -453,50 +306,75 @@ int dst_pass_grid(int64_t num_nodes, int nodes_per_cta, bool sparse) {
 
 using namespace etpgt;
 
-extern "C" int etpgt_tconv_fwd(const float* qkvs, int64_t num_nodes, int dim, int heads,
-                               const int32_t* rowptr, const int32_t* col, const int32_t* eperm,
-                               int64_t num_edges, const float* w_beta, const float* alpha_mask, float* out,
-                               float* agg, float* beta, float* m, float* inv_l, etpgt_stream_t stream_) {
+extern "C" size_t etpgt_tconv_hub_workspace_bytes(int64_t num_edges, int dim) {
+  // per-chunk partials: forward (m, l, acc) = dim + 16 floats, backward dst dq = dim, backward src (dk | dv) = 2*dim
+  const int row = 2 * dim > dim + 16 ? 2 * dim : dim + 16;
+  return align_up((size_t)hub_cap_chunks(num_edges < 0 ? 0 : num_edges) * row * sizeof(float)) + 256;
+}
+
+extern "C" int etpgt_tconv_fwd_hub(const float* qkvs, int64_t num_nodes, int dim, int heads,
+                                   const int32_t* rowptr, const int32_t* col, const int32_t* eperm,
+                                   int64_t num_edges, const float* w_beta, const float* alpha_mask, float* out,
+                                   float* agg, float* beta, float* m, float* inv_l, const void* hub_plan,
+                                   void* hub_ws, size_t hub_ws_bytes, etpgt_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ETPGT_REQUIRE(num_nodes >= 0 && num_edges >= 0, "tconv_fwd: negative size");
   ETPGT_REQUIRE(qkvs && rowptr && out && agg && m && inv_l, "tconv_fwd: null pointer");
   ETPGT_REQUIRE(num_edges == 0 || (col && eperm), "tconv_fwd: null edge arrays");
   ETPGT_REQUIRE(w_beta == nullptr || beta != nullptr, "tconv_fwd: beta output required with w_beta");
+  ETPGT_REQUIRE(hub_plan == nullptr || (hub_ws != nullptr && hub_ws_bytes >= etpgt_tconv_hub_workspace_bytes(num_edges, dim)),
+                "tconv_fwd: hub workspace %zu < %zu", hub_ws_bytes, etpgt_tconv_hub_workspace_bytes(num_edges, dim));
   if (num_nodes == 0) return ETPGT_OK;
   const bool sparse = num_edges < 8 * num_nodes;  // session batches: short rows -> shallower unroll, more warps
+  const int hub_threshold = hub_plan != nullptr ? kHubThreshold : INT_MAX;
 #define CALL(D, C)                                                                               \
   {                                                                                              \
     const int64_t npc = (kThreads / 32) * RowGeom<D>::GROUPS;                                    \
     const int64_t grid = (num_nodes + npc - 1) / npc;                                            \
     if (sparse)                                                                                  \
       tconv_fwd_kernel<D, C, 2><<<(unsigned)grid, kThreads, 0, stream>>>(qkvs, num_nodes, rowptr, col, eperm,   \
-                                                                        w_beta, alpha_mask, out, agg, beta, m, inv_l); \
+                                                          w_beta, alpha_mask, out, agg, beta, m, inv_l, hub_threshold); \
     else                                                                                         \
       tconv_fwd_kernel<D, C, 4><<<(unsigned)grid, kThreads, 0, stream>>>(qkvs, num_nodes, rowptr, col, eperm,   \
-                                                                        w_beta, alpha_mask, out, agg, beta, m, inv_l); \
+                                                          w_beta, alpha_mask, out, agg, beta, m, inv_l, hub_threshold); \
   }
   ETPGT_DISPATCH_DIM_HEADS(dim, heads, CALL)
 #undef CALL
   ETPGT_CHECK_LAUNCH("tconv_fwd");
+  if (hub_plan != nullptr)
+    return tconv_fwd_hubs(qkvs, dim, heads, col, eperm, num_edges, w_beta, alpha_mask, out, agg, beta, m, inv_l, hub_plan,
+                          hub_ws, stream);
   return ETPGT_OK;
+}
+
+extern "C" int etpgt_tconv_fwd(const float* qkvs, int64_t num_nodes, int dim, int heads,
+                               const int32_t* rowptr, const int32_t* col, const int32_t* eperm,
+                               int64_t num_edges, const float* w_beta, const float* alpha_mask, float* out,
+                               float* agg, float* beta, float* m, float* inv_l, etpgt_stream_t stream) {
+  return etpgt_tconv_fwd_hub(qkvs, num_nodes, dim, heads, rowptr, col, eperm, num_edges, w_beta, alpha_mask, out, agg,
+                             beta, m, inv_l, nullptr, nullptr, 0, stream);
 }
 
 extern "C" size_t etpgt_tconv_bwd_workspace_bytes(int64_t num_nodes, int64_t num_edges, int dim, int heads) {
   const int64_t src_ctas = 8 * kNumSMs;  // the source pass runs a capped, persistent grid when it sums columns
   return align_up((size_t)num_nodes * dim * sizeof(float)) +
          align_up((size_t)(num_edges > 0 ? num_edges : 1) * heads * sizeof(float2)) +
-         align_up((size_t)kNumSMs * 4 * 5 * dim * sizeof(float)) +
-         align_up((size_t)src_ctas * 2 * dim * sizeof(float)) + 256;
+         align_up((size_t)(kNumSMs * 4 + kHubColsumCtas) * 5 * dim * sizeof(float)) +
+         align_up((size_t)(src_ctas + kHubColsumCtas) * 2 * dim * sizeof(float)) + 256;
 }
 
-extern "C" int etpgt_tconv_bwd_split(const float* qkvs, const float* d_out, int64_t num_nodes, int dim, int heads,
-                                     const int32_t* rowptr, const int32_t* col, const int32_t* eperm,
-                                     const int32_t* colptr, const int32_t* row, const int32_t* cpos,
-                                     int64_t num_edges, const float* w_beta, const float* alpha_mask,
-                                     const float* agg, const float* beta, const float* m, const float* inv_l,
-                                     float* d_qkvs, void* d_hi_, void* d_lo_, float* d_colsum, float* d_w_beta,
-                                     void* ws, size_t ws_bytes, etpgt_stream_t stream_) {
+extern "C" int etpgt_tconv_bwd_split_hub(const float* qkvs, const float* d_out, int64_t num_nodes, int dim, int heads,
+                                         const int32_t* rowptr, const int32_t* col, const int32_t* eperm,
+                                         const int32_t* colptr, const int32_t* row, const int32_t* cpos,
+                                         int64_t num_edges, const float* w_beta, const float* alpha_mask,
+                                         const float* agg, const float* beta, const float* m, const float* inv_l,
+                                         float* d_qkvs, void* d_hi_, void* d_lo_, float* d_colsum, float* d_w_beta,
+                                         void* ws, size_t ws_bytes, const void* hub_plan, void* hub_ws,
+                                         size_t hub_ws_bytes, etpgt_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ETPGT_REQUIRE(hub_plan == nullptr || (hub_ws != nullptr && hub_ws_bytes >= etpgt_tconv_hub_workspace_bytes(num_edges, dim)),
+                "tconv_bwd: hub workspace %zu < %zu", hub_ws_bytes, etpgt_tconv_hub_workspace_bytes(num_edges, dim));
+  const int hub_threshold = hub_plan != nullptr ? kHubThreshold : INT_MAX;
   __nv_bfloat16* d_hi = static_cast<__nv_bfloat16*>(d_hi_);
   __nv_bfloat16* d_lo = static_cast<__nv_bfloat16*>(d_lo_);
   ETPGT_REQUIRE(num_nodes >= 0 && num_edges >= 0, "tconv_bwd: negative size");
@@ -521,7 +399,7 @@ extern "C" int etpgt_tconv_bwd_split(const float* qkvs, const float* d_out, int6
   Workspace w(ws, ws_bytes);
   float* d_agg = w.take<float>((size_t)num_nodes * dim);
   float2* ecoef = w.take<float2>((size_t)(num_edges > 0 ? num_edges : 1) * heads);
-  float* partial = w.take<float>((size_t)kNumSMs * 4 * 5 * dim);
+  float* partial = w.take<float>((size_t)(kNumSMs * 4 + kHubColsumCtas) * 5 * dim);
   int grid_a = 1;
 #define CALL(D, C)                                                                                   \
   {                                                                                                  \
@@ -531,17 +409,26 @@ extern "C" int etpgt_tconv_bwd_split(const float* qkvs, const float* d_out, int6
     auto kern = sparse ? (want_colsum ? tconv_bwd_dst_kernel<D, C, 2, true> : tconv_bwd_dst_kernel<D, C, 2, false>) \
                        : (want_colsum ? tconv_bwd_dst_kernel<D, C, 4, true> : tconv_bwd_dst_kernel<D, C, 4, false>); \
     kern<<<grid_a, kThreads, smem, stream>>>(qkvs, d_out, num_nodes, rowptr, col, eperm, w_beta, alpha_mask, agg,    \
-                                             beta, m, inv_l, d_qkvs, d_hi, d_lo, d_agg, ecoef, partial);            \
+                                             beta, m, inv_l, d_qkvs, d_hi, d_lo, d_agg, ecoef, partial, hub_threshold); \
   }
   ETPGT_DISPATCH_DIM_HEADS(dim, heads, CALL)
 #undef CALL
   ETPGT_CHECK_LAUNCH("tconv_bwd_dst");
+  int parts_a = grid_a;
+  if (hub_plan != nullptr) {
+    // hub destinations: per-edge coefficients and d_query by chunks; their d_query column sums arrive as
+    // kHubColsumCtas more partial rows behind the row kernel's
+    TRY_RC(tconv_bwd_dst_hubs(qkvs, dim, heads, col, eperm, num_edges, alpha_mask, agg, m, inv_l, d_agg, ecoef, d_qkvs,
+                              d_hi, d_lo, want_colsum ? partial + (size_t)grid_a * width : nullptr, width, width_a,
+                              hub_plan, hub_ws, stream));
+    if (want_colsum) parts_a += kHubColsumCtas;
+  }
   if (width > 0) {  // d_w_beta [3*dim]; bias gradients of query -> d_colsum[0:dim], skip -> d_colsum[3*dim:4*dim]
-    reduce_partials_kernel<<<(width + 31) / 32, kReduceWarps * 32, 0, stream>>>(partial, grid_a, width, width_a, d_w_beta, d_colsum,
+    reduce_partials_kernel<<<(width + 31) / 32, kReduceWarps * 32, 0, stream>>>(partial, parts_a, width, width_a, d_w_beta, d_colsum,
                                                                  dim, 0, 3 * dim);
     ETPGT_CHECK_LAUNCH("tconv dst partial reduce");
   }
-  float* src_partial = want_colsum ? w.take<float>((size_t)8 * kNumSMs * 2 * dim) : nullptr;
+  float* src_partial = want_colsum ? w.take<float>((size_t)(8 * kNumSMs + kHubColsumCtas) * 2 * dim) : nullptr;
   int64_t grid_src = 1;
 #define CALL(D, C)                                                                                  \
   {                                                                                                 \
@@ -551,17 +438,35 @@ extern "C" int etpgt_tconv_bwd_split(const float* qkvs, const float* d_out, int6
     const size_t smem = want_colsum ? (size_t)npc * 2 * D * sizeof(float) : 0;                      \
     auto kern = want_colsum ? tconv_bwd_src_kernel<D, C, true> : tconv_bwd_src_kernel<D, C, false>; \
     kern<<<(unsigned)grid_src, kThreads, smem, stream>>>(qkvs, num_nodes, colptr, row, cpos, d_agg, ecoef, d_qkvs, \
-                                                         d_hi, d_lo, src_partial);                  \
+                                                         d_hi, d_lo, src_partial, hub_threshold);   \
   }
   ETPGT_DISPATCH_DIM_HEADS(dim, heads, CALL)
 #undef CALL
   ETPGT_CHECK_LAUNCH("tconv_bwd_src");
+  int parts_src = (int)grid_src;
+  if (hub_plan != nullptr) {
+    TRY_RC(tconv_bwd_src_hubs(qkvs, dim, heads, row, cpos, num_edges, d_agg, ecoef, d_qkvs, d_hi, d_lo,
+                              want_colsum ? src_partial + (size_t)grid_src * 2 * dim : nullptr, hub_plan, hub_ws, stream));
+    if (want_colsum) parts_src += kHubColsumCtas;
+  }
   if (want_colsum) {  // key -> d_colsum[dim:2*dim], value -> d_colsum[2*dim:3*dim]
-    reduce_partials_kernel<<<(2 * dim + 31) / 32, kReduceWarps * 32, 0, stream>>>(src_partial, (int)grid_src, 2 * dim, 0, nullptr,
+    reduce_partials_kernel<<<(2 * dim + 31) / 32, kReduceWarps * 32, 0, stream>>>(src_partial, parts_src, 2 * dim, 0, nullptr,
                                                                    d_colsum, dim, dim, 2 * dim);
     ETPGT_CHECK_LAUNCH("tconv src colsum reduce");
   }
   return ETPGT_OK;
+}
+
+extern "C" int etpgt_tconv_bwd_split(const float* qkvs, const float* d_out, int64_t num_nodes, int dim, int heads,
+                                     const int32_t* rowptr, const int32_t* col, const int32_t* eperm,
+                                     const int32_t* colptr, const int32_t* row, const int32_t* cpos,
+                                     int64_t num_edges, const float* w_beta, const float* alpha_mask,
+                                     const float* agg, const float* beta, const float* m, const float* inv_l,
+                                     float* d_qkvs, void* d_hi, void* d_lo, float* d_colsum, float* d_w_beta,
+                                     void* ws, size_t ws_bytes, etpgt_stream_t stream) {
+  return etpgt_tconv_bwd_split_hub(qkvs, d_out, num_nodes, dim, heads, rowptr, col, eperm, colptr, row, cpos, num_edges,
+                                   w_beta, alpha_mask, agg, beta, m, inv_l, d_qkvs, d_hi, d_lo, d_colsum, d_w_beta, ws,
+                                   ws_bytes, nullptr, nullptr, 0, stream);
 }
 
 extern "C" int etpgt_tconv_bwd(const float* qkvs, const float* d_out, int64_t num_nodes, int dim, int heads,

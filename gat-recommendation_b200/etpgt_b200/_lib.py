@@ -39,6 +39,13 @@ _PROTOTYPES = {
     "etpgt_tconv_bwd_workspace_bytes": (Z, [L, L, I, I]),
     "etpgt_tconv_bwd": (I, [P, P, L, I, I, P, P, P, P, P, P, L, P, P, P, P, P, P, P, P, P, Z, P]),
     "etpgt_tconv_bwd_split": (I, [P, P, L, I, I, P, P, P, P, P, P, L, P, P, P, P, P, P, P, P, P, P, P, P, Z, P]),
+    "etpgt_hub_plan_bytes": (Z, [L]),
+    "etpgt_hub_plan_workspace_bytes": (Z, [L]),
+    "etpgt_hub_plan": (I, [P, P, L, L, P, P, Z, P]),
+    "etpgt_tconv_hub_workspace_bytes": (Z, [L, I]),
+    "etpgt_tconv_fwd_hub": (I, [P, L, I, I, P, P, P, L, P, P, P, P, P, P, P, P, P, Z, P]),
+    "etpgt_tconv_bwd_split_hub": (I, [P, P, L, I, I, P, P, P, P, P, P, L, P, P, P, P, P, P, P, P, P, P, P, P, Z, P, P, Z,
+                                      P]),
     "etpgt_split_bf16_workspace_bytes": (Z, [L, L]),
     "etpgt_split_bf16": (I, [P, L, L, L, P, P, L, P, P, L, P, P, Z, P]),
     "etpgt_gemm_bf16x3_workspace_bytes": (Z, [L, L, L, I]),

@@ -46,7 +46,10 @@ class GraphIndex:
     """Destination-sorted CSR + source-sorted CSC of one batched graph, built once per batch on
     the device and shared by every conv layer (forward and backward)."""
 
-    __slots__ = ("num_nodes", "num_edges", "rowptr", "col", "eperm", "colptr", "row", "cpos", "slot", "generation")
+    __slots__ = ("num_nodes", "num_edges", "rowptr", "col", "eperm", "colptr", "row", "cpos", "slot", "generation",
+                 "_hub")
+
+    HUB_THRESHOLD = 256      # kHubThreshold of csrc/tconv.cuh
 
     def __init__(self, edge_index: torch.Tensor, num_nodes: int, out: torch.Tensor | None = None,
                  ws: torch.Tensor | None = None, build: bool = True):
@@ -60,6 +63,7 @@ class GraphIndex:
         num_nodes = int(num_nodes)
         self.num_nodes, self.num_edges = num_nodes, e
         self.slot, self.generation = None, 0      # set by prepare_batch when the arrays live in a BatchPreparer slot
+        self._hub = None
         if out is None:
             out = torch.empty(self.out_elems(num_nodes, e), dtype=torch.int32, device=dev)
         o1 = _pad64(num_nodes + 1)
@@ -78,6 +82,23 @@ class GraphIndex:
     @staticmethod
     def out_elems(num_nodes: int, num_edges: int) -> int:
         return 2 * _pad64(num_nodes + 1) + 4 * _pad64(num_edges)
+
+    def hub_plan(self) -> torch.Tensor | None:
+        """The hub-row plan of this graph (etpgt_hub_plan: destinations / sources with more than 256 edges cut into
+        chunks) or None when it has no such row.  Built at first use and kept with the index; costs one host read
+        of the four counts (session batches, whose rows have at most 51 edges, answer None every time)."""
+        if self._hub is None:
+            self._hub = False
+            if self.num_edges > self.HUB_THRESHOLD:
+                dev = self.rowptr.device
+                plan = torch.empty(size("etpgt_hub_plan_bytes", self.num_edges), dtype=torch.uint8, device=dev)
+                ws = workspace(size("etpgt_hub_plan_workspace_bytes", self.num_nodes), dev)
+                call("etpgt_hub_plan", ptr(self.rowptr), ptr(self.colptr), self.num_nodes, self.num_edges, ptr(plan),
+                     ptr(ws), ws.numel(), stream())
+                counts = plan[:16].view(torch.int32).tolist()
+                if counts[0] or counts[2]:
+                    self._hub = plan
+        return self._hub if self._hub is not False else None
 
 
 def _pad64(n: int) -> int:
@@ -400,6 +421,28 @@ class EmbedPE(torch.autograd.Function):
 # ------------------------------------------------------------------------------ TransformerConv
 
 
+def _tconv_fwd(qkvs, n, dim, heads, index: GraphIndex, w_beta, mask, out, agg, beta, m, inv_l) -> None:
+    """etpgt_tconv_fwd, with the hub-row kernels when the graph has rows of more than 256 edges."""
+    hub = index.hub_plan()
+    hub_ws = workspace(size("etpgt_tconv_hub_workspace_bytes", index.num_edges, dim), qkvs.device) if hub is not None else None
+    call("etpgt_tconv_fwd_hub", ptr(qkvs), n, dim, heads, ptr(index.rowptr), ptr(index.col), ptr(index.eperm),
+         index.num_edges, ptr(w_beta), ptr(mask), ptr(out), ptr(agg), ptr(beta), ptr(m), ptr(inv_l), ptr(hub),
+         ptr(hub_ws), hub_ws.numel() if hub_ws is not None else 0, stream())
+
+
+def _tconv_bwd(qkvs, d_out, n, dim, heads, index: GraphIndex, w_beta, mask, agg, beta, m, inv_l, d_qkvs, g_hi, g_lo,
+               d_bias, d_w_beta) -> None:
+    """etpgt_tconv_bwd_split (fp32 d_qkvs, or the bf16 hi / lo operand pair + bias column sums), hub rows included."""
+    dev = qkvs.device
+    ws = workspace(size("etpgt_tconv_bwd_workspace_bytes", n, index.num_edges, dim, heads), dev)
+    hub = index.hub_plan()
+    hub_ws = workspace(size("etpgt_tconv_hub_workspace_bytes", index.num_edges, dim), dev) if hub is not None else None
+    call("etpgt_tconv_bwd_split_hub", ptr(qkvs), ptr(d_out), n, dim, heads, ptr(index.rowptr), ptr(index.col),
+         ptr(index.eperm), ptr(index.colptr), ptr(index.row), ptr(index.cpos), index.num_edges, ptr(w_beta), ptr(mask),
+         ptr(agg), ptr(beta), ptr(m), ptr(inv_l), ptr(d_qkvs), ptr(g_hi), ptr(g_lo), ptr(d_bias), ptr(d_w_beta), ptr(ws),
+         ws.numel(), ptr(hub), ptr(hub_ws), hub_ws.numel() if hub_ws is not None else 0, stream())
+
+
 class TransformerConvFn(torch.autograd.Function):
     """Fused attention + aggregation + gate over the CSR (etpgt_tconv_fwd / _bwd)."""
 
@@ -417,8 +460,7 @@ class TransformerConvFn(torch.autograd.Function):
         beta = torch.empty(n, **f32)
         m = torch.empty(n, heads, **f32)
         inv_l = torch.empty(n, heads, **f32)
-        call("etpgt_tconv_fwd", ptr(qkvs), n, dim, heads, ptr(index.rowptr), ptr(index.col), ptr(index.eperm),
-             index.num_edges, ptr(w_beta_c), ptr(mask_c), ptr(out), ptr(agg), ptr(beta), ptr(m), ptr(inv_l), stream())
+        _tconv_fwd(qkvs, n, dim, heads, index, w_beta_c, mask_c, out, agg, beta, m, inv_l)
         ctx.save_for_backward(qkvs, w_beta_c, mask_c, agg, beta, m, inv_l)
         ctx.index, ctx.heads = index, heads
         ctx.w_beta_shape = None if w_beta is None else tuple(w_beta.shape)
@@ -433,11 +475,8 @@ class TransformerConvFn(torch.autograd.Function):
         dev = qkvs.device
         d_qkvs = torch.empty_like(qkvs)
         d_w_beta = torch.empty(3 * dim, dtype=torch.float32, device=dev) if w_beta is not None else None
-        ws = workspace(size("etpgt_tconv_bwd_workspace_bytes", n, index.num_edges, dim, heads), dev)
-        call("etpgt_tconv_bwd", ptr(qkvs), ptr(d_out), n, dim, heads, ptr(index.rowptr), ptr(index.col),
-             ptr(index.eperm), ptr(index.colptr), ptr(index.row), ptr(index.cpos), index.num_edges, ptr(w_beta),
-             ptr(mask), ptr(agg), ptr(beta), ptr(m), ptr(inv_l), ptr(d_qkvs), ptr(d_w_beta), ptr(ws), ws.numel(),
-             stream())
+        _tconv_bwd(qkvs, d_out, n, dim, heads, index, w_beta, mask, agg, beta, m, inv_l, d_qkvs, None, None, None,
+                   d_w_beta)
         if d_w_beta is not None:
             d_w_beta = d_w_beta.view(ctx.w_beta_shape)
         return d_qkvs, d_w_beta, None, None, None
@@ -537,8 +576,7 @@ class TransformerConvLayer(torch.autograd.Function):
         f32 = dict(dtype=torch.float32, device=dev)
         out, agg = torch.empty(n, dim, **f32), torch.empty(n, dim, **f32)
         beta, m, inv_l = torch.empty(n, **f32), torch.empty(n, heads, **f32), torch.empty(n, heads, **f32)
-        call("etpgt_tconv_fwd", ptr(qkvs), n, dim, heads, ptr(index.rowptr), ptr(index.col), ptr(index.eperm),
-             index.num_edges, ptr(w_beta_c), ptr(mask_c), ptr(out), ptr(agg), ptr(beta), ptr(m), ptr(inv_l), stream())
+        _tconv_fwd(qkvs, n, dim, heads, index, w_beta_c, mask_c, out, agg, beta, m, inv_l)
         ctx.save_for_backward(x_hi, x_lo, w_hi, w_lo, qkvs, w_beta_c, mask_c, agg, beta, m, inv_l)
         ctx.index, ctx.heads = index, heads
         ctx.w_beta_shape = None if w_beta is None else tuple(w_beta.shape)
@@ -557,11 +595,8 @@ class TransformerConvLayer(torch.autograd.Function):
         g_lo = torch.empty(n, width, dtype=torch.bfloat16, device=dev)
         d_bias = torch.empty(width, dtype=torch.float32, device=dev)
         d_w_beta = torch.empty(3 * dim, dtype=torch.float32, device=dev) if w_beta is not None else None
-        ws = workspace(size("etpgt_tconv_bwd_workspace_bytes", n, index.num_edges, dim, heads), dev)
-        call("etpgt_tconv_bwd_split", ptr(qkvs), ptr(d_out), n, dim, heads, ptr(index.rowptr), ptr(index.col),
-             ptr(index.eperm), ptr(index.colptr), ptr(index.row), ptr(index.cpos), index.num_edges, ptr(w_beta),
-             ptr(mask), ptr(agg), ptr(beta), ptr(m), ptr(inv_l), None, ptr(g_hi), ptr(g_lo), ptr(d_bias),
-             ptr(d_w_beta), ptr(ws), ws.numel(), stream())
+        _tconv_bwd(qkvs, d_out, n, dim, heads, index, w_beta, mask, agg, beta, m, inv_l, None, g_hi, g_lo, d_bias,
+                   d_w_beta)
         d_x = d_w = None
         if ctx.needs_input_grad[0]:
             d_x = _gemm_x3(g_hi, g_lo, w_hi, w_lo, n, k, width, width, k, None, b_mn=True)
@@ -605,9 +640,7 @@ class TransformerLayer(torch.autograd.Function):
         f32 = dict(dtype=torch.float32, device=dev)
         conv_out, agg = torch.empty(n, dim, **f32), torch.empty(n, dim, **f32)
         beta, m, inv_l = torch.empty(n, **f32), torch.empty(n, heads, **f32), torch.empty(n, heads, **f32)
-        call("etpgt_tconv_fwd", ptr(qkvs), n, dim, heads, ptr(index.rowptr), ptr(index.col), ptr(index.eperm),
-             index.num_edges, ptr(w_beta_c), ptr(mask_c), ptr(conv_out), ptr(agg), ptr(beta), ptr(m), ptr(inv_l),
-             stream())
+        _tconv_fwd(qkvs, n, dim, heads, index, w_beta_c, mask_c, conv_out, agg, beta, m, inv_l)
         gamma_c, bn_bias_c = _f32(gamma), _f32(bn_bias)
         mean, invstd = torch.empty(dim, **f32), torch.empty(dim, **f32)
         count = float(n)
@@ -677,11 +710,8 @@ class TransformerLayer(torch.autograd.Function):
         g_lo = torch.empty(n, width, dtype=torch.bfloat16, device=dev)
         d_bias = torch.empty(width, **f32)
         d_w_beta = torch.empty(3 * dim, **f32) if w_beta is not None else None
-        ws = workspace(size("etpgt_tconv_bwd_workspace_bytes", n, index.num_edges, dim, heads), dev)
-        call("etpgt_tconv_bwd_split", ptr(qkvs), ptr(d_conv), n, dim, heads, ptr(index.rowptr), ptr(index.col),
-             ptr(index.eperm), ptr(index.colptr), ptr(index.row), ptr(index.cpos), index.num_edges, ptr(w_beta),
-             ptr(mask), ptr(agg), ptr(beta), ptr(m), ptr(inv_l), None, ptr(g_hi), ptr(g_lo), ptr(d_bias),
-             ptr(d_w_beta), ptr(ws), ws.numel(), stream())
+        _tconv_bwd(qkvs, d_conv, n, dim, heads, index, w_beta, mask, agg, beta, m, inv_l, None, g_hi, g_lo, d_bias,
+                   d_w_beta)
         d_x = d_w = None
         if ctx.needs_input_grad[0]:   # residual branch + projection branch, summed by the GEMM epilogue
             d_x = _gemm_x3(g_hi, g_lo, w_hi, w_lo, n, k, width, width, k, None, b_mn=True, accumulate_into=d_res)

@@ -156,3 +156,28 @@ def generate_scaled(num_sessions: int = 8_000_000, num_items: int = 1_000_000, s
     return generate(num_sessions=num_sessions, graph_sessions=None, num_items=num_items, clusters=12_500, p_local=0.9,
                     a_local=0.7, a_global=0.8, a_cluster=0.6, revisit=0.25, seed=seed, length_law="yoochoose",
                     build_graph=build_graph)
+
+
+def zipf_graph(num_nodes: int = 82_174, num_edges: int = 737_716, a: float = 1.5, seed: int = 44,
+               max_share: float = 0.02):
+    """An undirected graph whose endpoints follow the popularity law of the reference's own generator
+    (`np.random.zipf(1.5, num_items)` weights, scripts/data/00_generate_synthetic_data.py:53): `num_edges` distinct
+    pairs (item_i <= item_j, self pairs kept), a handful of nodes holding a large share of them — the hub-row case
+    of the edge kernels.  One endpoint of every pair is drawn from the zipf weights (a node's
+    share capped at `max_share`, else the heaviest draw would own almost every edge and there would not be enough
+    DISTINCT pairs), the other uniformly — popular items co-occur with everything.  Returns (item_i, item_j) int64."""
+    rng = np.random.default_rng(seed)
+    w = rng.zipf(a, size=num_nodes - 1).astype(np.float64)
+    for _ in range(8):                      # cap, renormalise, repeat: the cap holds after renormalisation
+        w = np.minimum(w, w.sum() * max_share)
+    p = w / w.sum()
+    keys = np.zeros(0, dtype=np.int64)
+    for _ in range(20):
+        if len(keys) >= num_edges:
+            break
+        need = int((num_edges - len(keys)) * 1.25) + 1024
+        x = 1 + rng.choice(num_nodes - 1, size=need, p=p)
+        y = 1 + rng.integers(0, num_nodes - 1, size=need)
+        keys = np.unique(np.concatenate([keys, np.minimum(x, y) * num_nodes + np.maximum(x, y)]))
+    keys = rng.permutation(keys)[:num_edges]
+    return keys // num_nodes, keys % num_nodes

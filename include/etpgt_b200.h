@@ -139,6 +139,31 @@ int etpgt_tconv_fwd(const float* qkvs, int64_t num_nodes, int dim, int heads,
 /* Backward, no atomics: a destination pass (d_query, d_skip, per-edge coefficients) then a
  * source pass over the CSC (d_key, d_value).  d_qkvs [N,4*dim] is overwritten; d_w_beta [3*dim]
  * overwritten (NULL when w_beta == NULL). */
+/* Hub rows.  A destination (forward, backward destination pass) or source (backward source pass) with more than
+ * 256 edges is cut into chunks of 256 edges; one CTA per chunk stages the row's query (and d_agg) in shared memory,
+ * its lane groups each walk a slice, and the (m, l, acc) / gradient partials are combined in a fixed order inside
+ * the CTA and then over the chunks of the row — no atomics, bit-reproducible (north_star (2): "shared-memory staging
+ * of hub-node rows"; the reference's generator is zipf(1.5), scripts/data/00_generate_synthetic_data.py:53).
+ * etpgt_hub_plan builds the row / chunk lists for the CSR (rowptr) and CSC (colptr) sides once per graph index,
+ * deterministically (prefix sums); plan[0..3] (int32, device) = #hub destinations, #their chunks, #hub sources,
+ * #their chunks.  The *_hub entry points take the plan (NULL = the plain row kernels) and a workspace for the
+ * per-chunk partials; rows at or below the threshold run in the row kernels as before. */
+size_t etpgt_hub_plan_bytes(int64_t num_edges);
+size_t etpgt_hub_plan_workspace_bytes(int64_t num_nodes);
+int etpgt_hub_plan(const int32_t* rowptr, const int32_t* colptr, int64_t num_nodes, int64_t num_edges, void* plan,
+                   void* ws, size_t ws_bytes, etpgt_stream_t stream);
+size_t etpgt_tconv_hub_workspace_bytes(int64_t num_edges, int dim);
+int etpgt_tconv_fwd_hub(const float* qkvs, int64_t num_nodes, int dim, int heads, const int32_t* rowptr,
+                        const int32_t* col, const int32_t* eperm, int64_t num_edges, const float* w_beta,
+                        const float* alpha_mask, float* out, float* agg, float* beta, float* m, float* inv_l,
+                        const void* hub_plan, void* hub_ws, size_t hub_ws_bytes, etpgt_stream_t stream);
+int etpgt_tconv_bwd_split_hub(const float* qkvs, const float* d_out, int64_t num_nodes, int dim, int heads,
+                              const int32_t* rowptr, const int32_t* col, const int32_t* eperm,
+                              const int32_t* colptr, const int32_t* row, const int32_t* cpos, int64_t num_edges,
+                              const float* w_beta, const float* alpha_mask, const float* agg, const float* beta,
+                              const float* m, const float* inv_l, float* d_qkvs, void* d_hi, void* d_lo,
+                              float* d_colsum, float* d_w_beta, void* ws, size_t ws_bytes, const void* hub_plan,
+                              void* hub_ws, size_t hub_ws_bytes, etpgt_stream_t stream);
 size_t etpgt_tconv_bwd_workspace_bytes(int64_t num_nodes, int64_t num_edges, int dim, int heads);
 int etpgt_tconv_bwd(const float* qkvs, const float* d_out, int64_t num_nodes, int dim, int heads,
                     const int32_t* rowptr, const int32_t* col, const int32_t* eperm,
