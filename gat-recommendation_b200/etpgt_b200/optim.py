@@ -148,20 +148,30 @@ class _DeviceAdam(torch.optim.Optimizer):
                 loss = closure()
         for group in self.param_groups:
             todo: dict[int, list] = {}
+            bumped: dict[int, int] = {}       # id(step tensor) -> its new value: one increment per distinct tensor
             for p in group["params"]:
                 if p.grad is None:
                     continue
-                if not p.is_cuda:
-                    raise RuntimeError("etpgt_b200 optimizers run on CUDA parameters only (no CPU fallback)")
-                if p.grad.is_sparse or p.dtype != torch.float32:
-                    raise RuntimeError("etpgt_b200 optimizers need dense fp32 parameters and gradients")
                 state = self.state[p]
                 if len(state) == 0:
-                    state["step"] = torch.tensor(0.0)
+                    if not p.is_cuda:
+                        raise RuntimeError("etpgt_b200 optimizers run on CUDA parameters only (no CPU fallback)")
+                    if p.grad.is_sparse or p.dtype != torch.float32:
+                        raise RuntimeError("etpgt_b200 optimizers need dense fp32 parameters and gradients")
+                    # the parameters of a group step together: they share ONE step counter tensor (a host scalar,
+                    # as in torch), so a step costs one host increment instead of one per parameter
+                    shared = group.get("_shared_step")
+                    state["step"] = shared if shared is not None else torch.tensor(0.0)
+                    if shared is None and not bumped:
+                        group["_shared_step"] = state["step"]
                     state["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     state["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                state["step"] += 1
-                todo.setdefault(int(state["step"].item()), []).append(p)
+                counter = state["step"]
+                step_no = bumped.get(id(counter))
+                if step_no is None:
+                    counter += 1
+                    step_no = bumped[id(counter)] = int(counter.item())
+                todo.setdefault(step_no, []).append(p)
             for step_no, plist in todo.items():
                 self._launch(group, step_no, plist)
         self._dirty = False
@@ -170,6 +180,24 @@ class _DeviceAdam(torch.optim.Optimizer):
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)
         self._plan_key = None      # the moment tensors were replaced: the cached launch plan holds freed pointers
+        for group in self.param_groups:     # loaded counters are per parameter again: share equal ones
+            group.pop("_shared_step", None)
+            by_value: dict[float, torch.Tensor] = {}
+            for p in group["params"]:
+                state = self.state.get(p)
+                if state and "step" in state:
+                    value = float(state["step"])
+                    state["step"] = by_value.setdefault(value, torch.as_tensor(state["step"], dtype=torch.float32).cpu())
+
+    def state_dict(self):
+        """torch's format; every parameter gets its own copy of the (shared) step counter."""
+        out = super().state_dict()
+        # (the packed per-parameter dicts are the live ones: copy before un-sharing the counter)
+        out["state"] = {k: ({**st, "step": st["step"].clone()} if "step" in st else dict(st))
+                        for k, st in out["state"].items()}
+        for group in out["param_groups"]:
+            group.pop("_shared_step", None)
+        return out
 
     def add_param_group(self, param_group):
         super().add_param_group(param_group)

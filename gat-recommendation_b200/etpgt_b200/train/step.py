@@ -103,6 +103,7 @@ class FusedTrainStep:
         self._desc.struct_bytes = ctypes.sizeof(_GtStep)
         self.graph = graph
         self._graph_cache, self._graph_stream = None, None
+        self._tracked, self._bound_key, self._pe = None, None, None
 
     # ------------------------------------------------------------------ what the driver covers
     @staticmethod
@@ -174,6 +175,76 @@ class FusedTrainStep:
             self._flat_key = key
         return self._block_ptr
 
+    def _tracked_tensors(self):
+        """Every tensor whose address the descriptor holds (parameters, BatchNorm buffers, the cached PE)."""
+        model = self.model
+        if self._tracked is None:
+            tensors = [model.item_embedding.weight]
+            for conv, bn in zip(model.convs, model.batch_norms):
+                tensors += [conv.lin_query.weight, conv.lin_key.weight, conv.lin_value.weight, conv.lin_skip.weight,
+                            conv.lin_query.bias, conv.lin_key.bias, conv.lin_value.bias, conv.lin_skip.bias]
+                if conv.lin_beta is not None:
+                    tensors.append(conv.lin_beta.weight)
+                tensors += [bn.weight, bn.bias, bn.running_mean, bn.running_var]
+                if bn.num_batches_tracked is not None:
+                    tensors.append(bn.num_batches_tracked)
+            if model.use_laplacian_pe:
+                tensors += [model.laplacian_pe.projection.weight, model.laplacian_pe.projection.bias]
+            self._tracked = tensors
+        return self._tracked
+
+    def _bind_model(self, backward: bool, peer) -> None:
+        model, d = self.model, self._desc
+        pe = model.laplacian_pe._cached_pe if model.use_laplacian_pe else None
+        if model.use_laplacian_pe and pe is None:
+            pe = model.laplacian_pe.cached()        # raises the reference's "not precomputed" error
+        key = (tuple(t.data_ptr() for t in self._tracked_tensors()), None if pe is None else (pe.data_ptr(), pe.dtype),
+               backward, id(peer), model.readout_type, self.loss, model.dropout_layer.p)
+        if key == self._bound_key:
+            return
+        layers = len(model.convs)
+        table = model.item_embedding.weight
+        d.num_items = table.size(0)
+        pad = model.item_embedding.padding_idx
+        d.padding_idx = -1 if pad is None else int(pad)
+        d.dim, d.heads, d.num_layers = model.hidden_dim, model.convs[0].heads, layers
+        d.readout_mode, d.loss_mode = ops.READOUT_MODES[model.readout_type], ops.LOSS_MODES[self.loss]
+        d.alpha, d.temperature = self.alpha, self.temperature
+        d.table = table.data_ptr()
+        w_pe = b_pe = None
+        self._pe = None
+        if model.use_laplacian_pe:
+            self._pe = pe = ops._f32(pe)            # kept alive: a converted copy would otherwise be freed
+            w_pe, b_pe = model.laplacian_pe.projection.weight, model.laplacian_pe.projection.bias
+            d.k_pe = pe.size(1)
+        else:
+            d.k_pe = 0
+        d.pe, d.w_pe, d.b_pe = _addr(pe), _addr(w_pe), _addr(b_pe)
+        block_ptr = iter(self._gradient_views()) if backward else None
+        for l, (conv, bn) in enumerate(zip(model.convs, model.batch_norms)):
+            if conv.dropout != model.convs[0].dropout or conv.heads != model.convs[0].heads:
+                raise NotImplementedError("FusedTrainStep: layers must share heads and attention dropout")
+            layer = d.layer[l]
+            layer.weight = conv.fused_store("weight")[0].data_ptr()
+            layer.bias = conv.fused_store("bias")[0].data_ptr()
+            layer.w_beta = _addr(conv.lin_beta.weight) if conv.lin_beta is not None else None
+            layer.bn_weight, layer.bn_bias = bn.weight.data_ptr(), bn.bias.data_ptr()
+            layer.running_mean, layer.running_var = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
+            layer.num_batches_tracked = _addr(bn.num_batches_tracked)
+            if backward:
+                layer.d_weight, layer.d_bias = next(block_ptr), next(block_ptr)
+                layer.d_w_beta = next(block_ptr) if conv.lin_beta is not None else None
+                layer.d_bn_weight, layer.d_bn_bias = next(block_ptr), next(block_ptr)
+            layer.momentum = 0.1 if bn.momentum is None else float(bn.momentum)
+            layer.eps = float(bn.eps)
+            layer.alpha_seed = layer.drop_seed = 0
+        if backward and model.use_laplacian_pe:
+            d.d_w_pe, d.d_b_pe = next(block_ptr), next(block_ptr)
+        else:
+            d.d_w_pe = d.d_b_pe = None
+        # fused_store() may have re-homed the four projection parameters of a layer: take the key again
+        self._bound_key = (tuple(t.data_ptr() for t in self._tracked_tensors()),) + key[1:]
+
     def _peer(self):
         """The PeerDataParallel of the model when its exchanges run over peer memory (world > 1), else None."""
         peer = getattr(self.model, "_etpgt_peer", None)
@@ -219,30 +290,17 @@ class FusedTrainStep:
         d.plan_nodes_perm = _addr(plan_nodes.perm) if plan_nodes else None
         d.plan_loss_key = _addr(plan_loss.sorted_key) if plan_loss else None
         d.plan_loss_perm = _addr(plan_loss.perm) if plan_loss else None
-        d.num_items = table.size(0)
-        pad = model.item_embedding.padding_idx
-        d.padding_idx = -1 if pad is None else int(pad)
-        d.dim, d.heads, d.num_layers = dim, model.convs[0].heads, layers
         d.num_neg = negatives.size(1)
-        d.readout_mode, d.loss_mode = ops.READOUT_MODES[model.readout_type], ops.LOSS_MODES[self.loss]
         d.training, d.backward, d.distributed = int(training), int(backward), int(distributed)
-        d.alpha, d.temperature = self.alpha, self.temperature
         d.total_sessions = float(total_sessions if total_sessions else b)
         alpha_p = float(model.convs[0].dropout) if training else 0.0
         drop_p = float(model.dropout_layer.p) if training else 0.0
         d.alpha_p, d.drop_p = alpha_p, drop_p
-        d.table = table.data_ptr()
-        pe = w_pe = b_pe = None
-        if model.use_laplacian_pe:
-            pe = ops._f32(model.laplacian_pe.cached())
-            w_pe, b_pe = model.laplacian_pe.projection.weight, model.laplacian_pe.projection.bias
-            d.k_pe = pe.size(1)
-        else:
-            d.k_pe = 0
-        d.pe, d.w_pe, d.b_pe = _addr(pe), _addr(w_pe), _addr(b_pe)
+        # everything of the descriptor that depends on the model only (parameter / buffer / gradient addresses,
+        # hyper-parameters) is bound once and re-bound when an address changes (model.to(), a re-homed table, ...)
+        self._bind_model(backward, peer)
 
         # gradients: dense ones into the flat buffer; the table's rows into the optimizer's sink or a dense .grad
-        block_ptr = iter(self._gradient_views()) if backward else None
         carried = []
         if backward:
             # gradients that were not cleared since the last backward: torch accumulates into them
@@ -261,29 +319,12 @@ class FusedTrainStep:
             d.d_table = None
         # the same draws, in the same order, as the per-operator path (nn.transformer_layer)
         per_layer = int(alpha_p > 0.0) + int(drop_p > 0.0)
-        seeds = iter(torch.randint(0, 2 ** 62, (per_layer * layers,)).tolist()) if per_layer else None
-        for l, (conv, bn) in enumerate(zip(model.convs, model.batch_norms)):
-            if conv.dropout != model.convs[0].dropout or conv.heads != model.convs[0].heads:
-                raise NotImplementedError("FusedTrainStep: layers must share heads and attention dropout")
-            layer = d.layer[l]
-            layer.weight = conv.fused_store("weight")[0].data_ptr()
-            layer.bias = conv.fused_store("bias")[0].data_ptr()
-            layer.w_beta = _addr(conv.lin_beta.weight) if conv.lin_beta is not None else None
-            layer.bn_weight, layer.bn_bias = bn.weight.data_ptr(), bn.bias.data_ptr()
-            layer.running_mean, layer.running_var = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
-            layer.num_batches_tracked = _addr(bn.num_batches_tracked)
-            if backward:
-                layer.d_weight, layer.d_bias = next(block_ptr), next(block_ptr)
-                layer.d_w_beta = next(block_ptr) if conv.lin_beta is not None else None
-                layer.d_bn_weight, layer.d_bn_bias = next(block_ptr), next(block_ptr)
-            layer.momentum = 0.1 if bn.momentum is None else float(bn.momentum)
-            layer.eps = float(bn.eps)
-            layer.alpha_seed = next(seeds) if alpha_p > 0.0 else 0
-            layer.drop_seed = next(seeds) if drop_p > 0.0 else 0
-        if backward and model.use_laplacian_pe:
-            d.d_w_pe, d.d_b_pe = next(block_ptr), next(block_ptr)
-        else:
-            d.d_w_pe = d.d_b_pe = None
+        if per_layer:
+            seeds = iter(torch.randint(0, 2 ** 62, (per_layer * layers,)).tolist())
+            for l in range(layers):
+                layer = d.layer[l]
+                layer.alpha_seed = next(seeds) if alpha_p > 0.0 else 0
+                layer.drop_seed = next(seeds) if drop_p > 0.0 else 0
 
         sess = torch.empty(b, dim, dtype=torch.float32, device=dev)
         losses = torch.empty(3, dtype=torch.float32, device=dev)

@@ -115,34 +115,43 @@ def test_zipf_graph_matches_oracle_and_the_row_kernels(ops):
         hi = torch.empty(n, 4 * dim, dtype=torch.bfloat16, device="cuda")
         lo = torch.empty_like(hi)
         d_qkvs, colsum, d_wb = torch.empty(n, 4 * dim, **f32), torch.empty(4 * dim, **f32), torch.empty(3 * dim, **f32)
-        call("etpgt_tconv_bwd_split_hub", ptr(qkvs), ptr(d_out), n, dim, heads, ptr(index.rowptr), ptr(index.col),
-             ptr(index.eperm), ptr(index.colptr), ptr(index.row), ptr(index.cpos), e, ptr(w_beta), None, ptr(agg),
-             ptr(bt), ptr(m), ptr(inv_l), ptr(d_qkvs), ptr(hi), ptr(lo), ptr(colsum), ptr(d_wb), ptr(ws), ws.numel(),
-             ptr(plan) if use_hubs else None, ptr(hub_ws) if use_hubs else None, hub_ws.numel() if use_hubs else 0,
-             stream())
+        # gradient rows come out either as fp32 or as the bf16 hi / lo pair: one call each
+        for fp32_rows in (True, False):
+            call("etpgt_tconv_bwd_split_hub", ptr(qkvs), ptr(d_out), n, dim, heads, ptr(index.rowptr), ptr(index.col),
+                 ptr(index.eperm), ptr(index.colptr), ptr(index.row), ptr(index.cpos), e, ptr(w_beta), None, ptr(agg),
+                 ptr(bt), ptr(m), ptr(inv_l), ptr(d_qkvs) if fp32_rows else None, None if fp32_rows else ptr(hi),
+                 None if fp32_rows else ptr(lo), ptr(colsum), ptr(d_wb), ptr(ws), ws.numel(),
+                 ptr(plan) if use_hubs else None, ptr(hub_ws) if use_hubs else None,
+                 hub_ws.numel() if use_hubs else 0, stream())
         return dict(out=out, agg=agg, beta=bt, m=m, inv_l=inv_l, d_qkvs=d_qkvs, hi=hi, lo=lo, colsum=colsum, d_wb=d_wb)
 
     a, b, again = run(True), run(False), run(True)
     for k in a:
         assert torch.equal(a[k], again[k]), f"{k}: two hub runs differ"         # bit-reproducible
-    for k in ("out", "agg", "beta", "inv_l", "d_qkvs", "colsum", "d_wb"):
-        assert rel_err(a[k], b[k]) < 2e-5, k                                     # summation order only
     assert torch.equal(a["m"], b["m"])                                           # the row maximum is exact
     # the split outputs are the split of the hub path's own fp32 gradient, the column sums its bias gradient
     want_hi = a["d_qkvs"].to(torch.bfloat16)
     assert torch.equal(a["hi"], want_hi) and torch.equal(a["lo"], (a["d_qkvs"] - want_hi.float()).to(torch.bfloat16))
     assert rel_err(a["colsum"], a["d_qkvs"].double().sum(0)) < 1e-5
-    # fp64 oracle of the forward on the same projected features
+    # fp64 oracle (forward and, through autograd, every gradient) on the same projected features
     import math
 
     from oracle.conv_ref import _scatter_rows, segment_softmax
 
-    q64 = qkvs.double().cpu()
+    q64 = qkvs.double().cpu().requires_grad_(True)
+    wb64 = w_beta.double().cpu().view(1, -1).requires_grad_(True)
     q, k, v, s = q64.split(dim, dim=1)
     c = dim // heads
     src, dst = torch.from_numpy(ei[0]), torch.from_numpy(ei[1])
     logits = (q.view(n, heads, c)[dst] * k.view(n, heads, c)[src]).sum(-1) / math.sqrt(c)
     alpha = segment_softmax(logits, dst, n)
     agg = _scatter_rows(v.view(n, heads, c)[src] * alpha.unsqueeze(-1), dst, n).reshape(n, dim)
-    bta = torch.sigmoid(torch.cat([agg, s, agg - s], dim=-1) @ w_beta.double().cpu().view(1, -1).t())
-    assert rel_err(a["out"], bta * s + (1 - bta) * agg) < TOL
+    bta = torch.sigmoid(torch.cat([agg, s, agg - s], dim=-1) @ wb64.t())
+    ref = bta * s + (1 - bta) * agg
+    ref.backward(d_out.double().cpu())
+    want = {"out": ref.detach(), "agg": agg.detach(), "d_qkvs": q64.grad, "d_wb": wb64.grad.view(-1)}
+    for name, w in want.items():
+        assert rel_err(a[name], w) < TOL, f"hub kernels, {name}"
+        # rows of > 10,000 edges through ONE lane group's serial fp32 walk (the plain row kernels): the same
+        # quantities, one order of magnitude looser — the chunked hub path is also the more accurate one
+        assert rel_err(b[name], w) < 10 * TOL, f"row kernels, {name}"

@@ -69,7 +69,9 @@ def _driver_step(model, batch, loss_kind, seed, phase_by_phase=False):
 
     _reset(model)
     torch.manual_seed(seed)
-    step = FusedTrainStep(model, loss_kind)
+    # phase by phase: the plain driver (the data-parallel control flow of the NCCL exchange); otherwise the default,
+    # which runs batches of this size as ONE CUDA graph launch
+    step = FusedTrainStep(model, loss_kind, graph=False if phase_by_phase else "auto")
     if phase_by_phase:
         # single-GPU run of the data-parallel control flow: one call per phase, no exchange in between
         calls = []

@@ -1,5 +1,3 @@
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 > gpurun_out/r02f_gpu_tests.txt
-timeout 900 python bench.py > gpurun_out/r02f_bench.json 2> gpurun_out/r02f_bench.err
-timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r02f_bench_ref.json 2> gpurun_out/r02f_bench_ref.err
-timeout 600 bash tools/prof_tconv.sh r02f > gpurun_out/r02f_prof.log 2>&1
-tail -5 gpurun_out/r02f_gpu_tests.txt; tail -3 gpurun_out/r02f_bench.err; tail -2 gpurun_out/r02f_prof.log
+timeout 600 python -m pytest tests/test_gpu_hub.py tests/test_gpu_optim.py tests/test_gpu_step.py -q 2>&1 | tail -5 > gpurun_out/r02i_gpu_tests.txt
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02i_small_launches.csv python tools/prof_small.py 1024 --ncu > gpurun_out/r02i_ncu.log 2>&1
+tail -3 gpurun_out/r02i_gpu_tests.txt
