@@ -395,6 +395,8 @@ def _two_gpu_worker(rank, world, port, out):
         def run_trainer(dp):
             m = make()
             m.dropout_layer.p = 0.0
+            if not dp:
+                m.bn_process_group = False     # a single-process replica inside an initialised process group
             o = optim.AdamW(m.parameters(), lr=1e-3, weight_decay=1e-5)      # created BEFORE the trainer re-homes the table
             train_l, val_l = loaders(dp)
             with tempfile.TemporaryDirectory() as tmp:

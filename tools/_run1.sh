@@ -1,3 +1,4 @@
-timeout 600 python -m pytest tests/test_gpu_hub.py tests/test_gpu_optim.py tests/test_gpu_step.py -q 2>&1 | tail -5 > gpurun_out/r02i_gpu_tests.txt
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02i_small_launches.csv python tools/prof_small.py 1024 --ncu > gpurun_out/r02i_ncu.log 2>&1
-tail -3 gpurun_out/r02i_gpu_tests.txt
+timeout 600 python -m pytest tests/test_gpu_hub.py -q 2>&1 | tail -15 > gpurun_out/r02j_gpu_tests.txt
+( time timeout 900 python bench.py > gpurun_out/r02j_bench.json 2> gpurun_out/r02j_bench.err ) 2> gpurun_out/r02j_bench.time
+( time timeout 600 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/r02j_bench_ref.json 2> gpurun_out/r02j_bench_ref.err ) 2> gpurun_out/r02j_bench_ref.time
+tail -3 gpurun_out/r02j_gpu_tests.txt; cat gpurun_out/r02j_bench.time gpurun_out/r02j_bench_ref.time; tail -3 gpurun_out/r02j_bench.err
