@@ -111,31 +111,47 @@ struct DpTableArgs {
   int64_t begin4, end4;
 };
 
+// UN elements per thread, ranks r < WMAX = 16 / UN: all UN * world gradient loads of a thread (up to 16 x 16 B,
+// most of them over NVLink, ~2 us away) are in flight before the first one is used, so ONE CTA per SM (a quarter of
+// its registers, no shared memory) keeps the links busy and leaves the SM to the kernels of the other stream (the
+// exchange runs underneath the last phase of the backward pass).
+template <int UN, int WMAX>
 __global__ void __launch_bounds__(kThreads)
 dp_adam_table_kernel(const __grid_constant__ CommView c, const DpTableArgs a, const AdamScalars s) {
-  const int64_t stride = (int64_t)gridDim.x * kThreads;
   float4* __restrict__ m4 = reinterpret_cast<float4*>(a.exp_avg);
   float4* __restrict__ v4 = reinterpret_cast<float4*>(a.exp_avg_sq);
   const float4* p_own = reinterpret_cast<const float4*>(c.base[c.rank] + a.param_offset);
-  for (int64_t i = a.begin4 + blockIdx.x * (int64_t)kThreads + threadIdx.x; i < a.end4; i += stride) {
-    float4 g[kMaxRanks];
+  const int64_t tile_elems = (int64_t)kThreads * UN;
+  const int64_t tiles = (a.end4 - a.begin4 + tile_elems - 1) / tile_elems;
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int64_t first = a.begin4 + tile * tile_elems + threadIdx.x;
+    float4 g[UN][WMAX];
 #pragma unroll
-    for (int r = 0; r < kMaxRanks; ++r)
-      if (r < c.world) g[r] = __ldcg(reinterpret_cast<const float4*>(c.base[r] + a.grad_offset) + i);
-    float4 P = p_own[i], M = m4[i], V = v4[i];
-    float4 G = g[0];
+    for (int u = 0; u < UN; ++u) {
+      const int64_t i = first + (int64_t)u * kThreads;
 #pragma unroll
-    for (int r = 1; r < kMaxRanks; ++r)
-      if (r < c.world) G = add4(G, g[r]);
-    adam_one(P.x, G.x, M.x, V.x, s);
-    adam_one(P.y, G.y, M.y, V.y, s);
-    adam_one(P.z, G.z, M.z, V.z, s);
-    adam_one(P.w, G.w, M.w, V.w, s);
+      for (int r = 0; r < WMAX; ++r)
+        if (r < c.world && i < a.end4) g[u][r] = __ldcg(reinterpret_cast<const float4*>(c.base[r] + a.grad_offset) + i);
+    }
 #pragma unroll
-    for (int r = 0; r < kMaxRanks; ++r)
-      if (r < c.world) reinterpret_cast<float4*>(c.base[r] + a.param_offset)[i] = P;
-    m4[i] = M;
-    v4[i] = V;
+    for (int u = 0; u < UN; ++u) {
+      const int64_t i = first + (int64_t)u * kThreads;
+      if (i >= a.end4) break;
+      float4 P = p_own[i], M = m4[i], V = v4[i];
+      float4 G = g[u][0];
+#pragma unroll
+      for (int r = 1; r < WMAX; ++r)
+        if (r < c.world) G = add4(G, g[u][r]);      // rank order: every owner would form the same sum
+      adam_one(P.x, G.x, M.x, V.x, s);
+      adam_one(P.y, G.y, M.y, V.y, s);
+      adam_one(P.z, G.z, M.z, V.z, s);
+      adam_one(P.w, G.w, M.w, V.w, s);
+#pragma unroll
+      for (int r = 0; r < WMAX; ++r)
+        if (r < c.world) reinterpret_cast<float4*>(c.base[r] + a.param_offset)[i] = P;
+      m4[i] = M;
+      v4[i] = V;
+    }
   }
   __threadfence_system();   // the pushed rows are visible to the peers before this rank enters the barrier
 }
@@ -236,7 +252,14 @@ extern "C" int etpgt_dp_adam_table(const etpgt_comm_t* comm, size_t param_offset
   a.exp_avg_sq = exp_avg_sq;
   a.begin4 = row_begin * (dim / 4);
   a.end4 = row_end * (dim / 4);
-  dp_adam_table_kernel<<<grid_for(a.end4 - a.begin4, kThreads * 2, 8), kThreads, 0, stream>>>(c, a, s);
+  // one CTA per SM: see the kernel's comment
+  if (c.world <= 2) {
+    dp_adam_table_kernel<8, 2><<<grid_for(a.end4 - a.begin4, kThreads * 8, 1), kThreads, 0, stream>>>(c, a, s);
+  } else if (c.world <= 4) {
+    dp_adam_table_kernel<4, 4><<<grid_for(a.end4 - a.begin4, kThreads * 4, 1), kThreads, 0, stream>>>(c, a, s);
+  } else {
+    dp_adam_table_kernel<2, 8><<<grid_for(a.end4 - a.begin4, kThreads * 2, 1), kThreads, 0, stream>>>(c, a, s);
+  }
   ETPGT_CHECK_LAUNCH("dp_adam_table");
   return ETPGT_OK;
 }

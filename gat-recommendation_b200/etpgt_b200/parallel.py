@@ -349,17 +349,45 @@ class PeerDataParallel:
         self._entered = True
         return self._reduced
 
+    def mark_table_ready(self) -> None:
+        """Called by the step driver where this rank's table gradient is complete (one phase before the end of the
+        backward pass): `update_table` then runs on the exchange stream from that point on."""
+        self.table_ready = torch.cuda.Event()
+        self.table_ready.record()
+
     def update_table(self, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, decoupled, step) -> None:
         """Reduce-scatter + AdamW + all-gather of the table (etpgt_dp_adam_table) between two barriers, then the
-        local gradient buffer is cleared (every peer has read its rows by then)."""
-        if not getattr(self, "_entered", False):
-            self.comm.barrier()
+        local gradient buffer is cleared (every peer has read its rows by then).
+
+        When the step driver marked the point where the table gradient was complete, all of this runs on the
+        exchange stream from that point — underneath the driver's last phase and the dense-parameter exchange —
+        with its own barrier channel; the caller's stream joins it at the end (the next step reads the table).
+        What keeps a peer from overwriting the flat dense-gradient buffer while this rank still sums it is the
+        next step's first in-kernel BatchNorm all-reduce, which every rank enters after its dense sum."""
         lo, hi = self.rows
-        _lib.call("etpgt_dp_adam_table", self.comm.handle, self.param_offset, self.grad_offset, _lib.ptr(exp_avg),
-                  _lib.ptr(exp_avg_sq), self.num_items, self.dim, lo, hi, float(lr), float(beta1), float(beta2),
-                  float(eps), float(weight_decay), int(decoupled), int(step), stream())
-        self.comm.barrier()
-        self.table_grad.zero_()
+        args = (self.comm.handle, self.param_offset, self.grad_offset, _lib.ptr(exp_avg), _lib.ptr(exp_avg_sq),
+                self.num_items, self.dim, lo, hi, float(lr), float(beta1), float(beta2), float(eps), float(weight_decay),
+                int(decoupled), int(step))
+        ready = getattr(self, "table_ready", None)
+        self.table_ready = None
+        if ready is None:
+            if not getattr(self, "_entered", False):
+                self.comm.barrier()
+            _lib.call("etpgt_dp_adam_table", *args, stream())
+            self.comm.barrier()
+            self.table_grad.zero_()
+            return
+        main = torch.cuda.current_stream()
+        if getattr(self, "_exchange_stream", None) is None:
+            self._exchange_stream = torch.cuda.Stream(device=self.table.device)
+        side = self._exchange_stream
+        side.wait_event(ready)
+        with torch.cuda.stream(side):
+            self.comm.barrier(1)
+            _lib.call("etpgt_dp_adam_table", *args, stream())
+            self.comm.barrier(1)
+            self.table_grad.zero_()
+        main.wait_stream(side)
 
     def end_exchange(self) -> None:
         """The optimizer step that consumed this exchange is queued: the next exchange_dense() starts a new one."""

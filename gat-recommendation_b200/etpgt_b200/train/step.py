@@ -356,6 +356,13 @@ class FusedTrainStep:
             # one host call; under peer-memory data parallelism the driver exchanges the BatchNorm sums itself
             if self.graph is True or (self.graph == "auto" and n <= self.GRAPH_MAX_NODES):
                 self._run_graph(phases)
+            elif peer is not None and backward:
+                # the table gradient is complete one phase before the end (the driver orders the backward tail that
+                # way): mark that point, so that the optimizer can run the table's reduce-scatter + AdamW + all-gather
+                # on its exchange stream UNDERNEATH the last phase (weight gradient of layer 0, PE projection gradient)
+                _lib.call("etpgt_gt_step_run", ctypes.byref(d), 0, phases - 1, stream())
+                peer.mark_table_ready()
+                _lib.call("etpgt_gt_step_run", ctypes.byref(d), phases - 1, phases, stream())
             else:
                 _lib.call("etpgt_gt_step_run", ctypes.byref(d), 0, phases, stream())
             if peer is not None and backward:

@@ -367,8 +367,12 @@ def _two_gpu_worker(rank, world, port, out):
         model.eval()
         with torch.no_grad():
             sess = model(batch_of(np.arange(600 + 50 * rank, 650 + 50 * rank), 9))
-            top = parallel.sharded_predict(model, sess, k=20)
-            single_top = ops.score_topk(sess, model.get_item_embeddings(), 20)[1]
+            # exact for either scorer: the fp32 CUDA-core one and the tcgen05 bf16 one
+            top_equal = True
+            for precision in ("fp32", "bf16"):
+                top = parallel.sharded_predict(model, sess, k=20, precision=precision)
+                single_top = ops.score_topk(sess, model.get_item_embeddings(), 20, precision=precision)[1]
+                top_equal = top_equal and bool(torch.equal(top, single_top))
         # the Trainer as one rank of a data-parallel job (process_group=True) vs. a single-process Trainer on the whole
         # batches: same epoch loss (global-batch mean), same Recall / NDCG (item-sharded scoring, counters summed)
         import tempfile
@@ -416,7 +420,7 @@ def _two_gpu_worker(rank, world, port, out):
                 for key in mb:
                     trainer_ok = trainer_ok and abs(ma[key] - mb[key]) <= 0.02
             notes.append(f"trainer dp {hist_dp} single {hist_single}")
-        out[rank] = (ok and trainer_ok, same, bool(torch.equal(top, single_top)), notes)
+        out[rank] = (ok and trainer_ok, same, top_equal, notes)
     finally:
         dist.destroy_process_group()
 

@@ -129,9 +129,11 @@ def main():
     with torch.no_grad():
         mine = data.build_batch(graph, store, ids[cuts[rank]:cuts[rank + 1]], 50, False, False)
         sess = dp_model(mine)
-        top = parallel.sharded_predict(dp_model, sess, k=20)
-        single = ops.score_topk(sess, dp_model.get_item_embeddings(), 20)[1]
-    same = bool(torch.equal(top, single))
+        same = True
+        for precision in ("fp32", "bf16"):     # exact for either scorer
+            top = parallel.sharded_predict(dp_model, sess, k=20, precision=precision)
+            single = ops.score_topk(sess, dp_model.get_item_embeddings(), 20, precision=precision)[1]
+            same = same and bool(torch.equal(top, single))
     if world > 1:
         flag = torch.tensor([int(same), int(ok)], device="cuda")
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)

@@ -2,15 +2,10 @@
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/dp_timeline.py [peer|nccl] [rr|scaled]
 
-Segments of one step, averaged over the timed steps, per rank (max / min over ranks printed by rank 0):
-  driver      forward + loss + backward (etpgt_gt_step_run; under the peer exchange it contains the four in-kernel
-              BatchNorm all-reduces, under NCCL the phase cuts + all-reduces)
-  barrier_1   peer: every rank's backward is complete (waits for the slowest rank = load imbalance)
-  dense_sum   peer: flat dense-gradient sum over the peers      | nccl: flat all-reduce
-  table       peer: reduce-scatter + AdamW + all-gather kernel   | nccl: (rest of) the table all-reduce
-  barrier_2   peer: all tables complete
-  clear+adam  peer: gradient-buffer memset + dense AdamW         | nccl: replicated AdamW over every parameter
-The same step on ONE rank (no exchange) is measured first as the reference point."""
+Prints, per mark, the mean offset from the start of its step (max / min over ranks): `driver` = end of forward + loss +
+backward; peer exchange: `table_grad_ready`, `side_barrier_in`, `side_table_done` (the table's reduce-scatter + AdamW +
+all-gather on the exchange stream), `main_barrier` (every rank's backward complete: waits for the slowest rank),
+`dense_sum`, `end`; NCCL: `allreduce`, `end`.  Run it with one process for the single-GPU reference point."""
 import json
 import os
 import sys
@@ -71,15 +66,18 @@ def main():
         e.record()
         marks.setdefault(name, []).append(e)
 
-    if peer is not None:        # split optimizer.step() of the peer exchange into its parts
+    if peer is not None:        # marks inside optimizer.step() of the peer exchange (each on the stream it runs on)
         comm = peer.comm
-        real_barrier, real_sum, real_update = comm.barrier, comm.sum_f32, peer.update_table
-        state = {"n": 0}
+        real_barrier, real_sum, real_ready = comm.barrier, comm.sum_f32, peer.mark_table_ready
+        state = {"side": 0}
 
         def barrier(channel=0):
             real_barrier(channel)
-            state["n"] += 1
-            mark("barrier_1" if state["n"] % 2 == 1 else "barrier_2")
+            if channel == 0:
+                mark("main_barrier")
+            else:
+                state["side"] += 1
+                mark("side_barrier_in" if state["side"] % 2 == 1 else "side_table_done")
         comm.barrier = barrier
 
         def sum_f32(*a):
@@ -87,7 +85,11 @@ def main():
             mark("dense_sum")
             return out
         comm.sum_f32 = sum_f32
-        table_call = ops._lib.call if hasattr(ops, "_lib") else None   # noqa: F841
+
+        def ready():
+            real_ready()
+            mark("table_grad_ready")
+        peer.mark_table_ready = ready
 
     def step(i):
         b = batches[i % rotate]
@@ -106,7 +108,7 @@ def main():
     torch.cuda.synchronize()
     marks.clear()
     if peer is not None:
-        state["n"] = 0
+        state["side"] = 0
     if world > 1:
         dist.barrier()
     for i in range(steps):
@@ -114,12 +116,11 @@ def main():
     torch.cuda.synchronize()
     if peer is not None:
         peer.comm.check()
-    names = ["start", "driver"] + (["barrier_1", "dense_sum", "barrier_2"] if peer is not None else
-                                   (["allreduce"] if world > 1 else [])) + ["end"]
+    # a timeline: mean offset (ms) of every mark from the start of its step
     seg = {}
-    for a, b in zip(names[:-1], names[1:]):
-        seg[f"{a}->{b}"] = float(np.mean([x.elapsed_time(y) for x, y in zip(marks[a], marks[b])]))
-    seg["step"] = float(np.mean([x.elapsed_time(y) for x, y in zip(marks["start"], marks["end"])]))
+    for name, events in marks.items():
+        if name != "start" and len(events) == len(marks["start"]):
+            seg[name] = float(np.mean([x.elapsed_time(y) for x, y in zip(marks["start"], events)]))
     seg["step_to_step"] = float(np.mean([x.elapsed_time(y) for x, y in zip(marks["start"][:-1], marks["start"][1:])]))
     seg["nodes"] = int(np.mean([b.x.numel() for b in batches]))
     if world > 1:
@@ -129,11 +130,12 @@ def main():
         gathered = [seg]
     if rank == 0:
         out = {"exchange": exchange if world > 1 else "none", "workload": workload, "world": world,
-               "segments_ms_max_over_ranks": {k: max(g[k] for g in gathered) for k in seg},
-               "segments_ms_min_over_ranks": {k: min(g[k] for g in gathered) for k in seg},
-               "notes": "peer: barrier_1->dense_sum = dense sum kernel, dense_sum->barrier_2 = table kernel "
-                        "(reduce-scatter + AdamW + all-gather) + barrier, barrier_2->end = gradient clear + dense AdamW; "
-                        "driver->barrier_1 = wait for the slowest rank"}
+               "offsets_ms_max_over_ranks": dict(sorted(((k, max(g[k] for g in gathered)) for k in seg), key=lambda kv: kv[1])),
+               "offsets_ms_min_over_ranks": dict(sorted(((k, min(g[k] for g in gathered)) for k in seg), key=lambda kv: kv[1])),
+               "notes": "mean offset of each mark from the start of its step; peer exchange: table_grad_ready (end of the "
+                        "phase that completes the table gradient) -> side_barrier_in -> side_table_done is the table's "
+                        "reduce-scatter + AdamW + all-gather on the exchange stream, underneath driver (end of backward) "
+                        "-> main_barrier (wait for the slowest rank) -> dense_sum -> end (dense AdamW, join)"}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
