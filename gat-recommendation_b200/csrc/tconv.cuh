@@ -278,7 +278,7 @@ inline HubPlanView hub_plan_view(void* plan, int64_t num_edges) {
 
 // tconv_hub.cu: the hub halves of the three passes (launched by tconv.cu after its own row kernels, which skip rows
 // with more than kHubThreshold edges when a plan is given).  `hub_ws` holds the per-chunk partials.
-constexpr int kHubColsumCtas = 8;    // CTAs (= partial rows) of the hub combine kernels that also sum columns
+constexpr int kHubColsumCtas = 32;   // CTAs (= partial rows) of the hub combine kernels: 256 rows in one round at dim 256
 int tconv_fwd_hubs(const float* qkvs, int dim, int heads, const int32_t* col, const int32_t* eperm,
                    int64_t num_edges, const float* w_beta, const float* alpha_mask, float* out, float* agg, float* beta,
                    float* m, float* inv_l, const void* hub_plan, void* hub_ws, cudaStream_t stream);

@@ -147,18 +147,33 @@ tconv_fwd_hub_combine_kernel(const float* __restrict__ qkvs, const int32_t* __re
     float4 acc[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) { m[v] = -INFINITY; l[v] = 0.f; acc[v] = zero4(); }
-    for (int c = 0; c < r.num_chunks; ++c) {   // chunk order: deterministic
-      const float* src = partial + (int64_t)(r.first_chunk + c) * STRIDE;
+    constexpr int kAhead = 4;   // chunk partials loaded ahead of the (ordered) merge: a long row is a chain of loads
+    for (int c0 = 0; c0 < r.num_chunks; c0 += kAhead) {
+      float mc[kAhead][V], lc[kAhead][V];
+      float4 a[kAhead][V];
 #pragma unroll
-      for (int v = 0; v < V; ++v) {
-        const int h = head_of<DIM, HEAD_DIM>(v, lig);
-        const float mc = src[DIM + h], lc = src[DIM + 8 + h];
-        const float4 a = ldg4(src + 4 * (v * LPN + lig));
-        const float m_new = fmaxf(m[v], mc);
-        const float w0 = expf(m[v] - m_new), w1 = expf(mc - m_new);
-        l[v] = l[v] * w0 + lc * w1;
-        acc[v] = fma4(w1, a, scale4(w0, acc[v]));
-        m[v] = m_new;
+      for (int u = 0; u < kAhead; ++u) {
+        const int c = min(c0 + u, r.num_chunks - 1);
+        const float* src = partial + (int64_t)(r.first_chunk + c) * STRIDE;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const int h = head_of<DIM, HEAD_DIM>(v, lig);
+          mc[u][v] = src[DIM + h];
+          lc[u][v] = src[DIM + 8 + h];
+          a[u][v] = ldg4(src + 4 * (v * LPN + lig));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kAhead; ++u) {   // chunk order: deterministic
+        if (c0 + u >= r.num_chunks) break;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const float m_new = fmaxf(m[v], mc[u][v]);
+          const float w0 = expf(m[v] - m_new), w1 = expf(mc[u][v] - m_new);
+          l[v] = l[v] * w0 + lc[u][v] * w1;
+          acc[v] = fma4(w1, a[u][v], scale4(w0, acc[v]));
+          m[v] = m_new;
+        }
       }
     }
     const int64_t nrow = r.node;
@@ -260,12 +275,26 @@ tconv_bwd_hub_combine_kernel(const int32_t* __restrict__ num_rows_ptr, const Hub
     for (int r = 0; r < ROWS; ++r)
 #pragma unroll
       for (int v = 0; v < V; ++v) s[r][v] = zero4();
-    for (int c = 0; c < hub.num_chunks; ++c) {
-      const float* src = partial + (int64_t)(hub.first_chunk + c) * ROWS * DIM;
+    constexpr int kAhead = 4;   // chunk partials loaded ahead of the (ordered) sum
+    for (int c0 = 0; c0 < hub.num_chunks; c0 += kAhead) {
+      float4 part[kAhead][ROWS][V];
 #pragma unroll
-      for (int r = 0; r < ROWS; ++r)
+      for (int u = 0; u < kAhead; ++u) {
+        const int c = min(c0 + u, hub.num_chunks - 1);
+        const float* src = partial + (int64_t)(hub.first_chunk + c) * ROWS * DIM;
 #pragma unroll
-        for (int v = 0; v < V; ++v) s[r][v] = add4(s[r][v], ldg4(src + r * DIM + 4 * (v * LPN + lig)));
+        for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+          for (int v = 0; v < V; ++v) part[u][r][v] = ldg4(src + r * DIM + 4 * (v * LPN + lig));
+      }
+#pragma unroll
+      for (int u = 0; u < kAhead; ++u) {
+        if (c0 + u >= hub.num_chunks) break;
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+          for (int v = 0; v < V; ++v) s[r][v] = add4(s[r][v], part[u][r][v]);
+      }
     }
 #pragma unroll
     for (int r = 0; r < ROWS; ++r)

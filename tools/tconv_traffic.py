@@ -7,6 +7,7 @@ batch shape to profiles/tconv_traffic.json, which bench.py reports as roofline.t
     python tools/tconv_traffic.py raw.csv bench_log tag      # on the GPU box: writes gpurun_out/<tag>_tconv_ncu_full.csv
                                                              # and gpurun_out/<tag>_tconv_traffic_entry.json
     python tools/tconv_traffic.py --merge tag                # here: copies both into profiles/ (tconv_traffic.json)
+    python tools/tconv_traffic.py --summary raw.csv out.csv  # the judged columns of any raw ncu dump
 """
 import csv
 import json
@@ -35,9 +36,28 @@ def merge(tag):
     print("merged", entry)
 
 
+def summary(raw, out_csv):
+    """The judged columns of any `ncu --page raw --csv` dump."""
+    rows = [r for r in csv.reader(open(raw)) if r]
+    hdr = next(r for r in rows if "Kernel Name" in r)
+    units = rows[rows.index(hdr) + 1]
+    data = [dict(zip(hdr, r)) for r in rows[rows.index(hdr) + 2:] if len(r) == len(hdr)]
+    unit = dict(zip(hdr, units))
+    keep = [k for k in KEEP if k in hdr]
+    with open(out_csv, "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(keep)
+        w.writerow([unit.get(k, "") for k in keep])
+        for d in data:
+            w.writerow([d[k] for k in keep])
+    print(f"{len(data)} launches -> {out_csv}")
+
+
 def main():
     if sys.argv[1] == "--merge":
         return merge(sys.argv[2])
+    if sys.argv[1] == "--summary":
+        return summary(sys.argv[2], sys.argv[3])
     raw, log, tag = sys.argv[1], sys.argv[2], sys.argv[3]
     rows = [r for r in csv.reader(open(raw)) if r]
     hdr = next(r for r in rows if "Kernel Name" in r)
