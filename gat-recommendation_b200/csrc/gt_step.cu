@@ -79,6 +79,7 @@ size_t scratch_bytes_of(const etpgt_gt_step_t& s) {
   need = max_sz(need, etpgt_gemm_bf16x3_workspace_bytes(n, dim, width, 1));
   need = max_sz(need, etpgt_gemm_bf16x3_workspace_bytes(width, dim, n, 0));
   need = max_sz(need, etpgt_bn_workspace_bytes(n, dim));
+  need = max_sz(need, etpgt_tconv_fwd_bn_workspace_bytes(dim));
   need = max_sz(need, etpgt_tconv_bwd_workspace_bytes(n, e, dim, s.heads));
   need = max_sz(need, etpgt_sampled_loss_workspace_bytes(b, s.num_neg, dim));
   need = max_sz(need, etpgt_embed_pe_bwd_workspace_bytes(n, dim, s.k_pe > 0 ? s.k_pe : 1));
@@ -208,16 +209,20 @@ extern "C" int etpgt_gt_step_run(const etpgt_gt_step_t* sp, int phase_begin, int
     TRY(etpgt_gemm_bf16x3_ex(B.x_hi, B.x_lo, B.w_hi, B.w_lo, n, width, dim, dim, dim, 0, 0, P.bias, 0, B.qkvs, width,
                              1, lay.scratch, etpgt_gemm_bf16x3_workspace_bytes(n, width, dim, 1), stream_));
     if (B.alpha_mask) TRY(etpgt_dropout_mask(P.alpha_seed, s.alpha_p, e * heads, B.alpha_mask, stream_));
-    TRY(etpgt_tconv_fwd(B.qkvs, n, dim, heads, s.rowptr, s.col, s.eperm, e, P.w_beta, B.alpha_mask, B.conv_out,
-                        B.agg, B.beta, B.m, B.inv_l, stream_));
     if (s.training) {
-      TRY(etpgt_bn_stats(B.conv_out, n, dim, fwd_sums(l), lay.scratch, etpgt_bn_workspace_bytes(n, dim), stream_));
+      // the BatchNorm statistics of the conv output come out of the conv kernel itself (no second pass over it)
+      TRY(etpgt_tconv_fwd_bn(B.qkvs, n, dim, heads, s.rowptr, s.col, s.eperm, e, P.w_beta, B.alpha_mask, B.conv_out,
+                             B.agg, B.beta, B.m, B.inv_l, nullptr, nullptr, 0, fwd_sums(l), lay.scratch,
+                             etpgt_tconv_fwd_bn_workspace_bytes(dim), stream_));
       if (s.distributed) {
         fill_tail_kernel<<<1, 32, 0, stream>>>(fwd_sums(l) + 2 * dim, (double)n, nullptr, 0.f);
         ETPGT_CHECK_LAUNCH("gt_step count");
         // peer memory: the exchange is one kernel of this stream instead of a phase cut + host collective
         if (s.comm) TRY(etpgt_comm_allreduce_f64(s.comm, fwd_sums(l), fwd_sums(l), sums_len, stream_));
       }
+    } else {
+      TRY(etpgt_tconv_fwd(B.qkvs, n, dim, heads, s.rowptr, s.col, s.eperm, e, P.w_beta, B.alpha_mask, B.conv_out,
+                          B.agg, B.beta, B.m, B.inv_l, stream_));
     }
     return ETPGT_OK;
   };

@@ -67,6 +67,69 @@ tconv_fwd_kernel(const float* __restrict__ qkvs, int64_t num_nodes, const int32_
                               invl_out);
 }
 
+// The same forward as a persistent kernel that also takes the BatchNorm statistics of its output (column sums of
+// out and out^2 in double) while the rows are in registers: the layer's separate statistics pass — one more read of
+// [N, DIM] — disappears.  Lane groups accumulate into their own shared-memory slots, the CTA's groups are added in a
+// fixed order into one partial row, a second stage adds the rows in a fixed order: deterministic, no atomics.
+template <int DIM, int HEAD_DIM, int UNROLL>
+__global__ void __launch_bounds__(kThreads, UNROLL <= 2 ? 4 : 2)
+tconv_fwd_stats_kernel(const float* __restrict__ qkvs, int64_t num_nodes, const int32_t* __restrict__ rowptr,
+                       const int32_t* __restrict__ col, const int32_t* __restrict__ eperm,
+                       const float* __restrict__ w_beta, const float* __restrict__ alpha_mask,
+                       float* __restrict__ out, float* __restrict__ agg_out, float* __restrict__ beta_out,
+                       float* __restrict__ m_out, float* __restrict__ invl_out, int hub_threshold,
+                       double* __restrict__ stat_partial /* [gridDim.x][2*DIM] */) {
+  using G = RowGeom<DIM>;
+  constexpr int V = G::V, LPN = G::LPN;
+  extern __shared__ double stat_s[];   // [(kThreads/32)*GROUPS][2*DIM]
+  const int lane = threadIdx.x & 31;
+  const int lig = lane % LPN;
+  const int warp_in_cta = threadIdx.x >> 5;
+  const int64_t nodes_per_cta = (kThreads / 32) * G::GROUPS;
+  double* stat_mine = stat_s + (size_t)(warp_in_cta * G::GROUPS + lane / LPN) * 2 * DIM;
+#pragma unroll
+  for (int v = 0; v < V; ++v)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { stat_mine[4 * (v * LPN + lig) + c] = 0.0; stat_mine[DIM + 4 * (v * LPN + lig) + c] = 0.0; }
+  for (int64_t base = blockIdx.x * nodes_per_cta; base < num_nodes; base += (int64_t)gridDim.x * nodes_per_cta) {
+    const int64_t warp_base = base + warp_in_cta * G::GROUPS;
+    if (warp_base >= num_nodes) continue;  // warp-uniform
+    const int64_t node = warp_base + lane / LPN;
+    const bool valid = node < num_nodes;
+    const int64_t nrow = valid ? node : 0;
+    const float* self = qkvs + nrow * 4 * DIM;
+    float4 q[V];
+    load_row<DIM>(self, lig, q);
+    const int begin = valid ? rowptr[nrow] : 0;
+    int deg = valid ? rowptr[nrow + 1] - begin : 0;
+    const bool hub = deg > hub_threshold;
+    if (hub) deg = 0;
+    int deg_max = deg;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) deg_max = max(deg_max, __shfl_xor_sync(0xffffffffu, deg_max, off));
+    float m[V], l[V];
+    float4 acc[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) { m[v] = -INFINITY; l[v] = 0.f; acc[v] = zero4(); }
+    fwd_edges<DIM, HEAD_DIM, UNROLL>(qkvs, q, col, eperm, alpha_mask, begin, deg, deg_max, nrow, lig, m, l, acc);
+    fwd_epilogue<DIM, HEAD_DIM>(self, valid && !hub, nrow, lig, m, l, acc, w_beta, out, agg_out, beta_out, m_out,
+                                invl_out, stat_mine);
+  }
+  stats_flush<DIM>(stat_s, stat_partial + (size_t)blockIdx.x * 2 * DIM);
+}
+
+// one warp per output column: lanes stride over the partial rows, fixed butterfly -> deterministic
+__global__ void stats_reduce_kernel(const double* __restrict__ partial, int parts, int width, double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= width) return;
+  double s = 0;
+  for (int p = lane; p < parts; p += 32) s += partial[(int64_t)p * width + i];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (lane == 0) out[i] = s;
+}
+
 // ------------------------------------------------------------ backward, destination pass
 // Per destination i: gate backward (d_agg, d_skip, w_beta partials), delta_h = <d_agg, agg>_h,
 // then over in-edges: alpha (recomputed from saved m, 1/l), d_alpha = <d_agg, v_j>_h,
@@ -314,11 +377,19 @@ extern "C" size_t etpgt_tconv_hub_workspace_bytes(int64_t num_edges, int dim) {
   return align_up((size_t)hub_cap_chunks(num_edges < 0 ? 0 : num_edges) * row * sizeof(float)) + 256;
 }
 
-extern "C" int etpgt_tconv_fwd_hub(const float* qkvs, int64_t num_nodes, int dim, int heads,
-                                   const int32_t* rowptr, const int32_t* col, const int32_t* eperm,
-                                   int64_t num_edges, const float* w_beta, const float* alpha_mask, float* out,
-                                   float* agg, float* beta, float* m, float* inv_l, const void* hub_plan,
-                                   void* hub_ws, size_t hub_ws_bytes, etpgt_stream_t stream_) {
+constexpr int kStatCtasPerSm = 4;
+
+extern "C" size_t etpgt_tconv_fwd_bn_workspace_bytes(int dim) {
+  return align_up((size_t)(kNumSMs * kStatCtasPerSm + kHubColsumCtas) * 2 * dim * sizeof(double)) + 256;
+}
+
+// bn_sums == NULL: the plain forward.  Else the persistent statistics variant: bn_sums [2*dim] doubles = column sums
+// of out and of out^2 over all rows (what etpgt_bn_stats computes from a second pass over out).
+static int tconv_fwd_impl(const float* qkvs, int64_t num_nodes, int dim, int heads, const int32_t* rowptr,
+                          const int32_t* col, const int32_t* eperm, int64_t num_edges, const float* w_beta,
+                          const float* alpha_mask, float* out, float* agg, float* beta, float* m, float* inv_l,
+                          const void* hub_plan, void* hub_ws, size_t hub_ws_bytes, double* bn_sums, void* bn_ws,
+                          size_t bn_ws_bytes, etpgt_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ETPGT_REQUIRE(num_nodes >= 0 && num_edges >= 0, "tconv_fwd: negative size");
   ETPGT_REQUIRE(qkvs && rowptr && out && agg && m && inv_l, "tconv_fwd: null pointer");
@@ -326,14 +397,30 @@ extern "C" int etpgt_tconv_fwd_hub(const float* qkvs, int64_t num_nodes, int dim
   ETPGT_REQUIRE(w_beta == nullptr || beta != nullptr, "tconv_fwd: beta output required with w_beta");
   ETPGT_REQUIRE(hub_plan == nullptr || (hub_ws != nullptr && hub_ws_bytes >= etpgt_tconv_hub_workspace_bytes(num_edges, dim)),
                 "tconv_fwd: hub workspace %zu < %zu", hub_ws_bytes, etpgt_tconv_hub_workspace_bytes(num_edges, dim));
-  if (num_nodes == 0) return ETPGT_OK;
+  ETPGT_REQUIRE(bn_sums == nullptr || (bn_ws != nullptr && bn_ws_bytes >= etpgt_tconv_fwd_bn_workspace_bytes(dim)),
+                "tconv_fwd_bn: workspace %zu < %zu", bn_ws_bytes, etpgt_tconv_fwd_bn_workspace_bytes(dim));
+  if (num_nodes == 0) {
+    if (bn_sums != nullptr) cudaMemsetAsync(bn_sums, 0, (size_t)2 * dim * sizeof(double), stream);
+    return ETPGT_OK;
+  }
   const bool sparse = num_edges < 8 * num_nodes;  // session batches: short rows -> shallower unroll, more warps
   const int hub_threshold = hub_plan != nullptr ? kHubThreshold : INT_MAX;
+  double* stat_partial = static_cast<double*>(bn_ws);
+  int parts = 0;
 #define CALL(D, C)                                                                               \
   {                                                                                              \
     const int64_t npc = (kThreads / 32) * RowGeom<D>::GROUPS;                                    \
     const int64_t grid = (num_nodes + npc - 1) / npc;                                            \
-    if (sparse)                                                                                  \
+    if (bn_sums != nullptr) {                                                                    \
+      parts = grid_for(num_nodes, (int)npc, sparse ? kStatCtasPerSm : 2);                        \
+      const size_t smem = (size_t)npc * 2 * D * sizeof(double);                                  \
+      if (sparse)                                                                                \
+        tconv_fwd_stats_kernel<D, C, 2><<<parts, kThreads, smem, stream>>>(qkvs, num_nodes, rowptr, col, eperm, w_beta, \
+                                            alpha_mask, out, agg, beta, m, inv_l, hub_threshold, stat_partial); \
+      else                                                                                       \
+        tconv_fwd_stats_kernel<D, C, 4><<<parts, kThreads, smem, stream>>>(qkvs, num_nodes, rowptr, col, eperm, w_beta, \
+                                            alpha_mask, out, agg, beta, m, inv_l, hub_threshold, stat_partial); \
+    } else if (sparse)                                                                           \
       tconv_fwd_kernel<D, C, 2><<<(unsigned)grid, kThreads, 0, stream>>>(qkvs, num_nodes, rowptr, col, eperm,   \
                                                           w_beta, alpha_mask, out, agg, beta, m, inv_l, hub_threshold); \
     else                                                                                         \
@@ -343,10 +430,35 @@ extern "C" int etpgt_tconv_fwd_hub(const float* qkvs, int64_t num_nodes, int dim
   ETPGT_DISPATCH_DIM_HEADS(dim, heads, CALL)
 #undef CALL
   ETPGT_CHECK_LAUNCH("tconv_fwd");
-  if (hub_plan != nullptr)
-    return tconv_fwd_hubs(qkvs, dim, heads, col, eperm, num_edges, w_beta, alpha_mask, out, agg, beta, m, inv_l, hub_plan,
-                          hub_ws, stream);
+  if (hub_plan != nullptr) {
+    TRY_RC(tconv_fwd_hubs(qkvs, dim, heads, col, eperm, num_edges, w_beta, alpha_mask, out, agg, beta, m, inv_l, hub_plan,
+                          hub_ws, bn_sums ? stat_partial + (size_t)parts * 2 * dim : nullptr, stream));
+    if (bn_sums != nullptr) parts += kHubColsumCtas;
+  }
+  if (bn_sums != nullptr) {
+    stats_reduce_kernel<<<(2 * dim * 32 + 255) / 256, 256, 0, stream>>>(stat_partial, parts, 2 * dim, bn_sums);
+    ETPGT_CHECK_LAUNCH("tconv_fwd statistics reduce");
+  }
   return ETPGT_OK;
+}
+
+extern "C" int etpgt_tconv_fwd_hub(const float* qkvs, int64_t num_nodes, int dim, int heads,
+                                   const int32_t* rowptr, const int32_t* col, const int32_t* eperm,
+                                   int64_t num_edges, const float* w_beta, const float* alpha_mask, float* out,
+                                   float* agg, float* beta, float* m, float* inv_l, const void* hub_plan,
+                                   void* hub_ws, size_t hub_ws_bytes, etpgt_stream_t stream) {
+  return tconv_fwd_impl(qkvs, num_nodes, dim, heads, rowptr, col, eperm, num_edges, w_beta, alpha_mask, out, agg, beta, m,
+                        inv_l, hub_plan, hub_ws, hub_ws_bytes, nullptr, nullptr, 0, stream);
+}
+
+extern "C" int etpgt_tconv_fwd_bn(const float* qkvs, int64_t num_nodes, int dim, int heads, const int32_t* rowptr,
+                                  const int32_t* col, const int32_t* eperm, int64_t num_edges, const float* w_beta,
+                                  const float* alpha_mask, float* out, float* agg, float* beta, float* m, float* inv_l,
+                                  const void* hub_plan, void* hub_ws, size_t hub_ws_bytes, double* bn_sums, void* bn_ws,
+                                  size_t bn_ws_bytes, etpgt_stream_t stream) {
+  ETPGT_REQUIRE(bn_sums != nullptr, "tconv_fwd_bn: null bn_sums");
+  return tconv_fwd_impl(qkvs, num_nodes, dim, heads, rowptr, col, eperm, num_edges, w_beta, alpha_mask, out, agg, beta, m,
+                        inv_l, hub_plan, hub_ws, hub_ws_bytes, bn_sums, bn_ws, bn_ws_bytes, stream);
 }
 
 extern "C" int etpgt_tconv_fwd(const float* qkvs, int64_t num_nodes, int dim, int heads,

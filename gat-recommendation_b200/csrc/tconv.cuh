@@ -95,13 +95,15 @@ __device__ __forceinline__ void fwd_edges(const float* __restrict__ qkvs, const 
 // Forward node epilogue: agg = acc / (l + eps), gate beta = sigmoid(w . [agg, x_r, agg - x_r]), out = beta x_r +
 // (1 - beta) agg; saves agg, beta, m, 1/l.  Every lane of the warp must call it (group_sum shuffles); `store`
 // says whether this lane group owns a row.
+// `stats` (or NULL): this lane group's running column sums in shared memory, [sum o | sum o^2] as 2*DIM doubles (each
+// lane owns its own slots): the BatchNorm statistics of the layer output, taken while the row is still in registers.
 template <int DIM, int HEAD_DIM>
 __device__ __forceinline__ void fwd_epilogue(const float* __restrict__ self, bool store, int64_t nrow, int lig,
                                              const float (&m)[RowGeom<DIM>::V], const float (&l)[RowGeom<DIM>::V],
                                              const float4 (&acc)[RowGeom<DIM>::V], const float* __restrict__ w_beta,
                                              float* __restrict__ out, float* __restrict__ agg_out,
                                              float* __restrict__ beta_out, float* __restrict__ m_out,
-                                             float* __restrict__ invl_out) {
+                                             float* __restrict__ invl_out, double* stats = nullptr) {
   using G = RowGeom<DIM>;
   constexpr int V = G::V, LPN = G::LPN;
   constexpr int HEADS = DIM / HEAD_DIM;
@@ -137,8 +139,27 @@ __device__ __forceinline__ void fwd_epilogue(const float* __restrict__ self, boo
     else o = add4(ag[v], xr[v]);
     st4(out + nrow * DIM + 4 * f, o);
     st4(agg_out + nrow * DIM + 4 * f, ag[v]);
+    if (stats != nullptr) {
+      double* s0 = stats + 4 * f;
+      double* s1 = stats + DIM + 4 * f;
+      s0[0] += o.x; s0[1] += o.y; s0[2] += o.z; s0[3] += o.w;
+      s1[0] += (double)o.x * o.x; s1[1] += (double)o.y * o.y; s1[2] += (double)o.z * o.z; s1[3] += (double)o.w * o.w;
+    }
   }
   if (lig == 0 && beta_out != nullptr) beta_out[nrow] = b;
+}
+
+// Fixed-order reduction of the lane groups' column sums of one CTA into its partial row (the statistics variants of
+// the forward kernels): every thread must call it.
+template <int DIM>
+__device__ __forceinline__ void stats_flush(const double* __restrict__ smem_stats, double* __restrict__ partial_row) {
+  constexpr int NG = (kThreads / 32) * RowGeom<DIM>::GROUPS;
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * DIM; i += kThreads) {
+    double s = 0.0;
+    for (int g = 0; g < NG; ++g) s += smem_stats[(size_t)g * 2 * DIM + i];
+    partial_row[i] = s;
+  }
 }
 
 // Backward, destination side: over `count` in-edges of destination i starting at CSR position `begin`:
@@ -279,9 +300,10 @@ inline HubPlanView hub_plan_view(void* plan, int64_t num_edges) {
 // tconv_hub.cu: the hub halves of the three passes (launched by tconv.cu after its own row kernels, which skip rows
 // with more than kHubThreshold edges when a plan is given).  `hub_ws` holds the per-chunk partials.
 constexpr int kHubColsumCtas = 32;   // CTAs (= partial rows) of the hub combine kernels: 256 rows in one round at dim 256
+// stat_rows (or NULL): kHubColsumCtas rows of 2*dim doubles receiving the hub rows' [sum out | sum out^2]
 int tconv_fwd_hubs(const float* qkvs, int dim, int heads, const int32_t* col, const int32_t* eperm,
                    int64_t num_edges, const float* w_beta, const float* alpha_mask, float* out, float* agg, float* beta,
-                   float* m, float* inv_l, const void* hub_plan, void* hub_ws, cudaStream_t stream);
+                   float* m, float* inv_l, const void* hub_plan, void* hub_ws, double* stat_rows, cudaStream_t stream);
 // dq of hub destinations; colsum_rows (or NULL): kHubColsumCtas rows of `width` floats whose columns
 // [col_offset, col_offset + dim) receive the column sums of those dq rows (the other columns are zeroed)
 int tconv_bwd_dst_hubs(const float* qkvs, int dim, int heads, const int32_t* col, const int32_t* eperm,

@@ -130,13 +130,23 @@ __global__ void __launch_bounds__(kThreads)
 tconv_fwd_hub_combine_kernel(const float* __restrict__ qkvs, const int32_t* __restrict__ num_rows_ptr,
                              const HubRow* __restrict__ rows, const float* __restrict__ partial,
                              const float* __restrict__ w_beta, float* __restrict__ out, float* __restrict__ agg_out,
-                             float* __restrict__ beta_out, float* __restrict__ m_out, float* __restrict__ invl_out) {
+                             float* __restrict__ beta_out, float* __restrict__ m_out, float* __restrict__ invl_out,
+                             double* __restrict__ stat_rows /* [gridDim.x][2*DIM] or NULL */) {
   using G = RowGeom<DIM>;
   constexpr int V = G::V, LPN = G::LPN, NG = HubGeom<DIM>::NG;
   constexpr int STRIDE = DIM + kPartPad;
+  extern __shared__ double stat_s[];   // [NG][2*DIM] when stat_rows != NULL
   const int lane = threadIdx.x & 31;
   const int lig = lane % LPN;
   const int num_rows = *num_rows_ptr;
+  double* stat_mine = nullptr;
+  if (stat_rows != nullptr) {
+    stat_mine = stat_s + (size_t)((threadIdx.x >> 5) * G::GROUPS + lane / LPN) * 2 * DIM;
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { stat_mine[4 * (v * LPN + lig) + c] = 0.0; stat_mine[DIM + 4 * (v * LPN + lig) + c] = 0.0; }
+  }
   for (int base = blockIdx.x * NG; base < num_rows; base += gridDim.x * NG) {
     const int warp_base = base + (threadIdx.x >> 5) * G::GROUPS;
     if (warp_base >= num_rows) continue;   // warp-uniform
@@ -178,8 +188,9 @@ tconv_fwd_hub_combine_kernel(const float* __restrict__ qkvs, const int32_t* __re
     }
     const int64_t nrow = r.node;
     fwd_epilogue<DIM, HEAD_DIM>(qkvs + nrow * 4 * DIM, valid, nrow, lig, m, l, acc, w_beta, out, agg_out, beta_out, m_out,
-                                invl_out);
+                                invl_out, stat_mine);
   }
+  if (stat_rows != nullptr) stats_flush<DIM>(stat_s, stat_rows + (size_t)blockIdx.x * 2 * DIM);
 }
 
 // ------------------------------------------------------------------------------- backward, destination side
@@ -368,7 +379,7 @@ int chunk_grid(int64_t num_edges) {
 
 int tconv_fwd_hubs(const float* qkvs, int dim, int heads, const int32_t* col, const int32_t* eperm, int64_t num_edges,
                    const float* w_beta, const float* alpha_mask, float* out, float* agg, float* beta, float* m,
-                   float* inv_l, const void* hub_plan, void* hub_ws, cudaStream_t stream) {
+                   float* inv_l, const void* hub_plan, void* hub_ws, double* stat_rows, cudaStream_t stream) {
   const HubPlanView plan = hub_plan_view(const_cast<void*>(hub_plan), num_edges);
   float* partial = static_cast<float*>(hub_ws);
   const int grid = chunk_grid(num_edges);
@@ -376,8 +387,9 @@ int tconv_fwd_hubs(const float* qkvs, int dim, int heads, const int32_t* col, co
   {                                                                                                                  \
     tconv_fwd_hub_chunk_kernel<D, C><<<grid, kThreads, 0, stream>>>(qkvs, col, eperm, alpha_mask, plan.counts + 1,  \
                                                                     plan.dst_chunks, partial);                      \
-    tconv_fwd_hub_combine_kernel<D, C><<<kHubColsumCtas, kThreads, 0, stream>>>(                                    \
-        qkvs, plan.counts, plan.dst_rows, partial, w_beta, out, agg, beta, m, inv_l);                               \
+    const size_t smem = stat_rows ? (size_t)HubGeom<D>::NG * 2 * D * sizeof(double) : 0;                            \
+    tconv_fwd_hub_combine_kernel<D, C><<<kHubColsumCtas, kThreads, smem, stream>>>(                                 \
+        qkvs, plan.counts, plan.dst_rows, partial, w_beta, out, agg, beta, m, inv_l, stat_rows);                    \
   }
   ETPGT_DISPATCH_DIM_HEADS(dim, heads, CALL)
 #undef CALL

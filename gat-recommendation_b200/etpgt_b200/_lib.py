@@ -44,6 +44,8 @@ _PROTOTYPES = {
     "etpgt_hub_plan": (I, [P, P, L, L, P, P, Z, P]),
     "etpgt_tconv_hub_workspace_bytes": (Z, [L, I]),
     "etpgt_tconv_fwd_hub": (I, [P, L, I, I, P, P, P, L, P, P, P, P, P, P, P, P, P, Z, P]),
+    "etpgt_tconv_fwd_bn_workspace_bytes": (Z, [I]),
+    "etpgt_tconv_fwd_bn": (I, [P, L, I, I, P, P, P, L, P, P, P, P, P, P, P, P, P, Z, P, P, Z, P]),
     "etpgt_tconv_bwd_split_hub": (I, [P, P, L, I, I, P, P, P, P, P, P, L, P, P, P, P, P, P, P, P, P, P, P, P, Z, P, P, Z,
                                       P]),
     "etpgt_split_bf16_workspace_bytes": (Z, [L, L]),

@@ -421,13 +421,21 @@ class EmbedPE(torch.autograd.Function):
 # ------------------------------------------------------------------------------ TransformerConv
 
 
-def _tconv_fwd(qkvs, n, dim, heads, index: GraphIndex, w_beta, mask, out, agg, beta, m, inv_l) -> None:
-    """etpgt_tconv_fwd, with the hub-row kernels when the graph has rows of more than 256 edges."""
+def _tconv_fwd(qkvs, n, dim, heads, index: GraphIndex, w_beta, mask, out, agg, beta, m, inv_l, bn_sums=None) -> None:
+    """etpgt_tconv_fwd, with the hub-row kernels when the graph has rows of more than 256 edges; bn_sums (double
+    [>= 2*dim]): the BatchNorm statistics of `out` are taken by the same kernel (etpgt_tconv_fwd_bn)."""
     hub = index.hub_plan()
     hub_ws = workspace(size("etpgt_tconv_hub_workspace_bytes", index.num_edges, dim), qkvs.device) if hub is not None else None
-    call("etpgt_tconv_fwd_hub", ptr(qkvs), n, dim, heads, ptr(index.rowptr), ptr(index.col), ptr(index.eperm),
+    hub_bytes = hub_ws.numel() if hub_ws is not None else 0
+    if bn_sums is None:
+        call("etpgt_tconv_fwd_hub", ptr(qkvs), n, dim, heads, ptr(index.rowptr), ptr(index.col), ptr(index.eperm),
+             index.num_edges, ptr(w_beta), ptr(mask), ptr(out), ptr(agg), ptr(beta), ptr(m), ptr(inv_l), ptr(hub),
+             ptr(hub_ws), hub_bytes, stream())
+        return
+    ws = workspace(size("etpgt_tconv_fwd_bn_workspace_bytes", dim), qkvs.device)
+    call("etpgt_tconv_fwd_bn", ptr(qkvs), n, dim, heads, ptr(index.rowptr), ptr(index.col), ptr(index.eperm),
          index.num_edges, ptr(w_beta), ptr(mask), ptr(out), ptr(agg), ptr(beta), ptr(m), ptr(inv_l), ptr(hub),
-         ptr(hub_ws), hub_ws.numel() if hub_ws is not None else 0, stream())
+         ptr(hub_ws), hub_bytes, ptr(bn_sums), ptr(ws), ws.numel(), stream())
 
 
 def _tconv_bwd(qkvs, d_out, n, dim, heads, index: GraphIndex, w_beta, mask, agg, beta, m, inv_l, d_qkvs, g_hi, g_lo,
@@ -640,14 +648,13 @@ class TransformerLayer(torch.autograd.Function):
         f32 = dict(dtype=torch.float32, device=dev)
         conv_out, agg = torch.empty(n, dim, **f32), torch.empty(n, dim, **f32)
         beta, m, inv_l = torch.empty(n, **f32), torch.empty(n, heads, **f32), torch.empty(n, heads, **f32)
-        _tconv_fwd(qkvs, n, dim, heads, index, w_beta_c, mask_c, conv_out, agg, beta, m, inv_l)
+        sums = torch.empty(2 * dim + 1, dtype=torch.float64, device=dev) if training else None
+        # (training: the BatchNorm statistics of the conv output are taken by the conv kernel itself)
+        _tconv_fwd(qkvs, n, dim, heads, index, w_beta_c, mask_c, conv_out, agg, beta, m, inv_l, bn_sums=sums)
         gamma_c, bn_bias_c = _f32(gamma), _f32(bn_bias)
         mean, invstd = torch.empty(dim, **f32), torch.empty(dim, **f32)
         count = float(n)
         if training:
-            sums = torch.empty(2 * dim + 1, dtype=torch.float64, device=dev)
-            ws = workspace(size("etpgt_bn_workspace_bytes", n, dim), dev)
-            call("etpgt_bn_stats", ptr(conv_out), n, dim, ptr(sums), ptr(ws), ws.numel(), stream())
             if _dist_ready(group):
                 sums[2 * dim:].fill_(count)
                 dist.all_reduce(sums, group=group or None)

@@ -157,6 +157,17 @@ int etpgt_tconv_fwd_hub(const float* qkvs, int64_t num_nodes, int dim, int heads
                         const int32_t* col, const int32_t* eperm, int64_t num_edges, const float* w_beta,
                         const float* alpha_mask, float* out, float* agg, float* beta, float* m, float* inv_l,
                         const void* hub_plan, void* hub_ws, size_t hub_ws_bytes, etpgt_stream_t stream);
+/* The forward that also takes the BatchNorm statistics of its output while the rows are in registers
+ * (graph_transformer.py:174-175: conv -> BatchNorm1d): bn_sums [2*dim] doubles = column sums of out and of out^2 over
+ * all num_nodes rows — the input of etpgt_bn_finalize (append the row count for the data-parallel exchange) — so the
+ * separate statistics pass of etpgt_bn_stats (one more read of [N, dim]) is not needed.  Persistent kernel, per-CTA
+ * partial rows added in a fixed order: deterministic.  hub_plan may be NULL. */
+size_t etpgt_tconv_fwd_bn_workspace_bytes(int dim);
+int etpgt_tconv_fwd_bn(const float* qkvs, int64_t num_nodes, int dim, int heads, const int32_t* rowptr,
+                       const int32_t* col, const int32_t* eperm, int64_t num_edges, const float* w_beta,
+                       const float* alpha_mask, float* out, float* agg, float* beta, float* m, float* inv_l,
+                       const void* hub_plan, void* hub_ws, size_t hub_ws_bytes, double* bn_sums, void* bn_ws,
+                       size_t bn_ws_bytes, etpgt_stream_t stream);
 int etpgt_tconv_bwd_split_hub(const float* qkvs, const float* d_out, int64_t num_nodes, int dim, int heads,
                               const int32_t* rowptr, const int32_t* col, const int32_t* eperm,
                               const int32_t* colptr, const int32_t* row, const int32_t* cpos, int64_t num_edges,

@@ -155,3 +155,53 @@ def test_zipf_graph_matches_oracle_and_the_row_kernels(ops):
         # rows of > 10,000 edges through ONE lane group's serial fp32 walk (the plain row kernels): the same
         # quantities, one order of magnitude looser — the chunked hub path is also the more accurate one
         assert rel_err(b[name], w) < 10 * TOL, f"row kernels, {name}"
+
+
+@pytest.mark.parametrize("graph_kind,dim,heads", [("sessions", 256, 2), ("zipf", 256, 2), ("sessions", 64, 4), ("zipf", 32, 1)])
+def test_forward_with_fused_batchnorm_statistics(ops, graph_kind, dim, heads):
+    """etpgt_tconv_fwd_bn: the persistent forward that also sums out and out^2 per column (double) — outputs
+    bit-identical to the plain forward, statistics equal to a separate etpgt_bn_stats pass over `out` (both are
+    exact-order double sums of the same floats: <= 1e-13 relative), identical bits on a second run."""
+    from etpgt_b200._lib import call, ptr, size, stream, workspace
+
+    rng = np.random.default_rng(dim + heads)
+    if graph_kind == "zipf":
+        n, e = 3000, 90_000
+        ei = zipf_graph(rng, n, e)
+    else:   # many tiny components, like a session batch
+        n, e = 20_000, 58_000
+        src = rng.integers(0, n, size=e)
+        ei = np.stack([src, np.minimum(src + rng.integers(0, 4, size=e), n - 1)]).astype(np.int64)
+    index = ops.GraphIndex(torch.from_numpy(ei).cuda(), n)
+    plan = index.hub_plan()
+    assert (plan is not None) == (graph_kind == "zipf")
+    g = torch.Generator().manual_seed(dim)
+    qkvs = (torch.randn(n, 4 * dim, generator=g) * 0.5).cuda()
+    w_beta = (torch.randn(3 * dim, generator=g) * 0.2).cuda()
+    f32 = dict(dtype=torch.float32, device="cuda")
+    hub_ws = workspace(size("etpgt_tconv_hub_workspace_bytes", e, dim), "cuda")
+    bn_ws = workspace(size("etpgt_tconv_fwd_bn_workspace_bytes", dim), "cuda")
+
+    def run(with_stats):
+        out, agg = torch.empty(n, dim, **f32), torch.empty(n, dim, **f32)
+        bt, m, inv_l = torch.empty(n, **f32), torch.empty(n, heads, **f32), torch.empty(n, heads, **f32)
+        sums = torch.full((2 * dim + 1,), float("nan"), dtype=torch.float64, device="cuda")
+        common = (ptr(qkvs), n, dim, heads, ptr(index.rowptr), ptr(index.col), ptr(index.eperm), e, ptr(w_beta), None,
+                  ptr(out), ptr(agg), ptr(bt), ptr(m), ptr(inv_l), ptr(plan), ptr(hub_ws) if plan is not None else None,
+                  hub_ws.numel() if plan is not None else 0)
+        if with_stats:
+            call("etpgt_tconv_fwd_bn", *common, ptr(sums), ptr(bn_ws), bn_ws.numel(), stream())
+        else:
+            call("etpgt_tconv_fwd_hub", *common, stream())
+        return out, agg, bt, m, inv_l, sums
+
+    plain, fused, again = run(False), run(True), run(True)
+    for a, b in zip(plain[:5], fused[:5]):
+        assert torch.equal(a, b)
+    assert torch.equal(fused[5][:2 * dim], again[5][:2 * dim])
+    want = torch.empty(2 * dim, dtype=torch.float64, device="cuda")
+    ws = workspace(size("etpgt_bn_workspace_bytes", n, dim), "cuda")
+    call("etpgt_bn_stats", ptr(fused[0]), n, dim, ptr(want), ptr(ws), ws.numel(), stream())
+    assert rel_err(fused[5][:2 * dim], want) < 1e-13
+    exact = torch.cat([fused[0].double().sum(0), (fused[0].double() ** 2).sum(0)])
+    assert rel_err(fused[5][:2 * dim], exact) < 1e-12
