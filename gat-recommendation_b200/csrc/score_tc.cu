@@ -315,7 +315,8 @@ constexpr int kSurvivorCap = 512;
 
 __global__ void __launch_bounds__(kSelectWarps * 32)
 score_select_kernel(DumpBuffers dump, int64_t batch, Schedule sch, int k, int64_t id_base,
-                    float* __restrict__ top_val, int64_t* __restrict__ top_idx, int32_t* __restrict__ redo) {
+                    float* __restrict__ top_val, int64_t* __restrict__ top_idx, int32_t* __restrict__ redo,
+                    const int64_t* __restrict__ targets, int32_t* __restrict__ hit_pos) {
   __shared__ uint64_t s_key[kSelectWarps][kSurvivorCap];  // (orderable score, ~column): larger = better
   __shared__ int s_count[kSelectWarps];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -415,12 +416,19 @@ score_select_kernel(DumpBuffers dump, int64_t batch, Schedule sch, int k, int64_
       prev = best;
     }
   }
+  float v;
+  int64_t col;
+  decode_key(mine, v, col);
+  const int64_t id = mine == 0 ? INT64_MAX : id_base + col;
   if (lane < k) {   // one coalesced store of the row's k results
-    float v;
-    int64_t col;
-    decode_key(mine, v, col);
     top_val[row * k + lane] = v;
-    top_idx[row * k + lane] = mine == 0 ? INT64_MAX : id_base + col;
+    top_idx[row * k + lane] = id;
+  }
+  if (targets != nullptr) {
+    // Recall / NDCG input (etpgt/utils/metrics.py:6-66) straight from the registers that hold the sorted list:
+    // position of the row's target among its k results (first match), or -1
+    const unsigned found = __ballot_sync(0xffffffffu, lane < k && id == targets[row]);
+    if (lane == 0) hit_pos[row] = found ? __ffs(found) - 1 : -1;
   }
 }
 
@@ -432,7 +440,8 @@ constexpr int kRedoThreads = 256;
 __global__ void __launch_bounds__(kRedoThreads)
 score_redo_kernel(const __nv_bfloat16* __restrict__ sess, const __nv_bfloat16* __restrict__ table, int64_t batch,
                   int64_t num_items, int dim, int k, int64_t id_base, const int32_t* __restrict__ redo,
-                  float* __restrict__ top_val, int64_t* __restrict__ top_idx) {
+                  float* __restrict__ top_val, int64_t* __restrict__ top_idx, const int64_t* __restrict__ targets,
+                  int32_t* __restrict__ hit_pos) {
   extern __shared__ float redo_smem[];       // session row [dim], then lists
   // a small persistent grid; the flags of kRedoThreads rows are read at once, so rows that need no
   // recomputation (normally all of them) cost one coalesced load per 256 rows
@@ -475,6 +484,7 @@ score_redo_kernel(const __nv_bfloat16* __restrict__ sess, const __nv_bfloat16* _
   __shared__ int32_t r_idx[kRedoThreads / 32];
   float prev_v = INFINITY;
   int32_t prev_i = -1;
+  int found = -1;
   for (int t = 0; t < k; ++t) {
     float bv = -INFINITY;
     int32_t bi = INT32_MAX;
@@ -498,11 +508,13 @@ score_redo_kernel(const __nv_bfloat16* __restrict__ sess, const __nv_bfloat16* _
     if (threadIdx.x == 0) {
       top_val[row * k + t] = bv;
       top_idx[row * k + t] = bi == INT32_MAX ? INT64_MAX : id_base + bi;
+      if (targets != nullptr && found < 0 && bi != INT32_MAX && id_base + bi == targets[row]) found = t;
     }
     prev_v = bv;
     prev_i = bi;
     __syncthreads();
   }
+  if (threadIdx.x == 0 && targets != nullptr) hit_pos[row] = found;
   }
   __syncthreads();                           // s_flag is rewritten by the next block of rows
   }
@@ -598,10 +610,12 @@ extern "C" size_t etpgt_score_topk_bf16_workspace_bytes(int64_t batch, int64_t n
          2 * align_up(units * sizeof(float)) + 2 * align_up((size_t)batch * sizeof(int32_t)) + 256;
 }
 
-extern "C" int etpgt_score_topk_bf16(const void* sess_bf16, const void* table_bf16, int64_t batch,
-                                     int64_t num_items, int dim, int k, int64_t id_base, float* top_val,
-                                     int64_t* top_idx, void* ws, size_t ws_bytes, etpgt_stream_t stream_) {
+extern "C" int etpgt_score_topk_bf16_eval(const void* sess_bf16, const void* table_bf16, int64_t batch,
+                                          int64_t num_items, int dim, int k, int64_t id_base, float* top_val,
+                                          int64_t* top_idx, const int64_t* targets, int32_t* hit_pos, void* ws,
+                                          size_t ws_bytes, etpgt_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ETPGT_REQUIRE((targets == nullptr) == (hit_pos == nullptr), "score_topk_bf16: targets and hit_pos come together");
   ETPGT_REQUIRE(dim == 64 || dim == 128 || dim == 192 || dim == 256,
                 "score_topk_bf16: dim %d must be a multiple of 64 up to 256", dim);
   ETPGT_REQUIRE(batch >= 0 && num_items >= 1 && num_items < (int64_t(1) << 31), "score_topk_bf16: bad sizes");
@@ -661,7 +675,7 @@ extern "C" int etpgt_score_topk_bf16(const void* sess_bf16, const void* table_bf
 #undef LAUNCH2
   ETPGT_CHECK_LAUNCH("score_dump_tc");
   score_select_kernel<<<(unsigned)((batch + kSelectWarps - 1) / kSelectWarps), kSelectWarps * 32, 0, stream>>>(
-      dump, batch, p.sch, k, id_base, top_val, top_idx, redo);
+      dump, batch, p.sch, k, id_base, top_val, top_idx, redo, targets, hit_pos);
   ETPGT_CHECK_LAUNCH("score_select");
   const size_t redo_smem = ((size_t)dim + (size_t)kRedoThreads * k * 2) * sizeof(float);
   if (redo_smem > 48 * 1024)
@@ -670,7 +684,14 @@ extern "C" int etpgt_score_topk_bf16(const void* sess_bf16, const void* table_bf
   const unsigned redo_grid = (unsigned)(redo_blocks < 2 * kNumSMs ? redo_blocks : 2 * kNumSMs);
   score_redo_kernel<<<redo_grid, kRedoThreads, redo_smem, stream>>>(
       static_cast<const __nv_bfloat16*>(sess_bf16), static_cast<const __nv_bfloat16*>(table_bf16), batch, num_items,
-      dim, k, id_base, redo, top_val, top_idx);
+      dim, k, id_base, redo, top_val, top_idx, targets, hit_pos);
   ETPGT_CHECK_LAUNCH("score_redo");
   return ETPGT_OK;
+}
+
+extern "C" int etpgt_score_topk_bf16(const void* sess_bf16, const void* table_bf16, int64_t batch,
+                                     int64_t num_items, int dim, int k, int64_t id_base, float* top_val,
+                                     int64_t* top_idx, void* ws, size_t ws_bytes, etpgt_stream_t stream) {
+  return etpgt_score_topk_bf16_eval(sess_bf16, table_bf16, batch, num_items, dim, k, id_base, top_val, top_idx, nullptr,
+                                    nullptr, ws, ws_bytes, stream);
 }

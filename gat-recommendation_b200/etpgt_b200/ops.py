@@ -1110,13 +1110,15 @@ def tensor_core_scoring_supported(dim: int, k: int) -> bool:
 
 @torch.no_grad()
 def score_topk(sess: torch.Tensor, table: torch.Tensor, k: int, id_base: int = 0, precision: str = "fp32",
-               out: tuple | None = None):
+               out: tuple | None = None, targets: torch.Tensor | None = None):
     """Top-k item ids by dot product, ties to the lower id — etpgt/model/base.py:59-78.
 
     precision "fp32": CUDA-core scorer with the reference's fp32 arithmetic.
     precision "bf16": tcgen05 tensor-core scorer (bf16 operands, fp32 accumulation in TMEM); `table`
     may already be a bf16 copy (an evaluation loop converts it once).
-    out: (top_val [B, k] f32, top_idx [B, k] i64) to write into (contiguous), else fresh tensors."""
+    out: (top_val [B, k] f32, top_idx [B, k] i64) to write into (contiguous), else fresh tensors.
+    targets [B] (bf16 scorer): also returns hit_pos [B] int32 — the position of each target in its row's results or
+    -1, taken inside the scorer's select epilogue (the input of `hit_metrics`): (top_val, top_idx, hit_pos)."""
     _require_cuda(sess, "session embeddings")
     b, dim = sess.shape
     items = table.size(0)
@@ -1132,16 +1134,25 @@ def score_topk(sess: torch.Tensor, table: torch.Tensor, k: int, id_base: int = 0
     if precision == "bf16":
         sess_h, table_h = to_bf16(sess), to_bf16(table)
         ws = workspace(size("etpgt_score_topk_bf16_workspace_bytes", b, items, k), dev)
-        call("etpgt_score_topk_bf16", ptr(sess_h), ptr(table_h), b, items, dim, k, id_base, ptr(top_val),
-             ptr(top_idx), ptr(ws), ws.numel(), stream())
-        return top_val, top_idx
+        hit_pos = None
+        if targets is not None:
+            targets = _i64(targets)
+            hit_pos = torch.empty(b, dtype=torch.int32, device=dev)
+        call("etpgt_score_topk_bf16_eval", ptr(sess_h), ptr(table_h), b, items, dim, k, id_base, ptr(top_val),
+             ptr(top_idx), ptr(targets), ptr(hit_pos), ptr(ws), ws.numel(), stream())
+        return (top_val, top_idx) if targets is None else (top_val, top_idx, hit_pos)
     if precision != "fp32":
         raise ValueError(f"Unknown scoring precision: {precision}")
     sess_c, table_c = _f32(sess.detach()), _f32(table.detach())
     ws = workspace(size("etpgt_score_topk_workspace_bytes", b, items, dim, k), dev)
     call("etpgt_score_topk_f32", ptr(sess_c), ptr(table_c), b, items, dim, k, id_base, ptr(top_val), ptr(top_idx),
          ptr(ws), ws.numel(), stream())
-    return top_val, top_idx
+    if targets is None:
+        return top_val, top_idx
+    # the fp32 CUDA-core scorer (small batches) has no fused epilogue: positions from its id matrix
+    match = top_idx == _i64(targets).view(-1, 1)
+    hit_pos = torch.where(match.any(dim=1), match.float().argmax(dim=1), torch.full((b,), -1, device=dev)).int()
+    return top_val, top_idx, hit_pos
 
 
 @torch.no_grad()

@@ -119,13 +119,9 @@ def sharded_predict(model, session_embeddings: torch.Tensor, k: int = 20, group=
     if size == 1:
         if precision == "auto":
             precision = "bf16" if b_local >= 64 and ops.tensor_core_scoring_supported(width, k) else "fp32"
-        top = ops.score_topk(session_embeddings, table, k, precision=precision)[1]
         if targets is None:
-            return top
-        hit = torch.full((b_local,), -1, dtype=torch.int32, device=dev)
-        match = top == ops._i64(targets).view(-1, 1)
-        found = match.any(dim=1)
-        hit[found] = match.float().argmax(dim=1)[found].int()
+            return ops.score_topk(session_embeddings, table, k, precision=precision)[1]
+        _, top, hit = ops.score_topk(session_embeddings, table, k, precision=precision, targets=targets)
         return top, hit
     if counts is None:
         mine = torch.tensor([b_local], dtype=torch.int64, device=dev)

@@ -158,9 +158,10 @@ class Trainer:
                 for j, k in enumerate(self.k_values):
                     ops.hit_metrics(hit, k, acc[2 * j:2 * j + 2])
             else:
-                top = self.model.predict(sess, k=k_max)
+                # fused scoring + top-k; the target's position comes out of the scorer's select epilogue
+                _, hit = parallel.sharded_predict(self.model, sess, k=k_max, targets=batch.target_item)
                 for j, k in enumerate(self.k_values):
-                    ops.topk_metrics(top, batch.target_item, k, acc[2 * j:2 * j + 2])
+                    ops.hit_metrics(hit, k, acc[2 * j:2 * j + 2])
             sessions += int(batch.target_item.shape[0])
         acc[-1] = sessions
         if self._world > 1:

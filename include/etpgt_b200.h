@@ -385,6 +385,14 @@ size_t etpgt_score_topk_bf16_workspace_bytes(int64_t batch, int64_t num_items, i
 int etpgt_score_topk_bf16(const void* sess_bf16, const void* table_bf16, int64_t batch, int64_t num_items,
                           int dim, int k, int64_t id_base, float* top_val, int64_t* top_idx,
                           void* ws, size_t ws_bytes, etpgt_stream_t stream);
+/* The same with the evaluation metric's input fused into the select epilogue: with targets [batch],
+ * hit_pos[b] = position of targets[b] among the row's k results (first match, etpgt/utils/metrics.py:49) or -1,
+ * taken from the registers that hold the sorted list — the [batch, k] id matrix is not read again.
+ * etpgt_hit_metrics turns hit_pos into the Recall@k / NDCG@k counters for any k <= the k scored. */
+int etpgt_score_topk_bf16_eval(const void* sess_bf16, const void* table_bf16, int64_t batch, int64_t num_items,
+                               int dim, int k, int64_t id_base, float* top_val, int64_t* top_idx,
+                               const int64_t* targets, int32_t* hit_pos, void* ws, size_t ws_bytes,
+                               etpgt_stream_t stream);
 /* exact merge of `parts` candidate lists per row ([B, parts*k] values + ids). */
 int etpgt_topk_merge(const float* cand_val, const int64_t* cand_idx, int64_t batch, int parts, int k,
                      float* top_val, int64_t* top_idx, etpgt_stream_t stream);

@@ -88,3 +88,32 @@ def test_bf16_conversion_matches_torch():
     x = torch.randn(1000, 64) * 100
     x[0, :4] = torch.tensor([1.00390625, -1.00390625, 3.0e38, 1e-40])   # ties-to-even, large, denormal
     assert torch.equal(ops.to_bf16(x.cuda()).cpu(), x.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("cap", [None, "2"])
+def test_target_positions_come_out_of_the_select_epilogue(monkeypatch, cap):
+    """etpgt_score_topk_bf16_eval: hit_pos[b] = position of the row's target among its k results or -1 (the input of
+    Recall@k / NDCG@k, etpgt/utils/metrics.py:6-66), from the select kernel's registers — and from the CUDA-core
+    fallback for rows whose slot buffer overflowed (cap = 2 forces every row there)."""
+    import etpgt_b200.ops as ops
+    from oracle import model_ref
+
+    if cap is not None:
+        monkeypatch.setenv("ETPGT_SCORE_CAP", cap)
+    g = torch.Generator().manual_seed(9)
+    batch, items, dim, k = 300, 4000, 256, 20
+    sess, table = torch.randn(batch, dim, generator=g).cuda(), torch.randn(items, dim, generator=g).cuda()
+    _, plain = ops.score_topk(sess, table, k, precision="bf16")
+    # targets: for two thirds of the rows an id that IS in the list (positions spread over 0..k-1), else a miss
+    pos = torch.arange(batch) % k
+    targets = plain.cpu()[torch.arange(batch), pos].clone()
+    miss = torch.arange(batch) % 3 == 0
+    targets[miss] = items + 5
+    val, idx, hit = ops.score_topk(sess, table, k, precision="bf16", targets=targets.cuda())
+    assert torch.equal(idx, plain)
+    want = torch.where(miss, torch.full_like(pos, -1), pos).int()
+    assert torch.equal(hit.cpu(), want)
+    for kk in (10, 20):
+        acc = ops.hit_metrics(hit, kk).cpu()
+        assert acc[0].item() == pytest.approx(model_ref.recall_at_k(idx.cpu()[:, :kk], targets, kk) * batch)
+        assert acc[1].item() == pytest.approx(model_ref.ndcg_at_k(idx.cpu()[:, :kk], targets, kk) * batch)

@@ -1,3 +1,2 @@
-timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -n 12 > gpurun_out/r02r_gpu_tests.txt
-timeout 600 python bench.py --skip-cpu-baseline > gpurun_out/r02r_bench.json 2> gpurun_out/r02r_bench.err
-tail -n 4 gpurun_out/r02r_gpu_tests.txt; tail -n 3 gpurun_out/r02r_bench.err
+timeout 900 python -m pytest tests/test_gpu_score_tc.py tests/test_gpu_step.py tests/test_gpu_peer.py tests/test_gpu_training.py -q 2>&1 | tail -n 15 > gpurun_out/r02t_gpu_tests.txt
+tail -n 6 gpurun_out/r02t_gpu_tests.txt

@@ -18,10 +18,10 @@ batch = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
 data = synth.generate()
 keys = synth.sorted_edge_keys(data)
 dev = torch.device("cuda")
-db = [h.to_device(dev) for h in bench.make_batches(data, keys, 0, batch, 2, seed=1, pin=False)]
+db = [h.to_device(dev) for h in bench.make_host_batches(data, keys, 0, batch, 2, seed=1, pin=False)]
 torch.manual_seed(0)
-model = (create_gat(bench.NUM_ITEMS, 256, 256, 3, 4, dropout=0.1) if kind == "gat"
-         else create_graphsage(bench.NUM_ITEMS, 256, 256, 3, dropout=0.1)).to(dev)
+model = (create_gat(82174, 256, 256, 3, 4, dropout=0.1) if kind == "gat"
+         else create_graphsage(82174, 256, 256, 3, dropout=0.1)).to(dev)
 opt = optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-5)
 model.train()
 

@@ -19,10 +19,10 @@ batch = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 data = synth.generate()
 keys = synth.sorted_edge_keys(data)
 dev = torch.device("cuda")
-hb = bench.make_batches(data, keys, 0, batch, 2, seed=1, pin=True)
+hb = bench.make_host_batches(data, keys, 0, batch, 2, seed=1, pin=True)
 db = [h.to_device(dev) for h in hb]
-model = create_graph_transformer_optimized(bench.NUM_ITEMS, 256, 256, 2, 2, dropout=0.1).to(dev)
-model.laplacian_pe._cached_pe = bench.cached_pe(bench.NUM_ITEMS).to(dev)
+model = create_graph_transformer_optimized(82174, 256, 256, 2, 2, dropout=0.1).to(dev)
+model.laplacian_pe._cached_pe = bench.cached_pe(82174).to(dev)
 opt = optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-5)
 model.train()
 
