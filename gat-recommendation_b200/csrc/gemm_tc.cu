@@ -239,6 +239,204 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
   }
 }
 
+// ---- the same GEMM on CTA pairs (cta_group::2) ---------------------------------------------------------------
+// The single-CTA kernel above is bound by L2 -> shared-memory traffic: every CTA pulls its own copy of the B tile
+// (the weights in the forward projection: all 148 CTAs reload the same 256 x 1024 matrix per k-block).  Here two
+// CTAs on the two SMs of a TPC execute ONE tcgen05.mma of M = 256: each loads its own 128 rows of A and only HALF
+// of the B tile, the tensor cores of both SMs read both halves — B traffic per SM halves, a stage shrinks from 96 to
+// 64 KB (three stages instead of two at BLOCK_N = 256).  Roles: warp 0 of BOTH CTAs is a TMA producer (its A rows,
+// its B half; completion bytes are counted on the LEADER's full barrier, which expects two producer arrivals),
+// warp 1 of the leader issues the MMAs and commits to the stage-empty / accumulator-full barriers of both CTAs
+// (multicast commit), warps 2-5 of both CTAs drain their own 128 accumulator rows from their own TMEM and release
+// the accumulator stage on the leader's barrier (8 arrivals).
+template <int PARTS, int BN> struct StageCount2 {
+  static constexpr int value = PARTS == 2 ? (BN == 256 ? 3 : 4) : 4;
+};
+
+template <int PARTS, int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16x3_2sm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                       const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                       const __grid_constant__ CUtensorMap map_c /* C, or the [split_k][M][N] partials */,
+                       int64_t M, int64_t N, int64_t K, int m_pairs, int n_tiles, int split_k, int kb_per_split,
+                       const float* __restrict__ bias, int a_mn, int b_mn, int accumulate) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  constexpr int kStages = StageCount2<PARTS, BLOCK_N>::value;
+  constexpr int kAccStages = kTmemCols / BLOCK_N;
+  constexpr int HALF_N = BLOCK_N / 2;
+  constexpr uint32_t B_HALF_BYTES = HALF_N * BLOCK_K * 2;   // this CTA's half of B: 8 / 16 KB per part per k-block
+  constexpr uint32_t kInstrDesc = instr_desc_bf16(2 * BLOCK_M, BLOCK_N);
+  constexpr uint32_t STAGE_BYTES = PARTS * (TILE_BYTES + B_HALF_BYTES);
+  uint8_t* smem_cd = smem + kStages * STAGE_BYTES;
+  GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(smem_cd + CD_BYTES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();          // 0 = leader
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int total_kb = (int)((K + BLOCK_K - 1) / BLOCK_K);
+  const int64_t total_units = (int64_t)m_pairs * n_tiles * split_k;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 4; ++s) { mbar_init(&bars->full[s], 2); mbar_init(&bars->empty[s], 1); }
+    for (int s = 0; s < 4; ++s) { mbar_init(&bars->acc_full[s], 1); mbar_init(&bars->acc_empty[s], 2 * kEpiWarps); }
+    fence_barrier_init();
+    tma_prefetch_desc(&map_a_hi);
+    tma_prefetch_desc(&map_b_hi);
+    tma_prefetch_desc(&map_c);
+    if (PARTS == 2) { tma_prefetch_desc(&map_a_lo); tma_prefetch_desc(&map_b_lo); }
+  }
+  if (warp == 1) tmem_alloc_2sm(&bars->tmem_base, kTmemCols);
+  tc_fence_before();
+  cluster_sync_all();        // both CTAs' barriers are initialised before anything crosses the pair
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  auto decode = [&](int64_t u, int& ks, int& mp, int& nt) {
+    nt = (int)(u % n_tiles);
+    mp = (int)((u / n_tiles) % m_pairs);
+    ks = (int)(u / ((int64_t)n_tiles * m_pairs));
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t u = pair; u < total_units; u += num_pairs) {
+        int ks, mp, nt;
+        decode(u, ks, mp, nt);
+        const int kb0 = ks * kb_per_split;
+        const int kb1 = kb0 + kb_per_split < total_kb ? kb0 + kb_per_split : total_kb;
+        const int m0 = (2 * mp + (int)rank) * BLOCK_M;           // this CTA's rows of A / C
+        const int n0 = nt * BLOCK_N + (int)rank * HALF_N;        // this CTA's half of the B tile
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&bars->empty[stage], phase ^ 1);
+          const uint32_t full = mapa_shared(smem_u32(&bars->full[stage]), 0);   // the leader's barrier
+          mbar_arrive_expect_tx_cluster(full, STAGE_BYTES);
+          uint8_t* st = smem + stage * STAGE_BYTES;
+          auto load = [&](const CUtensorMap* map, uint8_t* dst, int mn0, int mn_major, int rows) {
+            if (mn_major) {
+              for (int b = 0; b < rows / 64; ++b)
+                tma_load_2d_2sm(map, full, dst + b * MN_BOX_BYTES, mn0 + 64 * b, kb * BLOCK_K);
+            } else {
+              tma_load_2d_2sm(map, full, dst, kb * BLOCK_K, mn0);
+            }
+          };
+          load(&map_a_hi, st, m0, a_mn, BLOCK_M);
+          if (PARTS == 2) load(&map_a_lo, st + TILE_BYTES, m0, a_mn, BLOCK_M);
+          load(&map_b_hi, st + PARTS * TILE_BYTES, n0, b_mn, HALF_N);
+          if (PARTS == 2) load(&map_b_lo, st + PARTS * TILE_BYTES + B_HALF_BYTES, n0, b_mn, HALF_N);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int t = 0;
+      const uint32_t idesc = kInstrDesc | (a_mn ? 1u << 15 : 0u) | (b_mn ? 1u << 16 : 0u);
+      for (int64_t u = pair; u < total_units; u += num_pairs, ++t) {
+        int ks, mp, nt;
+        decode(u, ks, mp, nt);
+        const int kb0 = ks * kb_per_split;
+        const int kb1 = kb0 + kb_per_split < total_kb ? kb0 + kb_per_split : total_kb;
+        const int acc = t % kAccStages;
+        mbar_wait(&bars->acc_empty[acc], ((uint32_t)(t / kAccStages) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&bars->full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t a_lo = a_hi + TILE_BYTES;
+          const uint32_t b_hi = a_hi + PARTS * TILE_BYTES;
+          const uint32_t b_lo = b_hi + B_HALF_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+            const uint32_t off_a = a_mn ? kk * UMMA_K * 128 : kk * UMMA_K * 2;
+            const uint32_t off_b = b_mn ? kk * UMMA_K * 128 : kk * UMMA_K * 2;
+            const uint32_t first = (kb == kb0 && kk == 0) ? 0u : 1u;
+            const uint64_t da_hi = a_mn ? make_desc_mn_sw128(a_hi + off_a, MN_BOX_BYTES) : make_desc_sw128(a_hi + off_a);
+            const uint64_t db_hi = b_mn ? make_desc_mn_sw128(b_hi + off_b, MN_BOX_BYTES) : make_desc_sw128(b_hi + off_b);
+            umma_bf16_2sm(tmem_d, da_hi, db_hi, idesc, first);
+            if (PARTS == 2) {
+              const uint64_t da_lo = a_mn ? make_desc_mn_sw128(a_lo + off_a, MN_BOX_BYTES) : make_desc_sw128(a_lo + off_a);
+              const uint64_t db_lo = b_mn ? make_desc_mn_sw128(b_lo + off_b, MN_BOX_BYTES) : make_desc_sw128(b_lo + off_b);
+              umma_bf16_2sm(tmem_d, da_hi, db_lo, idesc, 1u);
+              umma_bf16_2sm(tmem_d, da_lo, db_hi, idesc, 1u);
+            }
+          }
+          umma_commit_2sm(&bars->empty[stage]);      // the stage is free in BOTH CTAs
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(&bars->acc_full[acc]);       // both CTAs' epilogues may read their accumulator rows
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    uint8_t* my_cd = smem_cd + (warp - 2) * 2 * CD_BOX_BYTES;
+    const bool add_bias = bias != nullptr && split_k == 1;
+    int buf = 0;
+    int t = 0;
+    for (int64_t u = pair; u < total_units; u += num_pairs, ++t) {
+      int ks, mp, nt;
+      decode(u, ks, mp, nt);
+      const int acc = t % kAccStages;
+      mbar_wait(&bars->acc_full[acc], (uint32_t)(t / kAccStages) & 1);
+      tc_fence_after();
+      const int row0 = (2 * mp + (int)rank) * BLOCK_M + quarter * 32;
+      const int col0 = nt * BLOCK_N;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        float4 bv[8];
+        const bool bias_on = add_bias && (int64_t)col0 + c0 + 32 <= N;
+        if (bias_on) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bv[j] = ldg4(bias + col0 + c0 + 4 * j);
+        }
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + (uint32_t)c0, v);
+        if (c0 + 32 == BLOCK_N) {  // accumulator fully read: release the stage on the LEADER's barrier
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&bars->acc_empty[acc]), 0));
+        }
+        if ((int64_t)col0 + c0 >= N || row0 >= M) continue;  // whole chunk outside the matrix (warp-uniform)
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+        uint8_t* box = my_cd + buf * CD_BOX_BYTES + lane * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                 __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+          const int64_t col = (int64_t)col0 + c0 + 4 * j;
+          if (bias_on) o = add4(o, bv[j]);
+          else if (add_bias && col + 3 < N) o = add4(o, ldg4(bias + col));
+          *reinterpret_cast<float4*>(box + ((j ^ (lane & 7)) << 4)) = o;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (accumulate && split_k == 1) tma_reduce_add_3d(&map_c, my_cd + buf * CD_BOX_BYTES, col0 + c0, row0, 0);
+          else tma_store_3d(&map_c, my_cd + buf * CD_BOX_BYTES, col0 + c0, row0, split_k > 1 ? ks : 0);
+          tma_store_commit();
+        }
+        buf ^= 1;
+      }
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  cluster_sync_all();        // neither CTA's shared memory / TMEM goes away while the other still uses it
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, kTmemCols);
+  }
+}
+
 // C[m][n] = bias[n] + sum_s partial[s][m][n], s ascending: deterministic split-K reduction.
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ partial, int split_k, int64_t M, int64_t N,
@@ -321,26 +519,40 @@ colsum_reduce_kernel(const float* __restrict__ partial, int64_t parts, int64_t c
 
 struct GemmPlan {
   int m_tiles, n_tiles, split_k, kb_per_split, grid, block_n;
+  bool pairs;    // CTA pairs (cta_group::2): m_tiles then counts 256-row tiles, grid = 2 x pairs
 };
+
+bool use_cta_pairs() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* env = getenv("ETPGT_GEMM_2CTA");      // default on; 0 selects the single-CTA kernel (comparison)
+    mode = env != nullptr ? (atoi(env) != 0) : 1;
+  }
+  return mode == 1;
+}
 
 GemmPlan gemm_plan(int64_t M, int64_t N, int64_t K, int want_split) {
   GemmPlan p;
   // 128 x 256 tiles for the short-K forward projection and for split-K problems (the weight gradient);
   // 128 x 128 otherwise (see the note at the top); ETPGT_GEMM_BN=128|256 overrides for tuning
-  p.block_n = (N > 128 && (K <= 512 || want_split != 1)) ? 256 : 128;
+  p.pairs = use_cta_pairs();
+  // (CTA pairs: a stage is 64 KB at 256 columns, three fit, so the long-K dX GEMM takes the wide tile as well)
+  p.block_n = (N > 128 && (p.pairs || K <= 512 || want_split != 1)) ? 256 : 128;
   if (const char* forced = getenv("ETPGT_GEMM_BN")) {
     const int f = atoi(forced);
     if (f == 128 || f == 256) p.block_n = f;
   }
-  p.m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M);
+  const int tile_m = p.pairs ? 2 * BLOCK_M : BLOCK_M;
+  p.m_tiles = (int)((M + tile_m - 1) / tile_m);
   p.n_tiles = (int)((N + p.block_n - 1) / p.block_n);
   const int total_kb = (int)((K + BLOCK_K - 1) / BLOCK_K);
   int split = 1;
   if (want_split != 1) {
     // few output tiles and a long K: split K until about two waves of units exist
     const int64_t tiles = (int64_t)p.m_tiles * p.n_tiles;
-    if (tiles < kNumSMs && total_kb >= 16) {
-      split = (int)((2 * kNumSMs + tiles - 1) / tiles);
+    const int workers = p.pairs ? kNumSMs / 2 : kNumSMs;
+    if (tiles < workers && total_kb >= 16) {
+      split = (int)((2 * workers + tiles - 1) / tiles);
       if (split > total_kb / 8) split = total_kb / 8;
       if (split < 1) split = 1;
     }
@@ -349,6 +561,11 @@ GemmPlan gemm_plan(int64_t M, int64_t N, int64_t K, int want_split) {
   p.kb_per_split = (total_kb + split - 1) / split;
   p.split_k = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
   const int64_t units = (int64_t)p.m_tiles * p.n_tiles * p.split_k;
+  if (p.pairs) {
+    p.grid = 2 * (int)(units < kNumSMs / 2 ? units : kNumSMs / 2);
+    if (p.grid < 2) p.grid = 2;
+    return p;
+  }
   p.grid = (int)(units < kNumSMs ? units : kNumSMs);
   if (p.grid < 1) p.grid = 1;
   return p;
@@ -424,7 +641,8 @@ extern "C" int etpgt_gemm_bf16x3_ex(const void* a_hi, const void* a_lo, const vo
     return a_mn_major ? make_map_bf16(m, ptr_, K, M, lda, 64) : make_map_bf16(m, ptr_, M, K, lda, BLOCK_M);
   };
   auto map_b = [&](CUtensorMap* m, const void* ptr_) {
-    return b_mn_major ? make_map_bf16(m, ptr_, K, N, ldb, 64) : make_map_bf16(m, ptr_, N, K, ldb, p.block_n);
+    return b_mn_major ? make_map_bf16(m, ptr_, K, N, ldb, 64)
+                      : make_map_bf16(m, ptr_, N, K, ldb, p.pairs ? p.block_n / 2 : p.block_n);
   };
   bool ok = map_a(&ma_hi, a_hi) && map_b(&mb_hi, b_hi);
   if (a_lo != nullptr) ok = ok && map_a(&ma_lo, a_lo) && map_b(&mb_lo, b_lo);
@@ -451,10 +669,37 @@ extern "C" int etpgt_gemm_bf16x3_ex(const void* a_hi, const void* a_lo, const vo
                                                                        p.kb_per_split, bias, a_mn_major != 0,     \
                                                                        b_mn_major != 0, accumulate != 0);         \
   }
-  if (parts == 2 && p.block_n == 256) LAUNCH(2, 256)
+#define LAUNCH2(PARTS_, BN_)                                                                                      \
+  {                                                                                                               \
+    const size_t smem = 1024 + (size_t)StageCount2<PARTS_, BN_>::value * PARTS_ * (TILE_BYTES + BN_ / 2 * BLOCK_K * 2) + \
+                        CD_BYTES + sizeof(GemmBarriers) + 64;                                                     \
+    cudaFuncSetAttribute(gemm_bf16x3_2sm_kernel<PARTS_, BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    cudaLaunchConfig_t cfg = {};                                                                                  \
+    cfg.gridDim = dim3(p.grid);                                                                                   \
+    cfg.blockDim = dim3(kThreads);                                                                                \
+    cfg.dynamicSmemBytes = smem;                                                                                  \
+    cfg.stream = stream;                                                                                          \
+    cudaLaunchAttribute attr[1];                                                                                  \
+    attr[0].id = cudaLaunchAttributeClusterDimension;                                                             \
+    attr[0].val.clusterDim.x = 2;                                                                                 \
+    attr[0].val.clusterDim.y = 1;                                                                                 \
+    attr[0].val.clusterDim.z = 1;                                                                                 \
+    cfg.attrs = attr;                                                                                             \
+    cfg.numAttrs = 1;                                                                                             \
+    cudaLaunchKernelEx(&cfg, gemm_bf16x3_2sm_kernel<PARTS_, BN_>, ma_hi, ma_lo, mb_hi, mb_lo, mc, M, N, K,        \
+                       p.m_tiles, p.n_tiles, p.split_k, p.kb_per_split, bias, (int)(a_mn_major != 0),             \
+                       (int)(b_mn_major != 0), (int)(accumulate != 0));                                           \
+  }
+  if (p.pairs) {
+    if (parts == 2 && p.block_n == 256) LAUNCH2(2, 256)
+    else if (parts == 2) LAUNCH2(2, 128)
+    else if (p.block_n == 256) LAUNCH2(1, 256)
+    else LAUNCH2(1, 128)
+  } else if (parts == 2 && p.block_n == 256) LAUNCH(2, 256)
   else if (parts == 2) LAUNCH(2, 128)
   else if (p.block_n == 256) LAUNCH(1, 256)
   else LAUNCH(1, 128)
+#undef LAUNCH2
 #undef LAUNCH
   ETPGT_CHECK_LAUNCH("gemm_bf16x3");
   if (p.split_k > 1) {

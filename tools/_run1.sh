@@ -1,2 +1,4 @@
-timeout 900 python -m pytest tests/test_gpu_score_tc.py tests/test_gpu_step.py tests/test_gpu_peer.py tests/test_gpu_training.py -q 2>&1 | tail -n 15 > gpurun_out/r02t_gpu_tests.txt
-tail -n 6 gpurun_out/r02t_gpu_tests.txt
+ETPGT_GEMM_BN=256 timeout 120 python tools/exp_gemm.py > gpurun_out/r02w_gemm_bn256.txt 2>&1
+ETPGT_GEMM_BN=128 timeout 120 python tools/exp_gemm.py > gpurun_out/r02w_gemm_bn128.txt 2>&1
+timeout 120 python tools/exp_gemm.py > gpurun_out/r02w_gemm_default.txt 2>&1
+tail -n 2 gpurun_out/r02w_gemm_bn256.txt gpurun_out/r02w_gemm_bn128.txt gpurun_out/r02w_gemm_default.txt
