@@ -10,24 +10,46 @@
 //               accumulators double-buffered in the 512 TMEM columns
 //   warps 2-5   epilogue, one warp per TMEM lane quarter (lane = session row)
 //
-// Epilogue = "chunk dump".  Measured on B200: with an epilogue that only loads TMEM and takes
+// Epilogue = "piece dump".  Measured on B200: with an epilogue that only loads TMEM and takes
 // maxima the pipeline runs at 84 % of the cuBLAS bf16 peak; every form of per-item candidate
 // handling inside the loop (shared-memory k-lists: 3 %, pending buffers: 23 %, register lists with
 // warp-uniform scans: 30 %) was bound by SIMT divergence — the 32 rows of a warp accept candidates
 // at different columns, so each accepted item costs the whole warp an insert.  So the loop keeps,
-// per row, only the K best 32-column CHUNK MAXIMA in a register-resident sorting network (values
-// only, branch-free, all lanes in lockstep), and a lane whose chunk maximum beats its row's
-// threshold dumps that chunk's 32 raw scores (one full 128-byte line) to a per-(row, range) slot
-// buffer in HBM.  K chunk maxima >= thr prove K items >= thr, so thr is a valid lower bound of the
-// row's K-th best score and no chunk holding a top-K item is ever skipped (chunks arrive in
-// ascending id order and the test is a strict '>', so ties keep the lower id).  About
-// K*ln(chunks/K) ~ 100 chunks (12 KB) per row are dumped.
+// per row, only the K best 16-column PIECE MAXIMA in a register-resident sorting network (values
+// only, branch-free, all lanes in lockstep), and a lane whose piece maximum beats its row's
+// threshold dumps that piece's 16 raw scores (64 bytes) to a per-(row, range) slot buffer in HBM.
+// K piece maxima >= thr prove K items >= thr, so thr is a valid lower bound of the row's K-th best
+// score and no piece holding a top-K item is ever skipped (a warp sees its pieces in ascending id
+// order and the test is a strict '>', so ties keep the lower id).
+//
+// At K = 256 an accumulator element receives only 16 MMAs: a 128 x 256 tile is produced in ~2,000
+// cycles, while ONE warp per TMEM lane quarter needed ~4,100 (round 1: ~790 instructions per tile
+// at ~5 cycles each — a single warp per scheduler cannot hide its own latencies).  So TWO warps
+// work on every lane quarter, columns 0-127 / 128-255 of each tile, each with its own sorted list,
+// threshold and pending buffer; they fill the row's slot buffer from both ends (no shared counter)
+// and read each other's threshold through shared memory (a piece must also reach the OTHER warp's
+// threshold — '>=' there, because that warp's pieces may have higher ids).  About 200-250 pieces
+// (14 KB) per row are dumped.  (A variant with the lists kept by separate merge warps in shared
+// memory was measured and dropped: whenever the merge fell behind, the thresholds went stale, more
+// pieces qualified and the merge fell further behind — 630-1,700 pieces per row.)
+//
+// CTA pairs (default): two CTAs on the two SMs of a TPC execute ONE tcgen05.mma of M = 256 (cta_group::2).  Each
+// keeps its own 128 session rows resident and loads only HALF of every item k-block (128 of the 256 item rows);
+// the tensor cores of both SMs read both halves, so the L2 -> shared-memory traffic per SM — 62 B/clk at the full
+// MMA rate against ~43 B/clk per SM that the L2 sustains chip-wide — halves, and a stage shrinks to 16 KB (six
+// stages).  The leader (cluster rank 0) issues the MMAs and commits to the barriers of both CTAs; each CTA's four
+// epilogue warps drain their own 128 accumulator rows.  The epilogue keeps one tcgen05.ld in flight while it works
+// on the previous 32 columns (at K = 256 an accumulator element receives only 16 MMAs, so the epilogue has ~2,000
+// cycles per 128 x 256 tile and a serial load -> wait -> compare chain does not fit in them).
 //
 // Select kernel (one warp per row): filters the dumped scores against the best range threshold and
 // picks the exact top-k by (score desc, id asc).  Rows whose slot buffer overflowed (adversarial
 // score orders) are recomputed exactly by a CUDA-core fallback kernel, so the result is always exact.
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
+
+#include <vector>
 
 #include "tc_common.cuh"
 
@@ -40,17 +62,16 @@ constexpr int BLOCK_M = 128;   // sessions per CTA (TMEM lanes)
 constexpr int BLOCK_N = 256;   // items per accumulator tile (TMEM columns)
 constexpr int CHUNK = 32;      // columns per tcgen05.ld
 constexpr int DUMPW = 16;      // columns per dumped piece (64 bytes)
-constexpr int kMaxStages = 3;  // ring of item k-blocks
+constexpr int kMaxStages = 6;  // ring of item k-blocks (3 of 32 KB per CTA, 6 of 16 KB per CTA of a pair)
 constexpr int kAccStages = 2;  // TMEM accumulator double buffer
 constexpr int kTmemCols = 512;
-constexpr int kEpilogueWarps = 4;
+constexpr int kEpilogueWarps = 8;   // two per TMEM lane quarter
 constexpr int kThreads = 32 * (2 + kEpilogueWarps);
 constexpr int kMaxKTc = 32;
 constexpr int kPendingMerge = 10;  // capacity: maxima a row may have waiting (merge threshold - 1 + pieces per chunk)
 constexpr int kDefaultPendingMerge = 8;
 constexpr uint32_t A_KBLOCK_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
-constexpr uint32_t B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;   // 32 KB
-constexpr uint32_t kInstrDesc = instr_desc_bf16(BLOCK_M, BLOCK_N);
+constexpr uint32_t B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;   // 32 KB (a pair: 16 KB in each CTA)
 
 struct __align__(8) Barriers {
   uint64_t a_full;
@@ -61,13 +82,20 @@ struct __align__(8) Barriers {
   uint32_t tmem_base;
 };
 
+// Shared-memory scratch of the epilogue warps.
+struct RowShared {
+  float pending[kEpilogueWarps][kPendingMerge][32];  // piece maxima waiting for the warp's lockstep merge
+  float thr[2][BLOCK_M];                             // [column half][row]: that warp's current threshold
+};
+
 // Dump buffers, per (row, range): `cap` slots of 32 scores + the chunk's first column (relative to the
 // range), a slot count (may exceed cap = overflow) and the range's final threshold.
 struct DumpBuffers {
-  float* scores;      // [rows*splits][cap][32]
+  float* scores;      // [rows*splits][cap][DUMPW]
   int32_t* chunk_col; // [rows*splits][cap]
-  int32_t* count;     // [rows*splits]
-  float* threshold;   // [rows*splits]
+  int32_t* count;     // [2][rows*splits]: slots filled from the bottom (columns 0-127 of the tiles) / from the top
+  float* threshold;   // [2][rows*splits]: final threshold of either column half
+  int64_t units;      // rows*splits
   int cap;
 };
 
@@ -76,11 +104,12 @@ struct DumpBuffers {
 // So the first `m_full` row tiles (whole waves) each scan the WHOLE catalogue as one unit, and only
 // the remaining row tiles are cut into `tail_splits` item ranges to fill the last wave.
 struct Schedule {
-  int m_full;           // row tiles with a single full-catalogue unit (a multiple of 148, may be 0)
+  int m_full;           // row tiles with a single full-catalogue unit (a multiple of the worker count, may be 0)
   int tail_splits;      // item ranges per remaining row tile
   int tiles_per_split;  // 256-item tiles per tail range
   int total_tiles;
-  __host__ __device__ int64_t full_rows() const { return (int64_t)m_full * BLOCK_M; }
+  int unit_rows;        // rows of a row tile: 128 (one CTA) or 256 (a CTA pair)
+  __host__ __device__ int64_t full_rows() const { return (int64_t)m_full * unit_rows; }
   __host__ __device__ int parts_of_row(int64_t row) const { return row < full_rows() ? 1 : tail_splits; }
   // index of (row, part) in the count / threshold arrays; x cap in the slot arrays
   __host__ __device__ int64_t part_index(int64_t row, int part) const {
@@ -93,68 +122,184 @@ struct Schedule {
   }
 };
 
-template <int NUM_KB, int KCAP>  // DIM / 64, number of chunk maxima tracked (>= k)
+__device__ __forceinline__ float ld_shared_volatile_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+// Per-row state of the piece-dump epilogue (one thread = one session row = one TMEM lane, one column half).
+template <int KCAP>
+struct RowState {
+  float best[KCAP];   // the KCAP largest piece maxima of this row (this half) so far, descending
+  float thr;          // = best[KCAP - 1] as of the last merge: a lower bound of the row's K-th best score
+  int count, pending;
+};
+
+// One 32-column chunk of a row: piece maxima, dump of the pieces that beat the thresholds, lockstep merge.
+//   slot_first / slot_step: this warp fills the slot buffer upwards from 0 or downwards from cap - 1
+// (One copy of this code per kernel: the hot loop has to stay inside the instruction cache — with four inlined
+// copies ncu showed 1.8 "no instruction" stall cycles per issued instruction.)
+template <int KCAP>
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&raw)[CHUNK], RowState<KCAP>& st, int col,
+                                               int limit_rel /* real columns left from this chunk on */,
+                                               float* my_scores, int32_t* my_cols, int cap, int slot_first,
+                                               int slot_step, uint32_t my_pending, uint32_t thr_own_addr,
+                                               float thr_other /* a little stale at worst: still a valid bound */,
+                                               int pending_merge) {
+  float v[CHUNK];
+#pragma unroll
+  for (int j = 0; j < CHUNK; ++j) v[j] = __uint_as_float(raw[j]);
+  if (limit_rel < CHUNK) {  // only the table's last tile: columns past the end never qualify
+#pragma unroll
+    for (int j = 0; j < CHUNK; ++j) v[j] = j < limit_rel ? v[j] : -INFINITY;
+  }
+  float g[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) g[q] = fmaxf(fmaxf(v[4 * q], v[4 * q + 1]), fmaxf(v[4 * q + 2], v[4 * q + 3]));
+  // dump granularity = DUMPW (16) columns: one 64-byte piece per hit instead of the whole 128-byte
+  // chunk — a third less dump traffic and half the store instructions on the divergent path
+  float mx[CHUNK / DUMPW];
+  bool hit[CHUNK / DUMPW];
+  bool any_hit = false;
+#pragma unroll
+  for (int h = 0; h < CHUNK / DUMPW; ++h) {
+    mx[h] = fmaxf(fmaxf(g[4 * h], g[4 * h + 1]), fmaxf(g[4 * h + 2], g[4 * h + 3]));
+    hit[h] = mx[h] > st.thr && mx[h] >= thr_other;   // rows past the batch carry thr = +inf
+    any_hit = any_hit || hit[h];
+  }
+  if (!__any_sync(0xffffffffu, any_hit)) return;  // warp-uniform
+#pragma unroll
+  for (int h = 0; h < CHUNK / DUMPW; ++h) {
+    if (hit[h]) {
+      const int n = st.count++;
+      st_shared_f32(my_pending + st.pending * 32 * sizeof(float), mx[h]);  // waits for the lockstep merge
+      ++st.pending;
+      if (n < cap) {
+        const int slot = slot_first + slot_step * n;
+        my_cols[slot] = col + h * DUMPW;
+        float4* dst = reinterpret_cast<float4*>(my_scores + (int64_t)slot * DUMPW);
+#pragma unroll
+        for (int q = 0; q < DUMPW / 4; ++q) {
+          const int j = h * DUMPW + 4 * q;
+          __stcs(dst + q, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+        }
+      }
+    }
+  }
+  // Merge the pending piece maxima of all 32 rows into the sorted lists TOGETHER: one pass of
+  // the sorting network then serves up to 32 rows at once (run per hit it would serve ~1).  The
+  // threshold is a little stale in between, which only dumps a few extra pieces.
+  if (__any_sync(0xffffffffu, st.pending >= pending_merge)) {
+    int most = st.pending;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) most = max(most, __shfl_xor_sync(0xffffffffu, most, off));
+#pragma unroll 1
+    for (int p = 0; p < most; ++p) {
+      float x = p < st.pending ? ld_shared_f32(my_pending + p * 32 * sizeof(float)) : -INFINITY;  // -inf: no-op
+#pragma unroll
+      for (int s = 0; s < KCAP; ++s) {
+        const float hi = fmaxf(st.best[s], x);
+        x = fminf(st.best[s], x);
+        st.best[s] = hi;
+      }
+    }
+    st.pending = 0;
+    st.thr = st.best[KCAP - 1];
+    st_shared_f32(thr_own_addr, st.thr);
+  }
+}
+
+template <int NUM_KB, int KCAP, bool PAIR>  // DIM / 64, piece maxima tracked per row and half (>= k), CTA pairs
 __global__ void __launch_bounds__(kThreads, 1)
 score_dump_tc_kernel(const __grid_constant__ CUtensorMap map_sess, const __grid_constant__ CUtensorMap map_items,
                      int64_t batch, int64_t num_items, int stages, Schedule sch, DumpBuffers dump,
                      int pending_merge /* <= kPendingMerge */) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  constexpr int LOAD_N = PAIR ? BLOCK_N / 2 : BLOCK_N;          // item rows this CTA loads per k-block
+  constexpr uint32_t STAGE_BYTES = LOAD_N * BLOCK_K * 2;
+  constexpr uint32_t kInstrDesc = instr_desc_bf16(PAIR ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
   uint8_t* smem_a = smem;                                   // NUM_KB x 16 KB
-  uint8_t* smem_b = smem_a + NUM_KB * A_KBLOCK_BYTES;       // stages x 32 KB
-  float* pend_max = reinterpret_cast<float*>(smem_b + stages * B_STAGE_BYTES);  // [kPendingMerge][128]
-  Barriers* bars = reinterpret_cast<Barriers*>(pend_max + kPendingMerge * BLOCK_M);
+  uint8_t* smem_b = smem_a + NUM_KB * A_KBLOCK_BYTES;       // stages x STAGE_BYTES
+  RowShared* rs = reinterpret_cast<RowShared*>(smem_b + stages * STAGE_BYTES);
+  Barriers* bars = reinterpret_cast<Barriers*>(rs + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  int m_tile, part;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0;       // 0 = the pair's leader
+  const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  int m_unit, part;
   int64_t tile_begin, tile_end;
-  if ((int)blockIdx.x < sch.m_full) {
-    m_tile = blockIdx.x; part = 0; tile_begin = 0; tile_end = sch.total_tiles;
+  if (unit < sch.m_full) {
+    m_unit = unit; part = 0; tile_begin = 0; tile_end = sch.total_tiles;
   } else {
-    const int v = blockIdx.x - sch.m_full;
-    m_tile = sch.m_full + v / sch.tail_splits;
+    const int v = unit - sch.m_full;
+    m_unit = sch.m_full + v / sch.tail_splits;
     part = v % sch.tail_splits;
     tile_begin = (int64_t)part * sch.tiles_per_split;
     tile_end = tile_begin + sch.tiles_per_split < sch.total_tiles ? tile_begin + sch.tiles_per_split : sch.total_tiles;
   }
+  const int m_tile = PAIR ? 2 * m_unit + (int)rank : m_unit;   // this CTA's 128 session rows
   const int num_tiles = tile_end > tile_begin ? (int)(tile_end - tile_begin) : 0;
 
   if (threadIdx.x == 0) {
-    mbar_init(&bars->a_full, 1);
-    for (int s = 0; s < kMaxStages; ++s) { mbar_init(&bars->b_full[s], 1); mbar_init(&bars->b_empty[s], 1); }
-    for (int s = 0; s < kAccStages; ++s) { mbar_init(&bars->acc_full[s], 1); mbar_init(&bars->acc_empty[s], kEpilogueWarps); }
+    // barriers that gate the MMAs count the producers of BOTH CTAs and live in the leader
+    mbar_init(&bars->a_full, PAIR ? 2 : 1);
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(&bars->b_full[s], PAIR ? 2 : 1); mbar_init(&bars->b_empty[s], 1); }
+    for (int s = 0; s < kAccStages; ++s) {
+      mbar_init(&bars->acc_full[s], 1);
+      mbar_init(&bars->acc_empty[s], PAIR ? 2 * kEpilogueWarps : kEpilogueWarps);
+    }
     fence_barrier_init();
     tma_prefetch_desc(&map_sess);
     tma_prefetch_desc(&map_items);
   }
-  if (warp == 1) tmem_alloc(&bars->tmem_base, kTmemCols);
+  for (int i = threadIdx.x; i < 2 * BLOCK_M; i += kThreads) (&rs->thr[0][0])[i] = -INFINITY;
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_2sm(&bars->tmem_base, kTmemCols);
+    else tmem_alloc(&bars->tmem_base, kTmemCols);
+  }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // both CTAs' barriers are initialised before anything crosses the pair
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
   if (warp == 0) {
-    // ===================== TMA producer (one elected lane) =====================
+    // ===================== TMA producer (one elected lane; in a pair: of each CTA) =====================
     if (lane == 0 && num_tiles > 0) {
-      mbar_expect_tx(&bars->a_full, NUM_KB * A_KBLOCK_BYTES);
-      for (int kb = 0; kb < NUM_KB; ++kb)
-        tma_load_2d(&map_sess, &bars->a_full, smem_a + kb * A_KBLOCK_BYTES, kb * BLOCK_K, m_tile * BLOCK_M);
+      if (PAIR) {
+        const uint32_t a_full = mapa_shared(smem_u32(&bars->a_full), 0);
+        mbar_arrive_expect_tx_cluster(a_full, NUM_KB * A_KBLOCK_BYTES);
+        for (int kb = 0; kb < NUM_KB; ++kb)
+          tma_load_2d_2sm(&map_sess, a_full, smem_a + kb * A_KBLOCK_BYTES, kb * BLOCK_K, m_tile * BLOCK_M);
+      } else {
+        mbar_expect_tx(&bars->a_full, NUM_KB * A_KBLOCK_BYTES);
+        for (int kb = 0; kb < NUM_KB; ++kb)
+          tma_load_2d(&map_sess, &bars->a_full, smem_a + kb * A_KBLOCK_BYTES, kb * BLOCK_K, m_tile * BLOCK_M);
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (int t = 0; t < num_tiles; ++t) {
-        const int row0 = (int)((tile_begin + t) * BLOCK_N);
+        const int row0 = (int)((tile_begin + t) * BLOCK_N) + (int)rank * LOAD_N;   // a pair: this CTA's half
         for (int kb = 0; kb < NUM_KB; ++kb) {
           mbar_wait(&bars->b_empty[stage], phase ^ 1);
-          mbar_expect_tx(&bars->b_full[stage], B_STAGE_BYTES);
-          tma_load_2d(&map_items, &bars->b_full[stage], smem_b + stage * B_STAGE_BYTES, kb * BLOCK_K, row0);
+          if (PAIR) {
+            const uint32_t full = mapa_shared(smem_u32(&bars->b_full[stage]), 0);
+            mbar_arrive_expect_tx_cluster(full, STAGE_BYTES);
+            tma_load_2d_2sm(&map_items, full, smem_b + stage * STAGE_BYTES, kb * BLOCK_K, row0);
+          } else {
+            mbar_expect_tx(&bars->b_full[stage], STAGE_BYTES);
+            tma_load_2d(&map_items, &bars->b_full[stage], smem_b + stage * STAGE_BYTES, kb * BLOCK_K, row0);
+          }
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one elected lane) =====================
-    if (lane == 0 && num_tiles > 0) {
+    // ===================== MMA issuer (one elected lane; in a pair: of the leader) =====================
+    if (lane == 0 && rank == 0 && num_tiles > 0) {
       mbar_wait(&bars->a_full, 0);
       tc_fence_after();
       int stage = 0;
@@ -169,22 +314,28 @@ score_dump_tc_kernel(const __grid_constant__ CUtensorMap map_sess, const __grid_
           mbar_wait(&bars->b_full[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem_a + kb * A_KBLOCK_BYTES);
-          const uint32_t b_addr = smem_u32(smem_b + stage * B_STAGE_BYTES);
+          const uint32_t b_addr = smem_u32(smem_b + stage * STAGE_BYTES);
 #pragma unroll
           for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
             const uint64_t da = make_desc_sw128(a_addr + kk * UMMA_K * 2);
             const uint64_t db = make_desc_sw128(b_addr + kk * UMMA_K * 2);
-            umma_bf16(tmem_d, da, db, kInstrDesc, (kb | kk) != 0 ? 1u : 0u);
+            if (PAIR) umma_bf16_2sm(tmem_d, da, db, kInstrDesc, (kb | kk) != 0 ? 1u : 0u);
+            else umma_bf16(tmem_d, da, db, kInstrDesc, (kb | kk) != 0 ? 1u : 0u);
           }
-          umma_commit(&bars->b_empty[stage]);  // frees the smem stage once these MMAs have read it
+          // frees the smem stage (in both CTAs) once these MMAs have read it
+          if (PAIR) umma_commit_2sm(&bars->b_empty[stage]);
+          else umma_commit(&bars->b_empty[stage]);
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&bars->acc_full[acc]);     // accumulator tile complete
+        // accumulator tile complete (each CTA's epilogue reads its own 128 rows from its own TMEM)
+        if (PAIR) umma_commit_2sm(&bars->acc_full[acc]);
+        else umma_commit(&bars->acc_full[acc]);
       }
     }
   } else {
-    // ===================== epilogue: 4 warps, TMEM lane quarter = warp % 4 =====================
+    // ========== epilogue: 8 warps; TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 ==========
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;       // session row inside the tile == TMEM lane
     const int64_t grow = (int64_t)m_tile * BLOCK_M + row;
     const bool live = grow < batch;
@@ -192,100 +343,60 @@ score_dump_tc_kernel(const __grid_constant__ CUtensorMap map_sess, const __grid_
     const int64_t slot0 = pidx * (int64_t)dump.cap;
     float* my_scores = dump.scores + slot0 * DUMPW;
     int32_t* my_cols = dump.chunk_col + slot0;
-    float best[KCAP];   // the KCAP largest chunk maxima of this row so far, descending
+    RowState<KCAP> st;
 #pragma unroll
-    for (int t = 0; t < KCAP; ++t) best[t] = -INFINITY;
-    float thr = -INFINITY;
-    int count = 0, pending = 0;
-    const uint32_t my_pending = smem_u32(pend_max + row);  // [kPendingMerge][128], row fastest (shared-space address)
+    for (int t = 0; t < KCAP; ++t) st.best[t] = live ? -INFINITY : INFINITY;   // rows past the batch never qualify
+    st.thr = st.best[KCAP - 1];
+    st.count = 0;
+    st.pending = 0;
+    const uint32_t my_pending = smem_u32(&rs->pending[warp - 2][0][lane]);
+    const uint32_t thr_own_addr = smem_u32(&rs->thr[half][row]), thr_other_addr = smem_u32(&rs->thr[half ^ 1][row]);
+    const uint32_t acc_empty0 = PAIR ? mapa_shared(smem_u32(&bars->acc_empty[0]), 0) : smem_u32(&bars->acc_empty[0]);
+    constexpr int HALF_N = BLOCK_N / 2;
+    // loop constants pinned in registers (as kernel parameters they were re-read from the constant bank on the
+    // divergent path: ~2 % of the epilogue's stall samples)
+    int cap = dump.cap, merge_at = pending_merge;
+    int slot_first = half ? dump.cap - 1 : 0, slot_step = half ? -1 : 1;
+    asm volatile("" : "+r"(cap), "+r"(merge_at), "+r"(slot_first), "+r"(slot_step));
     for (int t = 0; t < num_tiles; ++t) {
       const int acc = t & 1;
       const uint32_t acc_phase = (uint32_t)(t >> 1) & 1;
       mbar_wait(&bars->acc_full[acc], acc_phase);
       tc_fence_after();
-      const int64_t item0 = (tile_begin + t) * BLOCK_N;
-      const int limit = num_items - item0 < BLOCK_N ? (int)(num_items - item0) : BLOCK_N;  // real columns
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+      const int64_t item0 = (tile_begin + t) * BLOCK_N + half * HALF_N;
+      const int limit = num_items - item0 < HALF_N ? (int)(num_items - item0) : HALF_N;  // real columns of this half
+      const int col0 = t * BLOCK_N + half * HALF_N;
+      const uint32_t taddr =
+          tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + half * HALF_N);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += CHUNK) {
-        float v[CHUNK];
-        {
-          uint32_t raw[CHUNK];
-          tmem_ld_32x32(taddr + (uint32_t)c0, raw);
-#pragma unroll
-          for (int j = 0; j < CHUNK; ++j) v[j] = __uint_as_float(raw[j]);
-        }
-        if (limit - c0 < CHUNK) {  // only the table's last tile: columns past the end never qualify
-#pragma unroll
-          for (int j = 0; j < CHUNK; ++j) v[j] = c0 + j < limit ? v[j] : -INFINITY;
-        }
-        float g[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) g[q] = fmaxf(fmaxf(v[4 * q], v[4 * q + 1]), fmaxf(v[4 * q + 2], v[4 * q + 3]));
-        // dump granularity = DUMPW (16) columns: one 64-byte piece per hit instead of the whole 128-byte
-        // chunk — a third less dump traffic and half the store instructions on the divergent path
-        float mx[CHUNK / DUMPW];
-        bool hit[CHUNK / DUMPW];
-        bool any_hit = false;
-#pragma unroll
-        for (int h = 0; h < CHUNK / DUMPW; ++h) {
-          mx[h] = fmaxf(fmaxf(g[4 * h], g[4 * h + 1]), fmaxf(g[4 * h + 2], g[4 * h + 3]));
-          hit[h] = live && mx[h] > thr;
-          any_hit = any_hit || hit[h];
-        }
-        if (__any_sync(0xffffffffu, any_hit)) {  // warp-uniform
-#pragma unroll
-          for (int h = 0; h < CHUNK / DUMPW; ++h) {
-            if (hit[h]) {
-              const int slot = count++;
-              st_shared_f32(my_pending + pending * BLOCK_M * sizeof(float), mx[h]);  // waits for the lockstep merge
-              ++pending;
-              if (slot < dump.cap) {
-                my_cols[slot] = t * BLOCK_N + c0 + h * DUMPW;
-                float4* dst = reinterpret_cast<float4*>(my_scores + (int64_t)slot * DUMPW);
-#pragma unroll
-                for (int q = 0; q < DUMPW / 4; ++q) {
-                  const int j = h * DUMPW + 4 * q;
-                  __stcs(dst + q, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-                }
-              }
-            }
-          }
-          // Merge the pending chunk maxima of all 32 rows into the sorted lists TOGETHER: one pass of
-          // the sorting network then serves up to 32 rows at once (run per hit it would serve ~1).  The
-          // threshold is a little stale in between, which only dumps a few extra chunks.
-          if (__any_sync(0xffffffffu, pending >= pending_merge)) {
-            int most = pending;
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) most = max(most, __shfl_xor_sync(0xffffffffu, most, off));
-            for (int p = 0; p < most; ++p) {
-              float x = p < pending ? ld_shared_f32(my_pending + p * BLOCK_M * sizeof(float)) : -INFINITY;  // -inf: no-op
-#pragma unroll
-              for (int s = 0; s < KCAP; ++s) {
-                const float hi = fmaxf(best[s], x);
-                x = fminf(best[s], x);
-                best[s] = hi;
-              }
-            }
-            pending = 0;
-            thr = best[KCAP - 1];
+      for (int c0 = 0; c0 < HALF_N; c0 += CHUNK) {
+        const float thr_other = ld_shared_f32(thr_other_addr);   // in flight during the TMEM load
+        uint32_t raw[CHUNK];
+        tmem_ld_32x32(taddr + (uint32_t)c0, raw);
+        if (c0 + CHUNK == HALF_N) {   // this warp's columns are read: hand the accumulator back to the MMA issuer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (PAIR) mbar_arrive_cluster(acc_empty0 + (uint32_t)(acc * sizeof(uint64_t)));
+            else mbar_arrive(&bars->acc_empty[acc]);
           }
         }
+        epilogue_chunk<KCAP>(raw, st, col0 + c0, limit - c0, my_scores, my_cols, cap, slot_first, slot_step,
+                             my_pending, thr_own_addr, thr_other, merge_at);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
     }
     if (live) {
-      dump.count[pidx] = count;
-      dump.threshold[pidx] = thr;
+      dump.count[(int64_t)half * dump.units + pidx] = st.count;
+      dump.threshold[(int64_t)half * dump.units + pidx] = st.thr;
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // neither CTA's shared memory / TMEM goes away while the other still uses it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (PAIR) tmem_dealloc_2sm(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -327,14 +438,19 @@ score_select_kernel(DumpBuffers dump, int64_t batch, Schedule sch, int k, int64_
   bool overflow = false;
   const int splits = sch.parts_of_row(row);
   for (int s = 0; s < splits; ++s) {
-    tau = fmaxf(tau, dump.threshold[sch.part_index(row, s)]);
-    overflow = overflow || dump.count[sch.part_index(row, s)] > dump.cap;
+    const int64_t pi = sch.part_index(row, s);
+    tau = fmaxf(tau, fmaxf(dump.threshold[pi], dump.threshold[dump.units + pi]));
+    overflow = overflow || dump.count[pi] + dump.count[dump.units + pi] > dump.cap;
   }
   __syncwarp();
   if (!overflow) {
-    for (int s = 0; s < splits; ++s) {
-      const int n = dump.count[sch.part_index(row, s)];
-      const int64_t slot0 = sch.part_index(row, s) * (int64_t)dump.cap;
+    for (int seg = 0; seg < 2 * splits; ++seg) {
+      // a part's slot buffer was filled from both ends: pieces of columns 0-127 of every tile from the bottom,
+      // of columns 128-255 from the top
+      const int s = seg >> 1, top = seg & 1;
+      const int64_t pi = sch.part_index(row, s);
+      const int n = dump.count[top * dump.units + pi];
+      const int64_t slot0 = pi * (int64_t)dump.cap + (top ? dump.cap - n : 0);
       const int range_col0 = sch.first_tile(row, s) * BLOCK_N;
       // 128-bit loads: DUMPW/4 lanes cover one dumped piece, a warp load covers 128/DUMPW pieces, eight
       // independent loads in flight per lane (4 KB per warp and iteration)
@@ -535,17 +651,29 @@ struct TcPlan {
   Schedule sch;
   int grid;
   int cap;
+  bool pairs;   // CTA pairs (cta_group::2): a row tile is 256 rows, grid = 2 x units, workers = 74 SM pairs
 };
+
+bool use_cta_pairs() {
+  static const bool on = [] {
+    const char* e = getenv("ETPGT_SCORE_2CTA");   // comparison knob: 0 = one CTA per unit (round 1's kernel shape)
+    return e == nullptr || atoi(e) != 0;
+  }();
+  return on;
+}
 
 TcPlan tc_plan(int64_t batch, int64_t num_items, int k) {
   TcPlan p;
-  const int m_tiles = (int)((batch + BLOCK_M - 1) / BLOCK_M);
+  p.pairs = use_cta_pairs();
+  const int unit_rows = p.pairs ? 2 * BLOCK_M : BLOCK_M;
+  const int workers = p.pairs ? kNumSMs / 2 : kNumSMs;
+  const int m_tiles = (int)((batch + unit_rows - 1) / unit_rows);
   const int total_tiles = (int)((num_items + BLOCK_N - 1) / BLOCK_N);
   // tail ranges stay >= 64 tiles (512 chunks) so that every range's own threshold is tight enough for
   // the select kernel's survivor buffer
   int max_splits = total_tiles / 64 > 1 ? total_tiles / 64 : 1;
   if (max_splits > 32) max_splits = 32;
-  const int m_full = (m_tiles / kNumSMs) * kNumSMs;   // whole waves: one full-catalogue unit per row tile
+  const int m_full = (m_tiles / workers) * workers;   // whole waves: one full-catalogue unit per row tile
   const int tail = m_tiles - m_full;
   int splits = 1;
   if (tail > 0) {
@@ -554,7 +682,7 @@ TcPlan tc_plan(int64_t batch, int64_t num_items, int k) {
     for (int s = 1; s <= max_splits; ++s) {
       const int per = (total_tiles + s - 1) / s;
       const int real = (total_tiles + per - 1) / per;
-      const int waves = (real * tail + kNumSMs - 1) / kNumSMs;
+      const int waves = (real * tail + workers - 1) / workers;
       const double cost = (double)waves * ((double)per / (double)total_tiles + 0.5);
       if (cost < best_cost - 1e-9) { best_cost = cost; splits = s; }
     }
@@ -563,17 +691,19 @@ TcPlan tc_plan(int64_t batch, int64_t num_items, int k) {
       if (f >= 1 && f <= max_splits) splits = f;
     }
   }
+  p.sch.unit_rows = unit_rows;
   p.sch.m_full = m_full;
   p.sch.total_tiles = total_tiles;
   p.sch.tiles_per_split = (total_tiles + splits - 1) / splits;
   p.sch.tail_splits = (total_tiles + p.sch.tiles_per_split - 1) / p.sch.tiles_per_split;
-  p.grid = m_full + tail * p.sch.tail_splits;
-  // slots per (row, range): ~ K*(1 + ln(chunks/K)) chunks are expected; 1.6x head-room (sized for the
-  // longest range), overflow is handled exactly by the fallback kernel
+  p.grid = (m_full + tail * p.sch.tail_splits) * (p.pairs ? 2 : 1);
+  // slots per (row, range): either column half keeps its own list over half of the pieces, so
+  // ~ 2*K*(1 + ln(pieces/(2K))) pieces are expected (+ ~25 % from the lockstep merges); 1.6x head-room (sized
+  // for the longest range), overflow is handled exactly by the fallback kernel
   const double chunks = (double)(m_full > 0 ? total_tiles : p.sch.tiles_per_split) * (BLOCK_N / DUMPW);
   const int kc = k <= 10 ? 10 : k <= 20 ? 20 : 32;
-  double expect = kc * (1.0 + (chunks > kc ? log(chunks / kc) : 0.0));
-  int cap = (int)(1.6 * expect) + 8;
+  double expect = 2.0 * kc * (1.0 + (chunks > 2.0 * kc ? log(chunks / (2.0 * kc)) : 0.0));
+  int cap = (int)(1.6 * expect) + 16;
   if (cap > (int)chunks) cap = (int)chunks;
   if (const char* forced = getenv("ETPGT_SCORE_CAP")) {  // test hook: force slot-buffer overflow
     const int f = atoi(forced);
@@ -583,9 +713,9 @@ TcPlan tc_plan(int64_t batch, int64_t num_items, int k) {
   return p;
 }
 
-size_t tc_smem_bytes(int num_kb, int stages) {
-  return 1024 + (size_t)num_kb * A_KBLOCK_BYTES + (size_t)stages * B_STAGE_BYTES +
-         (size_t)kPendingMerge * BLOCK_M * sizeof(float) + sizeof(Barriers) + 64;
+size_t tc_smem_bytes(int num_kb, int stages, bool pairs) {
+  return 1024 + (size_t)num_kb * A_KBLOCK_BYTES + (size_t)stages * (pairs ? B_STAGE_BYTES / 2 : B_STAGE_BYTES) +
+         sizeof(RowShared) + sizeof(Barriers) + 64;
 }
 
 }  // namespace
@@ -607,7 +737,7 @@ extern "C" size_t etpgt_score_topk_bf16_workspace_bytes(int64_t batch, int64_t n
   const TcPlan p = tc_plan(batch, num_items, k);
   const size_t units = (size_t)p.sch.num_parts(batch);
   return align_up(units * p.cap * DUMPW * sizeof(float)) + align_up(units * p.cap * sizeof(int32_t)) +
-         2 * align_up(units * sizeof(float)) + 2 * align_up((size_t)batch * sizeof(int32_t)) + 256;
+         4 * align_up(units * sizeof(float)) + 2 * align_up((size_t)batch * sizeof(int32_t)) + 256;
 }
 
 extern "C" int etpgt_score_topk_bf16_eval(const void* sess_bf16, const void* table_bf16, int64_t batch,
@@ -634,36 +764,59 @@ extern "C" int etpgt_score_topk_bf16_eval(const void* sess_bf16, const void* tab
   DumpBuffers dump;
   dump.scores = w.take<float>(units * p.cap * DUMPW);
   dump.chunk_col = w.take<int32_t>(units * p.cap);
-  dump.count = w.take<int32_t>(units);
-  dump.threshold = w.take<float>(units);
+  dump.count = w.take<int32_t>(2 * units);
+  dump.threshold = w.take<float>(2 * units);
+  dump.units = (int64_t)units;
   dump.cap = p.cap;
   int32_t* redo = w.take<int32_t>(batch);
   CUtensorMap map_sess, map_items;
   if (!make_map_bf16(&map_sess, sess_bf16, batch, dim, dim, BLOCK_M) ||
-      !make_map_bf16(&map_items, table_bf16, num_items, dim, dim, BLOCK_N)) {
+      !make_map_bf16(&map_items, table_bf16, num_items, dim, dim, p.pairs ? BLOCK_N / 2 : BLOCK_N)) {
     set_error("score_topk_bf16: cuTensorMapEncodeTiled failed");
     return ETPGT_ECUDA;
   }
   const int num_kb = dim / BLOCK_K;
-  const int stages = kMaxStages;
+  const int stages = p.pairs ? kMaxStages : kMaxStages / 2;
   int pending_merge = kDefaultPendingMerge;
   if (const char* forced = getenv("ETPGT_SCORE_PENDING")) {  // tuning knob
     const int f = atoi(forced);
     if (f >= 1 && f <= kPendingMerge + 1 - CHUNK / DUMPW) pending_merge = f;
   }
-  const size_t smem = tc_smem_bytes(num_kb, stages);
-  const dim3 grid(p.grid);
-#define LAUNCH2(NKB, KC)                                                                                        \
-  {                                                                                                             \
-    cudaFuncSetAttribute(score_dump_tc_kernel<NKB, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    score_dump_tc_kernel<NKB, KC><<<grid, kThreads, smem, stream>>>(map_sess, map_items, batch, num_items, stages, \
-                                                                   p.sch, dump, pending_merge);                \
+  const size_t smem = tc_smem_bytes(num_kb, stages, p.pairs);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(p.grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = p.pairs ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+#define LAUNCH3(NKB, KC, PR)                                                                                          \
+  {                                                                                                                   \
+    cudaFuncSetAttribute(score_dump_tc_kernel<NKB, KC, PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    cudaLaunchKernelEx(&cfg, score_dump_tc_kernel<NKB, KC, PR>, map_sess, map_items, batch, num_items, stages, p.sch, \
+                       dump, pending_merge);                                                                          \
+  }
+#define LAUNCH2(NKB, KC)                  \
+  {                                       \
+    if (p.pairs) LAUNCH3(NKB, KC, true)   \
+    else LAUNCH3(NKB, KC, false)          \
   }
 #define LAUNCH(NKB)                    \
   {                                    \
     if (k <= 10) LAUNCH2(NKB, 10)      \
     else if (k <= 20) LAUNCH2(NKB, 20) \
     else LAUNCH2(NKB, 32)              \
+  }
+  const bool stats = getenv("ETPGT_SCORE_STATS") != nullptr;   // tuning aid (synchronises)
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  if (stats) {
+    for (auto& e : ev) cudaEventCreate(&e);
+    cudaEventRecord(ev[0], stream);
   }
   switch (num_kb) {
     case 1: LAUNCH(1) break;
@@ -673,10 +826,13 @@ extern "C" int etpgt_score_topk_bf16_eval(const void* sess_bf16, const void* tab
   }
 #undef LAUNCH
 #undef LAUNCH2
+#undef LAUNCH3
   ETPGT_CHECK_LAUNCH("score_dump_tc");
+  if (stats) cudaEventRecord(ev[1], stream);
   score_select_kernel<<<(unsigned)((batch + kSelectWarps - 1) / kSelectWarps), kSelectWarps * 32, 0, stream>>>(
       dump, batch, p.sch, k, id_base, top_val, top_idx, redo, targets, hit_pos);
   ETPGT_CHECK_LAUNCH("score_select");
+  if (stats) cudaEventRecord(ev[2], stream);
   const size_t redo_smem = ((size_t)dim + (size_t)kRedoThreads * k * 2) * sizeof(float);
   if (redo_smem > 48 * 1024)
     cudaFuncSetAttribute(score_redo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)redo_smem);
@@ -686,6 +842,26 @@ extern "C" int etpgt_score_topk_bf16_eval(const void* sess_bf16, const void* tab
       static_cast<const __nv_bfloat16*>(sess_bf16), static_cast<const __nv_bfloat16*>(table_bf16), batch, num_items,
       dim, k, id_base, redo, top_val, top_idx, targets, hit_pos);
   ETPGT_CHECK_LAUNCH("score_redo");
+  if (stats) {   // dump volume, fallback rows, kernel times
+    std::vector<int32_t> h_redo(batch), h_count(2 * units);
+    cudaStreamSynchronize(stream);
+    float ms_dump = 0.f, ms_select = 0.f;
+    cudaEventElapsedTime(&ms_dump, ev[0], ev[1]);
+    cudaEventElapsedTime(&ms_select, ev[1], ev[2]);
+    for (auto& e : ev) cudaEventDestroy(e);
+    fprintf(stderr, "score_topk_bf16: dump %.3f ms, select %.3f ms\n", ms_dump, ms_select);
+    cudaMemcpy(h_redo.data(), redo, batch * sizeof(int32_t), cudaMemcpyDeviceToHost);
+    cudaMemcpy(h_count.data(), dump.count, 2 * units * sizeof(int32_t), cudaMemcpyDeviceToHost);
+    int64_t redo_rows = 0, pieces = 0, worst = 0;
+    for (int64_t i = 0; i < batch; ++i) redo_rows += h_redo[i];
+    for (size_t i = 0; i < units; ++i) {
+      const int64_t c = (int64_t)h_count[i] + h_count[units + i];
+      pieces += c;
+      worst = c > worst ? c : worst;
+    }
+    fprintf(stderr, "score_topk_bf16: grid %d, %zu (row, range) units, cap %d, %.1f pieces per unit (max %lld), %lld rows recomputed\n",
+            p.grid, units, p.cap, (double)pieces / (double)units, (long long)worst, (long long)redo_rows);
+  }
   return ETPGT_OK;
 }
 
