@@ -68,7 +68,7 @@ constexpr int kTmemCols = 512;
 constexpr int kEpilogueWarps = 8;   // two per TMEM lane quarter
 constexpr int kThreads = 32 * (2 + kEpilogueWarps);
 constexpr int kMaxKTc = 32;
-constexpr int kPendingMerge = 10;  // capacity: maxima a row may have waiting (merge threshold - 1 + pieces per chunk)
+constexpr int kPendingMerge = 16;  // capacity: maxima a row may have waiting (merge threshold - 1 + pieces per tile half)
 constexpr int kDefaultPendingMerge = 8;
 constexpr uint32_t A_KBLOCK_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr uint32_t B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;   // 32 KB (a pair: 16 KB in each CTA)
@@ -92,7 +92,8 @@ struct RowShared {
 // range), a slot count (may exceed cap = overflow) and the range's final threshold.
 struct DumpBuffers {
   float* scores;      // [rows*splits][cap][DUMPW]
-  int32_t* chunk_col; // [rows*splits][cap]
+  int2* meta;         // [rows*splits][cap]: (first column of the piece relative to the range, bits of the piece's
+                      // maximum) — the select kernel reads these first
   int32_t* count;     // [2][rows*splits]: slots filled from the bottom (columns 0-127 of the tiles) / from the top
   float* threshold;   // [2][rows*splits]: final threshold of either column half
   int64_t units;      // rows*splits
@@ -136,17 +137,17 @@ struct RowState {
   int count, pending;
 };
 
-// One 32-column chunk of a row: piece maxima, dump of the pieces that beat the thresholds, lockstep merge.
+// One 32-column chunk of a row: piece maxima, dump of the pieces that beat the thresholds; their maxima wait in the
+// warp's pending buffer for the merge at the end of the tile.
 //   slot_first / slot_step: this warp fills the slot buffer upwards from 0 or downwards from cap - 1
-// (One copy of this code per kernel: the hot loop has to stay inside the instruction cache — with four inlined
-// copies ncu showed 1.8 "no instruction" stall cycles per issued instruction.)
+// (The hot loop has to stay inside the instruction cache: with four inlined copies of chunk + merge ncu showed 1.8
+// "no instruction" stall cycles per issued instruction; the merge exists once per kernel now.)
 template <int KCAP>
-__device__ __forceinline__ void epilogue_chunk(const uint32_t (&raw)[CHUNK], RowState<KCAP>& st, int col,
-                                               int limit_rel /* real columns left from this chunk on */,
-                                               float* my_scores, int32_t* my_cols, int cap, int slot_first,
-                                               int slot_step, uint32_t my_pending, uint32_t thr_own_addr,
-                                               float thr_other /* a little stale at worst: still a valid bound */,
-                                               int pending_merge) {
+__device__ __forceinline__ void chunk_hits(const uint32_t (&raw)[CHUNK], RowState<KCAP>& st, int col,
+                                           int limit_rel /* real columns left from this chunk on */,
+                                           float* my_scores, int2* my_meta, int cap, int slot_first, int slot_step,
+                                           uint32_t my_pending,
+                                           float thr_other /* a little stale at worst: still a valid bound */) {
   float v[CHUNK];
 #pragma unroll
   for (int j = 0; j < CHUNK; ++j) v[j] = __uint_as_float(raw[j]);
@@ -177,7 +178,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&raw)[CHUNK], Row
       ++st.pending;
       if (n < cap) {
         const int slot = slot_first + slot_step * n;
-        my_cols[slot] = col + h * DUMPW;
+        my_meta[slot] = make_int2(col + h * DUMPW, __float_as_int(mx[h]));
         float4* dst = reinterpret_cast<float4*>(my_scores + (int64_t)slot * DUMPW);
 #pragma unroll
         for (int q = 0; q < DUMPW / 4; ++q) {
@@ -187,27 +188,31 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&raw)[CHUNK], Row
       }
     }
   }
-  // Merge the pending piece maxima of all 32 rows into the sorted lists TOGETHER: one pass of
-  // the sorting network then serves up to 32 rows at once (run per hit it would serve ~1).  The
-  // threshold is a little stale in between, which only dumps a few extra pieces.
-  if (__any_sync(0xffffffffu, st.pending >= pending_merge)) {
-    int most = st.pending;
+}
+
+// Merge the pending piece maxima of all 32 rows into the sorted lists TOGETHER: one pass of the sorting network
+// then serves up to 32 rows at once (run per hit it would serve ~1).  The threshold is a little stale in between,
+// which only dumps a few extra pieces.
+template <int KCAP>
+__device__ __forceinline__ void merge_pending(RowState<KCAP>& st, uint32_t my_pending, uint32_t thr_own_addr,
+                                              int pending_merge) {
+  if (!__any_sync(0xffffffffu, st.pending >= pending_merge)) return;
+  int most = st.pending;
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) most = max(most, __shfl_xor_sync(0xffffffffu, most, off));
+  for (int off = 16; off > 0; off >>= 1) most = max(most, __shfl_xor_sync(0xffffffffu, most, off));
 #pragma unroll 1
-    for (int p = 0; p < most; ++p) {
-      float x = p < st.pending ? ld_shared_f32(my_pending + p * 32 * sizeof(float)) : -INFINITY;  // -inf: no-op
+  for (int p = 0; p < most; ++p) {
+    float x = p < st.pending ? ld_shared_f32(my_pending + p * 32 * sizeof(float)) : -INFINITY;  // -inf: no-op
 #pragma unroll
-      for (int s = 0; s < KCAP; ++s) {
-        const float hi = fmaxf(st.best[s], x);
-        x = fminf(st.best[s], x);
-        st.best[s] = hi;
-      }
+    for (int s = 0; s < KCAP; ++s) {
+      const float hi = fmaxf(st.best[s], x);
+      x = fminf(st.best[s], x);
+      st.best[s] = hi;
     }
-    st.pending = 0;
-    st.thr = st.best[KCAP - 1];
-    st_shared_f32(thr_own_addr, st.thr);
   }
+  st.pending = 0;
+  st.thr = st.best[KCAP - 1];
+  st_shared_f32(thr_own_addr, st.thr);
 }
 
 template <int NUM_KB, int KCAP, bool PAIR>  // DIM / 64, piece maxima tracked per row and half (>= k), CTA pairs
@@ -342,7 +347,7 @@ score_dump_tc_kernel(const __grid_constant__ CUtensorMap map_sess, const __grid_
     const int64_t pidx = live ? sch.part_index(grow, part) : 0;
     const int64_t slot0 = pidx * (int64_t)dump.cap;
     float* my_scores = dump.scores + slot0 * DUMPW;
-    int32_t* my_cols = dump.chunk_col + slot0;
+    int2* my_meta = dump.meta + slot0;
     RowState<KCAP> st;
 #pragma unroll
     for (int t = 0; t < KCAP; ++t) st.best[t] = live ? -INFINITY : INFINITY;   // rows past the batch never qualify
@@ -368,22 +373,30 @@ score_dump_tc_kernel(const __grid_constant__ CUtensorMap map_sess, const __grid_
       const int col0 = t * BLOCK_N + half * HALF_N;
       const uint32_t taddr =
           tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + half * HALF_N);
-#pragma unroll 1
-      for (int c0 = 0; c0 < HALF_N; c0 += CHUNK) {
-        const float thr_other = ld_shared_f32(thr_other_addr);   // in flight during the TMEM load
-        uint32_t raw[CHUNK];
-        tmem_ld_32x32(taddr + (uint32_t)c0, raw);
-        if (c0 + CHUNK == HALF_N) {   // this warp's columns are read: hand the accumulator back to the MMA issuer
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if (PAIR) mbar_arrive_cluster(acc_empty0 + (uint32_t)(acc * sizeof(uint64_t)));
-            else mbar_arrive(&bars->acc_empty[acc]);
-          }
-        }
-        epilogue_chunk<KCAP>(raw, st, col0 + c0, limit - c0, my_scores, my_cols, cap, slot_first, slot_step,
-                             my_pending, thr_own_addr, thr_other, merge_at);
+      // This warp's columns of the tile go to registers as early as the register file allows (three chunks, the
+      // fourth into the first one's registers once that is worked off) and the accumulator is handed back before
+      // the rest is processed and before any merge: the MMA issuer (which needs all 8 — in a pair 16 — warps to let
+      // go) no longer waits for a warp that is busy in a lockstep merge, and the epilogue gains a tile time of slack.
+      constexpr int NCH = HALF_N / CHUNK;   // 4
+      uint32_t raw[NCH - 1][CHUNK];
+#pragma unroll
+      for (int c = 0; c < NCH - 1; ++c) tmem_ld_32x32_issue(taddr + (uint32_t)(c * CHUNK), raw[c]);
+      const float thr_other = ld_shared_f32(thr_other_addr);
+#pragma unroll
+      for (int c = 0; c < NCH - 1; ++c) tmem_ld_wait(raw[c]);
+      chunk_hits<KCAP>(raw[0], st, col0, limit, my_scores, my_meta, cap, slot_first, slot_step, my_pending, thr_other);
+      tmem_ld_32x32(taddr + (uint32_t)((NCH - 1) * CHUNK), raw[0]);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(acc_empty0 + (uint32_t)(acc * sizeof(uint64_t)));
+        else mbar_arrive(&bars->acc_empty[acc]);
       }
+#pragma unroll
+      for (int c = 1; c < NCH; ++c)
+        chunk_hits<KCAP>(raw[c % (NCH - 1)], st, col0 + c * CHUNK, limit - c * CHUNK, my_scores, my_meta, cap,
+                         slot_first, slot_step, my_pending, thr_other);
+      merge_pending<KCAP>(st, my_pending, thr_own_addr, merge_at);
     }
     if (live) {
       dump.count[(int64_t)half * dump.units + pidx] = st.count;
@@ -452,29 +465,33 @@ score_select_kernel(DumpBuffers dump, int64_t batch, Schedule sch, int k, int64_
       const int n = dump.count[top * dump.units + pi];
       const int64_t slot0 = pi * (int64_t)dump.cap + (top ? dump.cap - n : 0);
       const int range_col0 = sch.first_tile(row, s) * BLOCK_N;
-      // 128-bit loads: DUMPW/4 lanes cover one dumped piece, a warp load covers 128/DUMPW pieces, eight
-      // independent loads in flight per lane (4 KB per warp and iteration)
-      constexpr int LPP = DUMPW / 4;            // lanes per piece
-      constexpr int PPL = 32 / LPP;             // pieces per warp load
-      const int sub = lane / LPP, quad = lane % LPP;
-      const float4* base = reinterpret_cast<const float4*>(dump.scores + slot0 * DUMPW) + quad;
-      for (int c0 = 0; c0 < n; c0 += 8 * PPL) {
-        float4 v[8];
+      // the piece maxima first (one coalesced 4-byte load per piece): only the pieces that reach tau — a few dozen
+      // of the ~200 dumped per row — are read at all (64 bytes each, by the lane that found them)
+      const int2* meta = dump.meta + slot0;
+      for (int c0 = 0; c0 < n; c0 += 128) {
+        int2 m[4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int piece = c0 + PPL * u + sub;
-          v[u] = piece < n ? __ldcs(base + (int64_t)piece * LPP) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-        }
+        for (int u = 0; u < 4; ++u)
+          m[u] = c0 + 32 * u + lane < n ? __ldcs(meta + c0 + 32 * u + lane) : make_int2(0, (int)0xff800000u);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const float e4[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+        for (int u = 0; u < 4; ++u) {
+          const float pm = __int_as_float(m[u].y);
+          if (pm >= tau && pm > -INFINITY) {
+            const int piece = c0 + 32 * u + lane;
+            const int col = range_col0 + m[u].x;
+            const float4* src = reinterpret_cast<const float4*>(dump.scores + (slot0 + piece) * DUMPW);
+            float4 v[DUMPW / 4];
 #pragma unroll
-          for (int comp = 0; comp < 4; ++comp) {
-            if (e4[comp] >= tau && e4[comp] > -INFINITY) {  // -inf marks columns past the end of the table
-              const int pos = atomicAdd(&s_count[w], 1);
-              if (pos < kSurvivorCap) {
-                s_key[w][pos] = candidate_key(
-                    e4[comp], range_col0 + dump.chunk_col[slot0 + c0 + PPL * u + sub] + 4 * quad + comp);
+            for (int q = 0; q < DUMPW / 4; ++q) v[q] = __ldcs(src + q);
+#pragma unroll
+            for (int q = 0; q < DUMPW / 4; ++q) {
+              const float e4[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+#pragma unroll
+              for (int comp = 0; comp < 4; ++comp) {
+                if (e4[comp] >= tau && e4[comp] > -INFINITY) {  // -inf marks columns past the end of the table
+                  const int pos = atomicAdd(&s_count[w], 1);
+                  if (pos < kSurvivorCap) s_key[w][pos] = candidate_key(e4[comp], col + 4 * q + comp);
+                }
               }
             }
           }
@@ -491,8 +508,22 @@ score_select_kernel(DumpBuffers dump, int64_t batch, Schedule sch, int k, int64_
   if (lane == 0) redo[row] = 0;
   const int n = s_count[w];
   uint64_t mine = 0;   // lane t ends up with the t-th best candidate (0 = none)
-  if (n <= 64) {
-    // the usual case (a few dozen survivors): bitonic sort of 64 keys, two per lane, descending
+  if (n <= 32) {
+    // a bitonic sort of 32 keys, one per lane, descending
+    uint64_t k0 = lane < n ? s_key[w][lane] : 0;
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        const uint64_t p0 = __shfl_xor_sync(0xffffffffu, k0, stride);
+        const bool lower = (lane & stride) == 0;
+        const bool desc = size == 32 || ((lane & size) == 0);
+        k0 = (lower == desc) ? (k0 > p0 ? k0 : p0) : (k0 < p0 ? k0 : p0);
+      }
+    }
+    mine = k0;
+  } else if (n <= 64) {
+    // a few dozen survivors: bitonic sort of 64 keys, two per lane, descending
     uint64_t k0 = lane < n ? s_key[w][lane] : 0, k1 = lane + 32 < n ? s_key[w][lane + 32] : 0;
 #pragma unroll
     for (int size = 2; size <= 64; size <<= 1) {
@@ -736,7 +767,7 @@ extern "C" size_t etpgt_score_topk_bf16_workspace_bytes(int64_t batch, int64_t n
   if (batch <= 0 || num_items <= 0 || k <= 0) return 256;
   const TcPlan p = tc_plan(batch, num_items, k);
   const size_t units = (size_t)p.sch.num_parts(batch);
-  return align_up(units * p.cap * DUMPW * sizeof(float)) + align_up(units * p.cap * sizeof(int32_t)) +
+  return align_up(units * p.cap * DUMPW * sizeof(float)) + align_up(units * p.cap * sizeof(int2)) +
          4 * align_up(units * sizeof(float)) + 2 * align_up((size_t)batch * sizeof(int32_t)) + 256;
 }
 
@@ -763,7 +794,7 @@ extern "C" int etpgt_score_topk_bf16_eval(const void* sess_bf16, const void* tab
   const size_t units = (size_t)p.sch.num_parts(batch);
   DumpBuffers dump;
   dump.scores = w.take<float>(units * p.cap * DUMPW);
-  dump.chunk_col = w.take<int32_t>(units * p.cap);
+  dump.meta = w.take<int2>(units * p.cap);
   dump.count = w.take<int32_t>(2 * units);
   dump.threshold = w.take<float>(2 * units);
   dump.units = (int64_t)units;
@@ -780,7 +811,7 @@ extern "C" int etpgt_score_topk_bf16_eval(const void* sess_bf16, const void* tab
   int pending_merge = kDefaultPendingMerge;
   if (const char* forced = getenv("ETPGT_SCORE_PENDING")) {  // tuning knob
     const int f = atoi(forced);
-    if (f >= 1 && f <= kPendingMerge + 1 - CHUNK / DUMPW) pending_merge = f;
+    if (f >= 1 && f <= kPendingMerge + 1 - BLOCK_N / 2 / DUMPW) pending_merge = f;
   }
   const size_t smem = tc_smem_bytes(num_kb, stages, p.pairs);
   cudaLaunchConfig_t cfg = {};
