@@ -51,6 +51,51 @@ struct __align__(8) GemmBarriers {
   uint32_t tmem_base;
 };
 
+// Optional second output of the epilogue (the FFN's first layer, etpgt/model/graph_transformer.py:109-124:
+// Linear -> GELU -> Dropout): next to the fp32 pre-activation C (kept for the backward pass) the epilogue
+// writes h = dropout(gelu(C)) directly as the split-bf16 operand pair of the next GEMM — the fp32 h and its
+// split pass never exist.  GELU is the exact (erf) form of nn.GELU(); the dropout mask is Philox keyed by
+// (seed, float4 index of the [M, N] tensor), the same bits etpgt_gelu_bwd_split regenerates.
+struct ActEpilogue {
+  __nv_bfloat16* hi;        // nullptr: no second output
+  __nv_bfloat16* lo;
+  int64_t ld;               // pitch of hi / lo in elements (multiple of 8)
+  uint64_t seed;
+  uint32_t drop_threshold;  // 0: no dropout
+  float keep_scale;
+};
+
+__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+// d/dx gelu(x) = Phi(x) + x phi(x)
+__device__ __forceinline__ float gelu_grad(float x) {
+  return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+}
+
+// eight consecutive output values of row `row` from column `col` on (col % 8 == 0)
+__device__ __forceinline__ void act_store8(const ActEpilogue& act, float4 a, float4 b, int64_t row, int64_t col,
+                                           int64_t N) {
+  float x[8] = {gelu_exact(a.x), gelu_exact(a.y), gelu_exact(a.z), gelu_exact(a.w),
+                gelu_exact(b.x), gelu_exact(b.y), gelu_exact(b.z), gelu_exact(b.w)};
+  if (act.drop_threshold != 0) {
+    const uint64_t i4 = (uint64_t)(row * N + col) >> 2;
+    const float4 f0 = dropout_factors4(act.seed, i4, act.drop_threshold, act.keep_scale);
+    const float4 f1 = dropout_factors4(act.seed, i4 + 1, act.drop_threshold, act.keep_scale);
+    x[0] *= f0.x; x[1] *= f0.y; x[2] *= f0.z; x[3] *= f0.w;
+    x[4] *= f1.x; x[5] *= f1.y; x[6] *= f1.z; x[7] *= f1.w;
+  }
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * t]), h1 = __float2bfloat16_rn(x[2 * t + 1]);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * t] - __bfloat162float(h0));
+    const __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * t + 1] - __bfloat162float(h1));
+    h[t] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    l[t] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  }
+  *reinterpret_cast<uint4*>(act.hi + row * act.ld + col) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(act.lo + row * act.ld + col) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
 // PARTS = 1: plain bf16 (A_hi, B_hi).  PARTS = 2: split operands, three products.
 template <int PARTS, int BLOCK_N>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -58,7 +103,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                    const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                    const __grid_constant__ CUtensorMap map_c /* C, or the [split_k][M][N] partials */,
                    int64_t M, int64_t N, int64_t K, int m_tiles, int n_tiles, int split_k, int kb_per_split,
-                   const float* __restrict__ bias, int a_mn, int b_mn, int accumulate) {
+                   const float* __restrict__ bias, int a_mn, int b_mn, int accumulate, const ActEpilogue act) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   constexpr int kStages = StageCount<PARTS, BLOCK_N>::value;
@@ -210,6 +255,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         if (lane == 0) tma_store_wait_read<1>();
         __syncwarp();
         uint8_t* box = my_cd + buf * CD_BOX_BYTES + lane * 128;
+        float4 prev = zero4();
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
@@ -218,6 +264,10 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
           if (bias_on) o = add4(o, bv[j]);
           else if (add_bias && col + 3 < N) o = add4(o, ldg4(bias + col));   // ragged last chunk
           *reinterpret_cast<float4*>(box + ((j ^ (lane & 7)) << 4)) = o;
+          if (act.hi != nullptr) {   // warp-uniform
+            if (j & 1) { if (row0 + lane < M && col + 3 < N) act_store8(act, prev, o, row0 + lane, col - 4, N); }
+            else prev = o;
+          }
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -259,7 +309,7 @@ gemm_bf16x3_2sm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
                        const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                        const __grid_constant__ CUtensorMap map_c /* C, or the [split_k][M][N] partials */,
                        int64_t M, int64_t N, int64_t K, int m_pairs, int n_tiles, int split_k, int kb_per_split,
-                       const float* __restrict__ bias, int a_mn, int b_mn, int accumulate) {
+                       const float* __restrict__ bias, int a_mn, int b_mn, int accumulate, const ActEpilogue act) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   constexpr int kStages = StageCount2<PARTS, BLOCK_N>::value;
@@ -408,6 +458,7 @@ gemm_bf16x3_2sm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
         if (lane == 0) tma_store_wait_read<1>();
         __syncwarp();
         uint8_t* box = my_cd + buf * CD_BOX_BYTES + lane * 128;
+        float4 prev = zero4();
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
@@ -416,6 +467,10 @@ gemm_bf16x3_2sm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
           if (bias_on) o = add4(o, bv[j]);
           else if (add_bias && col + 3 < N) o = add4(o, ldg4(bias + col));
           *reinterpret_cast<float4*>(box + ((j ^ (lane & 7)) << 4)) = o;
+          if (act.hi != nullptr) {   // warp-uniform
+            if (j & 1) { if (row0 + lane < M && col + 3 < N) act_store8(act, prev, o, row0 + lane, col - 4, N); }
+            else prev = o;
+          }
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -495,6 +550,49 @@ split_bf16_kernel(const float* __restrict__ src, int64_t rows, int64_t cols, int
       }
     }
   }
+  if (colsum_partial != nullptr && threadIdx.x < SPLIT_TILE) {
+    const int64_t c = c0 + threadIdx.x;
+    if (c < cols) {
+      float s = 0.f;
+      for (int rr = 0; rr < SPLIT_TILE; ++rr) s += tile[rr][threadIdx.x];
+      colsum_partial[(int64_t)blockIdx.y * cols + c] = s;
+    }
+  }
+}
+
+// Backward of the FFN's Linear -> GELU -> Dropout (the forward is the ActEpilogue of the GEMM):
+// du = d_h * dropout_factor * gelu'(u), written directly as the split-bf16 operand pair of the two weight / input
+// gradient GEMMs, with its column sums (the first layer's bias gradient) as per-CTA partials.
+__global__ void __launch_bounds__(256)
+gelu_bwd_split_kernel(const float* __restrict__ d_h, const float* __restrict__ u, int64_t rows, int64_t cols,
+                      uint64_t seed, uint32_t drop_threshold, float keep_scale, __nv_bfloat16* __restrict__ hi,
+                      __nv_bfloat16* __restrict__ lo, int64_t ld_out, float* __restrict__ colsum_partial) {
+  __shared__ float tile[SPLIT_TILE][SPLIT_TILE + 1];
+  const int64_t r0 = (int64_t)blockIdx.y * SPLIT_TILE, c0 = (int64_t)blockIdx.x * SPLIT_TILE;
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;  // 16 float4 columns x 16 rows
+  for (int rr = ty; rr < SPLIT_TILE; rr += 16) {
+    const int64_t r = r0 + rr, c = c0 + 4 * tx;
+    float4 x = zero4();
+    if (r < rows && c < cols) {
+      const float4 g = ldg4(d_h + r * cols + c), uv = ldg4(u + r * cols + c);
+      x = make_float4(g.x * gelu_grad(uv.x), g.y * gelu_grad(uv.y), g.z * gelu_grad(uv.z), g.w * gelu_grad(uv.w));
+      if (drop_threshold != 0) x = mul4(x, dropout_factors4(seed, (uint64_t)(r * cols + c) >> 2, drop_threshold, keep_scale));
+      const float e[4] = {x.x, x.y, x.z, x.w};
+      uint32_t h2[2], l2[2];
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_one(e[2 * t], h0, l0);
+        split_one(e[2 * t + 1], h1, l1);
+        h2[t] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        l2[t] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+      }
+      *reinterpret_cast<uint2*>(hi + r * ld_out + c) = make_uint2(h2[0], h2[1]);
+      *reinterpret_cast<uint2*>(lo + r * ld_out + c) = make_uint2(l2[0], l2[1]);
+    }
+    tile[rr][4 * tx] = x.x; tile[rr][4 * tx + 1] = x.y; tile[rr][4 * tx + 2] = x.z; tile[rr][4 * tx + 3] = x.w;
+  }
+  __syncthreads();
   if (colsum_partial != nullptr && threadIdx.x < SPLIT_TILE) {
     const int64_t c = c0 + threadIdx.x;
     if (c < cols) {
@@ -615,10 +713,10 @@ extern "C" size_t etpgt_gemm_bf16x3_workspace_bytes(int64_t M, int64_t N, int64_
   return (p.split_k > 1 ? align_up((size_t)p.split_k * M * N * sizeof(float)) : 0) + 256;
 }
 
-extern "C" int etpgt_gemm_bf16x3_ex(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int64_t M,
-                                    int64_t N, int64_t K, int64_t lda, int64_t ldb, int a_mn_major, int b_mn_major,
-                                    const float* bias, int accumulate, float* C, int64_t ldc, int split_k, void* ws,
-                                    size_t ws_bytes, etpgt_stream_t stream_) {
+static int gemm_run(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int64_t M, int64_t N,
+                    int64_t K, int64_t lda, int64_t ldb, int a_mn_major, int b_mn_major, const float* bias,
+                    int accumulate, float* C, int64_t ldc, int split_k, void* ws, size_t ws_bytes,
+                    etpgt_stream_t stream_, const ActEpilogue& act) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ETPGT_REQUIRE(M >= 0 && N > 0 && K > 0 && M < (int64_t(1) << 31) && N < (int64_t(1) << 31) && K < (int64_t(1) << 31),
                 "gemm_bf16x3: bad sizes");
@@ -667,7 +765,7 @@ extern "C" int etpgt_gemm_bf16x3_ex(const void* a_hi, const void* a_lo, const vo
     gemm_bf16x3_kernel<PARTS_, BN_><<<p.grid, kThreads, smem, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, mc, M, N, K,   \
                                                                        p.m_tiles, p.n_tiles, p.split_k,           \
                                                                        p.kb_per_split, bias, a_mn_major != 0,     \
-                                                                       b_mn_major != 0, accumulate != 0);         \
+                                                                       b_mn_major != 0, accumulate != 0, act);    \
   }
 #define LAUNCH2(PARTS_, BN_)                                                                                      \
   {                                                                                                               \
@@ -688,7 +786,7 @@ extern "C" int etpgt_gemm_bf16x3_ex(const void* a_hi, const void* a_lo, const vo
     cfg.numAttrs = 1;                                                                                             \
     cudaLaunchKernelEx(&cfg, gemm_bf16x3_2sm_kernel<PARTS_, BN_>, ma_hi, ma_lo, mb_hi, mb_lo, mc, M, N, K,        \
                        p.m_tiles, p.n_tiles, p.split_k, p.kb_per_split, bias, (int)(a_mn_major != 0),             \
-                       (int)(b_mn_major != 0), (int)(accumulate != 0));                                           \
+                       (int)(b_mn_major != 0), (int)(accumulate != 0), act);                                      \
   }
   if (p.pairs) {
     if (parts == 2 && p.block_n == 256) LAUNCH2(2, 256)
@@ -706,6 +804,70 @@ extern "C" int etpgt_gemm_bf16x3_ex(const void* a_hi, const void* a_lo, const vo
     splitk_reduce_kernel<<<grid_for(M * N / 4, 256 * 2, 8), 256, 0, stream>>>(partial, p.split_k, M, N, bias, C, ldc,
                                                                               accumulate != 0);
     ETPGT_CHECK_LAUNCH("splitk_reduce");
+  }
+  return ETPGT_OK;
+}
+
+extern "C" int etpgt_gemm_bf16x3_ex(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int64_t M,
+                                    int64_t N, int64_t K, int64_t lda, int64_t ldb, int a_mn_major, int b_mn_major,
+                                    const float* bias, int accumulate, float* C, int64_t ldc, int split_k, void* ws,
+                                    size_t ws_bytes, etpgt_stream_t stream) {
+  ActEpilogue none = {};
+  return gemm_run(a_hi, a_lo, b_hi, b_lo, M, N, K, lda, ldb, a_mn_major, b_mn_major, bias, accumulate, C, ldc, split_k,
+                  ws, ws_bytes, stream, none);
+}
+
+// p -> (threshold = p * 2^32, scale = 1 / (1 - p)); p == 0 disables the mask (the same mapping as bn.cu)
+static bool gelu_dropout_params(double p, uint32_t* threshold, float* keep_scale) {
+  if (!(p >= 0.0 && p < 1.0)) return false;
+  const double t = p * 4294967296.0;
+  *threshold = p > 0.0 ? (uint32_t)(t < 1.0 ? 1.0 : (t > 4294967295.0 ? 4294967295.0 : t)) : 0u;
+  *keep_scale = (float)(1.0 / (1.0 - p));
+  return true;
+}
+
+extern "C" int etpgt_gemm_bf16x3_gelu(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int64_t M,
+                                      int64_t N, int64_t K, int64_t lda, int64_t ldb, const float* bias, float* C,
+                                      int64_t ldc, void* h_hi, void* h_lo, int64_t ldh, double drop_p, uint64_t seed,
+                                      void* ws, size_t ws_bytes, etpgt_stream_t stream) {
+  ETPGT_REQUIRE(h_hi != nullptr && h_lo != nullptr && ldh >= N && ldh % 8 == 0 && N % 8 == 0,
+                "gemm_bf16x3_gelu: h_hi / h_lo required, N and ldh multiples of 8, ldh >= N");
+  ETPGT_REQUIRE((((uintptr_t)h_hi | (uintptr_t)h_lo) & 15) == 0, "gemm_bf16x3_gelu: outputs must be 16-byte aligned");
+  ActEpilogue act = {};
+  act.hi = static_cast<__nv_bfloat16*>(h_hi);
+  act.lo = static_cast<__nv_bfloat16*>(h_lo);
+  act.ld = ldh;
+  act.seed = seed;
+  ETPGT_REQUIRE(gelu_dropout_params(drop_p, &act.drop_threshold, &act.keep_scale),
+                "gemm_bf16x3_gelu: dropout p must be in [0, 1)");
+  return gemm_run(a_hi, a_lo, b_hi, b_lo, M, N, K, lda, ldb, 0, 0, bias, 0, C, ldc, 1, ws, ws_bytes, stream, act);
+}
+
+extern "C" int etpgt_gelu_bwd_split(const float* d_h, const float* u, int64_t rows, int64_t cols, double drop_p,
+                                    uint64_t seed, void* hi, void* lo, int64_t ld_out, float* colsum, void* ws,
+                                    size_t ws_bytes, etpgt_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ETPGT_REQUIRE(rows >= 0 && cols > 0 && cols % 4 == 0 && ld_out >= cols, "gelu_bwd_split: bad sizes");
+  ETPGT_REQUIRE(d_h != nullptr && u != nullptr && hi != nullptr && lo != nullptr, "gelu_bwd_split: null argument");
+  uint32_t threshold;
+  float keep_scale;
+  ETPGT_REQUIRE(gelu_dropout_params(drop_p, &threshold, &keep_scale), "gelu_bwd_split: dropout p must be in [0, 1)");
+  if (colsum != nullptr && ws_bytes < etpgt_split_bf16_workspace_bytes(rows, cols)) {
+    set_error("gelu_bwd_split: workspace too small");
+    return ETPGT_EWORKSPACE;
+  }
+  const int64_t row_tiles = (rows + SPLIT_TILE - 1) / SPLIT_TILE, col_tiles = (cols + SPLIT_TILE - 1) / SPLIT_TILE;
+  float* partial = colsum != nullptr ? static_cast<float*>(ws) : nullptr;
+  if (rows > 0) {
+    gelu_bwd_split_kernel<<<dim3((unsigned)col_tiles, (unsigned)row_tiles), 256, 0, stream>>>(
+        d_h, u, rows, cols, seed, threshold, keep_scale, static_cast<__nv_bfloat16*>(hi),
+        static_cast<__nv_bfloat16*>(lo), ld_out, partial);
+    ETPGT_CHECK_LAUNCH("gelu_bwd_split");
+  }
+  if (colsum != nullptr) {
+    colsum_reduce_kernel<<<(unsigned)((cols * 32 + 255) / 256), 256, 0, stream>>>(partial, rows > 0 ? row_tiles : 0, cols,
+                                                                                 colsum);
+    ETPGT_CHECK_LAUNCH("colsum_reduce");
   }
   return ETPGT_OK;
 }

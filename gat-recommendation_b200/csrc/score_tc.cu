@@ -200,7 +200,7 @@ __device__ __forceinline__ void merge_pending(RowState<KCAP>& st, uint32_t my_pe
   int most = st.pending;
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) most = max(most, __shfl_xor_sync(0xffffffffu, most, off));
-#pragma unroll 1
+#pragma unroll 2
   for (int p = 0; p < most; ++p) {
     float x = p < st.pending ? ld_shared_f32(my_pending + p * 32 * sizeof(float)) : -INFINITY;  // -inf: no-op
 #pragma unroll
@@ -436,17 +436,19 @@ __device__ __forceinline__ void decode_key(uint64_t key, float& v, int64_t& col)
 // packed keys, then sorted (bitonic network over 64 keys; selection passes when there are more).
 constexpr int kSelectWarps = 4;
 constexpr int kSurvivorCap = 512;
+constexpr int kFlagCap = 256;        // qualifying pieces per row (more: the row goes to the exact fallback)
 
 __global__ void __launch_bounds__(kSelectWarps * 32)
 score_select_kernel(DumpBuffers dump, int64_t batch, Schedule sch, int k, int64_t id_base,
                     float* __restrict__ top_val, int64_t* __restrict__ top_idx, int32_t* __restrict__ redo,
                     const int64_t* __restrict__ targets, int32_t* __restrict__ hit_pos) {
   __shared__ uint64_t s_key[kSelectWarps][kSurvivorCap];  // (orderable score, ~column): larger = better
-  __shared__ int s_count[kSelectWarps];
+  __shared__ int2 s_flag[kSelectWarps][kFlagCap];          // qualifying pieces: (slot relative to the row's first, column)
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = blockIdx.x * (int64_t)kSelectWarps + w;
   if (row >= batch) return;
-  if (lane == 0) s_count[w] = 0;
+  int n_flag = 0, n_surv = 0;                               // warp-uniform counters
+  const int64_t row_slot0 = sch.part_index(row, 0) * (int64_t)dump.cap;
   float tau = -INFINITY;
   bool overflow = false;
   const int splits = sch.parts_of_row(row);
@@ -465,8 +467,8 @@ score_select_kernel(DumpBuffers dump, int64_t batch, Schedule sch, int k, int64_
       const int n = dump.count[top * dump.units + pi];
       const int64_t slot0 = pi * (int64_t)dump.cap + (top ? dump.cap - n : 0);
       const int range_col0 = sch.first_tile(row, s) * BLOCK_N;
-      // the piece maxima first (one coalesced 4-byte load per piece): only the pieces that reach tau — a few dozen
-      // of the ~200 dumped per row — are read at all (64 bytes each, by the lane that found them)
+      // the piece maxima first (one coalesced 8-byte load per piece): the pieces that reach tau — a few dozen of the
+      // ~200 dumped per row — are collected as (slot, first column) pairs ...
       const int2* meta = dump.meta + slot0;
       for (int c0 = 0; c0 < n; c0 += 128) {
         int2 m[4];
@@ -476,37 +478,52 @@ score_select_kernel(DumpBuffers dump, int64_t batch, Schedule sch, int k, int64_
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const float pm = __int_as_float(m[u].y);
-          if (pm >= tau && pm > -INFINITY) {
-            const int piece = c0 + 32 * u + lane;
-            const int col = range_col0 + m[u].x;
-            const float4* src = reinterpret_cast<const float4*>(dump.scores + (slot0 + piece) * DUMPW);
-            float4 v[DUMPW / 4];
-#pragma unroll
-            for (int q = 0; q < DUMPW / 4; ++q) v[q] = __ldcs(src + q);
-#pragma unroll
-            for (int q = 0; q < DUMPW / 4; ++q) {
-              const float e4[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
-#pragma unroll
-              for (int comp = 0; comp < 4; ++comp) {
-                if (e4[comp] >= tau && e4[comp] > -INFINITY) {  // -inf marks columns past the end of the table
-                  const int pos = atomicAdd(&s_count[w], 1);
-                  if (pos < kSurvivorCap) s_key[w][pos] = candidate_key(e4[comp], col + 4 * q + comp);
-                }
-              }
-            }
+          const bool flag = pm >= tau && pm > -INFINITY;
+          const unsigned mask = __ballot_sync(0xffffffffu, flag);
+          if (flag) {
+            const int pos = n_flag + __popc(mask & ((1u << lane) - 1));
+            if (pos < kFlagCap) s_flag[w][pos] = make_int2((int)(slot0 - row_slot0) + c0 + 32 * u + lane, range_col0 + m[u].x);
           }
+          n_flag += __popc(mask);
         }
       }
     }
     __syncwarp();
-    overflow = s_count[w] > kSurvivorCap;  // a huge tie at the threshold
+    if (n_flag > kFlagCap) {
+      overflow = true;
+    } else {
+      // ... and read two at a time: half a warp per piece, one score per lane (a coalesced 64-byte line)
+      const int sub = lane >> 4, e = lane & 15;
+      for (int f0 = 0; f0 < n_flag; f0 += 8) {      // four independent loads in flight per lane
+        int2 fl[4];
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const bool have = f0 + 2 * u + sub < n_flag;
+          fl[u] = have ? s_flag[w][f0 + 2 * u + sub] : make_int2(0, 0);
+          v[u] = have ? __ldcs(dump.scores + (row_slot0 + fl[u].x) * DUMPW + e) : -INFINITY;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const bool keep = v[u] >= tau && v[u] > -INFINITY;   // -inf marks columns past the end of the table
+          const unsigned mask = __ballot_sync(0xffffffffu, keep);
+          if (keep) {
+            const int pos = n_surv + __popc(mask & ((1u << lane) - 1));
+            if (pos < kSurvivorCap) s_key[w][pos] = candidate_key(v[u], fl[u].y + e);
+          }
+          n_surv += __popc(mask);
+        }
+      }
+      __syncwarp();
+      overflow = n_surv > kSurvivorCap;  // a huge tie at the threshold
+    }
   }
   if (overflow) {
     if (lane == 0) redo[row] = 1;
     return;
   }
   if (lane == 0) redo[row] = 0;
-  const int n = s_count[w];
+  const int n = n_surv;
   uint64_t mine = 0;   // lane t ends up with the t-th best candidate (0 = none)
   if (n <= 32) {
     // a bitonic sort of 32 keys, one per lane, descending

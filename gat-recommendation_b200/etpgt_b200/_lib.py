@@ -53,6 +53,9 @@ _PROTOTYPES = {
     "etpgt_gemm_bf16x3_workspace_bytes": (Z, [L, L, L, I]),
     "etpgt_gemm_bf16x3": (I, [P, P, P, P, L, L, L, L, L, P, P, L, I, P, Z, P]),
     "etpgt_gemm_bf16x3_ex": (I, [P, P, P, P, L, L, L, L, L, I, I, P, I, P, L, I, P, Z, P]),
+    "etpgt_gemm_bf16x3_gelu": (I, [P, P, P, P, L, L, L, L, L, P, P, L, P, P, L, D, ctypes.c_uint64, P, Z, P]),
+    "etpgt_gelu_bwd_split": (I, [P, P, L, L, D, ctypes.c_uint64, P, P, L, P, P, Z, P]),
+    "etpgt_lap_sym_block": (I, [P, P, P, L, I, P, P, D, D, D, P, P]),
     "etpgt_gat_fwd": (I, [P, P, P, L, I, I, P, P, P, F, P, P, P, P, P, P]),
     "etpgt_gat_bwd_workspace_bytes": (Z, [L, L, I]),
     "etpgt_gat_bwd": (I, [P, P, P, P, P, L, I, I, P, P, P, P, P, P, L, F, P, P, P, P, P, P, P, P, Z, P]),

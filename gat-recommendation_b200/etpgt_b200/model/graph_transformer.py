@@ -3,6 +3,7 @@ attributes and state-dict keys follow etpgt/model/graph_transformer.py."""
 
 from __future__ import annotations
 
+import torch
 import torch.nn as nn
 
 from .. import ops
@@ -36,14 +37,19 @@ class GraphTransformer(BaseRecommendationModel):
         return nn.Sequential(nn.Linear(hidden_dim, inner), nn.GELU(), nn.Dropout(self.dropout),
                              nn.Linear(inner, hidden_dim), nn.Dropout(self.dropout))
 
-    @staticmethod
-    def _ffn(ffn: nn.Sequential, x):
-        """Linear -> GELU -> Dropout -> Linear -> Dropout (graph_transformer.py:109-124) with both dense
-        layers on the tcgen05 split-bf16 GEMM; the module (and its state-dict keys ffns.{l}.{0,3}) is the
+    def _ffn_block(self, ffn: nn.Sequential, x):
+        """x + Linear -> GELU -> Dropout -> Linear -> Dropout (graph_transformer.py:109-124,163-168): GEMM 1 with the
+        GELU (+ Philox dropout) in its epilogue feeding GEMM 2 through split-bf16 operands, residual added by the
+        second GEMM's TMA reduce (ops.FeedForward); the module (and its state-dict keys ffns.{l}.{0,3}) is the
         reference's nn.Sequential."""
         lin1, act, drop1, lin2, drop2 = ffn
+        if ops.feed_forward_supported(x, lin1.weight, lin2.weight) and lin1.bias is not None and lin2.bias is not None:
+            p1 = drop1.p if self.training else 0.0
+            p2 = drop2.p if self.training else 0.0
+            seeds = torch.randint(0, 2 ** 62, (2,)).tolist() if (p1 > 0.0 or p2 > 0.0) else (0, 0)
+            return ops.FeedForward.apply(x, lin1.weight, lin1.bias, lin2.weight, lin2.bias, p1, p2, seeds[0], seeds[1])
         h = drop1(act(ops.linear(x, lin1.weight, lin1.bias)))
-        return drop2(ops.linear(h, lin2.weight, lin2.bias))
+        return x + drop2(ops.linear(h, lin2.weight, lin2.bias))
 
     def forward(self, batch):
         ids, index = self._graph(batch)
@@ -74,7 +80,7 @@ class GraphTransformer(BaseRecommendationModel):
                 x = self.dropout_layer(x)
                 split = None
             if self.use_ffn:
-                x = x + self._ffn(self.ffns[layer], x)
+                x = self._ffn_block(self.ffns[layer], x)
         return self.readout(x, batch.batch, self._num_sessions(batch))
 
 

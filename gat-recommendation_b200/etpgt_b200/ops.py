@@ -774,6 +774,67 @@ def embed_split_supported(table: torch.Tensor, embedding_dim: int, hidden_dim: i
     return FUSED_LAYER and embedding_dim == hidden_dim and fused_conv_supported(table, embedding_dim, 4 * hidden_dim)
 
 
+class FeedForward(torch.autograd.Function):
+    """out = x + Dropout(Linear2(Dropout(GELU(Linear1(x))))) — the FFN block of the non-optimized GraphTransformer
+    (etpgt/model/graph_transformer.py:109-124,157-168).  Forward: GEMM 1 with the GELU (+ Philox dropout) in its
+    epilogue, which writes h directly as the split-bf16 operand pair of GEMM 2 next to the fp32 pre-activation u
+    (etpgt_gemm_bf16x3_gelu); GEMM 2 adds its tiles onto a copy of x (TMA reduce-add) when no second dropout is
+    active.  Backward: dH = dY W2, one element pass du = dH * mask * gelu'(u) that emits the split pair and the bias
+    column sums (etpgt_gelu_bwd_split), dX = du W1 added onto the residual gradient, two split-K weight gradients."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, p1: float, p2: float, seed1: int, seed2: int):
+        _require_cuda(x, "node features")
+        x, w1, w2, b1, b2 = _f32(x), _f32(w1), _f32(w2), _f32(b1), _f32(b2)
+        n, d = x.shape
+        f = w1.size(0)
+        dev = x.device
+        x_hi, x_lo, _, _, _, _ = _split(x, True, False)
+        w1_hi, w1_lo, _, _, _, _ = _split(w1, True, False)
+        w2_hi, w2_lo, _, _, _, _ = _split(w2, True, False)
+        u = torch.empty(n, f, dtype=torch.float32, device=dev)
+        h_hi = torch.empty(n, f, dtype=torch.bfloat16, device=dev)
+        h_lo = torch.empty(n, f, dtype=torch.bfloat16, device=dev)
+        ws = workspace(size("etpgt_gemm_bf16x3_workspace_bytes", n, f, d, 1), dev)
+        call("etpgt_gemm_bf16x3_gelu", ptr(x_hi), ptr(x_lo), ptr(w1_hi), ptr(w1_lo), n, f, d, d, d, ptr(b1), ptr(u), f,
+             ptr(h_hi), ptr(h_lo), f, float(p1), int(seed1), ptr(ws), ws.numel(), stream())
+        mask2 = None
+        if p2 > 0.0:
+            mask2 = dropout_mask(n * d, p2, dev, seed=seed2).view(n, d)
+            out = torch.addcmul(x, _gemm_x3(h_hi, h_lo, w2_hi, w2_lo, n, d, f, f, f, b2), mask2)
+        else:
+            out = _gemm_x3(h_hi, h_lo, w2_hi, w2_lo, n, d, f, f, f, b2, accumulate_into=x.clone())
+        ctx.save_for_backward(x_hi, x_lo, w1_hi, w1_lo, w2_hi, w2_lo, u, h_hi, h_lo, mask2)
+        ctx.p1, ctx.seed1 = float(p1), int(seed1)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        x_hi, x_lo, w1_hi, w1_lo, w2_hi, w2_lo, u, h_hi, h_lo, mask2 = ctx.saved_tensors
+        d_out = _f32(d_out)
+        n, d = x_hi.shape
+        f = w1_hi.size(0)
+        dev = d_out.device
+        d_y = d_out if mask2 is None else d_out * mask2
+        g_hi, g_lo, _, _, _, d_b2 = _split(d_y, True, False, colsum=True)
+        d_h = _gemm_x3(g_hi, g_lo, w2_hi, w2_lo, n, f, d, d, f, None, b_mn=True)                    # dY W2
+        d_w2 = _gemm_x3(g_hi, g_lo, h_hi, h_lo, d, f, n, d, f, None, split_k=0, a_mn=True, b_mn=True)  # dY^T H
+        du_hi = torch.empty(n, f, dtype=torch.bfloat16, device=dev)
+        du_lo = torch.empty(n, f, dtype=torch.bfloat16, device=dev)
+        d_b1 = torch.empty(f, dtype=torch.float32, device=dev)
+        ws = workspace(size("etpgt_split_bf16_workspace_bytes", n, f), dev)
+        call("etpgt_gelu_bwd_split", ptr(d_h), ptr(u), n, f, ctx.p1, ctx.seed1, ptr(du_hi), ptr(du_lo), f, ptr(d_b1),
+             ptr(ws), ws.numel(), stream())
+        d_x = _gemm_x3(du_hi, du_lo, w1_hi, w1_lo, n, d, f, f, d, None, b_mn=True, accumulate_into=d_out.clone())
+        d_w1 = _gemm_x3(du_hi, du_lo, x_hi, x_lo, f, d, n, f, d, None, split_k=0, a_mn=True, b_mn=True)
+        return d_x, d_w1, d_b1, d_w2, d_b2, None, None, None, None
+
+
+def feed_forward_supported(x: torch.Tensor, w1: torch.Tensor, w2: torch.Tensor) -> bool:
+    return (PROJECTION_BACKEND == "tcgen05" and x.is_cuda and x.size(0) > 0 and x.size(1) % 8 == 0
+            and w1.size(0) % 8 == 0 and w2.size(0) == x.size(1))
+
+
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None) -> torch.Tensor:
     """Dense projection of the path.  Tensor-core split-bf16 GEMM when the shape allows it
     (inner and outer widths multiples of 8), else a library fp32 GEMM."""

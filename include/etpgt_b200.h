@@ -231,6 +231,33 @@ int etpgt_gemm_bf16x3_ex(const void* a_hi, const void* a_lo, const void* b_hi, c
                          const float* bias, int accumulate, float* c, int64_t ldc, int split_k,
                          void* ws, size_t ws_bytes, etpgt_stream_t stream);
 
+/* ---- f4: the FFN variant's Linear -> GELU -> Dropout -> Linear -> Dropout (etpgt/model/graph_transformer.py:109-124,
+ * 157-168, create_graph_transformer).  etpgt_gemm_bf16x3_gelu is etpgt_gemm_bf16x3 (K-major operands, no split-K)
+ * whose epilogue has a second output: besides the fp32 pre-activation C = A B^T + bias (kept for the backward pass)
+ * it writes h = dropout_p(gelu(C)) directly as the split-bf16 operand pair h_hi / h_lo [M, N] (pitch ldh) of the
+ * second GEMM; the fp32 h and its split pass never exist.  GELU is nn.GELU()'s exact erf form; the mask is Philox
+ * keyed by (seed, element), p = 0 disables it.  etpgt_gelu_bwd_split is the matching backward element pass:
+ * du = d_h * mask * gelu'(u), written as the split-bf16 pair du_hi / du_lo [rows, cols] (pitch ld_out) with its
+ * column sums (the first layer's bias gradient, NULL to skip; workspace = etpgt_split_bf16_workspace_bytes). */
+int etpgt_gemm_bf16x3_gelu(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,
+                           int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb,
+                           const float* bias, float* c, int64_t ldc,
+                           void* h_hi, void* h_lo, int64_t ldh, double drop_p, uint64_t seed,
+                           void* ws, size_t ws_bytes, etpgt_stream_t stream);
+int etpgt_gelu_bwd_split(const float* d_h, const float* u, int64_t rows, int64_t cols, double drop_p, uint64_t seed,
+                         void* du_hi, void* du_lo, int64_t ld_out, float* colsum,
+                         void* ws, size_t ws_bytes, etpgt_stream_t stream);
+
+/* ---- f4: Laplacian positional encoding on the device (etpgt/encodings/laplacian_pe.py:19-66: PyG
+ * get_laplacian(normalization="sym") -> scipy eigsh(k+1, which="SM")).  The operator of the eigen solver
+ * (etpgt_b200.encodings.laplacian_pe.compute_laplacian_pe(..., method="device"), Chebyshev-filtered subspace
+ * iteration): y = alpha * (L x) + beta * x + gamma * z on a block of b <= 32 fp64 vectors stored [n, b] row-major,
+ * L = I - D^-1/2 A D^-1/2 given by the graph's CSR rows (rowptr int64 [n+1], col int32, self loops removed,
+ * parallel edges counted) and scale = deg^-1/2 (0 for isolated nodes).  z may be NULL; y must not alias x or z. */
+int etpgt_lap_sym_block(const int64_t* rowptr, const int32_t* col, const double* scale, int64_t n, int b,
+                        const double* x, const double* z, double alpha, double beta, double gamma,
+                        double* y, etpgt_stream_t stream);
+
 /* ---- a12: GAT edge-softmax aggregation and GraphSAGE mean aggregation ---------------------
  * PyG GATConv(add_self_loops=True) as used at etpgt/model/gat.py:49-109,137: h [N, width] with
  * width = heads*channels is the projected row, a_src/a_dst [N, heads] the attention scalars;

@@ -125,3 +125,86 @@ def test_fused_transformer_conv_layer_matches_fp64(n, e, dim, heads, in_dim):
     # the key bias is cancelled by the softmax (analytically zero): compare on the scale of the whole vector
     assert rel_err(bc.grad, torch.cat([b.grad for b in b64])) < tol
     assert rel_err(wbc.grad, wb64.grad) < tol
+
+
+def _ffn_reference(x, w1, b1, w2, b2, mask1=None, mask2=None):
+    """x + Linear2(mask1 * GELU(Linear1(x))) * mask2 in fp64 — etpgt/model/graph_transformer.py:109-124,163-168."""
+    h = torch.nn.functional.gelu(x @ w1.t() + b1)
+    if mask1 is not None:
+        h = h * mask1
+    y = h @ w2.t() + b2
+    return x + (y if mask2 is None else y * mask2)
+
+
+@pytest.mark.parametrize("n,d,f", [(3000, 256, 1024), (130, 64, 128), (1, 32, 64), (517, 64, 256)])
+def test_feed_forward_block_matches_fp64(n, d, f):
+    """ops.FeedForward (GEMM with the GELU epilogue -> GEMM with the residual added by the TMA reduce) and its
+    backward (etpgt_gelu_bwd_split between the GEMMs) against the fp64 formula."""
+    import etpgt_b200.ops as ops
+
+    g = torch.Generator().manual_seed(n + f)
+    x = torch.randn(n, d, generator=g, dtype=torch.float64)
+    w1 = torch.randn(f, d, generator=g, dtype=torch.float64) / d ** 0.5
+    b1 = torch.randn(f, generator=g, dtype=torch.float64) * 0.1
+    w2 = torch.randn(d, f, generator=g, dtype=torch.float64) / f ** 0.5
+    b2 = torch.randn(d, generator=g, dtype=torch.float64) * 0.1
+    d_out = torch.randn(n, d, generator=g, dtype=torch.float64)
+    ref = [t.clone().requires_grad_(True) for t in (x, w1, b1, w2, b2)]
+    want = _ffn_reference(*ref)
+    want.backward(d_out)
+    dev = [t.float().cuda().requires_grad_(True) for t in (x, w1, b1, w2, b2)]
+    got = ops.FeedForward.apply(*dev, 0.0, 0.0, 0, 0)
+    got.backward(d_out.float().cuda())
+    torch.cuda.synchronize()
+    assert rel_err(got, want) < 3e-5
+    for a, b in zip(dev, ref):
+        assert rel_err(a.grad, b.grad) < 5e-5
+
+
+def test_feed_forward_dropout_masks_are_regenerated_in_backward():
+    """With dropout the GELU epilogue and etpgt_gelu_bwd_split draw the same Philox bits: the masks are read back
+    from the forward's own outputs (h == 0 where dropped) and the fp64 formula with those masks must reproduce both
+    the output and every gradient; the keep rate is 1 - p."""
+    import etpgt_b200.ops as ops
+    from etpgt_b200.ops import call, ptr, size, stream, workspace
+
+    n, d, f, p1, p2 = 700, 64, 256, 0.25, 0.1
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(n, d, generator=g, dtype=torch.float64)
+    w1 = torch.randn(f, d, generator=g, dtype=torch.float64) / d ** 0.5
+    b1 = torch.randn(f, generator=g, dtype=torch.float64) * 0.1
+    w2 = torch.randn(d, f, generator=g, dtype=torch.float64) / f ** 0.5
+    b2 = torch.randn(d, generator=g, dtype=torch.float64) * 0.1
+    d_out = torch.randn(n, d, generator=g, dtype=torch.float64)
+    seed1, seed2 = 1234567, 7654321
+    # the first GEMM alone: pre-activation u and the split pair of h
+    xc, w1c = x.float().cuda(), w1.float().cuda()
+    x_hi, x_lo, _, _, _, _ = ops._split(xc, True, False)
+    w_hi, w_lo, _, _, _, _ = ops._split(w1c, True, False)
+    u = torch.empty(n, f, device="cuda")
+    h_hi = torch.empty(n, f, dtype=torch.bfloat16, device="cuda")
+    h_lo = torch.empty_like(h_hi)
+    ws = workspace(size("etpgt_gemm_bf16x3_workspace_bytes", n, f, d, 1), xc.device)
+    call("etpgt_gemm_bf16x3_gelu", ptr(x_hi), ptr(x_lo), ptr(w_hi), ptr(w_lo), n, f, d, d, d, ptr(b1.float().cuda()),
+         ptr(u), f, ptr(h_hi), ptr(h_lo), f, p1, seed1, ptr(ws), ws.numel(), stream())
+    torch.cuda.synchronize()
+    assert rel_err(u, x @ w1.t() + b1) < 3e-5
+    h = h_hi.double().cpu() + h_lo.double().cpu()
+    act = torch.nn.functional.gelu(x @ w1.t() + b1)
+    kept = h != 0
+    assert abs(kept.double().mean().item() - (1 - p1)) < 0.01
+    assert rel_err(h[kept], (act / (1 - p1))[kept]) < 3e-5
+    mask1 = kept.double() / (1 - p1)
+    mask2 = ops.dropout_mask(n * d, p2, xc.device, seed=seed2).view(n, d).double().cpu()
+    ref = [t.clone().requires_grad_(True) for t in (x, w1, b1, w2, b2)]
+    want = _ffn_reference(*ref, mask1=mask1, mask2=mask2)
+    want.backward(d_out)
+    dev = [t.float().cuda().requires_grad_(True) for t in (x, w1, b1, w2, b2)]
+    got = ops.FeedForward.apply(*dev, p1, p2, seed1, seed2)
+    got.backward(d_out.float().cuda())
+    torch.cuda.synchronize()
+    assert rel_err(got, want) < 3e-5
+    for a, b in zip(dev, ref):
+        assert rel_err(a.grad, b.grad) < 5e-5
+    again = ops.FeedForward.apply(*[t.detach() for t in dev], p1, p2, seed1, seed2)
+    assert torch.equal(again, got)
