@@ -65,8 +65,8 @@ constexpr int DUMPW = 16;      // columns per dumped piece (64 bytes)
 constexpr int kMaxStages = 6;  // ring of item k-blocks (3 of 32 KB per CTA, 6 of 16 KB per CTA of a pair)
 constexpr int kAccStages = 2;  // TMEM accumulator double buffer
 constexpr int kTmemCols = 512;
-constexpr int kEpilogueWarps = 8;   // two per TMEM lane quarter
-constexpr int kThreads = 32 * (2 + kEpilogueWarps);
+constexpr int kMaxColParts = 4;     // epilogue warps per TMEM lane quarter (each takes 256 / parts columns of a tile)
+constexpr int threads_for(int col_parts) { return 32 * (2 + 4 * col_parts); }
 constexpr int kMaxKTc = 32;
 constexpr int kPendingMerge = 16;  // capacity: maxima a row may have waiting (merge threshold - 1 + pieces per tile half)
 constexpr int kDefaultPendingMerge = 8;
@@ -84,8 +84,8 @@ struct __align__(8) Barriers {
 
 // Shared-memory scratch of the epilogue warps.
 struct RowShared {
-  float pending[kEpilogueWarps][kPendingMerge][32];  // piece maxima waiting for the warp's lockstep merge
-  float thr[2][BLOCK_M];                             // [column half][row]: that warp's current threshold
+  float pending[4 * kMaxColParts][kPendingMerge][32];  // piece maxima waiting for the warp's lockstep merge
+  float thr[kMaxColParts][BLOCK_M];                    // [column part][row]: that warp's current threshold
 };
 
 // Dump buffers, per (row, range): `cap` slots of 32 scores + the chunk's first column (relative to the
@@ -94,10 +94,12 @@ struct DumpBuffers {
   float* scores;      // [rows*splits][cap][DUMPW]
   int2* meta;         // [rows*splits][cap]: (first column of the piece relative to the range, bits of the piece's
                       // maximum) — the select kernel reads these first
-  int32_t* count;     // [2][rows*splits]: slots filled from the bottom (columns 0-127 of the tiles) / from the top
-  float* threshold;   // [2][rows*splits]: final threshold of either column half
+  int32_t* count;     // [col_parts][rows*splits]: pieces dumped by each column part
+  float* threshold;   // [col_parts][rows*splits]: final threshold of each column part
   int64_t units;      // rows*splits
-  int cap;
+  int cap;            // slots per (row, range) = (col_parts / 2) sub-buffers of cap_sub slots; two column parts share a
+  int cap_sub;        // sub-buffer and fill it from both ends (no shared counter)
+  int col_parts;
 };
 
 // Work units.  One CTA per SM and one long range per row is the cheapest (every range pays a warm-up
@@ -215,8 +217,9 @@ __device__ __forceinline__ void merge_pending(RowState<KCAP>& st, uint32_t my_pe
   st_shared_f32(thr_own_addr, st.thr);
 }
 
-template <int NUM_KB, int KCAP, bool PAIR>  // DIM / 64, piece maxima tracked per row and half (>= k), CTA pairs
-__global__ void __launch_bounds__(kThreads, 1)
+// NUM_KB = DIM / 64; KCAP = piece maxima tracked per row and column part (>= k); PAIR = CTA pairs; CP = column parts
+template <int NUM_KB, int KCAP, bool PAIR, int CP>
+__global__ void __launch_bounds__(threads_for(CP), 1)
 score_dump_tc_kernel(const __grid_constant__ CUtensorMap map_sess, const __grid_constant__ CUtensorMap map_items,
                      int64_t batch, int64_t num_items, int stages, Schedule sch, DumpBuffers dump,
                      int pending_merge /* <= kPendingMerge */) {
@@ -254,13 +257,13 @@ score_dump_tc_kernel(const __grid_constant__ CUtensorMap map_sess, const __grid_
     for (int s = 0; s < kMaxStages; ++s) { mbar_init(&bars->b_full[s], PAIR ? 2 : 1); mbar_init(&bars->b_empty[s], 1); }
     for (int s = 0; s < kAccStages; ++s) {
       mbar_init(&bars->acc_full[s], 1);
-      mbar_init(&bars->acc_empty[s], PAIR ? 2 * kEpilogueWarps : kEpilogueWarps);
+      mbar_init(&bars->acc_empty[s], PAIR ? 2 * 4 * CP : 4 * CP);
     }
     fence_barrier_init();
     tma_prefetch_desc(&map_sess);
     tma_prefetch_desc(&map_items);
   }
-  for (int i = threadIdx.x; i < 2 * BLOCK_M; i += kThreads) (&rs->thr[0][0])[i] = -INFINITY;
+  for (int i = threadIdx.x; i < kMaxColParts * BLOCK_M; i += threads_for(CP)) (&rs->thr[0][0])[i] = -INFINITY;
   if (warp == 1) {
     if (PAIR) tmem_alloc_2sm(&bars->tmem_base, kTmemCols);
     else tmem_alloc(&bars->tmem_base, kTmemCols);
@@ -338,14 +341,14 @@ score_dump_tc_kernel(const __grid_constant__ CUtensorMap map_sess, const __grid_
       }
     }
   } else {
-    // ========== epilogue: 8 warps; TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 ==========
+    // ========== epilogue: 4 * CP warps; TMEM lane quarter = warp % 4, column part = (warp - 2) / 4 ==========
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int cpart = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;       // session row inside the tile == TMEM lane
     const int64_t grow = (int64_t)m_tile * BLOCK_M + row;
     const bool live = grow < batch;
     const int64_t pidx = live ? sch.part_index(grow, part) : 0;
-    const int64_t slot0 = pidx * (int64_t)dump.cap;
+    const int64_t slot0 = pidx * (int64_t)dump.cap + (cpart >> 1) * dump.cap_sub;   // this pair of parts' sub-buffer
     float* my_scores = dump.scores + slot0 * DUMPW;
     int2* my_meta = dump.meta + slot0;
     RowState<KCAP> st;
@@ -355,52 +358,63 @@ score_dump_tc_kernel(const __grid_constant__ CUtensorMap map_sess, const __grid_
     st.count = 0;
     st.pending = 0;
     const uint32_t my_pending = smem_u32(&rs->pending[warp - 2][0][lane]);
-    const uint32_t thr_own_addr = smem_u32(&rs->thr[half][row]), thr_other_addr = smem_u32(&rs->thr[half ^ 1][row]);
+    const uint32_t thr_row_addr = smem_u32(&rs->thr[0][row]);
+    const uint32_t thr_own_addr = thr_row_addr + (uint32_t)(cpart * BLOCK_M * sizeof(float));
     const uint32_t acc_empty0 = PAIR ? mapa_shared(smem_u32(&bars->acc_empty[0]), 0) : smem_u32(&bars->acc_empty[0]);
-    constexpr int HALF_N = BLOCK_N / 2;
+    constexpr int PART_N = BLOCK_N / CP;
     // loop constants pinned in registers (as kernel parameters they were re-read from the constant bank on the
     // divergent path: ~2 % of the epilogue's stall samples)
-    int cap = dump.cap, merge_at = pending_merge;
-    int slot_first = half ? dump.cap - 1 : 0, slot_step = half ? -1 : 1;
+    int cap = dump.cap_sub, merge_at = pending_merge;
+    int slot_first = (cpart & 1) ? dump.cap_sub - 1 : 0, slot_step = (cpart & 1) ? -1 : 1;
     asm volatile("" : "+r"(cap), "+r"(merge_at), "+r"(slot_first), "+r"(slot_step));
     for (int t = 0; t < num_tiles; ++t) {
       const int acc = t & 1;
       const uint32_t acc_phase = (uint32_t)(t >> 1) & 1;
       mbar_wait(&bars->acc_full[acc], acc_phase);
       tc_fence_after();
-      const int64_t item0 = (tile_begin + t) * BLOCK_N + half * HALF_N;
-      const int limit = num_items - item0 < HALF_N ? (int)(num_items - item0) : HALF_N;  // real columns of this half
-      const int col0 = t * BLOCK_N + half * HALF_N;
+      const int64_t item0 = (tile_begin + t) * BLOCK_N + cpart * PART_N;
+      const int limit = num_items - item0 < PART_N ? (int)(num_items - item0) : PART_N;  // real columns of this part
+      const int col0 = t * BLOCK_N + cpart * PART_N;
       const uint32_t taddr =
-          tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + half * HALF_N);
-      // This warp's columns of the tile go to registers as early as the register file allows (three chunks, the
-      // fourth into the first one's registers once that is worked off) and the accumulator is handed back before
-      // the rest is processed and before any merge: the MMA issuer (which needs all 8 — in a pair 16 — warps to let
-      // go) no longer waits for a warp that is busy in a lockstep merge, and the epilogue gains a tile time of slack.
-      constexpr int NCH = HALF_N / CHUNK;   // 4
-      uint32_t raw[NCH - 1][CHUNK];
+          tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + cpart * PART_N);
+      // This warp's columns of the tile go to registers as early as the register file allows (all chunks but one,
+      // the last into the first one's registers once that is worked off) and the accumulator
+      // is handed back before the rest is processed and before any merge: the MMA issuer (which needs every epilogue
+      // warp — of both CTAs of a pair — to let go) no longer waits for a warp that is busy in a lockstep merge.
+      constexpr int NCH = PART_N / CHUNK;             // 4 or 2
+      constexpr int NBUF = NCH - 1;                   // 3 or 1 (96 registers per thread with 18 warps)
+      uint32_t raw[NBUF][CHUNK];
 #pragma unroll
-      for (int c = 0; c < NCH - 1; ++c) tmem_ld_32x32_issue(taddr + (uint32_t)(c * CHUNK), raw[c]);
-      const float thr_other = ld_shared_f32(thr_other_addr);
+      for (int c = 0; c < NBUF; ++c) tmem_ld_32x32_issue(taddr + (uint32_t)(c * CHUNK), raw[c]);
+      // the other column parts' thresholds: a little stale at worst, still valid bounds
+      float thr_other = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < NCH - 1; ++c) tmem_ld_wait(raw[c]);
-      chunk_hits<KCAP>(raw[0], st, col0, limit, my_scores, my_meta, cap, slot_first, slot_step, my_pending, thr_other);
-      tmem_ld_32x32(taddr + (uint32_t)((NCH - 1) * CHUNK), raw[0]);
+      for (int o = 1; o < CP; ++o)
+        thr_other = fmaxf(thr_other, ld_shared_f32(thr_row_addr + (uint32_t)(((cpart + o) % CP) * BLOCK_M * sizeof(float))));
+#pragma unroll
+      for (int c = 0; c < NBUF; ++c) tmem_ld_wait(raw[c]);
+      if (NCH > NBUF) {
+        chunk_hits<KCAP>(raw[0], st, col0, limit, my_scores, my_meta, cap, slot_first, slot_step, my_pending, thr_other);
+        tmem_ld_32x32(taddr + (uint32_t)(NBUF * CHUNK), raw[0]);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         if (PAIR) mbar_arrive_cluster(acc_empty0 + (uint32_t)(acc * sizeof(uint64_t)));
         else mbar_arrive(&bars->acc_empty[acc]);
       }
-#pragma unroll
-      for (int c = 1; c < NCH; ++c)
-        chunk_hits<KCAP>(raw[c % (NCH - 1)], st, col0 + c * CHUNK, limit - c * CHUNK, my_scores, my_meta, cap,
-                         slot_first, slot_step, my_pending, thr_other);
+      // the lockstep merge (long: up to 15 passes of the sorting network) comes AFTER the hand-back, so that it never
+      // sits between an accumulator becoming ready and this warp letting go of it
       merge_pending<KCAP>(st, my_pending, thr_own_addr, merge_at);
+#pragma unroll
+      for (int c = NCH > NBUF ? 1 : 0; c < NCH; ++c)
+        chunk_hits<KCAP>(raw[c % NBUF], st, col0 + c * CHUNK, limit - c * CHUNK, my_scores, my_meta, cap, slot_first,
+                         slot_step, my_pending, thr_other);
     }
+    merge_pending<KCAP>(st, my_pending, thr_own_addr, 1);   // what is still waiting: the final threshold
     if (live) {
-      dump.count[(int64_t)half * dump.units + pidx] = st.count;
-      dump.threshold[(int64_t)half * dump.units + pidx] = st.thr;
+      dump.count[(int64_t)cpart * dump.units + pidx] = st.count;
+      dump.threshold[(int64_t)cpart * dump.units + pidx] = st.thr;
     }
   }
   tc_fence_before();
@@ -452,20 +466,22 @@ score_select_kernel(DumpBuffers dump, int64_t batch, Schedule sch, int k, int64_
   float tau = -INFINITY;
   bool overflow = false;
   const int splits = sch.parts_of_row(row);
+  const int cparts = dump.col_parts;
   for (int s = 0; s < splits; ++s) {
     const int64_t pi = sch.part_index(row, s);
-    tau = fmaxf(tau, fmaxf(dump.threshold[pi], dump.threshold[dump.units + pi]));
-    overflow = overflow || dump.count[pi] + dump.count[dump.units + pi] > dump.cap;
+    for (int c = 0; c < cparts; c += 2) {
+      tau = fmaxf(tau, fmaxf(dump.threshold[c * dump.units + pi], dump.threshold[(c + 1) * dump.units + pi]));
+      overflow = overflow || dump.count[c * dump.units + pi] + dump.count[(c + 1) * dump.units + pi] > dump.cap_sub;
+    }
   }
   __syncwarp();
   if (!overflow) {
-    for (int seg = 0; seg < 2 * splits; ++seg) {
-      // a part's slot buffer was filled from both ends: pieces of columns 0-127 of every tile from the bottom,
-      // of columns 128-255 from the top
-      const int s = seg >> 1, top = seg & 1;
+    for (int seg = 0; seg < cparts * splits; ++seg) {
+      // a (row, range) slot buffer is col_parts / 2 sub-buffers, each filled from both ends by two column parts
+      const int s = seg / cparts, c = seg % cparts;
       const int64_t pi = sch.part_index(row, s);
-      const int n = dump.count[top * dump.units + pi];
-      const int64_t slot0 = pi * (int64_t)dump.cap + (top ? dump.cap - n : 0);
+      const int n = dump.count[c * dump.units + pi];
+      const int64_t slot0 = pi * (int64_t)dump.cap + (c >> 1) * dump.cap_sub + ((c & 1) ? dump.cap_sub - n : 0);
       const int range_col0 = sch.first_tile(row, s) * BLOCK_N;
       // the piece maxima first (one coalesced 8-byte load per piece): the pieces that reach tau — a few dozen of the
       // ~200 dumped per row — are collected as (slot, first column) pairs ...
@@ -698,7 +714,8 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16*
 struct TcPlan {
   Schedule sch;
   int grid;
-  int cap;
+  int cap, cap_sub;
+  int col_parts;   // epilogue warps per TMEM lane quarter: 2 (default) or 4
   bool pairs;   // CTA pairs (cta_group::2): a row tile is 256 rows, grid = 2 x units, workers = 74 SM pairs
 };
 
@@ -710,9 +727,20 @@ bool use_cta_pairs() {
   return on;
 }
 
+int epilogue_col_parts() {
+  static const int parts = [] {
+    // two epilogue warps per lane quarter; 4 (comparison knob) was measured slower: 350 instead of 215 dumped pieces
+    // per row (four lists over a quarter of the pieces each) and 0.93 instead of 0.75 ms
+    const char* e = getenv("ETPGT_SCORE_EPI");
+    return e != nullptr && atoi(e) == 4 ? 4 : 2;
+  }();
+  return parts;
+}
+
 TcPlan tc_plan(int64_t batch, int64_t num_items, int k) {
   TcPlan p;
   p.pairs = use_cta_pairs();
+  p.col_parts = epilogue_col_parts();
   const int unit_rows = p.pairs ? 2 * BLOCK_M : BLOCK_M;
   const int workers = p.pairs ? kNumSMs / 2 : kNumSMs;
   const int m_tiles = (int)((batch + unit_rows - 1) / unit_rows);
@@ -745,19 +773,22 @@ TcPlan tc_plan(int64_t batch, int64_t num_items, int k) {
   p.sch.tiles_per_split = (total_tiles + splits - 1) / splits;
   p.sch.tail_splits = (total_tiles + p.sch.tiles_per_split - 1) / p.sch.tiles_per_split;
   p.grid = (m_full + tail * p.sch.tail_splits) * (p.pairs ? 2 : 1);
-  // slots per (row, range): either column half keeps its own list over half of the pieces, so
-  // ~ 2*K*(1 + ln(pieces/(2K))) pieces are expected (+ ~25 % from the lockstep merges); 1.6x head-room (sized
+  // slots per (row, range): every column part keeps its own list over its share of the pieces, so
+  // ~ P*K*(1 + ln(pieces/(P*K))) pieces are expected (+ ~25 % from the lockstep merges); 1.6x head-room (sized
   // for the longest range), overflow is handled exactly by the fallback kernel
   const double chunks = (double)(m_full > 0 ? total_tiles : p.sch.tiles_per_split) * (BLOCK_N / DUMPW);
   const int kc = k <= 10 ? 10 : k <= 20 ? 20 : 32;
-  double expect = 2.0 * kc * (1.0 + (chunks > 2.0 * kc ? log(chunks / (2.0 * kc)) : 0.0));
+  const double lists = (double)p.col_parts * kc;
+  double expect = lists * (1.0 + (chunks > lists ? log(chunks / lists) : 0.0));
   int cap = (int)(1.6 * expect) + 16;
   if (cap > (int)chunks) cap = (int)chunks;
   if (const char* forced = getenv("ETPGT_SCORE_CAP")) {  // test hook: force slot-buffer overflow
     const int f = atoi(forced);
     if (f >= 1) cap = f;
   }
-  p.cap = cap < 1 ? 1 : cap;
+  const int subs = p.col_parts / 2;
+  p.cap_sub = (cap + subs - 1) / subs < 1 ? 1 : (cap + subs - 1) / subs;
+  p.cap = p.cap_sub * subs;
   return p;
 }
 
@@ -785,7 +816,7 @@ extern "C" size_t etpgt_score_topk_bf16_workspace_bytes(int64_t batch, int64_t n
   const TcPlan p = tc_plan(batch, num_items, k);
   const size_t units = (size_t)p.sch.num_parts(batch);
   return align_up(units * p.cap * DUMPW * sizeof(float)) + align_up(units * p.cap * sizeof(int2)) +
-         4 * align_up(units * sizeof(float)) + 2 * align_up((size_t)batch * sizeof(int32_t)) + 256;
+         2 * align_up(kMaxColParts * units * sizeof(float)) + 2 * align_up((size_t)batch * sizeof(int32_t)) + 256;
 }
 
 extern "C" int etpgt_score_topk_bf16_eval(const void* sess_bf16, const void* table_bf16, int64_t batch,
@@ -812,10 +843,12 @@ extern "C" int etpgt_score_topk_bf16_eval(const void* sess_bf16, const void* tab
   DumpBuffers dump;
   dump.scores = w.take<float>(units * p.cap * DUMPW);
   dump.meta = w.take<int2>(units * p.cap);
-  dump.count = w.take<int32_t>(2 * units);
-  dump.threshold = w.take<float>(2 * units);
+  dump.count = w.take<int32_t>(kMaxColParts * units);
+  dump.threshold = w.take<float>(kMaxColParts * units);
   dump.units = (int64_t)units;
   dump.cap = p.cap;
+  dump.cap_sub = p.cap_sub;
+  dump.col_parts = p.col_parts;
   int32_t* redo = w.take<int32_t>(batch);
   CUtensorMap map_sess, map_items;
   if (!make_map_bf16(&map_sess, sess_bf16, batch, dim, dim, BLOCK_M) ||
@@ -833,7 +866,7 @@ extern "C" int etpgt_score_topk_bf16_eval(const void* sess_bf16, const void* tab
   const size_t smem = tc_smem_bytes(num_kb, stages, p.pairs);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(p.grid);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(threads_for(p.col_parts));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -843,11 +876,17 @@ extern "C" int etpgt_score_topk_bf16_eval(const void* sess_bf16, const void* tab
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-#define LAUNCH3(NKB, KC, PR)                                                                                          \
-  {                                                                                                                   \
-    cudaFuncSetAttribute(score_dump_tc_kernel<NKB, KC, PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    cudaLaunchKernelEx(&cfg, score_dump_tc_kernel<NKB, KC, PR>, map_sess, map_items, batch, num_items, stages, p.sch, \
-                       dump, pending_merge);                                                                          \
+#define LAUNCH4(NKB, KC, PR, CP_)                                                                                  \
+  {                                                                                                                \
+    cudaFuncSetAttribute(score_dump_tc_kernel<NKB, KC, PR, CP_>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                         (int)smem);                                                                               \
+    cudaLaunchKernelEx(&cfg, score_dump_tc_kernel<NKB, KC, PR, CP_>, map_sess, map_items, batch, num_items, stages, \
+                       p.sch, dump, pending_merge);                                                                \
+  }
+#define LAUNCH3(NKB, KC, PR)                    \
+  {                                             \
+    if (p.col_parts == 4) LAUNCH4(NKB, KC, PR, 4) \
+    else LAUNCH4(NKB, KC, PR, 2)                \
   }
 #define LAUNCH2(NKB, KC)                  \
   {                                       \
@@ -875,6 +914,7 @@ extern "C" int etpgt_score_topk_bf16_eval(const void* sess_bf16, const void* tab
 #undef LAUNCH
 #undef LAUNCH2
 #undef LAUNCH3
+#undef LAUNCH4
   ETPGT_CHECK_LAUNCH("score_dump_tc");
   if (stats) cudaEventRecord(ev[1], stream);
   score_select_kernel<<<(unsigned)((batch + kSelectWarps - 1) / kSelectWarps), kSelectWarps * 32, 0, stream>>>(
@@ -891,7 +931,7 @@ extern "C" int etpgt_score_topk_bf16_eval(const void* sess_bf16, const void* tab
       dim, k, id_base, redo, top_val, top_idx, targets, hit_pos);
   ETPGT_CHECK_LAUNCH("score_redo");
   if (stats) {   // dump volume, fallback rows, kernel times
-    std::vector<int32_t> h_redo(batch), h_count(2 * units);
+    std::vector<int32_t> h_redo(batch), h_count(kMaxColParts * units);
     cudaStreamSynchronize(stream);
     float ms_dump = 0.f, ms_select = 0.f;
     cudaEventElapsedTime(&ms_dump, ev[0], ev[1]);
@@ -899,11 +939,12 @@ extern "C" int etpgt_score_topk_bf16_eval(const void* sess_bf16, const void* tab
     for (auto& e : ev) cudaEventDestroy(e);
     fprintf(stderr, "score_topk_bf16: dump %.3f ms, select %.3f ms\n", ms_dump, ms_select);
     cudaMemcpy(h_redo.data(), redo, batch * sizeof(int32_t), cudaMemcpyDeviceToHost);
-    cudaMemcpy(h_count.data(), dump.count, 2 * units * sizeof(int32_t), cudaMemcpyDeviceToHost);
+    cudaMemcpy(h_count.data(), dump.count, kMaxColParts * units * sizeof(int32_t), cudaMemcpyDeviceToHost);
     int64_t redo_rows = 0, pieces = 0, worst = 0;
     for (int64_t i = 0; i < batch; ++i) redo_rows += h_redo[i];
     for (size_t i = 0; i < units; ++i) {
-      const int64_t c = (int64_t)h_count[i] + h_count[units + i];
+      int64_t c = 0;
+      for (int cp = 0; cp < p.col_parts; ++cp) c += h_count[(size_t)cp * units + i];
       pieces += c;
       worst = c > worst ? c : worst;
     }

@@ -80,6 +80,8 @@ class _SymLaplacian:
         """alpha * (L x) + beta * x + gamma * z for x, z [n, b] fp64 contiguous, b <= 32."""
         from .._lib import call, ptr, stream
 
+        x = x.contiguous()                       # torch.linalg.qr hands back column-major factors
+        z = None if z is None else z.contiguous()
         y = torch.empty_like(x)
         call("etpgt_lap_sym_block", ptr(self.rowptr), ptr(self.col), ptr(self.scale), self.n, x.size(1), ptr(x),
              ptr(z), float(alpha), float(beta), float(gamma), ptr(y), stream())
