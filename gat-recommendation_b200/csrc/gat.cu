@@ -9,6 +9,8 @@
 // add_self_loops).  Gather-bound: W*4 B per edge + 2*W*4 B per node forward.
 #include <math.h>
 
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace etpgt {
@@ -27,6 +29,20 @@ __device__ __forceinline__ void load_row(const float* __restrict__ row, int lig,
 #pragma unroll
   for (int v = 0; v < RowGeom<W>::V; ++v) dst[v] = ldg4(row + 4 * (v * RowGeom<W>::LPN + lig));
 }
+// the gradient row of the per-head result when only d(head mean) [N, C] exists: d_agg[n, h, c] = d_out[n, c] / H
+template <int W, int C>
+__device__ __forceinline__ void load_grad_row(const float* __restrict__ d_agg, const float* __restrict__ d_out_mean,
+                                              int64_t node, int lig, float4 (&dst)[RowGeom<W>::V]) {
+  if (d_out_mean == nullptr) {
+    load_row<W>(d_agg + node * W, lig, dst);
+    return;
+  }
+  constexpr int HEAD_F4 = C / 4;
+  const float inv = 1.f / (float)(W / C);
+#pragma unroll
+  for (int v = 0; v < RowGeom<W>::V; ++v)
+    dst[v] = scale4(inv, ldg4(d_out_mean + node * C + 4 * ((v * RowGeom<W>::LPN + lig) % HEAD_F4)));
+}
 
 __device__ __forceinline__ float leaky(float z, float slope) { return z > 0.f ? z : slope * z; }
 
@@ -37,7 +53,7 @@ gat_fwd_kernel(const float* __restrict__ h, const float* __restrict__ a_src, con
                int64_t num_nodes, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                const int32_t* __restrict__ eperm, float slope, const float* __restrict__ mask_edges,
                const float* __restrict__ mask_self, float* __restrict__ agg, float* __restrict__ m_out,
-               float* __restrict__ invl_out) {
+               float* __restrict__ invl_out, const float* __restrict__ bias, float* __restrict__ out_mean) {
   using G = GatGeom<W>;
   constexpr int V = G::V, LPN = G::LPN, HEADS = W / C, HEAD_F4 = C / 4, U = G::UNROLL;
   const int lane = threadIdx.x & 31;
@@ -89,8 +105,27 @@ gat_fwd_kernel(const float* __restrict__ h, const float* __restrict__ a_src, con
   for (int v = 0; v < V; ++v) {
     const float inv = 1.f / (l[v] + kSoftmaxEps);
     const int f = v * LPN + lig;
-    st4(agg + node * W + 4 * f, scale4(inv, acc[v]));
+    acc[v] = scale4(inv, acc[v]);
+    st4(agg + node * W + 4 * f, acc[v]);
     if (f % HEAD_F4 == 0) { m_out[node * HEADS + hd[v]] = m[v]; invl_out[node * HEADS + hd[v]] = inv; }
+  }
+  // concat=False (etpgt/model/gat.py:100-109): mean over the heads + bias, written next to the per-head rows (kept
+  // for the backward pass).  When a head spans whole lane-group rounds (C/4 a multiple of the lanes per node) the
+  // H values of an output column sit in the same lane: no shuffles, no second pass over [N, heads*C].
+  if constexpr (HEAD_F4 % LPN == 0) {
+    if (out_mean != nullptr) {
+      constexpr int VH = HEAD_F4 / LPN;   // float4 slots per head and lane
+#pragma unroll
+      for (int vv = 0; vv < VH; ++vv) {
+        float4 s = acc[vv];
+#pragma unroll
+        for (int hh = 1; hh < HEADS; ++hh) s = add4(s, acc[hh * VH + vv]);   // head order 0..H-1, as the separate pass
+        s = scale4(1.f / (float)HEADS, s);
+        const int f = vv * LPN + lig;
+        if (bias != nullptr) s = add4(s, ldg4(bias + 4 * f));
+        st4(out_mean + node * C + 4 * f, s);
+      }
+    }
   }
 }
 
@@ -106,7 +141,7 @@ gat_bwd_dst_kernel(const float* __restrict__ h, const float* __restrict__ a_src,
                    const int32_t* __restrict__ eperm, float slope, const float* __restrict__ mask_edges,
                    const float* __restrict__ mask_self, const float* __restrict__ m_in,
                    const float* __restrict__ invl_in, float2* __restrict__ ecoef, float2* __restrict__ self_coef,
-                   float* __restrict__ d_a_dst) {
+                   float* __restrict__ d_a_dst, const float* __restrict__ d_out_mean) {
   using G = GatGeom<W>;
   constexpr int V = G::V, LPN = G::LPN, HEADS = W / C, HEAD_F4 = C / 4, U = G::UNROLL;
   const int lane = threadIdx.x & 31;
@@ -122,7 +157,7 @@ gat_bwd_dst_kernel(const float* __restrict__ h, const float* __restrict__ a_src,
   float4 g[V];
   {
     float4 ag[V];
-    load_row<W>(d_agg + nrow * W, lig, g);
+    load_grad_row<W, C>(d_agg, d_out_mean, nrow, lig, g);
     load_row<W>(agg + nrow * W, lig, ag);
 #pragma unroll
     for (int v = 0; v < V; ++v) {
@@ -197,7 +232,8 @@ __global__ void __launch_bounds__(kThreads)
 gat_bwd_src_kernel(const float* __restrict__ d_agg, int64_t num_nodes, const int32_t* __restrict__ colptr,
                    const int32_t* __restrict__ row, const int32_t* __restrict__ cpos,
                    const float2* __restrict__ ecoef, const float2* __restrict__ self_coef,
-                   float* __restrict__ d_h, float* __restrict__ d_a_src) {
+                   float* __restrict__ d_h, float* __restrict__ d_a_src, const float* __restrict__ d_out_mean,
+                   __nv_bfloat16* __restrict__ d_h_hi, __nv_bfloat16* __restrict__ d_h_lo) {
   using G = GatGeom<W>;
   constexpr int V = G::V, LPN = G::LPN, HEADS = W / C, HEAD_F4 = C / 4;
   const int lane = threadIdx.x & 31;
@@ -207,7 +243,7 @@ gat_bwd_src_kernel(const float* __restrict__ d_agg, int64_t num_nodes, const int
   int hd[V];
   float dsum[V];
   float4 acc[V], g[V];
-  load_row<W>(d_agg + node * W, lig, g);
+  load_grad_row<W, C>(d_agg, d_out_mean, node, lig, g);
 #pragma unroll
   for (int v = 0; v < V; ++v) {
     hd[v] = head_of<W, C>(v, lig);
@@ -219,7 +255,7 @@ gat_bwd_src_kernel(const float* __restrict__ d_agg, int64_t num_nodes, const int
   for (int p = begin; p < end; ++p) {
     const int64_t i = row[p];
     const int64_t e = cpos[p];
-    load_row<W>(d_agg + i * W, lig, g);
+    load_grad_row<W, C>(d_agg, d_out_mean, i, lig, g);   // [N, C]: a quarter of the gathered bytes at four heads
 #pragma unroll
     for (int v = 0; v < V; ++v) {
       const float2 c = ecoef[e * HEADS + hd[v]];  // (0,0) for dropped self loops
@@ -230,7 +266,22 @@ gat_bwd_src_kernel(const float* __restrict__ d_agg, int64_t num_nodes, const int
 #pragma unroll
   for (int v = 0; v < V; ++v) {
     const int f = v * LPN + lig;
-    st4(d_h + node * W + 4 * f, acc[v]);
+    if (d_h_hi != nullptr) {   // straight to the split-bf16 operands of the two projection-gradient GEMMs
+      const float e[4] = {acc[v].x, acc[v].y, acc[v].z, acc[v].w};
+      uint32_t hw[2], lw[2];
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(e[2 * t]), h1 = __float2bfloat16_rn(e[2 * t + 1]);
+        const __nv_bfloat16 l0 = __float2bfloat16_rn(e[2 * t] - __bfloat162float(h0));
+        const __nv_bfloat16 l1 = __float2bfloat16_rn(e[2 * t + 1] - __bfloat162float(h1));
+        hw[t] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        lw[t] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+      }
+      *reinterpret_cast<uint2*>(d_h_hi + node * W + 4 * f) = make_uint2(hw[0], hw[1]);
+      *reinterpret_cast<uint2*>(d_h_lo + node * W + 4 * f) = make_uint2(lw[0], lw[1]);
+    } else {
+      st4(d_h + node * W + 4 * f, acc[v]);
+    }
     if (f % HEAD_F4 == 0) d_a_src[node * HEADS + hd[v]] = dsum[v];
   }
 }
@@ -268,12 +319,13 @@ sage_mean_fwd_kernel(const float* __restrict__ x, int64_t num_nodes, const int32
   for (int v = 0; v < V; ++v) st4(mean + node * DIM + 4 * (v * LPN + lig), scale4(inv, acc[v]));
 }
 
-// d_x_j = sum over out-edges (j -> i) of d_mean_i / indeg(i)
+// d_x_j = sum over out-edges (j -> i) of d_mean_i / indeg(i)  (+ d_root_j: the lin_r branch of SAGEConv, when the two
+// gradients arrive as the column halves of one [N, 2*DIM] GEMM output — `ld` is that pitch)
 template <int DIM>
 __global__ void __launch_bounds__(kThreads)
-sage_mean_bwd_kernel(const float* __restrict__ d_mean, int64_t num_nodes, const int32_t* __restrict__ rowptr,
-                     const int32_t* __restrict__ colptr, const int32_t* __restrict__ row,
-                     float* __restrict__ d_x) {
+sage_mean_bwd_kernel(const float* __restrict__ d_mean, int64_t ld, const float* __restrict__ d_root,
+                     int64_t num_nodes, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colptr,
+                     const int32_t* __restrict__ row, float* __restrict__ d_x) {
   using G = RowGeom<DIM>;
   constexpr int V = G::V, LPN = G::LPN;
   const int lane = threadIdx.x & 31;
@@ -282,12 +334,13 @@ sage_mean_bwd_kernel(const float* __restrict__ d_mean, int64_t num_nodes, const 
   if (node >= num_nodes) return;
   float4 acc[V];
 #pragma unroll
-  for (int v = 0; v < V; ++v) acc[v] = zero4();
+  for (int v = 0; v < V; ++v)
+    acc[v] = d_root != nullptr ? ldg4(d_root + node * ld + 4 * (v * LPN + lig)) : zero4();
   for (int p = colptr[node]; p < colptr[node + 1]; ++p) {
     const int64_t i = row[p];
     const float inv = 1.f / (float)(rowptr[i + 1] - rowptr[i]);
 #pragma unroll
-    for (int v = 0; v < V; ++v) acc[v] = fma4(inv, ldg4(d_mean + i * DIM + 4 * (v * LPN + lig)), acc[v]);
+    for (int v = 0; v < V; ++v) acc[v] = fma4(inv, ldg4(d_mean + i * ld + 4 * (v * LPN + lig)), acc[v]);
   }
 #pragma unroll
   for (int v = 0; v < V; ++v) st4(d_x + node * DIM + 4 * (v * LPN + lig), acc[v]);
@@ -312,19 +365,30 @@ using namespace etpgt;
       return ETPGT_EINVAL;                                                                          \
   }
 
-extern "C" int etpgt_gat_fwd(const float* h, const float* a_src, const float* a_dst, int64_t num_nodes, int width,
-                             int heads, const int32_t* rowptr, const int32_t* col, const int32_t* eperm,
-                             float negative_slope, const float* mask_edges, const float* mask_self, float* agg,
-                             float* m, float* inv_l, etpgt_stream_t stream_) {
+extern "C" int etpgt_gat_mean_fused_supported(int width, int heads) {
+  if (heads < 1 || width % heads != 0) return 0;
+  const int lpn = width / 4 < 32 ? width / 4 : 32;
+  return lpn > 0 && (width / heads / 4) % lpn == 0 ? 1 : 0;
+}
+
+extern "C" int etpgt_gat_fwd_mean(const float* h, const float* a_src, const float* a_dst, int64_t num_nodes, int width,
+                                  int heads, const int32_t* rowptr, const int32_t* col, const int32_t* eperm,
+                                  float negative_slope, const float* mask_edges, const float* mask_self,
+                                  const float* bias, float* agg, float* m, float* inv_l, float* out_mean,
+                                  etpgt_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ETPGT_REQUIRE(num_nodes >= 0 && h && a_src && a_dst && rowptr && agg && m && inv_l, "gat_fwd: bad arguments");
   ETPGT_REQUIRE((mask_edges == nullptr) == (mask_self == nullptr), "gat_fwd: pass both masks or neither");
+  ETPGT_REQUIRE(out_mean == nullptr || etpgt_gat_mean_fused_supported(width, heads),
+                "gat_fwd_mean: the fused head mean needs channels/4 to be a multiple of the lanes per node "
+                "(width=%d heads=%d)", width, heads);
   if (num_nodes == 0) return ETPGT_OK;
 #define CALL(W, C)                                                                                        \
   {                                                                                                       \
     const int64_t npc = (kThreads / 32) * RowGeom<W>::GROUPS;                                             \
     gat_fwd_kernel<W, C><<<(unsigned)((num_nodes + npc - 1) / npc), kThreads, 0, stream>>>(                \
-        h, a_src, a_dst, num_nodes, rowptr, col, eperm, negative_slope, mask_edges, mask_self, agg, m, inv_l); \
+        h, a_src, a_dst, num_nodes, rowptr, col, eperm, negative_slope, mask_edges, mask_self, agg, m, inv_l, bias, \
+        out_mean);                                                                                        \
   }
   ETPGT_DISPATCH_GAT(width, heads, CALL)
 #undef CALL
@@ -332,21 +396,33 @@ extern "C" int etpgt_gat_fwd(const float* h, const float* a_src, const float* a_
   return ETPGT_OK;
 }
 
+extern "C" int etpgt_gat_fwd(const float* h, const float* a_src, const float* a_dst, int64_t num_nodes, int width,
+                             int heads, const int32_t* rowptr, const int32_t* col, const int32_t* eperm,
+                             float negative_slope, const float* mask_edges, const float* mask_self, float* agg,
+                             float* m, float* inv_l, etpgt_stream_t stream) {
+  return etpgt_gat_fwd_mean(h, a_src, a_dst, num_nodes, width, heads, rowptr, col, eperm, negative_slope, mask_edges,
+                            mask_self, nullptr, agg, m, inv_l, nullptr, stream);
+}
+
 extern "C" size_t etpgt_gat_bwd_workspace_bytes(int64_t num_nodes, int64_t num_edges, int heads) {
   return align_up((size_t)(num_edges > 0 ? num_edges : 1) * heads * sizeof(float2)) +
          align_up((size_t)(num_nodes > 0 ? num_nodes : 1) * heads * sizeof(float2)) + 256;
 }
 
-extern "C" int etpgt_gat_bwd(const float* h, const float* a_src, const float* a_dst, const float* d_agg,
-                             const float* agg, int64_t num_nodes, int width, int heads, const int32_t* rowptr,
-                             const int32_t* col, const int32_t* eperm, const int32_t* colptr, const int32_t* row,
-                             const int32_t* cpos, int64_t num_edges, float negative_slope, const float* mask_edges,
-                             const float* mask_self, const float* m, const float* inv_l, float* d_h,
-                             float* d_a_src, float* d_a_dst, void* ws, size_t ws_bytes, etpgt_stream_t stream_) {
+extern "C" int etpgt_gat_bwd_mean(const float* h, const float* a_src, const float* a_dst, const float* d_agg,
+                                  const float* d_out_mean, const float* agg, int64_t num_nodes, int width, int heads,
+                                  const int32_t* rowptr, const int32_t* col, const int32_t* eperm,
+                                  const int32_t* colptr, const int32_t* row, const int32_t* cpos, int64_t num_edges,
+                                  float negative_slope, const float* mask_edges, const float* mask_self,
+                                  const float* m, const float* inv_l, float* d_h, void* d_h_hi, void* d_h_lo,
+                                  float* d_a_src, float* d_a_dst, void* ws, size_t ws_bytes,
+                                  etpgt_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  ETPGT_REQUIRE(num_nodes >= 0 && num_edges >= 0 && h && a_src && a_dst && d_agg && agg && rowptr && colptr && m &&
-                    inv_l && d_h && d_a_src && d_a_dst,
-                "gat_bwd: bad arguments");
+  ETPGT_REQUIRE(num_nodes >= 0 && num_edges >= 0 && h && a_src && a_dst && agg && rowptr && colptr && m &&
+                    inv_l && d_a_src && d_a_dst && (d_agg != nullptr) != (d_out_mean != nullptr),
+                "gat_bwd: bad arguments (exactly one of d_agg [N, heads*C] and d_out_mean [N, C])");
+  ETPGT_REQUIRE((d_h != nullptr) != (d_h_hi != nullptr) && (d_h_hi == nullptr) == (d_h_lo == nullptr),
+                "gat_bwd: the projection gradient goes EITHER to d_h (fp32) or to d_h_hi / d_h_lo (split bf16)");
   ETPGT_REQUIRE((mask_edges == nullptr) == (mask_self == nullptr), "gat_bwd: pass both masks or neither");
   if (ws_bytes < etpgt_gat_bwd_workspace_bytes(num_nodes, num_edges, heads)) {
     set_error("gat_bwd: workspace too small");
@@ -362,15 +438,28 @@ extern "C" int etpgt_gat_bwd(const float* h, const float* a_src, const float* a_
     const unsigned grid = (unsigned)((num_nodes + npc - 1) / npc);                                          \
     gat_bwd_dst_kernel<W, C><<<grid, kThreads, 0, stream>>>(h, a_src, a_dst, d_agg, agg, num_nodes, rowptr, col, eperm, \
                                                            negative_slope, mask_edges, mask_self, m, inv_l, ecoef, \
-                                                           self_coef, d_a_dst);                             \
+                                                           self_coef, d_a_dst, d_out_mean);                 \
     gat_bwd_src_kernel<W, C><<<grid, kThreads, 0, stream>>>(d_agg, num_nodes, colptr, row, cpos, ecoef, self_coef, d_h, \
-                                                           d_a_src);                                        \
+                                                           d_a_src, d_out_mean, static_cast<__nv_bfloat16*>(d_h_hi), \
+                                                           static_cast<__nv_bfloat16*>(d_h_lo));             \
   }
   ETPGT_DISPATCH_GAT(width, heads, CALL)
 #undef CALL
   ETPGT_CHECK_LAUNCH("gat_bwd");
   count_launch(1);
   return ETPGT_OK;
+}
+
+extern "C" int etpgt_gat_bwd(const float* h, const float* a_src, const float* a_dst, const float* d_agg,
+                             const float* agg, int64_t num_nodes, int width, int heads, const int32_t* rowptr,
+                             const int32_t* col, const int32_t* eperm, const int32_t* colptr, const int32_t* row,
+                             const int32_t* cpos, int64_t num_edges, float negative_slope, const float* mask_edges,
+                             const float* mask_self, const float* m, const float* inv_l, float* d_h,
+                             float* d_a_src, float* d_a_dst, void* ws, size_t ws_bytes, etpgt_stream_t stream) {
+  ETPGT_REQUIRE(d_agg != nullptr, "gat_bwd: bad arguments");
+  return etpgt_gat_bwd_mean(h, a_src, a_dst, d_agg, nullptr, agg, num_nodes, width, heads, rowptr, col, eperm, colptr,
+                            row, cpos, num_edges, negative_slope, mask_edges, mask_self, m, inv_l, d_h, nullptr, nullptr,
+                            d_a_src, d_a_dst, ws, ws_bytes, stream);
 }
 
 extern "C" int etpgt_sage_mean_fwd(const float* x, int64_t num_nodes, int dim, const int32_t* rowptr,
@@ -391,20 +480,28 @@ extern "C" int etpgt_sage_mean_fwd(const float* x, int64_t num_nodes, int dim, c
   return ETPGT_OK;
 }
 
-extern "C" int etpgt_sage_mean_bwd(const float* d_mean, int64_t num_nodes, int dim, const int32_t* rowptr,
-                                   const int32_t* colptr, const int32_t* row, float* d_x, etpgt_stream_t stream_) {
+extern "C" int etpgt_sage_mean_bwd_ld(const float* d_mean, int64_t ld, const float* d_root, int64_t num_nodes, int dim,
+                                      const int32_t* rowptr, const int32_t* colptr, const int32_t* row, float* d_x,
+                                      etpgt_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ETPGT_REQUIRE(supported_dim(dim), "sage_mean_bwd: unsupported dim %d", dim);
-  ETPGT_REQUIRE(num_nodes >= 0 && d_mean && rowptr && colptr && d_x, "sage_mean_bwd: bad arguments");
+  ETPGT_REQUIRE(num_nodes >= 0 && d_mean && rowptr && colptr && d_x && ld >= dim && ld % 4 == 0,
+                "sage_mean_bwd: bad arguments");
   if (num_nodes == 0) return ETPGT_OK;
 #define CALL(D)                                                                                              \
   {                                                                                                          \
     const int64_t npc = (kThreads / 32) * RowGeom<D>::GROUPS;                                                \
-    sage_mean_bwd_kernel<D><<<(unsigned)((num_nodes + npc - 1) / npc), kThreads, 0, stream>>>(d_mean, num_nodes,  \
-                                                                                             rowptr, colptr, row, d_x); \
+    sage_mean_bwd_kernel<D><<<(unsigned)((num_nodes + npc - 1) / npc), kThreads, 0, stream>>>(d_mean, ld, d_root, \
+                                                                                             num_nodes, rowptr, colptr, \
+                                                                                             row, d_x);      \
   }
   ETPGT_DISPATCH_DIM(dim, CALL)
 #undef CALL
   ETPGT_CHECK_LAUNCH("sage_mean_bwd");
   return ETPGT_OK;
+}
+
+extern "C" int etpgt_sage_mean_bwd(const float* d_mean, int64_t num_nodes, int dim, const int32_t* rowptr,
+                                   const int32_t* colptr, const int32_t* row, float* d_x, etpgt_stream_t stream) {
+  return etpgt_sage_mean_bwd_ld(d_mean, dim, nullptr, num_nodes, dim, rowptr, colptr, row, d_x, stream);
 }

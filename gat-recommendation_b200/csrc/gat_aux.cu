@@ -76,6 +76,76 @@ __global__ void gat_scores_bwd_kernel(const float* __restrict__ h, const float* 
   }
 }
 
+// Attention scalars straight from the layer INPUT: a_src[n,h] = <lin(x)[n,h,:], att_src[h,:]> = <x[n,:], u[h,:]> with
+// u[h,:] = W_h^T att_src[h,:] (a [heads, in] fold of two parameters, made by the caller).  Reads the [N, in] input
+// instead of the [N, heads*C] projection (a quarter of the bytes at heads = 4), and — more importantly — its
+// backward no longer touches d(lin(x)): d_x += d_a u, d_u = d_a^T x.  One warp per node; u[r,:] for r < R = 2*heads
+// rows (sources then destinations) comes from L1.
+template <int R>
+__global__ void __launch_bounds__(kThreads)
+rows_dot_fwd_kernel(const float* __restrict__ x, const float* __restrict__ u, int64_t n, int dim,
+                    float* __restrict__ a_src, float* __restrict__ a_dst) {
+  const int lane = threadIdx.x & 31;
+  const int f4 = dim / 4;
+  for (int64_t node = (blockIdx.x * (int64_t)kThreads + threadIdx.x) >> 5; node < n;
+       node += ((int64_t)gridDim.x * kThreads) >> 5) {
+    float p[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) p[r] = 0.f;
+    for (int f = lane; f < f4; f += 32) {
+      const float4 xv = ldg4(x + node * dim + 4 * f);
+#pragma unroll
+      for (int r = 0; r < R; ++r) p[r] += dot4(xv, ldg4(u + (int64_t)r * dim + 4 * f));
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) p[r] = group_sum<32>(p[r]);
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < R / 2; ++r) {
+        a_src[node * (R / 2) + r] = p[r];
+        a_dst[node * (R / 2) + r] = p[R / 2 + r];
+      }
+    }
+  }
+}
+
+// d_x[n,:] = sum_r d_a[n,r] u[r,:]  (written, the caller's GEMM adds dY W onto it);
+// partial[cta][r][:] = sum over the CTA's rows of d_a[n,r] x[n,:]  (d_u, reduced in a fixed order)
+// blockDim = (dim/4, rows): thread (tx, ty) owns float4 column tx for rows ty, ty+RY, ... of the CTA's chunk.
+template <int R>
+__global__ void rows_dot_bwd_kernel(const float* __restrict__ x, const float* __restrict__ u,
+                                    const float* __restrict__ d_a_src, const float* __restrict__ d_a_dst, int64_t n,
+                                    int dim, int64_t chunk, float* __restrict__ d_x, float* __restrict__ partial) {
+  extern __shared__ float sm[];  // [blockDim.y][R][dim]
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  float4 uv[R], g[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) { uv[r] = ldg4(u + (int64_t)r * dim + 4 * tx); g[r] = zero4(); }
+  const int64_t begin = blockIdx.x * chunk;
+  const int64_t end = begin + chunk < n ? begin + chunk : n;
+  for (int64_t row = begin + ty; row < end; row += blockDim.y) {
+    const float4 xv = ldg4(x + row * dim + 4 * tx);
+    float4 dx = zero4();
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float d = r < R / 2 ? d_a_src[row * (R / 2) + r] : d_a_dst[row * (R / 2) + r - R / 2];
+      dx = fma4(d, uv[r], dx);
+      g[r] = fma4(d, xv, g[r]);
+    }
+    st4(d_x + row * dim + 4 * tx, dx);
+  }
+  float* mine = sm + (size_t)ty * R * dim;
+#pragma unroll
+  for (int r = 0; r < R; ++r) st4(mine + (size_t)r * dim + 4 * tx, g[r]);
+  __syncthreads();
+  const int tid = ty * blockDim.x + tx;
+  for (int i = tid; i < R * dim; i += blockDim.x * blockDim.y) {
+    float t = 0.f;
+    for (int yy = 0; yy < (int)blockDim.y; ++yy) t += sm[(size_t)yy * R * dim + i];
+    partial[(int64_t)blockIdx.x * R * dim + i] = t;
+  }
+}
+
 // out[n,c] = (1/H) sum_h agg[n,h,c] + bias[c]
 __global__ void __launch_bounds__(kThreads)
 head_mean_fwd_kernel(const float* __restrict__ agg, const float* __restrict__ bias, int64_t total4, int c4, int heads,
@@ -105,9 +175,11 @@ __global__ void head_mean_bwd_kernel(const float* __restrict__ d_out, int64_t n,
   for (int64_t r = begin + ty; r < end; r += blockDim.y) {
     const float4 g = ldg4(d_out + (r * c4 + tx) * 4);
     acc = add4(acc, g);
-    const float4 gi = scale4(inv, g);
-    float* row = d_agg + (r * heads) * (int64_t)(4 * c4) + 4 * tx;
-    for (int hd = 0; hd < heads; ++hd) st4(row + (int64_t)hd * 4 * c4, gi);
+    if (d_agg != nullptr) {   // (NULL: only the bias gradient — the fused GAT backward expands d_out in registers)
+      const float4 gi = scale4(inv, g);
+      float* row = d_agg + (r * heads) * (int64_t)(4 * c4) + 4 * tx;
+      for (int hd = 0; hd < heads; ++hd) st4(row + (int64_t)hd * 4 * c4, gi);
+    }
   }
   st4(sm + (size_t)ty * 4 * c4 + 4 * tx, acc);
   __syncthreads();
@@ -196,6 +268,70 @@ extern "C" int etpgt_gat_scores_bwd(const float* h, const float* att_src, const 
   return ETPGT_OK;
 }
 
+extern "C" size_t etpgt_gat_input_scores_workspace_bytes(int64_t num_nodes, int dim, int heads) {
+  return align_up((size_t)row_parts(num_nodes) * 2 * heads * dim * sizeof(float)) + 256;
+}
+
+extern "C" int etpgt_gat_input_scores_fwd(const float* x, const float* u, int64_t num_nodes, int dim, int heads,
+                                          float* a_src, float* a_dst, etpgt_stream_t stream) {
+  ETPGT_REQUIRE(dim >= 4 && dim % 4 == 0 && (heads == 1 || heads == 2 || heads == 4 || heads == 8),
+                "gat_input_scores: dim must be a multiple of 4, heads in {1,2,4,8}");
+  ETPGT_REQUIRE(num_nodes >= 0 && x && u && a_src && a_dst, "gat_input_scores_fwd: bad arguments");
+  if (num_nodes == 0) return ETPGT_OK;
+  const int grid = grid_for(num_nodes, kThreads / 32, 16);
+#define CALL(R) rows_dot_fwd_kernel<R><<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(x, u, num_nodes, dim, a_src, a_dst)
+  switch (heads) {
+    case 1: CALL(2); break;
+    case 2: CALL(4); break;
+    case 4: CALL(8); break;
+    default: CALL(16); break;
+  }
+#undef CALL
+  ETPGT_CHECK_LAUNCH("gat_input_scores_fwd");
+  return ETPGT_OK;
+}
+
+extern "C" int etpgt_gat_input_scores_bwd(const float* x, const float* u, const float* d_a_src, const float* d_a_dst,
+                                          int64_t num_nodes, int dim, int heads, float* d_x, float* d_u, void* ws,
+                                          size_t ws_bytes, etpgt_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ETPGT_REQUIRE(dim >= 4 && dim % 4 == 0 && dim <= 1024 && (heads == 1 || heads == 2 || heads == 4 || heads == 8),
+                "gat_input_scores: dim must be a multiple of 4 up to 1024, heads in {1,2,4,8}");
+  ETPGT_REQUIRE(num_nodes >= 0 && x && u && d_a_src && d_a_dst && d_x && d_u, "gat_input_scores_bwd: bad arguments");
+  if (ws_bytes < etpgt_gat_input_scores_workspace_bytes(num_nodes, dim, heads)) {
+    set_error("gat_input_scores_bwd: workspace too small");
+    return ETPGT_EWORKSPACE;
+  }
+  float* partial = static_cast<float*>(ws);
+  const int parts = num_nodes > 0 ? row_parts(num_nodes) : 0;
+  const int r = 2 * heads;
+  if (parts > 0) {
+    const int64_t chunk = (num_nodes + parts - 1) / parts;
+    const int tx = dim / 4;
+    int ty = 256 / tx > 0 ? 256 / tx : 1;
+    while (ty > 1 && (size_t)ty * r * dim * sizeof(float) > 96 * 1024) ty /= 2;
+    const size_t smem = (size_t)ty * r * dim * sizeof(float);
+#define CALL(R)                                                                                                  \
+  {                                                                                                              \
+    if (smem > 48 * 1024)                                                                                        \
+      cudaFuncSetAttribute(rows_dot_bwd_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+    rows_dot_bwd_kernel<R><<<parts, dim3(tx, ty), smem, stream>>>(x, u, d_a_src, d_a_dst, num_nodes, dim, chunk, d_x, \
+                                                                 partial);                                       \
+  }
+    switch (heads) {
+      case 1: CALL(2) break;
+      case 2: CALL(4) break;
+      case 4: CALL(8) break;
+      default: CALL(16) break;
+    }
+#undef CALL
+    ETPGT_CHECK_LAUNCH("gat_input_scores_bwd");
+  }
+  column_reduce_kernel<<<(r * dim + 31) / 32, 256, 0, stream>>>(partial, parts, r * dim, d_u, nullptr, r * dim);
+  ETPGT_CHECK_LAUNCH("gat_input_scores_bwd reduce");
+  return ETPGT_OK;
+}
+
 extern "C" int etpgt_head_mean_fwd(const float* agg, const float* bias, int64_t num_nodes, int heads, int channels,
                                    float* out, etpgt_stream_t stream) {
   ETPGT_REQUIRE(heads >= 1 && channels >= 4 && channels % 4 == 0, "head_mean: channels must be a multiple of 4");
@@ -213,7 +349,7 @@ extern "C" int etpgt_head_mean_bwd(const float* d_out, int64_t num_nodes, int he
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ETPGT_REQUIRE(heads >= 1 && channels >= 4 && channels % 4 == 0 && channels <= 1024,
                 "head_mean: channels must be a multiple of 4 up to 1024");
-  ETPGT_REQUIRE(num_nodes >= 0 && d_out && d_agg, "head_mean_bwd: bad arguments");
+  ETPGT_REQUIRE(num_nodes >= 0 && d_out && (d_agg || d_bias), "head_mean_bwd: bad arguments");
   if (ws_bytes < etpgt_gat_aux_workspace_bytes(num_nodes, channels)) {
     set_error("head_mean_bwd: workspace too small");
     return ETPGT_EWORKSPACE;

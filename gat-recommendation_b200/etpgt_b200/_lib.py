@@ -57,6 +57,12 @@ _PROTOTYPES = {
     "etpgt_gelu_bwd_split": (I, [P, P, L, L, D, ctypes.c_uint64, P, P, L, P, P, Z, P]),
     "etpgt_lap_sym_block": (I, [P, P, P, L, I, P, P, D, D, D, P, P]),
     "etpgt_gat_fwd": (I, [P, P, P, L, I, I, P, P, P, F, P, P, P, P, P, P]),
+    "etpgt_gat_mean_fused_supported": (I, [I, I]),
+    "etpgt_gat_fwd_mean": (I, [P, P, P, L, I, I, P, P, P, F, P, P, P, P, P, P, P, P]),
+    "etpgt_gat_bwd_mean": (I, [P, P, P, P, P, P, L, I, I, P, P, P, P, P, P, L, F, P, P, P, P, P, P, P, P, P, P, Z, P]),
+    "etpgt_gat_input_scores_workspace_bytes": (Z, [L, I, I]),
+    "etpgt_gat_input_scores_fwd": (I, [P, P, L, I, I, P, P, P]),
+    "etpgt_gat_input_scores_bwd": (I, [P, P, P, P, L, I, I, P, P, P, Z, P]),
     "etpgt_gat_bwd_workspace_bytes": (Z, [L, L, I]),
     "etpgt_gat_bwd": (I, [P, P, P, P, P, L, I, I, P, P, P, P, P, P, L, F, P, P, P, P, P, P, P, P, Z, P]),
     "etpgt_gat_aux_workspace_bytes": (Z, [L, I]),
@@ -66,6 +72,7 @@ _PROTOTYPES = {
     "etpgt_head_mean_bwd": (I, [P, L, I, I, P, P, P, Z, P]),
     "etpgt_sage_mean_fwd": (I, [P, L, I, P, P, P, P]),
     "etpgt_sage_mean_bwd": (I, [P, L, I, P, P, P, P, P]),
+    "etpgt_sage_mean_bwd_ld": (I, [P, L, P, L, I, P, P, P, P, P]),
     "etpgt_bn_workspace_bytes": (Z, [L, I]),
     "etpgt_bn_stats": (I, [P, L, I, P, P, Z, P]),
     "etpgt_bn_finalize": (I, [P, D, I, F, F, P, P, P, P, P]),

@@ -117,11 +117,15 @@ class GATConv(nn.Module):
     def forward(self, x, edge_index, mask_edges=None, mask_self=None):
         index = _as_index(edge_index, x.size(0))
         n, heads, c = x.size(0), self.heads, self.out_channels
-        h = ops.linear(x, self.lin.weight, None)      # tcgen05 split-bf16 GEMM (fp32-grade)
         if mask_edges is None and self.training and self.dropout > 0.0:
             masks = ops.dropout_mask((index.num_edges + n) * heads, self.dropout, x.device)   # one launch for both
             mask_edges = masks[: index.num_edges * heads].view(index.num_edges, heads)
             mask_self = masks[index.num_edges * heads:].view(n, heads)
+        if not self.concat and ops.gat_layer_supported(x, self.in_channels, heads * c, heads):
+            # projection, attention scalars from the input, edge softmax + aggregation + head mean: one autograd node
+            return ops.GatLayerFn.apply(x, self.lin.weight, self.att_src, self.att_dst, self.bias, mask_edges,
+                                        mask_self, index, heads, self.negative_slope)
+        h = ops.linear(x, self.lin.weight, None)      # tcgen05 split-bf16 GEMM (fp32-grade)
         if not self.concat and c % 4 == 0 and h.size(1) <= 1024:
             # attention scalars, edge softmax + aggregation, head mean + bias: one autograd node
             return ops.GatConvFn.apply(h, self.att_src, self.att_dst, self.bias, mask_edges, mask_self, index, heads,
@@ -150,6 +154,9 @@ class SAGEConv(nn.Module):
 
     def forward(self, x, edge_index):
         index = _as_index(edge_index, x.size(0))
+        if ops.sage_layer_supported(x, self.in_channels, self.out_channels):
+            # one GEMM over [mean | x] against [W_l | W_r] (and its two backward GEMMs) instead of two of each
+            return ops.SageLayerFn.apply(x, self.lin_l.weight, self.lin_l.bias, self.lin_r.weight, index)
         mean = ops.SageMeanFn.apply(x, index)
         return ops.linear(mean, self.lin_l.weight, self.lin_l.bias) + ops.linear(x, self.lin_r.weight, None)
 

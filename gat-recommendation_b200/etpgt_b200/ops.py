@@ -853,6 +853,15 @@ FUSED_LAYER = _os.environ.get("ETPGT_FUSED_LAYER", "1") != "0"   # ops.Transform
 # ------------------------------------------------------------------------------ GAT / GraphSAGE
 
 
+def _edge_mask(mask_edges):
+    """fp32 attention-dropout mask over the edges; an edgeless graph still needs a non-NULL pointer next to the
+    self-loop mask (the kernels take both masks or neither)."""
+    if mask_edges is None:
+        return None
+    me = _f32(mask_edges)
+    return me if me.numel() > 0 else me.new_zeros(1)
+
+
 class GatAggregateFn(torch.autograd.Function):
     """Edge softmax over leaky_relu(a_src[j] + a_dst[i]) and per-head aggregation of h_j, with the
     PyG self-loop rule (etpgt_gat_fwd / _bwd).  Returns the per-head result [N, heads*C]."""
@@ -863,7 +872,7 @@ class GatAggregateFn(torch.autograd.Function):
         h, a_src, a_dst = _f32(h), _f32(a_src), _f32(a_dst)
         n, width = h.shape
         dev = h.device
-        me = _f32(mask_edges) if mask_edges is not None else None
+        me = _edge_mask(mask_edges)
         ms = _f32(mask_self) if mask_self is not None else None
         agg = torch.empty(n, width, dtype=torch.float32, device=dev)
         m = torch.empty(n, heads, dtype=torch.float32, device=dev)
@@ -894,8 +903,9 @@ class GatAggregateFn(torch.autograd.Function):
 
 class GatConvFn(torch.autograd.Function):
     """Everything of PyG GATConv(concat=False) after the projection as one autograd node: attention
-    scalars (etpgt_gat_scores_fwd), edge softmax + aggregation (etpgt_gat_fwd), head mean + bias
-    (etpgt_head_mean_fwd), and the matching backward chain — etpgt/model/gat.py:49-109,137."""
+    scalars (etpgt_gat_scores_fwd), edge softmax + aggregation with the head mean + bias in its epilogue
+    (etpgt_gat_fwd_mean; etpgt_gat_fwd + etpgt_head_mean_fwd for narrow heads), and the matching backward chain
+    (etpgt_gat_bwd_mean from d_out [N, C]) — etpgt/model/gat.py:49-109,137."""
 
     @staticmethod
     def forward(ctx, h, att_src, att_dst, bias, mask_edges, mask_self, index: GraphIndex, heads: int, slope: float):
@@ -906,17 +916,23 @@ class GatConvFn(torch.autograd.Function):
         dev = h.device
         att_s, att_d = _f32(att_src).reshape(-1), _f32(att_dst).reshape(-1)
         bias_c = _f32(bias) if bias is not None else None
-        me = _f32(mask_edges) if mask_edges is not None else None
+        me = _edge_mask(mask_edges)
         ms = _f32(mask_self) if mask_self is not None else None
         f32 = dict(dtype=torch.float32, device=dev)
         a_src, a_dst = torch.empty(n, heads, **f32), torch.empty(n, heads, **f32)
         call("etpgt_gat_scores_fwd", ptr(h), ptr(att_s), ptr(att_d), n, width, heads, ptr(a_src), ptr(a_dst), stream())
         agg = torch.empty(n, width, **f32)
         m, inv_l = torch.empty(n, heads, **f32), torch.empty(n, heads, **f32)
-        call("etpgt_gat_fwd", ptr(h), ptr(a_src), ptr(a_dst), n, width, heads, ptr(index.rowptr), ptr(index.col),
-             ptr(index.eperm), float(slope), ptr(me), ptr(ms), ptr(agg), ptr(m), ptr(inv_l), stream())
         out = torch.empty(n, c, **f32)
-        call("etpgt_head_mean_fwd", ptr(agg), ptr(bias_c), n, heads, c, ptr(out), stream())
+        if size("etpgt_gat_mean_fused_supported", width, heads):
+            # head mean + bias inside the edge kernel (bit-identical to the separate pass: same head order)
+            call("etpgt_gat_fwd_mean", ptr(h), ptr(a_src), ptr(a_dst), n, width, heads, ptr(index.rowptr),
+                 ptr(index.col), ptr(index.eperm), float(slope), ptr(me), ptr(ms), ptr(bias_c), ptr(agg), ptr(m),
+                 ptr(inv_l), ptr(out), stream())
+        else:
+            call("etpgt_gat_fwd", ptr(h), ptr(a_src), ptr(a_dst), n, width, heads, ptr(index.rowptr), ptr(index.col),
+                 ptr(index.eperm), float(slope), ptr(me), ptr(ms), ptr(agg), ptr(m), ptr(inv_l), stream())
+            call("etpgt_head_mean_fwd", ptr(agg), ptr(bias_c), n, heads, c, ptr(out), stream())
         ctx.save_for_backward(h, att_s, att_d, a_src, a_dst, me, ms, agg, m, inv_l)
         ctx.index, ctx.heads, ctx.slope = index, heads, float(slope)
         ctx.shapes = (tuple(att_src.shape), tuple(att_dst.shape), bias is not None)
@@ -931,21 +947,113 @@ class GatConvFn(torch.autograd.Function):
         c = width // heads
         dev = h.device
         f32 = dict(dtype=torch.float32, device=dev)
-        d_agg = torch.empty(n, width, **f32)
         d_bias = torch.empty(c, **f32) if ctx.shapes[2] else None
         ws = workspace(size("etpgt_gat_aux_workspace_bytes", n, width), dev)
-        call("etpgt_head_mean_bwd", ptr(d_out), n, heads, c, ptr(d_agg), ptr(d_bias), ptr(ws), ws.numel(), stream())
         d_h = torch.empty_like(h)
         d_a_src, d_a_dst = torch.empty_like(a_src), torch.empty_like(a_dst)
         ws2 = workspace(size("etpgt_gat_bwd_workspace_bytes", n, index.num_edges, heads), dev)
-        call("etpgt_gat_bwd", ptr(h), ptr(a_src), ptr(a_dst), ptr(d_agg), ptr(agg), n, width, heads,
+        # the edge kernels expand d_out / heads in registers: the [N, heads*C] gradient of the per-head result is
+        # never written, and the source pass gathers C instead of heads*C floats per edge
+        if d_bias is not None:
+            call("etpgt_head_mean_bwd", ptr(d_out), n, heads, c, None, ptr(d_bias), ptr(ws), ws.numel(), stream())
+        call("etpgt_gat_bwd_mean", ptr(h), ptr(a_src), ptr(a_dst), None, ptr(d_out), ptr(agg), n, width, heads,
              ptr(index.rowptr), ptr(index.col), ptr(index.eperm), ptr(index.colptr), ptr(index.row), ptr(index.cpos),
-             index.num_edges, ctx.slope, ptr(me), ptr(ms), ptr(m), ptr(inv_l), ptr(d_h), ptr(d_a_src), ptr(d_a_dst),
-             ptr(ws2), ws2.numel(), stream())
+             index.num_edges, ctx.slope, ptr(me), ptr(ms), ptr(m), ptr(inv_l), ptr(d_h), None, None, ptr(d_a_src),
+             ptr(d_a_dst), ptr(ws2), ws2.numel(), stream())
         d_att_s, d_att_d = torch.empty(width, **f32), torch.empty(width, **f32)
         call("etpgt_gat_scores_bwd", ptr(h), ptr(att_s), ptr(att_d), ptr(d_a_src), ptr(d_a_dst), n, width, heads,
              ptr(d_h), ptr(d_att_s), ptr(d_att_d), ptr(ws), ws.numel(), stream())
         return (d_h, d_att_s.view(ctx.shapes[0]), d_att_d.view(ctx.shapes[1]), d_bias, None, None, None, None, None)
+
+
+class GatLayerFn(torch.autograd.Function):
+    """A whole PyG GATConv(concat=False) layer — projection included — as one autograd node
+    (etpgt/model/gat.py:49-109,137).  Compared with `linear` + GatConvFn:
+      * the attention scalars come from the layer INPUT: a_src[n,h] = <x[n,:], u_src[h,:]> with the fold
+        u_src[h,:] = W_h^T att_src[h,:] (etpgt_gat_input_scores_fwd reads [N, in] instead of [N, heads*C]);
+      * their backward therefore no longer touches d(lin(x)) (d_x += d_a u, d_u = d_a^T x — one pass over x), so
+      * the source pass of the edge backward writes d(lin(x)) directly as the split-bf16 operands of the two
+        projection-gradient GEMMs (no fp32 [N, heads*C] gradient, no split pass over it);
+      * head mean + bias sit in the forward edge kernel's epilogue, d_out / heads is expanded in registers.
+    The folds and their gradients (d_W += att (x) d_u, d_att = W d_u) are element-wise work on parameter-sized
+    tensors."""
+
+    @staticmethod
+    def forward(ctx, x, weight, att_src, att_dst, bias, mask_edges, mask_self, index: GraphIndex, heads: int,
+                slope: float):
+        _require_cuda(x, "node features")
+        x, weight = _f32(x), _f32(weight)
+        n, in_dim = x.shape
+        width = weight.size(0)
+        c = width // heads
+        dev = x.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        att_s, att_d = _f32(att_src).reshape(heads, c), _f32(att_dst).reshape(heads, c)
+        bias_c = _f32(bias) if bias is not None else None
+        me = _edge_mask(mask_edges)
+        ms = _f32(mask_self) if mask_self is not None else None
+        x_hi, x_lo, _, _, _, _ = _split(x, True, False)
+        w_hi, w_lo, _, _, _, _ = _split(weight, True, False)
+        h = _gemm_x3(x_hi, x_lo, w_hi, w_lo, n, width, in_dim, in_dim, in_dim, None)
+        w3 = weight.view(heads, c, in_dim)
+        u = torch.cat([(w3 * att_s.unsqueeze(-1)).sum(1), (w3 * att_d.unsqueeze(-1)).sum(1)]).contiguous()  # [2H, in]
+        a_src, a_dst = torch.empty(n, heads, **f32), torch.empty(n, heads, **f32)
+        call("etpgt_gat_input_scores_fwd", ptr(x), ptr(u), n, in_dim, heads, ptr(a_src), ptr(a_dst), stream())
+        agg = torch.empty(n, width, **f32)
+        m, inv_l = torch.empty(n, heads, **f32), torch.empty(n, heads, **f32)
+        out = torch.empty(n, c, **f32)
+        call("etpgt_gat_fwd_mean", ptr(h), ptr(a_src), ptr(a_dst), n, width, heads, ptr(index.rowptr), ptr(index.col),
+             ptr(index.eperm), float(slope), ptr(me), ptr(ms), ptr(bias_c), ptr(agg), ptr(m), ptr(inv_l), ptr(out),
+             stream())
+        ctx.save_for_backward(x, x_hi, x_lo, weight, w_hi, w_lo, att_s, att_d, u, h, a_src, a_dst, me, ms, agg, m, inv_l)
+        ctx.index, ctx.heads, ctx.slope = index, heads, float(slope)
+        ctx.shapes = (tuple(att_src.shape), tuple(att_dst.shape), bias is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        x, x_hi, x_lo, weight, w_hi, w_lo, att_s, att_d, u, h, a_src, a_dst, me, ms, agg, m, inv_l = ctx.saved_tensors
+        index, heads = ctx.index, ctx.heads
+        d_out = _f32(d_out)
+        n, in_dim = x.shape
+        width = weight.size(0)
+        c = width // heads
+        dev = x.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        d_bias = None
+        if ctx.shapes[2]:
+            d_bias = torch.empty(c, **f32)
+            ws = workspace(size("etpgt_gat_aux_workspace_bytes", n, width), dev)
+            call("etpgt_head_mean_bwd", ptr(d_out), n, heads, c, None, ptr(d_bias), ptr(ws), ws.numel(), stream())
+        g_hi = torch.empty(n, width, dtype=torch.bfloat16, device=dev)
+        g_lo = torch.empty(n, width, dtype=torch.bfloat16, device=dev)
+        d_a_src, d_a_dst = torch.empty_like(a_src), torch.empty_like(a_dst)
+        ws2 = workspace(size("etpgt_gat_bwd_workspace_bytes", n, index.num_edges, heads), dev)
+        call("etpgt_gat_bwd_mean", ptr(h), ptr(a_src), ptr(a_dst), None, ptr(d_out), ptr(agg), n, width, heads,
+             ptr(index.rowptr), ptr(index.col), ptr(index.eperm), ptr(index.colptr), ptr(index.row), ptr(index.cpos),
+             index.num_edges, ctx.slope, ptr(me), ptr(ms), ptr(m), ptr(inv_l), None, ptr(g_hi), ptr(g_lo), ptr(d_a_src),
+             ptr(d_a_dst), ptr(ws2), ws2.numel(), stream())
+        d_x = torch.empty_like(x)
+        d_u = torch.empty_like(u)
+        ws3 = workspace(size("etpgt_gat_input_scores_workspace_bytes", n, in_dim, heads), dev)
+        call("etpgt_gat_input_scores_bwd", ptr(x), ptr(u), ptr(d_a_src), ptr(d_a_dst), n, in_dim, heads, ptr(d_x),
+             ptr(d_u), ptr(ws3), ws3.numel(), stream())
+        # dX = d(lin) W added onto the scores' share; dW = d(lin)^T X (+ the folds' share below)
+        _gemm_x3(g_hi, g_lo, w_hi, w_lo, n, in_dim, width, width, in_dim, None, b_mn=True, accumulate_into=d_x)
+        d_w = _gemm_x3(g_hi, g_lo, x_hi, x_lo, width, in_dim, n, width, in_dim, None, split_k=0, a_mn=True, b_mn=True)
+        w3 = weight.view(heads, c, in_dim)
+        du_s, du_d = d_u[:heads], d_u[heads:]
+        d_w = d_w + (att_s.unsqueeze(-1) * du_s.unsqueeze(1) + att_d.unsqueeze(-1) * du_d.unsqueeze(1)).view(width, in_dim)
+        d_att_s = (w3 * du_s.unsqueeze(1)).sum(2)
+        d_att_d = (w3 * du_d.unsqueeze(1)).sum(2)
+        return (d_x, d_w, d_att_s.view(ctx.shapes[0]), d_att_d.view(ctx.shapes[1]), d_bias, None, None, None, None,
+                None)
+
+
+def gat_layer_supported(x: torch.Tensor, in_dim: int, width: int, heads: int) -> bool:
+    return (PROJECTION_BACKEND == "tcgen05" and x.is_cuda and x.size(0) > 0 and in_dim % 8 == 0 and width % 8 == 0
+            and in_dim <= 1024 and width <= 1024 and heads in (1, 2, 4, 8)
+            and bool(size("etpgt_gat_mean_fused_supported", width, heads)))
 
 
 class SageMeanFn(torch.autograd.Function):
@@ -970,6 +1078,69 @@ class SageMeanFn(torch.autograd.Function):
         call("etpgt_sage_mean_bwd", ptr(d_mean), n, dim, ptr(index.rowptr), ptr(index.colptr), ptr(index.row),
              ptr(d_x), stream())
         return d_x, None
+
+
+def _split_into(src: torch.Tensor, hi: torch.Tensor, lo: torch.Tensor, col0: int, colsum: bool = False):
+    """fp32 [R, C] -> bf16 hi/lo written into columns [col0, col0 + C) of the wider row-major operands `hi` / `lo`."""
+    r, c = src.shape
+    ld = hi.size(1)
+    sums = torch.empty(c, dtype=torch.float32, device=src.device) if colsum else None
+    ws = workspace(size("etpgt_split_bf16_workspace_bytes", r, c) if colsum else 256, src.device)
+    call("etpgt_split_bf16", ptr(src), r, c, c, ptr(hi.view(-1)[col0:]), ptr(lo.view(-1)[col0:]), ld, None, None, 0,
+         ptr(sums), ptr(ws), ws.numel(), stream())
+    return sums
+
+
+class SageLayerFn(torch.autograd.Function):
+    """A whole PyG SAGEConv(aggr="mean") layer, lin_l(mean_j x_j) + lin_r(x_i) (etpgt/model/graphsage.py:43-48,75),
+    as ONE GEMM over the concatenated operand [mean | x] (K = 2*in) against [W_l | W_r]: the mean kernel's output and
+    x are split straight into the two column halves of one bf16 operand pair.  Backward: dY is split once, one GEMM
+    gives [d_mean | d_root] side by side (N = 2*in), the mean-backward kernel reads the left half with its pitch and
+    adds the right half in (etpgt_sage_mean_bwd_ld), one split-K GEMM gives [dW_l | dW_r].  Per layer: 3 GEMMs
+    instead of 6, 3 split passes instead of 6, no element-wise adds."""
+
+    @staticmethod
+    def forward(ctx, x, w_l, b_l, w_r, index: GraphIndex):
+        _require_cuda(x, "node features")
+        x, w_l, w_r = _f32(x), _f32(w_l), _f32(w_r)
+        b_c = _f32(b_l) if b_l is not None else None
+        n, in_dim = x.shape
+        out_dim = w_l.size(0)
+        dev = x.device
+        mean = torch.empty_like(x)
+        call("etpgt_sage_mean_fwd", ptr(x), n, in_dim, ptr(index.rowptr), ptr(index.col), ptr(mean), stream())
+        bf = dict(dtype=torch.bfloat16, device=dev)
+        a_hi, a_lo = torch.empty(n, 2 * in_dim, **bf), torch.empty(n, 2 * in_dim, **bf)
+        _split_into(mean, a_hi, a_lo, 0)
+        _split_into(x, a_hi, a_lo, in_dim)
+        w_hi, w_lo = torch.empty(out_dim, 2 * in_dim, **bf), torch.empty(out_dim, 2 * in_dim, **bf)
+        _split_into(w_l, w_hi, w_lo, 0)
+        _split_into(w_r, w_hi, w_lo, in_dim)
+        y = _gemm_x3(a_hi, a_lo, w_hi, w_lo, n, out_dim, 2 * in_dim, 2 * in_dim, 2 * in_dim, b_c)
+        ctx.save_for_backward(a_hi, a_lo, w_hi, w_lo)
+        ctx.index, ctx.has_bias = index, b_l is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, d_y):
+        a_hi, a_lo, w_hi, w_lo = ctx.saved_tensors
+        index = ctx.index
+        d_y = _f32(d_y)
+        n, k2 = a_hi.shape
+        in_dim = k2 // 2
+        out_dim = w_hi.size(0)
+        g_hi, g_lo, _, _, _, d_b = _split(d_y, True, False, colsum=ctx.has_bias)
+        d_a = _gemm_x3(g_hi, g_lo, w_hi, w_lo, n, k2, out_dim, out_dim, k2, None, b_mn=True)   # [d_mean | d_root]
+        d_x = torch.empty(n, in_dim, dtype=torch.float32, device=d_y.device)
+        call("etpgt_sage_mean_bwd_ld", ptr(d_a), k2, ptr(d_a.view(-1)[in_dim:]), n, in_dim, ptr(index.rowptr),
+             ptr(index.colptr), ptr(index.row), ptr(d_x), stream())
+        d_w = _gemm_x3(g_hi, g_lo, a_hi, a_lo, out_dim, k2, n, out_dim, k2, None, split_k=0, a_mn=True, b_mn=True)
+        return d_x, d_w[:, :in_dim].contiguous(), d_b, d_w[:, in_dim:].contiguous(), None
+
+
+def sage_layer_supported(x: torch.Tensor, in_dim: int, out_dim: int) -> bool:
+    return (PROJECTION_BACKEND == "tcgen05" and x.is_cuda and x.size(0) > 0 and in_dim in (32, 64, 128, 256)
+            and out_dim % 8 == 0)
 
 
 # ------------------------------------------------------------------------------ BatchNorm (+res, +relu)

@@ -277,6 +277,37 @@ int etpgt_gat_bwd(const float* h, const float* a_src, const float* a_dst, const 
                   float negative_slope, const float* mask_edges, const float* mask_self,
                   const float* m, const float* inv_l, float* d_h, float* d_a_src, float* d_a_dst,
                   void* ws, size_t ws_bytes, etpgt_stream_t stream);
+/* concat=False (the reference's output layer and default, etpgt/model/gat.py:100-109) with the head mean inside the
+ * edge kernels: etpgt_gat_fwd_mean also writes out_mean [N, channels] = mean over heads of agg + bias (agg is still
+ * written: the backward pass reads it); needs etpgt_gat_mean_fused_supported(width, heads) != 0 (a head spans whole
+ * lane-group rounds, e.g. channels a multiple of 128 at width >= 128).  etpgt_gat_bwd_mean takes EITHER d_agg
+ * [N, heads*channels] or d_out_mean [N, channels] (the other NULL): with d_out_mean the per-head gradient
+ * d_out / heads is expanded in registers — the [N, heads*channels] gradient never exists and the source pass
+ * gathers channels*4 instead of heads*channels*4 bytes per edge.  The projection gradient goes EITHER to d_h (fp32)
+ * or to d_h_hi / d_h_lo (split bf16, see etpgt_gat_input_scores_*). */
+int etpgt_gat_mean_fused_supported(int width, int heads);
+int etpgt_gat_fwd_mean(const float* h, const float* a_src, const float* a_dst, int64_t num_nodes, int width,
+                       int heads, const int32_t* rowptr, const int32_t* col, const int32_t* eperm,
+                       float negative_slope, const float* mask_edges, const float* mask_self, const float* bias,
+                       float* agg, float* m, float* inv_l, float* out_mean, etpgt_stream_t stream);
+int etpgt_gat_bwd_mean(const float* h, const float* a_src, const float* a_dst, const float* d_agg,
+                       const float* d_out_mean, const float* agg, int64_t num_nodes, int width, int heads,
+                       const int32_t* rowptr, const int32_t* col, const int32_t* eperm,
+                       const int32_t* colptr, const int32_t* row, const int32_t* cpos, int64_t num_edges,
+                       float negative_slope, const float* mask_edges, const float* mask_self,
+                       const float* m, const float* inv_l, float* d_h, void* d_h_hi, void* d_h_lo,
+                       float* d_a_src, float* d_a_dst, void* ws, size_t ws_bytes, etpgt_stream_t stream);
+/* Attention scalars from the layer INPUT x [N, dim] instead of the projection: a_src[n,h] = <x[n,:], u[h,:]>,
+ * a_dst[n,h] = <x[n,:], u[heads+h,:]> with u [2*heads, dim] the fold W_h^T att_*[h] (made by the caller).  Backward:
+ * d_x [N, dim] = d_a u (written), d_u [2*heads, dim] = d_a^T x (deterministic).  With this, the backward of the
+ * scores no longer modifies d(lin(x)), so etpgt_gat_bwd_mean can write that gradient directly as the split-bf16
+ * operands d_h_hi / d_h_lo of the projection-gradient GEMMs (pass d_h = NULL). */
+size_t etpgt_gat_input_scores_workspace_bytes(int64_t num_nodes, int dim, int heads);
+int etpgt_gat_input_scores_fwd(const float* x, const float* u, int64_t num_nodes, int dim, int heads,
+                               float* a_src, float* a_dst, etpgt_stream_t stream);
+int etpgt_gat_input_scores_bwd(const float* x, const float* u, const float* d_a_src, const float* d_a_dst,
+                               int64_t num_nodes, int dim, int heads, float* d_x, float* d_u,
+                               void* ws, size_t ws_bytes, etpgt_stream_t stream);
 /* The node-wise parts of GATConv around the edge kernels, each one streaming pass (in PyTorch a dozen
  * element-wise / reduction launches over [N, heads*channels]):
  *   scores:    a_src[n,h] = <h[n,h,:], att_src[h,:]>, a_dst likewise (att_* are [heads*channels]);
@@ -301,6 +332,12 @@ int etpgt_sage_mean_fwd(const float* x, int64_t num_nodes, int dim, const int32_
                         const int32_t* col, float* mean, etpgt_stream_t stream);
 int etpgt_sage_mean_bwd(const float* d_mean, int64_t num_nodes, int dim, const int32_t* rowptr,
                         const int32_t* colptr, const int32_t* row, float* d_x, etpgt_stream_t stream);
+/* The same with the gradient of the mean given as the LEFT column half of a [N, ld] tensor and, optionally, the
+ * root branch's gradient d_root (lin_r of SAGEConv; same pitch) added in: d_x = scatter(d_mean) + d_root.  This is
+ * what the fused SAGEConv layer needs: one GEMM over [mean | x] produces both gradients side by side. */
+int etpgt_sage_mean_bwd_ld(const float* d_mean, int64_t ld, const float* d_root, int64_t num_nodes, int dim,
+                           const int32_t* rowptr, const int32_t* colptr, const int32_t* row, float* d_x,
+                           etpgt_stream_t stream);
 
 /* ---- a6: BatchNorm1d over node rows (+ residual, + ReLU) --------------------------------
  * graph_transformer.py:175-176, gat.py:138-140, graphsage.py:76-77.

@@ -203,3 +203,51 @@ def test_fused_layer_training_mode_dropout_statistics():
         assert p.grad is not None and torch.isfinite(p.grad).all(), name
     model.eval()
     assert (model(batch) == 0).float().mean().item() < 0.01
+
+
+@pytest.mark.parametrize("n,e,in_dim,c,heads", [(300, 1500, 64, 128, 4), (257, 900, 256, 256, 4), (64, 0, 32, 128, 2),
+                                                (200, 800, 64, 64, 4)])
+def test_gat_conv_layer_with_wide_heads_matches_fp64(n, e, in_dim, c, heads):
+    """GATConv(concat=False) as one layer at the reference's width (heads*C up to 1024): for C a multiple of 128 the
+    head mean + bias come out of the edge kernel's epilogue (etpgt_gat_fwd_mean) and the backward kernels expand
+    d_out / heads in registers (etpgt_gat_bwd_mean); the last case takes the separate head-mean pass in forward.
+    Oracle: oracle/conv_ref.gat_conv in fp64 (output and every gradient), with an injected attention-dropout mask."""
+    from etpgt_b200.nn import GATConv
+    from oracle import conv_ref
+
+    g = torch.Generator().manual_seed(n + c)
+    x = torch.randn(n, in_dim, generator=g, dtype=torch.float64)
+    src = torch.randint(0, n, (e,), generator=g)
+    dst = torch.randint(0, n, (e,), generator=g)
+    if e > 10:
+        dst[:5] = src[:5]                      # existing self loops are dropped, one per node is appended
+    ei = torch.stack([src, dst])
+    conv = GATConv(in_dim, c, heads=heads, concat=False, dropout=0.0)
+    with torch.no_grad():
+        conv.bias.copy_(torch.randn(c, generator=g) * 0.1)
+    keep = src != dst
+    n_kept = int(keep.sum())
+    mask_edges = (torch.rand(e, heads, generator=g) > 0.2).double() / 0.8
+    mask_self = (torch.rand(n, heads, generator=g) > 0.2).double() / 0.8
+    # the oracle's edge order: kept edges, then the appended self loops
+    oracle_mask = torch.cat([mask_edges[keep], mask_self])
+    assert oracle_mask.size(0) == n_kept + n
+    params64 = [p.detach().double().clone().requires_grad_(True) for p in (conv.lin.weight, conv.att_src, conv.att_dst,
+                                                                          conv.bias)]
+    x64 = x.clone().requires_grad_(True)
+    want = conv_ref.gat_conv(x64, ei, params64[0], params64[1], params64[2], params64[3], heads, False, 0.2, oracle_mask)
+    d_out = torch.randn(n, c, generator=g, dtype=torch.float64)
+    want.backward(d_out)
+    conv = conv.cuda()
+    xc = x.float().cuda().requires_grad_(True)
+    got = conv(xc, ei.cuda(), mask_edges=mask_edges.float().cuda(), mask_self=mask_self.float().cuda())
+    got.backward(d_out.float().cuda())
+    torch.cuda.synchronize()
+    assert got.shape == (n, c)
+    assert rel_err(got, want) < TOL
+    # analytically zero gradients (the attention vectors of an edgeless graph: a softmax over the one self loop)
+    # are compared on the scale of the layer's largest gradient, as in check_case
+    scale = max(float(q.grad.abs().max()) for q in params64)
+    assert rel_err(xc.grad, x64.grad, floor=1e-2 * float(x64.grad.abs().max())) < 5 * TOL
+    for p, q in zip((conv.lin.weight, conv.att_src, conv.att_dst, conv.bias), params64):
+        assert rel_err(p.grad, q.grad, floor=1e-2 * scale) < 5 * TOL

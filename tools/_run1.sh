@@ -1,12 +1,6 @@
-timeout 300 python -m pytest tests/test_gpu_score_tc.py -x -q > gpurun_out/r02ai_score_tests.txt 2>&1
-tail -n 3 gpurun_out/r02ai_score_tests.txt
-ETPGT_SCORE_EPI=2 timeout 300 python -m pytest tests/test_gpu_score_tc.py -x -q > gpurun_out/r02ai_score_tests_epi2.txt 2>&1
-tail -n 2 gpurun_out/r02ai_score_tests_epi2.txt
-timeout 600 python -m pytest tests/test_gpu_laplacian.py -q > gpurun_out/r02ai_lap_tests.txt 2>&1
-tail -n 15 gpurun_out/r02ai_lap_tests.txt
-timeout 120 python tools/prof_scoring.py > gpurun_out/r02ai_score.txt 2>&1 || exit 1
-timeout 120 python tools/prof_scoring.py 23861 popular >> gpurun_out/r02ai_score.txt 2>&1
-timeout 120 python tools/prof_scoring.py 100000 >> gpurun_out/r02ai_score.txt 2>&1
-ETPGT_SCORE_STATS=1 timeout 120 python tools/prof_scoring.py 2>&1 | tail -n 3 >> gpurun_out/r02ai_score.txt
-ETPGT_SCORE_EPI=2 ETPGT_SCORE_STATS=1 timeout 120 python tools/prof_scoring.py 2>&1 | tail -n 3 >> gpurun_out/r02ai_score.txt
-cat gpurun_out/r02ai_score.txt
+timeout 600 python -m pytest tests/test_gpu_models.py tests/test_gpu_kernels.py tests/test_gpu_training.py -q > gpurun_out/r02al_tests.txt 2>&1
+tail -n 12 gpurun_out/r02al_tests.txt
+timeout 300 python tools/prof_baselines.py gat 32768 2>&1 | tail -n 1
+timeout 300 python tools/prof_baselines.py sage 32768 2>&1 | tail -n 1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/r02al_gat_launches.csv python tools/prof_baselines.py gat 32768 > gpurun_out/r02al_gat.log 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/r02al_sage_launches.csv python tools/prof_baselines.py sage 32768 > gpurun_out/r02al_sage.log 2>&1
