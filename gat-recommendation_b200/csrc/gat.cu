@@ -290,7 +290,8 @@ gat_bwd_src_kernel(const float* __restrict__ d_agg, int64_t num_nodes, const int
 template <int DIM>
 __global__ void __launch_bounds__(kThreads)
 sage_mean_fwd_kernel(const float* __restrict__ x, int64_t num_nodes, const int32_t* __restrict__ rowptr,
-                     const int32_t* __restrict__ col, float* __restrict__ mean) {
+                     const int32_t* __restrict__ col, float* __restrict__ mean, __nv_bfloat16* __restrict__ mean_hi,
+                     __nv_bfloat16* __restrict__ mean_lo, int64_t ld) {
   using G = RowGeom<DIM>;
   constexpr int V = G::V, LPN = G::LPN;
   const int lane = threadIdx.x & 31;
@@ -316,7 +317,24 @@ sage_mean_fwd_kernel(const float* __restrict__ x, int64_t num_nodes, const int32
   }
   const float inv = end > begin ? 1.f / (float)(end - begin) : 0.f;
 #pragma unroll
-  for (int v = 0; v < V; ++v) st4(mean + node * DIM + 4 * (v * LPN + lig), scale4(inv, acc[v]));
+  for (int v = 0; v < V; ++v) {
+    const float4 r = scale4(inv, acc[v]);
+    if (mean != nullptr) st4(mean + node * DIM + 4 * (v * LPN + lig), r);
+    if (mean_hi != nullptr) {   // straight into (a column block of) the split-bf16 operand of the layer's GEMM
+      const float e[4] = {r.x, r.y, r.z, r.w};
+      uint32_t hw[2], lw[2];
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(e[2 * t]), h1 = __float2bfloat16_rn(e[2 * t + 1]);
+        const __nv_bfloat16 l0 = __float2bfloat16_rn(e[2 * t] - __bfloat162float(h0));
+        const __nv_bfloat16 l1 = __float2bfloat16_rn(e[2 * t + 1] - __bfloat162float(h1));
+        hw[t] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        lw[t] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+      }
+      *reinterpret_cast<uint2*>(mean_hi + node * ld + 4 * (v * LPN + lig)) = make_uint2(hw[0], hw[1]);
+      *reinterpret_cast<uint2*>(mean_lo + node * ld + 4 * (v * LPN + lig)) = make_uint2(lw[0], lw[1]);
+    }
+  }
 }
 
 // d_x_j = sum over out-edges (j -> i) of d_mean_i / indeg(i)  (+ d_root_j: the lin_r branch of SAGEConv, when the two
@@ -462,22 +480,32 @@ extern "C" int etpgt_gat_bwd(const float* h, const float* a_src, const float* a_
                             d_a_src, d_a_dst, ws, ws_bytes, stream);
 }
 
-extern "C" int etpgt_sage_mean_fwd(const float* x, int64_t num_nodes, int dim, const int32_t* rowptr,
-                                   const int32_t* col, float* mean, etpgt_stream_t stream_) {
+extern "C" int etpgt_sage_mean_fwd_split(const float* x, int64_t num_nodes, int dim, const int32_t* rowptr,
+                                         const int32_t* col, float* mean, void* mean_hi, void* mean_lo, int64_t ld,
+                                         etpgt_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ETPGT_REQUIRE(supported_dim(dim), "sage_mean_fwd: unsupported dim %d", dim);
-  ETPGT_REQUIRE(num_nodes >= 0 && x && rowptr && mean, "sage_mean_fwd: bad arguments");
+  ETPGT_REQUIRE(num_nodes >= 0 && x && rowptr && (mean || mean_hi) && (mean_hi == nullptr) == (mean_lo == nullptr),
+                "sage_mean_fwd: bad arguments");
+  ETPGT_REQUIRE(mean_hi == nullptr || (ld >= dim && ld % 4 == 0 && (((uintptr_t)mean_hi | (uintptr_t)mean_lo) & 7) == 0),
+                "sage_mean_fwd: the split outputs need a pitch >= dim (multiple of 4) and 8-byte alignment");
   if (num_nodes == 0) return ETPGT_OK;
 #define CALL(D)                                                                                              \
   {                                                                                                          \
     const int64_t npc = (kThreads / 32) * RowGeom<D>::GROUPS;                                                \
-    sage_mean_fwd_kernel<D><<<(unsigned)((num_nodes + npc - 1) / npc), kThreads, 0, stream>>>(x, num_nodes, rowptr, \
-                                                                                             col, mean);     \
+    sage_mean_fwd_kernel<D><<<(unsigned)((num_nodes + npc - 1) / npc), kThreads, 0, stream>>>(               \
+        x, num_nodes, rowptr, col, mean, static_cast<__nv_bfloat16*>(mean_hi), static_cast<__nv_bfloat16*>(mean_lo), ld); \
   }
   ETPGT_DISPATCH_DIM(dim, CALL)
 #undef CALL
   ETPGT_CHECK_LAUNCH("sage_mean_fwd");
   return ETPGT_OK;
+}
+
+extern "C" int etpgt_sage_mean_fwd(const float* x, int64_t num_nodes, int dim, const int32_t* rowptr,
+                                   const int32_t* col, float* mean, etpgt_stream_t stream) {
+  ETPGT_REQUIRE(mean != nullptr, "sage_mean_fwd: bad arguments");
+  return etpgt_sage_mean_fwd_split(x, num_nodes, dim, rowptr, col, mean, nullptr, nullptr, 0, stream);
 }
 
 extern "C" int etpgt_sage_mean_bwd_ld(const float* d_mean, int64_t ld, const float* d_root, int64_t num_nodes, int dim,

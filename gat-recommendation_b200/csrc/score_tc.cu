@@ -749,6 +749,7 @@ TcPlan tc_plan(int64_t batch, int64_t num_items, int k) {
   // the select kernel's survivor buffer
   int max_splits = total_tiles / 64 > 1 ? total_tiles / 64 : 1;
   if (max_splits > 32) max_splits = 32;
+  const int max_forced = total_tiles / 32 > 1 ? (total_tiles / 32 > 32 ? 32 : total_tiles / 32) : 1;   // tuning knob only
   const int m_full = (m_tiles / workers) * workers;   // whole waves: one full-catalogue unit per row tile
   const int tail = m_tiles - m_full;
   int splits = 1;
@@ -764,7 +765,7 @@ TcPlan tc_plan(int64_t batch, int64_t num_items, int k) {
     }
     if (const char* forced = getenv("ETPGT_SCORE_SPLITS")) {  // tuning knob
       const int f = atoi(forced);
-      if (f >= 1 && f <= max_splits) splits = f;
+      if (f >= 1 && f <= max_forced) splits = f;
     }
   }
   p.sch.unit_rows = unit_rows;

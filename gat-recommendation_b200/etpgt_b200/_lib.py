@@ -73,6 +73,7 @@ _PROTOTYPES = {
     "etpgt_sage_mean_fwd": (I, [P, L, I, P, P, P, P]),
     "etpgt_sage_mean_bwd": (I, [P, L, I, P, P, P, P, P]),
     "etpgt_sage_mean_bwd_ld": (I, [P, L, P, L, I, P, P, P, P, P]),
+    "etpgt_sage_mean_fwd_split": (I, [P, L, I, P, P, P, P, P, L, P]),
     "etpgt_bn_workspace_bytes": (Z, [L, I]),
     "etpgt_bn_stats": (I, [P, L, I, P, P, Z, P]),
     "etpgt_bn_finalize": (I, [P, D, I, F, F, P, P, P, P, P]),

@@ -1107,11 +1107,11 @@ class SageLayerFn(torch.autograd.Function):
         n, in_dim = x.shape
         out_dim = w_l.size(0)
         dev = x.device
-        mean = torch.empty_like(x)
-        call("etpgt_sage_mean_fwd", ptr(x), n, in_dim, ptr(index.rowptr), ptr(index.col), ptr(mean), stream())
         bf = dict(dtype=torch.bfloat16, device=dev)
         a_hi, a_lo = torch.empty(n, 2 * in_dim, **bf), torch.empty(n, 2 * in_dim, **bf)
-        _split_into(mean, a_hi, a_lo, 0)
+        # the mean goes straight into the left column half as a bf16 pair (no fp32 mean, no split pass over it)
+        call("etpgt_sage_mean_fwd_split", ptr(x), n, in_dim, ptr(index.rowptr), ptr(index.col), None, ptr(a_hi),
+             ptr(a_lo), 2 * in_dim, stream())
         _split_into(x, a_hi, a_lo, in_dim)
         w_hi, w_lo = torch.empty(out_dim, 2 * in_dim, **bf), torch.empty(out_dim, 2 * in_dim, **bf)
         _split_into(w_l, w_hi, w_lo, 0)

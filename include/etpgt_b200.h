@@ -330,6 +330,11 @@ int etpgt_head_mean_bwd(const float* d_out, int64_t num_nodes, int heads, int ch
  * x_j over in-edges (0 when there are none); backward distributes d_mean_i / indeg(i) to sources. */
 int etpgt_sage_mean_fwd(const float* x, int64_t num_nodes, int dim, const int32_t* rowptr,
                         const int32_t* col, float* mean, etpgt_stream_t stream);
+/* The same writing the mean directly as split-bf16 operands (mean = hi + lo) into rows of pitch `ld` elements — a
+ * column block of the fused SAGEConv layer's [mean | x] GEMM operand; `mean` (fp32) may then be NULL. */
+int etpgt_sage_mean_fwd_split(const float* x, int64_t num_nodes, int dim, const int32_t* rowptr,
+                              const int32_t* col, float* mean, void* mean_hi, void* mean_lo, int64_t ld,
+                              etpgt_stream_t stream);
 int etpgt_sage_mean_bwd(const float* d_mean, int64_t num_nodes, int dim, const int32_t* rowptr,
                         const int32_t* colptr, const int32_t* row, float* d_x, etpgt_stream_t stream);
 /* The same with the gradient of the mean given as the LEFT column half of a [N, ld] tensor and, optionally, the
