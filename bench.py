@@ -26,6 +26,10 @@ Prints ONE JSON line (rank 0).
   roofline  the dominant kernel group (fused TransformerConv fwd+bwd) timed alone with CUDA events: algorithmic
           bytes of SURVEY.md section 8(d) / time vs the measured HBM peak; `traffic` = DRAM bytes of the same launches
           from the ncu capture committed under profiles/ (this round's);
+  scoring   full-catalogue evaluation scoring + top-20 (23,861 x 82,174 x 256): dense flops / time vs the measured bf16
+          peak, with the GEMM kernel's tensor-pipe activity from the committed ncu capture;
+  baseline_models   BASELINE.json configs[2]: GAT / GraphSAGE training steps (+ the FFN variant of the transformer) and
+          their edge kernels alone; laplacian_pe_device: the one-off eigen solver on the co-occurrence graph;
   cpu_baseline  the oracle port (oracle/model_ref.py, a restatement of the reference's PyTorch/PyG path) on this
           box's host cores, on a bounded sample of the same workload, at the batch size printed with it.
 """
@@ -626,6 +630,7 @@ def run_b200(args, rank, world_size, local_rank):
         out["edges_per_s_tconv_fwd_bwd"] = out["roofline"].pop("edges_per_s")
         if world_size == 1 and not scaled:
             out["baseline_models"] = baseline_models(dev_batches, device, num_items)
+            out["laplacian_pe_device"] = laplacian_pe_device(data, device, num_items)
         if world_size == 1 and not args.skip_cpu_baseline and not scaled:
             # the oracle port on the host cores, 10-25 s: at the CPU arm's batch and at 4x that (its rate falls with
             # the batch, see CPU_BATCH_NOTE); the better of the two is the baseline
@@ -689,8 +694,18 @@ def baseline_models(dev_batches, device, num_items, steps=10):
 
     out = {}
     sessions = dev_batches[0].num_graphs
+    def ffn_variant():
+        # the non-optimized GraphTransformer (graph_transformer.py:185-227: 3 layers, 4 heads, FFN x4): its FFN blocks
+        # run as GEMM -> GELU (+ Philox dropout) in the epilogue -> GEMM (ops.FeedForward)
+        from etpgt_b200.model import create_graph_transformer
+
+        model = create_graph_transformer(num_items, DIM, DIM, 3, 4, dropout=0.1, laplacian_k=K_PE)
+        model.laplacian_pe._cached_pe = cached_pe(num_items)
+        return model
+
     for name, make in (("gat_l3_h4", lambda: create_gat(num_items, DIM, DIM, 3, 4, dropout=0.1)),
-                       ("graphsage_l3_mean", lambda: create_graphsage(num_items, DIM, DIM, 3, dropout=0.1))):
+                       ("graphsage_l3_mean", lambda: create_graphsage(num_items, DIM, DIM, 3, dropout=0.1)),
+                       ("graph_transformer_ffn_l3_h4", ffn_variant)):
         torch.manual_seed(0)
         model = make().to(device)
         opt = optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-5)
@@ -717,6 +732,24 @@ def baseline_models(dev_batches, device, num_items, steps=10):
         del model, opt
     out["edge_kernels"] = edge_kernel_rooflines(dev_batches[0], device)
     return out
+
+
+def laplacian_pe_device(data, device, num_items):
+    """the one-off Laplacian-PE eigendecomposition (etpgt/encodings/laplacian_pe.py:19-66) of the
+    co-occurrence graph on the device — the 17 smallest eigenpairs of the sym-normalised Laplacian of the undirected
+    graph (Chebyshev-filtered subspace iteration over etpgt_lap_sym_block), timed with the setup (CSR build)."""
+    from etpgt_b200.encodings.laplacian_pe import compute_laplacian_pe_device
+
+    ei = torch.from_numpy(np.stack([data.item_i, data.item_j])).to(device)
+    compute_laplacian_pe_device(ei, num_items, k=K_PE)          # warm-up (cuSOLVER handles, workspace)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    pe, info = compute_laplacian_pe_device(ei, num_items, k=K_PE, return_info=True)
+    torch.cuda.synchronize()
+    sec = time.perf_counter() - t0
+    return {"seconds": sec, "nodes": num_items, "undirected_edges": int(ei.size(1)), "k": K_PE,
+            "outer_iterations": int(info["iterations"]), "max_residual": float(info["residuals"].max()),
+            "zero_eigenvalues": int((info["eigenvalues"].abs() < 1e-9).sum())}
 
 
 def _time_launches(fn, flush, reps=20):
@@ -814,10 +847,31 @@ def scoring_roofline(model, device, num_items, sessions=23_861, k=20, reps=10):
     ms = a.elapsed_time(b) / reps
     flops = 2.0 * sessions * num_items * DIM
     achieved = flops / (ms / 1e3) / 1e12
-    return {"bound": "tensor", "kernel": "score_topk_tc (tcgen05 bf16 GEMM + fused top-k) + topk_merge",
-            "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"],
-            "peak_source": pk["source"], "ms": ms, "sessions": sessions, "items": num_items, "k": k,
-            "sessions_per_s": sessions / (ms / 1e3)}
+    out = {"bound": "tensor", "kernel": "score_dump_tc (tcgen05 bf16 GEMM on CTA pairs + fused piece dump) + score_select",
+           "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"],
+           "peak_source": pk["source"], "ms": ms, "sessions": sessions, "items": num_items, "k": k,
+           "sessions_per_s": sessions / (ms / 1e3)}
+    out.update(scoring_ncu_capture())
+    return out
+
+
+def scoring_ncu_capture() -> dict:
+    """Tensor-pipe utilisation of the scoring GEMM kernel from the committed `ncu --set full` capture of this shape
+    (profiles/r02_score_ncu_full.csv; tools/prof_scoring.py under ncu) — a profiler figure, not measured in this run."""
+    import csv
+
+    path = ROOT / "profiles" / "r02_score_ncu_full.csv"
+    if not path.exists():
+        return {"tensor_pipe_active_pct_ncu": None}
+    rows = list(csv.reader(path.open()))
+    hdr = rows[0]
+    for r in rows[2:]:
+        d = dict(zip(hdr, r))
+        if "score_dump_tc" in d.get("Kernel Name", ""):
+            return {"tensor_pipe_active_pct_ncu": float(d["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]),
+                    "gemm_kernel_us_ncu": float(d["gpu__time_duration.sum"]),
+                    "ncu_capture": "profiles/r02_score_ncu_full.csv (ncu --set full --clock-control none, 23,861 x 82,174 x 256)"}
+    return {"tensor_pipe_active_pct_ncu": None}
 
 
 def time_tconv(qkvs, w_beta, index, device, reps=20, hubs=True):
