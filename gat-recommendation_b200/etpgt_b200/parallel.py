@@ -107,10 +107,12 @@ def sharded_predict(model, session_embeddings: torch.Tensor, k: int = 20, group=
     (ids, hit_pos) where hit_pos[b] is the position of the target in the top-k or -1 (input of ops.hit_metrics).
 
     counts: every rank's session count (host ints), when the caller knows them (a sharding loader does);
-    otherwise they are exchanged, which costs one host read."""
+    otherwise they are exchanged, which costs one host read.
+    group=False: score on this process alone even when a process group is initialised (a single-process replica
+    inside a data-parallel job: no collective is entered)."""
     from . import ops
 
-    rank, size = world()
+    rank, size = (0, 1) if group is False else world()
     table = model.get_item_embeddings()
     b_local, width = session_embeddings.shape
     dev = session_embeddings.device

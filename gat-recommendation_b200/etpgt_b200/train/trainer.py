@@ -159,7 +159,8 @@ class Trainer:
                     ops.hit_metrics(hit, k, acc[2 * j:2 * j + 2])
             else:
                 # fused scoring + top-k; the target's position comes out of the scorer's select epilogue
-                _, hit = parallel.sharded_predict(self.model, sess, k=k_max, targets=batch.target_item)
+                # (group=False: this Trainer is not data parallel, even if the process has a group initialised)
+                _, hit = parallel.sharded_predict(self.model, sess, k=k_max, group=False, targets=batch.target_item)
                 for j, k in enumerate(self.k_values):
                     ops.hit_metrics(hit, k, acc[2 * j:2 * j + 2])
             sessions += int(batch.target_item.shape[0])

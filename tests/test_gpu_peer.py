@@ -304,6 +304,11 @@ def _free_port():
 def _two_gpu_worker(rank, world, port, out):
     import torch.distributed as dist
 
+    import faulthandler
+
+    # a worker that hangs (a collective only one rank entered, ...) dumps its Python stacks and exits instead of
+    # hanging the suite
+    faulthandler.dump_traceback_later(300, exit=True)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -422,6 +427,7 @@ def _two_gpu_worker(rank, world, port, out):
             notes.append(f"trainer dp {hist_dp} single {hist_single}")
         out[rank] = (ok and trainer_ok, same, top_equal, notes)
     finally:
+        faulthandler.cancel_dump_traceback_later()
         dist.destroy_process_group()
 
 
