@@ -277,12 +277,106 @@ def co_event_graph_case():
     print(f"wrote co_event_graph.npz: {stats['num_edges']} edges, {stats['num_nodes']} nodes")
 
 
+def trainer_case():
+    """Drives the reference's own training loop — etpgt/train/trainer.py `Trainer.train()` (train_epoch, evaluate,
+    checkpointing) with the reference model, `SessionDataset` + `collate_fn` batches and torch.optim.AdamW, as
+    scripts/train/train_baseline.py:252-300 wires them — on CPU in fp32, for two loss settings.  The batches
+    (negatives included) are materialised once and handed to the Trainer as lists, so that the B200 path can be fed
+    the very same batches: the fixture pins epoch losses, Recall / NDCG per epoch and the final weights."""
+    import logging
+
+    from torch.utils.data import DataLoader
+
+    from etpgt.train.trainer import Trainer
+
+    logging.disable(logging.CRITICAL)
+    rng = np.random.default_rng(21)
+    num_items, n_train, n_val, dim, k_pe = 150, 96, 64, 32, 8
+    sessions = [rng.integers(1, num_items, size=int(rng.integers(3, 10))) for _ in range(n_train + n_val)]
+    pairs = {}
+    for items in sessions[:n_train]:  # window-5 co-occurrence of the TRAIN sessions, canonical i<=j
+        for a in range(len(items)):
+            for b in range(a + 1, min(a + 6, len(items))):
+                i, j = sorted((int(items[a]), int(items[b])))
+                pairs[(i, j)] = pairs.get((i, j), 0) + 1
+    edges = sorted(pairs.items(), key=lambda kv: -kv[1])
+
+    def write_sessions(path, part, first_id):
+        with open(path, "w", newline="") as f:
+            w = csv.writer(f)
+            w.writerow(["timestamp", "visitorid", "event", "itemid", "transactionid", "session_id"])
+            for s, items in enumerate(part):
+                for t, it in enumerate(items):
+                    w.writerow([1000 * (first_id + s) + t, first_id + s, "view", int(it), "", first_id + s])
+
+    out = {"cfg_num_items": np.asarray(num_items), "cfg_dim": np.asarray(dim), "cfg_k_pe": np.asarray(k_pe)}
+    with tempfile.TemporaryDirectory() as tmp:
+        tp, vp, gp = Path(tmp) / "train.csv", Path(tmp) / "val.csv", Path(tmp) / "graph_edges.csv"
+        write_sessions(tp, sessions[:n_train], 0)
+        write_sessions(vp, sessions[n_train:], n_train)
+        with open(gp, "w", newline="") as f:
+            w = csv.writer(f)
+            w.writerow(["item_i", "item_j", "count", "last_ts", "event_pair_hist"])
+            for (i, j), c in edges:
+                w.writerow([i, j, c, 0, "{}"])
+        torch.manual_seed(0)
+        import random
+
+        random.seed(0)
+        np.random.seed(0)
+        train_ds = SessionDataset(tp, gp, num_negatives=5, max_session_length=50)
+        val_ds = SessionDataset(vp, gp, num_negatives=5, max_session_length=50)
+        train_batches = list(DataLoader(train_ds, batch_size=32, shuffle=False, collate_fn=collate_fn))
+        val_batches = list(DataLoader(val_ds, batch_size=32, shuffle=False, collate_fn=collate_fn))
+        for split, batches in (("train", train_batches), ("val", val_batches)):
+            out[f"n_{split}_batches"] = np.asarray(len(batches))
+            for b, batch in enumerate(batches):
+                out[f"{split}{b}/x"] = npy(batch.x)
+                out[f"{split}{b}/edge_index"] = npy(batch.edge_index)
+                out[f"{split}{b}/batch"] = npy(batch.batch)
+                out[f"{split}{b}/target"] = npy(batch.target_item)
+                out[f"{split}{b}/negatives"] = npy(batch.negative_items)      # flat [B * 5], as collate_fn leaves it
+        pe = torch.randn(num_items, k_pe, generator=torch.Generator().manual_seed(7)).abs()
+        out["pe"] = npy(pe)
+        for tag, loss_type in (("bpr", None), ("dual", "dual")):
+            torch.manual_seed(3)
+            model = create_graph_transformer_optimized(num_items=num_items, embedding_dim=dim, hidden_dim=dim,
+                                                       num_layers=2, num_heads=2, dropout=0.0, laplacian_k=k_pe)
+            model.laplacian_pe._cached_pe = pe.clone()
+            for k, v in model.state_dict().items():
+                if "_cached_pe" not in k:
+                    out[f"{tag}_init/{k}"] = npy(v).copy()      # a copy: the optimizer updates the parameters in place
+            optimizer = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-5)
+            loss_fn = create_loss_function(loss_type) if loss_type else None
+            trainer = Trainer(model, train_batches, val_batches, optimizer, device="cpu",
+                              output_dir=Path(tmp) / f"out_{tag}", max_epochs=3, patience=5, k_values=[10, 20],
+                              loss_fn=loss_fn)
+            history = trainer.train()
+            out[f"{tag}_train_loss"] = np.asarray(history["train_loss"], dtype=np.float64)
+            for key in ("recall@10", "ndcg@10", "recall@20", "ndcg@20"):
+                out[f"{tag}_{key}"] = np.asarray([m[key] for m in history["val_metrics"]], dtype=np.float64)
+            out[f"{tag}_best_val_metric"] = np.asarray(trainer.best_val_metric)
+            for k, v in model.state_dict().items():
+                if "_cached_pe" not in k:
+                    out[f"{tag}_final/{k}"] = npy(v)
+            files = sorted(p.name for p in (Path(tmp) / f"out_{tag}").iterdir())
+            out[f"{tag}_files"] = np.asarray(",".join(files))
+            print(f"trainer[{tag}]: loss {history['train_loss']}, val {history['val_metrics'][-1]}, files {files}")
+    logging.disable(logging.NOTSET)
+    np.savez_compressed(OUT / "trainer_loop.npz", **out)
+    print("wrote trainer_loop.npz")
+
+
 if __name__ == "__main__":
     OUT.mkdir(parents=True, exist_ok=True)
     if "--only-co-event" in sys.argv:
         co_event_graph_case()
         raise SystemExit(0)
+    if "--only-trainer" in sys.argv:
+        trainer_case()
+        raise SystemExit(0)
     model_cases()
     loss_readout_metric_cases()
     dataloader_case()
     co_event_graph_case()
+    trainer_case()
