@@ -12,7 +12,9 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parents[1]
 BUILD = ROOT / "gat-recommendation_b200" / "build"
-WANT = {"score_tc.o": "score_dump_tc_kernelILi4ELi20E", "gemm_tc.o": "gemm_bf16x3_kernelILi2ELi256E"}
+# the instantiations the bench runs: DIM = 256, k = 20, CTA pairs, two epilogue warps per lane quarter; split-bf16 GEMM
+# on CTA pairs with 256-column tiles
+WANT = {"score_tc.o": "score_dump_tc_kernelILi4ELi20ELb1ELi2E", "gemm_tc.o": "gemm_bf16x3_2sm_kernelILi2ELi256E"}
 KEY = re.compile(r"\b(UTCHMMA|UTCQMMA|UTCBAR|UTCCP|UTMALDG|UTMASTG|UTMAREDG|UTMAPF|UTMACCTL|LDTM|STTM|SYNCS|UTCATOMSWS|"
                  r"FENCE|ELECT)\b")
 
