@@ -125,12 +125,6 @@ struct Schedule {
   }
 };
 
-__device__ __forceinline__ float ld_shared_volatile_f32(uint32_t addr) {
-  float v;
-  asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
-  return v;
-}
-
 // Per-row state of the piece-dump epilogue (one thread = one session row = one TMEM lane, one column half).
 template <int KCAP>
 struct RowState {

@@ -76,5 +76,10 @@ class SessionReadout(nn.Module):
         if num_sessions is None:  # the reference syncs here as well (base.py:146)
             num_sessions = int(batch_indices.max().item()) + 1
         seg_ptr = ops.segment_ptr(batch_indices, num_sessions)
-        scores = self.attention(node_embeddings).squeeze(-1) if self.readout_type == "attention" else None
+        scores = None
+        if self.readout_type == "attention":      # nn.Linear(hidden, 1): one pass over the rows, no library GEMV
+            if ops.row_scores_supported(node_embeddings):
+                scores = ops.RowScores.apply(node_embeddings, self.attention.weight, self.attention.bias)
+            else:
+                scores = self.attention(node_embeddings).squeeze(-1)
         return ops.SegmentReadout.apply(node_embeddings, scores, seg_ptr, ops.READOUT_MODES[self.readout_type])

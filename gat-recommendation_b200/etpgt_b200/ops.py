@@ -1050,6 +1050,44 @@ class GatLayerFn(torch.autograd.Function):
                 None)
 
 
+class RowScores(torch.autograd.Function):
+    """score[n] = <x[n, :], w> + b — the attention readout's nn.Linear(hidden, 1) (etpgt/model/base.py:175-189) as one
+    pass over x on this library's kernels (etpgt_gat_input_scores_fwd/_bwd with one vector; the second vector of the
+    pair is zero) instead of a library GEMV: d_x = d_score (x) w, d_w = d_score^T x (deterministic), d_b = sum."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        _require_cuda(x, "node features")
+        x = _f32(x)
+        n, dim = x.shape
+        u = torch.zeros(2, dim, dtype=torch.float32, device=x.device)
+        u[0] = _f32(weight).reshape(-1)
+        score, unused = torch.empty(n, 1, dtype=torch.float32, device=x.device), torch.empty(n, 1, dtype=torch.float32,
+                                                                                             device=x.device)
+        call("etpgt_gat_input_scores_fwd", ptr(x), ptr(u), n, dim, 1, ptr(score), ptr(unused), stream())
+        ctx.save_for_backward(x, u)
+        ctx.has_bias = bias is not None
+        ctx.w_shape = tuple(weight.shape)
+        return score.view(n) + bias.reshape(()) if bias is not None else score.view(n)
+
+    @staticmethod
+    def backward(ctx, d_score):
+        x, u = ctx.saved_tensors
+        n, dim = x.shape
+        d_s = _f32(d_score).reshape(n, 1)
+        zeros = torch.zeros_like(d_s)
+        d_x, d_u = torch.empty_like(x), torch.empty_like(u)
+        ws = workspace(size("etpgt_gat_input_scores_workspace_bytes", n, dim, 1), x.device)
+        call("etpgt_gat_input_scores_bwd", ptr(x), ptr(u), ptr(d_s), ptr(zeros), n, dim, 1, ptr(d_x), ptr(d_u), ptr(ws),
+             ws.numel(), stream())
+        d_b = d_s.sum().reshape(1) if ctx.has_bias else None
+        return d_x, d_u[0].view(ctx.w_shape), d_b
+
+
+def row_scores_supported(x: torch.Tensor) -> bool:
+    return x.is_cuda and x.size(0) > 0 and x.size(1) % 4 == 0 and x.size(1) <= 1024
+
+
 def gat_layer_supported(x: torch.Tensor, in_dim: int, width: int, heads: int) -> bool:
     return (PROJECTION_BACKEND == "tcgen05" and x.is_cuda and x.size(0) > 0 and in_dim % 8 == 0 and width % 8 == 0
             and in_dim <= 1024 and width <= 1024 and heads in (1, 2, 4, 8)
