@@ -2,7 +2,10 @@
 raw device pointers + the current stream to the C-ABI kernels (include/etpgt_b200.h).
 
 PyTorch is plumbing here (device memory, streams, autograd bookkeeping); all arithmetic on the
-path runs in libetpgt_b200.so, except the dense node projections which are library GEMMs.
+path runs in libetpgt_b200.so — the dense node projections included (etpgt_gemm_bf16x3: tcgen05 split-bf16 GEMMs
+on CTA pairs).  What stays in torch is element-wise work on parameter-sized tensors (the GAT score folds, weight
+concatenations) and `torch.nn.functional.linear` for layer widths that are not multiples of 8 (no configuration of
+the reference has one; `linear` warns once when it takes that route).
 """
 
 from __future__ import annotations
@@ -841,7 +844,17 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None) -> 
     if PROJECTION_BACKEND == "tcgen05" and x.is_cuda and x.size(1) % 8 == 0 and weight.size(0) % 8 == 0 \
             and x.size(0) > 0:
         return LinearTensorCore.apply(x, weight, bias)
+    global _WARNED_LIBRARY_LINEAR
+    if not _WARNED_LIBRARY_LINEAR and x.is_cuda:
+        _WARNED_LIBRARY_LINEAR = True
+        import warnings
+
+        warnings.warn(f"etpgt_b200.ops.linear: widths {tuple(weight.shape)} are not multiples of 8 — this projection "
+                      "runs on the library GEMM (torch.nn.functional.linear), not on etpgt_gemm_bf16x3", stacklevel=2)
     return torch.nn.functional.linear(x, weight, bias)
+
+
+_WARNED_LIBRARY_LINEAR = False
 
 
 import os as _os  # noqa: E402
