@@ -529,7 +529,9 @@ def run_b200(args, rank, world_size, local_rank):
         drop_pending()
         return ms
 
-    warm = max(args.warmup, 2 * args.rotate + 1)
+    # W untimed warm-up steps, and never fewer than 24: the first timed loop of a process (`value`) showed one step of
+    # 4.6 ms (1 GPU) / 8.2 ms (8 GPUs) among 20 of ~2.9 / ~3.1 ms with nine warm-up steps, none of the later loops did
+    warm = max(args.warmup, 2 * args.rotate + 1, 24)
     with ClockSampler(local_rank) as clocks:
         # ---- device-resident timing (value); the warm-up visits every rotating batch so that the caching
         # allocator and the preparation ring have seen every shape before the clock starts
@@ -588,6 +590,7 @@ def run_b200(args, rank, world_size, local_rank):
         "step_ms": step_stats,      # device time between the ends of consecutive steps (rank 0)
         "final_loss": losses[-1] if losses else None,
         "batch_shape": {"nodes": int(dev_batches[0].x.numel()), "edges": int(dev_batches[0].edge_index.size(1))},
+        "warmup_steps_run": int(warm),      # untimed steps before the first timed loop: max(W, 24)
     }
     if e2e_extra is not None:
         out["e2e_from_sessions"] = e2e_extra
