@@ -407,6 +407,12 @@ def run_b200(args, rank, world_size, local_rank):
     step_stats = {}
 
     def timed(fn, steps, label="value"):
+        import gc
+
+        # the cyclic collector off inside the timed region (as timeit does): a generation-2 pass over the process's
+        # objects takes milliseconds on one rank, and under data parallelism every rank then waits for it
+        gc.collect()
+        gc.disable()
         sync()
         mallocs = torch.cuda.memory_stats(device).get("num_device_alloc", 0)
         marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
@@ -415,6 +421,7 @@ def run_b200(args, rank, world_size, local_rank):
             fn(i)
             marks[i + 1].record()
         sync()
+        gc.enable()
         mallocs = torch.cuda.memory_stats(device).get("num_device_alloc", 0) - mallocs
         if mallocs and rank == 0:   # a cudaMalloc inside the timed region means the warm-up was too short
             print(f"bench.py: {mallocs} device allocations inside the timed region '{label}'", file=sys.stderr)
