@@ -367,8 +367,52 @@ def trainer_case():
     print("wrote trainer_loop.npz")
 
 
+def laplacian_pe_case():
+    """Runs the reference's `compute_laplacian_pe` and `LaplacianPECached.precompute / forward / project`
+    (etpgt/encodings/laplacian_pe.py:19-199) on (a) a directed edge list with item_i <= item_j — what
+    scripts/train/train_baseline.py:234-243 passes — and (b) the same list symmetrised.  Pins the host path
+    (`method="scipy"`) of etpgt_b200.encodings.laplacian_pe, which must reproduce what checkpoints store."""
+    from etpgt.encodings.laplacian_pe import LaplacianPECached, compute_laplacian_pe
+
+    rng = np.random.default_rng(13)
+    n, k = 240, 8
+    pairs = set()
+    while len(pairs) < 900:
+        a, b = (int(v) for v in rng.integers(1, n, size=2))
+        pairs.add((min(a, b), max(a, b)))          # self pairs (a == b) are kept, as 04_build_graph.py keeps them
+    directed = torch.tensor(sorted(pairs), dtype=torch.long).t().contiguous()
+    symmetric = torch.cat([directed, directed.flip(0)], dim=1)
+    out = {"num_nodes": np.asarray(n), "k": np.asarray(k), "directed": npy(directed), "symmetric": npy(symmetric)}
+    for name, ei in (("directed", directed), ("symmetric", symmetric)):
+        first = compute_laplacian_pe(ei, n, k=k)
+        again = compute_laplacian_pe(ei, n, k=k)     # eigsh draws a new start vector on every call
+        out[f"pe_{name}"] = npy(first)
+        out[f"pe_{name}_again"] = npy(again)
+        print(f"  {name}: two calls of the reference on the same input differ by {float((first - again).abs().max()):.3e}"
+              f" (max entry {float(first.abs().max()):.3f})")
+
+    class Graph:
+        edge_index, num_nodes = directed, n
+
+    torch.manual_seed(5)
+    module = LaplacianPECached(k=k, embedding_dim=16)
+    module.precompute(Graph)
+    out["module_cached_pe"] = npy(module._cached_pe).copy()
+    ids = torch.tensor([3, 7, 7, 100, 239])
+    out["module_weight"] = npy(module.projection.weight).copy()
+    out["module_bias"] = npy(module.projection.bias).copy()
+    out["module_ids"] = npy(ids)
+    out["module_forward"] = npy(module(ids))
+    out["module_project"] = npy(module.project(module._cached_pe[ids]))
+    np.savez_compressed(OUT / "laplacian_pe.npz", **out)
+    print(f"wrote laplacian_pe.npz: directed {directed.size(1)} edges, pe max {float(out['pe_directed'].max()):.4f}")
+
+
 if __name__ == "__main__":
     OUT.mkdir(parents=True, exist_ok=True)
+    if "--only-laplacian" in sys.argv:
+        laplacian_pe_case()
+        raise SystemExit(0)
     if "--only-co-event" in sys.argv:
         co_event_graph_case()
         raise SystemExit(0)
@@ -380,3 +424,4 @@ if __name__ == "__main__":
     dataloader_case()
     co_event_graph_case()
     trainer_case()
+    laplacian_pe_case()
