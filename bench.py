@@ -124,6 +124,12 @@ class ClockSampler:
                 ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
                  "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            # wait for the first sample: nvidia-smi's start-up (process spawn + NVML initialisation, 0.1-1 s, with the
+            # driver lock held for part of it) must not land inside the first timed loop — under data parallelism
+            # eight of them start at once
+            deadline = time.time() + 5.0
+            while not self.samples and self.proc.poll() is None and time.time() < deadline:
+                time.sleep(0.01)
         except OSError:
             self.proc = None
         return self
